@@ -1,0 +1,191 @@
+/* uvip_orb.h — C ABI of the B200-native ORB front-end (libuvip_orb.so).
+ *
+ * This is the drop-in boundary for the one hot path of chintha/U-VIP-SLAM that this repository
+ * replaces: USLAM::ORBextractor and the descriptor path of USLAM::ORBmatcher.  The reference has no
+ * FFI of its own (it is one C++ process); the entry points below are what its two classes would bind
+ * if their bodies were moved behind a C boundary, and u-vip-slam_b200/host/ORBextractor.h / ORBmatcher.h
+ * are those classes re-written as thin forwarders (INTEGRATION.md shows the patch a maintainer applies).
+ * Each entry point cites the reference interface it replaces (paths relative to the reference checkout).
+ *
+ * Conventions: plain pointers and sizes, no C++/torch types; every function returns an int status
+ * (UVIP_OK = 0), never throws, never falls back to a CPU implementation.  "host" pointers are ordinary
+ * process memory; "device" pointers (suffix _device) are CUDA device memory on the handle's GPU and the
+ * call is asynchronous on the given cudaStream_t (passed as void*; NULL = the handle's own stream).
+ * A handle is not re-entrant (the reference extractor is stateful too, include/ORBextractor.h:90-91);
+ * use one handle per calling thread — Tracking, LocalMapping and LoopClosing each own one matcher.
+ */
+#ifndef UVIP_ORB_H
+#define UVIP_ORB_H
+#include <stddef.h>
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#define UVIP_ABI_VERSION 1
+
+enum {
+    UVIP_OK = 0,
+    UVIP_ERR_ARG = -1,          /* bad pointer / size / parameter */
+    UVIP_ERR_CAPACITY = -2,     /* caller buffer or internal candidate list too small (nothing is truncated silently) */
+    UVIP_ERR_CUDA = -3,         /* CUDA runtime error; uvip_last_error() has the text */
+    UVIP_ERR_UNSUPPORTED = -4,  /* shape outside the supported envelope (see uvip_extractor_create) */
+    UVIP_ERR_NO_DEVICE = -5     /* no usable CUDA device: there is no CPU fallback */
+};
+
+/* cv::KeyPoint layout, 28 bytes (OpenCV core/types.hpp; used at include/ORBextractor.h:56-58) */
+typedef struct uvip_keypoint {
+    float   x, y;       /* pt, level-0 pixels */
+    float   size;       /* (float)(int)(31 * scale[octave])     src/ORBextractor.cc:820,829 */
+    float   angle;      /* IC_Angle, degrees [0,360)             src/ORBextractor.cc:125-152 */
+    float   response;   /* FAST score                            src/ORBextractor.cc:792-799 */
+    int32_t octave;
+    int32_t class_id;   /* -1 */
+} uvip_keypoint;
+
+/* ---- extractor: replaces USLAM::ORBextractor (include/ORBextractor.h:45-94) ------------------------------- */
+typedef struct uvip_extractor uvip_extractor;
+
+typedef struct uvip_extractor_params {
+    /* the five constructor arguments, include/ORBextractor.h:51 */
+    int32_t nfeatures;
+    float   scale_factor;
+    int32_t nlevels;
+    int32_t score_type;     /* 0 HARRIS_SCORE, 1 FAST_SCORE — accepted and ignored like the reference's live path */
+    int32_t fast_th;
+    /* compile-time constants of the reference, exposed so tests can vary them (0 = reference value) */
+    int32_t retry_th;       /* 7   src/ORBextractor.cc:798 */
+    int32_t cell;           /* 30  src/ORBextractor.cc:752 */
+    /* capacity of the device working set */
+    int32_t device;         /* CUDA device ordinal */
+    int32_t max_width, max_height;   /* largest frame; levels smaller than 64x64 are unsupported */
+    int32_t max_batch;      /* frames resident per launch group (>=1) */
+} uvip_extractor_params;
+
+/* ORBextractor::ORBextractor (src/ORBextractor.cc:458-512): builds the scale / quota / umax tables, uploads
+ * the 512-point pattern, allocates the pyramid working set for max_batch frames. */
+int   uvip_extractor_create(const uvip_extractor_params* params, uvip_extractor** out);
+int   uvip_extractor_destroy(uvip_extractor* ex);
+/* ORBextractor::GetLevels / GetScaleFactor (include/ORBextractor.h:60-64) */
+int   uvip_extractor_levels(const uvip_extractor* ex);
+float uvip_extractor_scale_factor(const uvip_extractor* ex);
+/* constructor tables for inspection: scale[nlevels], inv_scale[nlevels], quota[nlevels], umax[16] (any may be NULL) */
+int   uvip_extractor_tables(const uvip_extractor* ex, float* scale, float* inv_scale, int32_t* quota, int32_t* umax);
+
+/* ORBextractor::operator() (include/ORBextractor.h:56-58, src/ORBextractor.cc:849-961), host buffers.
+ *   image        CV_8UC1 rows of `stride` bytes; NULL or w/h <= 0 = empty image: returns UVIP_OK, outputs untouched
+ *   (mask)       the reference ignores it; it has no parameter here
+ *   kps,n_inout  in: *n_inout incoming level-0 keypoints (kept only when full_detect == 0); out: cleared and replaced
+ *   desc         cap x 32 bytes, row i belongs to kps[i]
+ *   grid         Eigen::MatrixXi storage (column-major int32, grid_rows x grid_cols); read and incremented when
+ *                full_detect == 0, untouched otherwise; may be NULL when full_detect != 0
+ *   min_px_dist, full_detect, num_needed   as in the reference signature */
+int   uvip_extract(uvip_extractor* ex, const uint8_t* image, int w, int h, int stride,
+                   uvip_keypoint* kps, int* n_inout, int cap, uint8_t* desc,
+                   int32_t* grid, int grid_rows, int grid_cols, int min_px_dist,
+                   int full_detect, int num_needed);
+
+/* The same operator() over a batch of equally sized frames with FullDetect=true semantics per frame.
+ * frames: nframes images, frame f starts at frames + f*frame_pitch.  Outputs per frame f:
+ * n_out[f] keypoints at kps + f*cap and desc + f*cap*32.  Host buffers (copies are inside the call). */
+int   uvip_extract_batch(uvip_extractor* ex, const uint8_t* frames, int nframes, int w, int h, int stride,
+                         size_t frame_pitch, uvip_keypoint* kps, int32_t* n_out, int cap, uint8_t* desc);
+/* Device-resident variant: all pointers are device memory; asynchronous on `stream`.
+ * uvip_extractor_status() after synchronising reports capacity overflow of the launch group. */
+int   uvip_extract_batch_device(uvip_extractor* ex, const uint8_t* d_frames, int nframes, int w, int h, int stride,
+                                size_t frame_pitch, uvip_keypoint* d_kps, int32_t* d_n_out, int cap, uint8_t* d_desc,
+                                void* stream);
+int   uvip_extractor_status(uvip_extractor* ex);   /* synchronises the handle; UVIP_OK or the sticky error of the last group */
+
+/* debug taps for parity tests (valid after an extract call, frame < nframes of that call) */
+int   uvip_get_pyramid_level(uvip_extractor* ex, int frame, int level, int blurred,
+                             uint8_t* dst, int dstride, int* w, int* h);      /* interior, src/ORBextractor.cc:963-1004 / :942 */
+int   uvip_get_raw_corners(uvip_extractor* ex, int frame, int level,
+                           int32_t* xs, int32_t* ys, int32_t* scores, int cap, int* n); /* per-cell FAST output, window coords,
+                                                                                reference order (src/ORBextractor.cc:772-812) */
+int   uvip_get_level_keypoints(uvip_extractor* ex, int frame, int level,
+                               int32_t* xs, int32_t* ys, int32_t* scores, int cap, int* n); /* quadtree winners, level coords,
+                                                                                list order (src/ORBextractor.cc:817-831) */
+/* how many of this library's kernels the handle has launched so far (bench.py's gpu_launches) */
+long long uvip_extractor_launch_count(const uvip_extractor* ex);
+
+/* ---- matcher: replaces the descriptor path of USLAM::ORBmatcher (include/ORBmatcher.h:41-94) ------------- */
+typedef struct uvip_matcher uvip_matcher;
+
+enum { UVIP_TH_HIGH = 100, UVIP_TH_LOW = 50, UVIP_HISTO_LENGTH = 30 };   /* src/ORBmatcher.cc:40-42 */
+
+int   uvip_matcher_create(int device, uvip_matcher** out);
+int   uvip_matcher_destroy(uvip_matcher* m);
+long long uvip_matcher_launch_count(const uvip_matcher* m);
+
+/* ORBmatcher::DescriptorDistance (src/ORBmatcher.cc:1794-1810) for n row pairs: out[i] = popcount(a_i ^ b_i) */
+int   uvip_descriptor_distance(uvip_matcher* m, const uint8_t* a, const uint8_t* b, int n, int32_t* out);
+
+/* Brute-force k=2 nearest neighbours in Hamming space: the best/second-best scan every ORBmatcher search shares
+ * (e.g. src/ORBmatcher.cc:201-226) run over the whole train set == BFMatcher(NORM_HAMMING).knnMatch(k=2) of
+ * haloc::Utils::ratioMatching (include/utils.h:81-111).  Order = (distance, train index) ascending.
+ * idx2/dist2 are nq x 2; a missing neighbour has idx -1, dist 257.  Host buffers. */
+int   uvip_knn2(uvip_matcher* m, const uint8_t* q, int nq, const uint8_t* t, int nt, int32_t* idx2, int32_t* dist2);
+/* device-resident; train rows carry global indices idx_base + row so shards of a database can be merged */
+int   uvip_knn2_device(uvip_matcher* m, const uint8_t* d_q, int nq, const uint8_t* d_t, int nt, int idx_base,
+                       int32_t* d_idx2, int32_t* d_dist2, void* stream);
+/* npairs independent (query set, train set) problems in one launch: pair p matches d_q + p*q_pitch (nq[p] rows)
+ * against d_t + p*t_pitch (nt[p] rows); results at d_idx2/d_dist2 + p*2*res_pitch.  d_nq/d_nt are device int32. */
+int   uvip_knn2_batch_device(uvip_matcher* m, const uint8_t* d_q, const int32_t* d_nq, size_t q_pitch,
+                             const uint8_t* d_t, const int32_t* d_nt, size_t t_pitch, int npairs, int max_nq,
+                             int32_t* d_idx2, int32_t* d_dist2, size_t res_pitch, void* stream);
+/* merge `nparts` partial top-2 lists (each nq x 2, parts are part_stride int32 apart) by (distance, global index);
+ * shard-count invariant.  Used after the NCCL all-gather of the database-sharded kNN. */
+int   uvip_knn2_merge_device(uvip_matcher* m, const int32_t* d_idx_parts, const int32_t* d_dist_parts, int nparts,
+                             size_t part_stride, int nq, int32_t* d_idx2, int32_t* d_dist2, void* stream);
+/* ratio test of include/utils.h:104-108: match[i] = idx2[2i] if dist0 <= dist1 * ratio (float x double), else -1 */
+int   uvip_ratio_filter(uvip_matcher* m, const int32_t* idx2, const int32_t* dist2, int nq, double ratio,
+                        int32_t* match, int* nmatches);
+/* rotation-consistency histogram (bin code src/ORBmatcher.cc:232-241, ComputeThreeMaxima :1748-1789, rollback
+ * :263-281): match[i] (train index or -1) is cleared unless bin(angle_a[i] - angle_b[match[i]]) is one of the
+ * three fullest bins.  Host buffers. */
+int   uvip_rot_hist_filter(uvip_matcher* m, int32_t* match, int n, const float* angle_a, const float* angle_b,
+                           int* nkept);
+
+/* Frame keypoint grid (src/FrameKTL.cc:250-264, PosInGrid :426-436): CSR over cols x rows cells,
+ * cell id = ix*rows + iy, items ascending keypoint index.  cell_start has cols*rows+1 entries. */
+int   uvip_grid_build(uvip_matcher* m, const float* kx, const float* ky, int n,
+                      float min_x, float min_y, float inv_w, float inv_h, int cols, int rows,
+                      int32_t* cell_start, int32_t* cell_items);
+
+/* Grid-windowed search with claims: ORBmatcher::SearchByProjection(FrameKTL&, vector<MapPoint*>&, th)
+ * (src/ORBmatcher.cc:49-125) when mode == 0, and the search loop of SearchByProjection(FrameKTL&, KeyFrame*, ...)
+ * (src/ORBmatcher.cc:1683-1715) when mode == 1; candidates come from FrameKTL::GetFeaturesInArea
+ * (src/FrameKTL.cc:359-424).  The caller (shim) projects the map points and supplies per query
+ * (u, v, radius, minLevel, maxLevel, descriptor).  taken[] (nk): -1 = free, anything else = keypoint already has a
+ * map point; on return claimed keypoints hold the claiming query index.  match[q] = keypoint index or -1.
+ * The sequential claim order of the reference is reproduced exactly. */
+typedef struct uvip_search_params {
+    int32_t mode;        /* 0: top-2 with same-level ratio rule; 1: best only */
+    int32_t th_dist;     /* UVIP_TH_HIGH for mode 0, ORBdist for mode 1 */
+    float   ratio;       /* mfNNratio */
+    float   min_x, min_y, inv_w, inv_h;   /* FrameKTL::mnMinX, mnMinY, mfGridElementWidthInv, mfGridElementHeightInv */
+    int32_t cols, rows;  /* FRAME_GRID_COLS 64, FRAME_GRID_ROWS 48 (include/FrameKTL.h:45-46) */
+} uvip_search_params;
+int   uvip_search_window(uvip_matcher* m, const uvip_search_params* sp,
+                         const float* qu, const float* qv, const float* qr, const int32_t* qmin_level,
+                         const int32_t* qmax_level, const uint8_t* qdesc, int nq,
+                         const float* kx, const float* ky, const int32_t* octave, const uint8_t* kdesc, int nk,
+                         const int32_t* cell_start, const int32_t* cell_items,
+                         int32_t* taken, int32_t* match, int* nmatches);
+/* ORBmatcher::RadiusByViewingCos (src/ORBmatcher.cc:127-133) */
+float uvip_radius_by_viewing_cos(float view_cos);
+
+/* ---- misc ---------------------------------------------------------------------------------------------- */
+int         uvip_abi_version(void);
+const char* uvip_last_error(void);          /* thread-local text of the last failure */
+int         uvip_device_count(void);
+/* measurement utility (no reference counterpart): sustained __popc throughput of `device` in popc/s — the
+ * denominator of the Hamming-kNN roofline */
+int         uvip_popc_peak(int device, int iters, double* popc_per_s);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* UVIP_ORB_H */

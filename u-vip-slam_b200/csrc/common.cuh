@@ -1,0 +1,91 @@
+// common.cuh — shared helpers for libuvip_orb.so (sm_100a only).
+#pragma once
+#include <cuda_runtime.h>
+#include <stdint.h>
+#include <stdio.h>
+#include <string.h>
+#include <mutex>
+#include <string>
+#include "../../include/uvip_orb.h"
+
+namespace uvip {
+
+void set_last_error(const char* fmt, ...);
+
+#define UVIP_CUDA(call)                                                                         \
+    do {                                                                                        \
+        cudaError_t e__ = (call);                                                               \
+        if (e__ != cudaSuccess) {                                                               \
+            uvip::set_last_error("%s:%d %s -> %s", __FILE__, __LINE__, #call, cudaGetErrorString(e__)); \
+            return UVIP_ERR_CUDA;                                                               \
+        }                                                                                       \
+    } while (0)
+
+#define UVIP_CHECK_ARG(cond)                                                                    \
+    do {                                                                                        \
+        if (!(cond)) {                                                                          \
+            uvip::set_last_error("%s:%d bad argument: %s", __FILE__, __LINE__, #cond);          \
+            return UVIP_ERR_ARG;                                                                \
+        }                                                                                       \
+    } while (0)
+
+static inline int div_up(int a, int b) { return (a + b - 1) / b; }
+static inline size_t align_up(size_t a, size_t b) { return (a + b - 1) / b * b; }
+
+// RAII guard: make `device` current for the duration of a C-ABI call, restore afterwards
+struct DeviceGuard {
+    int prev = -1;
+    bool ok = true;
+    explicit DeviceGuard(int device) {
+        if (cudaGetDevice(&prev) != cudaSuccess) { ok = false; return; }
+        if (prev != device && cudaSetDevice(device) != cudaSuccess) ok = false;
+    }
+    ~DeviceGuard() { if (prev >= 0) cudaSetDevice(prev); }
+};
+
+// growable device scratch buffer owned by a handle
+struct DevBuf {
+    void* p = nullptr;
+    size_t cap = 0;
+    int reserve(size_t bytes) {
+        if (bytes <= cap) return UVIP_OK;
+        if (p) cudaFree(p);
+        p = nullptr; cap = 0;
+        size_t want = align_up(bytes, 256);
+        cudaError_t e = cudaMalloc(&p, want);
+        if (e != cudaSuccess) { set_last_error("cudaMalloc(%zu) -> %s", want, cudaGetErrorString(e)); return UVIP_ERR_CUDA; }
+        cap = want;
+        return UVIP_OK;
+    }
+    void release() { if (p) cudaFree(p); p = nullptr; cap = 0; }
+    template <typename T> T* as() const { return reinterpret_cast<T*>(p); }
+};
+
+#ifdef __CUDACC__
+// ---- PTX helpers: mbarrier + 1-D bulk async copy (TMA engine, SASS UBLKCP) ----
+__device__ __forceinline__ uint32_t smem_u32(const void* p) { return (uint32_t)__cvta_generic_to_shared(p); }
+__device__ __forceinline__ void mbar_init(uint64_t* bar, uint32_t count) {
+    asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(smem_u32(bar)), "r"(count) : "memory");
+}
+__device__ __forceinline__ void mbar_fence_init() { asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory"); }
+__device__ __forceinline__ void mbar_arrive_expect_tx(uint64_t* bar, uint32_t bytes) {
+    asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(smem_u32(bar)), "r"(bytes) : "memory");
+}
+__device__ __forceinline__ void mbar_wait(uint64_t* bar, uint32_t parity) {
+    asm volatile(
+        "{\n"
+        ".reg .pred p;\n"
+        "LAB_WAIT_%=:\n"
+        "mbarrier.try_wait.parity.shared::cta.b64 p, [%0], %1;\n"
+        "@p bra LAB_DONE_%=;\n"
+        "bra LAB_WAIT_%=;\n"
+        "LAB_DONE_%=:\n"
+        "}\n" ::"r"(smem_u32(bar)), "r"(parity) : "memory");
+}
+__device__ __forceinline__ void bulk_g2s(void* dst_smem, const void* src_gmem, uint32_t bytes, uint64_t* bar) {
+    asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];"
+                 ::"r"(smem_u32(dst_smem)), "l"(src_gmem), "r"(bytes), "r"(smem_u32(bar)) : "memory");
+}
+#endif
+
+}  // namespace uvip

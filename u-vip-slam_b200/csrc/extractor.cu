@@ -1,0 +1,1298 @@
+// extractor.cu — USLAM::ORBextractor on sm_100a.  C-ABI: include/uvip_orb.h.
+//
+// Pipeline per launch group (a batch of equally sized frames resident in HBM), one kernel per stage over the
+// whole batch:  K1 import + cascaded fixed-point bilinear pyramid with reflect-101 border  ->  K2/K3 tiled FAST-9/16
+// score map, cell-local NMS, warp-aggregated candidate emission + per-cell maxima (the empty-cell retry rule)  ->
+// K4 quadtree distribution, one CTA per (frame, level), nodes kept in list order in shared memory  ->
+// K6 7x7 fixed-point Gaussian  ->  K8 selection (FullDetect / occupancy grid)  ->  K5+K7 one warp per keypoint:
+// IC_Angle on the unblurred level and rotated BRIEF on the blurred one.
+//
+// Reference semantics restated here (never its code): src/ORBextractor.cc:74-78,125-195,458-512,748-1004,1006-1287.
+#include "common.cuh"
+#include <math.h>
+#include <algorithm>
+#include <vector>
+
+namespace uvip {
+
+constexpr int MAXLEV = 16;
+constexpr int EDGE = 16;            // EDGE_THRESHOLD: layout padding of every pyramid plane
+constexpr int BORDER_W = 4;         // border pixels actually materialised (only <=3 are ever read: SURVEY A.2)
+constexpr int HALF_PATCH = 15;
+
+static const int8_t h_pattern[1024] = {
+#include "orb_pattern.inc"
+};
+__constant__ int8_t c_pattern[1024];
+__constant__ int c_umax[HALF_PATCH + 1];
+
+struct LevelInfo {
+    int w, h;                 // interior size
+    int pstride;              // padded row stride in bytes (multiple of 32)
+    unsigned poff;            // byte offset of the padded origin inside a frame block
+    int ncols, nrows, wcell, hcell, cell_off;     // FAST cells (src/ORBextractor.cc:767-770)
+    int quota;                // mnFeaturesPerLevel
+    int raw_cap, raw_off;     // candidate list (u32 entries) inside the frame's candidate block
+    int kp_cap, kp_off;       // quadtree winners
+    int ftile_off, fntx, fnty;    // FAST tiles over the detection region
+    int btile_off, bntx, bnty;    // blur tiles
+    int tab_off;              // offset of this level's resize tables
+    int nini;                 // quadtree roots
+    float hx;
+    float scale;              // mvScaleFactor
+    float size;               // keypoint size (float)(int)(31*scale)
+};
+
+struct Plan {
+    int nlevels, W, H;
+    int fast_th, retry_th, t1, t2, tmin;   // effective thresholds (>=1)
+    int cells_per_frame, raw_per_frame, kp_per_frame;
+    int ftiles, btiles;
+    int node_cap;             // quadtree node capacity (power of two)
+    unsigned long long frame_bytes;
+    LevelInfo lv[MAXLEV];
+};
+
+// --------------------------------------------------------------------------------------------------------
+// K1a: import level 0 into the padded plane (+ reflect-101 border)
+// --------------------------------------------------------------------------------------------------------
+__device__ __forceinline__ void store_mirrors(uint8_t* inner, int ps, int w, int h, int x, int y, uint8_t v)
+{
+    // write the reflections of interior pixel (x,y) that fall into the BORDER_W-wide border ring
+    int xs[3], ys[3], nx = 1, ny = 1;
+    xs[0] = x; ys[0] = y;
+    if (x >= 1 && x <= BORDER_W) xs[nx++] = -x;
+    if (x >= w - 1 - BORDER_W && x <= w - 2) xs[nx++] = 2 * (w - 1) - x;
+    if (y >= 1 && y <= BORDER_W) ys[ny++] = -y;
+    if (y >= h - 1 - BORDER_W && y <= h - 2) ys[ny++] = 2 * (h - 1) - y;
+    for (int j = 0; j < ny; j++)
+        for (int i = 0; i < nx; i++)
+            if (i | j) inner[(ptrdiff_t)ys[j] * ps + xs[i]] = v;
+}
+__device__ __forceinline__ bool near_edge(int x0, int y, int w, int h)
+{
+    return x0 <= BORDER_W || x0 + 3 >= w - 1 - BORDER_W || y <= BORDER_W || y >= h - 1 - BORDER_W;
+}
+
+__global__ void __launch_bounds__(256)
+k_import(const uint8_t* __restrict__ frames, int stride, size_t frame_pitch, uint8_t* __restrict__ pyr, const __grid_constant__ Plan P)
+{
+    const LevelInfo& L = P.lv[0];
+    const int f = blockIdx.z;
+    const int x0 = (blockIdx.x * 64 + (threadIdx.x & 63)) * 4;     // 4 pixels per thread
+    const int y = blockIdx.y * 4 + (threadIdx.x >> 6);
+    if (x0 >= L.w || y >= L.h) return;
+    const uint8_t* src = frames + (size_t)f * frame_pitch + (size_t)y * stride + x0;
+    uint8_t* inner = pyr + (size_t)f * P.frame_bytes + L.poff + (size_t)EDGE * L.pstride + EDGE;
+    uint8_t v[4];
+#pragma unroll
+    for (int k = 0; k < 4; k++) v[k] = (x0 + k < L.w) ? __ldg(src + k) : 0;
+    uint8_t* o = inner + (size_t)y * L.pstride + x0;
+    if (x0 + 3 < L.w) *reinterpret_cast<uchar4*>(o) = make_uchar4(v[0], v[1], v[2], v[3]);
+    else for (int k = 0; k < 4; k++) if (x0 + k < L.w) o[k] = v[k];     // never touch the border ring here: its owners are the mirror stores
+    if (near_edge(x0, y, L.w, L.h))
+        for (int k = 0; k < 4; k++) if (x0 + k < L.w) store_mirrors(inner, L.pstride, L.w, L.h, x0 + k, y, v[k]);
+}
+
+// --------------------------------------------------------------------------------------------------------
+// K1b: level l from level l-1, cv::resize INTER_LINEAR 8-bit fixed point (11-bit coefficients), cascaded.
+// tables (host-built, per level): xofs[w] int32, xcoef[w] {a0,a1} int16x2, yofs[h], ycoef[h]
+// --------------------------------------------------------------------------------------------------------
+__global__ void __launch_bounds__(256)
+k_resize(uint8_t* __restrict__ pyr, const int* __restrict__ tabs, int level, const __grid_constant__ Plan P)
+{
+    const LevelInfo& D = P.lv[level];
+    const LevelInfo& S = P.lv[level - 1];
+    const int f = blockIdx.z;
+    const int x0 = (blockIdx.x * 64 + (threadIdx.x & 63)) * 4;
+    const int y = blockIdx.y * 4 + (threadIdx.x >> 6);
+    if (x0 >= D.w || y >= D.h) return;
+    const int* xofs = tabs + D.tab_off;
+    const int* xcoef = xofs + D.w;
+    const int* yofs = xcoef + D.w;
+    const int* ycoef = yofs + D.h;
+    uint8_t* base = pyr + (size_t)f * P.frame_bytes;
+    const uint8_t* sin_ = base + S.poff + (size_t)EDGE * S.pstride + EDGE;
+    uint8_t* inner = base + D.poff + (size_t)EDGE * D.pstride + EDGE;
+    const int sy = __ldg(yofs + y);
+    const int yc = __ldg(ycoef + y);
+    const int b0 = (short)(yc & 0xFFFF), b1 = (short)(yc >> 16);
+    const uint8_t* r0p = sin_ + (size_t)sy * S.pstride;
+    const uint8_t* r1p = r0p + S.pstride;            // row sy+1 is valid memory (border) when sy == h-1, and b1 == 0 there
+    uint8_t v[4];
+#pragma unroll
+    for (int k = 0; k < 4; k++) {
+        const int x = min(x0 + k, D.w - 1);
+        const int sx = __ldg(xofs + x);
+        const int xc = __ldg(xcoef + x);
+        const int a0 = (short)(xc & 0xFFFF), a1 = (short)(xc >> 16);
+        const int h0 = (int)__ldg(r0p + sx) * a0 + (int)__ldg(r0p + sx + 1) * a1;
+        const int h1 = (int)__ldg(r1p + sx) * a0 + (int)__ldg(r1p + sx + 1) * a1;
+        int o = (((b0 * (h0 >> 4)) >> 16) + ((b1 * (h1 >> 4)) >> 16) + 2) >> 2;
+        v[k] = (uint8_t)min(max(o, 0), 255);
+    }
+    uint8_t* o = inner + (size_t)y * D.pstride + x0;
+    if (x0 + 3 < D.w) *reinterpret_cast<uchar4*>(o) = make_uchar4(v[0], v[1], v[2], v[3]);
+    else for (int k = 0; k < 4; k++) if (x0 + k < D.w) o[k] = v[k];
+    if (near_edge(x0, y, D.w, D.h))
+        for (int k = 0; k < 4; k++) if (x0 + k < D.w) store_mirrors(inner, D.pstride, D.w, D.h, x0 + k, y, v[k]);
+}
+
+// --------------------------------------------------------------------------------------------------------
+// K2+K3: FAST-9/16.  One CTA per 64x32 tile of a level's detection region [16,w-16)x[16,h-16).
+//   A  stage the tile + 4 px halo in shared memory (32-bit loads)
+//   B  cheap rejection on the opposite-pixel pairs (0,8) and (4,12) -> queue of surviving positions
+//   C  dense pass over the queue: 16-bit brighter/darker ring masks, 9-contiguous test, exact score
+//      s = max_arc min_k |ring_k - v| - 1  (== OpenCV cornerScore) into a shared score map
+//   D  cell-local 3x3 NMS (neighbours in another 30-px cell count as 0, src/ORBextractor.cc:772-799 runs FAST
+//      per cell ROI), survivors with s >= tmin are appended to the (frame, level) candidate list and raise the
+//      per-cell maximum that decides between fastTh and the retry threshold later (K4).
+// --------------------------------------------------------------------------------------------------------
+constexpr int FT_W = 64, FT_H = 32;
+constexpr int FI_W = FT_W + 8, FI_H = FT_H + 8;      // image tile with 4 px halo
+constexpr int FS_W = FT_W + 2, FS_H = FT_H + 2;      // score tile with 1 px halo
+constexpr int FS_STRIDE = 68;
+constexpr int FAST_OUT_CAP = 768;
+
+__device__ __forceinline__ int cyc_contig9(unsigned m)   // m: 16-bit ring mask; nonzero iff >= 9 contiguous (cyclic) bits
+{
+    unsigned r = m | (m << 16);
+    r &= r >> 1;        // runs >= 2
+    r &= r >> 2;        // runs >= 4
+    r &= r >> 4;        // runs >= 8
+    r &= (m | (m << 16)) >> 8;   // runs >= 9
+    return (r & 0xFFFFu) != 0;
+}
+
+__global__ void __launch_bounds__(256)
+k_fast(const uint8_t* __restrict__ pyr, unsigned* __restrict__ cand, int* __restrict__ cand_count,
+       int* __restrict__ cellmax, int* __restrict__ status, const __grid_constant__ Plan P)
+{
+    __shared__ __align__(16) uint8_t s_img[FI_H][FI_W];
+    __shared__ uint8_t s_score[FS_H][FS_STRIDE];
+    __shared__ unsigned short s_queue[FS_W * FS_H];
+    __shared__ unsigned s_out[FAST_OUT_CAP];          // survivors of this tile (NMS => ~1 per 2x2 inside a cell)
+    __shared__ int s_nq, s_nout, s_base;
+
+    // which level / tile
+    int level = 0;
+    const int tile = blockIdx.x;
+#pragma unroll 1
+    for (int l = 1; l < P.nlevels; l++) if (tile >= P.lv[l].ftile_off) level = l;
+    const LevelInfo& L = P.lv[level];
+    const int f = blockIdx.y;
+    const int tl = tile - L.ftile_off;
+    const int tx0 = EDGE + (tl % L.fntx) * FT_W, ty0 = EDGE + (tl / L.fntx) * FT_H;   // tile origin, level coords
+    const int tid = threadIdx.x;
+    const uint8_t* inner = pyr + (size_t)f * P.frame_bytes + L.poff + (size_t)EDGE * L.pstride + EDGE;
+
+    if (tid == 0) { s_nq = 0; s_nout = 0; }
+    // A: load (tx0-4 .. tx0+68) x (ty0-4 .. ty0+36); x origin is 4-byte aligned
+    for (int i = tid; i < FI_H * (FI_W / 4); i += 256) {
+        const int r = i / (FI_W / 4), c = i % (FI_W / 4);
+        const int y = ty0 - 4 + r, x = tx0 - 4 + c * 4;
+        unsigned v = 0;
+        if (y < L.h + EDGE && x + 4 <= L.pstride - EDGE) v = __ldg(reinterpret_cast<const unsigned*>(inner + (ptrdiff_t)y * L.pstride + x));
+        *reinterpret_cast<unsigned*>(&s_img[r][c * 4]) = v;
+    }
+    for (int i = tid; i < FS_H * FS_STRIDE / 4; i += 256) reinterpret_cast<unsigned*>(&s_score[0][0])[i] = 0;
+    __syncthreads();
+
+    const int xmax = L.w - EDGE, ymax = L.h - EDGE;     // detection region end (exclusive)
+    const int t = P.tmin;
+    // B: quick rejection over the score tile (tile + 1 px ring)
+    for (int i = tid; i < FS_W * FS_H; i += 256) {
+        const int sy = i / FS_W, sx = i % FS_W;
+        const int x = tx0 - 1 + sx, y = ty0 - 1 + sy;
+        bool pass = false;
+        if (x >= EDGE && x < xmax && y >= EDGE && y < ymax) {
+            const int iy = sy + 3, ix = sx + 3;       // position inside s_img
+            const int v = s_img[iy][ix];
+            const int p0 = s_img[iy + 3][ix], p8 = s_img[iy - 3][ix];
+            const int lo = v - t, hi = v + t;
+            // a 9-arc contains one pixel of every opposite pair; if both are within +-t the pixel is no corner
+            const bool in08 = (p0 >= lo && p0 <= hi) && (p8 >= lo && p8 <= hi);
+            if (!in08) {
+                const int p4 = s_img[iy][ix + 3], p12 = s_img[iy][ix - 3];
+                const bool in412 = (p4 >= lo && p4 <= hi) && (p12 >= lo && p12 <= hi);
+                pass = !in412;
+            }
+        }
+        if (pass) { const int slot = atomicAdd(&s_nq, 1); s_queue[slot] = (unsigned short)i; }
+    }
+    __syncthreads();
+    const int nq = s_nq;
+    // C: full test + score
+    for (int qi = tid; qi < nq; qi += 256) {
+        const int i = s_queue[qi];
+        const int sy = i / FS_W, sx = i % FS_W;
+        const int iy = sy + 3, ix = sx + 3;
+        const int v = s_img[iy][ix];
+        int d[16];
+        d[0] = s_img[iy + 3][ix] - v;      d[1] = s_img[iy + 3][ix + 1] - v;  d[2] = s_img[iy + 2][ix + 2] - v;  d[3] = s_img[iy + 1][ix + 3] - v;
+        d[4] = s_img[iy][ix + 3] - v;      d[5] = s_img[iy - 1][ix + 3] - v;  d[6] = s_img[iy - 2][ix + 2] - v;  d[7] = s_img[iy - 3][ix + 1] - v;
+        d[8] = s_img[iy - 3][ix] - v;      d[9] = s_img[iy - 3][ix - 1] - v;  d[10] = s_img[iy - 2][ix - 2] - v; d[11] = s_img[iy - 1][ix - 3] - v;
+        d[12] = s_img[iy][ix - 3] - v;     d[13] = s_img[iy + 1][ix - 3] - v; d[14] = s_img[iy + 2][ix - 2] - v; d[15] = s_img[iy + 3][ix - 1] - v;
+        unsigned mb = 0, md = 0;
+#pragma unroll
+        for (int k = 0; k < 16; k++) { mb |= (unsigned)(d[k] > t) << k; md |= (unsigned)(d[k] < -t) << k; }
+        if (!(cyc_contig9(mb) | cyc_contig9(md))) continue;
+        // exact score: A = max over 9-arcs of min(d), B = max over 9-arcs of min(-d); 9-windows as 3x3 min3/max3
+        int mn3[16], mx3[16];
+#pragma unroll
+        for (int k = 0; k < 16; k++) {
+            mn3[k] = __vimin3_s32(d[k], d[(k + 1) & 15], d[(k + 2) & 15]);
+            mx3[k] = __vimax3_s32(d[k], d[(k + 1) & 15], d[(k + 2) & 15]);
+        }
+        int A = -256, Bn = 256;
+#pragma unroll
+        for (int k = 0; k < 16; k++) {
+            A = max(A, __vimin3_s32(mn3[k], mn3[(k + 3) & 15], mn3[(k + 6) & 15]));
+            Bn = min(Bn, __vimax3_s32(mx3[k], mx3[(k + 3) & 15], mx3[(k + 6) & 15]));
+        }
+        const int s = max(A, -Bn) - 1;
+        s_score[sy][sx] = (uint8_t)s;                 // s >= tmin >= 1 here
+    }
+    __syncthreads();
+    // D: cell-local NMS over queued positions inside the tile proper
+    for (int qi = tid; qi < nq; qi += 256) {
+        const int i = s_queue[qi];
+        const int sy = i / FS_W, sx = i % FS_W;
+        if (sx < 1 || sx > FT_W || sy < 1 || sy > FT_H) continue;
+        const int s = s_score[sy][sx];
+        if (s == 0) continue;
+        const int x = tx0 - 1 + sx, y = ty0 - 1 + sy;
+        const int cx = (x - EDGE) / L.wcell, cy = (y - EDGE) / L.hcell;
+        const int rx = (x - EDGE) - cx * L.wcell, ry = (y - EDGE) - cy * L.hcell;
+        const bool hasL = rx > 0, hasR = (rx < L.wcell - 1) && (x + 1 < xmax);
+        const bool hasU = ry > 0, hasD = (ry < L.hcell - 1) && (y + 1 < ymax);
+        bool keep = true;
+        if (hasL) keep &= s > s_score[sy][sx - 1];
+        if (hasR) keep &= s > s_score[sy][sx + 1];
+        if (hasU) {
+            keep &= s > s_score[sy - 1][sx];
+            if (hasL) keep &= s > s_score[sy - 1][sx - 1];
+            if (hasR) keep &= s > s_score[sy - 1][sx + 1];
+        }
+        if (hasD) {
+            keep &= s > s_score[sy + 1][sx];
+            if (hasL) keep &= s > s_score[sy + 1][sx - 1];
+            if (hasR) keep &= s > s_score[sy + 1][sx + 1];
+        }
+        if (!keep) continue;
+        const int slot = atomicAdd(&s_nout, 1);
+        if (slot < FAST_OUT_CAP) s_out[slot] = (unsigned)x | ((unsigned)y << 12) | ((unsigned)s << 24);
+        atomicMax(&cellmax[(size_t)f * P.cells_per_frame + L.cell_off + cy * L.ncols + cx], s);
+    }
+    __syncthreads();
+    const int nout = s_nout;
+    if (nout == 0) return;
+    if (nout > FAST_OUT_CAP) { if (tid == 0) atomicOr(status, 1); return; }
+    int* cnt = cand_count + (size_t)f * P.nlevels + level;
+    if (tid == 0) s_base = atomicAdd(cnt, nout);
+    __syncthreads();
+    const int base = s_base;
+    if (base + nout > L.raw_cap) { if (tid == 0) atomicOr(status, 1); return; }
+    unsigned* dst = cand + (size_t)f * P.raw_per_frame + L.raw_off + base;
+    for (int i = tid; i < nout; i += 256) dst[i] = s_out[i];
+}
+
+// --------------------------------------------------------------------------------------------------------
+// K4: DistributeOctTree (src/ORBextractor.cc:1006-1287) — one CTA per (frame, level).
+// Array formulation (tools/quadtree_proto.py): nodes live in LIST ORDER in shared memory (slot == position in the
+// reference's std::list), keys stay where they are and carry a node label.  A round divides a ranked set of nodes
+// and rebuilds the list as  reverse(children in creation order) ++ surviving nodes in old order — exactly what
+// push_front + erase do.  Near the quota the reference expands the largest nodes first and stops at the first
+// moment |list| >= N (:1140-1204); here every candidate is divided speculatively in parallel and a prefix sum over
+// the sorted order finds that stopping point.  The sort tie on node POINTER (:1151) is pinned to creation order
+// (later-created = nearer the list front = first), same as the oracle.
+// --------------------------------------------------------------------------------------------------------
+constexpr int QT_THREADS = 256;
+
+struct QtShared {          // laid out in dynamic shared memory, all arrays node_cap long unless noted
+    int* box[2];           // 4 ints per node: x0,y0,x1,y1
+    int* cnt[2];
+    int* cc;               // 4 per node: child key counts
+    int* rank;             // processing rank of a slot, -1 = not divided
+    int* slot_of_rank;
+    int* scan;             // node_cap + 1
+    int* newpos;
+    int* childpos;         // 4 per node
+    unsigned* sortk;       // node_cap
+    int* best_score;
+    unsigned* best_okey;
+};
+
+__device__ int block_excl_scan(int* a, int n, int* s_warp)     // in-place exclusive scan of a[0..n), returns total (all threads)
+{
+    const int tid = threadIdx.x;
+    const int per = (n + QT_THREADS - 1) / QT_THREADS;
+    const int b = tid * per, e = min(b + per, n);
+    int sum = 0;
+    for (int i = b; i < e; i++) sum += a[i];
+    // warp scan of sums
+    int incl = sum;
+#pragma unroll
+    for (int o = 1; o < 32; o <<= 1) { const int v = __shfl_up_sync(0xFFFFFFFFu, incl, o); if ((tid & 31) >= o) incl += v; }
+    if ((tid & 31) == 31) s_warp[tid >> 5] = incl;
+    __syncthreads();
+    int woff = 0, total = 0;
+#pragma unroll
+    for (int w = 0; w < QT_THREADS / 32; w++) { const int v = s_warp[w]; if (w < (tid >> 5)) woff += v; total += v; }
+    int run = woff + incl - sum;
+    for (int i = b; i < e; i++) { const int v = a[i]; a[i] = run; run += v; }
+    __syncthreads();
+    return total;
+}
+
+__device__ __forceinline__ void child_box(const int* pb, int q, int* cb)
+{
+    const int x0 = pb[0], y0 = pb[1], x1 = pb[2], y1 = pb[3];
+    const int hx = (x1 - x0 + 1) >> 1, hy = (y1 - y0 + 1) >> 1;     // ceil(float(d)/2), d >= 0
+    cb[0] = (q & 1) ? x0 + hx : x0;  cb[2] = (q & 1) ? x1 : x0 + hx;
+    cb[1] = (q & 2) ? y0 + hy : y0;  cb[3] = (q & 2) ? y1 : y0 + hy;
+}
+__device__ __forceinline__ int quadrant(const int* pb, int x, int y)
+{
+    const int hx = (pb[2] - pb[0] + 1) >> 1, hy = (pb[3] - pb[1] + 1) >> 1;
+    return (x >= pb[0] + hx ? 1 : 0) | (y >= pb[1] + hy ? 2 : 0);   // 0:n1(UL) 1:n2(UR) 2:n3(BL) 3:n4(BR)
+}
+
+__global__ void __launch_bounds__(QT_THREADS)
+k_quadtree(const unsigned* __restrict__ cand, const int* __restrict__ cand_count, const int* __restrict__ cellmax,
+           unsigned* __restrict__ keys, int* __restrict__ key_count, unsigned short* __restrict__ labels,
+           unsigned* __restrict__ winners, int* __restrict__ win_count, int* __restrict__ status,
+           const __grid_constant__ Plan P)
+{
+    extern __shared__ int s_dyn[];
+    __shared__ int s_warp[QT_THREADS / 32];
+    __shared__ int s_n, s_nexp, s_ncand, s_ndiv;
+
+    const int level = blockIdx.x, f = blockIdx.y;
+    const LevelInfo& L = P.lv[level];
+    const int cap = P.node_cap;
+    const int tid = threadIdx.x;
+    QtShared S;
+    {
+        int* p = s_dyn;
+        S.box[0] = p; p += 4 * cap; S.box[1] = p; p += 4 * cap;
+        S.cnt[0] = p; p += cap; S.cnt[1] = p; p += cap;
+        S.cc = p; p += 4 * cap; S.rank = p; p += cap; S.slot_of_rank = p; p += cap;
+        S.scan = p; p += cap + 1; S.newpos = p; p += cap; S.childpos = p; p += 4 * cap;
+        S.sortk = reinterpret_cast<unsigned*>(p); p += cap;
+        S.best_score = p; p += cap; S.best_okey = reinterpret_cast<unsigned*>(p); p += cap;
+    }
+    const unsigned* cin = cand + (size_t)f * P.raw_per_frame + L.raw_off;
+    unsigned* kk = keys + (size_t)f * P.raw_per_frame + L.raw_off;
+    unsigned short* lab = labels + (size_t)f * P.raw_per_frame + L.raw_off;
+    const int* cmax = cellmax + (size_t)f * P.cells_per_frame + L.cell_off;
+    const int ncand_in = min(cand_count[(size_t)f * P.nlevels + level], L.raw_cap);
+    const int N = L.quota;
+
+    // ---- a. cell rule: a cell keeps its fastTh corners, or — if it has none — its retry-threshold corners
+    if (tid == 0) s_n = 0;
+    __syncthreads();
+    for (int i0 = 0; i0 < ncand_in; i0 += QT_THREADS) {
+        const int i = i0 + tid;
+        bool keep = false; unsigned c = 0;
+        if (i < ncand_in) {
+            c = cin[i];
+            const int x = c & 0xFFF, y = (c >> 12) & 0xFFF, s = c >> 24;
+            const int cx = (x - EDGE) / L.wcell, cy = (y - EDGE) / L.hcell;
+            const int m = cmax[cy * L.ncols + cx];
+            keep = (s >= P.t1) || (m < P.t1 && s >= P.t2);
+        }
+        const unsigned bal = __ballot_sync(0xFFFFFFFFu, keep);
+        int wbase = 0;
+        if ((tid & 31) == 0 && bal) wbase = atomicAdd(&s_n, __popc(bal));
+        wbase = __shfl_sync(0xFFFFFFFFu, wbase, 0);
+        if (keep) kk[wbase + __popc(bal & ((1u << (tid & 31)) - 1))] = c;
+    }
+    __syncthreads();
+    const int n = s_n;
+    if (tid == 0) key_count[(size_t)f * P.nlevels + level] = n;
+    unsigned* wout = winners + (size_t)f * P.kp_per_frame + L.kp_off;
+    if (n == 0) { if (tid == 0) win_count[(size_t)f * P.nlevels + level] = 0; return; }
+
+    // ---- b. roots (:1010-1053).  window coords = level coords - 13
+    const int minB = EDGE - 3;
+    const int nini = L.nini;
+    const float hX = L.hx;
+    for (int i = tid; i < nini; i += QT_THREADS) {
+        int* b = S.box[0] + 4 * i;
+        b[0] = (int)__fmul_rn(hX, (float)i); b[1] = 0; b[2] = (int)__fmul_rn(hX, (float)(i + 1)); b[3] = L.h - 2 * minB;
+        S.cnt[0][i] = 0;
+    }
+    __syncthreads();
+    for (int i = tid; i < n; i += QT_THREADS) {
+        const int x = (int)(kk[i] & 0xFFF) - minB;
+        int r = (int)__fdiv_rn((float)x, hX);
+        r = min(max(r, 0), nini - 1);
+        lab[i] = (unsigned short)r;
+        atomicAdd(&S.cnt[0][r], 1);
+    }
+    __syncthreads();
+    // drop empty roots (keeps order)
+    for (int i = tid; i < nini; i += QT_THREADS) S.scan[i] = S.cnt[0][i] > 0 ? 1 : 0;
+    __syncthreads();
+    int size = block_excl_scan(S.scan, nini, s_warp);
+    for (int i = tid; i < nini; i += QT_THREADS)
+        if (S.cnt[0][i] > 0) {
+            const int p = S.scan[i];
+            S.newpos[i] = p;
+            for (int k = 0; k < 4; k++) S.box[1][4 * p + k] = S.box[0][4 * i + k];
+            S.cnt[1][p] = S.cnt[0][i];
+        }
+    __syncthreads();
+    for (int i = tid; i < n; i += QT_THREADS) lab[i] = (unsigned short)S.newpos[lab[i]];
+    int cur = 1;                      // current node buffer
+    int cprev = size;
+    bool phase2 = false, finish = false;
+    __syncthreads();
+
+    // ---- c. rounds
+    while (!finish) {
+        const int prev_size = size;
+        int* box = S.box[cur]; int* cnt = S.cnt[cur];
+        int* nbox = S.box[cur ^ 1]; int* ncnt = S.cnt[cur ^ 1];
+        int ncandidates;
+        // 1. candidates and their processing order
+        if (!phase2) {
+            for (int s = tid; s < size; s += QT_THREADS) S.scan[s] = cnt[s] > 1 ? 1 : 0;
+            __syncthreads();
+            ncandidates = block_excl_scan(S.scan, size, s_warp);
+            for (int s = tid; s < size; s += QT_THREADS) {
+                if (cnt[s] > 1) { S.rank[s] = S.scan[s]; S.slot_of_rank[S.scan[s]] = s; } else S.rank[s] = -1;
+            }
+        } else {
+            int m = 1; while (m < cprev) m <<= 1;
+            for (int s = tid; s < m; s += QT_THREADS)
+                S.sortk[s] = (s < cprev && cnt[s] > 1) ? (((unsigned)(0xFFFFF - min(cnt[s], 0xFFFFF)) << 12) | (unsigned)s) : 0xFFFFFFFFu;
+            for (int s = tid; s < size; s += QT_THREADS) S.rank[s] = -1;
+            if (tid == 0) s_ncand = 0;
+            __syncthreads();
+            for (int k2 = 2; k2 <= m; k2 <<= 1)                      // bitonic sort ascending
+                for (int j = k2 >> 1; j > 0; j >>= 1) {
+                    for (int i = tid; i < m; i += QT_THREADS) {
+                        const int ixj = i ^ j;
+                        if (ixj > i) {
+                            const unsigned a = S.sortk[i], b = S.sortk[ixj];
+                            const bool up = (i & k2) == 0;
+                            if ((a > b) == up) { S.sortk[i] = b; S.sortk[ixj] = a; }
+                        }
+                    }
+                    __syncthreads();
+                }
+            int local = 0;
+            for (int r = tid; r < m; r += QT_THREADS)
+                if (S.sortk[r] != 0xFFFFFFFFu) { const int s = S.sortk[r] & 0xFFF; S.rank[s] = r; S.slot_of_rank[r] = s; local++; }
+            if (local) atomicAdd(&s_ncand, local);
+            __syncthreads();
+            ncandidates = s_ncand;
+        }
+        __syncthreads();
+        // 2. child key counts of every candidate
+        for (int i = tid; i < 4 * size; i += QT_THREADS) S.cc[i] = 0;
+        __syncthreads();
+        for (int i = tid; i < n; i += QT_THREADS) {
+            const int s = lab[i];
+            if (S.rank[s] >= 0) {
+                const unsigned c = kk[i];
+                const int q = quadrant(box + 4 * s, (int)(c & 0xFFF) - minB, (int)((c >> 12) & 0xFFF) - minB);
+                atomicAdd(&S.cc[4 * s + q], 1);
+            }
+        }
+        __syncthreads();
+        // 3. children per candidate in rank order; stopping point in phase 2
+        for (int r = tid; r < ncandidates; r += QT_THREADS) {
+            const int* c4 = S.cc + 4 * S.slot_of_rank[r];
+            S.scan[r] = (c4[0] > 0) + (c4[1] > 0) + (c4[2] > 0) + (c4[3] > 0);
+        }
+        if (tid == 0) { s_ndiv = ncandidates; s_nexp = 0; }
+        __syncthreads();
+        block_excl_scan(S.scan, ncandidates, s_warp);                 // scan[r] = children created before rank r
+        if (phase2) {
+            for (int r = tid; r < ncandidates; r += QT_THREADS) {
+                const int* c4 = S.cc + 4 * S.slot_of_rank[r];
+                const int nch = (c4[0] > 0) + (c4[1] > 0) + (c4[2] > 0) + (c4[3] > 0);
+                const int after = size + S.scan[r] + nch - (r + 1);   // |list| after dividing ranks 0..r
+                if (after >= N) atomicMin(&s_ndiv, r + 1);
+            }
+            __syncthreads();
+        }
+        const int ndiv = s_ndiv;
+        for (int r = ndiv + tid; r < ncandidates; r += QT_THREADS) S.rank[S.slot_of_rank[r]] = -1;
+        __syncthreads();
+        // 4. totals
+        int C = 0;
+        if (ndiv > 0) {
+            const int sl = S.slot_of_rank[ndiv - 1]; const int* c4 = S.cc + 4 * sl;
+            C = S.scan[ndiv - 1] + (c4[0] > 0) + (c4[1] > 0) + (c4[2] > 0) + (c4[3] > 0);
+        }
+        __syncthreads();
+        // children (scan[] is consumed here before it is reused for the survivors)
+        for (int r = tid; r < ndiv; r += QT_THREADS) {
+            const int s = S.slot_of_rank[r];
+            int t = S.scan[r];
+            int nexp = 0;
+            for (int q = 0; q < 4; q++) {
+                const int c = S.cc[4 * s + q];
+                if (c > 0) {
+                    const int pos = C - 1 - t; t++;
+                    child_box(box + 4 * s, q, nbox + 4 * pos);
+                    ncnt[pos] = c;
+                    S.childpos[4 * s + q] = pos;
+                    nexp += c > 1;
+                }
+            }
+            if (nexp) atomicAdd(&s_nexp, nexp);
+        }
+        __syncthreads();
+        for (int s = tid; s < size; s += QT_THREADS) S.scan[s] = S.rank[s] < 0 ? 1 : 0;
+        __syncthreads();
+        const int nsurv = block_excl_scan(S.scan, size, s_warp);
+        if (C + nsurv > cap) { if (tid == 0) { atomicOr(status, 2); win_count[(size_t)f * P.nlevels + level] = 0; } return; }
+        for (int s = tid; s < size; s += QT_THREADS)
+            if (S.rank[s] < 0) {
+                const int pos = C + S.scan[s];
+                S.newpos[s] = pos;
+                for (int k = 0; k < 4; k++) nbox[4 * pos + k] = box[4 * s + k];
+                ncnt[pos] = cnt[s];
+            }
+        __syncthreads();
+        // 6. relabel keys
+        for (int i = tid; i < n; i += QT_THREADS) {
+            const int s = lab[i];
+            if (S.rank[s] >= 0) {
+                const unsigned c = kk[i];
+                const int q = quadrant(box + 4 * s, (int)(c & 0xFFF) - minB, (int)((c >> 12) & 0xFFF) - minB);
+                lab[i] = (unsigned short)S.childpos[4 * s + q];
+            } else lab[i] = (unsigned short)S.newpos[s];
+        }
+        __syncthreads();
+        size = C + nsurv; cprev = C; cur ^= 1;
+        const int nexp = s_nexp;
+        // 7. control flow of :1141-1204
+        if (size >= N || size == prev_size) finish = true;
+        else if (!phase2 && size + 3 * nexp > N) phase2 = true;
+        __syncthreads();
+    }
+
+    // ---- d. best key per node: max response, first in the reference's raw order on ties (:1208-1227)
+    for (int s = tid; s < size; s += QT_THREADS) { S.best_score[s] = -1; S.best_okey[s] = 0xFFFFFFFFu; }
+    __syncthreads();
+    for (int i = tid; i < n; i += QT_THREADS) atomicMax(&S.best_score[lab[i]], (int)(kk[i] >> 24));
+    __syncthreads();
+    auto okey = [&](unsigned c) -> unsigned {
+        const int x = (int)(c & 0xFFF) - EDGE, y = (int)((c >> 12) & 0xFFF) - EDGE;
+        const int cx = x / L.wcell, cy = y / L.hcell;
+        return ((unsigned)(cy * L.ncols + cx) << 14) | ((unsigned)(y - cy * L.hcell) << 7) | (unsigned)(x - cx * L.wcell);
+    };
+    for (int i = tid; i < n; i += QT_THREADS) {
+        const unsigned c = kk[i];
+        if ((int)(c >> 24) == S.best_score[lab[i]]) atomicMin(&S.best_okey[lab[i]], okey(c));
+    }
+    __syncthreads();
+    if (size > L.kp_cap) { if (tid == 0) { atomicOr(status, 4); win_count[(size_t)f * P.nlevels + level] = 0; } return; }
+    for (int i = tid; i < n; i += QT_THREADS) {
+        const unsigned c = kk[i];
+        const int s = lab[i];
+        if ((int)(c >> 24) == S.best_score[s] && okey(c) == S.best_okey[s]) wout[s] = c;
+    }
+    if (tid == 0) win_count[(size_t)f * P.nlevels + level] = size;
+}
+
+// --------------------------------------------------------------------------------------------------------
+// K6: GaussianBlur 7x7 sigma 2, fixed point [18,34,48,56,48,34,18]/256 per axis, out = (sum + 2^15) >> 16
+// (SURVEY A.6 variant A).  The blurred plane keeps the layout of the pyramid plane; its 4-px border ring holds the
+// UNBLURRED reflect-101 border, which is what the reference's in-place ROI blur leaves there.
+// --------------------------------------------------------------------------------------------------------
+constexpr int BT_W = 64, BT_H = 32;
+__global__ void __launch_bounds__(256)
+k_blur(const uint8_t* __restrict__ pyr, uint8_t* __restrict__ blur, const __grid_constant__ Plan P)
+{
+    __shared__ __align__(16) uint8_t s_in[BT_H + 6][BT_W + 8];
+    __shared__ unsigned short s_h[BT_H + 6][BT_W];
+    int level = 0;
+    const int tile = blockIdx.x;
+#pragma unroll 1
+    for (int l = 1; l < P.nlevels; l++) if (tile >= P.lv[l].btile_off) level = l;
+    const LevelInfo& L = P.lv[level];
+    const int f = blockIdx.y, tid = threadIdx.x;
+    const int tl = tile - L.btile_off;
+    const int tx0 = -BORDER_W + (tl % L.bntx) * BT_W, ty0 = -BORDER_W + (tl / L.bntx) * BT_H;   // level coords, may be negative
+    const size_t plane = (size_t)f * P.frame_bytes + L.poff + (size_t)EDGE * L.pstride + EDGE;
+    const uint8_t* in = pyr + plane;
+    uint8_t* out = blur + plane;
+    // load rows ty0-3 .. ty0+BT_H+3, cols tx0-4 .. tx0+BT_W+4 (4-byte aligned)
+    for (int i = tid; i < (BT_H + 6) * ((BT_W + 8) / 4); i += 256) {
+        const int r = i / ((BT_W + 8) / 4), c = i % ((BT_W + 8) / 4);
+        const int y = ty0 - 3 + r, x = tx0 - 4 + c * 4;
+        unsigned v = 0;
+        if (y >= -EDGE && y < L.h + EDGE && x >= -EDGE && x + 4 <= L.pstride - EDGE)
+            v = __ldg(reinterpret_cast<const unsigned*>(in + (ptrdiff_t)y * L.pstride + x));
+        *reinterpret_cast<unsigned*>(&s_in[r][c * 4]) = v;
+    }
+    __syncthreads();
+    for (int i = tid; i < (BT_H + 6) * BT_W; i += 256) {
+        const int r = i / BT_W, c = i % BT_W;
+        const uint8_t* p = &s_in[r][c + 1];          // p[0..6] = x-3 .. x+3
+        s_h[r][c] = (unsigned short)(18 * (p[0] + p[6]) + 34 * (p[1] + p[5]) + 48 * (p[2] + p[4]) + 56 * p[3]);
+    }
+    __syncthreads();
+    for (int i = tid; i < BT_H * (BT_W / 4); i += 256) {
+        const int r = i / (BT_W / 4), c4 = (i % (BT_W / 4)) * 4;
+        const int y = ty0 + r, x0 = tx0 + c4;
+        if (y >= L.h + BORDER_W || x0 >= L.w + BORDER_W) continue;
+        uint8_t v[4];
+#pragma unroll
+        for (int k = 0; k < 4; k++) {
+            const int c = c4 + k, x = x0 + k;
+            if (x >= 0 && x < L.w && y >= 0 && y < L.h) {
+                const int a = 18 * (s_h[r][c] + s_h[r + 6][c]) + 34 * (s_h[r + 1][c] + s_h[r + 5][c]) +
+                              48 * (s_h[r + 2][c] + s_h[r + 4][c]) + 56 * s_h[r + 3][c];
+                v[k] = (uint8_t)((a + 32768) >> 16);
+            } else v[k] = s_in[r + 3][c + 4];        // border ring: unblurred copy
+        }
+        *reinterpret_cast<uchar4*>(out + (ptrdiff_t)y * L.pstride + x0) = make_uchar4(v[0], v[1], v[2], v[3]);
+    }
+}
+
+// --------------------------------------------------------------------------------------------------------
+// K8: selection — which (level, winner) pairs become output rows, in output order (src/ORBextractor.cc:872-915).
+// full_detect: all winners, level-major.  Otherwise the greedy occupancy-grid filter (inherently sequential: one
+// thread per frame replays it).  sel entry = level << 16 | index; 0xFFFF0000 | i marks incoming keypoint i.
+// --------------------------------------------------------------------------------------------------------
+__global__ void __launch_bounds__(256)
+k_select(const unsigned* __restrict__ winners, const int* __restrict__ win_count, unsigned* __restrict__ sel, int* __restrict__ nsel,
+         int sel_cap, int full_detect, int n_incoming, int32_t* __restrict__ grid, int grid_rows, int grid_cols, int min_px_dist, int num_needed,
+         int* __restrict__ status, const __grid_constant__ Plan P)
+{
+    const int f = blockIdx.x, tid = threadIdx.x;
+    const int* wc = win_count + (size_t)f * P.nlevels;
+    unsigned* out = sel + (size_t)f * sel_cap;
+    if (full_detect) {
+        int off = 0;
+        for (int l = 0; l < P.nlevels; l++) {
+            const int c = wc[l];
+            if (off + c <= sel_cap) for (int i = tid; i < c; i += 256) out[off + i] = ((unsigned)l << 16) | (unsigned)i;
+            off += c;
+        }
+        if (tid == 0) { if (off > sel_cap) { atomicOr(status, 8); off = 0; } nsel[f] = off; }
+        return;
+    }
+    if (tid != 0) return;
+    int n = 0;
+    bool over = false;
+    for (int i = 0; i < n_incoming; i++) { if (n < sel_cap) out[n] = 0xFFFF0000u | (unsigned)i; else over = true; n++; }
+    int total = 0, kp = 0; bool brk = false;
+    for (int l = 0; l < P.nlevels && !brk; l++) {
+        const int c = wc[l];
+        if (c == 0) continue;
+        const int quota = num_needed * (8 - l) / 30;
+        const float scale = P.lv[l].scale;
+        const unsigned* w = winners + (size_t)f * P.kp_per_frame + P.lv[l].kp_off;
+        for (int i = 0; i < c; i++) {
+            const unsigned e = w[i];
+            const float tx = __fmul_rn((float)(e & 0xFFF), scale), ty = __fmul_rn((float)((e >> 12) & 0xFFF), scale);
+            const int r = (int)__fdiv_rn(ty, (float)min_px_dist), cc = (int)__fdiv_rn(tx, (float)min_px_dist);
+            if (r < 0 || r >= grid_rows || cc < 0 || cc >= grid_cols) continue;   // the reference would index out of bounds
+            int32_t* cell = grid + (size_t)cc * grid_rows + r;
+            if (*cell > 0) continue;
+            if (n < sel_cap) out[n] = ((unsigned)l << 16) | (unsigned)i; else over = true;
+            n++;
+            (*cell)++;
+            kp++; total++;
+            if (kp == quota) { kp = 0; break; }
+            if (total == num_needed) { brk = true; break; }
+        }
+    }
+    if (over) { atomicOr(status, 8); n = 0; }
+    nsel[f] = n;
+}
+
+// --------------------------------------------------------------------------------------------------------
+// K5+K7: one warp per output keypoint.  IC_Angle (src/ORBextractor.cc:125-152) on the unblurred plane: lane u
+// accumulates column u-15 of the radius-15 disc, warp-shuffle reduction of the two moments, cv::fastAtan2
+// polynomial with every float op rounded separately.  computeOrbDescriptor (:155-195) on the blurred plane: lane i
+// produces descriptor byte i from its 16 pattern points (pattern staged transposed in shared memory).
+// --------------------------------------------------------------------------------------------------------
+__device__ __forceinline__ float fast_atan2_deg(float y, float x)
+{
+    const float sc = (float)(180.0 / 3.14159265358979323846);
+    const float p1 = 0.9997878412794807f * sc, p3 = -0.3258083974640975f * sc;
+    const float p5 = 0.1555786518463281f * sc, p7 = -0.04432655554792128f * sc;
+    const float ax = fabsf(x), ay = fabsf(y);
+    float a, c, c2;
+    if (ax >= ay) {
+        c = __fdiv_rn(ay, __fadd_rn(ax, (float)2.2204460492503131e-16));
+        c2 = __fmul_rn(c, c);
+        a = __fmul_rn(__fadd_rn(__fmul_rn(__fadd_rn(__fmul_rn(__fadd_rn(__fmul_rn(p7, c2), p5), c2), p3), c2), p1), c);
+    } else {
+        c = __fdiv_rn(ax, __fadd_rn(ay, (float)2.2204460492503131e-16));
+        c2 = __fmul_rn(c, c);
+        a = __fsub_rn(90.f, __fmul_rn(__fadd_rn(__fmul_rn(__fadd_rn(__fmul_rn(__fadd_rn(__fmul_rn(p7, c2), p5), c2), p3), c2), p1), c));
+    }
+    if (x < 0) a = __fsub_rn(180.f, a);
+    if (y < 0) a = __fsub_rn(360.f, a);
+    return a;
+}
+
+constexpr int DESC_WARPS = 8;
+__global__ void __launch_bounds__(DESC_WARPS * 32)
+k_describe(const uint8_t* __restrict__ pyr, const uint8_t* __restrict__ blur, const unsigned* __restrict__ winners,
+           const unsigned* __restrict__ sel, const int* __restrict__ nsel, int sel_cap,
+           const uvip_keypoint* __restrict__ incoming,
+           uvip_keypoint* __restrict__ kps, uint8_t* __restrict__ desc, int32_t* __restrict__ n_out, int out_cap,
+           int* __restrict__ status, const __grid_constant__ Plan P)
+{
+    __shared__ short s_pat[16][32][2];          // [k][lane] -> (x, y) of pattern point 16*lane + k
+    for (int i = threadIdx.x; i < 512; i += blockDim.x) {
+        const int lane = i >> 4, k = i & 15;
+        s_pat[k][lane][0] = c_pattern[2 * i]; s_pat[k][lane][1] = c_pattern[2 * i + 1];
+    }
+    __syncthreads();
+    const int f = blockIdx.y;
+    const int lane = threadIdx.x & 31;
+    const int slot = blockIdx.x * DESC_WARPS + (threadIdx.x >> 5);
+    const int n = nsel[f];
+    if (slot == 0 && lane == 0) { n_out[f] = n; if (n > out_cap) atomicOr(status, 8); }
+    if (slot >= n) return;
+    const unsigned e = sel[(size_t)f * sel_cap + slot];
+    int level, cx, cy; float response, size, ox, oy; int octave, class_id;
+    if ((e >> 16) == 0xFFFFu) {                // incoming level-0 keypoint (ComputeKeyPointsCopy, :523-534)
+        const uvip_keypoint k = incoming[e & 0xFFFF];
+        level = 0; cx = __float2int_rn(k.x); cy = __float2int_rn(k.y);
+        response = k.response; size = k.size; ox = k.x; oy = k.y; octave = k.octave; class_id = k.class_id;
+    } else {
+        level = e >> 16;
+        const unsigned w = winners[(size_t)f * P.kp_per_frame + P.lv[level].kp_off + (e & 0xFFFF)];
+        cx = w & 0xFFF; cy = (w >> 12) & 0xFFF;
+        response = (float)(w >> 24); size = P.lv[level].size; octave = level; class_id = -1;
+        ox = (float)cx; oy = (float)cy;
+        if (level != 0) { ox = __fmul_rn(ox, P.lv[level].scale); oy = __fmul_rn(oy, P.lv[level].scale); }   // :951-957
+    }
+    const LevelInfo& L = P.lv[level];
+    const size_t plane = (size_t)f * P.frame_bytes + L.poff + (size_t)EDGE * L.pstride + EDGE;
+    const uint8_t* c0 = pyr + plane + (ptrdiff_t)cy * L.pstride + cx;
+    // ---- IC_Angle
+    int m10 = 0, m01 = 0;
+    if (lane < 31) {
+        const int u = lane - HALF_PATCH, au = abs(u);
+#pragma unroll 1
+        for (int v = -HALF_PATCH; v <= HALF_PATCH; v++) {
+            if (au <= c_umax[abs(v)]) {
+                const int val = __ldg(c0 + (ptrdiff_t)v * L.pstride + u);
+                m10 += u * val; m01 += v * val;
+            }
+        }
+    }
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) { m10 += __shfl_xor_sync(0xFFFFFFFFu, m10, o); m01 += __shfl_xor_sync(0xFFFFFFFFu, m01, o); }
+    const float angle = fast_atan2_deg((float)m01, (float)m10);
+    // ---- rotated BRIEF
+    const float factorPI = (float)(3.14159265358979323846 / 180.f);
+    const float ang = __fmul_rn(angle, factorPI);
+    // glibc cosf/sinf are correctly rounded in practice; double-precision evaluation rounded once reproduces them
+    const float a = (float)cos((double)ang), b = (float)sin((double)ang);
+    const uint8_t* cb = blur + plane + (ptrdiff_t)cy * L.pstride + cx;
+    unsigned val = 0;
+#pragma unroll
+    for (int k = 0; k < 8; k++) {
+        const float x0 = (float)s_pat[2 * k][lane][0], y0 = (float)s_pat[2 * k][lane][1];
+        const float x1 = (float)s_pat[2 * k + 1][lane][0], y1 = (float)s_pat[2 * k + 1][lane][1];
+        const int r0 = __float2int_rn(__fadd_rn(__fmul_rn(x0, b), __fmul_rn(y0, a))), q0 = __float2int_rn(__fsub_rn(__fmul_rn(x0, a), __fmul_rn(y0, b)));
+        const int r1 = __float2int_rn(__fadd_rn(__fmul_rn(x1, b), __fmul_rn(y1, a))), q1 = __float2int_rn(__fsub_rn(__fmul_rn(x1, a), __fmul_rn(y1, b)));
+        const int t0 = __ldg(cb + (ptrdiff_t)r0 * L.pstride + q0), t1 = __ldg(cb + (ptrdiff_t)r1 * L.pstride + q1);
+        val |= (unsigned)(t0 < t1) << k;
+    }
+    desc[((size_t)f * out_cap + slot) * 32 + lane] = (uint8_t)val;
+    if (lane == 0) {
+        uvip_keypoint o;
+        o.x = ox; o.y = oy; o.size = size; o.angle = angle; o.response = response; o.octave = octave; o.class_id = class_id;
+        kps[(size_t)f * out_cap + slot] = o;
+    }
+}
+
+}  // namespace uvip
+
+// =====================================================================================================
+// host side
+// =====================================================================================================
+using namespace uvip;
+
+static inline int cv_round_f(float v) { return (int)lrintf(v); }
+
+struct uvip_extractor {
+    uvip_extractor_params prm;
+    int device = 0;
+    cudaStream_t stream = nullptr;
+    float scale[MAXLEV], inv_scale[MAXLEV];
+    int quota[MAXLEV];
+    int umax[HALF_PATCH + 1];
+    Plan plan;                 // for (plan.W, plan.H); W == 0 -> none yet
+    // working set sized for (max_width, max_height, max_batch)
+    size_t cap_frame_bytes = 0; int cap_cells = 0, cap_raw = 0, cap_kp = 0, cap_tab = 0;
+    DevBuf pyr, blur, cand, keys, labels, winners, counters, cellmax, sel, nsel, tabs, status, grid, incoming;
+    DevBuf in_frames, out_kps, out_desc, out_n;      // staging for the host-buffer entry points
+    int sel_cap = 0;
+    int last_frames = 0;
+    long long launches = 0;
+    std::mutex mu;
+};
+
+// per-axis resize table of cv::resize INTER_LINEAR (8-bit fixed point), see SURVEY A.2
+static void build_axis_table(int src_n, int dst_n, int* ofs, int* coef)
+{
+    const double inv_scale = (double)dst_n / src_n;
+    const double scale = 1. / inv_scale;
+    for (int d = 0; d < dst_n; d++) {
+        float fx = (float)((d + 0.5) * scale - 0.5);
+        int s = (int)floorf(fx);
+        fx -= s;
+        if (s < 0) { s = 0; fx = 0; }
+        if (s >= src_n - 1) { s = src_n - 1; fx = 0; }
+        ofs[d] = s;
+        int a0 = cv_round_f((1.f - fx) * 2048.f), a1 = cv_round_f(fx * 2048.f);
+        a0 = a0 > 32767 ? 32767 : (a0 < -32768 ? -32768 : a0);
+        a1 = a1 > 32767 ? 32767 : (a1 < -32768 ? -32768 : a1);
+        coef[d] = (int)(((unsigned)a0 & 0xFFFFu) | ((unsigned)a1 << 16));
+    }
+}
+
+// geometry of a launch group for frames of w x h; returns UVIP_ERR_UNSUPPORTED if outside the envelope
+static int make_plan(const uvip_extractor* ex, int w, int h, Plan* out, std::vector<int>* tabs)
+{
+    Plan P; memset(&P, 0, sizeof(P));
+    const uvip_extractor_params& p = ex->prm;
+    P.nlevels = p.nlevels; P.W = w; P.H = h;
+    P.fast_th = p.fast_th; P.retry_th = p.retry_th;
+    P.t1 = p.fast_th > 1 ? p.fast_th : 1; P.t2 = p.retry_th > 1 ? p.retry_th : 1;
+    P.tmin = P.t1 < P.t2 ? P.t1 : P.t2;
+    if (P.t1 > 254 || P.t2 > 254) { set_last_error("FAST thresholds above 254 are unsupported"); return UVIP_ERR_UNSUPPORTED; }
+    size_t off = 0; int cells = 0, raw = 0, kp = 0, ft = 0, bt = 0, tab = 0, maxN = 0;
+    for (int l = 0; l < p.nlevels; l++) {
+        LevelInfo& L = P.lv[l];
+        L.w = cv_round_f((float)w * ex->inv_scale[l]);          // src/ORBextractor.cc:968
+        L.h = cv_round_f((float)h * ex->inv_scale[l]);
+        if (L.w < 64 || L.h < 64 || L.w > 4095 || L.h > 4095) {
+            set_last_error("level %d is %dx%d: supported level sizes are 64..4095", l, L.w, L.h);
+            return UVIP_ERR_UNSUPPORTED;
+        }
+        L.pstride = (int)align_up((size_t)L.w + 2 * EDGE, 32);
+        L.poff = (unsigned)off;
+        off += align_up((size_t)L.pstride * (L.h + 2 * EDGE) + 64, 256);
+        // cells, src/ORBextractor.cc:756-770
+        const int minB = EDGE - 3, maxBX = L.w - EDGE + 3, maxBY = L.h - EDGE + 3;
+        const float width = (float)(maxBX - minB), height = (float)(maxBY - minB);
+        const float Wc = (float)p.cell;
+        L.ncols = (int)(width / Wc); L.nrows = (int)(height / Wc);
+        if (L.ncols < 1 || L.nrows < 1) { set_last_error("level %d has no FAST cell", l); return UVIP_ERR_UNSUPPORTED; }
+        L.wcell = (int)ceilf(width / L.ncols); L.hcell = (int)ceilf(height / L.nrows);
+        if (L.wcell > 127 || L.hcell > 127) { set_last_error("cell larger than 127 px"); return UVIP_ERR_UNSUPPORTED; }
+        L.cell_off = cells; cells += L.ncols * L.nrows;
+        L.quota = ex->quota[l]; if (L.quota > maxN) maxN = L.quota;
+        const int area = (L.w - 2 * EDGE) * (L.h - 2 * EDGE);
+        L.raw_cap = area / 6 + 256;          // local maxima of the score map; overflow is reported, never truncated
+        L.raw_off = raw; raw += (L.raw_cap + 3) & ~3;
+        // quadtree roots, :1010-1012
+        L.nini = (int)roundf((float)(maxBX - minB) / (float)(maxBY - minB));
+        if (L.nini < 1) { set_last_error("portrait frames with aspect < 0.5 are unsupported (reference divides by zero)"); return UVIP_ERR_UNSUPPORTED; }
+        L.hx = (float)(maxBX - minB) / (float)L.nini;
+        L.kp_cap = (L.quota + 4 > 4 * L.nini ? L.quota + 4 : 4 * L.nini);
+        L.kp_off = kp; kp += L.kp_cap;
+        L.fntx = div_up(L.w - 2 * EDGE, FT_W); L.fnty = div_up(L.h - 2 * EDGE, FT_H);
+        L.ftile_off = ft; ft += L.fntx * L.fnty;
+        L.bntx = div_up(L.w + 2 * BORDER_W, BT_W); L.bnty = div_up(L.h + 2 * BORDER_W, BT_H);
+        L.btile_off = bt; bt += L.bntx * L.bnty;
+        L.tab_off = tab; if (l > 0) tab += 2 * L.w + 2 * L.h;
+        L.scale = ex->scale[l];
+        L.size = (float)(int)(31 * ex->scale[l]);               // :820
+    }
+    P.frame_bytes = off; P.cells_per_frame = cells; P.raw_per_frame = raw; P.kp_per_frame = kp;
+    P.ftiles = ft; P.btiles = bt;
+    int nc = 64; while (nc < maxN + 8 || nc < 16) nc <<= 1;
+    for (int l = 0; l < p.nlevels; l++) while (nc < 4 * P.lv[l].nini + 4) nc <<= 1;
+    if (nc > 4096) { set_last_error("per-level quota %d exceeds the quadtree node capacity", maxN); return UVIP_ERR_UNSUPPORTED; }
+    P.node_cap = nc;
+    if (tabs) {
+        tabs->assign(tab > 0 ? tab : 1, 0);
+        for (int l = 1; l < p.nlevels; l++) {
+            const LevelInfo& D = P.lv[l]; const LevelInfo& S = P.lv[l - 1];
+            int* t = tabs->data() + D.tab_off;
+            build_axis_table(S.w, D.w, t, t + D.w);
+            build_axis_table(S.h, D.h, t + 2 * D.w, t + 2 * D.w + D.h);
+        }
+    }
+    *out = P;
+    return UVIP_OK;
+}
+
+static size_t qt_smem_bytes(int cap) { return (size_t)(4 * cap * 2 + cap * 2 + 4 * cap + cap + cap + (cap + 1) + cap + 4 * cap + cap + cap + cap) * 4; }
+
+static int ensure_plan(uvip_extractor* ex, int w, int h)
+{
+    if (ex->plan.W == w && ex->plan.H == h) return UVIP_OK;
+    UVIP_CHECK_ARG(w <= ex->prm.max_width && h <= ex->prm.max_height);
+    Plan P; std::vector<int> tabs;
+    int rc = make_plan(ex, w, h, &P, &tabs);
+    if (rc) return rc;
+    if (P.frame_bytes > ex->cap_frame_bytes || P.cells_per_frame > ex->cap_cells || P.raw_per_frame > ex->cap_raw ||
+        P.kp_per_frame > ex->cap_kp || (int)tabs.size() > ex->cap_tab) {
+        set_last_error("frame %dx%d needs a larger working set than max_width x max_height provides", w, h);
+        return UVIP_ERR_UNSUPPORTED;
+    }
+    UVIP_CUDA(cudaStreamSynchronize(ex->stream));
+    UVIP_CUDA(cudaFuncSetAttribute(k_quadtree, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)qt_smem_bytes(P.node_cap)));
+    UVIP_CUDA(cudaMemcpy(ex->tabs.p, tabs.data(), tabs.size() * sizeof(int), cudaMemcpyHostToDevice));
+    ex->plan = P;
+    return UVIP_OK;
+}
+
+// enqueue the whole pipeline for nframes frames on st
+static int enqueue_group(uvip_extractor* ex, const uint8_t* d_frames, int nframes, int stride, size_t frame_pitch,
+                         uvip_keypoint* d_kps, int32_t* d_n_out, int out_cap, uint8_t* d_desc,
+                         int full_detect, int n_incoming, int grid_rows, int grid_cols, int min_px_dist, int num_needed, cudaStream_t st)
+{
+    const Plan& P = ex->plan;
+    uint8_t* pyr = ex->pyr.as<uint8_t>(); uint8_t* blur = ex->blur.as<uint8_t>();
+    int* counters = ex->counters.as<int>();
+    const size_t cstride = (size_t)ex->prm.max_batch * P.nlevels;
+    int* cand_count = counters; int* key_count = counters + cstride; int* win_count = counters + 2 * cstride;
+    UVIP_CUDA(cudaMemsetAsync(counters, 0, 3 * cstride * sizeof(int), st));
+    UVIP_CUDA(cudaMemsetAsync(ex->cellmax.p, 0, (size_t)nframes * P.cells_per_frame * sizeof(int), st));
+    UVIP_CUDA(cudaMemsetAsync(ex->status.p, 0, sizeof(int), st));
+    {
+        const LevelInfo& L = P.lv[0];
+        dim3 g(div_up(L.w, 256), div_up(L.h, 4), nframes);
+        k_import<<<g, 256, 0, st>>>(d_frames, stride, frame_pitch, pyr, P);
+        ex->launches++;
+    }
+    for (int l = 1; l < P.nlevels; l++) {
+        const LevelInfo& L = P.lv[l];
+        dim3 g(div_up(L.w, 256), div_up(L.h, 4), nframes);
+        k_resize<<<g, 256, 0, st>>>(pyr, ex->tabs.as<int>(), l, P);
+        ex->launches++;
+    }
+    k_fast<<<dim3(P.ftiles, nframes), 256, 0, st>>>(pyr, ex->cand.as<unsigned>(), cand_count, ex->cellmax.as<int>(), ex->status.as<int>(), P);
+    ex->launches++;
+    k_quadtree<<<dim3(P.nlevels, nframes), QT_THREADS, qt_smem_bytes(P.node_cap), st>>>(
+        ex->cand.as<unsigned>(), cand_count, ex->cellmax.as<int>(), ex->keys.as<unsigned>(), key_count,
+        ex->labels.as<unsigned short>(), ex->winners.as<unsigned>(), win_count, ex->status.as<int>(), P);
+    ex->launches++;
+    k_blur<<<dim3(P.btiles, nframes), 256, 0, st>>>(pyr, blur, P);
+    ex->launches++;
+    k_select<<<nframes, 256, 0, st>>>(ex->winners.as<unsigned>(), win_count, ex->sel.as<unsigned>(), ex->nsel.as<int>(), ex->sel_cap,
+                                       full_detect, n_incoming, ex->grid.as<int32_t>(), grid_rows, grid_cols, min_px_dist, num_needed,
+                                       ex->status.as<int>(), P);
+    ex->launches++;
+    const int slots = out_cap < ex->sel_cap ? out_cap : ex->sel_cap;
+    k_describe<<<dim3(div_up(slots, DESC_WARPS), nframes), DESC_WARPS * 32, 0, st>>>(
+        pyr, blur, ex->winners.as<unsigned>(), ex->sel.as<unsigned>(), ex->nsel.as<int>(), ex->sel_cap,
+        ex->incoming.as<uvip_keypoint>(), d_kps, d_desc, d_n_out, out_cap, ex->status.as<int>(), P);
+    ex->launches++;
+    UVIP_CUDA(cudaGetLastError());
+    ex->last_frames = nframes;
+    return UVIP_OK;
+}
+
+static int read_status(uvip_extractor* ex, cudaStream_t st)
+{
+    int s = 0;
+    UVIP_CUDA(cudaMemcpyAsync(&s, ex->status.p, sizeof(int), cudaMemcpyDeviceToHost, st));
+    UVIP_CUDA(cudaStreamSynchronize(st));
+    if (s) {
+        set_last_error("device capacity overflow, flags 0x%x (1 FAST candidates, 2 quadtree nodes, 4 winners, 8 output rows)", s);
+        return UVIP_ERR_CAPACITY;
+    }
+    return UVIP_OK;
+}
+
+extern "C" {
+
+int uvip_extractor_create(const uvip_extractor_params* params, uvip_extractor** out)
+{
+    UVIP_CHECK_ARG(params && out);
+    *out = nullptr;
+    UVIP_CHECK_ARG(params->nlevels >= 1 && params->nlevels <= MAXLEV && params->nfeatures >= 1);
+    UVIP_CHECK_ARG(params->scale_factor > 1.0f && params->max_batch >= 1 && params->max_width >= 64 && params->max_height >= 64);
+    UVIP_CHECK_ARG(params->fast_th >= 0);
+    int ndev = 0;
+    if (cudaGetDeviceCount(&ndev) != cudaSuccess || ndev == 0) {
+        set_last_error("no CUDA device available; libuvip_orb has no CPU fallback");
+        return UVIP_ERR_NO_DEVICE;
+    }
+    UVIP_CHECK_ARG(params->device >= 0 && params->device < ndev);
+    DeviceGuard g(params->device);
+    uvip_extractor* ex = new uvip_extractor();
+    ex->prm = *params;
+    if (ex->prm.retry_th <= 0) ex->prm.retry_th = 7;
+    if (ex->prm.cell <= 0) ex->prm.cell = 30;
+    ex->device = params->device;
+    memset(&ex->plan, 0, sizeof(ex->plan));
+    // constructor tables, src/ORBextractor.cc:458-512
+    const double scaleFactor = (double)params->scale_factor;
+    const int nl = params->nlevels;
+    ex->scale[0] = 1.0f;
+    for (int i = 1; i < nl; i++) ex->scale[i] = (float)((double)ex->scale[i - 1] * scaleFactor);
+    const float invScaleFactor = (float)(1.0f / scaleFactor);
+    ex->inv_scale[0] = 1.0f;
+    for (int i = 1; i < nl; i++) ex->inv_scale[i] = ex->inv_scale[i - 1] * invScaleFactor;
+    const float factor = (float)(1.0 / scaleFactor);
+    float nDesired = params->nfeatures * (1 - factor) / (1 - (float)pow((double)factor, (double)nl));
+    int sum = 0;
+    for (int l = 0; l < nl - 1; l++) { ex->quota[l] = cv_round_f(nDesired); sum += ex->quota[l]; nDesired *= factor; }
+    ex->quota[nl - 1] = params->nfeatures - sum > 0 ? params->nfeatures - sum : 0;
+    {
+        int v, v0;
+        const int vmax = (int)floor(HALF_PATCH * sqrtf(2.f) / 2 + 1), vmin = (int)ceil(HALF_PATCH * sqrtf(2.f) / 2);
+        const double hp2 = HALF_PATCH * HALF_PATCH;
+        for (v = 0; v <= vmax; ++v) ex->umax[v] = (int)lrint(sqrt(hp2 - v * v));
+        for (v = HALF_PATCH, v0 = 0; v >= vmin; --v) { while (ex->umax[v0] == ex->umax[v0 + 1]) ++v0; ex->umax[v] = v0; ++v0; }
+    }
+    // capacity from the maximal frame
+    Plan P;
+    int rc = make_plan(ex, params->max_width, params->max_height, &P, nullptr);
+    if (rc) { delete ex; return rc; }
+    const int B = params->max_batch;
+    ex->cap_frame_bytes = P.frame_bytes; ex->cap_cells = P.cells_per_frame; ex->cap_raw = P.raw_per_frame; ex->cap_kp = P.kp_per_frame;
+    int tab = 0; for (int l = 1; l < nl; l++) tab += 2 * P.lv[l].w + 2 * P.lv[l].h;
+    ex->cap_tab = tab + 64;
+    ex->sel_cap = P.kp_per_frame + 4096;     // output rows per frame: quadtree winners + up to 4096 incoming keypoints
+    cudaError_t e = cudaStreamCreateWithFlags(&ex->stream, cudaStreamNonBlocking);
+    if (e != cudaSuccess) { set_last_error("cudaStreamCreate -> %s", cudaGetErrorString(e)); delete ex; return UVIP_ERR_CUDA; }
+    rc = 0;
+    rc |= ex->pyr.reserve((size_t)B * P.frame_bytes + 4096);
+    rc |= ex->blur.reserve((size_t)B * P.frame_bytes + 4096);
+    rc |= ex->cand.reserve((size_t)B * P.raw_per_frame * 4);
+    rc |= ex->keys.reserve((size_t)B * P.raw_per_frame * 4);
+    rc |= ex->labels.reserve((size_t)B * P.raw_per_frame * 2);
+    rc |= ex->winners.reserve((size_t)B * P.kp_per_frame * 4);
+    rc |= ex->counters.reserve((size_t)3 * B * nl * 4);
+    rc |= ex->cellmax.reserve((size_t)B * P.cells_per_frame * 4);
+    rc |= ex->sel.reserve((size_t)B * ex->sel_cap * 4);
+    rc |= ex->nsel.reserve((size_t)B * 4);
+    rc |= ex->tabs.reserve((size_t)ex->cap_tab * 4);
+    rc |= ex->status.reserve(16);
+    rc |= ex->grid.reserve(16);
+    rc |= ex->incoming.reserve(sizeof(uvip_keypoint));
+    if (rc) { uvip_extractor_destroy(ex); return UVIP_ERR_CUDA; }
+    // zero the planes once so halo loads never see uninitialised memory
+    cudaMemset(ex->pyr.p, 0, ex->pyr.cap); cudaMemset(ex->blur.p, 0, ex->blur.cap);
+    cudaMemset(ex->status.p, 0, 16);
+    if (cudaMemcpyToSymbol(c_pattern, h_pattern, sizeof(h_pattern)) != cudaSuccess ||
+        cudaMemcpyToSymbol(c_umax, ex->umax, sizeof(ex->umax)) != cudaSuccess) {
+        set_last_error("cudaMemcpyToSymbol failed: %s", cudaGetErrorString(cudaGetLastError()));
+        uvip_extractor_destroy(ex); return UVIP_ERR_CUDA;
+    }
+    const size_t qsm = qt_smem_bytes(P.node_cap);
+    if (cudaFuncSetAttribute(k_quadtree, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)qsm) != cudaSuccess) {
+        set_last_error("quadtree kernel needs %zu bytes of shared memory: %s", qsm, cudaGetErrorString(cudaGetLastError()));
+        uvip_extractor_destroy(ex); return UVIP_ERR_UNSUPPORTED;
+    }
+    *out = ex;
+    return UVIP_OK;
+}
+
+int uvip_extractor_destroy(uvip_extractor* ex)
+{
+    if (!ex) return UVIP_OK;
+    DeviceGuard g(ex->device);
+    if (ex->stream) cudaStreamSynchronize(ex->stream);
+    DevBuf* bufs[] = {&ex->pyr, &ex->blur, &ex->cand, &ex->keys, &ex->labels, &ex->winners, &ex->counters, &ex->cellmax, &ex->sel,
+                      &ex->nsel, &ex->tabs, &ex->status, &ex->grid, &ex->incoming, &ex->in_frames, &ex->out_kps, &ex->out_desc, &ex->out_n};
+    for (DevBuf* b : bufs) b->release();
+    if (ex->stream) cudaStreamDestroy(ex->stream);
+    delete ex;
+    return UVIP_OK;
+}
+
+int uvip_extractor_levels(const uvip_extractor* ex) { return ex ? ex->prm.nlevels : 0; }
+float uvip_extractor_scale_factor(const uvip_extractor* ex) { return ex ? (float)(double)ex->prm.scale_factor : 0.f; }
+long long uvip_extractor_launch_count(const uvip_extractor* ex) { return ex ? ex->launches : 0; }
+
+int uvip_extractor_tables(const uvip_extractor* ex, float* scale, float* inv_scale, int32_t* quota, int32_t* umax)
+{
+    UVIP_CHECK_ARG(ex);
+    for (int l = 0; l < ex->prm.nlevels; l++) {
+        if (scale) scale[l] = ex->scale[l];
+        if (inv_scale) inv_scale[l] = ex->inv_scale[l];
+        if (quota) quota[l] = ex->quota[l];
+    }
+    if (umax) for (int v = 0; v <= HALF_PATCH; v++) umax[v] = ex->umax[v];
+    return UVIP_OK;
+}
+
+int uvip_extract_batch_device(uvip_extractor* ex, const uint8_t* d_frames, int nframes, int w, int h, int stride,
+                              size_t frame_pitch, uvip_keypoint* d_kps, int32_t* d_n_out, int cap, uint8_t* d_desc, void* stream)
+{
+    UVIP_CHECK_ARG(ex && d_frames && d_kps && d_n_out && d_desc);
+    UVIP_CHECK_ARG(nframes >= 1 && nframes <= ex->prm.max_batch && w > 0 && h > 0 && stride >= w && cap >= 1);
+    DeviceGuard g(ex->device);
+    int rc = ensure_plan(ex, w, h);
+    if (rc) return rc;
+    cudaStream_t st = stream ? (cudaStream_t)stream : ex->stream;
+    return enqueue_group(ex, d_frames, nframes, stride, frame_pitch, d_kps, d_n_out, cap, d_desc, 1, 0, 1, 1, 1, 0, st);
+}
+
+int uvip_extractor_status(uvip_extractor* ex)
+{
+    UVIP_CHECK_ARG(ex);
+    DeviceGuard g(ex->device);
+    UVIP_CUDA(cudaDeviceSynchronize());
+    return read_status(ex, ex->stream);
+}
+
+int uvip_extract_batch(uvip_extractor* ex, const uint8_t* frames, int nframes, int w, int h, int stride,
+                       size_t frame_pitch, uvip_keypoint* kps, int32_t* n_out, int cap, uint8_t* desc)
+{
+    UVIP_CHECK_ARG(ex && frames && kps && n_out && desc && nframes >= 1 && w > 0 && h > 0 && stride >= w && cap >= 1);
+    UVIP_CHECK_ARG(frame_pitch >= (size_t)stride * (h - 1) + w);
+    std::lock_guard<std::mutex> lk(ex->mu);
+    DeviceGuard g(ex->device);
+    int rc = ensure_plan(ex, w, h);
+    if (rc) return rc;
+    const int B = ex->prm.max_batch;
+    const size_t fbytes = (size_t)stride * h;
+    if ((rc = ex->in_frames.reserve((size_t)B * fbytes))) return rc;
+    if ((rc = ex->out_kps.reserve((size_t)B * cap * sizeof(uvip_keypoint)))) return rc;
+    if ((rc = ex->out_desc.reserve((size_t)B * cap * 32))) return rc;
+    if ((rc = ex->out_n.reserve((size_t)B * 4))) return rc;
+    cudaStream_t st = ex->stream;
+    for (int f0 = 0; f0 < nframes; f0 += B) {
+        const int nb = nframes - f0 < B ? nframes - f0 : B;
+        if (frame_pitch == fbytes) UVIP_CUDA(cudaMemcpyAsync(ex->in_frames.p, frames + (size_t)f0 * frame_pitch, (size_t)nb * fbytes, cudaMemcpyHostToDevice, st));
+        else UVIP_CUDA(cudaMemcpy2DAsync(ex->in_frames.p, fbytes, frames + (size_t)f0 * frame_pitch, frame_pitch, fbytes - (stride - w), nb, cudaMemcpyHostToDevice, st));
+        rc = enqueue_group(ex, ex->in_frames.as<uint8_t>(), nb, stride, fbytes, ex->out_kps.as<uvip_keypoint>(), ex->out_n.as<int32_t>(),
+                           cap, ex->out_desc.as<uint8_t>(), 1, 0, 1, 1, 1, 0, st);
+        if (rc) return rc;
+        UVIP_CUDA(cudaMemcpyAsync(n_out + f0, ex->out_n.p, (size_t)nb * 4, cudaMemcpyDeviceToHost, st));
+        UVIP_CUDA(cudaMemcpyAsync(kps + (size_t)f0 * cap, ex->out_kps.p, (size_t)nb * cap * sizeof(uvip_keypoint), cudaMemcpyDeviceToHost, st));
+        UVIP_CUDA(cudaMemcpyAsync(desc + (size_t)f0 * cap * 32, ex->out_desc.p, (size_t)nb * cap * 32, cudaMemcpyDeviceToHost, st));
+        if ((rc = read_status(ex, st))) return rc;
+    }
+    return UVIP_OK;
+}
+
+int uvip_extract(uvip_extractor* ex, const uint8_t* image, int w, int h, int stride,
+                 uvip_keypoint* kps, int* n_inout, int cap, uint8_t* desc,
+                 int32_t* grid, int grid_rows, int grid_cols, int min_px_dist, int full_detect, int num_needed)
+{
+    UVIP_CHECK_ARG(ex && n_inout);
+    if (!image || w <= 0 || h <= 0) return UVIP_OK;               // empty image: outputs untouched (src/ORBextractor.cc:852-853)
+    UVIP_CHECK_ARG(kps && desc && stride >= w && cap >= 1);
+    const int n_in = (!full_detect && *n_inout > 0) ? *n_inout : 0;
+    UVIP_CHECK_ARG(n_in <= 4096 && n_in <= cap);
+    if (!full_detect) UVIP_CHECK_ARG(grid && grid_rows > 0 && grid_cols > 0 && min_px_dist > 0);
+    std::lock_guard<std::mutex> lk(ex->mu);
+    DeviceGuard g(ex->device);
+    int rc = ensure_plan(ex, w, h);
+    if (rc) return rc;
+    const size_t fbytes = (size_t)stride * h;
+    if ((rc = ex->in_frames.reserve(fbytes))) return rc;
+    if ((rc = ex->out_kps.reserve((size_t)cap * sizeof(uvip_keypoint)))) return rc;
+    if ((rc = ex->out_desc.reserve((size_t)cap * 32))) return rc;
+    if ((rc = ex->out_n.reserve(4))) return rc;
+    cudaStream_t st = ex->stream;
+    UVIP_CUDA(cudaMemcpyAsync(ex->in_frames.p, image, fbytes - (stride - w), cudaMemcpyHostToDevice, st));
+    if (!full_detect) {
+        if ((rc = ex->grid.reserve((size_t)grid_rows * grid_cols * 4))) return rc;
+        UVIP_CUDA(cudaMemcpyAsync(ex->grid.p, grid, (size_t)grid_rows * grid_cols * 4, cudaMemcpyHostToDevice, st));
+        if (n_in) {
+            if ((rc = ex->incoming.reserve((size_t)n_in * sizeof(uvip_keypoint)))) return rc;
+            UVIP_CUDA(cudaMemcpyAsync(ex->incoming.p, kps, (size_t)n_in * sizeof(uvip_keypoint), cudaMemcpyHostToDevice, st));
+        }
+    }
+    rc = enqueue_group(ex, ex->in_frames.as<uint8_t>(), 1, stride, fbytes, ex->out_kps.as<uvip_keypoint>(), ex->out_n.as<int32_t>(),
+                       cap, ex->out_desc.as<uint8_t>(), full_detect ? 1 : 0, n_in, grid_rows, grid_cols, min_px_dist, num_needed, st);
+    if (rc) return rc;
+    int n = 0;
+    UVIP_CUDA(cudaMemcpyAsync(&n, ex->out_n.p, 4, cudaMemcpyDeviceToHost, st));
+    if ((rc = read_status(ex, st))) return rc;
+    if (n > cap) { set_last_error("%d keypoints do not fit cap %d", n, cap); return UVIP_ERR_CAPACITY; }
+    if (n) {
+        UVIP_CUDA(cudaMemcpyAsync(kps, ex->out_kps.p, (size_t)n * sizeof(uvip_keypoint), cudaMemcpyDeviceToHost, st));
+        UVIP_CUDA(cudaMemcpyAsync(desc, ex->out_desc.p, (size_t)n * 32, cudaMemcpyDeviceToHost, st));
+    }
+    if (!full_detect) UVIP_CUDA(cudaMemcpyAsync(grid, ex->grid.p, (size_t)grid_rows * grid_cols * 4, cudaMemcpyDeviceToHost, st));
+    UVIP_CUDA(cudaStreamSynchronize(st));
+    *n_inout = n;
+    return UVIP_OK;
+}
+
+// ---- debug taps ------------------------------------------------------------------------------------
+int uvip_get_pyramid_level(uvip_extractor* ex, int frame, int level, int blurred, uint8_t* dst, int dstride, int* w, int* h)
+{
+    UVIP_CHECK_ARG(ex && ex->plan.W > 0 && frame >= 0 && frame < ex->last_frames && level >= 0 && level < ex->prm.nlevels);
+    const LevelInfo& L = ex->plan.lv[level];
+    if (w) *w = L.w; if (h) *h = L.h;
+    if (!dst) return UVIP_OK;
+    UVIP_CHECK_ARG(dstride >= L.w);
+    DeviceGuard g(ex->device);
+    UVIP_CUDA(cudaDeviceSynchronize());
+    const uint8_t* base = (blurred ? ex->blur.as<uint8_t>() : ex->pyr.as<uint8_t>()) + (size_t)frame * ex->plan.frame_bytes + L.poff +
+                          (size_t)EDGE * L.pstride + EDGE;
+    UVIP_CUDA(cudaMemcpy2D(dst, dstride, base, L.pstride, L.w, L.h, cudaMemcpyDeviceToHost));
+    return UVIP_OK;
+}
+
+static int fetch_list(uvip_extractor* ex, const DevBuf& buf, size_t elem_off, int n, std::vector<unsigned>* out)
+{
+    out->resize(n > 0 ? n : 0);
+    if (n > 0) UVIP_CUDA(cudaMemcpy(out->data(), buf.as<unsigned>() + elem_off, (size_t)n * 4, cudaMemcpyDeviceToHost));
+    return UVIP_OK;
+}
+
+int uvip_get_raw_corners(uvip_extractor* ex, int frame, int level, int32_t* xs, int32_t* ys, int32_t* scores, int cap, int* n)
+{
+    UVIP_CHECK_ARG(ex && n && ex->plan.W > 0 && frame >= 0 && frame < ex->last_frames && level >= 0 && level < ex->prm.nlevels);
+    DeviceGuard g(ex->device);
+    UVIP_CUDA(cudaDeviceSynchronize());
+    const Plan& P = ex->plan; const LevelInfo& L = P.lv[level];
+    int cnt = 0;
+    const size_t cstride = (size_t)ex->prm.max_batch * P.nlevels;
+    UVIP_CUDA(cudaMemcpy(&cnt, ex->counters.as<int>() + cstride + (size_t)frame * P.nlevels + level, 4, cudaMemcpyDeviceToHost));
+    std::vector<unsigned> v;
+    int rc = fetch_list(ex, ex->keys, (size_t)frame * P.raw_per_frame + L.raw_off, cnt, &v);
+    if (rc) return rc;
+    // reference order: cell row, cell column, then y, x inside the cell (src/ORBextractor.cc:772-812)
+    auto okey = [&](unsigned c) {
+        const int x = (int)(c & 0xFFF) - EDGE, y = (int)((c >> 12) & 0xFFF) - EDGE;
+        const int cx = x / L.wcell, cy = y / L.hcell;
+        return ((unsigned long long)(cy * L.ncols + cx) << 24) | ((unsigned long long)y << 12) | (unsigned long long)x;
+    };
+    std::vector<std::pair<unsigned long long, unsigned>> s; s.reserve(v.size());
+    for (unsigned c : v) s.emplace_back(okey(c), c);
+    std::sort(s.begin(), s.end());
+    *n = cnt;
+    for (int i = 0; i < cnt && i < cap; i++) {
+        const unsigned c = s[i].second;
+        if (xs) xs[i] = (int)(c & 0xFFF) - (EDGE - 3);          // window coords (relative to minBorder = 13)
+        if (ys) ys[i] = (int)((c >> 12) & 0xFFF) - (EDGE - 3);
+        if (scores) scores[i] = (int)(c >> 24);
+    }
+    return UVIP_OK;
+}
+
+int uvip_get_level_keypoints(uvip_extractor* ex, int frame, int level, int32_t* xs, int32_t* ys, int32_t* scores, int cap, int* n)
+{
+    UVIP_CHECK_ARG(ex && n && ex->plan.W > 0 && frame >= 0 && frame < ex->last_frames && level >= 0 && level < ex->prm.nlevels);
+    DeviceGuard g(ex->device);
+    UVIP_CUDA(cudaDeviceSynchronize());
+    const Plan& P = ex->plan; const LevelInfo& L = P.lv[level];
+    int cnt = 0;
+    const size_t cstride = (size_t)ex->prm.max_batch * P.nlevels;
+    UVIP_CUDA(cudaMemcpy(&cnt, ex->counters.as<int>() + 2 * cstride + (size_t)frame * P.nlevels + level, 4, cudaMemcpyDeviceToHost));
+    std::vector<unsigned> v;
+    int rc = fetch_list(ex, ex->winners, (size_t)frame * P.kp_per_frame + L.kp_off, cnt, &v);
+    if (rc) return rc;
+    *n = cnt;
+    for (int i = 0; i < cnt && i < cap; i++) {
+        if (xs) xs[i] = (int)(v[i] & 0xFFF);
+        if (ys) ys[i] = (int)((v[i] >> 12) & 0xFFF);
+        if (scores) scores[i] = (int)(v[i] >> 24);
+    }
+    return UVIP_OK;
+}
+
+}  // extern "C"

@@ -1,0 +1,704 @@
+// matcher.cu — descriptor path of USLAM::ORBmatcher on sm_100a: 256-bit Hamming distance, brute-force
+// k=2 nearest neighbours (popc-pipe bound), shard merge, ratio test, rotation histogram, frame grid and
+// the grid-windowed search with sequentially-consistent claims.  C-ABI: include/uvip_orb.h.
+//
+// Reference semantics restated here (never its code): src/ORBmatcher.cc:40-133,1748-1810,
+// src/FrameKTL.cc:250-264,359-436, include/utils.h:81-111.
+#include "common.cuh"
+#include <stdarg.h>
+#include <limits.h>
+
+namespace uvip {
+
+static thread_local char g_err[512] = "";
+void set_last_error(const char* fmt, ...) {
+    va_list ap; va_start(ap, fmt);
+    vsnprintf(g_err, sizeof(g_err), fmt, ap);
+    va_end(ap);
+}
+
+// =====================================================================================================
+// K9: tiled Hamming top-2.  One thread per query (descriptor in 8 registers); train rows stream through
+// shared memory in 8 KB stages filled by the TMA engine (cp.async.bulk + mbarrier), every lane reads the
+// same train row (LDS.128 broadcast), so per descriptor pair the SM executes 8 LOP3 + 8 POPC + 4 IADD3/LEA
+// + 3 VIMNMX.  POPC issues at 16 lanes/clk/SM -> 2 pairs/clk/SM is the roofline.
+// Running top-2 is kept as packed 32-bit keys (dist << 16 | row-in-supertile): unique keys give the
+// (distance, index) order, i.e. the reference's strict '<' scan where the first candidate wins ties.
+// =====================================================================================================
+constexpr int KNN_THREADS = 128;
+constexpr int KNN_TILE = 256;                      // train rows per stage
+constexpr int KNN_STAGE_BYTES = KNN_TILE * 32;
+constexpr int KNN_SUPER = 256;                     // tiles per 16-bit index window (65536 rows)
+
+__device__ __forceinline__ void top2_push(int d, int gi, int& d1, int& i1, int& d2, int& i2) {
+    if (d < d1) { d2 = d1; i2 = i1; d1 = d; i1 = gi; }
+    else if (d < d2) { d2 = d; i2 = gi; }
+}
+
+__global__ void __launch_bounds__(KNN_THREADS)
+k_knn2(const uint8_t* __restrict__ q_base, const int32_t* __restrict__ d_nq, size_t q_pitch,
+       const uint8_t* __restrict__ t_base, const int32_t* __restrict__ d_nt, size_t t_pitch,
+       int nq_fixed, int nt_fixed, int idx_base,
+       int32_t* __restrict__ idx2, int32_t* __restrict__ dist2, size_t res_pitch)
+{
+    __shared__ __align__(128) uint8_t s_tile[2][KNN_STAGE_BYTES];
+    __shared__ __align__(8) uint64_t s_bar[2];
+
+    const int pair = blockIdx.y;
+    const int nq = d_nq ? d_nq[pair] : nq_fixed;
+    const int nt = d_nt ? d_nt[pair] : nt_fixed;
+    if ((int)(blockIdx.x * KNN_THREADS) >= nq) return;          // uniform per block
+    const uint8_t* q = q_base + (size_t)pair * q_pitch;
+    const uint8_t* t = t_base + (size_t)pair * t_pitch;
+    const int tid = threadIdx.x;
+    const int qi = blockIdx.x * KNN_THREADS + tid;
+    const bool live = qi < nq;
+
+    uint32_t a0 = 0, a1 = 0, a2 = 0, a3 = 0, a4 = 0, a5 = 0, a6 = 0, a7 = 0;
+    if (live) {
+        const uint4* qp = reinterpret_cast<const uint4*>(q + (size_t)qi * 32);
+        uint4 u = __ldg(qp), v = __ldg(qp + 1);
+        a0 = u.x; a1 = u.y; a2 = u.z; a3 = u.w; a4 = v.x; a5 = v.y; a6 = v.z; a7 = v.w;
+    }
+
+    const int ntiles = (nt + KNN_TILE - 1) / KNN_TILE;
+    if (tid == 0) {
+        mbar_init(&s_bar[0], 1);
+        mbar_init(&s_bar[1], 1);
+        mbar_fence_init();
+    }
+    __syncthreads();
+    if (tid == 0) {
+        for (int s = 0; s < 2 && s < ntiles; s++) {
+            const int rows = min(KNN_TILE, nt - s * KNN_TILE);
+            mbar_arrive_expect_tx(&s_bar[s], rows * 32);
+            bulk_g2s(s_tile[s], t + (size_t)s * KNN_STAGE_BYTES, rows * 32, &s_bar[s]);
+        }
+    }
+
+    int g1d = 257, g2d = 257, g1i = -1, g2i = -1;
+    uint32_t b1 = 0xFFFFFFFFu, b2 = 0xFFFFFFFFu;
+
+    for (int i = 0; i < ntiles; i++) {
+        const int s = i & 1;
+        mbar_wait(&s_bar[s], (i >> 1) & 1);
+        const int rows = min(KNN_TILE, nt - i * KNN_TILE);
+        const uint4* T = reinterpret_cast<const uint4*>(s_tile[s]);
+        uint32_t key = (uint32_t)((i & (KNN_SUPER - 1)) * KNN_TILE);
+#pragma unroll 4
+        for (int j = 0; j < rows; j++) {
+            const uint4 u = T[2 * j], v = T[2 * j + 1];
+            const int d = (__popc(a0 ^ u.x) + __popc(a1 ^ u.y) + __popc(a2 ^ u.z)) +
+                          (__popc(a3 ^ u.w) + __popc(a4 ^ v.x) + __popc(a5 ^ v.y)) +
+                          (__popc(a6 ^ v.z) + __popc(a7 ^ v.w));
+            const uint32_t k = ((uint32_t)d << 16) + key + (uint32_t)j;
+            const uint32_t lo = min(b1, k), hi = max(b1, k);
+            b2 = min(b2, hi);
+            b1 = lo;
+        }
+        __syncthreads();                                           // stage s fully consumed
+        if (tid == 0 && i + 2 < ntiles) {
+            const int r2 = min(KNN_TILE, nt - (i + 2) * KNN_TILE);
+            mbar_arrive_expect_tx(&s_bar[s], r2 * 32);
+            bulk_g2s(s_tile[s], t + (size_t)(i + 2) * KNN_STAGE_BYTES, r2 * 32, &s_bar[s]);
+        }
+        if ((i & (KNN_SUPER - 1)) == KNN_SUPER - 1 || i == ntiles - 1) {
+            const int sbase = idx_base + (i & ~(KNN_SUPER - 1)) * KNN_TILE;
+            if (b1 != 0xFFFFFFFFu) top2_push((int)(b1 >> 16), sbase + (int)(b1 & 0xFFFFu), g1d, g1i, g2d, g2i);
+            if (b2 != 0xFFFFFFFFu) top2_push((int)(b2 >> 16), sbase + (int)(b2 & 0xFFFFu), g1d, g1i, g2d, g2i);
+            b1 = b2 = 0xFFFFFFFFu;
+        }
+    }
+    if (live) {
+        int32_t* oi = idx2 + (size_t)pair * 2 * res_pitch + 2 * (size_t)qi;
+        int32_t* od = dist2 + (size_t)pair * 2 * res_pitch + 2 * (size_t)qi;
+        *reinterpret_cast<int2*>(oi) = make_int2(g1i, g2i);
+        *reinterpret_cast<int2*>(od) = make_int2(g1d, g2d);
+    }
+}
+
+// K12 merge: lexicographic min-2 over (dist, global index) across partial lists — shard-count invariant
+__global__ void k_knn2_merge(const int32_t* __restrict__ idx_parts, const int32_t* __restrict__ dist_parts, int nparts,
+                             size_t part_stride, int nq, int32_t* __restrict__ idx2, int32_t* __restrict__ dist2)
+{
+    const int qi = blockIdx.x * blockDim.x + threadIdx.x;
+    if (qi >= nq) return;
+    int d1 = 257, d2 = 257, i1 = -1, i2 = -1;
+    for (int p = 0; p < nparts; p++) {
+        const int2 ii = *reinterpret_cast<const int2*>(idx_parts + p * part_stride + 2 * (size_t)qi);
+        const int2 dd = *reinterpret_cast<const int2*>(dist_parts + p * part_stride + 2 * (size_t)qi);
+        const int ci[2] = {ii.x, ii.y}, cd[2] = {dd.x, dd.y};
+#pragma unroll
+        for (int k = 0; k < 2; k++) {
+            const int d = cd[k], gi = ci[k];
+            if (gi < 0) continue;
+            if (d < d1 || (d == d1 && gi < i1)) { d2 = d1; i2 = i1; d1 = d; i1 = gi; }
+            else if (d < d2 || (d == d2 && gi < i2)) { d2 = d; i2 = gi; }
+        }
+    }
+    *reinterpret_cast<int2*>(idx2 + 2 * (size_t)qi) = make_int2(i1, i2);
+    *reinterpret_cast<int2*>(dist2 + 2 * (size_t)qi) = make_int2(d1, d2);
+}
+
+// M1: DescriptorDistance for n row pairs
+__global__ void k_descriptor_distance(const uint8_t* __restrict__ a, const uint8_t* __restrict__ b, int n, int32_t* __restrict__ out)
+{
+    const int i = blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= n) return;
+    const uint4* pa = reinterpret_cast<const uint4*>(a + (size_t)i * 32);
+    const uint4* pb = reinterpret_cast<const uint4*>(b + (size_t)i * 32);
+    const uint4 u = pa[0], v = pa[1], x = pb[0], y = pb[1];
+    out[i] = __popc(u.x ^ x.x) + __popc(u.y ^ x.y) + __popc(u.z ^ x.z) + __popc(u.w ^ x.w) +
+             __popc(v.x ^ y.x) + __popc(v.y ^ y.y) + __popc(v.z ^ y.z) + __popc(v.w ^ y.w);
+}
+
+// ratio test, include/utils.h:104-108 (float distances, double ratio)
+__global__ void k_ratio_filter(const int32_t* __restrict__ idx2, const int32_t* __restrict__ dist2, int nq, double ratio,
+                               int32_t* __restrict__ match, int* __restrict__ nmatches)
+{
+    const int i = blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= nq) return;
+    int m = -1;
+    if (idx2[2 * i] >= 0 && idx2[2 * i + 1] >= 0) {
+        const float d0 = (float)dist2[2 * i], d1 = (float)dist2[2 * i + 1];
+        if ((double)d0 <= __dmul_rn((double)d1, ratio)) m = idx2[2 * i];
+    }
+    match[i] = m;
+    if (m >= 0) atomicAdd(nmatches, 1);
+}
+
+// K11 rotation histogram: single CTA
+__global__ void k_rot_hist(int32_t* __restrict__ match, int n, const float* __restrict__ angle_a, const float* __restrict__ angle_b,
+                           int* __restrict__ nkept)
+{
+    __shared__ int hist[UVIP_HISTO_LENGTH];
+    __shared__ int keep[3];
+    __shared__ int kept;
+    const float factor = 1.0f / UVIP_HISTO_LENGTH;
+    for (int i = threadIdx.x; i < UVIP_HISTO_LENGTH; i += blockDim.x) hist[i] = 0;
+    if (threadIdx.x == 0) kept = 0;
+    __syncthreads();
+    auto bin_of = [&](int i) -> int {
+        float rot = __fsub_rn(angle_a[i], angle_b[match[i]]);
+        if (rot < 0.0f) rot = __fadd_rn(rot, 360.0f);
+        int bin = (int)roundf(__fmul_rn(rot, factor));
+        if (bin == UVIP_HISTO_LENGTH) bin = 0;
+        return bin;
+    };
+    for (int i = threadIdx.x; i < n; i += blockDim.x) {
+        if (match[i] < 0) continue;
+        const int b = bin_of(i);
+        if (b >= 0 && b < UVIP_HISTO_LENGTH) atomicAdd(&hist[b], 1);
+    }
+    __syncthreads();
+    if (threadIdx.x == 0) {     // ComputeThreeMaxima, src/ORBmatcher.cc:1748-1789
+        int max1 = 0, max2 = 0, max3 = 0, ind1 = -1, ind2 = -1, ind3 = -1;
+        for (int i = 0; i < UVIP_HISTO_LENGTH; i++) {
+            const int s = hist[i];
+            if (s > max1) { max3 = max2; max2 = max1; max1 = s; ind3 = ind2; ind2 = ind1; ind1 = i; }
+            else if (s > max2) { max3 = max2; max2 = s; ind3 = ind2; ind2 = i; }
+            else if (s > max3) { max3 = s; ind3 = i; }
+        }
+        if ((float)max2 < __fmul_rn(0.1f, (float)max1)) { ind2 = -1; ind3 = -1; }
+        else if ((float)max3 < __fmul_rn(0.1f, (float)max1)) { ind3 = -1; }
+        keep[0] = ind1; keep[1] = ind2; keep[2] = ind3;
+    }
+    __syncthreads();
+    for (int i = threadIdx.x; i < n; i += blockDim.x) {
+        if (match[i] < 0) continue;
+        const int b = bin_of(i);
+        if (b >= 0 && b < UVIP_HISTO_LENGTH && b != keep[0] && b != keep[1] && b != keep[2]) match[i] = -1;
+        else atomicAdd(&kept, 1);
+    }
+    __syncthreads();
+    if (threadIdx.x == 0) *nkept = kept;
+}
+
+// frame grid: FrameKTL.cc:250-264 + PosInGrid :426-436.  Single CTA; counts/cursors in dynamic smem.
+__global__ void k_grid_build(const float* __restrict__ kx, const float* __restrict__ ky, int n,
+                             float min_x, float min_y, float inv_w, float inv_h, int cols, int rows,
+                             int32_t* __restrict__ cell_start, int32_t* __restrict__ cell_items, int32_t* __restrict__ cell_of)
+{
+    extern __shared__ int s_cnt[];      // ncell + 1 counts, then ncell cursors
+    const int ncell = cols * rows;
+    int* s_cur = s_cnt + ncell + 1;
+    for (int c = threadIdx.x; c <= ncell; c += blockDim.x) s_cnt[c] = 0;
+    for (int c = threadIdx.x; c < ncell; c += blockDim.x) s_cur[c] = 0;
+    __syncthreads();
+    for (int i = threadIdx.x; i < n; i += blockDim.x) {
+        const int px = (int)roundf(__fmul_rn(__fsub_rn(kx[i], min_x), inv_w));
+        const int py = (int)roundf(__fmul_rn(__fsub_rn(ky[i], min_y), inv_h));
+        int c = -1;
+        if (px >= 0 && px < cols && py >= 0 && py < rows) { c = px * rows + py; atomicAdd(&s_cnt[c + 1], 1); }
+        cell_of[i] = c;
+    }
+    __syncthreads();
+    if (threadIdx.x == 0) for (int c = 0; c < ncell; c++) s_cnt[c + 1] += s_cnt[c];
+    __syncthreads();
+    for (int c = threadIdx.x; c <= ncell; c += blockDim.x) cell_start[c] = s_cnt[c];
+    for (int i = threadIdx.x; i < n; i += blockDim.x) {
+        const int c = cell_of[i];
+        if (c >= 0) cell_items[s_cnt[c] + atomicAdd(&s_cur[c], 1)] = i;
+    }
+    __syncthreads();
+    for (int c = threadIdx.x; c < ncell; c += blockDim.x) {       // ascending keypoint index inside a cell
+        const int b = s_cnt[c], e = s_cnt[c + 1];
+        for (int i = b + 1; i < e; i++) {
+            const int v = cell_items[i];
+            int j = i - 1;
+            while (j >= b && cell_items[j] > v) { cell_items[j + 1] = cell_items[j]; j--; }
+            cell_items[j + 1] = v;
+        }
+    }
+}
+
+// K10: grid-windowed search (GetFeaturesInArea + best/second-best scan + accept rule) for one query under a
+// given view of the claims: keypoint idx is unavailable iff owner[idx] < q.
+struct SearchCtx {
+    uvip_search_params sp;
+    const float *qu, *qv, *qr; const int32_t *qminL, *qmaxL; const uint8_t* qdesc;
+    const float *kx, *ky; const int32_t* octave; const uint8_t* kdesc;
+    const int32_t *cell_start, *cell_items;
+};
+
+__device__ __forceinline__ int hamming256(const uint4& u, const uint4& v, const uint8_t* __restrict__ row)
+{
+    const uint4 x = __ldg(reinterpret_cast<const uint4*>(row)), y = __ldg(reinterpret_cast<const uint4*>(row) + 1);
+    return __popc(u.x ^ x.x) + __popc(u.y ^ x.y) + __popc(u.z ^ x.z) + __popc(u.w ^ x.w) +
+           __popc(v.x ^ y.x) + __popc(v.y ^ y.y) + __popc(v.z ^ y.z) + __popc(v.w ^ y.w);
+}
+
+__device__ int search_one(const SearchCtx& c, int q, const int* __restrict__ owner)
+{
+    const uvip_search_params& sp = c.sp;
+    const float x = c.qu[q], y = c.qv[q], r = c.qr[q];
+    const int minL = c.qminL[q], maxL = c.qmaxL[q];
+    // FrameKTL::GetFeaturesInArea, src/FrameKTL.cc:359-386 (float ops rounded one by one, no FMA)
+    int cx0 = (int)floorf(__fmul_rn(__fsub_rn(__fsub_rn(x, sp.min_x), r), sp.inv_w)); cx0 = max(0, cx0);
+    if (cx0 >= sp.cols) return -1;
+    int cx1 = (int)ceilf(__fmul_rn(__fadd_rn(__fsub_rn(x, sp.min_x), r), sp.inv_w)); cx1 = min(sp.cols - 1, cx1);
+    if (cx1 < 0) return -1;
+    int cy0 = (int)floorf(__fmul_rn(__fsub_rn(__fsub_rn(y, sp.min_y), r), sp.inv_h)); cy0 = max(0, cy0);
+    if (cy0 >= sp.rows) return -1;
+    int cy1 = (int)ceilf(__fmul_rn(__fadd_rn(__fsub_rn(y, sp.min_y), r), sp.inv_h)); cy1 = min(sp.rows - 1, cy1);
+    if (cy1 < 0) return -1;
+    const bool check = !(minL == -1 && maxL == -1);
+    const bool same = check && (minL == maxL);
+    const uint4 u = __ldg(reinterpret_cast<const uint4*>(c.qdesc + (size_t)q * 32));
+    const uint4 v = __ldg(reinterpret_cast<const uint4*>(c.qdesc + (size_t)q * 32) + 1);
+    int bestDist = sp.mode == 0 ? 256 : INT_MAX, bestDist2 = 256, bestLevel = -1, bestLevel2 = -1, bestIdx = -1;
+    for (int ix = cx0; ix <= cx1; ix++)
+        for (int iy = cy0; iy <= cy1; iy++) {
+            const int cell = ix * sp.rows + iy;
+            const int e = c.cell_start[cell + 1];
+            for (int j = c.cell_start[cell]; j < e; j++) {
+                const int id = c.cell_items[j];
+                const int oct = c.octave[id];
+                if (check) {
+                    if (same) { if (oct != minL) continue; }
+                    else if (oct < minL || oct > maxL) continue;
+                }
+                if (fabsf(__fsub_rn(c.kx[id], x)) > r || fabsf(__fsub_rn(c.ky[id], y)) > r) continue;
+                if (owner[id] < q) continue;                       // F.mvpMapPoints[idx] already set (:91 / :1689)
+                const int dist = hamming256(u, v, c.kdesc + (size_t)id * 32);
+                if (sp.mode == 0) {                                // src/ORBmatcher.cc:98-111
+                    if (dist < bestDist) { bestDist2 = bestDist; bestDist = dist; bestLevel2 = bestLevel; bestLevel = oct; bestIdx = id; }
+                    else if (dist < bestDist2) { bestLevel2 = oct; bestDist2 = dist; }
+                } else if (dist < bestDist) { bestDist = dist; bestIdx = id; }   // :1697-1701
+            }
+        }
+    if (bestIdx < 0 || bestDist > sp.th_dist) return -1;
+    if (sp.mode == 0 && bestLevel == bestLevel2 && (float)bestDist > __fmul_rn(sp.ratio, (float)bestDist2)) return -1;   // :116-117
+    return bestIdx;
+}
+
+// The reference loop is sequential: a query skips keypoints claimed by EARLIER queries.  Here every query
+// runs in parallel against the claims of the previous round (owner[idx] = lowest query index that claimed idx)
+// and rounds repeat until the claim table is a fixed point; by induction over the query index the fixed point
+// is exactly the sequential result ("claims").
+__global__ void __launch_bounds__(1024)
+k_search_window(SearchCtx c, int nq, int nk, int32_t* __restrict__ taken, int32_t* __restrict__ match,
+                int* __restrict__ ownerA, int* __restrict__ ownerB, int* __restrict__ out_counts)
+{
+    __shared__ int s_changed, s_n;
+    int* prev = ownerA; int* cur = ownerB;
+    for (int i = threadIdx.x; i < nk; i += blockDim.x) prev[i] = (taken[i] != -1) ? -2 : INT_MAX;
+    __syncthreads();
+    int rounds = 0;
+    for (;;) {
+        for (int i = threadIdx.x; i < nk; i += blockDim.x) cur[i] = (taken[i] != -1) ? -2 : INT_MAX;
+        if (threadIdx.x == 0) s_changed = 0;
+        __syncthreads();
+        for (int q = threadIdx.x; q < nq; q += blockDim.x) {
+            const int r = search_one(c, q, prev);
+            match[q] = r;
+            if (r >= 0) atomicMin(&cur[r], q);
+        }
+        __syncthreads();
+        int ch = 0;
+        for (int i = threadIdx.x; i < nk; i += blockDim.x) ch |= (cur[i] != prev[i]);
+        if (ch) s_changed = 1;
+        __syncthreads();
+        rounds++;
+        const int changed = s_changed;
+        int* tmp = prev; prev = cur; cur = tmp;
+        __syncthreads();
+        if (!changed) break;
+    }
+    if (threadIdx.x == 0) s_n = 0;
+    __syncthreads();
+    int n = 0;
+    for (int i = threadIdx.x; i < nk; i += blockDim.x) {
+        const int o = prev[i];
+        if (o >= 0 && o != INT_MAX) { taken[i] = o; n++; }
+    }
+    if (n) atomicAdd(&s_n, n);
+    __syncthreads();
+    if (threadIdx.x == 0) { out_counts[0] = s_n; out_counts[1] = rounds; }
+}
+
+// popc-pipe microbenchmark (roofline denominator for K9): 8 independent popc chains per thread
+__global__ void k_popc_peak(int iters, uint32_t seed, uint32_t* __restrict__ out)
+{
+    uint32_t v0 = seed ^ threadIdx.x, v1 = v0 * 3u, v2 = v0 * 5u, v3 = v0 * 7u, v4 = v0 * 11u, v5 = v0 * 13u, v6 = v0 * 17u, v7 = v0 * 19u;
+    uint32_t s0 = 0, s1 = 0, s2 = 0, s3 = 0, s4 = 0, s5 = 0, s6 = 0, s7 = 0;
+#pragma unroll 4
+    for (int i = 0; i < iters; i++) {
+        s0 += __popc(v0 ^ i); s1 += __popc(v1 ^ i); s2 += __popc(v2 ^ i); s3 += __popc(v3 ^ i);
+        s4 += __popc(v4 ^ i); s5 += __popc(v5 ^ i); s6 += __popc(v6 ^ i); s7 += __popc(v7 ^ i);
+    }
+    out[blockIdx.x * blockDim.x + threadIdx.x] = s0 + s1 + s2 + s3 + s4 + s5 + s6 + s7;
+}
+
+}  // namespace uvip
+
+// =====================================================================================================
+// C ABI
+// =====================================================================================================
+using namespace uvip;
+
+struct uvip_matcher {
+    int device = 0;
+    cudaStream_t stream = nullptr;
+    DevBuf q, t, idx, dist, misc, misc2, misc3, misc4;
+    long long launches = 0;
+    std::mutex mu;
+};
+
+extern "C" {
+
+int uvip_abi_version(void) { return UVIP_ABI_VERSION; }
+const char* uvip_last_error(void) { return g_err; }
+int uvip_device_count(void) { int n = 0; if (cudaGetDeviceCount(&n) != cudaSuccess) return 0; return n; }
+float uvip_radius_by_viewing_cos(float view_cos) { return ((double)view_cos > 0.998) ? 2.5f : 4.0f; }
+
+int uvip_matcher_create(int device, uvip_matcher** out)
+{
+    UVIP_CHECK_ARG(out != nullptr);
+    *out = nullptr;
+    int ndev = 0;
+    if (cudaGetDeviceCount(&ndev) != cudaSuccess || ndev == 0) {
+        set_last_error("no CUDA device available; libuvip_orb has no CPU fallback");
+        return UVIP_ERR_NO_DEVICE;
+    }
+    UVIP_CHECK_ARG(device >= 0 && device < ndev);
+    DeviceGuard g(device);
+    uvip_matcher* m = new uvip_matcher();
+    m->device = device;
+    cudaError_t e = cudaStreamCreateWithFlags(&m->stream, cudaStreamNonBlocking);
+    if (e != cudaSuccess) { set_last_error("cudaStreamCreate -> %s", cudaGetErrorString(e)); delete m; return UVIP_ERR_CUDA; }
+    *out = m;
+    return UVIP_OK;
+}
+
+int uvip_matcher_destroy(uvip_matcher* m)
+{
+    if (!m) return UVIP_OK;
+    DeviceGuard g(m->device);
+    cudaStreamSynchronize(m->stream);
+    m->q.release(); m->t.release(); m->idx.release(); m->dist.release();
+    m->misc.release(); m->misc2.release(); m->misc3.release(); m->misc4.release();
+    cudaStreamDestroy(m->stream);
+    delete m;
+    return UVIP_OK;
+}
+
+long long uvip_matcher_launch_count(const uvip_matcher* m) { return m ? m->launches : 0; }
+
+static int launch_knn2(uvip_matcher* m, const uint8_t* d_q, const int32_t* d_nq, size_t q_pitch,
+                       const uint8_t* d_t, const int32_t* d_nt, size_t t_pitch, int npairs, int max_nq,
+                       int nq_fixed, int nt_fixed, int idx_base, int32_t* d_idx2, int32_t* d_dist2, size_t res_pitch,
+                       cudaStream_t st)
+{
+    UVIP_CHECK_ARG(((uintptr_t)d_q & 15) == 0 && ((uintptr_t)d_t & 15) == 0 && (q_pitch & 15) == 0 && (t_pitch & 15) == 0);
+    UVIP_CHECK_ARG(((uintptr_t)d_idx2 & 7) == 0 && ((uintptr_t)d_dist2 & 7) == 0);
+    if (npairs <= 0 || max_nq <= 0) return UVIP_OK;
+    dim3 grid(div_up(max_nq, KNN_THREADS), npairs);
+    k_knn2<<<grid, KNN_THREADS, 0, st>>>(d_q, d_nq, q_pitch, d_t, d_nt, t_pitch, nq_fixed, nt_fixed, idx_base,
+                                          d_idx2, d_dist2, res_pitch);
+    m->launches++;
+    UVIP_CUDA(cudaGetLastError());
+    return UVIP_OK;
+}
+
+int uvip_knn2_device(uvip_matcher* m, const uint8_t* d_q, int nq, const uint8_t* d_t, int nt, int idx_base,
+                     int32_t* d_idx2, int32_t* d_dist2, void* stream)
+{
+    UVIP_CHECK_ARG(m && nq >= 0 && nt >= 0);
+    UVIP_CHECK_ARG(nq == 0 || (d_q && d_idx2 && d_dist2));
+    UVIP_CHECK_ARG(nt == 0 || d_t);
+    DeviceGuard g(m->device);
+    cudaStream_t st = stream ? (cudaStream_t)stream : m->stream;
+    return launch_knn2(m, d_q, nullptr, 0, d_t ? d_t : d_q, nullptr, 0, 1, nq, nq, nt, idx_base, d_idx2, d_dist2, 0, st);
+}
+
+int uvip_knn2_batch_device(uvip_matcher* m, const uint8_t* d_q, const int32_t* d_nq, size_t q_pitch,
+                           const uint8_t* d_t, const int32_t* d_nt, size_t t_pitch, int npairs, int max_nq,
+                           int32_t* d_idx2, int32_t* d_dist2, size_t res_pitch, void* stream)
+{
+    UVIP_CHECK_ARG(m && d_q && d_t && d_nq && d_nt && d_idx2 && d_dist2 && npairs >= 0 && max_nq >= 0);
+    UVIP_CHECK_ARG(res_pitch >= (size_t)max_nq);
+    DeviceGuard g(m->device);
+    cudaStream_t st = stream ? (cudaStream_t)stream : m->stream;
+    return launch_knn2(m, d_q, d_nq, q_pitch, d_t, d_nt, t_pitch, npairs, max_nq, 0, 0, 0, d_idx2, d_dist2, res_pitch, st);
+}
+
+int uvip_knn2(uvip_matcher* m, const uint8_t* q, int nq, const uint8_t* t, int nt, int32_t* idx2, int32_t* dist2)
+{
+    UVIP_CHECK_ARG(m && nq >= 0 && nt >= 0);
+    if (nq == 0) return UVIP_OK;
+    UVIP_CHECK_ARG(q && idx2 && dist2 && (nt == 0 || t));
+    std::lock_guard<std::mutex> lk(m->mu);
+    DeviceGuard g(m->device);
+    int rc;
+    if ((rc = m->q.reserve((size_t)nq * 32))) return rc;
+    if ((rc = m->t.reserve((size_t)(nt > 0 ? nt : 1) * 32))) return rc;
+    if ((rc = m->idx.reserve((size_t)nq * 8))) return rc;
+    if ((rc = m->dist.reserve((size_t)nq * 8))) return rc;
+    UVIP_CUDA(cudaMemcpyAsync(m->q.p, q, (size_t)nq * 32, cudaMemcpyHostToDevice, m->stream));
+    if (nt) UVIP_CUDA(cudaMemcpyAsync(m->t.p, t, (size_t)nt * 32, cudaMemcpyHostToDevice, m->stream));
+    rc = launch_knn2(m, m->q.as<uint8_t>(), nullptr, 0, m->t.as<uint8_t>(), nullptr, 0, 1, nq, nq, nt, 0,
+                     m->idx.as<int32_t>(), m->dist.as<int32_t>(), 0, m->stream);
+    if (rc) return rc;
+    UVIP_CUDA(cudaMemcpyAsync(idx2, m->idx.p, (size_t)nq * 8, cudaMemcpyDeviceToHost, m->stream));
+    UVIP_CUDA(cudaMemcpyAsync(dist2, m->dist.p, (size_t)nq * 8, cudaMemcpyDeviceToHost, m->stream));
+    UVIP_CUDA(cudaStreamSynchronize(m->stream));
+    return UVIP_OK;
+}
+
+int uvip_knn2_merge_device(uvip_matcher* m, const int32_t* d_idx_parts, const int32_t* d_dist_parts, int nparts,
+                           size_t part_stride, int nq, int32_t* d_idx2, int32_t* d_dist2, void* stream)
+{
+    UVIP_CHECK_ARG(m && d_idx_parts && d_dist_parts && d_idx2 && d_dist2 && nparts >= 1 && nq >= 0);
+    UVIP_CHECK_ARG((part_stride & 1) == 0);
+    if (nq == 0) return UVIP_OK;
+    DeviceGuard g(m->device);
+    cudaStream_t st = stream ? (cudaStream_t)stream : m->stream;
+    k_knn2_merge<<<div_up(nq, 256), 256, 0, st>>>(d_idx_parts, d_dist_parts, nparts, part_stride, nq, d_idx2, d_dist2);
+    m->launches++;
+    UVIP_CUDA(cudaGetLastError());
+    return UVIP_OK;
+}
+
+int uvip_descriptor_distance(uvip_matcher* m, const uint8_t* a, const uint8_t* b, int n, int32_t* out)
+{
+    UVIP_CHECK_ARG(m && n >= 0);
+    if (n == 0) return UVIP_OK;
+    UVIP_CHECK_ARG(a && b && out);
+    std::lock_guard<std::mutex> lk(m->mu);
+    DeviceGuard g(m->device);
+    int rc;
+    if ((rc = m->q.reserve((size_t)n * 32))) return rc;
+    if ((rc = m->t.reserve((size_t)n * 32))) return rc;
+    if ((rc = m->idx.reserve((size_t)n * 4))) return rc;
+    UVIP_CUDA(cudaMemcpyAsync(m->q.p, a, (size_t)n * 32, cudaMemcpyHostToDevice, m->stream));
+    UVIP_CUDA(cudaMemcpyAsync(m->t.p, b, (size_t)n * 32, cudaMemcpyHostToDevice, m->stream));
+    k_descriptor_distance<<<div_up(n, 256), 256, 0, m->stream>>>(m->q.as<uint8_t>(), m->t.as<uint8_t>(), n, m->idx.as<int32_t>());
+    m->launches++;
+    UVIP_CUDA(cudaGetLastError());
+    UVIP_CUDA(cudaMemcpyAsync(out, m->idx.p, (size_t)n * 4, cudaMemcpyDeviceToHost, m->stream));
+    UVIP_CUDA(cudaStreamSynchronize(m->stream));
+    return UVIP_OK;
+}
+
+int uvip_ratio_filter(uvip_matcher* m, const int32_t* idx2, const int32_t* dist2, int nq, double ratio,
+                      int32_t* match, int* nmatches)
+{
+    UVIP_CHECK_ARG(m && nq >= 0);
+    if (nmatches) *nmatches = 0;
+    if (nq == 0) return UVIP_OK;
+    UVIP_CHECK_ARG(idx2 && dist2 && match);
+    std::lock_guard<std::mutex> lk(m->mu);
+    DeviceGuard g(m->device);
+    int rc;
+    if ((rc = m->idx.reserve((size_t)nq * 8))) return rc;
+    if ((rc = m->dist.reserve((size_t)nq * 8))) return rc;
+    if ((rc = m->misc.reserve((size_t)nq * 4 + 16))) return rc;
+    int32_t* d_match = m->misc.as<int32_t>() + 4;
+    int* d_n = m->misc.as<int>();
+    UVIP_CUDA(cudaMemcpyAsync(m->idx.p, idx2, (size_t)nq * 8, cudaMemcpyHostToDevice, m->stream));
+    UVIP_CUDA(cudaMemcpyAsync(m->dist.p, dist2, (size_t)nq * 8, cudaMemcpyHostToDevice, m->stream));
+    UVIP_CUDA(cudaMemsetAsync(d_n, 0, 4, m->stream));
+    k_ratio_filter<<<div_up(nq, 256), 256, 0, m->stream>>>(m->idx.as<int32_t>(), m->dist.as<int32_t>(), nq, ratio, d_match, d_n);
+    m->launches++;
+    UVIP_CUDA(cudaGetLastError());
+    int n = 0;
+    UVIP_CUDA(cudaMemcpyAsync(match, d_match, (size_t)nq * 4, cudaMemcpyDeviceToHost, m->stream));
+    UVIP_CUDA(cudaMemcpyAsync(&n, d_n, 4, cudaMemcpyDeviceToHost, m->stream));
+    UVIP_CUDA(cudaStreamSynchronize(m->stream));
+    if (nmatches) *nmatches = n;
+    return UVIP_OK;
+}
+
+int uvip_rot_hist_filter(uvip_matcher* m, int32_t* match, int n, const float* angle_a, const float* angle_b, int* nkept)
+{
+    UVIP_CHECK_ARG(m && n >= 0);
+    if (nkept) *nkept = 0;
+    if (n == 0) return UVIP_OK;
+    UVIP_CHECK_ARG(match && angle_a && angle_b);
+    int nb = 0;
+    for (int i = 0; i < n; i++) if (match[i] >= nb) nb = match[i] + 1;
+    std::lock_guard<std::mutex> lk(m->mu);
+    DeviceGuard g(m->device);
+    int rc;
+    if ((rc = m->misc.reserve((size_t)n * 4 + 16))) return rc;
+    if ((rc = m->misc2.reserve((size_t)n * 4))) return rc;
+    if ((rc = m->misc3.reserve((size_t)(nb > 0 ? nb : 1) * 4))) return rc;
+    int32_t* d_match = m->misc.as<int32_t>() + 4;
+    int* d_n = m->misc.as<int>();
+    UVIP_CUDA(cudaMemcpyAsync(d_match, match, (size_t)n * 4, cudaMemcpyHostToDevice, m->stream));
+    UVIP_CUDA(cudaMemcpyAsync(m->misc2.p, angle_a, (size_t)n * 4, cudaMemcpyHostToDevice, m->stream));
+    if (nb) UVIP_CUDA(cudaMemcpyAsync(m->misc3.p, angle_b, (size_t)nb * 4, cudaMemcpyHostToDevice, m->stream));
+    k_rot_hist<<<1, 256, 0, m->stream>>>(d_match, n, m->misc2.as<float>(), m->misc3.as<float>(), d_n);
+    m->launches++;
+    UVIP_CUDA(cudaGetLastError());
+    int kept = 0;
+    UVIP_CUDA(cudaMemcpyAsync(match, d_match, (size_t)n * 4, cudaMemcpyDeviceToHost, m->stream));
+    UVIP_CUDA(cudaMemcpyAsync(&kept, d_n, 4, cudaMemcpyDeviceToHost, m->stream));
+    UVIP_CUDA(cudaStreamSynchronize(m->stream));
+    if (nkept) *nkept = kept;
+    return UVIP_OK;
+}
+
+int uvip_grid_build(uvip_matcher* m, const float* kx, const float* ky, int n,
+                    float min_x, float min_y, float inv_w, float inv_h, int cols, int rows,
+                    int32_t* cell_start, int32_t* cell_items)
+{
+    UVIP_CHECK_ARG(m && n >= 0 && cols > 0 && rows > 0 && cell_start);
+    const int ncell = cols * rows;
+    UVIP_CHECK_ARG((size_t)(2 * ncell + 1) * 4 <= 200 * 1024);
+    UVIP_CHECK_ARG(n == 0 || (kx && ky && cell_items));
+    std::lock_guard<std::mutex> lk(m->mu);
+    DeviceGuard g(m->device);
+    int rc;
+    const size_t nn = n > 0 ? n : 1;
+    if ((rc = m->misc.reserve(nn * 4))) return rc;
+    if ((rc = m->misc2.reserve(nn * 4))) return rc;
+    if ((rc = m->misc3.reserve((size_t)(ncell + 1) * 4))) return rc;
+    if ((rc = m->misc4.reserve(nn * 8))) return rc;
+    if (n) {
+        UVIP_CUDA(cudaMemcpyAsync(m->misc.p, kx, (size_t)n * 4, cudaMemcpyHostToDevice, m->stream));
+        UVIP_CUDA(cudaMemcpyAsync(m->misc2.p, ky, (size_t)n * 4, cudaMemcpyHostToDevice, m->stream));
+    }
+    const size_t smem = (size_t)(2 * ncell + 1) * 4;
+    UVIP_CUDA(cudaFuncSetAttribute(k_grid_build, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+    int32_t* d_items = m->misc4.as<int32_t>();
+    int32_t* d_cellof = d_items + nn;
+    k_grid_build<<<1, 1024, smem, m->stream>>>(m->misc.as<float>(), m->misc2.as<float>(), n, min_x, min_y, inv_w, inv_h,
+                                                cols, rows, m->misc3.as<int32_t>(), d_items, d_cellof);
+    m->launches++;
+    UVIP_CUDA(cudaGetLastError());
+    UVIP_CUDA(cudaMemcpyAsync(cell_start, m->misc3.p, (size_t)(ncell + 1) * 4, cudaMemcpyDeviceToHost, m->stream));
+    UVIP_CUDA(cudaStreamSynchronize(m->stream));
+    const int nitems = cell_start[ncell];
+    if (nitems) UVIP_CUDA(cudaMemcpy(cell_items, d_items, (size_t)nitems * 4, cudaMemcpyDeviceToHost));
+    return UVIP_OK;
+}
+
+int uvip_search_window(uvip_matcher* m, const uvip_search_params* sp,
+                       const float* qu, const float* qv, const float* qr, const int32_t* qmin_level,
+                       const int32_t* qmax_level, const uint8_t* qdesc, int nq,
+                       const float* kx, const float* ky, const int32_t* octave, const uint8_t* kdesc, int nk,
+                       const int32_t* cell_start, const int32_t* cell_items,
+                       int32_t* taken, int32_t* match, int* nmatches)
+{
+    UVIP_CHECK_ARG(m && sp && nq >= 0 && nk >= 0 && sp->cols > 0 && sp->rows > 0);
+    if (nmatches) *nmatches = 0;
+    if (nq == 0) return UVIP_OK;
+    UVIP_CHECK_ARG(qu && qv && qr && qmin_level && qmax_level && qdesc && match && cell_start);
+    UVIP_CHECK_ARG(nk == 0 || (kx && ky && octave && kdesc && taken && cell_items));
+    std::lock_guard<std::mutex> lk(m->mu);
+    DeviceGuard g(m->device);
+    const int ncell = sp->cols * sp->rows;
+    const int nitems = cell_start[ncell];
+    // one staging buffer, 32-byte aligned sections
+    size_t off = 0;
+    auto sect = [&](size_t bytes) { size_t o = off; off = align_up(off + bytes, 32); return o; };
+    const size_t nkk = nk > 0 ? nk : 1;
+    const size_t o_qu = sect((size_t)nq * 4), o_qv = sect((size_t)nq * 4), o_qr = sect((size_t)nq * 4);
+    const size_t o_qmin = sect((size_t)nq * 4), o_qmax = sect((size_t)nq * 4), o_qd = sect((size_t)nq * 32);
+    const size_t o_kx = sect(nkk * 4), o_ky = sect(nkk * 4), o_oct = sect(nkk * 4), o_kd = sect(nkk * 32);
+    const size_t o_cs = sect((size_t)(ncell + 1) * 4), o_ci = sect((size_t)(nitems > 0 ? nitems : 1) * 4);
+    const size_t o_taken = sect(nkk * 4), o_match = sect((size_t)nq * 4), o_oa = sect(nkk * 4), o_ob = sect(nkk * 4);
+    const size_t o_cnt = sect(16);
+    int rc;
+    if ((rc = m->misc.reserve(off))) return rc;
+    uint8_t* base = m->misc.as<uint8_t>();
+    cudaStream_t st = m->stream;
+#define UP(o, src, bytes) if ((bytes) > 0) UVIP_CUDA(cudaMemcpyAsync(base + (o), (src), (bytes), cudaMemcpyHostToDevice, st))
+    UP(o_qu, qu, (size_t)nq * 4); UP(o_qv, qv, (size_t)nq * 4); UP(o_qr, qr, (size_t)nq * 4);
+    UP(o_qmin, qmin_level, (size_t)nq * 4); UP(o_qmax, qmax_level, (size_t)nq * 4); UP(o_qd, qdesc, (size_t)nq * 32);
+    UP(o_kx, kx, (size_t)nk * 4); UP(o_ky, ky, (size_t)nk * 4); UP(o_oct, octave, (size_t)nk * 4); UP(o_kd, kdesc, (size_t)nk * 32);
+    UP(o_cs, cell_start, (size_t)(ncell + 1) * 4); UP(o_ci, cell_items, (size_t)nitems * 4);
+    UP(o_taken, taken, (size_t)nk * 4);
+#undef UP
+    SearchCtx c;
+    c.sp = *sp;
+    c.qu = (const float*)(base + o_qu); c.qv = (const float*)(base + o_qv); c.qr = (const float*)(base + o_qr);
+    c.qminL = (const int32_t*)(base + o_qmin); c.qmaxL = (const int32_t*)(base + o_qmax); c.qdesc = base + o_qd;
+    c.kx = (const float*)(base + o_kx); c.ky = (const float*)(base + o_ky); c.octave = (const int32_t*)(base + o_oct);
+    c.kdesc = base + o_kd; c.cell_start = (const int32_t*)(base + o_cs); c.cell_items = (const int32_t*)(base + o_ci);
+    k_search_window<<<1, 1024, 0, st>>>(c, nq, nk, (int32_t*)(base + o_taken), (int32_t*)(base + o_match),
+                                         (int*)(base + o_oa), (int*)(base + o_ob), (int*)(base + o_cnt));
+    m->launches++;
+    UVIP_CUDA(cudaGetLastError());
+    int counts[2] = {0, 0};
+    UVIP_CUDA(cudaMemcpyAsync(match, base + o_match, (size_t)nq * 4, cudaMemcpyDeviceToHost, st));
+    if (nk) UVIP_CUDA(cudaMemcpyAsync(taken, base + o_taken, (size_t)nk * 4, cudaMemcpyDeviceToHost, st));
+    UVIP_CUDA(cudaMemcpyAsync(counts, base + o_cnt, 8, cudaMemcpyDeviceToHost, st));
+    UVIP_CUDA(cudaStreamSynchronize(st));
+    if (nmatches) *nmatches = counts[0];
+    return UVIP_OK;
+}
+
+/* measurement utility (not part of the reference surface): sustained __popc throughput of `device`, in popc/s */
+int uvip_popc_peak(int device, int iters, double* popc_per_s)
+{
+    UVIP_CHECK_ARG(popc_per_s && iters > 0);
+    int ndev = 0;
+    if (cudaGetDeviceCount(&ndev) != cudaSuccess || device < 0 || device >= ndev) return UVIP_ERR_NO_DEVICE;
+    DeviceGuard g(device);
+    cudaDeviceProp prop;
+    UVIP_CUDA(cudaGetDeviceProperties(&prop, device));
+    const int blocks = prop.multiProcessorCount * 8, threads = 256;
+    uint32_t* d_out = nullptr;
+    UVIP_CUDA(cudaMalloc(&d_out, (size_t)blocks * threads * 4));
+    cudaEvent_t e0, e1;
+    UVIP_CUDA(cudaEventCreate(&e0)); UVIP_CUDA(cudaEventCreate(&e1));
+    k_popc_peak<<<blocks, threads>>>(iters, 12345u, d_out);
+    UVIP_CUDA(cudaDeviceSynchronize());
+    float best = 1e30f;
+    for (int r = 0; r < 5; r++) {
+        UVIP_CUDA(cudaEventRecord(e0));
+        k_popc_peak<<<blocks, threads>>>(iters, 12345u + r, d_out);
+        UVIP_CUDA(cudaEventRecord(e1));
+        UVIP_CUDA(cudaEventSynchronize(e1));
+        float ms = 0; UVIP_CUDA(cudaEventElapsedTime(&ms, e0, e1));
+        if (ms < best) best = ms;
+    }
+    cudaEventDestroy(e0); cudaEventDestroy(e1); cudaFree(d_out);
+    *popc_per_s = (double)blocks * threads * 8.0 * iters / (best * 1e-3);
+    return UVIP_OK;
+}
+
+}  // extern "C"

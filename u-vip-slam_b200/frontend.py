@@ -1,0 +1,221 @@
+"""Host-side mirror of the two reference classes over the C-ABI, used by tests/, bench.py and smoke().
+
+    ORBextractor  <->  USLAM::ORBextractor  (include/ORBextractor.h:45-94 of the reference)
+    ORBmatcher    <->  USLAM::ORBmatcher    (include/ORBmatcher.h:41-94), descriptor path only
+
+Same constructor arguments, same operator() argument meaning, same error behaviour (empty image -> outputs
+untouched).  numpy arrays stand in for cv::Mat / std::vector<cv::KeyPoint> / Eigen::MatrixXi (Fortran-ordered
+int32).  The C++ shim with the literal reference signatures is host/ORBextractor.h, host/ORBmatcher.h."""
+import ctypes as C
+
+import numpy as np
+
+from . import capi
+from .capi import KP_DTYPE, ExtractorParams, SearchParams, check, lib, ptr
+
+
+class ORBextractor:
+    HARRIS_SCORE = 0
+    FAST_SCORE = 1
+
+    def __init__(self, nfeatures=1000, scaleFactor=1.2, nlevels=8, scoreType=0, fastTh=7,
+                 device=0, max_width=1280, max_height=1024, max_batch=1, retry_th=0, cell=0):
+        self.params = ExtractorParams(nfeatures, scaleFactor, nlevels, scoreType, fastTh, retry_th, cell, device,
+                                      max_width, max_height, max_batch)
+        self.h = C.c_void_p()
+        check(lib().uvip_extractor_create(C.byref(self.params), C.byref(self.h)))
+        self.nfeatures, self.nlevels = nfeatures, nlevels
+
+    def close(self):
+        if getattr(self, 'h', None) is not None and self.h:
+            lib().uvip_extractor_destroy(self.h)
+            self.h = C.c_void_p()
+
+    def __del__(self):
+        try:
+            self.close()
+        except Exception:
+            pass
+
+    def GetLevels(self):
+        return lib().uvip_extractor_levels(self.h)
+
+    def GetScaleFactor(self):
+        return lib().uvip_extractor_scale_factor(self.h)
+
+    def tables(self):
+        n = self.nlevels
+        sc = np.zeros(n, np.float32); inv = np.zeros(n, np.float32)
+        quota = np.zeros(n, np.int32); umax = np.zeros(16, np.int32)
+        check(lib().uvip_extractor_tables(self.h, ptr(sc), ptr(inv), ptr(quota), ptr(umax)))
+        return sc, inv, quota, umax
+
+    def __call__(self, image, mask=None, keypoints=None, grid_2d=None, min_px_dist=1, FullDetect=True,
+                 num_featsneeded=0, cap=None):
+        """operator()(image, mask, keypoints, descriptors, grid_2d, min_px_dist, FullDetect, num_featsneeded).
+        Returns (keypoints, descriptors); an empty image returns the inputs untouched: (keypoints, None)."""
+        if image is None or image.size == 0:
+            return keypoints, None
+        if image.dtype != np.uint8 or image.ndim != 2:
+            raise AssertionError('image.type() == CV_8UC1')          # src/ORBextractor.cc:856
+        if image.strides[1] != 1:
+            image = np.ascontiguousarray(image)
+        H, W = image.shape
+        n_in = 0 if keypoints is None else len(keypoints)
+        if cap is None:
+            cap = self.nfeatures + 8 * self.nlevels + 64 + n_in
+        kps = np.zeros(cap, KP_DTYPE)
+        if n_in:
+            kps[:n_in] = keypoints
+        desc = np.zeros((cap, 32), np.uint8)
+        n = C.c_int(n_in)
+        gr = gc = 0
+        if grid_2d is not None:
+            assert grid_2d.dtype == np.int32 and grid_2d.flags.f_contiguous, 'Eigen::MatrixXi is column-major int32'
+            gr, gc = grid_2d.shape
+        check(lib().uvip_extract(self.h, ptr(image), W, H, image.strides[0], ptr(kps), C.byref(n), cap, ptr(desc),
+                                 ptr(grid_2d), gr, gc, int(min_px_dist), int(bool(FullDetect)), int(num_featsneeded)))
+        return kps[:n.value].copy(), desc[:n.value].copy()
+
+    def extract_batch(self, frames, cap=None):
+        frames = np.ascontiguousarray(frames, np.uint8)
+        nf, H, W = frames.shape
+        if cap is None:
+            cap = self.nfeatures + 8 * self.nlevels + 64
+        kps = np.zeros((nf, cap), KP_DTYPE); desc = np.zeros((nf, cap, 32), np.uint8); n = np.zeros(nf, np.int32)
+        check(lib().uvip_extract_batch(self.h, ptr(frames), nf, W, H, W, W * H, ptr(kps), ptr(n), cap, ptr(desc)))
+        return kps, n, desc
+
+    def extract_batch_device(self, d_frames, nframes, W, H, d_kps, d_n, cap, d_desc, stream=0):
+        """all pointers are integers (device addresses, e.g. torch tensor.data_ptr()); asynchronous"""
+        check(lib().uvip_extract_batch_device(self.h, ptr(d_frames), nframes, W, H, W, W * H, ptr(d_kps), ptr(d_n), cap,
+                                              ptr(d_desc), C.c_void_p(stream) if stream else None))
+
+    def status(self):
+        check(lib().uvip_extractor_status(self.h))
+
+    def launch_count(self):
+        return int(lib().uvip_extractor_launch_count(self.h))
+
+    # ---- debug taps
+    def level(self, l, blurred=False, frame=0):
+        w = C.c_int(); h = C.c_int()
+        check(lib().uvip_get_pyramid_level(self.h, frame, l, int(blurred), None, 0, C.byref(w), C.byref(h)))
+        out = np.zeros((h.value, w.value), np.uint8)
+        check(lib().uvip_get_pyramid_level(self.h, frame, l, int(blurred), ptr(out), w.value, C.byref(w), C.byref(h)))
+        return out
+
+    def _list(self, fn, l, frame):
+        cap = 1 << 20
+        xs = np.zeros(cap, np.int32); ys = np.zeros(cap, np.int32); sc = np.zeros(cap, np.int32)
+        n = C.c_int()
+        check(fn(self.h, frame, l, ptr(xs), ptr(ys), ptr(sc), cap, C.byref(n)))
+        return xs[:n.value].copy(), ys[:n.value].copy(), sc[:n.value].copy()
+
+    def raw_corners(self, l, frame=0):
+        return self._list(lib().uvip_get_raw_corners, l, frame)
+
+    def level_keypoints(self, l, frame=0):
+        return self._list(lib().uvip_get_level_keypoints, l, frame)
+
+
+class ORBmatcher:
+    TH_HIGH = 100
+    TH_LOW = 50
+    HISTO_LENGTH = 30
+    FRAME_GRID_COLS = 64
+    FRAME_GRID_ROWS = 48
+
+    def __init__(self, nnratio=0.6, checkOri=True, device=0):
+        self.mfNNratio = float(nnratio)
+        self.mbCheckOrientation = bool(checkOri)
+        self.h = C.c_void_p()
+        check(lib().uvip_matcher_create(device, C.byref(self.h)))
+
+    def close(self):
+        if getattr(self, 'h', None) is not None and self.h:
+            lib().uvip_matcher_destroy(self.h)
+            self.h = C.c_void_p()
+
+    def __del__(self):
+        try:
+            self.close()
+        except Exception:
+            pass
+
+    def launch_count(self):
+        return int(lib().uvip_matcher_launch_count(self.h))
+
+    def DescriptorDistance(self, a, b):
+        """static int DescriptorDistance(const cv::Mat&, const cv::Mat&): one pair, or row-wise for 2-D inputs"""
+        a = np.ascontiguousarray(a, np.uint8).reshape(-1, 32); b = np.ascontiguousarray(b, np.uint8).reshape(-1, 32)
+        out = np.zeros(len(a), np.int32)
+        check(lib().uvip_descriptor_distance(self.h, ptr(a), ptr(b), len(a), ptr(out)))
+        return int(out[0]) if len(out) == 1 else out
+
+    def knn2(self, q, t):
+        q = np.ascontiguousarray(q, np.uint8).reshape(-1, 32); t = np.ascontiguousarray(t, np.uint8).reshape(-1, 32)
+        idx = np.zeros((len(q), 2), np.int32); dist = np.zeros((len(q), 2), np.int32)
+        check(lib().uvip_knn2(self.h, ptr(q), len(q), ptr(t), len(t), ptr(idx), ptr(dist)))
+        return idx, dist
+
+    def ratio_filter(self, idx, dist, ratio=None):
+        idx = np.ascontiguousarray(idx, np.int32); dist = np.ascontiguousarray(dist, np.int32)
+        m = np.zeros(len(idx), np.int32); n = C.c_int()
+        check(lib().uvip_ratio_filter(self.h, ptr(idx), ptr(dist), len(idx), float(self.mfNNratio if ratio is None else ratio),
+                                      ptr(m), C.byref(n)))
+        return m
+
+    def rot_hist_filter(self, match, angle_a, angle_b):
+        m = np.ascontiguousarray(match, np.int32).copy()
+        a = np.ascontiguousarray(angle_a, np.float32); b = np.ascontiguousarray(angle_b, np.float32)
+        n = C.c_int()
+        check(lib().uvip_rot_hist_filter(self.h, ptr(m), len(m), ptr(a), ptr(b), C.byref(n)))
+        return m
+
+    def ratioMatching(self, desc1, desc2, ratio, angles1=None, angles2=None):
+        """haloc::Utils::ratioMatching (include/utils.h:81-111) + optional rotation-consistency histogram"""
+        idx, dist = self.knn2(desc1, desc2)
+        m = self.ratio_filter(idx, dist, ratio)
+        if self.mbCheckOrientation and angles1 is not None:
+            m = self.rot_hist_filter(m, angles1, angles2)
+        return m
+
+    def grid_build(self, kx, ky, bounds, cols=FRAME_GRID_COLS, rows=FRAME_GRID_ROWS):
+        kx = np.ascontiguousarray(kx, np.float32); ky = np.ascontiguousarray(ky, np.float32)
+        minX, maxX, minY, maxY = bounds
+        inv_w = np.float32(cols) / np.float32(maxX - minX); inv_h = np.float32(rows) / np.float32(maxY - minY)
+        start = np.zeros(cols * rows + 1, np.int32); items = np.zeros(max(len(kx), 1), np.int32)
+        check(lib().uvip_grid_build(self.h, ptr(kx), ptr(ky), len(kx), float(minX), float(minY), float(inv_w), float(inv_h),
+                                    cols, rows, ptr(start), ptr(items)))
+        return dict(start=start, items=items[:start[-1]].copy(), minX=float(minX), minY=float(minY),
+                    inv_w=float(inv_w), inv_h=float(inv_h), cols=cols, rows=rows)
+
+    def search_window(self, mode, th_dist, qu, qv, qr, qminL, qmaxL, qdesc, kx, ky, octave, kdesc, grid, taken=None):
+        f32 = lambda a: np.ascontiguousarray(a, np.float32)
+        i32 = lambda a: np.ascontiguousarray(a, np.int32)
+        qu, qv, qr, kx, ky = f32(qu), f32(qv), f32(qr), f32(kx), f32(ky)
+        qminL, qmaxL, octave = i32(qminL), i32(qmaxL), i32(octave)
+        qdesc = np.ascontiguousarray(qdesc, np.uint8); kdesc = np.ascontiguousarray(kdesc, np.uint8)
+        nq, nk = len(qu), len(kx)
+        tk = np.full(nk, -1, np.int32) if taken is None else i32(taken).copy()
+        match = np.full(nq, -1, np.int32)
+        sp = SearchParams(mode, th_dist, self.mfNNratio, grid['minX'], grid['minY'], grid['inv_w'], grid['inv_h'],
+                          grid['cols'], grid['rows'])
+        n = C.c_int()
+        check(lib().uvip_search_window(self.h, C.byref(sp), ptr(qu), ptr(qv), ptr(qr), ptr(qminL), ptr(qmaxL), ptr(qdesc), nq,
+                                       ptr(kx), ptr(ky), ptr(octave), ptr(kdesc), nk, ptr(i32(grid['start'])),
+                                       ptr(i32(grid['items'])), ptr(tk), ptr(match), C.byref(n)))
+        return n.value, match, tk
+
+    def SearchByProjection(self, frame, map_points, th=1.0, taken=None):
+        """SearchByProjection(FrameKTL&, const vector<MapPoint*>&, float th) (src/ORBmatcher.cc:49-125) over flat arrays.
+        frame: dict(kx, ky, octave, kdesc, grid, scale_factors); map_points: dict(u, v, level, view_cos, desc)."""
+        sf = np.asarray(frame['scale_factors'], np.float32)
+        lvl = np.asarray(map_points['level'], np.int32)
+        r = np.array([lib().uvip_radius_by_viewing_cos(float(c)) for c in map_points['view_cos']], np.float32)
+        if th != 1.0:
+            r = (r * np.float32(th)).astype(np.float32)
+        r = (r * sf[lvl]).astype(np.float32)
+        return self.search_window(0, self.TH_HIGH, map_points['u'], map_points['v'], r, lvl - 1, lvl, map_points['desc'],
+                                  frame['kx'], frame['ky'], frame['octave'], frame['kdesc'], frame['grid'], taken)
