@@ -1,0 +1,338 @@
+#!/usr/bin/env python
+"""bench.py — ORB front-end throughput on B200 (BASELINE.json metric), one JSON line on stdout.
+
+A step = one pass of the hot path over one batch of synthetic frames: ORBextractor over `--batch` frames of
+752x480 at 1000 keypoints (8 levels, 1.2, FAST 20/7 — the shape the metric is quoted on) followed by brute-force
+Hamming kNN2 between consecutive frames' descriptors.  `value` is measured with inputs resident in HBM through the
+device-pointer C-ABI; `e2e` goes through the host-buffer C-ABI calls (pinned host memory, H2D + D2H inside the timed
+region).  N > 1: one process per GPU (torchrun), frames sharded, no data-path collective (weak scaling).
+
+    python bench.py [--gpus N] [--steps K] [--warmup W] [--impl reference]
+"""
+import argparse
+import json
+import os
+import subprocess
+import sys
+import threading
+import time
+
+ROOT = os.path.dirname(os.path.abspath(__file__))
+if ROOT not in sys.path:
+    sys.path.insert(0, ROOT)
+
+METRIC = 'ORB frames/s @752x480,1000kp; Hamming pairs/s; % of HBM/popc roofline'
+W, H, NFEAT, NLEVELS, SCALE, FAST_TH = 752, 480, 1000, 8, 1.2, 20
+B_FRAME_BYTES = 1177367          # 360 960 in + 756 407 pyramid out + 1000 x 60 B of keypoints/descriptors
+FALLBACK_HBM_GBS = 6650.0        # B200_PROFILING.md fallback when MEASURED_PEAKS.json is absent
+
+
+def parse():
+    ap = argparse.ArgumentParser()
+    ap.add_argument('--gpus', type=int, default=1)
+    ap.add_argument('--steps', type=int, default=20)
+    ap.add_argument('--warmup', type=int, default=3)
+    ap.add_argument('--impl', default='ours', choices=['ours', 'reference'])
+    ap.add_argument('--batch', type=int, default=256, help='frames per step and per GPU')
+    ap.add_argument('--ref-frames', type=int, default=0, help='frames per step of the reference arm (0 = 4 x cores)')
+    ap.add_argument('--no-extras', action='store_true', help='skip the Hamming-only and cpu_baseline legs')
+    return ap.parse_args()
+
+
+def make_frames(synth, n, seed0):
+    """n distinct synthetic EuRoC-shaped frames; generated in a few worker processes (numpy, ~50 ms each)"""
+    from concurrent.futures import ThreadPoolExecutor
+    import numpy as np
+    with ThreadPoolExecutor(max_workers=min(8, os.cpu_count() or 1)) as pool:
+        frames = list(pool.map(lambda i: synth.synth_frame(seed0 + i, W, H), range(n)))
+    return np.stack(frames)
+
+
+class ClockSampler:
+    """nvidia-smi clocks + throttle reasons sampled DURING the timed region (B200_PROFILING.md recipe)"""
+    Q = ('index,clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.hw_slowdown,'
+         'clocks_event_reasons.hw_thermal_slowdown,clocks_event_reasons.sw_thermal_slowdown,clocks_event_reasons.sw_power_cap')
+
+    def __init__(self, index):
+        self.index, self.proc, self.lines = index, None, []
+
+    def start(self):
+        try:
+            self.proc = subprocess.Popen(['nvidia-smi', '-i', str(self.index), '--query-gpu=' + self.Q, '--format=csv,noheader,nounits',
+                                          '-lms', '100'], stdout=subprocess.PIPE, stderr=subprocess.DEVNULL, text=True)
+            self.th = threading.Thread(target=self._read, daemon=True)
+            self.th.start()
+        except Exception:
+            self.proc = None
+
+    def _read(self):
+        for line in self.proc.stdout:
+            self.lines.append(line.strip())
+
+    def stop(self):
+        if not self.proc:
+            return {'sm_mhz': None, 'sm_max_mhz': None, 'reasons': ['nvidia-smi unavailable']}
+        self.proc.terminate()
+        try:
+            self.proc.wait(timeout=5)
+        except Exception:
+            self.proc.kill()
+        sm, mx, reasons = [], [], set()
+        for ln in self.lines:
+            p = [x.strip() for x in ln.split(',')]
+            if len(p) < 8:
+                continue
+            try:
+                sm.append(float(p[1])); mx.append(float(p[2]))
+            except ValueError:
+                continue
+            for name, v in zip(('hw_slowdown', 'hw_thermal_slowdown', 'sw_thermal_slowdown', 'sw_power_cap'), p[4:8]):
+                if v.lower().startswith('active'):
+                    reasons.add(name)
+        sm.sort()
+        return {'sm_mhz': sm[len(sm) // 2] if sm else None, 'sm_max_mhz': max(mx) if mx else None,
+                'reasons': sorted(reasons), 'samples': len(sm)}
+
+
+def hbm_peak():
+    try:
+        return float(json.load(open(os.path.join(ROOT, 'MEASURED_PEAKS.json')))['hbm_gbs']), 'measured'
+    except Exception:
+        return FALLBACK_HBM_GBS, 'fallback'
+
+
+def ncu_traffic():
+    """dram bytes per launch of the dominant kernel from the committed ncu --set full capture, if any"""
+    try:
+        return json.load(open(os.path.join(ROOT, 'profiles', 'roofline_traffic.json')))
+    except Exception:
+        return {}
+
+
+# ------------------------------------------------------------------------------------------------ reference arm
+def cpu_reference(frames, threads, want_knn=True):
+    """the reference's CPU path for one batch: oracle ORBextractor over all frames (OpenMP over frames) + brute-force
+    kNN2 between consecutive frames.  Returns seconds."""
+    import numpy as np
+    from oracle import oracle as O
+    t0 = time.perf_counter()
+    kps, n, desc = O.extract_batch(frames, NFEAT, SCALE, NLEVELS, FAST_TH, threads=threads)
+    if want_knn:
+        for f in range(len(frames) - 1):
+            O.knn2(desc[f, :n[f]], desc[f + 1, :n[f + 1]], threads=threads)
+    return time.perf_counter() - t0
+
+
+def run_reference(args):
+    rank = int(os.environ.get('RANK', '0'))
+    if rank != 0:
+        return 0
+    import __graft_entry__ as ge
+    pkg = ge.load_package()
+    from oracle import oracle as O
+    O.lib()
+    cores = os.cpu_count() or 1
+    nfr = args.ref_frames or max(8, 4 * cores)
+    frames = make_frames(pkg.synth, nfr, 1)
+    for _ in range(max(1, min(args.warmup, 1))):
+        cpu_reference(frames[:max(2, cores)], cores)
+    t = 0.0
+    for _ in range(args.steps):
+        t += cpu_reference(frames, cores)
+    fps = nfr * args.steps / t
+    line = {
+        'impl': 'reference', 'metric': METRIC, 'value': fps, 'unit': 'frames/s', 'n_gpus': args.gpus, 'steps': args.steps,
+        'warmup': args.warmup, 'ms_per_step': 1e3 * t / args.steps, 'higher_is_better': True, 'scaling': 'weak',
+        'vs_baseline': None, 'dtype': 'u8', 'data': 'synthetic',
+        'config': {'workload': 'ORBextractor 752x480 / 1000 kp / 8 levels / 1.2 / FAST 20-7 + brute-force Hamming kNN2 of consecutive '
+                               'frames (BASELINE config 1 shape, batched)', 'frames_per_step': nfr, 'keypoints': NFEAT},
+        'cpu_baseline': {'value': fps, 'unit': 'frames/s', 'cores': cores, 'kind': 'port',
+                         'sample': '%d frames per step, OpenMP over frames; the reference itself cannot be built here '
+                                   '(needs OpenCV 3.4 C++/ROS/Eigen), so this is the C oracle restating it' % nfr},
+        'e2e': {'value': fps, 'unit': 'frames/s', 'h2d_bytes_per_step': 0, 'd2h_bytes_per_step': 0},
+    }
+    print(json.dumps(line), flush=True)
+    return 0
+
+
+# ------------------------------------------------------------------------------------------------ our arm
+def run_ours(args):
+    import ctypes as C
+    import numpy as np
+    import torch
+    import __graft_entry__ as ge
+    pkg = ge.load_package()
+    rank = int(os.environ.get('RANK', '0')); world = int(os.environ.get('WORLD_SIZE', '1'))
+    local = int(os.environ.get('LOCAL_RANK', '0'))
+    if not torch.cuda.is_available():
+        raise SystemExit('bench.py needs a CUDA device: the product path has no CPU fallback')
+    torch.cuda.set_device(local)
+    dev = torch.device('cuda', local)
+    if world > 1:
+        import torch.distributed as dist
+        dist.init_process_group('nccl', device_id=dev)
+    L = pkg.capi.lib()
+    chk = pkg.capi.check
+    B, K, Wm = args.batch, args.steps, max(args.warmup, 3)
+    cap = NFEAT + 8 * NLEVELS + 24
+
+    frames = make_frames(pkg.synth, B, 1 + 100000 * rank)
+    host_in = torch.from_numpy(frames).pin_memory()
+    d_in = [host_in.to(dev, non_blocking=True), torch.roll(host_in, 1, 0).to(dev, non_blocking=True)]   # 2 x 92 MB > L2 together
+    d_kps = torch.zeros((B, cap, 28), dtype=torch.uint8, device=dev)
+    d_desc = torch.zeros((B, cap, 32), dtype=torch.uint8, device=dev)
+    d_n = torch.zeros(B, dtype=torch.int32, device=dev)
+    d_idx = torch.zeros((B, cap, 2), dtype=torch.int32, device=dev); d_dist = torch.zeros_like(d_idx)
+
+    ex = pkg.ORBextractor(NFEAT, SCALE, NLEVELS, pkg.ORBextractor.FAST_SCORE, FAST_TH, device=local, max_width=W, max_height=H,
+                          max_batch=B)
+    m = pkg.ORBmatcher(0.75, True, device=local)
+    stream = torch.cuda.current_stream(dev)
+    sp = C.c_void_p(stream.cuda_stream) if stream.cuda_stream else None
+    knn_ev = []
+
+    def step(i, timed=False):
+        chk(L.uvip_extract_batch_device(ex.h, C.c_void_p(d_in[i & 1].data_ptr()), B, W, H, W, W * H, C.c_void_p(d_kps.data_ptr()),
+                                        C.c_void_p(d_n.data_ptr()), cap, C.c_void_p(d_desc.data_ptr()), sp))
+        if timed:
+            e0 = torch.cuda.Event(enable_timing=True); e1 = torch.cuda.Event(enable_timing=True)
+            e0.record(stream)
+        # frame f (queries) against frame f+1 (train): B-1 consecutive pairs of the sequence
+        chk(L.uvip_knn2_batch_device(m.h, C.c_void_p(d_desc.data_ptr()), C.c_void_p(d_n.data_ptr()), cap * 32,
+                                     C.c_void_p(d_desc.data_ptr() + cap * 32), C.c_void_p(d_n.data_ptr() + 4), cap * 32,
+                                     B - 1, cap, C.c_void_p(d_idx.data_ptr()), C.c_void_p(d_dist.data_ptr()), cap, sp))
+        if timed:
+            e1.record(stream); knn_ev.append((e0, e1))
+
+    def barrier():
+        torch.cuda.synchronize(dev)
+        if world > 1:
+            dist.barrier()
+
+    for i in range(Wm):
+        step(i)
+    torch.cuda.synchronize(dev)
+    ex.status()                                            # loud if any capacity flag was raised
+    n_host = d_n.cpu().numpy()
+    assert n_host.min() >= NFEAT, 'extractor returned fewer than nfeatures keypoints: %d' % n_host.min()
+
+    ex.profile(True)
+    launches0 = ex.launch_count() + m.launch_count()
+    clocks = ClockSampler(local); clocks.start()
+    barrier()
+    t0 = torch.cuda.Event(enable_timing=True); t1 = torch.cuda.Event(enable_timing=True)
+    t0.record(stream)
+    for i in range(K):
+        step(i, timed=True)
+    t1.record(stream)
+    barrier()
+    ms = t0.elapsed_time(t1)
+    clk = clocks.stop()
+    launches = ex.launch_count() + m.launch_count() - launches0
+    ex.status()
+    stage_ms, ngroups = ex.stage_ms()
+    ex.profile(False)
+    knn_ms = sum(a.elapsed_time(b) for a, b in knn_ev)
+    pairs_step = float((n_host[:-1].astype(np.int64) * n_host[1:].astype(np.int64)).sum())
+    if world > 1:
+        tt = torch.tensor([ms], dtype=torch.float64, device=dev)
+        dist.all_reduce(tt, op=dist.ReduceOp.MAX)
+        ms = float(tt.item())
+    fps = world * B * K / (ms * 1e-3)
+
+    # ---- end to end through the host-buffer C-ABI (pinned host memory in, host memory out), copies inside the timed region
+    host_k = torch.zeros((B, cap, 28), dtype=torch.uint8).pin_memory(); host_d = torch.zeros((B, cap, 32), dtype=torch.uint8).pin_memory()
+    host_n = torch.zeros(B, dtype=torch.int32).pin_memory()
+    host_i = torch.zeros((B, cap, 2), dtype=torch.int32).pin_memory(); host_dd = torch.zeros_like(host_i).pin_memory()
+    hp = lambda t: C.c_void_p(t.data_ptr())
+
+    def e2e_step():
+        chk(L.uvip_extract_batch(ex.h, hp(host_in), B, W, H, W, W * H, hp(host_k), hp(host_n), cap, hp(host_d)))
+        chk(L.uvip_knn2_batch(m.h, hp(host_d), hp(host_n), cap * 32, C.c_void_p(host_d.data_ptr() + cap * 32),
+                              C.c_void_p(host_n.data_ptr() + 4), cap * 32, B - 1, cap, hp(host_i), hp(host_dd), cap))
+
+    Ke = max(3, min(K, 10))
+    e2e_step(); e2e_step()
+    barrier()
+    te = time.perf_counter()
+    for _ in range(Ke):
+        e2e_step()
+    barrier()
+    e2e_s = time.perf_counter() - te
+    if world > 1:
+        tt = torch.tensor([e2e_s], dtype=torch.float64, device=dev)
+        dist.all_reduce(tt, op=dist.ReduceOp.MAX)
+        e2e_s = float(tt.item())
+    e2e_fps = world * B * Ke / e2e_s
+    h2d = B * W * H + 2 * (B - 1) * cap * 32 + 2 * (B - 1) * 4
+    d2h = B * cap * 60 + B * 4 + 2 * (B - 1) * cap * 8
+
+    # ---- roofline of the dominant extraction kernel (algorithmic bytes of SURVEY 8(d) / its measured duration)
+    peak, peak_kind = hbm_peak()
+    dom = max(stage_ms, key=stage_ms.get)
+    dom_ms = stage_ms[dom] / max(ngroups, 1)
+    achieved = B_FRAME_BYTES * B / (dom_ms * 1e-3) / 1e9
+    traffic = ncu_traffic()
+    roofline = {'bound': 'hbm', 'kernel': dom, 'achieved': achieved, 'peak': peak, 'unit': 'GB/s', 'frac': achieved / peak,
+                'traffic': traffic.get(dom), 'peak_source': peak_kind + ' (MEASURED_PEAKS.json hbm_gbs)' if peak_kind == 'measured' else 'fallback 6.65 TB/s',
+                'algorithmic_bytes_per_launch': B_FRAME_BYTES * B, 'launch_ms': dom_ms,
+                'stage_ms_per_step': {k: v / max(ngroups, 1) for k, v in stage_ms.items()}, 'knn_ms_per_step': knn_ms / K,
+                'whole_step_frac': (B_FRAME_BYTES * B * K / (ms * 1e-3) / 1e9) / peak}
+
+    line = {
+        'metric': METRIC, 'value': fps, 'unit': 'frames/s', 'n_gpus': world, 'steps': K, 'warmup': Wm, 'ms_per_step': ms / K,
+        'higher_is_better': True, 'scaling': 'weak', 'vs_baseline': None, 'dtype': 'u8', 'data': 'synthetic',
+        'config': {'workload': 'ORBextractor 752x480 / 1000 kp / 8 levels / 1.2 / FAST 20-7 + brute-force Hamming kNN2 of consecutive '
+                               'frames (BASELINE config 1 shape, batched)', 'frames_per_step_per_gpu': B, 'keypoints': NFEAT,
+                   'l2': 'inputs alternate between two 92 MB batches and each step streams a 0.7 GB pyramid working set (> 126 MB L2)',
+                   'parallelism': 'frames sharded over %d GPU(s), no collective' % world},
+        'clocks': clk,
+        'e2e': {'value': e2e_fps, 'unit': 'frames/s', 'h2d_bytes_per_step': h2d, 'd2h_bytes_per_step': d2h, 'steps': Ke},
+        'gpu_launches': int(launches),
+        'roofline': roofline,
+        'hamming': {'pairs_per_s_in_step': pairs_step * K / (knn_ms * 1e-3) if knn_ms > 0 else None, 'pairs_per_step': pairs_step},
+    }
+
+    if rank == 0 and not args.no_extras:
+        # Hamming-only leg: database-scale kNN2 (cfg4 shape at 64k x 64k) against the measured popc-pipe peak
+        nq = nt = 65536
+        T, Q = pkg.synth.knn_database(nt, nq)
+        dT = torch.from_numpy(T).to(dev); dQ = torch.from_numpy(Q).to(dev)
+        oi = torch.zeros((nq, 2), dtype=torch.int32, device=dev); od = torch.zeros_like(oi)
+        run = lambda: chk(L.uvip_knn2_device(m.h, C.c_void_p(dQ.data_ptr()), nq, C.c_void_p(dT.data_ptr()), nt, 0,
+                                             C.c_void_p(oi.data_ptr()), C.c_void_p(od.data_ptr()), sp))
+        for _ in range(3):
+            run()
+        torch.cuda.synchronize(dev)
+        a = torch.cuda.Event(enable_timing=True); b = torch.cuda.Event(enable_timing=True)
+        a.record(stream)
+        for _ in range(5):
+            run()
+        b.record(stream); torch.cuda.synchronize(dev)
+        pps = 5.0 * nq * nt / (a.elapsed_time(b) * 1e-3)
+        popc = C.c_double()
+        chk(L.uvip_popc_peak(local, 4096, C.byref(popc)))
+        line['hamming'].update({'knn2_64k_pairs_per_s': pps, 'popc_per_pair': 8, 'popc_peak_measured_per_s': popc.value,
+                                'popc_frac': pps * 8 / popc.value,
+                                'popc_peak_nominal_per_s': 148 * 16 * (clk.get('sm_max_mhz') or 1965.0) * 1e6})
+        if world == 1:
+            # cpu_baseline: the oracle on this box's host cores, bounded sample of the same workload
+            cores = os.cpu_count() or 1
+            ns = max(16, 4 * cores)
+            sample = frames[:ns] if ns <= B else make_frames(pkg.synth, ns, 1)
+            cpu_reference(sample[:max(2, cores)], cores)
+            tc = cpu_reference(sample, cores)
+            t1c = cpu_reference(sample[:max(4, ns // 8)], 1)
+            line['cpu_baseline'] = {'value': len(sample) / tc, 'unit': 'frames/s', 'cores': cores, 'kind': 'port',
+                                    'sample': '%d frames of the same workload (extraction + consecutive-frame kNN2), OpenMP over frames' % len(sample),
+                                    'single_thread_frames_per_s': max(4, ns // 8) / t1c}
+    if rank == 0:
+        print(json.dumps(line), flush=True)
+    if world > 1:
+        dist.destroy_process_group()
+    return 0
+
+
+if __name__ == '__main__':
+    a = parse()
+    sys.exit(run_reference(a) if a.impl == 'reference' else run_ours(a))

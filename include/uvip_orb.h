@@ -109,6 +109,12 @@ int   uvip_get_level_keypoints(uvip_extractor* ex, int frame, int level,
                                                                                 list order (src/ORBextractor.cc:817-831) */
 /* how many of this library's kernels the handle has launched so far (bench.py's gpu_launches) */
 long long uvip_extractor_launch_count(const uvip_extractor* ex);
+/* per-stage device time (CUDA events recorded between the stage kernels on the launching stream), summed over
+ * the launch groups since profiling was enabled (at most the last 256).  Stages: 0 pyramid (import + 7 resizes),
+ * 1 FAST, 2 quadtree, 3 blur, 4 select, 5 orientation + descriptors.  Measurement utility for bench.py. */
+#define UVIP_NUM_STAGES 6
+int   uvip_extractor_profile(uvip_extractor* ex, int enable);
+int   uvip_extractor_stage_ms(uvip_extractor* ex, float* ms /* [UVIP_NUM_STAGES] */, int* ngroups);
 
 /* ---- matcher: replaces the descriptor path of USLAM::ORBmatcher (include/ORBmatcher.h:41-94) ------------- */
 typedef struct uvip_matcher uvip_matcher;
@@ -135,6 +141,10 @@ int   uvip_knn2_device(uvip_matcher* m, const uint8_t* d_q, int nq, const uint8_
 int   uvip_knn2_batch_device(uvip_matcher* m, const uint8_t* d_q, const int32_t* d_nq, size_t q_pitch,
                              const uint8_t* d_t, const int32_t* d_nt, size_t t_pitch, int npairs, int max_nq,
                              int32_t* d_idx2, int32_t* d_dist2, size_t res_pitch, void* stream);
+/* host-buffer form of the batch call (copies are inside the call): frame-to-frame matching of a whole sequence */
+int   uvip_knn2_batch(uvip_matcher* m, const uint8_t* q, const int32_t* nq, size_t q_pitch,
+                      const uint8_t* t, const int32_t* nt, size_t t_pitch, int npairs, int max_nq,
+                      int32_t* idx2, int32_t* dist2, size_t res_pitch);
 /* merge `nparts` partial top-2 lists (each nq x 2, parts are part_stride int32 apart) by (distance, global index);
  * shard-count invariant.  Used after the NCCL all-gather of the database-sharded kNN. */
 int   uvip_knn2_merge_device(uvip_matcher* m, const int32_t* d_idx_parts, const int32_t* d_dist_parts, int nparts,

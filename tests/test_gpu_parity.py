@@ -1,0 +1,300 @@
+"""GPU parity tests (-m gpu): the CUDA path, called through the C-ABI (ctypes -> libuvip_orb.so), against the CPU
+oracle on the same seeded inputs.  Bars (BASELINE.json north_star): pyramid, blur, FAST keypoint sets, Hamming
+distances and match indices bit-exact; angles within 1e-3 rad; descriptor bits >= 99.9 %."""
+import hashlib
+
+import numpy as np
+import pytest
+
+pytestmark = pytest.mark.gpu
+
+ANGLE_TOL_DEG = 1e-3 * 180.0 / np.pi       # 1e-3 rad
+DESC_BITS_MIN = 0.999
+
+
+def sha(a):
+    return hashlib.sha256(np.ascontiguousarray(a).tobytes()).hexdigest()
+
+
+@pytest.fixture(scope='module')
+def gpu(pkg):
+    if pkg.capi.lib().uvip_device_count() < 1:
+        pytest.fail('no CUDA device: the gpu-marked tests must run on the B200 box')
+    return pkg
+
+
+def compare_frame(gpu_ex, ora_ex, img, golden=None, tag=None, **kw):
+    kps, desc = gpu_ex(img, **kw)
+    okw = dict(full_detect=kw.get('FullDetect', True), num_needed=kw.get('num_featsneeded', 0),
+               min_px_dist=kw.get('min_px_dist', 1))
+    okps, odesc = ora_ex(img, keypoints=kw.get('keypoints'), grid=kw.get('ogrid'), **okw)
+    nlev = ora_ex.nlevels
+    for l in range(nlev):
+        lv = gpu_ex.level(l)
+        assert np.array_equal(lv, ora_ex.level(l)), ('pyramid level', l)
+        if golden is not None:
+            assert sha(lv) == golden['pyr_sha_' + tag][l]
+        assert np.array_equal(gpu_ex.level(l, blurred=True), ora_ex.level(l, blurred=True)), ('blurred level', l)
+        gx, gy, gs = gpu_ex.raw_corners(l)
+        ox, oy, os_ = ora_ex.raw_corners(l)
+        assert len(gx) == len(ox), ('raw corner count', l, len(gx), len(ox))
+        assert np.array_equal(gx, ox) and np.array_equal(gy, oy) and np.array_equal(gs, os_), ('raw corners + order', l)
+        wx, wy, ws = gpu_ex.level_keypoints(l)
+        ok = ora_ex.level_keypoints(l)
+        assert len(wx) == len(ok), ('quadtree winners', l, len(wx), len(ok))
+        assert np.array_equal(wx, ok['x'].astype(np.int32)) and np.array_equal(wy, ok['y'].astype(np.int32)), ('winner order', l)
+        assert np.array_equal(ws, ok['response'].astype(np.int32))
+    assert len(kps) == len(okps)
+    for fld in ('x', 'y', 'size', 'response', 'octave', 'class_id'):
+        assert np.array_equal(kps[fld], okps[fld]), fld
+    if len(kps):
+        assert np.abs(kps['angle'] - okps['angle']).max() <= ANGLE_TOL_DEG
+        agree = 1.0 - np.unpackbits(desc ^ odesc).mean()
+        assert agree >= DESC_BITS_MIN, agree
+    return kps, desc, okps, odesc
+
+
+def test_extract_cfg1_euroc_frame(gpu, oracle, synth, golden):
+    """BASELINE config 1: 752x480, 1000 kp, 8 levels, 1.2, FAST 20/7."""
+    img = synth.synth_frame(1, 752, 480)
+    ex = gpu.ORBextractor(1000, 1.2, 8, gpu.ORBextractor.FAST_SCORE, 20, max_width=752, max_height=480)
+    oex = oracle.Extractor(1000, 1.2, 8, 1, 20)
+    kps, desc, okps, odesc = compare_frame(ex, oex, img, golden, '752x480')
+    assert len(kps) >= 1000
+    # measured expectation: angles and descriptors are bit-identical, not merely within tolerance
+    assert np.array_equal(kps['angle'], okps['angle'])
+    assert np.array_equal(desc, odesc)
+    assert ex.GetLevels() == 8 and ex.GetScaleFactor() == np.float32(1.2)
+    sc, inv, quota, umax = ex.tables()
+    osc, oinv, oquota, oumax = oex.tables()
+    assert np.array_equal(sc, osc) and np.array_equal(inv, oinv) and np.array_equal(quota, oquota) and np.array_equal(umax, oumax)
+
+
+@pytest.mark.parametrize('seed,W,H,nf,th', [(1000, 640, 512, 1500, 20), (100000, 1280, 1024, 2000, 20), (7, 320, 240, 400, 7),
+                                            (8, 968, 608, 800, 10), (9, 401, 307, 600, 1), (10, 640, 480, 1000, 40)])
+def test_extract_other_shapes(gpu, oracle, synth, seed, W, H, nf, th):
+    img = synth.synth_frame(seed, W, H)
+    ex = gpu.ORBextractor(nf, 1.2, 8, 0, th, max_width=W, max_height=H)
+    compare_frame(ex, oracle.Extractor(nf, 1.2, 8, 0, th), img)
+
+
+def test_extract_hard_images(gpu, oracle, synth):
+    ex = gpu.ORBextractor(500, 1.2, 8, 1, 20, max_width=400, max_height=300)
+    oex = oracle.Extractor(500, 1.2, 8, 1, 20)
+    flat = np.full((300, 400), 90, np.uint8)                      # constant image -> 0 keypoints, descriptors released
+    kps, desc = ex(flat)
+    assert len(kps) == 0 and len(desc) == 0
+    noise = (synth.draw(5, np.arange(1, 400 * 300 + 1, dtype=np.uint64)) % np.uint64(256)).astype(np.uint8).reshape(300, 400)
+    compare_frame(ex, oex, noise)                                 # white noise: densest possible corner field
+    ramp = np.tile(np.arange(400, dtype=np.uint8), (300, 1))
+    compare_frame(ex, oex, ramp)
+    sparse = np.full((300, 400), 50, np.uint8); sparse[100:140, 120:180] = 58; sparse[200:203, 300:303] = 66
+    compare_frame(ex, oex, sparse)                                # only retry-threshold (7) corners exist
+
+
+def test_extract_empty_image_and_strided_roi(gpu, oracle, synth):
+    ex = gpu.ORBextractor(300, 1.2, 8, 1, 20, max_width=400, max_height=300)
+    marker = np.zeros(3, gpu.capi.KP_DTYPE)
+    out_k, out_d = ex(np.zeros((0, 0), np.uint8), keypoints=marker)
+    assert out_k is marker and out_d is None                      # empty image: silent return, outputs untouched
+    with pytest.raises(AssertionError):
+        ex(np.zeros((10, 10), np.float32))
+    big = synth.synth_frame(3, 500, 400)
+    roi = big[50:350, 60:460]                                     # image is a ROI of a larger buffer (stride > width)
+    k1, d1 = ex(roi)
+    k2, d2 = ex(np.ascontiguousarray(roi))
+    assert np.array_equal(k1, k2) and np.array_equal(d1, d2)
+    ok, od = oracle.Extractor(300, 1.2, 8, 1, 20)(np.ascontiguousarray(roi))
+    assert np.array_equal(k1['x'], ok['x']) and np.array_equal(d1, od)
+
+
+def test_extract_occupancy_grid_path(gpu, oracle, synth):
+    """FullDetect=false: greedy occupancy filter on the caller's column-major grid, incoming keypoints kept
+    (src/ORBextractor.cc:872-910, Tracking.cc:901-946)."""
+    W, H, mpd = 752, 480, 20
+    img = synth.synth_frame(21, W, H)
+    ex = gpu.ORBextractor(1000, 1.2, 8, 1, 20, max_width=W, max_height=H)
+    oex = oracle.Extractor(1000, 1.2, 8, 1, 20)
+    for n_in, need in ((0, 400), (25, 150), (5, 1000)):
+        grid = np.zeros((H // mpd + 2, W // mpd + 2), np.int32, order='F')
+        rng = np.random.default_rng(n_in)
+        inc = np.zeros(n_in, gpu.capi.KP_DTYPE)
+        inc['x'] = rng.integers(40, W - 40, n_in); inc['y'] = rng.integers(40, H - 40, n_in)
+        inc['size'] = 31; inc['angle'] = -1; inc['octave'] = 0; inc['class_id'] = 7
+        for k in inc:
+            grid[int(k['y'] / mpd), int(k['x'] / mpd)] += 1
+        g1 = grid.copy(order='F'); g2 = grid.copy(order='F')
+        kps, desc = ex(img, keypoints=inc, grid_2d=g1, min_px_dist=mpd, FullDetect=False, num_featsneeded=need)
+        okps, odesc = oex(img, keypoints=inc, grid=g2, min_px_dist=mpd, full_detect=False, num_needed=need)
+        assert np.array_equal(g1, g2)
+        assert len(kps) == len(okps) and len(kps) >= n_in
+        for fld in ('x', 'y', 'size', 'response', 'octave', 'class_id'):
+            assert np.array_equal(kps[fld], okps[fld]), fld
+        assert np.abs(kps['angle'] - okps['angle']).max() <= ANGLE_TOL_DEG
+        assert 1.0 - np.unpackbits(desc ^ odesc).mean() >= DESC_BITS_MIN
+    # FullDetect=true leaves the grid untouched and drops incoming keypoints
+    g3 = grid.copy(order='F')
+    kps, _ = ex(img, keypoints=inc, grid_2d=g3, min_px_dist=mpd, FullDetect=True, num_featsneeded=10)
+    assert np.array_equal(g3, grid) and len(kps) >= 1000
+
+
+def test_extract_batch_matches_single_frames(gpu, oracle, synth):
+    """BASELINE config 2 shape: 640x512, 1500 kp, one HBM-resident batch; each frame equals its single-frame result."""
+    nfr = 6
+    frames = synth.synth_batch(1000, nfr, 640, 512)
+    ex = gpu.ORBextractor(1500, 1.2, 8, 1, 20, max_width=640, max_height=512, max_batch=4)   # 6 frames -> groups of 4 + 2
+    kps, n, desc = ex.extract_batch(frames)
+    okps, on, odesc = oracle.extract_batch(frames, 1500, 1.2, 8, 20, cap=kps.shape[1])
+    assert np.array_equal(n, on) and n.min() >= 1500
+    for f in range(nfr):
+        a, b = kps[f, :n[f]], okps[f, :n[f]]
+        for fld in ('x', 'y', 'size', 'response', 'octave', 'class_id'):
+            assert np.array_equal(a[fld], b[fld]), (f, fld)
+        assert np.abs(a['angle'] - b['angle']).max() <= ANGLE_TOL_DEG
+        assert 1.0 - np.unpackbits(desc[f, :n[f]] ^ odesc[f, :n[f]]).mean() >= DESC_BITS_MIN
+    # size-independent property: a batch is order-equivariant
+    kps2, n2, desc2 = ex.extract_batch(frames[::-1].copy())
+    assert np.array_equal(n2, n[::-1]) and np.array_equal(desc2[0, :n2[0]], desc[nfr - 1, :n[nfr - 1]])
+
+
+def test_capacity_overflow_is_loud(gpu, synth):
+    ex = gpu.ORBextractor(1000, 1.2, 8, 1, 20, max_width=752, max_height=480)
+    with pytest.raises(gpu.capi.UvipError) as e:
+        ex(synth.synth_frame(1, 752, 480), cap=100)              # 1000+ keypoints do not fit 100 rows
+    assert e.value.code == gpu.capi.ERR_CAPACITY
+    with pytest.raises(gpu.capi.UvipError) as e:
+        ex(synth.synth_frame(1, 800, 480))                       # wider than max_width
+    assert e.value.code in (gpu.capi.ERR_ARG, gpu.capi.ERR_UNSUPPORTED)
+    with pytest.raises(gpu.capi.UvipError):
+        gpu.ORBextractor(1000, 1.2, 8, 1, 20, max_width=120, max_height=100)   # top level would be < 64 px
+
+
+# ------------------------------------------------------------------------------------------------ matcher
+def test_descriptor_distance(gpu, oracle, synth):
+    m = gpu.ORBmatcher()
+    a = synth.random_descriptors(1, 300); b = synth.random_descriptors(2, 300)
+    b[0] = a[0]; b[1] = ~a[1]
+    d = m.DescriptorDistance(a, b)
+    ref = np.array([oracle.descriptor_distance(x, y) for x, y in zip(a, b)], np.int32)
+    assert np.array_equal(d, ref) and d[0] == 0 and d[1] == 256
+    assert m.DescriptorDistance(a[5], b[5]) == ref[5]
+    assert m.TH_HIGH == 100 and m.TH_LOW == 50 and m.HISTO_LENGTH == 30
+
+
+def test_knn2_cfg1_frame_pair_and_ratio_and_histogram(gpu, oracle, synth):
+    """config 1: brute-force kNN2 between a frame and its shifted twin, ratios {0.6,0.75,0.8,0.9}, rotation histogram."""
+    ex = gpu.ORBextractor(1000, 1.2, 8, 1, 20, max_width=752, max_height=480)
+    ka, da = ex(synth.synth_frame(1, 752, 480))
+    kb, db = ex(synth.synth_frame(1, 752, 480, dx=5, dy=3, noise_seed=2))
+    m = gpu.ORBmatcher(0.75, True)
+    idx, dist = m.knn2(da, db)
+    oidx, odist = oracle.knn2(da, db)
+    assert np.array_equal(idx, oidx) and np.array_equal(dist, odist)
+    for ratio in (0.6, 0.75, 0.8, 0.9):
+        got = m.ratio_filter(idx, dist, ratio)
+        ref = oracle.ratio_filter(oidx, odist, ratio)
+        assert np.array_equal(got, ref)
+        g2 = m.rot_hist_filter(got, ka['angle'], kb['angle'])
+        r2 = oracle.rot_hist_filter(ref, ka['angle'], kb['angle'])
+        assert np.array_equal(g2, r2)
+        assert np.array_equal(m.ratioMatching(da, db, ratio, ka['angle'], kb['angle']), r2)
+    assert (m.ratio_filter(idx, dist, 0.75) >= 0).sum() > 200      # the twin really matches
+
+
+def test_knn2_golden_ties_and_ragged_sizes(gpu, oracle, synth, golden):
+    m = gpu.ORBmatcher()
+    q = synth.random_descriptors(31, 200); t = synth.random_descriptors(32, 2000)
+    t[100] = t[7]; t[300] = q[5]; t[301] = q[5]; t[1999] = q[9]
+    idx, dist = m.knn2(q, t)
+    assert np.array_equal(idx, golden['knn_idx']) and np.array_equal(dist, golden['knn_dist'])
+    for nq, nt in ((1, 1), (1, 2), (3, 255), (129, 256), (130, 257), (257, 513), (5, 70000), (1000, 1)):
+        qq = synth.random_descriptors(100 + nq, nq); tt = synth.random_descriptors(200 + nt, nt)
+        if nt > 600:
+            tt[nt - 1] = tt[0]; tt[65536 % nt] = tt[0]          # ties across tiles and across the 65536-row index window
+        i1, d1 = m.knn2(qq, tt)
+        i2, d2 = oracle.knn2(qq, tt)
+        assert np.array_equal(i1, i2) and np.array_equal(d1, d2), (nq, nt)
+    i, d = m.knn2(q[:4], t[:1])
+    assert i[:, 1].tolist() == [-1] * 4 and d[:, 1].tolist() == [257] * 4   # a single train row has no second neighbour
+    i, d = m.knn2(q[:0], t)
+    assert i.shape == (0, 2)
+
+
+def test_knn2_shard_invariance_via_device_api(gpu, oracle, synth):
+    """cfg4 shape in miniature: database rows sharded contiguously, per-shard top-2 with global indices, merged by
+    (distance, index) — identical for every shard count (the multi-GPU path runs the same two entry points)."""
+    import ctypes as C
+    import torch
+    L = gpu.capi.lib()
+    T, Q = synth.knn_database(8192, 2048)
+    ref_i, ref_d = oracle.knn2(Q, T)
+    m = gpu.ORBmatcher()
+    dq = torch.from_numpy(Q).cuda(); dt = torch.from_numpy(T).cuda()
+    for G in (1, 2, 3, 8):
+        bounds = [(g * len(T)) // G for g in range(G + 1)]
+        pi = torch.empty((G, len(Q), 2), dtype=torch.int32, device='cuda'); pd = torch.empty_like(pi)
+        for g in range(G):
+            sh = dt[bounds[g]:bounds[g + 1]]
+            gpu.capi.check(L.uvip_knn2_device(m.h, C.c_void_p(dq.data_ptr()), len(Q), C.c_void_p(sh.data_ptr()), sh.shape[0],
+                                              bounds[g], C.c_void_p(pi[g].data_ptr()), C.c_void_p(pd[g].data_ptr()), None))
+        oi = torch.empty((len(Q), 2), dtype=torch.int32, device='cuda'); od = torch.empty_like(oi)
+        gpu.capi.check(L.uvip_knn2_merge_device(m.h, C.c_void_p(pi.data_ptr()), C.c_void_p(pd.data_ptr()), G, len(Q) * 2, len(Q),
+                                                C.c_void_p(oi.data_ptr()), C.c_void_p(od.data_ptr()), None))
+        torch.cuda.synchronize()
+        assert np.array_equal(oi.cpu().numpy(), ref_i) and np.array_equal(od.cpu().numpy(), ref_d), G
+
+
+def test_grid_and_search_by_projection_cfg3(gpu, oracle, synth):
+    """config 3: 10k projected map points vs a 2000-keypoint frame; claims replayed in the reference's order."""
+    c = synth.projection_case()
+    m = gpu.ORBmatcher(0.8, True)
+    grid = m.grid_build(c['kx'], c['ky'], c['bounds'])
+    ostart, oitems = oracle.grid_build(c['kx'], c['ky'], grid['minX'], grid['minY'], grid['inv_w'], grid['inv_h'])
+    assert np.array_equal(grid['start'], ostart) and np.array_equal(grid['items'], oitems)
+    sf = gpu.ORBextractor(1000, 1.2, 8, 1, 20, max_width=752, max_height=480).tables()[0]
+    frame = dict(kx=c['kx'], ky=c['ky'], octave=c['octave'], kdesc=c['kdesc'], grid=grid, scale_factors=sf)
+    mps = dict(u=c['u'], v=c['v'], level=c['level'], view_cos=c['view_cos'], desc=c['qdesc'])
+    for th in (1.0, 3.0):
+        n, match, taken = m.SearchByProjection(frame, mps, th)
+        r = np.array([oracle.lib().uo_radius_by_viewing_cos(float(v)) for v in c['view_cos']], np.float32)
+        if th != 1.0:
+            r = (r * np.float32(th)).astype(np.float32)
+        r = (r * sf[c['level']]).astype(np.float32)
+        on, omatch, otaken = oracle.search_window(0, 100, 0.8, c['u'], c['v'], r, c['level'] - 1, c['level'], c['qdesc'],
+                                                  c['kx'], c['ky'], c['octave'], c['kdesc'], ostart, oitems,
+                                                  grid['minX'], grid['minY'], grid['inv_w'], grid['inv_h'])
+        assert n == on and n > 500
+        assert np.array_equal(match, omatch) and np.array_equal(taken, otaken)
+    # M5 semantics: th=10 window, levels [l-1, l+1], best only, ORBdist 100, pre-taken keypoints, then the histogram
+    lvl = c['level']
+    r = (np.float32(10) * sf[lvl]).astype(np.float32)
+    pre = np.full(len(c['kx']), -1, np.int32); pre[::7] = -2
+    n, match, taken = m.search_window(1, 100, c['u'], c['v'], r, lvl - 1, lvl + 1, c['qdesc'], c['kx'], c['ky'], c['octave'],
+                                      c['kdesc'], grid, taken=pre)
+    on, omatch, otaken = oracle.search_window(1, 100, 0.8, c['u'], c['v'], r, lvl - 1, lvl + 1, c['qdesc'], c['kx'], c['ky'],
+                                              c['octave'], c['kdesc'], ostart, oitems, grid['minX'], grid['minY'],
+                                              grid['inv_w'], grid['inv_h'], taken=pre)
+    assert n == on and np.array_equal(match, omatch) and np.array_equal(taken, otaken)
+    assert (match[match >= 0] % 7 != 0).all()                     # pre-taken keypoints are never claimed
+    g = m.rot_hist_filter(match, c['qangle'], c['kangle'])
+    o = oracle.rot_hist_filter(omatch, c['qangle'], c['kangle'])
+    assert np.array_equal(g, o) and (g >= 0).sum() < (match >= 0).sum()
+
+
+def test_search_window_claim_chain(gpu, oracle, synth):
+    """adversarial claims: every query wants the same few keypoints, so results depend on the sequential order."""
+    nk, nq = 40, 300
+    kx = (100 + (np.arange(nk) % 8) * 0.5).astype(np.float32); ky = (100 + (np.arange(nk) // 8) * 0.5).astype(np.float32)
+    octave = np.zeros(nk, np.int32)
+    kdesc = synth.random_descriptors(77, nk)
+    qdesc = synth.flip_bits(np.repeat(kdesc[:1], nq, 0), 900, (np.arange(nq) % 5).tolist())
+    m = gpu.ORBmatcher(0.99, True)
+    grid = m.grid_build(kx, ky, (0, 752, 0, 480))
+    qu = np.full(nq, 101, np.float32); qv = np.full(nq, 101, np.float32); qr = np.full(nq, 6, np.float32)
+    ml = np.full(nq, -1, np.int32)
+    for mode, th in ((0, 256), (1, 256), (0, 100)):
+        n, match, taken = m.search_window(mode, th, qu, qv, qr, ml, ml, qdesc, kx, ky, octave, kdesc, grid)
+        on, omatch, otaken = oracle.search_window(mode, th, 0.99, qu, qv, qr, ml, ml, qdesc, kx, ky, octave, kdesc,
+                                                  grid['start'], grid['items'], grid['minX'], grid['minY'], grid['inv_w'], grid['inv_h'])
+        assert n == on and np.array_equal(match, omatch) and np.array_equal(taken, otaken), mode
+    assert n <= nk

@@ -70,6 +70,8 @@ def lib():
         L.uvip_get_raw_corners.argtypes = [vp, i, i, vp, vp, vp, i, C.POINTER(i)]
         L.uvip_get_level_keypoints.argtypes = [vp, i, i, vp, vp, vp, i, C.POINTER(i)]
         L.uvip_extractor_launch_count.argtypes = [vp]
+        L.uvip_extractor_profile.argtypes = [vp, i]
+        L.uvip_extractor_stage_ms.argtypes = [vp, vp, C.POINTER(i)]
         L.uvip_matcher_create.argtypes = [i, C.POINTER(vp)]
         L.uvip_matcher_destroy.argtypes = [vp]
         L.uvip_matcher_launch_count.argtypes = [vp]
@@ -77,6 +79,7 @@ def lib():
         L.uvip_knn2.argtypes = [vp, vp, i, vp, i, vp, vp]
         L.uvip_knn2_device.argtypes = [vp, vp, i, vp, i, i, vp, vp, vp]
         L.uvip_knn2_batch_device.argtypes = [vp, vp, vp, sz, vp, vp, sz, i, i, vp, vp, sz, vp]
+        L.uvip_knn2_batch.argtypes = [vp, vp, vp, sz, vp, vp, sz, i, i, vp, vp, sz]
         L.uvip_knn2_merge_device.argtypes = [vp, vp, vp, i, sz, i, vp, vp, vp]
         L.uvip_ratio_filter.argtypes = [vp, vp, vp, i, C.c_double, vp, C.POINTER(i)]
         L.uvip_rot_hist_filter.argtypes = [vp, vp, i, vp, vp, C.POINTER(i)]

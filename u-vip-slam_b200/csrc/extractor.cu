@@ -838,8 +838,13 @@ struct uvip_extractor {
     int sel_cap = 0;
     int last_frames = 0;
     long long launches = 0;
+    // optional per-stage timing (bench.py roofline): a ring of event sets, one per launch group
+    bool prof = false;
+    std::vector<cudaEvent_t> prof_ev;      // PROF_RING * (UVIP_NUM_STAGES + 1)
+    long long prof_groups = 0;
     std::mutex mu;
 };
+constexpr int PROF_RING = 256;
 
 // per-axis resize table of cv::resize INTER_LINEAR (8-bit fixed point), see SURVEY A.2
 static void build_axis_table(int src_n, int dst_n, int* ofs, int* coef)
@@ -893,7 +898,7 @@ static int make_plan(const uvip_extractor* ex, int w, int h, Plan* out, std::vec
         L.cell_off = cells; cells += L.ncols * L.nrows;
         L.quota = ex->quota[l]; if (L.quota > maxN) maxN = L.quota;
         const int area = (L.w - 2 * EDGE) * (L.h - 2 * EDGE);
-        L.raw_cap = area / 6 + 256;          // local maxima of the score map; overflow is reported, never truncated
+        L.raw_cap = area / 4 + area / 32 + 256;   // bound on cell-local maxima of the score map; overflow is reported, never truncated
         L.raw_off = raw; raw += (L.raw_cap + 3) & ~3;
         // quadtree roots, :1010-1012
         L.nini = (int)roundf((float)(maxBX - minB) / (float)(maxBY - minB));
@@ -962,6 +967,9 @@ static int enqueue_group(uvip_extractor* ex, const uint8_t* d_frames, int nframe
     UVIP_CUDA(cudaMemsetAsync(counters, 0, 3 * cstride * sizeof(int), st));
     UVIP_CUDA(cudaMemsetAsync(ex->cellmax.p, 0, (size_t)nframes * P.cells_per_frame * sizeof(int), st));
     UVIP_CUDA(cudaMemsetAsync(ex->status.p, 0, sizeof(int), st));
+    cudaEvent_t* pe = ex->prof ? ex->prof_ev.data() + (size_t)(ex->prof_groups % PROF_RING) * (UVIP_NUM_STAGES + 1) : nullptr;
+#define PROF_MARK(i) do { if (pe) UVIP_CUDA(cudaEventRecord(pe[i], st)); } while (0)
+    PROF_MARK(0);
     {
         const LevelInfo& L = P.lv[0];
         dim3 g(div_up(L.w, 256), div_up(L.h, 4), nframes);
@@ -974,23 +982,31 @@ static int enqueue_group(uvip_extractor* ex, const uint8_t* d_frames, int nframe
         k_resize<<<g, 256, 0, st>>>(pyr, ex->tabs.as<int>(), l, P);
         ex->launches++;
     }
+    PROF_MARK(1);
     k_fast<<<dim3(P.ftiles, nframes), 256, 0, st>>>(pyr, ex->cand.as<unsigned>(), cand_count, ex->cellmax.as<int>(), ex->status.as<int>(), P);
     ex->launches++;
+    PROF_MARK(2);
     k_quadtree<<<dim3(P.nlevels, nframes), QT_THREADS, qt_smem_bytes(P.node_cap), st>>>(
         ex->cand.as<unsigned>(), cand_count, ex->cellmax.as<int>(), ex->keys.as<unsigned>(), key_count,
         ex->labels.as<unsigned short>(), ex->winners.as<unsigned>(), win_count, ex->status.as<int>(), P);
     ex->launches++;
+    PROF_MARK(3);
     k_blur<<<dim3(P.btiles, nframes), 256, 0, st>>>(pyr, blur, P);
     ex->launches++;
+    PROF_MARK(4);
     k_select<<<nframes, 256, 0, st>>>(ex->winners.as<unsigned>(), win_count, ex->sel.as<unsigned>(), ex->nsel.as<int>(), ex->sel_cap,
                                        full_detect, n_incoming, ex->grid.as<int32_t>(), grid_rows, grid_cols, min_px_dist, num_needed,
                                        ex->status.as<int>(), P);
     ex->launches++;
     const int slots = out_cap < ex->sel_cap ? out_cap : ex->sel_cap;
+    PROF_MARK(5);
     k_describe<<<dim3(div_up(slots, DESC_WARPS), nframes), DESC_WARPS * 32, 0, st>>>(
         pyr, blur, ex->winners.as<unsigned>(), ex->sel.as<unsigned>(), ex->nsel.as<int>(), ex->sel_cap,
         ex->incoming.as<uvip_keypoint>(), d_kps, d_desc, d_n_out, out_cap, ex->status.as<int>(), P);
     ex->launches++;
+    PROF_MARK(6);
+#undef PROF_MARK
+    if (pe) ex->prof_groups++;
     UVIP_CUDA(cudaGetLastError());
     ex->last_frames = nframes;
     return UVIP_OK;
@@ -1102,6 +1118,7 @@ int uvip_extractor_destroy(uvip_extractor* ex)
     DevBuf* bufs[] = {&ex->pyr, &ex->blur, &ex->cand, &ex->keys, &ex->labels, &ex->winners, &ex->counters, &ex->cellmax, &ex->sel,
                       &ex->nsel, &ex->tabs, &ex->status, &ex->grid, &ex->incoming, &ex->in_frames, &ex->out_kps, &ex->out_desc, &ex->out_n};
     for (DevBuf* b : bufs) b->release();
+    for (cudaEvent_t e : ex->prof_ev) cudaEventDestroy(e);
     if (ex->stream) cudaStreamDestroy(ex->stream);
     delete ex;
     return UVIP_OK;
@@ -1217,6 +1234,36 @@ int uvip_extract(uvip_extractor* ex, const uint8_t* image, int w, int h, int str
     if (!full_detect) UVIP_CUDA(cudaMemcpyAsync(grid, ex->grid.p, (size_t)grid_rows * grid_cols * 4, cudaMemcpyDeviceToHost, st));
     UVIP_CUDA(cudaStreamSynchronize(st));
     *n_inout = n;
+    return UVIP_OK;
+}
+
+// ---- per-stage timing --------------------------------------------------------------------------------
+int uvip_extractor_profile(uvip_extractor* ex, int enable)
+{
+    UVIP_CHECK_ARG(ex);
+    DeviceGuard g(ex->device);
+    UVIP_CUDA(cudaDeviceSynchronize());
+    if (enable && ex->prof_ev.empty()) {
+        ex->prof_ev.resize((size_t)PROF_RING * (UVIP_NUM_STAGES + 1));
+        for (auto& e : ex->prof_ev) UVIP_CUDA(cudaEventCreate(&e));
+    }
+    ex->prof = enable != 0;
+    ex->prof_groups = 0;
+    return UVIP_OK;
+}
+
+int uvip_extractor_stage_ms(uvip_extractor* ex, float* ms, int* ngroups)
+{
+    UVIP_CHECK_ARG(ex && ms);
+    DeviceGuard g(ex->device);
+    UVIP_CUDA(cudaDeviceSynchronize());
+    for (int i = 0; i < UVIP_NUM_STAGES; i++) ms[i] = 0.f;
+    const long long n = ex->prof_groups < PROF_RING ? ex->prof_groups : PROF_RING;
+    for (long long gI = 0; gI < n; gI++) {
+        cudaEvent_t* pe = ex->prof_ev.data() + (size_t)gI * (UVIP_NUM_STAGES + 1);
+        for (int i = 0; i < UVIP_NUM_STAGES; i++) { float t = 0; UVIP_CUDA(cudaEventElapsedTime(&t, pe[i], pe[i + 1])); ms[i] += t; }
+    }
+    if (ngroups) *ngroups = (int)n;
     return UVIP_OK;
 }
 

@@ -486,6 +486,41 @@ int uvip_knn2(uvip_matcher* m, const uint8_t* q, int nq, const uint8_t* t, int n
     return UVIP_OK;
 }
 
+int uvip_knn2_batch(uvip_matcher* m, const uint8_t* q, const int32_t* nq, size_t q_pitch,
+                    const uint8_t* t, const int32_t* nt, size_t t_pitch, int npairs, int max_nq,
+                    int32_t* idx2, int32_t* dist2, size_t res_pitch)
+{
+    UVIP_CHECK_ARG(m && q && t && nq && nt && idx2 && dist2 && npairs >= 0 && max_nq >= 0 && res_pitch >= (size_t)max_nq);
+    UVIP_CHECK_ARG((q_pitch & 31) == 0 && (t_pitch & 31) == 0);
+    if (npairs == 0 || max_nq == 0) return UVIP_OK;
+    int max_nt = 0;
+    for (int p = 0; p < npairs; p++) {
+        UVIP_CHECK_ARG(nq[p] >= 0 && nq[p] <= max_nq && (size_t)nq[p] * 32 <= q_pitch && nt[p] >= 0 && (size_t)nt[p] * 32 <= t_pitch);
+        if (nt[p] > max_nt) max_nt = nt[p];
+    }
+    std::lock_guard<std::mutex> lk(m->mu);
+    DeviceGuard g(m->device);
+    int rc;
+    if ((rc = m->q.reserve((size_t)npairs * q_pitch))) return rc;
+    if ((rc = m->t.reserve((size_t)npairs * t_pitch))) return rc;
+    if ((rc = m->idx.reserve((size_t)npairs * res_pitch * 8))) return rc;
+    if ((rc = m->dist.reserve((size_t)npairs * res_pitch * 8))) return rc;
+    if ((rc = m->misc.reserve((size_t)npairs * 8))) return rc;
+    cudaStream_t st = m->stream;
+    int32_t* d_nq = m->misc.as<int32_t>(); int32_t* d_nt = d_nq + npairs;
+    UVIP_CUDA(cudaMemcpyAsync(m->q.p, q, (size_t)npairs * q_pitch, cudaMemcpyHostToDevice, st));
+    UVIP_CUDA(cudaMemcpyAsync(m->t.p, t, (size_t)npairs * t_pitch, cudaMemcpyHostToDevice, st));
+    UVIP_CUDA(cudaMemcpyAsync(d_nq, nq, (size_t)npairs * 4, cudaMemcpyHostToDevice, st));
+    UVIP_CUDA(cudaMemcpyAsync(d_nt, nt, (size_t)npairs * 4, cudaMemcpyHostToDevice, st));
+    rc = launch_knn2(m, m->q.as<uint8_t>(), d_nq, q_pitch, m->t.as<uint8_t>(), d_nt, t_pitch, npairs, max_nq, 0, 0, 0,
+                     m->idx.as<int32_t>(), m->dist.as<int32_t>(), res_pitch, st);
+    if (rc) return rc;
+    UVIP_CUDA(cudaMemcpyAsync(idx2, m->idx.p, (size_t)npairs * res_pitch * 8, cudaMemcpyDeviceToHost, st));
+    UVIP_CUDA(cudaMemcpyAsync(dist2, m->dist.p, (size_t)npairs * res_pitch * 8, cudaMemcpyDeviceToHost, st));
+    UVIP_CUDA(cudaStreamSynchronize(st));
+    return UVIP_OK;
+}
+
 int uvip_knn2_merge_device(uvip_matcher* m, const int32_t* d_idx_parts, const int32_t* d_dist_parts, int nparts,
                            size_t part_stride, int nq, int32_t* d_idx2, int32_t* d_dist2, void* stream)
 {

@@ -97,6 +97,16 @@ class ORBextractor:
     def launch_count(self):
         return int(lib().uvip_extractor_launch_count(self.h))
 
+    STAGES = ('pyramid', 'fast', 'quadtree', 'blur', 'select', 'describe')
+
+    def profile(self, enable=True):
+        check(lib().uvip_extractor_profile(self.h, int(enable)))
+
+    def stage_ms(self):
+        ms = np.zeros(len(self.STAGES), np.float32); n = C.c_int()
+        check(lib().uvip_extractor_stage_ms(self.h, ptr(ms), C.byref(n)))
+        return dict(zip(self.STAGES, ms.tolist())), n.value
+
     # ---- debug taps
     def level(self, l, blurred=False, frame=0):
         w = C.c_int(); h = C.c_int()
