@@ -187,8 +187,10 @@ def run_ours(args):
     ex = pkg.ORBextractor(NFEAT, SCALE, NLEVELS, pkg.ORBextractor.FAST_SCORE, FAST_TH, device=local, max_width=W, max_height=H,
                           max_batch=B)
     m = pkg.ORBmatcher(0.75, True, device=local)
-    stream = torch.cuda.current_stream(dev)
-    sp = C.c_void_p(stream.cuda_stream) if stream.cuda_stream else None
+    stream = torch.cuda.Stream(dev)              # an explicit stream: torch events and our kernels share it
+    torch.cuda.set_stream(stream)
+    sp = C.c_void_p(stream.cuda_stream)
+    assert stream.cuda_stream != 0
     knn_ev = []
 
     def step(i, timed=False):

@@ -1,0 +1,62 @@
+"""Per-source-line instruction / stall-sample summary of one kernel from an ncu report.
+ncu's CSV source page is SASS-level; line numbers come from nvdisasm --print-line-info on the cubin embedded in the
+library (the i-th SASS instruction of the function in both listings).
+   python tools/ncu_lines.py <report.ncu-rep> <kernel regex> [top N] [library.so]"""
+import csv, io, os, re, subprocess, sys, tempfile
+
+rep, kern = sys.argv[1], sys.argv[2]
+top = int(sys.argv[3]) if len(sys.argv) > 3 else 40
+so = sys.argv[4] if len(sys.argv) > 4 else os.path.join(os.path.dirname(os.path.dirname(os.path.abspath(__file__))),
+                                                        'u-vip-slam_b200', 'libuvip_orb.so')
+out = subprocess.run(['ncu', '-i', rep, '--page', 'source', '--csv', '--kernel-name', 'regex:' + kern],
+                     capture_output=True, text=True).stdout
+rows = list(csv.reader(io.StringIO(out)))
+hdr = None; data = []
+for r in rows:
+    if r and r[0] == 'Address' and 'Source' in r:
+        if hdr is not None:
+            break                      # first matching launch only
+        hdr = r; continue
+    if hdr and len(r) == len(hdr):
+        data.append(r)
+iS = hdr.index('Source'); iI = hdr.index('Instructions Executed'); iT = hdr.index('Thread Instructions Executed'); iN = hdr.index('# Samples')
+# line info
+tmp = tempfile.mkdtemp()
+subprocess.run(['cuobjdump', '-xelf', 'all', so], cwd=tmp, capture_output=True)
+lines = []
+for cb in sorted(os.listdir(tmp)):
+    if not cb.endswith('.cubin') or '-' in cb:
+        continue
+    asm = subprocess.run(['nvdisasm', '--print-line-info', os.path.join(tmp, cb)], capture_output=True, text=True).stdout
+    cur = None; line = 0; fn = None
+    for ln in asm.split('\n'):
+        m = re.match(r'\s*\.section\s+\.text\.(\S+?),', ln)
+        if m:
+            fn = m.group(1); cur = [] if re.search(kern, fn) else None
+            if cur is not None:
+                lines.append((fn, cur))
+            continue
+        if cur is None:
+            continue
+        m = re.search(r'//## File ".*?", line (\d+)', ln)
+        if m:
+            line = int(m.group(1)); continue
+        if re.match(r'\s*/\*[0-9a-f]{4,}\*/\s+\S', ln):
+            cur.append(line)
+best = None
+for fn, l in lines:
+    if len(l) == len(data):
+        best = l
+if best is None:
+    print('could not align SASS listings:', [(fn, len(l)) for fn, l in lines], len(data)); sys.exit(1)
+src = open(os.path.join(os.path.dirname(so), 'csrc', 'extractor.cu' if 'extract' not in kern and False else
+                        ('matcher.cu' if re.search('knn|search|grid|rot|ratio|popc|descriptor_distance', kern) else 'extractor.cu'))).read().split('\n')
+agg = {}
+for r, ln in zip(data, best):
+    a = agg.setdefault(ln, [0, 0, 0])
+    a[0] += int(r[iI] or 0); a[1] += int(r[iT] or 0); a[2] += int(r[iN] or 0)
+tot = sum(a[0] for a in agg.values()); tots = sum(a[2] for a in agg.values())
+print('kernel', kern, 'SASS instructions', len(data), 'warp-instr executed', tot, 'samples', tots)
+for ln, a in sorted(agg.items(), key=lambda kv: -kv[1][0])[:top]:
+    text = src[ln - 1].strip()[:110] if 0 < ln <= len(src) else ''
+    print('%5.1f%% inst %5.1f%% smp thr/warp=%4.1f  L%-4d %s' % (a[0] * 100 / max(tot, 1), a[2] * 100 / max(tots, 1), a[1] / max(a[0], 1), ln, text))

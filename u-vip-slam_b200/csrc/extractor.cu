@@ -34,7 +34,7 @@ struct LevelInfo {
     int quota;                // mnFeaturesPerLevel
     int raw_cap, raw_off;     // candidate list (u32 entries) inside the frame's candidate block
     int kp_cap, kp_off;       // quadtree winners
-    int ftile_off, fntx, fnty;    // FAST tiles over the detection region
+    int ftile_off, fntx, fnty, fcw;   // FAST tiles: fcw (1 or 2) cells wide, one cell high
     int btile_off, bntx, bnty;    // blur tiles
     int tab_off;              // offset of this level's resize tables
     int nini;                 // quadtree roots
@@ -49,6 +49,7 @@ struct Plan {
     int cells_per_frame, raw_per_frame, kp_per_frame;
     int ftiles, btiles;
     int node_cap;             // quadtree node capacity (power of two)
+    int f_irow, f_irows, f_srow, f_srows, f_qcap, f_ocap;   // FAST shared-memory carve-up (largest tile over all levels)
     unsigned long long frame_bytes;
     LevelInfo lv[MAXLEV];
 };
@@ -139,155 +140,237 @@ k_resize(uint8_t* __restrict__ pyr, const int* __restrict__ tabs, int level, con
 }
 
 // --------------------------------------------------------------------------------------------------------
-// K2+K3: FAST-9/16.  One CTA per 64x32 tile of a level's detection region [16,w-16)x[16,h-16).
-//   A  stage the tile + 4 px halo in shared memory (32-bit loads)
-//   B  cheap rejection on the opposite-pixel pairs (0,8) and (4,12) -> queue of surviving positions
-//   C  dense pass over the queue: 16-bit brighter/darker ring masks, 9-contiguous test, exact score
-//      s = max_arc min_k |ring_k - v| - 1  (== OpenCV cornerScore) into a shared score map
-//   D  cell-local 3x3 NMS (neighbours in another 30-px cell count as 0, src/ORBextractor.cc:772-799 runs FAST
-//      per cell ROI), survivors with s >= tmin are appended to the (frame, level) candidate list and raise the
-//      per-cell maximum that decides between fastTh and the retry threshold later (K4).
+// K2+K3: FAST-9/16 exactly as the reference runs it: cv::FAST(th, nms=true) per 30-px cell ROI, and a second run at
+// the retry threshold when a cell returned nothing (src/ORBextractor.cc:772-812).  One CTA per tile of up to two
+// horizontally adjacent cells (cell-aligned, so the empty-cell decision never leaves the CTA):
+//   A  stage the tile + 3 px halo in shared memory with aligned 32-bit loads
+//   B  SWAR corner test, 4 pixels per thread per step: ring pixel k of 4 neighbouring pixels is one funnel-shifted
+//      32-bit word; "brighter than v+t" / "darker than v-t" are per-byte carry tricks (3 ALU ops per word each);
+//      opposite ring pairs are tested progressively (a 9-arc contains one pixel of every opposite pair) so flat and
+//      gradient regions leave after 2..8 of the 16 ring words; only then the 9-contiguity AND-chains run
+//   C  exact score s = max_arc min_k |ring_k - v| - 1 (== OpenCV cornerScore) for the queued corners (DPX min3/max3)
+//   D  3x3 strict NMS inside the cell, survivors appended to the (frame, level) raw-corner list
+// Pass 2 repeats B..D at the retry threshold for the cells of the tile that produced no survivor.
 // --------------------------------------------------------------------------------------------------------
-constexpr int FT_W = 64, FT_H = 32;
-constexpr int FI_W = FT_W + 8, FI_H = FT_H + 8;      // image tile with 4 px halo
-constexpr int FS_W = FT_W + 2, FS_H = FT_H + 2;      // score tile with 1 px halo
-constexpr int FS_STRIDE = 68;
-constexpr int FAST_OUT_CAP = 768;
+__device__ __forceinline__ unsigned swar_gt(unsigned a, unsigned b, unsigned nb7)
+{   // bit 7 of every byte: a > b (unsigned bytes); nb7 = ~b & 0x7f7f7f7f precomputed
+    const unsigned s = (a & 0x7f7f7f7fu) + nb7;
+    return (a & ~b) | (~(a ^ b) & s);
+}
+__device__ __forceinline__ unsigned swar_lt(unsigned a, unsigned b, unsigned b7)
+{   // bit 7 of every byte: a < b; b7 = b & 0x7f7f7f7f precomputed
+    const unsigned s = b7 + (~a & 0x7f7f7f7fu);
+    return (b & ~a) | (~(a ^ b) & s);
+}
 
-__device__ __forceinline__ int cyc_contig9(unsigned m)   // m: 16-bit ring mask; nonzero iff >= 9 contiguous (cyclic) bits
+// corner flags (bit 7 per byte) of the 4 pixels whose centre word is W[0]; rs = row stride in words
+__device__ __forceinline__ unsigned fast_swar4(const unsigned* __restrict__ W, int rs, unsigned t4, unsigned valid)
 {
-    unsigned r = m | (m << 16);
-    r &= r >> 1;        // runs >= 2
-    r &= r >> 2;        // runs >= 4
-    r &= r >> 4;        // runs >= 8
-    r &= (m | (m << 16)) >> 8;   // runs >= 9
-    return (r & 0xFFFFu) != 0;
+    const unsigned v = W[0];
+    const unsigned hi = __vaddus4(v, t4), lo = __vsubus4(v, t4);
+    const unsigned nhi7 = ~hi & 0x7f7f7f7fu, lo7 = lo & 0x7f7f7f7fu;
+    unsigned b[16], d[16];
+#define RING(k, word) do { const unsigned r_ = (word); b[k] = swar_gt(r_, hi, nhi7); d[k] = swar_lt(r_, lo, lo7); } while (0)
+    RING(0, W[3 * rs]);
+    RING(8, W[-3 * rs]);
+    unsigned pb = b[0] | b[8], pd = d[0] | d[8];
+    if (((pb | pd) & valid) == 0) return 0;
+    {
+        const unsigned l = W[-1], c = v, r = W[1];
+        RING(4, __funnelshift_r(c, r, 24));
+        RING(12, __funnelshift_r(l, c, 8));
+    }
+    pb &= b[4] | b[12]; pd &= d[4] | d[12];
+    if (((pb | pd) & valid) == 0) return 0;
+    {
+        const unsigned* p = W + 2 * rs; const unsigned* q = W - 2 * rs;
+        RING(2, __funnelshift_r(p[0], p[1], 16));
+        RING(14, __funnelshift_r(p[-1], p[0], 16));
+        RING(6, __funnelshift_r(q[0], q[1], 16));
+        RING(10, __funnelshift_r(q[-1], q[0], 16));
+    }
+    pb &= (b[2] | b[10]) & (b[6] | b[14]); pd &= (d[2] | d[10]) & (d[6] | d[14]);
+    if (((pb | pd) & valid) == 0) return 0;
+    {
+        const unsigned* p = W + 3 * rs; const unsigned* q = W - 3 * rs;
+        RING(1, __funnelshift_r(p[0], p[1], 8));
+        RING(15, __funnelshift_r(p[-1], p[0], 24));
+        RING(7, __funnelshift_r(q[0], q[1], 8));
+        RING(9, __funnelshift_r(q[-1], q[0], 24));
+        p = W + rs; q = W - rs;
+        RING(3, __funnelshift_r(p[0], p[1], 24));
+        RING(13, __funnelshift_r(p[-1], p[0], 8));
+        RING(5, __funnelshift_r(q[0], q[1], 24));
+        RING(11, __funnelshift_r(q[-1], q[0], 8));
+    }
+#undef RING
+    pb &= (b[1] | b[9]) & (b[3] | b[11]) & (b[5] | b[13]) & (b[7] | b[15]);
+    pd &= (d[1] | d[9]) & (d[3] | d[11]) & (d[5] | d[13]) & (d[7] | d[15]);
+    unsigned out = 0;
+    if (pb & valid) {
+        unsigned c3[16];
+#pragma unroll
+        for (int k = 0; k < 16; k++) c3[k] = b[k] & b[(k + 1) & 15] & b[(k + 2) & 15];
+#pragma unroll
+        for (int k = 0; k < 16; k++) out |= c3[k] & c3[(k + 3) & 15] & c3[(k + 6) & 15];
+    }
+    if (pd & valid) {
+        unsigned c3[16];
+#pragma unroll
+        for (int k = 0; k < 16; k++) c3[k] = d[k] & d[(k + 1) & 15] & d[(k + 2) & 15];
+#pragma unroll
+        for (int k = 0; k < 16; k++) out |= c3[k] & c3[(k + 3) & 15] & c3[(k + 6) & 15];
+    }
+    return out & valid;
 }
 
 __global__ void __launch_bounds__(256)
 k_fast(const uint8_t* __restrict__ pyr, unsigned* __restrict__ cand, int* __restrict__ cand_count,
-       int* __restrict__ cellmax, int* __restrict__ status, const __grid_constant__ Plan P)
+       int* __restrict__ status, const __grid_constant__ Plan P)
 {
-    __shared__ __align__(16) uint8_t s_img[FI_H][FI_W];
-    __shared__ uint8_t s_score[FS_H][FS_STRIDE];
-    __shared__ unsigned short s_queue[FS_W * FS_H];
-    __shared__ unsigned s_out[FAST_OUT_CAP];          // survivors of this tile (NMS => ~1 per 2x2 inside a cell)
-    __shared__ int s_nq, s_nout, s_base;
+    extern __shared__ __align__(16) unsigned char s_fast[];
+    __shared__ int s_nq, s_nout, s_base, s_surv[2];
+    __shared__ unsigned s_colvalid[64];
 
-    // which level / tile
     int level = 0;
     const int tile = blockIdx.x;
 #pragma unroll 1
     for (int l = 1; l < P.nlevels; l++) if (tile >= P.lv[l].ftile_off) level = l;
     const LevelInfo& L = P.lv[level];
-    const int f = blockIdx.y;
+    const int f = blockIdx.y, tid = threadIdx.x;
     const int tl = tile - L.ftile_off;
-    const int tx0 = EDGE + (tl % L.fntx) * FT_W, ty0 = EDGE + (tl / L.fntx) * FT_H;   // tile origin, level coords
-    const int tid = threadIdx.x;
+    const int cy = tl / L.fntx, cx0 = (tl - cy * L.fntx) * L.fcw;
+    const int ncell = min(L.fcw, L.ncols - cx0);
+    const int xend = L.w - EDGE, yend = L.h - EDGE;
+    const int X0 = EDGE + cx0 * L.wcell, Xs = X0 + L.wcell, X1 = min(EDGE + (cx0 + ncell) * L.wcell, xend);
+    const int Y0 = EDGE + cy * L.hcell, Y1 = min(Y0 + L.hcell, yend);
+    if (X0 >= X1 || Y0 >= Y1) return;
+    // shared-memory carve-up (sizes from the plan: the largest tile over all levels)
+    const int irow = P.f_irow;                 // image row stride, bytes (multiple of 4)
+    const int srow = P.f_srow;                 // score row stride, bytes
+    unsigned* s_img = reinterpret_cast<unsigned*>(s_fast);
+    uint8_t* s_score = s_fast + (size_t)irow * P.f_irows;
+    unsigned short* s_queue = reinterpret_cast<unsigned short*>(s_score + (size_t)srow * P.f_srows);
+    unsigned* s_out = reinterpret_cast<unsigned*>(s_queue + P.f_qcap);
+
+    const int gx0 = X0 & ~3, gxe = (X1 - 1) & ~3;          // first / last 4-pixel group (image coords)
+    const int ngx = ((gxe - gx0) >> 2) + 1;
+    const int ax0 = gx0 - 4, ay0 = Y0 - 3;                // image coords of s_img[0][0]
+    const int ncw = ngx + 2, nrows_img = (Y1 - Y0) + 6;
+    const int rsw = irow >> 2;
     const uint8_t* inner = pyr + (size_t)f * P.frame_bytes + L.poff + (size_t)EDGE * L.pstride + EDGE;
-
-    if (tid == 0) { s_nq = 0; s_nout = 0; }
-    // A: load (tx0-4 .. tx0+68) x (ty0-4 .. ty0+36); x origin is 4-byte aligned
-    for (int i = tid; i < FI_H * (FI_W / 4); i += 256) {
-        const int r = i / (FI_W / 4), c = i % (FI_W / 4);
-        const int y = ty0 - 4 + r, x = tx0 - 4 + c * 4;
-        unsigned v = 0;
-        if (y < L.h + EDGE && x + 4 <= L.pstride - EDGE) v = __ldg(reinterpret_cast<const unsigned*>(inner + (ptrdiff_t)y * L.pstride + x));
-        *reinterpret_cast<unsigned*>(&s_img[r][c * 4]) = v;
+    if (tid == 0) { s_nout = 0; s_surv[0] = 0; s_surv[1] = 0; }
+    // A: stage
+    {
+        const unsigned rcp = 0xFFFFFFFFu / (unsigned)ncw + 1u;
+        for (int i = tid; i < nrows_img * ncw; i += 256) {
+            const int r = __umulhi((unsigned)i, rcp), c = i - r * ncw;
+            const int y = ay0 + r, x = ax0 + 4 * c;
+            unsigned v = 0;
+            if (x >= -EDGE && x + 4 <= L.pstride - EDGE) v = __ldg(reinterpret_cast<const unsigned*>(inner + (ptrdiff_t)y * L.pstride + x));
+            s_img[r * rsw + c] = v;
+        }
+        for (int i = tid; i < (srow * P.f_srows) >> 2; i += 256) reinterpret_cast<unsigned*>(s_score)[i] = 0;
     }
-    for (int i = tid; i < FS_H * FS_STRIDE / 4; i += 256) reinterpret_cast<unsigned*>(&s_score[0][0])[i] = 0;
-    __syncthreads();
+    const int nrows = Y1 - Y0, ngroups = ngx * nrows;
+    const unsigned rcpg = 0xFFFFFFFFu / (unsigned)ngx + 1u;
 
-    const int xmax = L.w - EDGE, ymax = L.h - EDGE;     // detection region end (exclusive)
-    const int t = P.tmin;
-    // B: quick rejection over the score tile (tile + 1 px ring)
-    for (int i = tid; i < FS_W * FS_H; i += 256) {
-        const int sy = i / FS_W, sx = i % FS_W;
-        const int x = tx0 - 1 + sx, y = ty0 - 1 + sy;
-        bool pass = false;
-        if (x >= EDGE && x < xmax && y >= EDGE && y < ymax) {
-            const int iy = sy + 3, ix = sx + 3;       // position inside s_img
-            const int v = s_img[iy][ix];
-            const int p0 = s_img[iy + 3][ix], p8 = s_img[iy - 3][ix];
-            const int lo = v - t, hi = v + t;
-            // a 9-arc contains one pixel of every opposite pair; if both are within +-t the pixel is no corner
-            const bool in08 = (p0 >= lo && p0 <= hi) && (p8 >= lo && p8 <= hi);
-            if (!in08) {
-                const int p4 = s_img[iy][ix + 3], p12 = s_img[iy][ix - 3];
-                const bool in412 = (p4 >= lo && p4 <= hi) && (p12 >= lo && p12 <= hi);
-                pass = !in412;
+    for (int pass = 0; pass < 2; pass++) {
+        const int t = pass ? P.t2 : P.t1;
+        __syncthreads();                                   // staging / previous pass complete
+        bool act0 = true, act1 = ncell > 1;
+        if (pass) {
+            if (P.t2 >= P.t1) break;                       // the retry cannot add anything (uniform)
+            act0 = s_surv[0] == 0; act1 = (ncell > 1) && s_surv[1] == 0;
+            if (!act0 && !act1) break;                     // uniform
+        }
+        // per-group-column byte masks: inside [X0,X1) and in a cell evaluated in this pass
+        if (tid < ngx) {
+            unsigned m = 0;
+            for (int bb = 0; bb < 4; bb++) {
+                const int x = gx0 + 4 * tid + bb;
+                const bool in = x >= X0 && x < X1 && ((x < Xs) ? act0 : act1);
+                if (in) m |= 0x80u << (8 * bb);
+            }
+            s_colvalid[tid] = m;
+        }
+        if (tid == 0) s_nq = 0;
+        __syncthreads();
+        // B: SWAR corner test
+        const unsigned t4 = (unsigned)t * 0x01010101u;
+        for (int g = tid; g < ngroups; g += 256) {
+            const int r = __umulhi((unsigned)g, rcpg), c = g - r * ngx;
+            const unsigned valid = s_colvalid[c];
+            if (!valid) continue;
+            unsigned cf = fast_swar4(s_img + (r + 3) * rsw + (c + 1), rsw, t4, valid);
+            while (cf) {
+                const int bb = (__ffs(cf) - 1) >> 3;
+                cf &= cf - 1;
+                const int slot = atomicAdd(&s_nq, 1);
+                s_queue[slot] = (unsigned short)((r + 1) * srow + (gx0 + 4 * c + bb - X0 + 1));
             }
         }
-        if (pass) { const int slot = atomicAdd(&s_nq, 1); s_queue[slot] = (unsigned short)i; }
-    }
-    __syncthreads();
-    const int nq = s_nq;
-    // C: full test + score
-    for (int qi = tid; qi < nq; qi += 256) {
-        const int i = s_queue[qi];
-        const int sy = i / FS_W, sx = i % FS_W;
-        const int iy = sy + 3, ix = sx + 3;
-        const int v = s_img[iy][ix];
-        int d[16];
-        d[0] = s_img[iy + 3][ix] - v;      d[1] = s_img[iy + 3][ix + 1] - v;  d[2] = s_img[iy + 2][ix + 2] - v;  d[3] = s_img[iy + 1][ix + 3] - v;
-        d[4] = s_img[iy][ix + 3] - v;      d[5] = s_img[iy - 1][ix + 3] - v;  d[6] = s_img[iy - 2][ix + 2] - v;  d[7] = s_img[iy - 3][ix + 1] - v;
-        d[8] = s_img[iy - 3][ix] - v;      d[9] = s_img[iy - 3][ix - 1] - v;  d[10] = s_img[iy - 2][ix - 2] - v; d[11] = s_img[iy - 1][ix - 3] - v;
-        d[12] = s_img[iy][ix - 3] - v;     d[13] = s_img[iy + 1][ix - 3] - v; d[14] = s_img[iy + 2][ix - 2] - v; d[15] = s_img[iy + 3][ix - 1] - v;
-        unsigned mb = 0, md = 0;
+        __syncthreads();
+        const int nq = s_nq;
+        // C: exact score
+        for (int qi = tid; qi < nq; qi += 256) {
+            const int pos = s_queue[qi];
+            const int sy = pos / srow, sx = pos - sy * srow;
+            const uint8_t* pc = reinterpret_cast<const uint8_t*>(s_img) + (sy - 1 + 3) * irow + (sx - 1 + X0 - ax0);
+            const int v = pc[0];
+            int d[16];
+            d[0] = pc[3 * irow] - v;       d[1] = pc[3 * irow + 1] - v;   d[2] = pc[2 * irow + 2] - v;   d[3] = pc[irow + 3] - v;
+            d[4] = pc[3] - v;              d[5] = pc[-irow + 3] - v;      d[6] = pc[-2 * irow + 2] - v;  d[7] = pc[-3 * irow + 1] - v;
+            d[8] = pc[-3 * irow] - v;      d[9] = pc[-3 * irow - 1] - v;  d[10] = pc[-2 * irow - 2] - v; d[11] = pc[-irow - 3] - v;
+            d[12] = pc[-3] - v;            d[13] = pc[irow - 3] - v;      d[14] = pc[2 * irow - 2] - v;  d[15] = pc[3 * irow - 1] - v;
+            int mn3[16], mx3[16];
 #pragma unroll
-        for (int k = 0; k < 16; k++) { mb |= (unsigned)(d[k] > t) << k; md |= (unsigned)(d[k] < -t) << k; }
-        if (!(cyc_contig9(mb) | cyc_contig9(md))) continue;
-        // exact score: A = max over 9-arcs of min(d), B = max over 9-arcs of min(-d); 9-windows as 3x3 min3/max3
-        int mn3[16], mx3[16];
+            for (int k = 0; k < 16; k++) {
+                mn3[k] = __vimin3_s32(d[k], d[(k + 1) & 15], d[(k + 2) & 15]);
+                mx3[k] = __vimax3_s32(d[k], d[(k + 1) & 15], d[(k + 2) & 15]);
+            }
+            int A = -256, Bn = 256;
 #pragma unroll
-        for (int k = 0; k < 16; k++) {
-            mn3[k] = __vimin3_s32(d[k], d[(k + 1) & 15], d[(k + 2) & 15]);
-            mx3[k] = __vimax3_s32(d[k], d[(k + 1) & 15], d[(k + 2) & 15]);
+            for (int k = 0; k < 16; k++) {
+                A = max(A, __vimin3_s32(mn3[k], mn3[(k + 3) & 15], mn3[(k + 6) & 15]));
+                Bn = min(Bn, __vimax3_s32(mx3[k], mx3[(k + 3) & 15], mx3[(k + 6) & 15]));
+            }
+            s_score[pos] = (uint8_t)(max(A, -Bn) - 1);     // >= t >= 1 for a corner at t
         }
-        int A = -256, Bn = 256;
-#pragma unroll
-        for (int k = 0; k < 16; k++) {
-            A = max(A, __vimin3_s32(mn3[k], mn3[(k + 3) & 15], mn3[(k + 6) & 15]));
-            Bn = min(Bn, __vimax3_s32(mx3[k], mx3[(k + 3) & 15], mx3[(k + 6) & 15]));
+        __syncthreads();
+        // D: strict 3x3 NMS inside the cell (positions outside the cell interior count as 0)
+        for (int qi = tid; qi < nq; qi += 256) {
+            const int pos = s_queue[qi];
+            const int sy = pos / srow, sx = pos - sy * srow;
+            const int x = X0 + sx - 1, y = Y0 + sy - 1;
+            const int cell = x >= Xs ? 1 : 0;
+            const int cxa = cell ? Xs : X0, cxb = cell ? X1 : min(Xs, X1);
+            const int s = s_score[pos];
+            const bool hasL = x > cxa, hasR = x + 1 < cxb, hasU = y > Y0, hasD = y + 1 < Y1;
+            const uint8_t* sp = s_score + pos;
+            bool keep = true;
+            if (hasL) keep &= s > sp[-1];
+            if (hasR) keep &= s > sp[1];
+            if (hasU) {
+                keep &= s > sp[-srow];
+                if (hasL) keep &= s > sp[-srow - 1];
+                if (hasR) keep &= s > sp[-srow + 1];
+            }
+            if (hasD) {
+                keep &= s > sp[srow];
+                if (hasL) keep &= s > sp[srow - 1];
+                if (hasR) keep &= s > sp[srow + 1];
+            }
+            if (!keep) continue;
+            const int slot = atomicAdd(&s_nout, 1);
+            if (slot < P.f_ocap) s_out[slot] = (unsigned)x | ((unsigned)y << 12) | ((unsigned)s << 24);
+            atomicAdd(&s_surv[cell], 1);
         }
-        const int s = max(A, -Bn) - 1;
-        s_score[sy][sx] = (uint8_t)s;                 // s >= tmin >= 1 here
-    }
-    __syncthreads();
-    // D: cell-local NMS over queued positions inside the tile proper
-    for (int qi = tid; qi < nq; qi += 256) {
-        const int i = s_queue[qi];
-        const int sy = i / FS_W, sx = i % FS_W;
-        if (sx < 1 || sx > FT_W || sy < 1 || sy > FT_H) continue;
-        const int s = s_score[sy][sx];
-        if (s == 0) continue;
-        const int x = tx0 - 1 + sx, y = ty0 - 1 + sy;
-        const int cx = (x - EDGE) / L.wcell, cy = (y - EDGE) / L.hcell;
-        const int rx = (x - EDGE) - cx * L.wcell, ry = (y - EDGE) - cy * L.hcell;
-        const bool hasL = rx > 0, hasR = (rx < L.wcell - 1) && (x + 1 < xmax);
-        const bool hasU = ry > 0, hasD = (ry < L.hcell - 1) && (y + 1 < ymax);
-        bool keep = true;
-        if (hasL) keep &= s > s_score[sy][sx - 1];
-        if (hasR) keep &= s > s_score[sy][sx + 1];
-        if (hasU) {
-            keep &= s > s_score[sy - 1][sx];
-            if (hasL) keep &= s > s_score[sy - 1][sx - 1];
-            if (hasR) keep &= s > s_score[sy - 1][sx + 1];
-        }
-        if (hasD) {
-            keep &= s > s_score[sy + 1][sx];
-            if (hasL) keep &= s > s_score[sy + 1][sx - 1];
-            if (hasR) keep &= s > s_score[sy + 1][sx + 1];
-        }
-        if (!keep) continue;
-        const int slot = atomicAdd(&s_nout, 1);
-        if (slot < FAST_OUT_CAP) s_out[slot] = (unsigned)x | ((unsigned)y << 12) | ((unsigned)s << 24);
-        atomicMax(&cellmax[(size_t)f * P.cells_per_frame + L.cell_off + cy * L.ncols + cx], s);
     }
     __syncthreads();
     const int nout = s_nout;
     if (nout == 0) return;
-    if (nout > FAST_OUT_CAP) { if (tid == 0) atomicOr(status, 1); return; }
+    if (nout > P.f_ocap) { if (tid == 0) atomicOr(status, 1); return; }
     int* cnt = cand_count + (size_t)f * P.nlevels + level;
     if (tid == 0) s_base = atomicAdd(cnt, nout);
     __syncthreads();
@@ -359,14 +442,13 @@ __device__ __forceinline__ int quadrant(const int* pb, int x, int y)
 }
 
 __global__ void __launch_bounds__(QT_THREADS)
-k_quadtree(const unsigned* __restrict__ cand, const int* __restrict__ cand_count, const int* __restrict__ cellmax,
-           unsigned* __restrict__ keys, int* __restrict__ key_count, unsigned short* __restrict__ labels,
+k_quadtree(const unsigned* __restrict__ cand, const int* __restrict__ cand_count, unsigned short* __restrict__ labels,
            unsigned* __restrict__ winners, int* __restrict__ win_count, int* __restrict__ status,
            const __grid_constant__ Plan P)
 {
     extern __shared__ int s_dyn[];
     __shared__ int s_warp[QT_THREADS / 32];
-    __shared__ int s_n, s_nexp, s_ncand, s_ndiv;
+    __shared__ int s_nexp, s_ncand, s_ndiv;
 
     const int level = blockIdx.x, f = blockIdx.y;
     const LevelInfo& L = P.lv[level];
@@ -382,35 +464,10 @@ k_quadtree(const unsigned* __restrict__ cand, const int* __restrict__ cand_count
         S.sortk = reinterpret_cast<unsigned*>(p); p += cap;
         S.best_score = p; p += cap; S.best_okey = reinterpret_cast<unsigned*>(p); p += cap;
     }
-    const unsigned* cin = cand + (size_t)f * P.raw_per_frame + L.raw_off;
-    unsigned* kk = keys + (size_t)f * P.raw_per_frame + L.raw_off;
+    const unsigned* kk = cand + (size_t)f * P.raw_per_frame + L.raw_off;     // raw corners of this (frame, level), any order
     unsigned short* lab = labels + (size_t)f * P.raw_per_frame + L.raw_off;
-    const int* cmax = cellmax + (size_t)f * P.cells_per_frame + L.cell_off;
-    const int ncand_in = min(cand_count[(size_t)f * P.nlevels + level], L.raw_cap);
+    const int n = min(cand_count[(size_t)f * P.nlevels + level], L.raw_cap);
     const int N = L.quota;
-
-    // ---- a. cell rule: a cell keeps its fastTh corners, or — if it has none — its retry-threshold corners
-    if (tid == 0) s_n = 0;
-    __syncthreads();
-    for (int i0 = 0; i0 < ncand_in; i0 += QT_THREADS) {
-        const int i = i0 + tid;
-        bool keep = false; unsigned c = 0;
-        if (i < ncand_in) {
-            c = cin[i];
-            const int x = c & 0xFFF, y = (c >> 12) & 0xFFF, s = c >> 24;
-            const int cx = (x - EDGE) / L.wcell, cy = (y - EDGE) / L.hcell;
-            const int m = cmax[cy * L.ncols + cx];
-            keep = (s >= P.t1) || (m < P.t1 && s >= P.t2);
-        }
-        const unsigned bal = __ballot_sync(0xFFFFFFFFu, keep);
-        int wbase = 0;
-        if ((tid & 31) == 0 && bal) wbase = atomicAdd(&s_n, __popc(bal));
-        wbase = __shfl_sync(0xFFFFFFFFu, wbase, 0);
-        if (keep) kk[wbase + __popc(bal & ((1u << (tid & 31)) - 1))] = c;
-    }
-    __syncthreads();
-    const int n = s_n;
-    if (tid == 0) key_count[(size_t)f * P.nlevels + level] = n;
     unsigned* wout = winners + (size_t)f * P.kp_per_frame + L.kp_off;
     if (n == 0) { if (tid == 0) win_count[(size_t)f * P.nlevels + level] = 0; return; }
 
@@ -833,7 +890,7 @@ struct uvip_extractor {
     Plan plan;                 // for (plan.W, plan.H); W == 0 -> none yet
     // working set sized for (max_width, max_height, max_batch)
     size_t cap_frame_bytes = 0; int cap_cells = 0, cap_raw = 0, cap_kp = 0, cap_tab = 0;
-    DevBuf pyr, blur, cand, keys, labels, winners, counters, cellmax, sel, nsel, tabs, status, grid, incoming;
+    DevBuf pyr, blur, cand, labels, winners, counters, sel, nsel, tabs, status, grid, incoming;
     DevBuf in_frames, out_kps, out_desc, out_n;      // staging for the host-buffer entry points
     int sel_cap = 0;
     int last_frames = 0;
@@ -875,7 +932,7 @@ static int make_plan(const uvip_extractor* ex, int w, int h, Plan* out, std::vec
     P.t1 = p.fast_th > 1 ? p.fast_th : 1; P.t2 = p.retry_th > 1 ? p.retry_th : 1;
     P.tmin = P.t1 < P.t2 ? P.t1 : P.t2;
     if (P.t1 > 254 || P.t2 > 254) { set_last_error("FAST thresholds above 254 are unsupported"); return UVIP_ERR_UNSUPPORTED; }
-    size_t off = 0; int cells = 0, raw = 0, kp = 0, ft = 0, bt = 0, tab = 0, maxN = 0;
+    size_t off = 0; int cells = 0, raw = 0, kp = 0, ft = 0, bt = 0, tab = 0, maxN = 0, max_tw = 0, max_th = 0;
     for (int l = 0; l < p.nlevels; l++) {
         LevelInfo& L = P.lv[l];
         L.w = cv_round_f((float)w * ex->inv_scale[l]);          // src/ORBextractor.cc:968
@@ -894,7 +951,7 @@ static int make_plan(const uvip_extractor* ex, int w, int h, Plan* out, std::vec
         L.ncols = (int)(width / Wc); L.nrows = (int)(height / Wc);
         if (L.ncols < 1 || L.nrows < 1) { set_last_error("level %d has no FAST cell", l); return UVIP_ERR_UNSUPPORTED; }
         L.wcell = (int)ceilf(width / L.ncols); L.hcell = (int)ceilf(height / L.nrows);
-        if (L.wcell > 127 || L.hcell > 127) { set_last_error("cell larger than 127 px"); return UVIP_ERR_UNSUPPORTED; }
+        if (L.wcell > 64 || L.hcell > 64) { set_last_error("FAST cell larger than 64 px"); return UVIP_ERR_UNSUPPORTED; }
         L.cell_off = cells; cells += L.ncols * L.nrows;
         L.quota = ex->quota[l]; if (L.quota > maxN) maxN = L.quota;
         const int area = (L.w - 2 * EDGE) * (L.h - 2 * EDGE);
@@ -906,8 +963,11 @@ static int make_plan(const uvip_extractor* ex, int w, int h, Plan* out, std::vec
         L.hx = (float)(maxBX - minB) / (float)L.nini;
         L.kp_cap = (L.quota + 4 > 4 * L.nini ? L.quota + 4 : 4 * L.nini);
         L.kp_off = kp; kp += L.kp_cap;
-        L.fntx = div_up(L.w - 2 * EDGE, FT_W); L.fnty = div_up(L.h - 2 * EDGE, FT_H);
+        L.fcw = L.ncols > 1 ? 2 : 1;
+        L.fntx = div_up(L.ncols, L.fcw); L.fnty = L.nrows;
         L.ftile_off = ft; ft += L.fntx * L.fnty;
+        if (L.fcw * L.wcell > max_tw) max_tw = L.fcw * L.wcell;
+        if (L.hcell > max_th) max_th = L.hcell;
         L.bntx = div_up(L.w + 2 * BORDER_W, BT_W); L.bnty = div_up(L.h + 2 * BORDER_W, BT_H);
         L.btile_off = bt; bt += L.bntx * L.bnty;
         L.tab_off = tab; if (l > 0) tab += 2 * L.w + 2 * L.h;
@@ -920,6 +980,12 @@ static int make_plan(const uvip_extractor* ex, int w, int h, Plan* out, std::vec
     for (int l = 0; l < p.nlevels; l++) while (nc < 4 * P.lv[l].nini + 4) nc <<= 1;
     if (nc > 4096) { set_last_error("per-level quota %d exceeds the quadtree node capacity", maxN); return UVIP_ERR_UNSUPPORTED; }
     P.node_cap = nc;
+    {
+        const int ngx_max = (max_tw + 2) / 4 + 1;
+        P.f_irow = 4 * (ngx_max + 2); P.f_irows = max_th + 6;
+        P.f_srow = (int)align_up((size_t)max_tw + 2, 4); P.f_srows = max_th + 2;
+        P.f_qcap = (max_tw * max_th + 1) & ~1; P.f_ocap = P.f_qcap / 3 + 64;
+    }
     if (tabs) {
         tabs->assign(tab > 0 ? tab : 1, 0);
         for (int l = 1; l < p.nlevels; l++) {
@@ -933,6 +999,7 @@ static int make_plan(const uvip_extractor* ex, int w, int h, Plan* out, std::vec
     return UVIP_OK;
 }
 
+static size_t fast_smem_bytes(const Plan& P) { return (size_t)P.f_irow * P.f_irows + (size_t)P.f_srow * P.f_srows + 2 * (size_t)P.f_qcap + 4 * (size_t)P.f_ocap; }
 static size_t qt_smem_bytes(int cap) { return (size_t)(4 * cap * 2 + cap * 2 + 4 * cap + cap + cap + (cap + 1) + cap + 4 * cap + cap + cap + cap) * 4; }
 
 static int ensure_plan(uvip_extractor* ex, int w, int h)
@@ -949,6 +1016,7 @@ static int ensure_plan(uvip_extractor* ex, int w, int h)
     }
     UVIP_CUDA(cudaStreamSynchronize(ex->stream));
     UVIP_CUDA(cudaFuncSetAttribute(k_quadtree, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)qt_smem_bytes(P.node_cap)));
+    UVIP_CUDA(cudaFuncSetAttribute(k_fast, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)fast_smem_bytes(P)));
     UVIP_CUDA(cudaMemcpy(ex->tabs.p, tabs.data(), tabs.size() * sizeof(int), cudaMemcpyHostToDevice));
     ex->plan = P;
     return UVIP_OK;
@@ -963,9 +1031,8 @@ static int enqueue_group(uvip_extractor* ex, const uint8_t* d_frames, int nframe
     uint8_t* pyr = ex->pyr.as<uint8_t>(); uint8_t* blur = ex->blur.as<uint8_t>();
     int* counters = ex->counters.as<int>();
     const size_t cstride = (size_t)ex->prm.max_batch * P.nlevels;
-    int* cand_count = counters; int* key_count = counters + cstride; int* win_count = counters + 2 * cstride;
-    UVIP_CUDA(cudaMemsetAsync(counters, 0, 3 * cstride * sizeof(int), st));
-    UVIP_CUDA(cudaMemsetAsync(ex->cellmax.p, 0, (size_t)nframes * P.cells_per_frame * sizeof(int), st));
+    int* cand_count = counters; int* win_count = counters + cstride;
+    UVIP_CUDA(cudaMemsetAsync(counters, 0, 2 * cstride * sizeof(int), st));
     UVIP_CUDA(cudaMemsetAsync(ex->status.p, 0, sizeof(int), st));
     cudaEvent_t* pe = ex->prof ? ex->prof_ev.data() + (size_t)(ex->prof_groups % PROF_RING) * (UVIP_NUM_STAGES + 1) : nullptr;
 #define PROF_MARK(i) do { if (pe) UVIP_CUDA(cudaEventRecord(pe[i], st)); } while (0)
@@ -983,12 +1050,12 @@ static int enqueue_group(uvip_extractor* ex, const uint8_t* d_frames, int nframe
         ex->launches++;
     }
     PROF_MARK(1);
-    k_fast<<<dim3(P.ftiles, nframes), 256, 0, st>>>(pyr, ex->cand.as<unsigned>(), cand_count, ex->cellmax.as<int>(), ex->status.as<int>(), P);
+    k_fast<<<dim3(P.ftiles, nframes), 256, fast_smem_bytes(P), st>>>(pyr, ex->cand.as<unsigned>(), cand_count, ex->status.as<int>(), P);
     ex->launches++;
     PROF_MARK(2);
     k_quadtree<<<dim3(P.nlevels, nframes), QT_THREADS, qt_smem_bytes(P.node_cap), st>>>(
-        ex->cand.as<unsigned>(), cand_count, ex->cellmax.as<int>(), ex->keys.as<unsigned>(), key_count,
-        ex->labels.as<unsigned short>(), ex->winners.as<unsigned>(), win_count, ex->status.as<int>(), P);
+        ex->cand.as<unsigned>(), cand_count, ex->labels.as<unsigned short>(), ex->winners.as<unsigned>(), win_count,
+        ex->status.as<int>(), P);
     ex->launches++;
     PROF_MARK(3);
     k_blur<<<dim3(P.btiles, nframes), 256, 0, st>>>(pyr, blur, P);
@@ -1081,11 +1148,9 @@ int uvip_extractor_create(const uvip_extractor_params* params, uvip_extractor** 
     rc |= ex->pyr.reserve((size_t)B * P.frame_bytes + 4096);
     rc |= ex->blur.reserve((size_t)B * P.frame_bytes + 4096);
     rc |= ex->cand.reserve((size_t)B * P.raw_per_frame * 4);
-    rc |= ex->keys.reserve((size_t)B * P.raw_per_frame * 4);
     rc |= ex->labels.reserve((size_t)B * P.raw_per_frame * 2);
     rc |= ex->winners.reserve((size_t)B * P.kp_per_frame * 4);
-    rc |= ex->counters.reserve((size_t)3 * B * nl * 4);
-    rc |= ex->cellmax.reserve((size_t)B * P.cells_per_frame * 4);
+    rc |= ex->counters.reserve((size_t)2 * B * nl * 4);
     rc |= ex->sel.reserve((size_t)B * ex->sel_cap * 4);
     rc |= ex->nsel.reserve((size_t)B * 4);
     rc |= ex->tabs.reserve((size_t)ex->cap_tab * 4);
@@ -1106,6 +1171,10 @@ int uvip_extractor_create(const uvip_extractor_params* params, uvip_extractor** 
         set_last_error("quadtree kernel needs %zu bytes of shared memory: %s", qsm, cudaGetErrorString(cudaGetLastError()));
         uvip_extractor_destroy(ex); return UVIP_ERR_UNSUPPORTED;
     }
+    if (cudaFuncSetAttribute(k_fast, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)fast_smem_bytes(P)) != cudaSuccess) {
+        set_last_error("FAST kernel needs %zu bytes of shared memory: %s", fast_smem_bytes(P), cudaGetErrorString(cudaGetLastError()));
+        uvip_extractor_destroy(ex); return UVIP_ERR_UNSUPPORTED;
+    }
     *out = ex;
     return UVIP_OK;
 }
@@ -1115,7 +1184,7 @@ int uvip_extractor_destroy(uvip_extractor* ex)
     if (!ex) return UVIP_OK;
     DeviceGuard g(ex->device);
     if (ex->stream) cudaStreamSynchronize(ex->stream);
-    DevBuf* bufs[] = {&ex->pyr, &ex->blur, &ex->cand, &ex->keys, &ex->labels, &ex->winners, &ex->counters, &ex->cellmax, &ex->sel,
+    DevBuf* bufs[] = {&ex->pyr, &ex->blur, &ex->cand, &ex->labels, &ex->winners, &ex->counters, &ex->sel,
                       &ex->nsel, &ex->tabs, &ex->status, &ex->grid, &ex->incoming, &ex->in_frames, &ex->out_kps, &ex->out_desc, &ex->out_n};
     for (DevBuf* b : bufs) b->release();
     for (cudaEvent_t e : ex->prof_ev) cudaEventDestroy(e);
@@ -1298,9 +1367,10 @@ int uvip_get_raw_corners(uvip_extractor* ex, int frame, int level, int32_t* xs, 
     const Plan& P = ex->plan; const LevelInfo& L = P.lv[level];
     int cnt = 0;
     const size_t cstride = (size_t)ex->prm.max_batch * P.nlevels;
-    UVIP_CUDA(cudaMemcpy(&cnt, ex->counters.as<int>() + cstride + (size_t)frame * P.nlevels + level, 4, cudaMemcpyDeviceToHost));
+    UVIP_CUDA(cudaMemcpy(&cnt, ex->counters.as<int>() + (size_t)frame * P.nlevels + level, 4, cudaMemcpyDeviceToHost));
+    (void)cstride;
     std::vector<unsigned> v;
-    int rc = fetch_list(ex, ex->keys, (size_t)frame * P.raw_per_frame + L.raw_off, cnt, &v);
+    int rc = fetch_list(ex, ex->cand, (size_t)frame * P.raw_per_frame + L.raw_off, cnt, &v);
     if (rc) return rc;
     // reference order: cell row, cell column, then y, x inside the cell (src/ORBextractor.cc:772-812)
     auto okey = [&](unsigned c) {
@@ -1329,7 +1399,7 @@ int uvip_get_level_keypoints(uvip_extractor* ex, int frame, int level, int32_t* 
     const Plan& P = ex->plan; const LevelInfo& L = P.lv[level];
     int cnt = 0;
     const size_t cstride = (size_t)ex->prm.max_batch * P.nlevels;
-    UVIP_CUDA(cudaMemcpy(&cnt, ex->counters.as<int>() + 2 * cstride + (size_t)frame * P.nlevels + level, 4, cudaMemcpyDeviceToHost));
+    UVIP_CUDA(cudaMemcpy(&cnt, ex->counters.as<int>() + cstride + (size_t)frame * P.nlevels + level, 4, cudaMemcpyDeviceToHost));
     std::vector<unsigned> v;
     int rc = fetch_list(ex, ex->winners, (size_t)frame * P.kp_per_frame + L.kp_off, cnt, &v);
     if (rc) return rc;
