@@ -28,7 +28,7 @@ for cb in sorted(os.listdir(tmp)):
     if not cb.endswith('.cubin') or '-' in cb:
         continue
     asm = subprocess.run(['nvdisasm', '--print-line-info', os.path.join(tmp, cb)], capture_output=True, text=True).stdout
-    cur = None; line = 0; fn = None
+    cur = None; line = ('', 0); fn = None
     for ln in asm.split('\n'):
         m = re.match(r'\s*\.section\s+\.text\.(\S+?),', ln)
         if m:
@@ -38,9 +38,9 @@ for cb in sorted(os.listdir(tmp)):
             continue
         if cur is None:
             continue
-        m = re.search(r'//## File ".*?", line (\d+)', ln)
+        m = re.search(r'//## File "(.*?)", line (\d+)', ln)
         if m:
-            line = int(m.group(1)); continue
+            line = (os.path.basename(m.group(1)), int(m.group(2))); continue
         if re.match(r'\s*/\*[0-9a-f]{4,}\*/\s+\S', ln):
             cur.append(line)
 best = None
@@ -49,14 +49,31 @@ for fn, l in lines:
         best = l
 if best is None:
     print('could not align SASS listings:', [(fn, len(l)) for fn, l in lines], len(data)); sys.exit(1)
-src = open(os.path.join(os.path.dirname(so), 'csrc', 'extractor.cu' if 'extract' not in kern and False else
-                        ('matcher.cu' if re.search('knn|search|grid|rot|ratio|popc|descriptor_distance', kern) else 'extractor.cu'))).read().split('\n')
+srcs = {}
+def src_line(fn, ln):
+    if fn not in srcs:
+        try:
+            srcs[fn] = open(os.path.join(os.path.dirname(so), 'csrc', fn)).read().split('\n')
+        except Exception:
+            srcs[fn] = None
+    t = srcs[fn]
+    return t[ln - 1].strip()[:105] if t and 0 < ln <= len(t) else '<' + fn + '>'
 agg = {}
 for r, ln in zip(data, best):
     a = agg.setdefault(ln, [0, 0, 0])
     a[0] += int(r[iI] or 0); a[1] += int(r[iT] or 0); a[2] += int(r[iN] or 0)
 tot = sum(a[0] for a in agg.values()); tots = sum(a[2] for a in agg.values())
 print('kernel', kern, 'SASS instructions', len(data), 'warp-instr executed', tot, 'samples', tots)
-for ln, a in sorted(agg.items(), key=lambda kv: -kv[1][0])[:top]:
-    text = src[ln - 1].strip()[:110] if 0 < ln <= len(src) else ''
-    print('%5.1f%% inst %5.1f%% smp thr/warp=%4.1f  L%-4d %s' % (a[0] * 100 / max(tot, 1), a[2] * 100 / max(tots, 1), a[1] / max(a[0], 1), ln, text))
+key = (lambda kv: -kv[1][2]) if os.environ.get('BY_SAMPLES') else (lambda kv: -kv[1][0])
+for (fn, ln), a in sorted(agg.items(), key=key)[:top]:
+    print('%5.1f%% inst %5.1f%% smp thr/warp=%4.1f  L%-4d %s' % (a[0] * 100 / max(tot, 1), a[2] * 100 / max(tots, 1), a[1] / max(a[0], 1), ln, src_line(fn, ln)))
+
+if os.environ.get('RANGES'):
+    # RANGES="name:lo-hi,name:lo-hi" sums instruction share per source-line range of extractor.cu / matcher.cu
+    for spec in os.environ['RANGES'].split(','):
+        name, rng = spec.split(':'); lo, hi = [int(v) for v in rng.split('-')]
+        ins = sum(a[0] for (fn, ln), a in agg.items() if fn.endswith('.cu') and lo <= ln <= hi)
+        smp = sum(a[2] for (fn, ln), a in agg.items() if fn.endswith('.cu') and lo <= ln <= hi)
+        print('%-12s %5.1f%% inst %5.1f%% samples' % (name, ins * 100 / max(tot, 1), smp * 100 / max(tots, 1)))
+    ins = sum(a[0] for (fn, ln), a in agg.items() if not fn.endswith('.cu'))
+    print('%-12s %5.1f%% inst (CUDA headers: intrinsics, atomics)' % ('headers', ins * 100 / max(tot, 1)))

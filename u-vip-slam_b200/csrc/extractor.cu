@@ -9,6 +9,7 @@
 //
 // Reference semantics restated here (never its code): src/ORBextractor.cc:74-78,125-195,458-512,748-1004,1006-1287.
 #include "common.cuh"
+#include <cuda.h>
 #include <math.h>
 #include <algorithm>
 #include <vector>
@@ -34,7 +35,7 @@ struct LevelInfo {
     int quota;                // mnFeaturesPerLevel
     int raw_cap, raw_off;     // candidate list (u32 entries) inside the frame's candidate block
     int kp_cap, kp_off;       // quadtree winners
-    int ftile_off, fntx, fnty, fcw;   // FAST tiles: fcw (1 or 2) cells wide, one cell high
+    int ftile_off, fntx, fnty;        // FAST tiles of FAST_CW x FAST_CH cells
     int btile_off, bntx, bnty;    // blur tiles
     int tab_off;              // offset of this level's resize tables
     int nini;                 // quadtree roots
@@ -47,9 +48,9 @@ struct Plan {
     int nlevels, W, H;
     int fast_th, retry_th, t1, t2, tmin;   // effective thresholds (>=1)
     int cells_per_frame, raw_per_frame, kp_per_frame;
-    int ftiles, btiles;
+    int ftiles, btiles, tile_tab_off;
     int node_cap;             // quadtree node capacity (power of two)
-    int f_irow, f_irows, f_srow, f_srows, f_qcap, f_ocap;   // FAST shared-memory carve-up (largest tile over all levels)
+    int f_irow, f_irows, f_srow, f_srows, f_gcap, f_qcap;   // FAST shared-memory carve-up (largest tile over all levels)
     unsigned long long frame_bytes;
     LevelInfo lv[MAXLEV];
 };
@@ -141,17 +142,21 @@ k_resize(uint8_t* __restrict__ pyr, const int* __restrict__ tabs, int level, con
 
 // --------------------------------------------------------------------------------------------------------
 // K2+K3: FAST-9/16 exactly as the reference runs it: cv::FAST(th, nms=true) per 30-px cell ROI, and a second run at
-// the retry threshold when a cell returned nothing (src/ORBextractor.cc:772-812).  One CTA per tile of up to two
-// horizontally adjacent cells (cell-aligned, so the empty-cell decision never leaves the CTA):
-//   A  stage the tile + 3 px halo in shared memory with aligned 32-bit loads
-//   B  SWAR corner test, 4 pixels per thread per step: ring pixel k of 4 neighbouring pixels is one funnel-shifted
-//      32-bit word; "brighter than v+t" / "darker than v-t" are per-byte carry tricks (3 ALU ops per word each);
-//      opposite ring pairs are tested progressively (a 9-arc contains one pixel of every opposite pair) so flat and
-//      gradient regions leave after 2..8 of the 16 ring words; only then the 9-contiguity AND-chains run
-//   C  exact score s = max_arc min_k |ring_k - v| - 1 (== OpenCV cornerScore) for the queued corners (DPX min3/max3)
-//   D  3x3 strict NMS inside the cell, survivors appended to the (frame, level) raw-corner list
+// the retry threshold when a cell returned nothing (src/ORBextractor.cc:772-812).  One CTA per tile of up to 4x2
+// cells (cell-aligned, so the empty-cell decision never leaves the CTA):
+//   A   stage the tile + 3 px halo in shared memory with aligned 32-bit loads
+//   B1  SWAR pre-test, 4 pixels per thread per step, all groups: |ring - v| > t on the compass pairs (0,8),(4,12)
+//       via VABSDIFF4 + a per-byte carry trick; a 9-arc contains one pixel of every opposite pair, so groups where
+//       no pixel passes are dropped (85 % on the benchmark frame).  Survivors are compacted (warp ballot) so that
+//   B2  the full test runs on dense warps: ring pixel k of 4 neighbouring pixels is one funnel-shifted 32-bit word,
+//       "brighter than v+t" / "darker than v-t" are 3 ALU ops per word each, opposite pairs are AND-ed progressively,
+//       then the 9-contiguity AND-chains; corner pixels are queued
+//   C   exact score s = max_arc min_k |ring_k - v| - 1 (== OpenCV cornerScore) for the queued corners (DPX min3/max3)
+//   D   3x3 strict NMS inside the cell, survivors appended to the (frame, level) raw-corner list (warp-aggregated)
 // Pass 2 repeats B..D at the retry threshold for the cells of the tile that produced no survivor.
 // --------------------------------------------------------------------------------------------------------
+constexpr int FAST_CW = 4, FAST_CH = 2;      // cells per tile
+
 __device__ __forceinline__ unsigned swar_gt(unsigned a, unsigned b, unsigned nb7)
 {   // bit 7 of every byte: a > b (unsigned bytes); nb7 = ~b & 0x7f7f7f7f precomputed
     const unsigned s = (a & 0x7f7f7f7fu) + nb7;
@@ -162,8 +167,27 @@ __device__ __forceinline__ unsigned swar_lt(unsigned a, unsigned b, unsigned b7)
     const unsigned s = b7 + (~a & 0x7f7f7f7fu);
     return (b & ~a) | (~(a ^ b) & s);
 }
+// bit 7 of every byte: a > t for a constant threshold; k7 = (0x7f - (t & 0x7f)) * 0x01010101
+__device__ __forceinline__ unsigned swar_gt_const(unsigned a, unsigned k7, bool t_low)
+{
+    const unsigned s = (a & 0x7f7f7f7fu) + k7;
+    return t_low ? (s | a) : (s & a);          // t < 128: high bit alone decides; t >= 128: need both
+}
 
-// corner flags (bit 7 per byte) of the 4 pixels whose centre word is W[0]; rs = row stride in words
+// B1: does any of the 4 pixels of this group pass the compass pre-test?  (bit 7 per byte)
+__device__ __forceinline__ unsigned fast_pre4(const unsigned* __restrict__ W, int rs, unsigned k7, bool t_low)
+{
+    const unsigned v = W[0];
+    const unsigned g0 = swar_gt_const(__vabsdiffu4(W[3 * rs], v), k7, t_low);
+    const unsigned g8 = swar_gt_const(__vabsdiffu4(W[-3 * rs], v), k7, t_low);
+    const unsigned p08 = g0 | g8;
+    if ((p08 & 0x80808080u) == 0) return 0;
+    const unsigned g4 = swar_gt_const(__vabsdiffu4(__funnelshift_r(v, W[1], 24), v), k7, t_low);
+    const unsigned g12 = swar_gt_const(__vabsdiffu4(__funnelshift_r(W[-1], v, 8), v), k7, t_low);
+    return p08 & (g4 | g12) & 0x80808080u;
+}
+
+// B2: corner flags (bit 7 per byte) of the 4 pixels whose centre word is W[0]; rs = row stride in words
 __device__ __forceinline__ unsigned fast_swar4(const unsigned* __restrict__ W, int rs, unsigned t4, unsigned valid)
 {
     const unsigned v = W[0];
@@ -173,14 +197,12 @@ __device__ __forceinline__ unsigned fast_swar4(const unsigned* __restrict__ W, i
 #define RING(k, word) do { const unsigned r_ = (word); b[k] = swar_gt(r_, hi, nhi7); d[k] = swar_lt(r_, lo, lo7); } while (0)
     RING(0, W[3 * rs]);
     RING(8, W[-3 * rs]);
-    unsigned pb = b[0] | b[8], pd = d[0] | d[8];
-    if (((pb | pd) & valid) == 0) return 0;
     {
-        const unsigned l = W[-1], c = v, r = W[1];
-        RING(4, __funnelshift_r(c, r, 24));
-        RING(12, __funnelshift_r(l, c, 8));
+        const unsigned l = W[-1], r = W[1];
+        RING(4, __funnelshift_r(v, r, 24));
+        RING(12, __funnelshift_r(l, v, 8));
     }
-    pb &= b[4] | b[12]; pd &= d[4] | d[12];
+    unsigned pb = (b[0] | b[8]) & (b[4] | b[12]), pd = (d[0] | d[8]) & (d[4] | d[12]);
     if (((pb | pd) & valid) == 0) return 0;
     {
         const unsigned* p = W + 2 * rs; const unsigned* q = W - 2 * rs;
@@ -225,84 +247,106 @@ __device__ __forceinline__ unsigned fast_swar4(const unsigned* __restrict__ W, i
 }
 
 __global__ void __launch_bounds__(256)
-k_fast(const uint8_t* __restrict__ pyr, unsigned* __restrict__ cand, int* __restrict__ cand_count,
-       int* __restrict__ status, const __grid_constant__ Plan P)
+k_fast(const CUtensorMap* __restrict__ tmaps, const unsigned* __restrict__ tile_tab, unsigned* __restrict__ cand,
+       int* __restrict__ cand_count, int* __restrict__ status, const __grid_constant__ Plan P)
 {
-    extern __shared__ __align__(16) unsigned char s_fast[];
-    __shared__ int s_nq, s_nout, s_base, s_surv[2];
-    __shared__ unsigned s_colvalid[64];
+    extern __shared__ __align__(128) unsigned char s_fast[];
+    __shared__ __align__(8) uint64_t s_mbar;
+    __shared__ unsigned s_colvalid[FAST_CH][64];
+    __shared__ int s_ng, s_nq, s_surv[FAST_CW * FAST_CH];
+    __shared__ unsigned char s_rowact[2][8];     // [cell row][cell col] evaluated in this pass
 
-    int level = 0;
-    const int tile = blockIdx.x;
-#pragma unroll 1
-    for (int l = 1; l < P.nlevels; l++) if (tile >= P.lv[l].ftile_off) level = l;
+    const unsigned te = __ldg(tile_tab + blockIdx.x);     // level | cy0 << 4 | cx0 << 16
+    const int level = te & 15, cy0 = (te >> 4) & 0xFFF, cx0 = te >> 16;
     const LevelInfo& L = P.lv[level];
-    const int f = blockIdx.y, tid = threadIdx.x;
-    const int tl = tile - L.ftile_off;
-    const int cy = tl / L.fntx, cx0 = (tl - cy * L.fntx) * L.fcw;
-    const int ncell = min(L.fcw, L.ncols - cx0);
+    const int f = blockIdx.y, tid = threadIdx.x, lane = tid & 31;
+    const int ncx = min(FAST_CW, L.ncols - cx0), ncy = min(FAST_CH, L.nrows - cy0);
     const int xend = L.w - EDGE, yend = L.h - EDGE;
-    const int X0 = EDGE + cx0 * L.wcell, Xs = X0 + L.wcell, X1 = min(EDGE + (cx0 + ncell) * L.wcell, xend);
-    const int Y0 = EDGE + cy * L.hcell, Y1 = min(Y0 + L.hcell, yend);
+    const int X0 = EDGE + cx0 * L.wcell, X1 = min(EDGE + (cx0 + ncx) * L.wcell, xend);
+    const int Y0 = EDGE + cy0 * L.hcell, Y1 = min(EDGE + (cy0 + ncy) * L.hcell, yend);
     if (X0 >= X1 || Y0 >= Y1) return;
-    // shared-memory carve-up (sizes from the plan: the largest tile over all levels)
-    const int irow = P.f_irow;                 // image row stride, bytes (multiple of 4)
-    const int srow = P.f_srow;                 // score row stride, bytes
+    const int irow = P.f_irow, srow = P.f_srow;           // shared-memory strides (bytes) from the plan
     unsigned* s_img = reinterpret_cast<unsigned*>(s_fast);
     uint8_t* s_score = s_fast + (size_t)irow * P.f_irows;
-    unsigned short* s_queue = reinterpret_cast<unsigned short*>(s_score + (size_t)srow * P.f_srows);
-    unsigned* s_out = reinterpret_cast<unsigned*>(s_queue + P.f_qcap);
+    unsigned short* s_gq = reinterpret_cast<unsigned short*>(s_score + (size_t)srow * P.f_srows);
+    unsigned short* s_queue = s_gq + P.f_gcap;
 
-    const int gx0 = X0 & ~3, gxe = (X1 - 1) & ~3;          // first / last 4-pixel group (image coords)
+    const int gx0 = X0 & ~3, gxe = (X1 - 1) & ~3;         // first / last 4-pixel group (image coords)
     const int ngx = ((gxe - gx0) >> 2) + 1;
-    const int ax0 = gx0 - 4, ay0 = Y0 - 3;                // image coords of s_img[0][0]
-    const int ncw = ngx + 2, nrows_img = (Y1 - Y0) + 6;
+    const int ax0 = ((gx0 - 4 + EDGE) & ~15) - EDGE;      // image coords of s_img[0][0]: TMA needs a 16-byte aligned start
+    const int ay0 = Y0 - 3;
+    const int cofs = (gx0 - 4 - ax0) >> 2;                // word column of the first group's left neighbour
     const int rsw = irow >> 2;
-    const uint8_t* inner = pyr + (size_t)f * P.frame_bytes + L.poff + (size_t)EDGE * L.pstride + EDGE;
-    if (tid == 0) { s_nout = 0; s_surv[0] = 0; s_surv[1] = 0; }
-    // A: stage
-    {
-        const unsigned rcp = 0xFFFFFFFFu / (unsigned)ncw + 1u;
-        for (int i = tid; i < nrows_img * ncw; i += 256) {
-            const int r = __umulhi((unsigned)i, rcp), c = i - r * ncw;
-            const int y = ay0 + r, x = ax0 + 4 * c;
-            unsigned v = 0;
-            if (x >= -EDGE && x + 4 <= L.pstride - EDGE) v = __ldg(reinterpret_cast<const unsigned*>(inner + (ptrdiff_t)y * L.pstride + x));
-            s_img[r * rsw + c] = v;
-        }
-        for (int i = tid; i < (srow * P.f_srows) >> 2; i += 256) reinterpret_cast<unsigned*>(s_score)[i] = 0;
+    if (tid < FAST_CW * FAST_CH) s_surv[tid] = 0;
+    // A: stage the tile with one TMA box load (zero-filled outside the padded plane); the box is the plan's
+    //    largest tile, so every CTA issues the same shape
+    if (tid == 0) { mbar_init(&s_mbar, 1); mbar_fence_init(); }
+    __syncthreads();
+    if (tid == 0) {
+        mbar_arrive_expect_tx(&s_mbar, (unsigned)(irow * P.f_irows));
+        tma_load_3d(s_img, tmaps + level, ax0 + EDGE, ay0 + EDGE, f, &s_mbar);
     }
+    for (int i = tid; i < (srow * P.f_srows) >> 2; i += 256) reinterpret_cast<unsigned*>(s_score)[i] = 0;
+    mbar_wait(&s_mbar, 0);
     const int nrows = Y1 - Y0, ngroups = ngx * nrows;
     const unsigned rcpg = 0xFFFFFFFFu / (unsigned)ngx + 1u;
+    const unsigned rcps = 0xFFFFFFFFu / (unsigned)srow + 1u;
+    int* gcount = cand_count + (size_t)f * P.nlevels + level;
+    unsigned* gdst = cand + (size_t)f * P.raw_per_frame + L.raw_off;
 
     for (int pass = 0; pass < 2; pass++) {
         const int t = pass ? P.t2 : P.t1;
         __syncthreads();                                   // staging / previous pass complete
-        bool act0 = true, act1 = ncell > 1;
         if (pass) {
             if (P.t2 >= P.t1) break;                       // the retry cannot add anything (uniform)
-            act0 = s_surv[0] == 0; act1 = (ncell > 1) && s_surv[1] == 0;
-            if (!act0 && !act1) break;                     // uniform
+            int any = 0;
+            for (int i = 0; i < ncy; i++) for (int j = 0; j < ncx; j++) any |= (s_surv[i * FAST_CW + j] == 0);
+            if (!any) break;                               // uniform
         }
-        // per-group-column byte masks: inside [X0,X1) and in a cell evaluated in this pass
-        if (tid < ngx) {
-            unsigned m = 0;
-            for (int bb = 0; bb < 4; bb++) {
-                const int x = gx0 + 4 * tid + bb;
-                const bool in = x >= X0 && x < X1 && ((x < Xs) ? act0 : act1);
-                if (in) m |= 0x80u << (8 * bb);
-            }
-            s_colvalid[tid] = m;
+        if (tid < FAST_CW * FAST_CH) {
+            const int i = tid / FAST_CW, j = tid % FAST_CW;
+            s_rowact[i][j] = (i < ncy && j < ncx && (pass == 0 || s_surv[tid] == 0)) ? 1 : 0;
         }
-        if (tid == 0) s_nq = 0;
+        if (tid == 0) { s_ng = 0; s_nq = 0; }
         __syncthreads();
-        // B: SWAR corner test
+        if (tid < FAST_CH * 64) {                           // byte masks per (cell row, group column): inside [X0,X1) and cell active
+            const int ci = tid >> 6, c = tid & 63;
+            unsigned m = 0;
+            if (c < ngx)
+                for (int bb = 0; bb < 4; bb++) {
+                    const int x = gx0 + 4 * c + bb;
+                    if (x >= X0 && x < X1 && s_rowact[ci][min((x - X0) / L.wcell, FAST_CW - 1)]) m |= 0x80u << (8 * bb);
+                }
+            s_colvalid[ci][c] = m;
+        }
+        // B1: compass pre-test over all groups, survivors compacted into s_gq
+        const bool t_low = t < 128;
+        const unsigned k7 = (unsigned)(0x7f - (t & 0x7f)) * 0x01010101u;
+        for (int g0 = 0; g0 < ngroups; g0 += 256) {
+            const int g = g0 + tid;
+            unsigned pf = 0;
+            if (g < ngroups) {
+                const int r = __umulhi((unsigned)g, rcpg), c = g - r * ngx;
+                pf = fast_pre4(s_img + (r + 3) * rsw + (cofs + c + 1), rsw, k7, t_low);
+            }
+            const unsigned bal = __ballot_sync(0xFFFFFFFFu, pf != 0);
+            if (bal) {
+                int base = 0;
+                if (lane == 0) base = atomicAdd(&s_ng, __popc(bal));
+                base = __shfl_sync(0xFFFFFFFFu, base, 0);
+                if (pf) s_gq[base + __popc(bal & ((1u << lane) - 1))] = (unsigned short)g;
+            }
+        }
+        __syncthreads();
+        const int ng = s_ng;
+        // B2: full SWAR test on the compacted groups
         const unsigned t4 = (unsigned)t * 0x01010101u;
-        for (int g = tid; g < ngroups; g += 256) {
+        for (int gi = tid; gi < ng; gi += 256) {
+            const int g = s_gq[gi];
             const int r = __umulhi((unsigned)g, rcpg), c = g - r * ngx;
-            const unsigned valid = s_colvalid[c];
+            const unsigned valid = s_colvalid[(r >= L.hcell) ? 1 : 0][c];
             if (!valid) continue;
-            unsigned cf = fast_swar4(s_img + (r + 3) * rsw + (c + 1), rsw, t4, valid);
+            unsigned cf = fast_swar4(s_img + (r + 3) * rsw + (cofs + c + 1), rsw, t4, valid);
             while (cf) {
                 const int bb = (__ffs(cf) - 1) >> 3;
                 cf &= cf - 1;
@@ -315,7 +359,7 @@ k_fast(const uint8_t* __restrict__ pyr, unsigned* __restrict__ cand, int* __rest
         // C: exact score
         for (int qi = tid; qi < nq; qi += 256) {
             const int pos = s_queue[qi];
-            const int sy = pos / srow, sx = pos - sy * srow;
+            const int sy = __umulhi((unsigned)pos, rcps), sx = pos - sy * srow;
             const uint8_t* pc = reinterpret_cast<const uint8_t*>(s_img) + (sy - 1 + 3) * irow + (sx - 1 + X0 - ax0);
             const int v = pc[0];
             int d[16];
@@ -338,46 +382,49 @@ k_fast(const uint8_t* __restrict__ pyr, unsigned* __restrict__ cand, int* __rest
             s_score[pos] = (uint8_t)(max(A, -Bn) - 1);     // >= t >= 1 for a corner at t
         }
         __syncthreads();
-        // D: strict 3x3 NMS inside the cell (positions outside the cell interior count as 0)
-        for (int qi = tid; qi < nq; qi += 256) {
-            const int pos = s_queue[qi];
-            const int sy = pos / srow, sx = pos - sy * srow;
-            const int x = X0 + sx - 1, y = Y0 + sy - 1;
-            const int cell = x >= Xs ? 1 : 0;
-            const int cxa = cell ? Xs : X0, cxb = cell ? X1 : min(Xs, X1);
-            const int s = s_score[pos];
-            const bool hasL = x > cxa, hasR = x + 1 < cxb, hasU = y > Y0, hasD = y + 1 < Y1;
-            const uint8_t* sp = s_score + pos;
-            bool keep = true;
-            if (hasL) keep &= s > sp[-1];
-            if (hasR) keep &= s > sp[1];
-            if (hasU) {
-                keep &= s > sp[-srow];
-                if (hasL) keep &= s > sp[-srow - 1];
-                if (hasR) keep &= s > sp[-srow + 1];
+        // D: strict 3x3 NMS inside the cell (positions outside the cell interior count as 0); append survivors
+        for (int q0 = 0; q0 < nq; q0 += 256) {
+            const int qi = q0 + tid;
+            bool keep = false; unsigned rec = 0; int cell = 0;
+            if (qi < nq) {
+                const int pos = s_queue[qi];
+                const int sy = __umulhi((unsigned)pos, rcps), sx = pos - sy * srow;
+                const int x = X0 + sx - 1, y = Y0 + sy - 1;
+                const int cj = (x - X0) / L.wcell, ci = (y - Y0 >= L.hcell) ? 1 : 0;
+                const int cxa = X0 + cj * L.wcell, cxb = min(cxa + L.wcell, X1);
+                const int cya = Y0 + ci * L.hcell, cyb = min(cya + L.hcell, Y1);
+                const int s = s_score[pos];
+                const bool hasL = x > cxa, hasR = x + 1 < cxb, hasU = y > cya, hasD = y + 1 < cyb;
+                const uint8_t* sp = s_score + pos;
+                keep = true;
+                if (hasL) keep &= s > sp[-1];
+                if (hasR) keep &= s > sp[1];
+                if (hasU) {
+                    keep &= s > sp[-srow];
+                    if (hasL) keep &= s > sp[-srow - 1];
+                    if (hasR) keep &= s > sp[-srow + 1];
+                }
+                if (hasD) {
+                    keep &= s > sp[srow];
+                    if (hasL) keep &= s > sp[srow - 1];
+                    if (hasR) keep &= s > sp[srow + 1];
+                }
+                rec = (unsigned)x | ((unsigned)y << 12) | ((unsigned)s << 24);
+                cell = ci * FAST_CW + cj;
             }
-            if (hasD) {
-                keep &= s > sp[srow];
-                if (hasL) keep &= s > sp[srow - 1];
-                if (hasR) keep &= s > sp[srow + 1];
+            const unsigned bal = __ballot_sync(0xFFFFFFFFu, keep);
+            if (bal) {
+                int base = 0;
+                if (lane == 0) base = atomicAdd(gcount, __popc(bal));
+                base = __shfl_sync(0xFFFFFFFFu, base, 0);
+                if (keep) {
+                    const int o = base + __popc(bal & ((1u << lane) - 1));
+                    if (o < L.raw_cap) gdst[o] = rec; else atomicOr(status, 1);
+                    atomicAdd(&s_surv[cell], 1);
+                }
             }
-            if (!keep) continue;
-            const int slot = atomicAdd(&s_nout, 1);
-            if (slot < P.f_ocap) s_out[slot] = (unsigned)x | ((unsigned)y << 12) | ((unsigned)s << 24);
-            atomicAdd(&s_surv[cell], 1);
         }
     }
-    __syncthreads();
-    const int nout = s_nout;
-    if (nout == 0) return;
-    if (nout > P.f_ocap) { if (tid == 0) atomicOr(status, 1); return; }
-    int* cnt = cand_count + (size_t)f * P.nlevels + level;
-    if (tid == 0) s_base = atomicAdd(cnt, nout);
-    __syncthreads();
-    const int base = s_base;
-    if (base + nout > L.raw_cap) { if (tid == 0) atomicOr(status, 1); return; }
-    unsigned* dst = cand + (size_t)f * P.raw_per_frame + L.raw_off + base;
-    for (int i = tid; i < nout; i += 256) dst[i] = s_out[i];
 }
 
 // --------------------------------------------------------------------------------------------------------
@@ -890,7 +937,7 @@ struct uvip_extractor {
     Plan plan;                 // for (plan.W, plan.H); W == 0 -> none yet
     // working set sized for (max_width, max_height, max_batch)
     size_t cap_frame_bytes = 0; int cap_cells = 0, cap_raw = 0, cap_kp = 0, cap_tab = 0;
-    DevBuf pyr, blur, cand, labels, winners, counters, sel, nsel, tabs, status, grid, incoming;
+    DevBuf pyr, blur, cand, labels, winners, counters, sel, nsel, tabs, status, grid, incoming, tmaps;
     DevBuf in_frames, out_kps, out_desc, out_n;      // staging for the host-buffer entry points
     int sel_cap = 0;
     int last_frames = 0;
@@ -963,11 +1010,10 @@ static int make_plan(const uvip_extractor* ex, int w, int h, Plan* out, std::vec
         L.hx = (float)(maxBX - minB) / (float)L.nini;
         L.kp_cap = (L.quota + 4 > 4 * L.nini ? L.quota + 4 : 4 * L.nini);
         L.kp_off = kp; kp += L.kp_cap;
-        L.fcw = L.ncols > 1 ? 2 : 1;
-        L.fntx = div_up(L.ncols, L.fcw); L.fnty = L.nrows;
+        L.fntx = div_up(L.ncols, FAST_CW); L.fnty = div_up(L.nrows, FAST_CH);
         L.ftile_off = ft; ft += L.fntx * L.fnty;
-        if (L.fcw * L.wcell > max_tw) max_tw = L.fcw * L.wcell;
-        if (L.hcell > max_th) max_th = L.hcell;
+        { const int tw = (L.ncols < FAST_CW ? L.ncols : FAST_CW) * L.wcell, th = (L.nrows < FAST_CH ? L.nrows : FAST_CH) * L.hcell;
+          if (tw > max_tw) max_tw = tw; if (th > max_th) max_th = th; }
         L.bntx = div_up(L.w + 2 * BORDER_W, BT_W); L.bnty = div_up(L.h + 2 * BORDER_W, BT_H);
         L.btile_off = bt; bt += L.bntx * L.bnty;
         L.tab_off = tab; if (l > 0) tab += 2 * L.w + 2 * L.h;
@@ -982,12 +1028,19 @@ static int make_plan(const uvip_extractor* ex, int w, int h, Plan* out, std::vec
     P.node_cap = nc;
     {
         const int ngx_max = (max_tw + 2) / 4 + 1;
-        P.f_irow = 4 * (ngx_max + 2); P.f_irows = max_th + 6;
+        P.f_irow = (int)align_up((size_t)4 * (ngx_max + 2) + 12, 16); P.f_irows = max_th + 6;   // TMA box: 16-byte aligned start and extent
         P.f_srow = (int)align_up((size_t)max_tw + 2, 4); P.f_srows = max_th + 2;
-        P.f_qcap = (max_tw * max_th + 1) & ~1; P.f_ocap = P.f_qcap / 3 + 64;
+        P.f_gcap = (ngx_max * max_th + 1) & ~1; P.f_qcap = (max_tw * max_th + 1) & ~1;
     }
+    P.tile_tab_off = tab;
     if (tabs) {
-        tabs->assign(tab > 0 ? tab : 1, 0);
+        tabs->assign(tab + ft + 1, 0);
+        for (int l = 0; l < p.nlevels; l++) {
+            const LevelInfo& L = P.lv[l];
+            for (int ty = 0; ty < L.fnty; ty++)
+                for (int tx = 0; tx < L.fntx; tx++)
+                    (*tabs)[tab + L.ftile_off + ty * L.fntx + tx] = (int)((unsigned)l | ((unsigned)(ty * FAST_CH) << 4) | ((unsigned)(tx * FAST_CW) << 16));
+        }
         for (int l = 1; l < p.nlevels; l++) {
             const LevelInfo& D = P.lv[l]; const LevelInfo& S = P.lv[l - 1];
             int* t = tabs->data() + D.tab_off;
@@ -999,7 +1052,7 @@ static int make_plan(const uvip_extractor* ex, int w, int h, Plan* out, std::vec
     return UVIP_OK;
 }
 
-static size_t fast_smem_bytes(const Plan& P) { return (size_t)P.f_irow * P.f_irows + (size_t)P.f_srow * P.f_srows + 2 * (size_t)P.f_qcap + 4 * (size_t)P.f_ocap; }
+static size_t fast_smem_bytes(const Plan& P) { return (size_t)P.f_irow * P.f_irows + (size_t)P.f_srow * P.f_srows + 2 * (size_t)P.f_gcap + 2 * (size_t)P.f_qcap + 128; }
 static size_t qt_smem_bytes(int cap) { return (size_t)(4 * cap * 2 + cap * 2 + 4 * cap + cap + cap + (cap + 1) + cap + 4 * cap + cap + cap + cap) * 4; }
 
 static int ensure_plan(uvip_extractor* ex, int w, int h)
@@ -1018,6 +1071,29 @@ static int ensure_plan(uvip_extractor* ex, int w, int h)
     UVIP_CUDA(cudaFuncSetAttribute(k_quadtree, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)qt_smem_bytes(P.node_cap)));
     UVIP_CUDA(cudaFuncSetAttribute(k_fast, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)fast_smem_bytes(P)));
     UVIP_CUDA(cudaMemcpy(ex->tabs.p, tabs.data(), tabs.size() * sizeof(int), cudaMemcpyHostToDevice));
+    // TMA descriptors of the pyramid planes: (x bytes, rows, frame) with a box of one FAST tile
+    {
+        typedef CUresult (*encode_fn)(CUtensorMap*, CUtensorMapDataType, cuuint32_t, void*, const cuuint64_t*, const cuuint64_t*,
+                                      const cuuint32_t*, const cuuint32_t*, CUtensorMapInterleave, CUtensorMapSwizzle,
+                                      CUtensorMapL2promotion, CUtensorMapFloatOOBfill);
+        void* fp = nullptr; cudaDriverEntryPointQueryResult qres;
+        UVIP_CUDA(cudaGetDriverEntryPoint("cuTensorMapEncodeTiled", &fp, cudaEnableDefault, &qres));
+        if (!fp || qres != cudaDriverEntryPointSuccess) { set_last_error("cuTensorMapEncodeTiled is not available in this driver"); return UVIP_ERR_CUDA; }
+        alignas(64) CUtensorMap maps[MAXLEV];
+        memset(maps, 0, sizeof(maps));
+        for (int l = 0; l < P.nlevels; l++) {
+            const LevelInfo& L = P.lv[l];
+            const cuuint64_t gdim[3] = {(cuuint64_t)L.pstride, (cuuint64_t)(L.h + 2 * EDGE), (cuuint64_t)ex->prm.max_batch};
+            const cuuint64_t gstr[2] = {(cuuint64_t)L.pstride, (cuuint64_t)P.frame_bytes};
+            const cuuint32_t box[3] = {(cuuint32_t)P.f_irow, (cuuint32_t)P.f_irows, 1};
+            const cuuint32_t estr[3] = {1, 1, 1};
+            CUresult r = ((encode_fn)fp)(&maps[l], CU_TENSOR_MAP_DATA_TYPE_UINT8, 3, ex->pyr.as<uint8_t>() + L.poff, gdim, gstr, box, estr,
+                                         CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_NONE, CU_TENSOR_MAP_L2_PROMOTION_L2_128B,
+                                         CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+            if (r != CUDA_SUCCESS) { set_last_error("cuTensorMapEncodeTiled(level %d) failed: %d", l, (int)r); return UVIP_ERR_CUDA; }
+        }
+        UVIP_CUDA(cudaMemcpy(ex->tmaps.p, maps, sizeof(CUtensorMap) * P.nlevels, cudaMemcpyHostToDevice));
+    }
     ex->plan = P;
     return UVIP_OK;
 }
@@ -1050,7 +1126,8 @@ static int enqueue_group(uvip_extractor* ex, const uint8_t* d_frames, int nframe
         ex->launches++;
     }
     PROF_MARK(1);
-    k_fast<<<dim3(P.ftiles, nframes), 256, fast_smem_bytes(P), st>>>(pyr, ex->cand.as<unsigned>(), cand_count, ex->status.as<int>(), P);
+    k_fast<<<dim3(P.ftiles, nframes), 256, fast_smem_bytes(P), st>>>(ex->tmaps.as<CUtensorMap>(), ex->tabs.as<unsigned>() + P.tile_tab_off, ex->cand.as<unsigned>(),
+                                                                     cand_count, ex->status.as<int>(), P);
     ex->launches++;
     PROF_MARK(2);
     k_quadtree<<<dim3(P.nlevels, nframes), QT_THREADS, qt_smem_bytes(P.node_cap), st>>>(
@@ -1140,7 +1217,7 @@ int uvip_extractor_create(const uvip_extractor_params* params, uvip_extractor** 
     const int B = params->max_batch;
     ex->cap_frame_bytes = P.frame_bytes; ex->cap_cells = P.cells_per_frame; ex->cap_raw = P.raw_per_frame; ex->cap_kp = P.kp_per_frame;
     int tab = 0; for (int l = 1; l < nl; l++) tab += 2 * P.lv[l].w + 2 * P.lv[l].h;
-    ex->cap_tab = tab + 64;
+    ex->cap_tab = tab + P.ftiles + 4096;      // resize tables + FAST tile table (+ slack for other aspect ratios)
     ex->sel_cap = P.kp_per_frame + 4096;     // output rows per frame: quadtree winners + up to 4096 incoming keypoints
     cudaError_t e = cudaStreamCreateWithFlags(&ex->stream, cudaStreamNonBlocking);
     if (e != cudaSuccess) { set_last_error("cudaStreamCreate -> %s", cudaGetErrorString(e)); delete ex; return UVIP_ERR_CUDA; }
@@ -1157,6 +1234,7 @@ int uvip_extractor_create(const uvip_extractor_params* params, uvip_extractor** 
     rc |= ex->status.reserve(16);
     rc |= ex->grid.reserve(16);
     rc |= ex->incoming.reserve(sizeof(uvip_keypoint));
+    rc |= ex->tmaps.reserve(sizeof(CUtensorMap) * MAXLEV);
     if (rc) { uvip_extractor_destroy(ex); return UVIP_ERR_CUDA; }
     // zero the planes once so halo loads never see uninitialised memory
     cudaMemset(ex->pyr.p, 0, ex->pyr.cap); cudaMemset(ex->blur.p, 0, ex->blur.cap);
@@ -1185,7 +1263,7 @@ int uvip_extractor_destroy(uvip_extractor* ex)
     DeviceGuard g(ex->device);
     if (ex->stream) cudaStreamSynchronize(ex->stream);
     DevBuf* bufs[] = {&ex->pyr, &ex->blur, &ex->cand, &ex->labels, &ex->winners, &ex->counters, &ex->sel,
-                      &ex->nsel, &ex->tabs, &ex->status, &ex->grid, &ex->incoming, &ex->in_frames, &ex->out_kps, &ex->out_desc, &ex->out_n};
+                      &ex->nsel, &ex->tabs, &ex->status, &ex->grid, &ex->incoming, &ex->tmaps, &ex->in_frames, &ex->out_kps, &ex->out_desc, &ex->out_n};
     for (DevBuf* b : bufs) b->release();
     for (cudaEvent_t e : ex->prof_ev) cudaEventDestroy(e);
     if (ex->stream) cudaStreamDestroy(ex->stream);
