@@ -710,55 +710,81 @@ k_quadtree(const unsigned* __restrict__ cand, const int* __restrict__ cand_count
 // K6: GaussianBlur 7x7 sigma 2, fixed point [18,34,48,56,48,34,18]/256 per axis, out = (sum + 2^15) >> 16
 // (SURVEY A.6 variant A).  The blurred plane keeps the layout of the pyramid plane; its 4-px border ring holds the
 // UNBLURRED reflect-101 border, which is what the reference's in-place ROI blur leaves there.
+// One CTA per 128x64 tile: the tile + halo arrives as one TMA box; each thread owns 4 adjacent columns and walks
+// down 8 rows with a 7-row register window of horizontal sums (2 IDP4A per pixel), so the vertical pass never
+// touches shared memory.  The last tile entry of every level copies the border ring.
 // --------------------------------------------------------------------------------------------------------
-constexpr int BT_W = 64, BT_H = 32;
+constexpr int BL_W = 128, BL_H = 64, BL_R = 8;          // tile, rows per warp
+constexpr int BL_BOXW = BL_W + 32, BL_BOXH = BL_H + 6;  // TMA box: 16 B aligned start, 16 px slack left and right
+
 __global__ void __launch_bounds__(256)
-k_blur(const uint8_t* __restrict__ pyr, uint8_t* __restrict__ blur, const __grid_constant__ Plan P)
+k_blur(const CUtensorMap* __restrict__ tmaps, const uint8_t* __restrict__ pyr, uint8_t* __restrict__ blur, const __grid_constant__ Plan P)
 {
-    __shared__ __align__(16) uint8_t s_in[BT_H + 6][BT_W + 8];
-    __shared__ unsigned short s_h[BT_H + 6][BT_W];
+    __shared__ __align__(128) unsigned s_in[BL_BOXH * (BL_BOXW / 4)];
+    __shared__ __align__(8) uint64_t s_mbar;
     int level = 0;
     const int tile = blockIdx.x;
 #pragma unroll 1
     for (int l = 1; l < P.nlevels; l++) if (tile >= P.lv[l].btile_off) level = l;
     const LevelInfo& L = P.lv[level];
-    const int f = blockIdx.y, tid = threadIdx.x;
+    const int f = blockIdx.y, tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
     const int tl = tile - L.btile_off;
-    const int tx0 = -BORDER_W + (tl % L.bntx) * BT_W, ty0 = -BORDER_W + (tl / L.bntx) * BT_H;   // level coords, may be negative
     const size_t plane = (size_t)f * P.frame_bytes + L.poff + (size_t)EDGE * L.pstride + EDGE;
-    const uint8_t* in = pyr + plane;
     uint8_t* out = blur + plane;
-    // load rows ty0-3 .. ty0+BT_H+3, cols tx0-4 .. tx0+BT_W+4 (4-byte aligned)
-    for (int i = tid; i < (BT_H + 6) * ((BT_W + 8) / 4); i += 256) {
-        const int r = i / ((BT_W + 8) / 4), c = i % ((BT_W + 8) / 4);
-        const int y = ty0 - 3 + r, x = tx0 - 4 + c * 4;
-        unsigned v = 0;
-        if (y >= -EDGE && y < L.h + EDGE && x >= -EDGE && x + 4 <= L.pstride - EDGE)
-            v = __ldg(reinterpret_cast<const unsigned*>(in + (ptrdiff_t)y * L.pstride + x));
-        *reinterpret_cast<unsigned*>(&s_in[r][c * 4]) = v;
-    }
-    __syncthreads();
-    for (int i = tid; i < (BT_H + 6) * BT_W; i += 256) {
-        const int r = i / BT_W, c = i % BT_W;
-        const uint8_t* p = &s_in[r][c + 1];          // p[0..6] = x-3 .. x+3
-        s_h[r][c] = (unsigned short)(18 * (p[0] + p[6]) + 34 * (p[1] + p[5]) + 48 * (p[2] + p[4]) + 56 * p[3]);
-    }
-    __syncthreads();
-    for (int i = tid; i < BT_H * (BT_W / 4); i += 256) {
-        const int r = i / (BT_W / 4), c4 = (i % (BT_W / 4)) * 4;
-        const int y = ty0 + r, x0 = tx0 + c4;
-        if (y >= L.h + BORDER_W || x0 >= L.w + BORDER_W) continue;
-        uint8_t v[4];
-#pragma unroll
-        for (int k = 0; k < 4; k++) {
-            const int c = c4 + k, x = x0 + k;
-            if (x >= 0 && x < L.w && y >= 0 && y < L.h) {
-                const int a = 18 * (s_h[r][c] + s_h[r + 6][c]) + 34 * (s_h[r + 1][c] + s_h[r + 5][c]) +
-                              48 * (s_h[r + 2][c] + s_h[r + 4][c]) + 56 * s_h[r + 3][c];
-                v[k] = (uint8_t)((a + 32768) >> 16);
-            } else v[k] = s_in[r + 3][c + 4];        // border ring: unblurred copy
+    if (tl == L.bntx * L.bnty) {                          // ring tile: unblurred border copy
+        const uint8_t* in = pyr + plane;
+        const int rw = L.w + 2 * BORDER_W;
+        for (int i = tid; i < 2 * BORDER_W * rw; i += 256) {           // rows -4..-1 and h..h+3
+            const int r = i / rw, x = i - r * rw - BORDER_W;
+            const int y = r < BORDER_W ? r - BORDER_W : L.h + (r - BORDER_W);
+            out[(ptrdiff_t)y * L.pstride + x] = in[(ptrdiff_t)y * L.pstride + x];
         }
-        *reinterpret_cast<uchar4*>(out + (ptrdiff_t)y * L.pstride + x0) = make_uchar4(v[0], v[1], v[2], v[3]);
+        for (int i = tid; i < 2 * BORDER_W * L.h; i += 256) {          // columns -4..-1 and w..w+3
+            const int y = i / (2 * BORDER_W), k = i - y * (2 * BORDER_W);
+            const int x = k < BORDER_W ? k - BORDER_W : L.w + (k - BORDER_W);
+            out[(ptrdiff_t)y * L.pstride + x] = in[(ptrdiff_t)y * L.pstride + x];
+        }
+        return;
+    }
+    const int x0 = (tl % L.bntx) * BL_W, y0 = (tl / L.bntx) * BL_H;
+    if (tid == 0) { mbar_init(&s_mbar, 1); mbar_fence_init(); }
+    __syncthreads();
+    if (tid == 0) {
+        mbar_arrive_expect_tx(&s_mbar, BL_BOXW * BL_BOXH);
+        tma_load_3d(s_in, tmaps + MAXLEV + level, x0, y0 + EDGE - 3, f, &s_mbar);   // padded coords: image (x0-16, y0-3)
+    }
+    mbar_wait(&s_mbar, 0);
+    const int x = x0 + 4 * lane;                          // first of this thread's 4 columns
+    const int yw = y0 + BL_R * warp;                      // first output row of this warp
+    if (x >= L.w || yw >= L.h) return;
+    const unsigned K0 = 18u | (34u << 8) | (48u << 16) | (56u << 24);     // taps for bytes x-3..x
+    const unsigned K1 = 48u | (34u << 8) | (18u << 16);                   // taps for bytes x+1..x+3
+    const unsigned* S = s_in + (BL_R * warp) * (BL_BOXW / 4) + 4 + lane;  // row yw-3, centre word
+    int h[7][4];
+#pragma unroll
+    for (int r = 0; r < BL_R + 6; r++) {
+        const unsigned l = S[r * (BL_BOXW / 4) - 1], m = S[r * (BL_BOXW / 4)], n = S[r * (BL_BOXW / 4) + 1];
+        int* hr = h[r % 7];
+        hr[0] = __dp4a(__funnelshift_r(l, m, 8), K0, __dp4a(__funnelshift_r(m, n, 8), K1, 0u));
+        hr[1] = __dp4a(__funnelshift_r(l, m, 16), K0, __dp4a(__funnelshift_r(m, n, 16), K1, 0u));
+        hr[2] = __dp4a(__funnelshift_r(l, m, 24), K0, __dp4a(__funnelshift_r(m, n, 24), K1, 0u));
+        hr[3] = __dp4a(m, K0, __dp4a(n, K1, 0u));
+        if (r >= 6) {
+            const int j = r - 6;                          // output row yw + j uses window rows j..j+6
+            const int y = yw + j;
+            if (y < L.h) {
+                unsigned o = 0;
+#pragma unroll
+                for (int k = 0; k < 4; k++) {
+                    const int a = 18 * (h[j % 7][k] + h[(j + 6) % 7][k]) + 34 * (h[(j + 1) % 7][k] + h[(j + 5) % 7][k]) +
+                                  48 * (h[(j + 2) % 7][k] + h[(j + 4) % 7][k]) + 56 * h[(j + 3) % 7][k];
+                    o |= (unsigned)((a + 32768) >> 16) << (8 * k);
+                }
+                uint8_t* dst = out + (ptrdiff_t)y * L.pstride + x;
+                if (x + 3 < L.w) *reinterpret_cast<unsigned*>(dst) = o;
+                else for (int k = 0; k < 4; k++) if (x + k < L.w) dst[k] = (uint8_t)(o >> (8 * k));
+            }
+        }
     }
 }
 
@@ -883,13 +909,14 @@ k_describe(const uint8_t* __restrict__ pyr, const uint8_t* __restrict__ blur, co
     int m10 = 0, m01 = 0;
     if (lane < 31) {
         const int u = lane - HALF_PATCH, au = abs(u);
-#pragma unroll 1
-        for (int v = -HALF_PATCH; v <= HALF_PATCH; v++) {
-            if (au <= c_umax[abs(v)]) {
-                const int val = __ldg(c0 + (ptrdiff_t)v * L.pstride + u);
-                m10 += u * val; m01 += v * val;
-            }
-        }
+        int vals[2 * HALF_PATCH + 1];
+#pragma unroll
+        for (int v = -HALF_PATCH; v <= HALF_PATCH; v++)            // all 31 row loads in flight at once
+            vals[v + HALF_PATCH] = (au <= c_umax[v < 0 ? -v : v]) ? (int)__ldg(c0 + (ptrdiff_t)v * L.pstride + u) : 0;
+        int colsum = 0;
+#pragma unroll
+        for (int v = -HALF_PATCH; v <= HALF_PATCH; v++) { colsum += vals[v + HALF_PATCH]; m01 += v * vals[v + HALF_PATCH]; }
+        m10 = u * colsum;
     }
 #pragma unroll
     for (int o = 16; o > 0; o >>= 1) { m10 += __shfl_xor_sync(0xFFFFFFFFu, m10, o); m01 += __shfl_xor_sync(0xFFFFFFFFu, m01, o); }
@@ -1014,8 +1041,8 @@ static int make_plan(const uvip_extractor* ex, int w, int h, Plan* out, std::vec
         L.ftile_off = ft; ft += L.fntx * L.fnty;
         { const int tw = (L.ncols < FAST_CW ? L.ncols : FAST_CW) * L.wcell, th = (L.nrows < FAST_CH ? L.nrows : FAST_CH) * L.hcell;
           if (tw > max_tw) max_tw = tw; if (th > max_th) max_th = th; }
-        L.bntx = div_up(L.w + 2 * BORDER_W, BT_W); L.bnty = div_up(L.h + 2 * BORDER_W, BT_H);
-        L.btile_off = bt; bt += L.bntx * L.bnty;
+        L.bntx = div_up(L.w, BL_W); L.bnty = div_up(L.h, BL_H);
+        L.btile_off = bt; bt += L.bntx * L.bnty + 1;            // + 1 ring tile
         L.tab_off = tab; if (l > 0) tab += 2 * L.w + 2 * L.h;
         L.scale = ex->scale[l];
         L.size = (float)(int)(31 * ex->scale[l]);               // :820
@@ -1079,7 +1106,7 @@ static int ensure_plan(uvip_extractor* ex, int w, int h)
         void* fp = nullptr; cudaDriverEntryPointQueryResult qres;
         UVIP_CUDA(cudaGetDriverEntryPoint("cuTensorMapEncodeTiled", &fp, cudaEnableDefault, &qres));
         if (!fp || qres != cudaDriverEntryPointSuccess) { set_last_error("cuTensorMapEncodeTiled is not available in this driver"); return UVIP_ERR_CUDA; }
-        alignas(64) CUtensorMap maps[MAXLEV];
+        alignas(64) CUtensorMap maps[2 * MAXLEV];         // [0, MAXLEV): FAST tile boxes; [MAXLEV, 2 MAXLEV): blur tile boxes
         memset(maps, 0, sizeof(maps));
         for (int l = 0; l < P.nlevels; l++) {
             const LevelInfo& L = P.lv[l];
@@ -1091,8 +1118,13 @@ static int ensure_plan(uvip_extractor* ex, int w, int h)
                                          CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_NONE, CU_TENSOR_MAP_L2_PROMOTION_L2_128B,
                                          CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
             if (r != CUDA_SUCCESS) { set_last_error("cuTensorMapEncodeTiled(level %d) failed: %d", l, (int)r); return UVIP_ERR_CUDA; }
+            const cuuint32_t bbox[3] = {(cuuint32_t)BL_BOXW, (cuuint32_t)BL_BOXH, 1};
+            r = ((encode_fn)fp)(&maps[MAXLEV + l], CU_TENSOR_MAP_DATA_TYPE_UINT8, 3, ex->pyr.as<uint8_t>() + L.poff, gdim, gstr, bbox, estr,
+                                CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_NONE, CU_TENSOR_MAP_L2_PROMOTION_L2_128B,
+                                CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+            if (r != CUDA_SUCCESS) { set_last_error("cuTensorMapEncodeTiled(blur, level %d) failed: %d", l, (int)r); return UVIP_ERR_CUDA; }
         }
-        UVIP_CUDA(cudaMemcpy(ex->tmaps.p, maps, sizeof(CUtensorMap) * P.nlevels, cudaMemcpyHostToDevice));
+        UVIP_CUDA(cudaMemcpy(ex->tmaps.p, maps, sizeof(maps), cudaMemcpyHostToDevice));
     }
     ex->plan = P;
     return UVIP_OK;
@@ -1135,7 +1167,7 @@ static int enqueue_group(uvip_extractor* ex, const uint8_t* d_frames, int nframe
         ex->status.as<int>(), P);
     ex->launches++;
     PROF_MARK(3);
-    k_blur<<<dim3(P.btiles, nframes), 256, 0, st>>>(pyr, blur, P);
+    k_blur<<<dim3(P.btiles, nframes), 256, 0, st>>>(ex->tmaps.as<CUtensorMap>(), pyr, blur, P);
     ex->launches++;
     PROF_MARK(4);
     k_select<<<nframes, 256, 0, st>>>(ex->winners.as<unsigned>(), win_count, ex->sel.as<unsigned>(), ex->nsel.as<int>(), ex->sel_cap,
@@ -1234,7 +1266,7 @@ int uvip_extractor_create(const uvip_extractor_params* params, uvip_extractor** 
     rc |= ex->status.reserve(16);
     rc |= ex->grid.reserve(16);
     rc |= ex->incoming.reserve(sizeof(uvip_keypoint));
-    rc |= ex->tmaps.reserve(sizeof(CUtensorMap) * MAXLEV);
+    rc |= ex->tmaps.reserve(sizeof(CUtensorMap) * 2 * MAXLEV);
     if (rc) { uvip_extractor_destroy(ex); return UVIP_ERR_CUDA; }
     // zero the planes once so halo loads never see uninitialised memory
     cudaMemset(ex->pyr.p, 0, ex->pyr.cap); cudaMemset(ex->blur.p, 0, ex->blur.cap);
