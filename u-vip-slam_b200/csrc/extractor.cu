@@ -50,13 +50,15 @@ struct Plan {
     int cells_per_frame, raw_per_frame, kp_per_frame;
     int ftiles, btiles, tile_tab_off;
     int node_cap;             // quadtree node capacity (power of two)
+    unsigned rcp_cpr;         // ceil(2^32 / chunks-per-row) for the import kernel
+    int rs_boxw, rs_boxh;     // resize: TMA box of the source level
     int f_irow, f_irows, f_srow, f_srows, f_gcap, f_qcap;   // FAST shared-memory carve-up (largest tile over all levels)
     unsigned long long frame_bytes;
     LevelInfo lv[MAXLEV];
 };
 
 // --------------------------------------------------------------------------------------------------------
-// K1a: import level 0 into the padded plane (+ reflect-101 border)
+// K1a: import level 0 into the padded plane (+ reflect-101 border), 16 pixels per thread
 // --------------------------------------------------------------------------------------------------------
 __device__ __forceinline__ void store_mirrors(uint8_t* inner, int ps, int w, int h, int x, int y, uint8_t v)
 {
@@ -71,73 +73,119 @@ __device__ __forceinline__ void store_mirrors(uint8_t* inner, int ps, int w, int
         for (int i = 0; i < nx; i++)
             if (i | j) inner[(ptrdiff_t)ys[j] * ps + xs[i]] = v;
 }
-__device__ __forceinline__ bool near_edge(int x0, int y, int w, int h)
-{
-    return x0 <= BORDER_W || x0 + 3 >= w - 1 - BORDER_W || y <= BORDER_W || y >= h - 1 - BORDER_W;
-}
 
 __global__ void __launch_bounds__(256)
-k_import(const uint8_t* __restrict__ frames, int stride, size_t frame_pitch, uint8_t* __restrict__ pyr, const __grid_constant__ Plan P)
+k_import(const uint8_t* __restrict__ frames, int stride, size_t frame_pitch, int vec_ok, uint8_t* __restrict__ pyr, const __grid_constant__ Plan P)
 {
     const LevelInfo& L = P.lv[0];
-    const int f = blockIdx.z;
-    const int x0 = (blockIdx.x * 64 + (threadIdx.x & 63)) * 4;     // 4 pixels per thread
-    const int y = blockIdx.y * 4 + (threadIdx.x >> 6);
-    if (x0 >= L.w || y >= L.h) return;
+    const int f = blockIdx.y;
+    const int cpr = (L.w + 15) >> 4;                        // 16-px chunks per row
+    const int idx = blockIdx.x * 256 + threadIdx.x;
+    if (idx >= cpr * L.h) return;
+    const int y = __umulhi((unsigned)idx, P.rcp_cpr), x0 = (idx - y * cpr) << 4;
     const uint8_t* src = frames + (size_t)f * frame_pitch + (size_t)y * stride + x0;
     uint8_t* inner = pyr + (size_t)f * P.frame_bytes + L.poff + (size_t)EDGE * L.pstride + EDGE;
-    uint8_t v[4];
+    uint8_t* dst = inner + (size_t)y * L.pstride + x0;
+    const bool full = x0 + 16 <= L.w;
+    unsigned v[4] = {0, 0, 0, 0};
+    if (full && vec_ok) { const uint4 q = __ldg(reinterpret_cast<const uint4*>(src)); v[0] = q.x; v[1] = q.y; v[2] = q.z; v[3] = q.w; }
+    else {
 #pragma unroll
-    for (int k = 0; k < 4; k++) v[k] = (x0 + k < L.w) ? __ldg(src + k) : 0;
-    uint8_t* o = inner + (size_t)y * L.pstride + x0;
-    if (x0 + 3 < L.w) *reinterpret_cast<uchar4*>(o) = make_uchar4(v[0], v[1], v[2], v[3]);
-    else for (int k = 0; k < 4; k++) if (x0 + k < L.w) o[k] = v[k];     // never touch the border ring here: its owners are the mirror stores
-    if (near_edge(x0, y, L.w, L.h))
-        for (int k = 0; k < 4; k++) if (x0 + k < L.w) store_mirrors(inner, L.pstride, L.w, L.h, x0 + k, y, v[k]);
+        for (int k = 0; k < 16; k++) if (x0 + k < L.w) v[k >> 2] |= (unsigned)__ldg(src + k) << (8 * (k & 3));
+    }
+    if (full) *reinterpret_cast<uint4*>(dst) = make_uint4(v[0], v[1], v[2], v[3]);
+    else {
+#pragma unroll
+        for (int k = 0; k < 16; k++) if (x0 + k < L.w) dst[k] = (uint8_t)(v[k >> 2] >> (8 * (k & 3)));   // never touch the border ring: the mirror stores own it
+    }
+    if (x0 <= BORDER_W || x0 + 15 >= L.w - 1 - BORDER_W || y <= BORDER_W || y >= L.h - 1 - BORDER_W) {
+#pragma unroll
+        for (int k = 0; k < 16; k++)
+            if (x0 + k < L.w) store_mirrors(inner, L.pstride, L.w, L.h, x0 + k, y, (uint8_t)(v[k >> 2] >> (8 * (k & 3))));
+    }
 }
 
 // --------------------------------------------------------------------------------------------------------
-// K1b: level l from level l-1, cv::resize INTER_LINEAR 8-bit fixed point (11-bit coefficients), cascaded.
+// K1b: level l from level l-1, cv::resize INTER_LINEAR 8-bit fixed point (11-bit coefficients), cascaded
+// (src/ORBextractor.cc:982).  One CTA per 128x64 output tile; the source region arrives as one TMA box.  A thread
+// owns 4 output columns (source offsets and coefficient pairs live in registers) and walks down 8 rows; the
+// horizontal pass of a source row is one IDP.2A per pixel on a funnel-shifted word and is reused by the next output
+// row whenever that row's upper source row is this row's lower one (5 rows out of 6 at scale 1.2).
 // tables (host-built, per level): xofs[w] int32, xcoef[w] {a0,a1} int16x2, yofs[h], ycoef[h]
 // --------------------------------------------------------------------------------------------------------
+constexpr int RS_W = 128, RS_H = 64, RS_R = 8;
+
 __global__ void __launch_bounds__(256)
-k_resize(uint8_t* __restrict__ pyr, const int* __restrict__ tabs, int level, const __grid_constant__ Plan P)
+k_resize(const CUtensorMap* __restrict__ tmaps, uint8_t* __restrict__ pyr, const int* __restrict__ tabs, int level, const __grid_constant__ Plan P)
 {
+    extern __shared__ __align__(128) unsigned char s_rs[];
+    __shared__ __align__(8) uint64_t s_mbar;
     const LevelInfo& D = P.lv[level];
-    const LevelInfo& S = P.lv[level - 1];
-    const int f = blockIdx.z;
-    const int x0 = (blockIdx.x * 64 + (threadIdx.x & 63)) * 4;
-    const int y = blockIdx.y * 4 + (threadIdx.x >> 6);
-    if (x0 >= D.w || y >= D.h) return;
+    const int f = blockIdx.y, tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+    const int ntx = (D.w + RS_W - 1) / RS_W;
+    const int ty = blockIdx.x / ntx, tx = blockIdx.x - ty * ntx;
+    const int X0 = tx * RS_W, Y0 = ty * RS_H;
     const int* xofs = tabs + D.tab_off;
     const int* xcoef = xofs + D.w;
     const int* yofs = xcoef + D.w;
     const int* ycoef = yofs + D.h;
-    uint8_t* base = pyr + (size_t)f * P.frame_bytes;
-    const uint8_t* sin_ = base + S.poff + (size_t)EDGE * S.pstride + EDGE;
-    uint8_t* inner = base + D.poff + (size_t)EDGE * D.pstride + EDGE;
-    const int sy = __ldg(yofs + y);
-    const int yc = __ldg(ycoef + y);
-    const int b0 = (short)(yc & 0xFFFF), b1 = (short)(yc >> 16);
-    const uint8_t* r0p = sin_ + (size_t)sy * S.pstride;
-    const uint8_t* r1p = r0p + S.pstride;            // row sy+1 is valid memory (border) when sy == h-1, and b1 == 0 there
-    uint8_t v[4];
-#pragma unroll
-    for (int k = 0; k < 4; k++) {
-        const int x = min(x0 + k, D.w - 1);
-        const int sx = __ldg(xofs + x);
-        const int xc = __ldg(xcoef + x);
-        const int a0 = (short)(xc & 0xFFFF), a1 = (short)(xc >> 16);
-        const int h0 = (int)__ldg(r0p + sx) * a0 + (int)__ldg(r0p + sx + 1) * a1;
-        const int h1 = (int)__ldg(r1p + sx) * a0 + (int)__ldg(r1p + sx + 1) * a1;
-        int o = (((b0 * (h0 >> 4)) >> 16) + ((b1 * (h1 >> 4)) >> 16) + 2) >> 2;
-        v[k] = (uint8_t)min(max(o, 0), 255);
+    const int bx = (__ldg(xofs + X0) + EDGE) & ~15;        // padded source coords of the box origin (16 B aligned for TMA)
+    const int by = __ldg(yofs + Y0) + EDGE;
+    if (tid == 0) { mbar_init(&s_mbar, 1); mbar_fence_init(); }
+    __syncthreads();
+    if (tid == 0) {
+        mbar_arrive_expect_tx(&s_mbar, (unsigned)(P.rs_boxw * P.rs_boxh));
+        tma_load_3d(s_rs, tmaps + 2 * MAXLEV + (level - 1), bx, by, f, &s_mbar);
     }
-    uint8_t* o = inner + (size_t)y * D.pstride + x0;
-    if (x0 + 3 < D.w) *reinterpret_cast<uchar4*>(o) = make_uchar4(v[0], v[1], v[2], v[3]);
-    else for (int k = 0; k < 4; k++) if (x0 + k < D.w) o[k] = v[k];
-    if (near_edge(x0, y, D.w, D.h))
-        for (int k = 0; k < 4; k++) if (x0 + k < D.w) store_mirrors(inner, D.pstride, D.w, D.h, x0 + k, y, v[k]);
+    const int x = X0 + 4 * lane;
+    const int yw = Y0 + RS_R * warp;
+    const bool live = x < D.w && yw < D.h;
+    int wk[4], sh[4]; unsigned ck[4];
+    if (live) {
+#pragma unroll
+        for (int k = 0; k < 4; k++) {
+            const int xk = min(x + k, D.w - 1);
+            const int s = __ldg(xofs + xk) + EDGE - bx;    // byte offset inside a box row
+            wk[k] = s >> 2; sh[k] = (s & 3) << 3; ck[k] = (unsigned)__ldg(xcoef + xk);
+        }
+    }
+    mbar_wait(&s_mbar, 0);
+    if (!live) return;
+    const unsigned* S = reinterpret_cast<const unsigned*>(s_rs);
+    const int rw = P.rs_boxw >> 2;
+    uint8_t* inner = pyr + (size_t)f * P.frame_bytes + D.poff + (size_t)EDGE * D.pstride + EDGE;
+    const bool edge_tile = X0 <= BORDER_W || X0 + RS_W >= D.w - 1 - BORDER_W || Y0 <= BORDER_W || Y0 + RS_H >= D.h - 1 - BORDER_W;
+    int prev_sy = -100, h1[4] = {0, 0, 0, 0};
+#pragma unroll 2
+    for (int j = 0; j < RS_R; j++) {
+        const int y = yw + j;
+        if (y >= D.h) break;
+        const int sy = __ldg(yofs + y) + EDGE - by;
+        const int yc = __ldg(ycoef + y);
+        const int b0 = (short)(yc & 0xFFFF), b1 = (short)(yc >> 16);
+        const unsigned* R0 = S + sy * rw;
+        const unsigned* R1 = R0 + rw;                      // row sy+1 is valid (border row) when sy is the last row, and b1 == 0 there
+        int h0[4];
+        const bool reuse = sy == prev_sy + 1;
+#pragma unroll
+        for (int k = 0; k < 4; k++) {
+            h0[k] = reuse ? h1[k] : (int)__dp2a_lo(ck[k], __funnelshift_r(R0[wk[k]], R0[wk[k] + 1], sh[k]), 0u);
+            h1[k] = (int)__dp2a_lo(ck[k], __funnelshift_r(R1[wk[k]], R1[wk[k] + 1], sh[k]), 0u);
+        }
+        prev_sy = sy;
+        unsigned o = 0; uint8_t ob[4];
+#pragma unroll
+        for (int k = 0; k < 4; k++) {
+            int v = (((b0 * (h0[k] >> 4)) >> 16) + ((b1 * (h1[k] >> 4)) >> 16) + 2) >> 2;
+            v = min(max(v, 0), 255);
+            ob[k] = (uint8_t)v; o |= (unsigned)v << (8 * k);
+        }
+        uint8_t* dst = inner + (size_t)y * D.pstride + x;
+        if (x + 3 < D.w) *reinterpret_cast<unsigned*>(dst) = o;
+        else for (int k = 0; k < 4; k++) if (x + k < D.w) dst[k] = ob[k];
+        if (edge_tile)
+            for (int k = 0; k < 4; k++) if (x + k < D.w) store_mirrors(inner, D.pstride, D.w, D.h, x + k, y, ob[k]);
+    }
 }
 
 // --------------------------------------------------------------------------------------------------------
@@ -1059,6 +1107,31 @@ static int make_plan(const uvip_extractor* ex, int w, int h, Plan* out, std::vec
         P.f_srow = (int)align_up((size_t)max_tw + 2, 4); P.f_srows = max_th + 2;
         P.f_gcap = (ngx_max * max_th + 1) & ~1; P.f_qcap = (max_tw * max_th + 1) & ~1;
     }
+    P.rcp_cpr = 0xFFFFFFFFu / (unsigned)((P.lv[0].w + 15) >> 4) + 1u;
+    {
+        // source extent of a 128x64 output tile: exact maximum over all tiles of all levels (tables are exact)
+        int bw = 16, bh = 2;
+        std::vector<int> ofs;
+        for (int l = 1; l < p.nlevels; l++) {
+            const LevelInfo& D = P.lv[l]; const LevelInfo& S = P.lv[l - 1];
+            ofs.assign(2 * (D.w > D.h ? D.w : D.h), 0);
+            build_axis_table(S.w, D.w, ofs.data(), ofs.data() + D.w);
+            for (int X0 = 0; X0 < D.w; X0 += RS_W) {
+                const int X1 = (X0 + RS_W < D.w ? X0 + RS_W : D.w) - 1;
+                const int bx = (ofs[X0] + EDGE) & ~15;
+                const int need = ofs[X1] + EDGE + 2 - bx + 3;       // + next pixel, + funnel-shift over-read of one word
+                if (need > bw) bw = need;
+            }
+            build_axis_table(S.h, D.h, ofs.data(), ofs.data() + D.h);
+            for (int Y0 = 0; Y0 < D.h; Y0 += RS_H) {
+                const int Y1 = (Y0 + RS_H < D.h ? Y0 + RS_H : D.h) - 1;
+                const int need = ofs[Y1] + 2 - ofs[Y0];
+                if (need > bh) bh = need;
+            }
+        }
+        P.rs_boxw = (int)align_up((size_t)bw + 4, 16); P.rs_boxh = bh;
+        if (P.rs_boxw > 256 || P.rs_boxh > 256) { set_last_error("scale factor too large for the resize tile"); return UVIP_ERR_UNSUPPORTED; }
+    }
     P.tile_tab_off = tab;
     if (tabs) {
         tabs->assign(tab + ft + 1, 0);
@@ -1097,6 +1170,7 @@ static int ensure_plan(uvip_extractor* ex, int w, int h)
     UVIP_CUDA(cudaStreamSynchronize(ex->stream));
     UVIP_CUDA(cudaFuncSetAttribute(k_quadtree, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)qt_smem_bytes(P.node_cap)));
     UVIP_CUDA(cudaFuncSetAttribute(k_fast, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)fast_smem_bytes(P)));
+    UVIP_CUDA(cudaFuncSetAttribute(k_resize, cudaFuncAttributeMaxDynamicSharedMemorySize, P.rs_boxw * P.rs_boxh + 128));
     UVIP_CUDA(cudaMemcpy(ex->tabs.p, tabs.data(), tabs.size() * sizeof(int), cudaMemcpyHostToDevice));
     // TMA descriptors of the pyramid planes: (x bytes, rows, frame) with a box of one FAST tile
     {
@@ -1106,7 +1180,7 @@ static int ensure_plan(uvip_extractor* ex, int w, int h)
         void* fp = nullptr; cudaDriverEntryPointQueryResult qres;
         UVIP_CUDA(cudaGetDriverEntryPoint("cuTensorMapEncodeTiled", &fp, cudaEnableDefault, &qres));
         if (!fp || qres != cudaDriverEntryPointSuccess) { set_last_error("cuTensorMapEncodeTiled is not available in this driver"); return UVIP_ERR_CUDA; }
-        alignas(64) CUtensorMap maps[2 * MAXLEV];         // [0, MAXLEV): FAST tile boxes; [MAXLEV, 2 MAXLEV): blur tile boxes
+        alignas(64) CUtensorMap maps[3 * MAXLEV];         // FAST tile boxes | blur tile boxes | resize source boxes
         memset(maps, 0, sizeof(maps));
         for (int l = 0; l < P.nlevels; l++) {
             const LevelInfo& L = P.lv[l];
@@ -1123,6 +1197,11 @@ static int ensure_plan(uvip_extractor* ex, int w, int h)
                                 CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_NONE, CU_TENSOR_MAP_L2_PROMOTION_L2_128B,
                                 CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
             if (r != CUDA_SUCCESS) { set_last_error("cuTensorMapEncodeTiled(blur, level %d) failed: %d", l, (int)r); return UVIP_ERR_CUDA; }
+            const cuuint32_t rbox[3] = {(cuuint32_t)P.rs_boxw, (cuuint32_t)P.rs_boxh, 1};
+            r = ((encode_fn)fp)(&maps[2 * MAXLEV + l], CU_TENSOR_MAP_DATA_TYPE_UINT8, 3, ex->pyr.as<uint8_t>() + L.poff, gdim, gstr, rbox, estr,
+                                CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_NONE, CU_TENSOR_MAP_L2_PROMOTION_L2_128B,
+                                CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+            if (r != CUDA_SUCCESS) { set_last_error("cuTensorMapEncodeTiled(resize, level %d) failed: %d", l, (int)r); return UVIP_ERR_CUDA; }
         }
         UVIP_CUDA(cudaMemcpy(ex->tmaps.p, maps, sizeof(maps), cudaMemcpyHostToDevice));
     }
@@ -1147,14 +1226,15 @@ static int enqueue_group(uvip_extractor* ex, const uint8_t* d_frames, int nframe
     PROF_MARK(0);
     {
         const LevelInfo& L = P.lv[0];
-        dim3 g(div_up(L.w, 256), div_up(L.h, 4), nframes);
-        k_import<<<g, 256, 0, st>>>(d_frames, stride, frame_pitch, pyr, P);
+        const int chunks = ((L.w + 15) >> 4) * L.h;
+        const int vec_ok = (((uintptr_t)d_frames & 15) == 0 && (stride & 15) == 0 && (frame_pitch & 15) == 0) ? 1 : 0;
+        k_import<<<dim3(div_up(chunks, 256), nframes), 256, 0, st>>>(d_frames, stride, frame_pitch, vec_ok, pyr, P);
         ex->launches++;
     }
     for (int l = 1; l < P.nlevels; l++) {
         const LevelInfo& L = P.lv[l];
-        dim3 g(div_up(L.w, 256), div_up(L.h, 4), nframes);
-        k_resize<<<g, 256, 0, st>>>(pyr, ex->tabs.as<int>(), l, P);
+        k_resize<<<dim3(div_up(L.w, RS_W) * div_up(L.h, RS_H), nframes), 256, (size_t)P.rs_boxw * P.rs_boxh + 128, st>>>(
+            ex->tmaps.as<CUtensorMap>(), pyr, ex->tabs.as<int>(), l, P);
         ex->launches++;
     }
     PROF_MARK(1);
@@ -1266,7 +1346,7 @@ int uvip_extractor_create(const uvip_extractor_params* params, uvip_extractor** 
     rc |= ex->status.reserve(16);
     rc |= ex->grid.reserve(16);
     rc |= ex->incoming.reserve(sizeof(uvip_keypoint));
-    rc |= ex->tmaps.reserve(sizeof(CUtensorMap) * 2 * MAXLEV);
+    rc |= ex->tmaps.reserve(sizeof(CUtensorMap) * 3 * MAXLEV);
     if (rc) { uvip_extractor_destroy(ex); return UVIP_ERR_CUDA; }
     // zero the planes once so halo loads never see uninitialised memory
     cudaMemset(ex->pyr.p, 0, ex->pyr.cap); cudaMemset(ex->blur.p, 0, ex->blur.cap);
