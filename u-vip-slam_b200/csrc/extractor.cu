@@ -62,16 +62,16 @@ struct Plan {
 // --------------------------------------------------------------------------------------------------------
 __device__ __forceinline__ void store_mirrors(uint8_t* inner, int ps, int w, int h, int x, int y, uint8_t v)
 {
-    // write the reflections of interior pixel (x,y) that fall into the BORDER_W-wide border ring
-    int xs[3], ys[3], nx = 1, ny = 1;
-    xs[0] = x; ys[0] = y;
-    if (x >= 1 && x <= BORDER_W) xs[nx++] = -x;
-    if (x >= w - 1 - BORDER_W && x <= w - 2) xs[nx++] = 2 * (w - 1) - x;
-    if (y >= 1 && y <= BORDER_W) ys[ny++] = -y;
-    if (y >= h - 1 - BORDER_W && y <= h - 2) ys[ny++] = 2 * (h - 1) - y;
-    for (int j = 0; j < ny; j++)
-        for (int i = 0; i < nx; i++)
-            if (i | j) inner[(ptrdiff_t)ys[j] * ps + xs[i]] = v;
+    // write the reflections of interior pixel (x,y) that fall into the BORDER_W-wide border ring (reflect-101)
+    const bool l = x >= 1 && x <= BORDER_W, r = x >= w - 1 - BORDER_W && x <= w - 2;
+    const bool t = y >= 1 && y <= BORDER_W, b = y >= h - 1 - BORDER_W && y <= h - 2;
+    if (!(l | r | t | b)) return;
+    const int xl = -x, xr = 2 * (w - 1) - x;
+    uint8_t* row = inner + (ptrdiff_t)y * ps;
+    if (l) row[xl] = v;
+    if (r) row[xr] = v;
+    if (t) { uint8_t* q = inner + (ptrdiff_t)(-y) * ps; q[x] = v; if (l) q[xl] = v; if (r) q[xr] = v; }
+    if (b) { uint8_t* q = inner + (ptrdiff_t)(2 * (h - 1) - y) * ps; q[x] = v; if (l) q[xl] = v; if (r) q[xr] = v; }
 }
 
 __global__ void __launch_bounds__(256)
@@ -99,7 +99,7 @@ k_import(const uint8_t* __restrict__ frames, int stride, size_t frame_pitch, int
         for (int k = 0; k < 16; k++) if (x0 + k < L.w) dst[k] = (uint8_t)(v[k >> 2] >> (8 * (k & 3)));   // never touch the border ring: the mirror stores own it
     }
     if (x0 <= BORDER_W || x0 + 15 >= L.w - 1 - BORDER_W || y <= BORDER_W || y >= L.h - 1 - BORDER_W) {
-#pragma unroll
+#pragma unroll 1
         for (int k = 0; k < 16; k++)
             if (x0 + k < L.w) store_mirrors(inner, L.pstride, L.w, L.h, x0 + k, y, (uint8_t)(v[k >> 2] >> (8 * (k & 3))));
     }
@@ -154,7 +154,7 @@ k_resize(const CUtensorMap* __restrict__ tmaps, uint8_t* __restrict__ pyr, const
     const unsigned* S = reinterpret_cast<const unsigned*>(s_rs);
     const int rw = P.rs_boxw >> 2;
     uint8_t* inner = pyr + (size_t)f * P.frame_bytes + D.poff + (size_t)EDGE * D.pstride + EDGE;
-    const bool edge_tile = X0 <= BORDER_W || X0 + RS_W >= D.w - 1 - BORDER_W || Y0 <= BORDER_W || Y0 + RS_H >= D.h - 1 - BORDER_W;
+    const bool edge_col = x <= BORDER_W || x + 3 >= D.w - 1 - BORDER_W;      // this thread's 4 columns touch the mirror zone
     int prev_sy = -100, h1[4] = {0, 0, 0, 0};
 #pragma unroll 2
     for (int j = 0; j < RS_R; j++) {
@@ -173,18 +173,20 @@ k_resize(const CUtensorMap* __restrict__ tmaps, uint8_t* __restrict__ pyr, const
             h1[k] = (int)__dp2a_lo(ck[k], __funnelshift_r(R1[wk[k]], R1[wk[k] + 1], sh[k]), 0u);
         }
         prev_sy = sy;
-        unsigned o = 0; uint8_t ob[4];
+        unsigned o = 0;
 #pragma unroll
         for (int k = 0; k < 4; k++) {
-            int v = (((b0 * (h0[k] >> 4)) >> 16) + ((b1 * (h1[k] >> 4)) >> 16) + 2) >> 2;
-            v = min(max(v, 0), 255);
-            ob[k] = (uint8_t)v; o |= (unsigned)v << (8 * k);
+            // <= 255 by construction: coefficient pairs sum to at most 2049 on each axis
+            const int v = (((b0 * (h0[k] >> 4)) >> 16) + ((b1 * (h1[k] >> 4)) >> 16) + 2) >> 2;
+            o |= (unsigned)v << (8 * k);
         }
         uint8_t* dst = inner + (size_t)y * D.pstride + x;
         if (x + 3 < D.w) *reinterpret_cast<unsigned*>(dst) = o;
-        else for (int k = 0; k < 4; k++) if (x + k < D.w) dst[k] = ob[k];
-        if (edge_tile)
-            for (int k = 0; k < 4; k++) if (x + k < D.w) store_mirrors(inner, D.pstride, D.w, D.h, x + k, y, ob[k]);
+        else for (int k = 0; k < 4; k++) if (x + k < D.w) dst[k] = (uint8_t)(o >> (8 * k));
+        if (edge_col || y <= BORDER_W || y >= D.h - 1 - BORDER_W) {
+#pragma unroll 1
+            for (int k = 0; k < 4; k++) if (x + k < D.w) store_mirrors(inner, D.pstride, D.w, D.h, x + k, y, (uint8_t)(o >> (8 * k)));
+        }
     }
 }
 
