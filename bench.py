@@ -36,6 +36,9 @@ def parse():
     ap.add_argument('--batch', type=int, default=256, help='frames per step and per GPU')
     ap.add_argument('--ref-frames', type=int, default=0, help='frames per step of the reference arm (0 = 4 x cores)')
     ap.add_argument('--no-extras', action='store_true', help='skip the Hamming-only and cpu_baseline legs')
+    ap.add_argument('--workload', default='frames', choices=['frames', 'knn'],
+                    help="'frames' = the headline metric; 'knn' = BASELINE config 4: database-sharded brute-force kNN2 with NCCL top-2 merge")
+    ap.add_argument('--knn-n', type=int, default=262144, help='rows of the query and train sets for --workload knn (config 4 is 1048576)')
     return ap.parse_args()
 
 
@@ -335,6 +338,68 @@ def run_ours(args):
     return 0
 
 
+def run_knn(args):
+    """config 4: nq x nt brute-force kNN2, train rows sharded contiguously over the ranks, queries replicated, per-query
+    top-2 all-gathered over NCCL and merged by (distance, global index).  value = descriptor pairs per second."""
+    import ctypes as C
+    import numpy as np
+    import torch
+    import __graft_entry__ as ge
+    pkg = ge.load_package()
+    rank = int(os.environ.get('RANK', '0')); world = int(os.environ.get('WORLD_SIZE', '1')); local = int(os.environ.get('LOCAL_RANK', '0'))
+    torch.cuda.set_device(local)
+    dev = torch.device('cuda', local)
+    dist = None
+    if world > 1:
+        import torch.distributed as dist
+        dist.init_process_group('nccl', device_id=dev)
+    n = args.knn_n
+    T, Q = pkg.synth.knn_database(n, n)
+    b = pkg.sharding.shard_bounds(n, world)
+    dq = torch.from_numpy(Q).to(dev); dt = torch.from_numpy(T[b[rank]:b[rank + 1]]).to(dev)
+    m = pkg.ORBmatcher(0.75, True, device=local)
+    stream = torch.cuda.Stream(dev); torch.cuda.set_stream(stream)
+    K, Wm = args.steps, max(args.warmup, 3)
+    for _ in range(Wm):
+        oi, od = pkg.sharding.gpu_sharded_knn2(pkg, m, dq, dt, b[rank], world, dist, stream.cuda_stream)
+    torch.cuda.synchronize(dev)
+    if world > 1:
+        dist.barrier()
+    clocks = ClockSampler(local); clocks.start()
+    e0 = torch.cuda.Event(enable_timing=True); e1 = torch.cuda.Event(enable_timing=True)
+    e0.record(stream)
+    for _ in range(K):
+        oi, od = pkg.sharding.gpu_sharded_knn2(pkg, m, dq, dt, b[rank], world, dist, stream.cuda_stream)
+    e1.record(stream)
+    torch.cuda.synchronize(dev)
+    if world > 1:
+        dist.barrier()
+    ms = e0.elapsed_time(e1)
+    clk = clocks.stop()
+    if world > 1:
+        tt = torch.tensor([ms], dtype=torch.float64, device=dev); dist.all_reduce(tt, op=dist.ReduceOp.MAX); ms = float(tt.item())
+    pps = float(n) * n * K / (ms * 1e-3)
+    check = None
+    if rank == 0 and n <= 65536:
+        from oracle import oracle as O
+        ri, rd = O.knn2(Q[:2048], T)
+        check = bool(np.array_equal(oi[:2048].cpu().numpy(), ri) and np.array_equal(od[:2048].cpu().numpy(), rd))
+    if rank == 0:
+        popc = C.c_double(); pkg.capi.check(pkg.capi.lib().uvip_popc_peak(local, 4096, C.byref(popc)))
+        print(json.dumps({'metric': 'Hamming pairs/s (brute-force kNN2, database sharded over GPUs, NCCL top-2 merge)', 'value': pps,
+                          'unit': 'pairs/s', 'n_gpus': world, 'steps': K, 'warmup': Wm, 'ms_per_step': ms / K, 'higher_is_better': True,
+                          'scaling': 'strong', 'vs_baseline': None, 'dtype': 'u32 popc', 'data': 'synthetic',
+                          'config': {'workload': 'BASELINE config 4 shape: %d x %d 256-bit descriptors, ratio 0.75' % (n, n)},
+                          'clocks': clk, 'roofline': {'bound': 'popc', 'popc_per_pair': 8, 'achieved_popc_per_s': pps * 8,
+                                                      'peak_popc_per_s_measured_one_gpu': popc.value, 'frac_of_n_gpus': pps * 8 / (popc.value * world)},
+                          'matches_oracle_first_2048_queries': check}), flush=True)
+    if world > 1:
+        dist.destroy_process_group()
+    return 0
+
+
 if __name__ == '__main__':
     a = parse()
-    sys.exit(run_reference(a) if a.impl == 'reference' else run_ours(a))
+    if a.impl == 'reference':
+        sys.exit(run_reference(a))
+    sys.exit(run_knn(a) if a.workload == 'knn' else run_ours(a))

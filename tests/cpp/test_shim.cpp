@@ -1,0 +1,90 @@
+// C++ host-shim test: drives USLAM::ORBextractor / USLAM::ORBmatcher (u-vip-slam_b200/host) exactly the way
+// Tracking.cc does (src/Tracking.cc:893-964, :2177-2231) and dumps the results for the pytest harness, which
+// compares them with the CPU oracle.  usage: test_shim <in.bin> <out.bin>
+//   in.bin : int32 w, h, nfeatures, fastTh, min_px_dist, num_needed ; w*h bytes image
+//   out.bin: [full detect] int32 n ; n*28 B keypoints ; n*32 B descriptors ; [grid path] same + grid ints ;
+//            [matcher] int32 nmatches ; nq int32 (keypoint index per map point or -1)
+#include <cstdio>
+#include <cstdlib>
+#include <vector>
+#include "../../u-vip-slam_b200/host/ORBextractor.h"
+#include "../../u-vip-slam_b200/host/ORBmatcher.h"
+
+struct MockMapPoint {
+    bool mbTrackInView = true; int mnTrackScaleLevel = 0; float mTrackViewCos = 0.9f, mTrackProjX = 0, mTrackProjY = 0;
+    cv::Mat desc; bool bad = false;
+    bool isBad() const { return bad; }
+    cv::Mat GetDescriptor() const { return desc; }
+};
+struct MockFrame {
+    std::vector<cv::KeyPoint> mvKeysUn; cv::Mat mDescriptors; std::vector<MockMapPoint*> mvpMapPoints; std::vector<float> mvScaleFactors;
+    int mnMinX = 0, mnMinY = 0; float mfGridElementWidthInv = 0, mfGridElementHeightInv = 0;
+};
+
+static void put(FILE* f, const void* p, size_t n) { if (fwrite(p, 1, n, f) != n) { perror("write"); exit(2); } }
+
+int main(int argc, char** argv)
+{
+    if (argc < 3) { fprintf(stderr, "usage: test_shim in.bin out.bin\n"); return 2; }
+    FILE* fi = fopen(argv[1], "rb"); if (!fi) { perror("in"); return 2; }
+    int hdr[6]; if (fread(hdr, 4, 6, fi) != 6) return 2;
+    const int w = hdr[0], h = hdr[1], nfeatures = hdr[2], fastTh = hdr[3]; int min_px_dist = hdr[4]; const int num_needed = hdr[5];
+    std::vector<unsigned char> pix((size_t)w * h);
+    if (fread(pix.data(), 1, pix.size(), fi) != pix.size()) return 2;
+    fclose(fi);
+    FILE* fo = fopen(argv[2], "wb"); if (!fo) { perror("out"); return 2; }
+    try {
+        USLAM::ORBextractor ex(nfeatures, 1.2f, 8, USLAM::ORBextractor::FAST_SCORE, fastTh);
+        cv::Mat img(h, w, CV_8UC1, pix.data(), (size_t)w);
+        // 1. full detection, as in the NOT_INITIALIZED / LOST states (Tracking.cc:942-946)
+        std::vector<cv::KeyPoint> kps; cv::Mat desc;
+        Eigen::MatrixXi grid = Eigen::MatrixXi::Zero(h / min_px_dist + 2, w / min_px_dist + 2);
+        ex(img, cv::Mat(), kps, desc, grid, min_px_dist, true, 0);
+        int n = (int)kps.size();
+        put(fo, &n, 4); put(fo, kps.data(), (size_t)n * 28);
+        for (int i = 0; i < n; i++) put(fo, desc.ptr(i), 32);
+        // 2. replenishing detection while WORKING: existing points mark the grid (Tracking.cc:901-909)
+        std::vector<cv::KeyPoint> kps2(kps.begin(), kps.begin() + (n < 20 ? n : 20));
+        for (auto& k : kps2) { k.pt.x = (float)(int)k.pt.x; k.pt.y = (float)(int)k.pt.y; k.octave = 0; }
+        for (const auto& k : kps2) grid((int)(k.pt.y / min_px_dist), (int)(k.pt.x / min_px_dist))++;
+        cv::Mat desc2;
+        ex(img, cv::Mat(), kps2, desc2, grid, min_px_dist, false, num_needed);
+        int n2 = (int)kps2.size();
+        put(fo, &n2, 4); put(fo, kps2.data(), (size_t)n2 * 28);
+        for (int i = 0; i < n2; i++) put(fo, desc2.ptr(i), 32);
+        int gr = grid.rows(), gc = grid.cols();
+        put(fo, &gr, 4); put(fo, &gc, 4); put(fo, grid.data(), (size_t)gr * gc * 4);
+        // empty image: silent return, outputs untouched
+        std::vector<cv::KeyPoint> keep(3); cv::Mat keepd;
+        ex(cv::Mat(), cv::Mat(), keep, keepd, grid, min_px_dist, true, 0);
+        int untouched = keep.size() == 3 ? 1 : 0; put(fo, &untouched, 4);
+        // 3. SearchByProjection: project every detected keypoint back as a map point with a slightly wrong position
+        MockFrame F;
+        F.mvKeysUn = kps; F.mDescriptors = desc; F.mvpMapPoints.assign((size_t)n, nullptr);
+        F.mvScaleFactors.resize(8); F.mvScaleFactors[0] = 1.0f;
+        for (int i = 1; i < 8; i++) F.mvScaleFactors[i] = F.mvScaleFactors[i - 1] * ex.GetScaleFactor();
+        F.mfGridElementWidthInv = 64.0f / (float)w; F.mfGridElementHeightInv = 48.0f / (float)h;
+        std::vector<MockMapPoint> mps((size_t)n); std::vector<MockMapPoint*> vp;
+        for (int i = 0; i < n; i++) {
+            mps[i].mTrackProjX = kps[i].pt.x + ((i % 5) - 2) * 0.7f; mps[i].mTrackProjY = kps[i].pt.y + ((i % 3) - 1) * 0.9f;
+            mps[i].mnTrackScaleLevel = kps[i].octave; mps[i].mTrackViewCos = (i & 1) ? 0.9990f : 0.9f;
+            mps[i].mbTrackInView = (i % 11) != 0; mps[i].bad = (i % 13) == 0;
+            mps[i].desc = desc.row(i);
+            vp.push_back(&mps[i]);
+        }
+        USLAM::ORBmatcher matcher(0.8f);
+        const int nm = matcher.SearchByProjection(F, vp, 1.0f);
+        put(fo, &nm, 4);
+        std::vector<int> owner((size_t)n, -1);
+        for (int i = 0; i < n; i++) if (F.mvpMapPoints[i]) owner[i] = (int)(F.mvpMapPoints[i] - mps.data());
+        put(fo, owner.data(), (size_t)n * 4);
+        int dd = USLAM::ORBmatcher::DescriptorDistance(desc.row(0), desc.row(n > 1 ? 1 : 0));
+        put(fo, &dd, 4);
+    } catch (const std::exception& e) {
+        fprintf(stderr, "shim error: %s\n", e.what());
+        fclose(fo);
+        return 3;
+    }
+    fclose(fo);
+    return 0;
+}

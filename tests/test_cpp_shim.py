@@ -1,0 +1,105 @@
+"""The C++ drop-in shim (u-vip-slam_b200/host/ORBextractor.h, ORBmatcher.h): same class names and call signatures as
+the reference's include/ORBextractor.h / include/ORBmatcher.h, forwarding to the C-ABI.  CPU: it compiles and links
+against libuvip_orb.so and fails loudly without a device.  GPU: driven the way Tracking.cc drives it and compared with
+the oracle."""
+import os
+import struct
+import subprocess
+
+import numpy as np
+import pytest
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+
+
+@pytest.fixture(scope='module')
+def shim_exe(pkg, tmp_path_factory):
+    pkg.capi.lib()
+    out = str(tmp_path_factory.mktemp('shim') / 'test_shim')
+    libdir = os.path.join(ROOT, 'u-vip-slam_b200')
+    cxx = '/usr/bin/g++' if os.path.exists('/usr/bin/g++') else 'g++'
+    subprocess.check_call([cxx, '-std=c++14', '-O2', '-Wall', '-Werror', '-o', out, os.path.join(ROOT, 'tests', 'cpp', 'test_shim.cpp'),
+                           '-L', libdir, '-luvip_orb', '-Wl,-rpath,' + libdir])
+    return out
+
+
+def _write_input(path, img, nfeatures, fast_th, mpd, need):
+    h, w = img.shape
+    with open(path, 'wb') as f:
+        f.write(struct.pack('6i', w, h, nfeatures, fast_th, mpd, need))
+        f.write(np.ascontiguousarray(img, np.uint8).tobytes())
+
+
+def test_shim_compiles_and_refuses_without_device(pkg, synth, shim_exe, tmp_path):
+    if pkg.capi.lib().uvip_device_count() > 0:
+        pytest.skip('a CUDA device is present')
+    _write_input(tmp_path / 'in.bin', synth.synth_frame(3, 320, 240), 300, 20, 20, 100)
+    r = subprocess.run([shim_exe, str(tmp_path / 'in.bin'), str(tmp_path / 'out.bin')], capture_output=True, text=True)
+    assert r.returncode == 3 and 'no CPU fallback' in r.stderr
+
+
+@pytest.mark.gpu
+def test_shim_matches_oracle(pkg, oracle, synth, shim_exe, tmp_path):
+    W, H, NF, TH, MPD, NEED = 752, 480, 1000, 20, 20, 300
+    img = synth.synth_frame(1, W, H)
+    _write_input(tmp_path / 'in.bin', img, NF, TH, MPD, NEED)
+    r = subprocess.run([shim_exe, str(tmp_path / 'in.bin'), str(tmp_path / 'out.bin')], capture_output=True, text=True)
+    assert r.returncode == 0, r.stderr
+    buf = open(tmp_path / 'out.bin', 'rb').read()
+    KP = pkg.capi.KP_DTYPE
+    off = 0
+
+    def take(dtype, count):
+        nonlocal off
+        a = np.frombuffer(buf, dtype, count, off); off += a.nbytes
+        return a
+
+    # 1. full detection
+    n = int(take(np.int32, 1)[0]); kps = take(KP, n); desc = take(np.uint8, n * 32).reshape(n, 32)
+    oex = oracle.Extractor(NF, 1.2, 8, 1, TH)
+    okps, odesc = oex(img)
+    assert n == len(okps)
+    for fld in ('x', 'y', 'size', 'response', 'octave', 'class_id'):
+        assert np.array_equal(kps[fld], okps[fld]), fld
+    assert np.abs(kps['angle'] - okps['angle']).max() <= 1e-3 * 180 / np.pi
+    assert 1.0 - np.unpackbits(desc ^ odesc).mean() >= 0.999
+    # 2. replenishing detection on the caller's occupancy grid
+    n2 = int(take(np.int32, 1)[0]); kps2 = take(KP, n2); desc2 = take(np.uint8, n2 * 32).reshape(n2, 32)
+    gr, gc = [int(v) for v in take(np.int32, 2)]
+    grid = take(np.int32, gr * gc).reshape(gc, gr).T            # column-major
+    inc = okps[:20].copy(); inc['x'] = np.floor(inc['x']); inc['y'] = np.floor(inc['y']); inc['octave'] = 0
+    og = np.zeros((H // MPD + 2, W // MPD + 2), np.int32, order='F')
+    for k in inc:
+        og[int(k['y'] / MPD), int(k['x'] / MPD)] += 1
+    okps2, odesc2 = oex(img, keypoints=inc, grid=og, min_px_dist=MPD, full_detect=False, num_needed=NEED)
+    assert n2 == len(okps2) and (gr, gc) == og.shape and np.array_equal(grid, og)
+    for fld in ('x', 'y', 'size', 'response', 'octave', 'class_id'):
+        assert np.array_equal(kps2[fld], okps2[fld]), fld
+    assert 1.0 - np.unpackbits(desc2 ^ odesc2).mean() >= 0.999
+    assert int(take(np.int32, 1)[0]) == 1                        # empty image left the outputs untouched
+    # 3. SearchByProjection through the matcher shim, claims included
+    nm = int(take(np.int32, 1)[0]); owner = take(np.int32, n)
+    i = np.arange(n)
+    u = (okps['x'] + ((i % 5) - 2).astype(np.float32) * np.float32(0.7)).astype(np.float32)
+    v = (okps['y'] + ((i % 3) - 1).astype(np.float32) * np.float32(0.9)).astype(np.float32)
+    lvl = okps['octave'].astype(np.int32)
+    cosv = np.where(i & 1, np.float32(0.9990), np.float32(0.9)).astype(np.float32)
+    use = ((i % 11) != 0) & ((i % 13) != 0)
+    sf = [np.float32(1)]
+    for _ in range(7):
+        sf.append(np.float32(sf[-1] * np.float32(1.2)))
+    sf = np.array(sf, np.float32)
+    r_ = np.array([oracle.lib().uo_radius_by_viewing_cos(float(c)) for c in cosv], np.float32) * sf[lvl]
+    inv_w = np.float32(64.0) / np.float32(W); inv_h = np.float32(48.0) / np.float32(H)
+    start, items = oracle.grid_build(okps['x'], okps['y'], 0.0, 0.0, float(inv_w), float(inv_h))
+    q = np.nonzero(use)[0]
+    on, omatch, otaken = oracle.search_window(0, 100, np.float32(0.8), u[q], v[q], r_[q].astype(np.float32), lvl[q] - 1, lvl[q], odesc[q],
+                                              okps['x'], okps['y'], lvl, odesc, start, items, 0.0, 0.0, float(inv_w), float(inv_h))
+    assert nm == on and nm > 500
+    expect_owner = np.full(n, -1, np.int32)
+    for qi, k in enumerate(omatch):
+        if k >= 0:
+            expect_owner[k] = q[qi]
+    assert np.array_equal(owner, expect_owner)
+    dd = int(take(np.int32, 1)[0])
+    assert dd == oracle.descriptor_distance(odesc[0], odesc[1])

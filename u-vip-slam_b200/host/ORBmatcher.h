@@ -1,0 +1,135 @@
+// ORBmatcher.h — drop-in for the descriptor path of the reference's include/ORBmatcher.h (chintha/U-VIP-SLAM, :41-94).
+// Same class name, constructor, constants and call signatures; the pointer-rich containers of the reference
+// (FrameKTL, MapPoint) are GATHERED into flat arrays, sent through the C-ABI (include/uvip_orb.h), and the results
+// SCATTERED back, so Tracking / LocalMapping / LoopClosing stay untouched.  The member templates accept
+// the reference's own FrameKTL / MapPoint types (they only use the members cited below), or mock types in tests.
+#pragma once
+#include <cstring>
+#include <stdexcept>
+#include <string>
+#include <vector>
+#ifdef UVIP_WITH_OPENCV
+#include <opencv2/core/core.hpp>
+#else
+#include "uvip_compat.h"
+#endif
+#include "../../include/uvip_orb.h"
+
+namespace USLAM {
+
+class ORBmatcher {
+public:
+    ORBmatcher(float nnratio = 0.6, bool checkOri = true) : mfNNratio(nnratio), mbCheckOrientation(checkOri) {}
+    ~ORBmatcher() { if (handle_) uvip_matcher_destroy(handle_); }
+    ORBmatcher(const ORBmatcher&) = delete;
+    ORBmatcher& operator=(const ORBmatcher&) = delete;
+
+    // src/ORBmatcher.cc:1794-1810.  One pair of 32-byte rows: stays a host popcount, exactly as SURVEY section 2 row 4
+    // prescribes for MapPoint::ComputeDistinctiveDescriptors (N is tiny); batches go through uvip_descriptor_distance.
+    static int DescriptorDistance(const cv::Mat& a, const cv::Mat& b)
+    {
+        const unsigned char* pa = a.ptr<unsigned char>(); const unsigned char* pb = b.ptr<unsigned char>();
+        int dist = 0;
+        for (int i = 0; i < 8; i++) {
+            uint32_t x, y; std::memcpy(&x, pa + 4 * i, 4); std::memcpy(&y, pb + 4 * i, 4);
+            dist += __builtin_popcount(x ^ y);
+        }
+        return dist;
+    }
+
+    // SearchByProjection(FrameKTL&, const vector<MapPoint*>&, th)  (src/ORBmatcher.cc:49-125)
+    // FrameT needs: mvKeysUn, mDescriptors, mvpMapPoints, mvScaleFactors, mnMinX, mnMinY, mfGridElementWidthInv,
+    //               mfGridElementHeightInv (include/FrameKTL.h);  MapPointT needs: mbTrackInView, isBad(), mnTrackScaleLevel,
+    //               mTrackViewCos, mTrackProjX, mTrackProjY, GetDescriptor() (include/MapPoint.h)
+    template <class FrameT, class MapPointT>
+    int SearchByProjection(FrameT& F, const std::vector<MapPointT*>& vpMapPoints, const float th = 3)
+    {
+        ensure();
+        const bool bFactor = th != 1.0;
+        std::vector<float> qu, qv, qr; std::vector<int32_t> qmin, qmax; std::vector<unsigned char> qd; std::vector<MapPointT*> who;
+        for (size_t i = 0; i < vpMapPoints.size(); i++) {
+            MapPointT* pMP = vpMapPoints[i];
+            if (!pMP->mbTrackInView) continue;
+            if (pMP->isBad()) continue;
+            const int lvl = pMP->mnTrackScaleLevel;
+            float r = uvip_radius_by_viewing_cos(pMP->mTrackViewCos);
+            if (bFactor) r *= th;
+            qu.push_back(pMP->mTrackProjX); qv.push_back(pMP->mTrackProjY); qr.push_back(r * F.mvScaleFactors[lvl]);
+            qmin.push_back(lvl - 1); qmax.push_back(lvl);
+            const cv::Mat d = pMP->GetDescriptor();
+            qd.insert(qd.end(), d.ptr(0), d.ptr(0) + 32);
+            who.push_back(pMP);
+        }
+        const int nq = (int)who.size(), nk = (int)F.mvKeysUn.size();
+        if (nq == 0) return 0;
+        std::vector<float> kx((size_t)nk), ky((size_t)nk); std::vector<int32_t> oct((size_t)nk), taken((size_t)nk);
+        std::vector<unsigned char> kd((size_t)nk * 32);
+        for (int i = 0; i < nk; i++) {
+            kx[i] = F.mvKeysUn[i].pt.x; ky[i] = F.mvKeysUn[i].pt.y; oct[i] = F.mvKeysUn[i].octave;
+            taken[i] = F.mvpMapPoints[i] ? -2 : -1;
+            std::memcpy(&kd[(size_t)i * 32], F.mDescriptors.ptr(i), 32);
+        }
+        uvip_search_params sp;
+        sp.mode = 0; sp.th_dist = TH_HIGH; sp.ratio = mfNNratio;
+        sp.min_x = (float)F.mnMinX; sp.min_y = (float)F.mnMinY; sp.inv_w = F.mfGridElementWidthInv; sp.inv_h = F.mfGridElementHeightInv;
+        sp.cols = 64; sp.rows = 48;
+        std::vector<int32_t> cs(64 * 48 + 1), ci((size_t)(nk > 0 ? nk : 1)), match((size_t)nq);
+        check(uvip_grid_build(handle_, kx.data(), ky.data(), nk, sp.min_x, sp.min_y, sp.inv_w, sp.inv_h, 64, 48, cs.data(), ci.data()), "uvip_grid_build");
+        int nmatches = 0;
+        check(uvip_search_window(handle_, &sp, qu.data(), qv.data(), qr.data(), qmin.data(), qmax.data(), qd.data(), nq,
+                                 kx.data(), ky.data(), oct.data(), kd.data(), nk, cs.data(), ci.data(), taken.data(), match.data(), &nmatches),
+              "uvip_search_window");
+        for (int q = 0; q < nq; q++) if (match[q] >= 0) F.mvpMapPoints[match[q]] = who[q];     // :119
+        return nmatches;
+    }
+
+    // haloc::Utils::ratioMatching (include/utils.h:81-111): brute-force k=2 + ratio test; match[i] = train row or -1
+    int RatioMatching(const cv::Mat& descriptors1, const cv::Mat& descriptors2, double ratio, std::vector<int>& match)
+    {
+        ensure();
+        match.assign((size_t)descriptors1.rows, -1);
+        if (descriptors1.empty() || descriptors2.empty()) return 0;
+        const int nq = descriptors1.rows, nt = descriptors2.rows;
+        std::vector<unsigned char> q((size_t)nq * 32), t((size_t)nt * 32);
+        for (int i = 0; i < nq; i++) std::memcpy(&q[(size_t)i * 32], descriptors1.ptr(i), 32);
+        for (int i = 0; i < nt; i++) std::memcpy(&t[(size_t)i * 32], descriptors2.ptr(i), 32);
+        std::vector<int32_t> idx((size_t)nq * 2), dist((size_t)nq * 2), m((size_t)nq);
+        check(uvip_knn2(handle_, q.data(), nq, t.data(), nt, idx.data(), dist.data()), "uvip_knn2");
+        int n = 0;
+        check(uvip_ratio_filter(handle_, idx.data(), dist.data(), nq, ratio, m.data(), &n), "uvip_ratio_filter");
+        for (int i = 0; i < nq; i++) match[(size_t)i] = m[(size_t)i];
+        return n;
+    }
+
+    // rotation-consistency histogram (src/ORBmatcher.cc:232-241, :263-281, :1748-1789) over an index match list
+    int CheckOrientation(std::vector<int>& match, const std::vector<float>& angles1, const std::vector<float>& angles2)
+    {
+        ensure();
+        if (!mbCheckOrientation || match.empty()) { int n = 0; for (int v : match) n += v >= 0; return n; }
+        std::vector<int32_t> m(match.begin(), match.end());
+        int kept = 0;
+        check(uvip_rot_hist_filter(handle_, m.data(), (int)m.size(), angles1.data(), angles2.data(), &kept), "uvip_rot_hist_filter");
+        for (size_t i = 0; i < match.size(); i++) match[i] = m[i];
+        return kept;
+    }
+
+public:
+    static const int TH_LOW = UVIP_TH_LOW;
+    static const int TH_HIGH = UVIP_TH_HIGH;
+    static const int HISTO_LENGTH = UVIP_HISTO_LENGTH;
+
+protected:
+    float RadiusByViewingCos(const float& viewCos) { return uvip_radius_by_viewing_cos(viewCos); }
+    void ensure()
+    {
+        if (!handle_ && uvip_matcher_create(0, &handle_) != UVIP_OK)
+            throw std::runtime_error(std::string("uvip_matcher_create: ") + uvip_last_error());
+    }
+    static void check(int rc, const char* what) { if (rc != UVIP_OK) throw std::runtime_error(std::string(what) + ": " + uvip_last_error()); }
+
+    float mfNNratio;
+    bool mbCheckOrientation;
+    uvip_matcher* handle_ = nullptr;
+};
+
+}  // namespace USLAM
