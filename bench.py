@@ -251,8 +251,12 @@ def run_ours(args):
     host_i = torch.zeros((B, cap, 2), dtype=torch.int32).pin_memory(); host_dd = torch.zeros_like(host_i).pin_memory()
     hp = lambda t: C.c_void_p(t.data_ptr())
 
+    # the host-buffer entry point pipelines chunks of max_batch frames (H2D | kernels | D2H on three streams)
+    ex_e2e = pkg.ORBextractor(NFEAT, SCALE, NLEVELS, pkg.ORBextractor.FAST_SCORE, FAST_TH, device=local, max_width=W, max_height=H,
+                              max_batch=max(1, B // 8))
+
     def e2e_step():
-        chk(L.uvip_extract_batch(ex.h, hp(host_in), B, W, H, W, W * H, hp(host_k), hp(host_n), cap, hp(host_d)))
+        chk(L.uvip_extract_batch(ex_e2e.h, hp(host_in), B, W, H, W, W * H, hp(host_k), hp(host_n), cap, hp(host_d)))
         chk(L.uvip_knn2_batch(m.h, hp(host_d), hp(host_n), cap * 32, C.c_void_p(host_d.data_ptr() + cap * 32),
                               C.c_void_p(host_n.data_ptr() + 4), cap * 32, B - 1, cap, hp(host_i), hp(host_dd), cap))
 
@@ -269,7 +273,7 @@ def run_ours(args):
         dist.all_reduce(tt, op=dist.ReduceOp.MAX)
         e2e_s = float(tt.item())
     e2e_fps = world * B * Ke / e2e_s
-    h2d = B * W * H + 2 * (B - 1) * cap * 32 + 2 * (B - 1) * 4
+    h2d = B * W * H + B * cap * 32 + 2 * (B - 1) * 4
     d2h = B * cap * 60 + B * 4 + 2 * (B - 1) * cap * 8
 
     # ---- roofline of the dominant extraction kernel (algorithmic bytes of SURVEY 8(d) / its measured duration)

@@ -142,7 +142,7 @@ def test_extract_batch_matches_single_frames(gpu, oracle, synth):
     """BASELINE config 2 shape: 640x512, 1500 kp, one HBM-resident batch; each frame equals its single-frame result."""
     nfr = 6
     frames = synth.synth_batch(1000, nfr, 640, 512)
-    ex = gpu.ORBextractor(1500, 1.2, 8, 1, 20, max_width=640, max_height=512, max_batch=4)   # 6 frames -> groups of 4 + 2
+    ex = gpu.ORBextractor(1500, 1.2, 8, 1, 20, max_width=640, max_height=512, max_batch=2)   # 6 frames -> 3 pipelined chunks (double-buffered staging)
     kps, n, desc = ex.extract_batch(frames)
     okps, on, odesc = oracle.extract_batch(frames, 1500, 1.2, 8, 20, cap=kps.shape[1])
     assert np.array_equal(n, on) and n.min() >= 1500

@@ -1016,6 +1016,9 @@ struct uvip_extractor {
     size_t cap_frame_bytes = 0; int cap_cells = 0, cap_raw = 0, cap_kp = 0, cap_tab = 0;
     DevBuf pyr, blur, cand, labels, winners, counters, sel, nsel, tabs, status, grid, incoming, tmaps;
     DevBuf in_frames, out_kps, out_desc, out_n;      // staging for the host-buffer entry points
+    DevBuf in2, kps2, desc2, n2;                     // second staging set: uvip_extract_batch double-buffers its chunks
+    cudaStream_t h2d_stream = nullptr, d2h_stream = nullptr;
+    cudaEvent_t ev_h2d[2] = {nullptr, nullptr}, ev_comp[2] = {nullptr, nullptr}, ev_d2h[2] = {nullptr, nullptr};
     int sel_cap = 0;
     int last_frames = 0;
     long long launches = 0;
@@ -1214,7 +1217,8 @@ static int ensure_plan(uvip_extractor* ex, int w, int h)
 // enqueue the whole pipeline for nframes frames on st
 static int enqueue_group(uvip_extractor* ex, const uint8_t* d_frames, int nframes, int stride, size_t frame_pitch,
                          uvip_keypoint* d_kps, int32_t* d_n_out, int out_cap, uint8_t* d_desc,
-                         int full_detect, int n_incoming, int grid_rows, int grid_cols, int min_px_dist, int num_needed, cudaStream_t st)
+                         int full_detect, int n_incoming, int grid_rows, int grid_cols, int min_px_dist, int num_needed, cudaStream_t st,
+                         bool reset_status = true)
 {
     const Plan& P = ex->plan;
     uint8_t* pyr = ex->pyr.as<uint8_t>(); uint8_t* blur = ex->blur.as<uint8_t>();
@@ -1222,7 +1226,7 @@ static int enqueue_group(uvip_extractor* ex, const uint8_t* d_frames, int nframe
     const size_t cstride = (size_t)ex->prm.max_batch * P.nlevels;
     int* cand_count = counters; int* win_count = counters + cstride;
     UVIP_CUDA(cudaMemsetAsync(counters, 0, 2 * cstride * sizeof(int), st));
-    UVIP_CUDA(cudaMemsetAsync(ex->status.p, 0, sizeof(int), st));
+    if (reset_status) UVIP_CUDA(cudaMemsetAsync(ex->status.p, 0, sizeof(int), st));
     cudaEvent_t* pe = ex->prof ? ex->prof_ev.data() + (size_t)(ex->prof_groups % PROF_RING) * (UVIP_NUM_STAGES + 1) : nullptr;
 #define PROF_MARK(i) do { if (pe) UVIP_CUDA(cudaEventRecord(pe[i], st)); } while (0)
     PROF_MARK(0);
@@ -1377,9 +1381,13 @@ int uvip_extractor_destroy(uvip_extractor* ex)
     DeviceGuard g(ex->device);
     if (ex->stream) cudaStreamSynchronize(ex->stream);
     DevBuf* bufs[] = {&ex->pyr, &ex->blur, &ex->cand, &ex->labels, &ex->winners, &ex->counters, &ex->sel,
-                      &ex->nsel, &ex->tabs, &ex->status, &ex->grid, &ex->incoming, &ex->tmaps, &ex->in_frames, &ex->out_kps, &ex->out_desc, &ex->out_n};
+                      &ex->nsel, &ex->tabs, &ex->status, &ex->grid, &ex->incoming, &ex->tmaps, &ex->in_frames, &ex->out_kps, &ex->out_desc, &ex->out_n,
+                      &ex->in2, &ex->kps2, &ex->desc2, &ex->n2};
     for (DevBuf* b : bufs) b->release();
     for (cudaEvent_t e : ex->prof_ev) cudaEventDestroy(e);
+    for (int i = 0; i < 2; i++) { if (ex->ev_h2d[i]) cudaEventDestroy(ex->ev_h2d[i]); if (ex->ev_comp[i]) cudaEventDestroy(ex->ev_comp[i]); if (ex->ev_d2h[i]) cudaEventDestroy(ex->ev_d2h[i]); }
+    if (ex->h2d_stream) cudaStreamDestroy(ex->h2d_stream);
+    if (ex->d2h_stream) cudaStreamDestroy(ex->d2h_stream);
     if (ex->stream) cudaStreamDestroy(ex->stream);
     delete ex;
     return UVIP_OK;
@@ -1430,26 +1438,51 @@ int uvip_extract_batch(uvip_extractor* ex, const uint8_t* frames, int nframes, i
     DeviceGuard g(ex->device);
     int rc = ensure_plan(ex, w, h);
     if (rc) return rc;
+    // Chunks of max_batch frames flow through a 3-stream pipeline: H2D of chunk c+1 and D2H of chunk c-1 overlap the
+    // kernels of chunk c (two staging sets; pinned host memory is needed for the copies to be truly asynchronous).
     const int B = ex->prm.max_batch;
     const size_t fbytes = (size_t)stride * h;
-    if ((rc = ex->in_frames.reserve((size_t)B * fbytes))) return rc;
-    if ((rc = ex->out_kps.reserve((size_t)B * cap * sizeof(uvip_keypoint)))) return rc;
-    if ((rc = ex->out_desc.reserve((size_t)B * cap * 32))) return rc;
-    if ((rc = ex->out_n.reserve((size_t)B * 4))) return rc;
-    cudaStream_t st = ex->stream;
-    for (int f0 = 0; f0 < nframes; f0 += B) {
-        const int nb = nframes - f0 < B ? nframes - f0 : B;
-        if (frame_pitch == fbytes) UVIP_CUDA(cudaMemcpyAsync(ex->in_frames.p, frames + (size_t)f0 * frame_pitch, (size_t)nb * fbytes, cudaMemcpyHostToDevice, st));
-        else UVIP_CUDA(cudaMemcpy2DAsync(ex->in_frames.p, fbytes, frames + (size_t)f0 * frame_pitch, frame_pitch, fbytes - (stride - w), nb, cudaMemcpyHostToDevice, st));
-        rc = enqueue_group(ex, ex->in_frames.as<uint8_t>(), nb, stride, fbytes, ex->out_kps.as<uvip_keypoint>(), ex->out_n.as<int32_t>(),
-                           cap, ex->out_desc.as<uint8_t>(), 1, 0, 1, 1, 1, 0, st);
-        if (rc) return rc;
-        UVIP_CUDA(cudaMemcpyAsync(n_out + f0, ex->out_n.p, (size_t)nb * 4, cudaMemcpyDeviceToHost, st));
-        UVIP_CUDA(cudaMemcpyAsync(kps + (size_t)f0 * cap, ex->out_kps.p, (size_t)nb * cap * sizeof(uvip_keypoint), cudaMemcpyDeviceToHost, st));
-        UVIP_CUDA(cudaMemcpyAsync(desc + (size_t)f0 * cap * 32, ex->out_desc.p, (size_t)nb * cap * 32, cudaMemcpyDeviceToHost, st));
-        if ((rc = read_status(ex, st))) return rc;
+    DevBuf* in[2] = {&ex->in_frames, &ex->in2}; DevBuf* ok[2] = {&ex->out_kps, &ex->kps2};
+    DevBuf* od[2] = {&ex->out_desc, &ex->desc2}; DevBuf* on[2] = {&ex->out_n, &ex->n2};
+    const int nchunks = (nframes + B - 1) / B;
+    for (int s = 0; s < (nchunks > 1 ? 2 : 1); s++) {
+        if ((rc = in[s]->reserve((size_t)B * fbytes))) return rc;
+        if ((rc = ok[s]->reserve((size_t)B * cap * sizeof(uvip_keypoint)))) return rc;
+        if ((rc = od[s]->reserve((size_t)B * cap * 32))) return rc;
+        if ((rc = on[s]->reserve((size_t)B * 4))) return rc;
     }
-    return UVIP_OK;
+    if (!ex->h2d_stream) {
+        UVIP_CUDA(cudaStreamCreateWithFlags(&ex->h2d_stream, cudaStreamNonBlocking));
+        UVIP_CUDA(cudaStreamCreateWithFlags(&ex->d2h_stream, cudaStreamNonBlocking));
+        for (int i = 0; i < 2; i++) {
+            UVIP_CUDA(cudaEventCreateWithFlags(&ex->ev_h2d[i], cudaEventDisableTiming));
+            UVIP_CUDA(cudaEventCreateWithFlags(&ex->ev_comp[i], cudaEventDisableTiming));
+            UVIP_CUDA(cudaEventCreateWithFlags(&ex->ev_d2h[i], cudaEventDisableTiming));
+        }
+    }
+    cudaStream_t st = ex->stream, sh = ex->h2d_stream, sd = ex->d2h_stream;
+    UVIP_CUDA(cudaMemsetAsync(ex->status.p, 0, sizeof(int), st));
+    for (int c = 0; c < nchunks; c++) {
+        const int s = c & 1, f0 = c * B;
+        const int nb = nframes - f0 < B ? nframes - f0 : B;
+        if (c >= 2) UVIP_CUDA(cudaStreamWaitEvent(sh, ex->ev_comp[s], 0));          // kernels of chunk c-2 are done with in[s]
+        if (frame_pitch == fbytes) UVIP_CUDA(cudaMemcpyAsync(in[s]->p, frames + (size_t)f0 * frame_pitch, (size_t)nb * fbytes, cudaMemcpyHostToDevice, sh));
+        else UVIP_CUDA(cudaMemcpy2DAsync(in[s]->p, fbytes, frames + (size_t)f0 * frame_pitch, frame_pitch, fbytes - (stride - w), nb, cudaMemcpyHostToDevice, sh));
+        UVIP_CUDA(cudaEventRecord(ex->ev_h2d[s], sh));
+        UVIP_CUDA(cudaStreamWaitEvent(st, ex->ev_h2d[s], 0));
+        if (c >= 2) UVIP_CUDA(cudaStreamWaitEvent(st, ex->ev_d2h[s], 0));           // results of chunk c-2 have left out[s]
+        rc = enqueue_group(ex, in[s]->as<uint8_t>(), nb, stride, fbytes, ok[s]->as<uvip_keypoint>(), on[s]->as<int32_t>(),
+                           cap, od[s]->as<uint8_t>(), 1, 0, 1, 1, 1, 0, st, false);
+        if (rc) return rc;
+        UVIP_CUDA(cudaEventRecord(ex->ev_comp[s], st));
+        UVIP_CUDA(cudaStreamWaitEvent(sd, ex->ev_comp[s], 0));
+        UVIP_CUDA(cudaMemcpyAsync(n_out + f0, on[s]->p, (size_t)nb * 4, cudaMemcpyDeviceToHost, sd));
+        UVIP_CUDA(cudaMemcpyAsync(kps + (size_t)f0 * cap, ok[s]->p, (size_t)nb * cap * sizeof(uvip_keypoint), cudaMemcpyDeviceToHost, sd));
+        UVIP_CUDA(cudaMemcpyAsync(desc + (size_t)f0 * cap * 32, od[s]->p, (size_t)nb * cap * 32, cudaMemcpyDeviceToHost, sd));
+        UVIP_CUDA(cudaEventRecord(ex->ev_d2h[s], sd));
+    }
+    UVIP_CUDA(cudaStreamSynchronize(sd));
+    return read_status(ex, st);
 }
 
 int uvip_extract(uvip_extractor* ex, const uint8_t* image, int w, int h, int stride,

@@ -501,18 +501,22 @@ int uvip_knn2_batch(uvip_matcher* m, const uint8_t* q, const int32_t* nq, size_t
     std::lock_guard<std::mutex> lk(m->mu);
     DeviceGuard g(m->device);
     int rc;
-    if ((rc = m->q.reserve((size_t)npairs * q_pitch))) return rc;
-    if ((rc = m->t.reserve((size_t)npairs * t_pitch))) return rc;
+    // frame-to-frame matching passes t = q + k*pitch (descriptors of the following frames): upload the union once
+    const bool alias = t >= q && t_pitch == q_pitch && (size_t)(t - q) % q_pitch == 0 && (size_t)(t - q) <= (size_t)npairs * q_pitch;
+    const size_t q_bytes = alias ? (size_t)(t - q) + (size_t)npairs * t_pitch : (size_t)npairs * q_pitch;
+    if ((rc = m->q.reserve(q_bytes))) return rc;
+    if (!alias && (rc = m->t.reserve((size_t)npairs * t_pitch))) return rc;
     if ((rc = m->idx.reserve((size_t)npairs * res_pitch * 8))) return rc;
     if ((rc = m->dist.reserve((size_t)npairs * res_pitch * 8))) return rc;
     if ((rc = m->misc.reserve((size_t)npairs * 8))) return rc;
     cudaStream_t st = m->stream;
     int32_t* d_nq = m->misc.as<int32_t>(); int32_t* d_nt = d_nq + npairs;
-    UVIP_CUDA(cudaMemcpyAsync(m->q.p, q, (size_t)npairs * q_pitch, cudaMemcpyHostToDevice, st));
-    UVIP_CUDA(cudaMemcpyAsync(m->t.p, t, (size_t)npairs * t_pitch, cudaMemcpyHostToDevice, st));
+    UVIP_CUDA(cudaMemcpyAsync(m->q.p, q, q_bytes, cudaMemcpyHostToDevice, st));
+    if (!alias) UVIP_CUDA(cudaMemcpyAsync(m->t.p, t, (size_t)npairs * t_pitch, cudaMemcpyHostToDevice, st));
     UVIP_CUDA(cudaMemcpyAsync(d_nq, nq, (size_t)npairs * 4, cudaMemcpyHostToDevice, st));
     UVIP_CUDA(cudaMemcpyAsync(d_nt, nt, (size_t)npairs * 4, cudaMemcpyHostToDevice, st));
-    rc = launch_knn2(m, m->q.as<uint8_t>(), d_nq, q_pitch, m->t.as<uint8_t>(), d_nt, t_pitch, npairs, max_nq, 0, 0, 0,
+    const uint8_t* d_t = alias ? m->q.as<uint8_t>() + (size_t)(t - q) : m->t.as<uint8_t>();
+    rc = launch_knn2(m, m->q.as<uint8_t>(), d_nq, q_pitch, d_t, d_nt, t_pitch, npairs, max_nq, 0, 0, 0,
                      m->idx.as<int32_t>(), m->dist.as<int32_t>(), res_pitch, st);
     if (rc) return rc;
     UVIP_CUDA(cudaMemcpyAsync(idx2, m->idx.p, (size_t)npairs * res_pitch * 8, cudaMemcpyDeviceToHost, st));
