@@ -303,6 +303,7 @@ k_fast(const CUtensorMap* __restrict__ tmaps, const unsigned* __restrict__ tile_
     extern __shared__ __align__(128) unsigned char s_fast[];
     __shared__ __align__(8) uint64_t s_mbar;
     __shared__ unsigned s_colvalid[FAST_CH][64];
+    __shared__ unsigned char s_xcell[FAST_CW * 64 + 8];       // cell column of every pixel column of the tile
     __shared__ int s_ng, s_nq, s_surv[FAST_CW * FAST_CH];
     __shared__ unsigned char s_rowact[2][8];     // [cell row][cell col] evaluated in this pass
 
@@ -328,6 +329,7 @@ k_fast(const CUtensorMap* __restrict__ tmaps, const unsigned* __restrict__ tile_
     const int cofs = (gx0 - 4 - ax0) >> 2;                // word column of the first group's left neighbour
     const int rsw = irow >> 2;
     if (tid < FAST_CW * FAST_CH) s_surv[tid] = 0;
+    for (int i = tid; i < X1 - X0; i += 256) s_xcell[i] = (unsigned char)min(i / L.wcell, FAST_CW - 1);
     // A: stage the tile with one TMA box load (zero-filled outside the padded plane); the box is the plan's
     //    largest tile, so every CTA issues the same shape
     if (tid == 0) { mbar_init(&s_mbar, 1); mbar_fence_init(); }
@@ -346,17 +348,14 @@ k_fast(const CUtensorMap* __restrict__ tmaps, const unsigned* __restrict__ tile_
 
     for (int pass = 0; pass < 2; pass++) {
         const int t = pass ? P.t2 : P.t1;
-        __syncthreads();                                   // staging / previous pass complete
-        if (pass) {
-            if (P.t2 >= P.t1) break;                       // the retry cannot add anything (uniform)
-            int any = 0;
-            for (int i = 0; i < ncy; i++) for (int j = 0; j < ncx; j++) any |= (s_surv[i * FAST_CW + j] == 0);
-            if (!any) break;                               // uniform
-        }
+        if (pass && P.t2 >= P.t1) break;                   // the retry cannot add anything (uniform)
+        bool mine = false;                                 // is "my" cell (tid < 8) evaluated in this pass?
         if (tid < FAST_CW * FAST_CH) {
             const int i = tid / FAST_CW, j = tid % FAST_CW;
-            s_rowact[i][j] = (i < ncy && j < ncx && (pass == 0 || s_surv[tid] == 0)) ? 1 : 0;
+            mine = i < ncy && j < ncx && (pass == 0 || s_surv[tid] == 0);
         }
+        if (!__syncthreads_or(mine)) break;                // also orders staging / the previous pass (uniform exit)
+        if (tid < FAST_CW * FAST_CH) s_rowact[tid / FAST_CW][tid % FAST_CW] = mine ? 1 : 0;
         if (tid == 0) { s_ng = 0; s_nq = 0; }
         __syncthreads();
         if (tid < FAST_CH * 64) {                           // byte masks per (cell row, group column): inside [X0,X1) and cell active
@@ -365,7 +364,7 @@ k_fast(const CUtensorMap* __restrict__ tmaps, const unsigned* __restrict__ tile_
             if (c < ngx)
                 for (int bb = 0; bb < 4; bb++) {
                     const int x = gx0 + 4 * c + bb;
-                    if (x >= X0 && x < X1 && s_rowact[ci][min((x - X0) / L.wcell, FAST_CW - 1)]) m |= 0x80u << (8 * bb);
+                    if (x >= X0 && x < X1 && s_rowact[ci][s_xcell[x - X0]]) m |= 0x80u << (8 * bb);
                 }
             s_colvalid[ci][c] = m;
         }
@@ -391,17 +390,28 @@ k_fast(const CUtensorMap* __restrict__ tmaps, const unsigned* __restrict__ tile_
         const int ng = s_ng;
         // B2: full SWAR test on the compacted groups
         const unsigned t4 = (unsigned)t * 0x01010101u;
-        for (int gi = tid; gi < ng; gi += 256) {
-            const int g = s_gq[gi];
+        for (int g0 = 0; g0 < ng; g0 += 256) {
+            const int gi = g0 + tid;
+            const int g = gi < ng ? s_gq[gi] : 0;
             const int r = __umulhi((unsigned)g, rcpg), c = g - r * ngx;
-            const unsigned valid = s_colvalid[(r >= L.hcell) ? 1 : 0][c];
-            if (!valid) continue;
-            unsigned cf = fast_swar4(s_img + (r + 3) * rsw + (cofs + c + 1), rsw, t4, valid);
-            while (cf) {
-                const int bb = (__ffs(cf) - 1) >> 3;
-                cf &= cf - 1;
-                const int slot = atomicAdd(&s_nq, 1);
-                s_queue[slot] = (unsigned short)((r + 1) * srow + (gx0 + 4 * c + bb - X0 + 1));
+            const unsigned valid = gi < ng ? s_colvalid[(r >= L.hcell) ? 1 : 0][c] : 0u;
+            unsigned cf = valid ? fast_swar4(s_img + (r + 3) * rsw + (cofs + c + 1), rsw, t4, valid) : 0u;
+            // warp-aggregated append of the corner pixels (<= 4 per lane): inclusive scan of the per-lane counts
+            const int cnt = __popc(cf);
+            int incl = cnt;
+#pragma unroll
+            for (int o = 1; o < 32; o <<= 1) { const int v = __shfl_up_sync(0xFFFFFFFFu, incl, o); if (lane >= o) incl += v; }
+            const int total = __shfl_sync(0xFFFFFFFFu, incl, 31);
+            if (total) {
+                int base = 0;
+                if (lane == 31) base = atomicAdd(&s_nq, total);
+                base = __shfl_sync(0xFFFFFFFFu, base, 31) + incl - cnt;
+                const int p0 = (r + 1) * srow + (gx0 + 4 * c - X0 + 1);
+                while (cf) {
+                    const int bb = (__ffs(cf) - 1) >> 3;
+                    cf &= cf - 1;
+                    s_queue[base++] = (unsigned short)(p0 + bb);
+                }
             }
         }
         __syncthreads();
@@ -440,7 +450,7 @@ k_fast(const CUtensorMap* __restrict__ tmaps, const unsigned* __restrict__ tile_
                 const int pos = s_queue[qi];
                 const int sy = __umulhi((unsigned)pos, rcps), sx = pos - sy * srow;
                 const int x = X0 + sx - 1, y = Y0 + sy - 1;
-                const int cj = (x - X0) / L.wcell, ci = (y - Y0 >= L.hcell) ? 1 : 0;
+                const int cj = s_xcell[x - X0], ci = (y - Y0 >= L.hcell) ? 1 : 0;
                 const int cxa = X0 + cj * L.wcell, cxb = min(cxa + L.wcell, X1);
                 const int cya = Y0 + ci * L.hcell, cyb = min(cya + L.hcell, Y1);
                 const int s = s_score[pos];
@@ -474,6 +484,7 @@ k_fast(const CUtensorMap* __restrict__ tmaps, const unsigned* __restrict__ tile_
                 }
             }
         }
+        __syncthreads();                                   // s_surv complete before the retry pass reads it
     }
 }
 
