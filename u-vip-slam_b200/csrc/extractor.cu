@@ -929,80 +929,106 @@ __device__ __forceinline__ float fast_atan2_deg(float y, float x)
     return a;
 }
 
-constexpr int DESC_WARPS = 8;
+// sin / cos of a float angle (radians, |x| < ~7) evaluated in double and rounded once to float.  glibc's sinf/cosf
+// (what the reference's `cos(angle)` / `sin(angle)` resolve to) are correctly rounded except in vanishingly rare
+// cases, so a double evaluation with ~1e-16 error reproduces their bits.  Cody-Waite reduction by pi/2 + the classic
+// fdlibm kernel polynomials on [-pi/4, pi/4].
+__device__ __forceinline__ void sincos_as_float(float xf, float* s_out, float* c_out)
+{
+    const double x = (double)xf;
+    const double q = rint(x * 0.63661977236758134308);            // 2/pi
+    double r = fma(-q, 1.57079632673412561417e+00, x);            // pi/2 split in three parts (fdlibm pio2_1, pio2_1t hi/lo)
+    r = fma(-q, 6.07710050650619224932e-11, r);
+    r = fma(-q, 2.02226624879595063154e-21, r);
+    const double z = r * r;
+    const double ps = fma(z, fma(z, fma(z, fma(z, fma(z, 1.58969099521155010221e-10, -2.50507602534068634195e-08), 2.75573137070700676789e-06),
+                                         -1.98412698298579493134e-04), 8.33333333332248946124e-03), -1.66666666666666324348e-01);
+    const double sn = fma(z * r, ps, r);
+    const double pc = fma(z, fma(z, fma(z, fma(z, fma(z, -1.13596475577881948265e-11, 2.08757232129817482790e-09), -2.75573143513906633035e-07),
+                                         2.48015872894767294178e-05), -1.38888888888741095749e-03), 4.16666666666666019037e-02);
+    const double cs = fma(z * z, pc, fma(z, -0.5, 1.0));
+    const int n = (int)q & 3;
+    const double s = (n & 1) ? cs : sn, c = (n & 1) ? sn : cs;
+    *s_out = (float)((n & 2) ? -s : s);
+    *c_out = (float)(((n + 1) & 2) ? -c : c);
+}
+
+constexpr int DESC_WARPS = 8, DESC_KPW = 4;           // warps per CTA, keypoints per warp
 __global__ void __launch_bounds__(DESC_WARPS * 32)
 k_describe(const uint8_t* __restrict__ pyr, const uint8_t* __restrict__ blur, const unsigned* __restrict__ winners,
            const unsigned* __restrict__ sel, const int* __restrict__ nsel, int sel_cap,
-           const uvip_keypoint* __restrict__ incoming,
+           const uvip_keypoint* __restrict__ incoming, const float2* __restrict__ pat_t,
            uvip_keypoint* __restrict__ kps, uint8_t* __restrict__ desc, int32_t* __restrict__ n_out, int out_cap,
            int* __restrict__ status, const __grid_constant__ Plan P)
 {
-    __shared__ short s_pat[16][32][2];          // [k][lane] -> (x, y) of pattern point 16*lane + k
-    for (int i = threadIdx.x; i < 512; i += blockDim.x) {
-        const int lane = i >> 4, k = i & 15;
-        s_pat[k][lane][0] = c_pattern[2 * i]; s_pat[k][lane][1] = c_pattern[2 * i + 1];
-    }
-    __syncthreads();
     const int f = blockIdx.y;
     const int lane = threadIdx.x & 31;
-    const int slot = blockIdx.x * DESC_WARPS + (threadIdx.x >> 5);
     const int n = nsel[f];
-    if (slot == 0 && lane == 0) { n_out[f] = n; if (n > out_cap) atomicOr(status, 8); }
-    if (slot >= n) return;
-    const unsigned e = sel[(size_t)f * sel_cap + slot];
-    int level, cx, cy; float response, size, ox, oy; int octave, class_id;
-    if ((e >> 16) == 0xFFFFu) {                // incoming level-0 keypoint (ComputeKeyPointsCopy, :523-534)
-        const uvip_keypoint k = incoming[e & 0xFFFF];
-        level = 0; cx = __float2int_rn(k.x); cy = __float2int_rn(k.y);
-        response = k.response; size = k.size; ox = k.x; oy = k.y; octave = k.octave; class_id = k.class_id;
-    } else {
-        level = e >> 16;
-        const unsigned w = winners[(size_t)f * P.kp_per_frame + P.lv[level].kp_off + (e & 0xFFFF)];
-        cx = w & 0xFFF; cy = (w >> 12) & 0xFFF;
-        response = (float)(w >> 24); size = P.lv[level].size; octave = level; class_id = -1;
-        ox = (float)cx; oy = (float)cy;
-        if (level != 0) { ox = __fmul_rn(ox, P.lv[level].scale); oy = __fmul_rn(oy, P.lv[level].scale); }   // :951-957
-    }
-    const LevelInfo& L = P.lv[level];
-    const size_t plane = (size_t)f * P.frame_bytes + L.poff + (size_t)EDGE * L.pstride + EDGE;
-    const uint8_t* c0 = pyr + plane + (ptrdiff_t)cy * L.pstride + cx;
-    // ---- IC_Angle
-    int m10 = 0, m01 = 0;
-    if (lane < 31) {
-        const int u = lane - HALF_PATCH, au = abs(u);
-        int vals[2 * HALF_PATCH + 1];
+    if (blockIdx.x == 0 && threadIdx.x == 0) { n_out[f] = n; if (n > out_cap) atomicOr(status, 8); }
+    const int slot0 = (blockIdx.x * DESC_WARPS + (threadIdx.x >> 5)) * DESC_KPW;
+    if (slot0 >= n) return;
+    // this lane's 16 pattern points (descriptor byte `lane`), transposed table [k][lane] -> coalesced loads, kept in registers
+    float px[16], py[16];
 #pragma unroll
-        for (int v = -HALF_PATCH; v <= HALF_PATCH; v++)            // all 31 row loads in flight at once
-            vals[v + HALF_PATCH] = (au <= c_umax[v < 0 ? -v : v]) ? (int)__ldg(c0 + (ptrdiff_t)v * L.pstride + u) : 0;
-        int colsum = 0;
+    for (int k = 0; k < 16; k++) { const float2 p = __ldg(pat_t + k * 32 + lane); px[k] = p.x; py[k] = p.y; }
+    const int u = lane - HALF_PATCH;
+    const int vm = lane < 31 ? c_umax[u < 0 ? -u : u] : -1;       // disc rows |v| <= vm belong to column u (umax is symmetric)
+#pragma unroll 1
+    for (int i = 0; i < DESC_KPW; i++) {
+        const int slot = slot0 + i;
+        if (slot >= n || slot >= out_cap) break;
+        const unsigned e = sel[(size_t)f * sel_cap + slot];
+        int level, cx, cy; float response, size, ox, oy; int octave, class_id;
+        if ((e >> 16) == 0xFFFFu) {                // incoming level-0 keypoint (ComputeKeyPointsCopy, :523-534)
+            const uvip_keypoint k = incoming[e & 0xFFFF];
+            level = 0; cx = __float2int_rn(k.x); cy = __float2int_rn(k.y);
+            response = k.response; size = k.size; ox = k.x; oy = k.y; octave = k.octave; class_id = k.class_id;
+        } else {
+            level = e >> 16;
+            const unsigned w = winners[(size_t)f * P.kp_per_frame + P.lv[level].kp_off + (e & 0xFFFF)];
+            cx = w & 0xFFF; cy = (w >> 12) & 0xFFF;
+            response = (float)(w >> 24); size = P.lv[level].size; octave = level; class_id = -1;
+            ox = (float)cx; oy = (float)cy;
+            if (level != 0) { ox = __fmul_rn(ox, P.lv[level].scale); oy = __fmul_rn(oy, P.lv[level].scale); }   // :951-957
+        }
+        const LevelInfo& L = P.lv[level];
+        const int ps = L.pstride;
+        const size_t plane = (size_t)f * P.frame_bytes + L.poff + (size_t)EDGE * ps + EDGE;
+        // ---- IC_Angle: lane u sums column u of the radius-15 disc; all row loads are issued before the first use
+        int m10 = 0, m01 = 0;
+        {
+            const uint8_t* p = pyr + plane + (ptrdiff_t)(cy - HALF_PATCH) * ps + (cx + u);
+            int vals[2 * HALF_PATCH + 1];
 #pragma unroll
-        for (int v = -HALF_PATCH; v <= HALF_PATCH; v++) { colsum += vals[v + HALF_PATCH]; m01 += v * vals[v + HALF_PATCH]; }
-        m10 = u * colsum;
-    }
+            for (int v = -HALF_PATCH; v <= HALF_PATCH; v++) { vals[v + HALF_PATCH] = ((v < 0 ? -v : v) <= vm) ? (int)__ldg(p) : 0; p += ps; }
+            int colsum = 0;
 #pragma unroll
-    for (int o = 16; o > 0; o >>= 1) { m10 += __shfl_xor_sync(0xFFFFFFFFu, m10, o); m01 += __shfl_xor_sync(0xFFFFFFFFu, m01, o); }
-    const float angle = fast_atan2_deg((float)m01, (float)m10);
-    // ---- rotated BRIEF
-    const float factorPI = (float)(3.14159265358979323846 / 180.f);
-    const float ang = __fmul_rn(angle, factorPI);
-    // glibc cosf/sinf are correctly rounded in practice; double-precision evaluation rounded once reproduces them
-    const float a = (float)cos((double)ang), b = (float)sin((double)ang);
-    const uint8_t* cb = blur + plane + (ptrdiff_t)cy * L.pstride + cx;
-    unsigned val = 0;
+            for (int v = -HALF_PATCH; v <= HALF_PATCH; v++) { colsum += vals[v + HALF_PATCH]; m01 += v * vals[v + HALF_PATCH]; }
+            m10 = u * colsum;
+        }
 #pragma unroll
-    for (int k = 0; k < 8; k++) {
-        const float x0 = (float)s_pat[2 * k][lane][0], y0 = (float)s_pat[2 * k][lane][1];
-        const float x1 = (float)s_pat[2 * k + 1][lane][0], y1 = (float)s_pat[2 * k + 1][lane][1];
-        const int r0 = __float2int_rn(__fadd_rn(__fmul_rn(x0, b), __fmul_rn(y0, a))), q0 = __float2int_rn(__fsub_rn(__fmul_rn(x0, a), __fmul_rn(y0, b)));
-        const int r1 = __float2int_rn(__fadd_rn(__fmul_rn(x1, b), __fmul_rn(y1, a))), q1 = __float2int_rn(__fsub_rn(__fmul_rn(x1, a), __fmul_rn(y1, b)));
-        const int t0 = __ldg(cb + (ptrdiff_t)r0 * L.pstride + q0), t1 = __ldg(cb + (ptrdiff_t)r1 * L.pstride + q1);
-        val |= (unsigned)(t0 < t1) << k;
-    }
-    desc[((size_t)f * out_cap + slot) * 32 + lane] = (uint8_t)val;
-    if (lane == 0) {
-        uvip_keypoint o;
-        o.x = ox; o.y = oy; o.size = size; o.angle = angle; o.response = response; o.octave = octave; o.class_id = class_id;
-        kps[(size_t)f * out_cap + slot] = o;
+        for (int o = 16; o > 0; o >>= 1) { m10 += __shfl_xor_sync(0xFFFFFFFFu, m10, o); m01 += __shfl_xor_sync(0xFFFFFFFFu, m01, o); }
+        const float angle = fast_atan2_deg((float)m01, (float)m10);
+        // ---- rotated BRIEF (:155-195): every float op rounded separately, cvRound = round-half-even
+        const float factorPI = (float)(3.14159265358979323846 / 180.f);
+        float a, b;
+        sincos_as_float(__fmul_rn(angle, factorPI), &b, &a);
+        const uint8_t* cb = blur + plane + (ptrdiff_t)cy * ps + cx;
+        unsigned val = 0;
+#pragma unroll
+        for (int k = 0; k < 8; k++) {
+            const float x0 = px[2 * k], y0 = py[2 * k], x1 = px[2 * k + 1], y1 = py[2 * k + 1];
+            const int r0 = __float2int_rn(__fadd_rn(__fmul_rn(x0, b), __fmul_rn(y0, a))), q0 = __float2int_rn(__fsub_rn(__fmul_rn(x0, a), __fmul_rn(y0, b)));
+            const int r1 = __float2int_rn(__fadd_rn(__fmul_rn(x1, b), __fmul_rn(y1, a))), q1 = __float2int_rn(__fsub_rn(__fmul_rn(x1, a), __fmul_rn(y1, b)));
+            const int t0 = __ldg(cb + (r0 * ps + q0)), t1 = __ldg(cb + (r1 * ps + q1));
+            val |= (unsigned)(t0 < t1) << k;
+        }
+        desc[((size_t)f * out_cap + slot) * 32 + lane] = (uint8_t)val;
+        if (lane == 0) {
+            uvip_keypoint o;
+            o.x = ox; o.y = oy; o.size = size; o.angle = angle; o.response = response; o.octave = octave; o.class_id = class_id;
+            kps[(size_t)f * out_cap + slot] = o;
+        }
     }
 }
 
@@ -1025,7 +1051,7 @@ struct uvip_extractor {
     Plan plan;                 // for (plan.W, plan.H); W == 0 -> none yet
     // working set sized for (max_width, max_height, max_batch)
     size_t cap_frame_bytes = 0; int cap_cells = 0, cap_raw = 0, cap_kp = 0, cap_tab = 0;
-    DevBuf pyr, blur, cand, labels, winners, counters, sel, nsel, tabs, status, grid, incoming, tmaps;
+    DevBuf pyr, blur, cand, labels, winners, counters, sel, nsel, tabs, status, grid, incoming, tmaps, pat_t;
     DevBuf in_frames, out_kps, out_desc, out_n;      // staging for the host-buffer entry points
     DevBuf in2, kps2, desc2, n2;                     // second staging set: uvip_extract_batch double-buffers its chunks
     cudaStream_t h2d_stream = nullptr, d2h_stream = nullptr;
@@ -1273,9 +1299,9 @@ static int enqueue_group(uvip_extractor* ex, const uint8_t* d_frames, int nframe
     ex->launches++;
     const int slots = out_cap < ex->sel_cap ? out_cap : ex->sel_cap;
     PROF_MARK(5);
-    k_describe<<<dim3(div_up(slots, DESC_WARPS), nframes), DESC_WARPS * 32, 0, st>>>(
+    k_describe<<<dim3(div_up(slots, DESC_WARPS * DESC_KPW), nframes), DESC_WARPS * 32, 0, st>>>(
         pyr, blur, ex->winners.as<unsigned>(), ex->sel.as<unsigned>(), ex->nsel.as<int>(), ex->sel_cap,
-        ex->incoming.as<uvip_keypoint>(), d_kps, d_desc, d_n_out, out_cap, ex->status.as<int>(), P);
+        ex->incoming.as<uvip_keypoint>(), ex->pat_t.as<float2>(), d_kps, d_desc, d_n_out, out_cap, ex->status.as<int>(), P);
     ex->launches++;
     PROF_MARK(6);
 #undef PROF_MARK
@@ -1364,10 +1390,23 @@ int uvip_extractor_create(const uvip_extractor_params* params, uvip_extractor** 
     rc |= ex->grid.reserve(16);
     rc |= ex->incoming.reserve(sizeof(uvip_keypoint));
     rc |= ex->tmaps.reserve(sizeof(CUtensorMap) * 3 * MAXLEV);
+    rc |= ex->pat_t.reserve(sizeof(float) * 2 * 512);
     if (rc) { uvip_extractor_destroy(ex); return UVIP_ERR_CUDA; }
     // zero the planes once so halo loads never see uninitialised memory
     cudaMemset(ex->pyr.p, 0, ex->pyr.cap); cudaMemset(ex->blur.p, 0, ex->blur.cap);
     cudaMemset(ex->status.p, 0, 16);
+    {   // pattern transposed for the descriptor kernel: entry [k][lane] = point 16*lane + k as (x, y) floats
+        std::vector<float> pt(2 * 512);
+        for (int lane = 0; lane < 32; lane++)
+            for (int k = 0; k < 16; k++) {
+                pt[2 * (k * 32 + lane)] = (float)h_pattern[2 * (16 * lane + k)];
+                pt[2 * (k * 32 + lane) + 1] = (float)h_pattern[2 * (16 * lane + k) + 1];
+            }
+        cudaMemcpy(ex->pat_t.p, pt.data(), pt.size() * sizeof(float), cudaMemcpyHostToDevice);
+        for (int uu = 0; uu <= HALF_PATCH; uu++)               // the descriptor kernel relies on the disc table being symmetric
+            for (int vv = 0; vv <= HALF_PATCH; vv++)
+                if ((uu <= ex->umax[vv]) != (vv <= ex->umax[uu])) { set_last_error("umax table is not symmetric"); uvip_extractor_destroy(ex); return UVIP_ERR_UNSUPPORTED; }
+    }
     if (cudaMemcpyToSymbol(c_pattern, h_pattern, sizeof(h_pattern)) != cudaSuccess ||
         cudaMemcpyToSymbol(c_umax, ex->umax, sizeof(ex->umax)) != cudaSuccess) {
         set_last_error("cudaMemcpyToSymbol failed: %s", cudaGetErrorString(cudaGetLastError()));
@@ -1392,7 +1431,7 @@ int uvip_extractor_destroy(uvip_extractor* ex)
     DeviceGuard g(ex->device);
     if (ex->stream) cudaStreamSynchronize(ex->stream);
     DevBuf* bufs[] = {&ex->pyr, &ex->blur, &ex->cand, &ex->labels, &ex->winners, &ex->counters, &ex->sel,
-                      &ex->nsel, &ex->tabs, &ex->status, &ex->grid, &ex->incoming, &ex->tmaps, &ex->in_frames, &ex->out_kps, &ex->out_desc, &ex->out_n,
+                      &ex->nsel, &ex->tabs, &ex->status, &ex->grid, &ex->incoming, &ex->tmaps, &ex->pat_t, &ex->in_frames, &ex->out_kps, &ex->out_desc, &ex->out_n,
                       &ex->in2, &ex->kps2, &ex->desc2, &ex->n2};
     for (DevBuf* b : bufs) b->release();
     for (cudaEvent_t e : ex->prof_ev) cudaEventDestroy(e);
