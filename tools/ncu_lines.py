@@ -47,6 +47,11 @@ best = None
 for fn, l in lines:
     if len(l) == len(data):
         best = l
+if best is None and lines:
+    # nvdisasm lists a few trailing padding instructions that ncu omits: align from the front
+    fn, l = min(lines, key=lambda t: abs(len(t[1]) - len(data)))
+    print('note: listing lengths differ (%d vs %d), aligned from the front' % (len(l), len(data)))
+    best = l[:len(data)] + [l[-1]] * max(0, len(data) - len(l))
 if best is None:
     print('could not align SASS listings:', [(fn, len(l)) for fn, l in lines], len(data)); sys.exit(1)
 srcs = {}

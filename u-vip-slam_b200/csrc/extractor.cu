@@ -60,48 +60,59 @@ struct Plan {
 // --------------------------------------------------------------------------------------------------------
 // K1a: import level 0 into the padded plane (+ reflect-101 border), 16 pixels per thread
 // --------------------------------------------------------------------------------------------------------
-__device__ __forceinline__ void store_mirrors(uint8_t* inner, int ps, int w, int h, int x, int y, uint8_t v)
+// reflect-101 source coordinate of ring coordinate r in [-BORDER_W, n + BORDER_W)
+__device__ __forceinline__ int reflect101(int r, int n) { return r < 0 ? -r : (r >= n ? 2 * (n - 1) - r : r); }
+
+// Border ring owned by a tile: every ring pixel whose reflect-101 SOURCE pixel lies inside [X0,X1) x [Y0,Y1).
+// fetch(sx, sy) returns the source pixel (from the input frame for level 0, from the freshly written plane otherwise).
+template <class Fetch>
+__device__ __forceinline__ void build_ring(uint8_t* inner, int ps, int w, int h, int X0, int X1, int Y0, int Y1, int tid, int nthreads, Fetch fetch)
 {
-    // write the reflections of interior pixel (x,y) that fall into the BORDER_W-wide border ring (reflect-101)
-    const bool l = x >= 1 && x <= BORDER_W, r = x >= w - 1 - BORDER_W && x <= w - 2;
-    const bool t = y >= 1 && y <= BORDER_W, b = y >= h - 1 - BORDER_W && y <= h - 2;
-    if (!(l | r | t | b)) return;
-    const int xl = -x, xr = 2 * (w - 1) - x;
-    uint8_t* row = inner + (ptrdiff_t)y * ps;
-    if (l) row[xl] = v;
-    if (r) row[xr] = v;
-    if (t) { uint8_t* q = inner + (ptrdiff_t)(-y) * ps; q[x] = v; if (l) q[xl] = v; if (r) q[xr] = v; }
-    if (b) { uint8_t* q = inner + (ptrdiff_t)(2 * (h - 1) - y) * ps; q[x] = v; if (l) q[xl] = v; if (r) q[xr] = v; }
+    // ring coordinates whose source falls into the tile, per axis (at most 2*BORDER_W each)
+    int rx[2 * BORDER_W], ry[2 * BORDER_W], nrx = 0, nry = 0;
+#pragma unroll
+    for (int k = 1; k <= BORDER_W; k++) {
+        if (k >= X0 && k < X1) rx[nrx++] = -k;
+        if (w - 1 - k >= X0 && w - 1 - k < X1) rx[nrx++] = w - 1 + k;
+        if (k >= Y0 && k < Y1) ry[nry++] = -k;
+        if (h - 1 - k >= Y0 && h - 1 - k < Y1) ry[nry++] = h - 1 + k;
+    }
+    if ((nrx | nry) == 0) return;
+    const int tw = X1 - X0, th = Y1 - Y0;
+    // A: mirrored columns x (interior rows + mirrored rows);  B: interior columns x mirrored rows
+    const int na = nrx * (th + nry), nb = tw * nry;
+    for (int i = tid; i < na + nb; i += nthreads) {
+        int x, y;
+        if (i < na) { const int c = i / (th + nry), r = i - c * (th + nry); x = rx[c]; y = r < th ? Y0 + r : ry[r - th]; }
+        else { const int j = i - na; const int r = j / tw; x = X0 + (j - r * tw); y = ry[r]; }
+        inner[(ptrdiff_t)y * ps + x] = fetch(reflect101(x, w), reflect101(y, h));
+    }
 }
 
 __global__ void __launch_bounds__(256)
-k_import(const uint8_t* __restrict__ frames, int stride, size_t frame_pitch, int vec_ok, uint8_t* __restrict__ pyr, const __grid_constant__ Plan P)
+k_import(const uint8_t* __restrict__ frames, int stride, size_t frame_pitch, int vec_ok, int copy_blocks, uint8_t* __restrict__ pyr,
+         const __grid_constant__ Plan P)
 {
     const LevelInfo& L = P.lv[0];
     const int f = blockIdx.y;
+    const uint8_t* fsrc = frames + (size_t)f * frame_pitch;
+    uint8_t* inner = pyr + (size_t)f * P.frame_bytes + L.poff + (size_t)EDGE * L.pstride + EDGE;
+    if ((int)blockIdx.x >= copy_blocks) {                       // ring blocks: reflect-101 border straight from the input frame
+        const int nb = gridDim.x - copy_blocks, b = blockIdx.x - copy_blocks;
+        build_ring(inner, L.pstride, L.w, L.h, 0, L.w, 0, L.h, b * 256 + threadIdx.x, nb * 256,
+                   [&](int sx, int sy) { return __ldg(fsrc + (size_t)sy * stride + sx); });
+        return;
+    }
     const int cpr = (L.w + 15) >> 4;                        // 16-px chunks per row
     const int idx = blockIdx.x * 256 + threadIdx.x;
     if (idx >= cpr * L.h) return;
     const int y = __umulhi((unsigned)idx, P.rcp_cpr), x0 = (idx - y * cpr) << 4;
-    const uint8_t* src = frames + (size_t)f * frame_pitch + (size_t)y * stride + x0;
-    uint8_t* inner = pyr + (size_t)f * P.frame_bytes + L.poff + (size_t)EDGE * L.pstride + EDGE;
+    const uint8_t* src = fsrc + (size_t)y * stride + x0;
     uint8_t* dst = inner + (size_t)y * L.pstride + x0;
-    const bool full = x0 + 16 <= L.w;
-    unsigned v[4] = {0, 0, 0, 0};
-    if (full && vec_ok) { const uint4 q = __ldg(reinterpret_cast<const uint4*>(src)); v[0] = q.x; v[1] = q.y; v[2] = q.z; v[3] = q.w; }
+    if (x0 + 16 <= L.w && vec_ok) *reinterpret_cast<uint4*>(dst) = __ldg(reinterpret_cast<const uint4*>(src));
     else {
-#pragma unroll
-        for (int k = 0; k < 16; k++) if (x0 + k < L.w) v[k >> 2] |= (unsigned)__ldg(src + k) << (8 * (k & 3));
-    }
-    if (full) *reinterpret_cast<uint4*>(dst) = make_uint4(v[0], v[1], v[2], v[3]);
-    else {
-#pragma unroll
-        for (int k = 0; k < 16; k++) if (x0 + k < L.w) dst[k] = (uint8_t)(v[k >> 2] >> (8 * (k & 3)));   // never touch the border ring: the mirror stores own it
-    }
-    if (x0 <= BORDER_W || x0 + 15 >= L.w - 1 - BORDER_W || y <= BORDER_W || y >= L.h - 1 - BORDER_W) {
 #pragma unroll 1
-        for (int k = 0; k < 16; k++)
-            if (x0 + k < L.w) store_mirrors(inner, L.pstride, L.w, L.h, x0 + k, y, (uint8_t)(v[k >> 2] >> (8 * (k & 3))));
+        for (int k = 0; k < 16 && x0 + k < L.w; k++) dst[k] = __ldg(src + k);      // never touches the border ring
     }
 }
 
@@ -150,11 +161,10 @@ k_resize(const CUtensorMap* __restrict__ tmaps, uint8_t* __restrict__ pyr, const
         }
     }
     mbar_wait(&s_mbar, 0);
-    if (!live) return;
     const unsigned* S = reinterpret_cast<const unsigned*>(s_rs);
     const int rw = P.rs_boxw >> 2;
     uint8_t* inner = pyr + (size_t)f * P.frame_bytes + D.poff + (size_t)EDGE * D.pstride + EDGE;
-    const bool edge_col = x <= BORDER_W || x + 3 >= D.w - 1 - BORDER_W;      // this thread's 4 columns touch the mirror zone
+    if (live) {
     int prev_sy = -100, h1[4] = {0, 0, 0, 0};
 #pragma unroll 2
     for (int j = 0; j < RS_R; j++) {
@@ -183,11 +193,12 @@ k_resize(const CUtensorMap* __restrict__ tmaps, uint8_t* __restrict__ pyr, const
         uint8_t* dst = inner + (size_t)y * D.pstride + x;
         if (x + 3 < D.w) *reinterpret_cast<unsigned*>(dst) = o;
         else for (int k = 0; k < 4; k++) if (x + k < D.w) dst[k] = (uint8_t)(o >> (8 * k));
-        if (edge_col || y <= BORDER_W || y >= D.h - 1 - BORDER_W) {
-#pragma unroll 1
-            for (int k = 0; k < 4; k++) if (x + k < D.w) store_mirrors(inner, D.pstride, D.w, D.h, x + k, y, (uint8_t)(o >> (8 * k)));
-        }
     }
+    }
+    // reflect-101 ring: every ring pixel whose source lies in this tile, after the tile is complete
+    __syncthreads();
+    build_ring(inner, D.pstride, D.w, D.h, X0, min(X0 + RS_W, D.w), Y0, min(Y0 + RS_H, D.h), tid, 256,
+               [&](int sx, int sy) { return inner[(ptrdiff_t)sy * D.pstride + sx]; });
 }
 
 // --------------------------------------------------------------------------------------------------------
@@ -1271,7 +1282,8 @@ static int enqueue_group(uvip_extractor* ex, const uint8_t* d_frames, int nframe
         const LevelInfo& L = P.lv[0];
         const int chunks = ((L.w + 15) >> 4) * L.h;
         const int vec_ok = (((uintptr_t)d_frames & 15) == 0 && (stride & 15) == 0 && (frame_pitch & 15) == 0) ? 1 : 0;
-        k_import<<<dim3(div_up(chunks, 256), nframes), 256, 0, st>>>(d_frames, stride, frame_pitch, vec_ok, pyr, P);
+        const int copy_blocks = div_up(chunks, 256);
+        k_import<<<dim3(copy_blocks + 8, nframes), 256, 0, st>>>(d_frames, stride, frame_pitch, vec_ok, copy_blocks, pyr, P);
         ex->launches++;
     }
     for (int l = 1; l < P.nlevels; l++) {
