@@ -184,6 +184,15 @@ int   uvip_search_window(uvip_matcher* m, const uvip_search_params* sp,
                          const float* kx, const float* ky, const int32_t* octave, const uint8_t* kdesc, int nk,
                          const int32_t* cell_start, const int32_t* cell_items,
                          int32_t* taken, int32_t* match, int* nmatches);
+/* Node-restricted search with claims over explicit candidate lists (CSR: cand_start[nq+1], cand_idx[]): the inner
+ * loops of SearchByBoW(KeyFrame*, FrameKTL&, ...) (src/ORBmatcher.cc:186-245; mode 2: best <= th and
+ * (float)best < ratio*(float)best2) and SearchByBoW(KeyFrame*, KeyFrame*, ...) (:751-811; mode 3: best < th, same
+ * ratio rule); mode 1 = best only, best <= th (Fuse / SearchByProjection(KF,Scw) with caller-built candidate lists,
+ * :1075-1100).  Queries are processed in array order (list them node-major like the reference's merge-join);
+ * taken/match as in uvip_search_window.  The DBoW2 feature vectors that define the lists stay on the caller's side. */
+int   uvip_search_lists(uvip_matcher* m, int mode, int th_dist, float ratio, const uint8_t* qdesc, int nq,
+                        const int32_t* cand_start, const int32_t* cand_idx, const uint8_t* kdesc, int nk,
+                        int32_t* taken, int32_t* match, int* nmatches);
 /* ORBmatcher::RadiusByViewingCos (src/ORBmatcher.cc:127-133) */
 float uvip_radius_by_viewing_cos(float view_cos);
 

@@ -274,3 +274,13 @@ def search_window(mode, th_dist, ratio, qu, qv, qr, qminL, qmaxL, qdesc, kx, ky,
                                C.c_float(minX), C.c_float(minY), C.c_float(inv_w), C.c_float(inv_h), cols, rows,
                                _p(tk), _p(match))
     return n, match, tk
+
+
+def search_lists(mode, th_dist, ratio, qdesc, cand_start, cand_idx, kdesc, taken=None):
+    qdesc = np.ascontiguousarray(qdesc, np.uint8); kdesc = np.ascontiguousarray(kdesc, np.uint8)
+    cs = np.ascontiguousarray(cand_start, np.int32); ci = np.ascontiguousarray(cand_idx, np.int32)
+    nq, nk = len(qdesc), len(kdesc)
+    tk = np.full(nk, -1, np.int32) if taken is None else np.ascontiguousarray(taken, np.int32).copy()
+    match = np.zeros(nq, np.int32)
+    n = lib().uo_search_lists(int(mode), int(th_dist), C.c_float(ratio), _p(qdesc), nq, _p(cs), _p(ci), _p(kdesc), nk, _p(tk), _p(match))
+    return n, match, tk

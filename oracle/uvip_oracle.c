@@ -868,3 +868,34 @@ int uo_search_window(const uo_search_params* sp,
     free(cand);
     return nmatches;
 }
+
+/* candidate-list search with claims: the node-restricted loops of SearchByBoW.
+ * mode 2 = SearchByBoW(KeyFrame*, FrameKTL&, ...) ORBmatcher.cc:186-245: top-2 from INT_MAX, accept best <= th && (float)best < ratio*(float)best2
+ * mode 3 = SearchByBoW(KeyFrame*, KeyFrame*, ...) ORBmatcher.cc:751-811: same scan, accept best < th (strict) && ratio
+ * mode 1 = best only, accept best <= th (Fuse / SearchByProjection(KF,Scw) with host-built candidate lists, :1075-1100)
+ * queries are visited in array order (the caller lists them in the reference's node-major order). */
+int uo_search_lists(int mode, int th_dist, float ratio, const uint8_t* qdesc, int nq,
+                    const int32_t* cand_start, const int32_t* cand_idx, const uint8_t* kdesc, int nk,
+                    int32_t* taken, int32_t* match_of_query)
+{
+    int nmatches = 0;
+    (void)nk;
+    for (int q = 0; q < nq; q++) {
+        match_of_query[q] = -1;
+        const uint8_t* d = qdesc + (size_t)q * 32;
+        int best1 = 2147483647, best2 = 2147483647, bestIdx = -1;
+        for (int c = cand_start[q]; c < cand_start[q + 1]; c++) {
+            const int idx = cand_idx[c];
+            if (taken[idx] != -1) continue;
+            const int dist = uo_descriptor_distance(d, kdesc + (size_t)idx * 32);
+            if (dist < best1) { best2 = best1; best1 = dist; bestIdx = idx; }
+            else if (dist < best2) best2 = dist;
+        }
+        int ok;
+        if (mode == 1) ok = best1 <= th_dist;
+        else if (mode == 2) ok = best1 <= th_dist && (float)best1 < ratio * (float)best2;
+        else ok = best1 < th_dist && (float)best1 < ratio * (float)best2;
+        if (ok && bestIdx >= 0) { taken[bestIdx] = q; match_of_query[q] = bestIdx; nmatches++; }
+    }
+    return nmatches;
+}

@@ -298,3 +298,36 @@ def test_search_window_claim_chain(gpu, oracle, synth):
                                                   grid['start'], grid['items'], grid['minX'], grid['minY'], grid['inv_w'], grid['inv_h'])
         assert n == on and np.array_equal(match, omatch) and np.array_equal(taken, otaken), mode
     assert n <= nk
+
+
+def test_search_by_bow_node_restricted_lists(gpu, oracle, synth):
+    """M6: SearchByBoW inner loops (src/ORBmatcher.cc:186-245, :751-811) over explicit candidate lists: top-2 inside a
+    vocabulary node, TH_LOW, ratio, sequential claims, rotation histogram."""
+    rng = np.random.default_rng(11)
+    n1, n2 = 1500, 1700
+    d1 = synth.random_descriptors(61, n1)
+    src = rng.integers(0, n1, n2)
+    d2 = synth.flip_bits(d1[src], 700, rng.integers(0, 40, n2).tolist())
+    fresh = rng.random(n2) < 0.3
+    d2[fresh] = synth.random_descriptors(62, n2)[fresh]
+    nodes1 = rng.integers(0, 60, n1)
+    nodes2 = np.where(rng.random(n2) < 0.9, nodes1[src], rng.integers(0, 60, n2))
+    a1 = rng.uniform(0, 360, n1).astype(np.float32)
+    a2 = np.mod(a1[src] + rng.normal(0, 4, n2), 360).astype(np.float32)
+    m = gpu.ORBmatcher(0.75, True)
+    # flat lists in the reference's node-major order
+    order = np.lexsort((np.arange(n1), nodes1))
+    lists = [np.nonzero(nodes2 == nodes1[i])[0] for i in order]
+    cs = np.zeros(n1 + 1, np.int32); cs[1:] = np.cumsum([len(l) for l in lists]); ci = np.concatenate(lists).astype(np.int32)
+    pre = np.full(n2, -1, np.int32); pre[::9] = -2
+    for mode, th in ((2, 50), (3, 50), (1, 50), (2, 256)):
+        n, match, taken = m.search_lists(mode, th, d1[order], cs, ci, d2, taken=pre)
+        on, omatch, otaken = oracle.search_lists(mode, th, np.float32(0.75), d1[order], cs, ci, d2, taken=pre)
+        assert n == on and np.array_equal(match, omatch) and np.array_equal(taken, otaken), mode
+        assert (match[match >= 0] % 9 != 0).all()
+    assert n > 300
+    full = m.SearchByBoW(d1, nodes1, a1, d2, nodes2, a2)
+    on, omatch, _ = oracle.search_lists(2, 50, np.float32(0.75), d1[order], cs, ci, d2)
+    ofull = np.full(n1, -1, np.int32); ofull[order] = omatch
+    assert np.array_equal(full, oracle.rot_hist_filter(ofull, a1, a2))
+    assert 0 < (full >= 0).sum() <= (ofull >= 0).sum()

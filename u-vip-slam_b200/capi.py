@@ -86,6 +86,7 @@ def lib():
         L.uvip_grid_build.argtypes = [vp, vp, vp, i, C.c_float, C.c_float, C.c_float, C.c_float, i, i, vp, vp]
         L.uvip_search_window.argtypes = [vp, C.POINTER(SearchParams), vp, vp, vp, vp, vp, vp, i,
                                          vp, vp, vp, vp, i, vp, vp, vp, vp, C.POINTER(i)]
+        L.uvip_search_lists.argtypes = [vp, i, i, C.c_float, vp, i, vp, vp, vp, i, vp, vp, C.POINTER(i)]
         L.uvip_popc_peak.argtypes = [i, i, C.POINTER(C.c_double)]
         _LIB = L
     return _LIB

@@ -259,6 +259,7 @@ struct SearchCtx {
     const float *qu, *qv, *qr; const int32_t *qminL, *qmaxL; const uint8_t* qdesc;
     const float *kx, *ky; const int32_t* octave; const uint8_t* kdesc;
     const int32_t *cell_start, *cell_items;
+    const int32_t *cand_start, *cand_idx;          // explicit candidate lists (node-restricted searches); NULL = grid window
 };
 
 __device__ __forceinline__ int hamming256(const uint4& u, const uint4& v, const uint8_t* __restrict__ row)
@@ -312,6 +313,29 @@ __device__ int search_one(const SearchCtx& c, int q, const int* __restrict__ own
     return bestIdx;
 }
 
+// node-restricted search (SearchByBoW inner loops, src/ORBmatcher.cc:186-245 and :751-811; mode 1 = best-only lists)
+__device__ int search_one_list(const SearchCtx& c, int q, const int* __restrict__ owner)
+{
+    const uvip_search_params& sp = c.sp;
+    const uint4 u = __ldg(reinterpret_cast<const uint4*>(c.qdesc + (size_t)q * 32));
+    const uint4 v = __ldg(reinterpret_cast<const uint4*>(c.qdesc + (size_t)q * 32) + 1);
+    int best1 = INT_MAX, best2 = INT_MAX, bestIdx = -1;
+    const int e = c.cand_start[q + 1];
+    for (int j = c.cand_start[q]; j < e; j++) {
+        const int id = c.cand_idx[j];
+        if (owner[id] < q) continue;                                   // vpMapPointMatches[realIdxF] / vbMatched2[idx2] already set
+        const int dist = hamming256(u, v, c.kdesc + (size_t)id * 32);
+        if (dist < best1) { best2 = best1; best1 = dist; bestIdx = id; }
+        else if (dist < best2) best2 = dist;
+    }
+    if (bestIdx < 0) return -1;
+    bool ok;
+    if (sp.mode == 1) ok = best1 <= sp.th_dist;
+    else if (sp.mode == 2) ok = best1 <= sp.th_dist && (float)best1 < __fmul_rn(sp.ratio, (float)best2);
+    else ok = best1 < sp.th_dist && (float)best1 < __fmul_rn(sp.ratio, (float)best2);
+    return ok ? bestIdx : -1;
+}
+
 // The reference loop is sequential: a query skips keypoints claimed by EARLIER queries.  Here every query
 // runs in parallel against the claims of the previous round (owner[idx] = lowest query index that claimed idx)
 // and rounds repeat until the claim table is a fixed point; by induction over the query index the fixed point
@@ -330,7 +354,7 @@ k_search_window(SearchCtx c, int nq, int nk, int32_t* __restrict__ taken, int32_
         if (threadIdx.x == 0) s_changed = 0;
         __syncthreads();
         for (int q = threadIdx.x; q < nq; q += blockDim.x) {
-            const int r = search_one(c, q, prev);
+            const int r = c.cand_start ? search_one_list(c, q, prev) : search_one(c, q, prev);
             match[q] = r;
             if (r >= 0) atomicMin(&cur[r], q);
         }
@@ -691,12 +715,55 @@ int uvip_search_window(uvip_matcher* m, const uvip_search_params* sp,
     UP(o_cs, cell_start, (size_t)(ncell + 1) * 4); UP(o_ci, cell_items, (size_t)nitems * 4);
     UP(o_taken, taken, (size_t)nk * 4);
 #undef UP
-    SearchCtx c;
+    SearchCtx c; memset(&c, 0, sizeof(c));
     c.sp = *sp;
     c.qu = (const float*)(base + o_qu); c.qv = (const float*)(base + o_qv); c.qr = (const float*)(base + o_qr);
     c.qminL = (const int32_t*)(base + o_qmin); c.qmaxL = (const int32_t*)(base + o_qmax); c.qdesc = base + o_qd;
     c.kx = (const float*)(base + o_kx); c.ky = (const float*)(base + o_ky); c.octave = (const int32_t*)(base + o_oct);
     c.kdesc = base + o_kd; c.cell_start = (const int32_t*)(base + o_cs); c.cell_items = (const int32_t*)(base + o_ci);
+    k_search_window<<<1, 1024, 0, st>>>(c, nq, nk, (int32_t*)(base + o_taken), (int32_t*)(base + o_match),
+                                         (int*)(base + o_oa), (int*)(base + o_ob), (int*)(base + o_cnt));
+    m->launches++;
+    UVIP_CUDA(cudaGetLastError());
+    int counts[2] = {0, 0};
+    UVIP_CUDA(cudaMemcpyAsync(match, base + o_match, (size_t)nq * 4, cudaMemcpyDeviceToHost, st));
+    if (nk) UVIP_CUDA(cudaMemcpyAsync(taken, base + o_taken, (size_t)nk * 4, cudaMemcpyDeviceToHost, st));
+    UVIP_CUDA(cudaMemcpyAsync(counts, base + o_cnt, 8, cudaMemcpyDeviceToHost, st));
+    UVIP_CUDA(cudaStreamSynchronize(st));
+    if (nmatches) *nmatches = counts[0];
+    return UVIP_OK;
+}
+
+int uvip_search_lists(uvip_matcher* m, int mode, int th_dist, float ratio, const uint8_t* qdesc, int nq,
+                      const int32_t* cand_start, const int32_t* cand_idx, const uint8_t* kdesc, int nk,
+                      int32_t* taken, int32_t* match, int* nmatches)
+{
+    UVIP_CHECK_ARG(m && nq >= 0 && nk >= 0 && mode >= 1 && mode <= 3);
+    if (nmatches) *nmatches = 0;
+    if (nq == 0) return UVIP_OK;
+    UVIP_CHECK_ARG(qdesc && cand_start && match && (nk == 0 || (kdesc && taken)));
+    const int ncand = cand_start[nq];
+    UVIP_CHECK_ARG(ncand >= 0 && (ncand == 0 || cand_idx));
+    for (int i = 0; i < ncand; i++) UVIP_CHECK_ARG(cand_idx[i] >= 0 && cand_idx[i] < nk);
+    std::lock_guard<std::mutex> lk(m->mu);
+    DeviceGuard g(m->device);
+    size_t off = 0;
+    auto sect = [&](size_t bytes) { size_t o = off; off = align_up(off + bytes, 32); return o; };
+    const size_t nkk = nk > 0 ? nk : 1;
+    const size_t o_qd = sect((size_t)nq * 32), o_kd = sect(nkk * 32), o_cs = sect((size_t)(nq + 1) * 4), o_ci = sect((size_t)(ncand > 0 ? ncand : 1) * 4);
+    const size_t o_taken = sect(nkk * 4), o_match = sect((size_t)nq * 4), o_oa = sect(nkk * 4), o_ob = sect(nkk * 4), o_cnt = sect(16);
+    int rc;
+    if ((rc = m->misc.reserve(off))) return rc;
+    uint8_t* base = m->misc.as<uint8_t>();
+    cudaStream_t st = m->stream;
+#define UP(o, src, bytes) if ((bytes) > 0) UVIP_CUDA(cudaMemcpyAsync(base + (o), (src), (bytes), cudaMemcpyHostToDevice, st))
+    UP(o_qd, qdesc, (size_t)nq * 32); UP(o_kd, kdesc, (size_t)nk * 32); UP(o_cs, cand_start, (size_t)(nq + 1) * 4);
+    UP(o_ci, cand_idx, (size_t)ncand * 4); UP(o_taken, taken, (size_t)nk * 4);
+#undef UP
+    SearchCtx c; memset(&c, 0, sizeof(c));
+    c.sp.mode = mode; c.sp.th_dist = th_dist; c.sp.ratio = ratio;
+    c.qdesc = base + o_qd; c.kdesc = base + o_kd;
+    c.cand_start = (const int32_t*)(base + o_cs); c.cand_idx = (const int32_t*)(base + o_ci);
     k_search_window<<<1, 1024, 0, st>>>(c, nq, nk, (int32_t*)(base + o_taken), (int32_t*)(base + o_match),
                                          (int*)(base + o_oa), (int*)(base + o_ob), (int*)(base + o_cnt));
     m->launches++;

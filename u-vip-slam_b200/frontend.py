@@ -218,6 +218,34 @@ class ORBmatcher:
                                        ptr(i32(grid['items'])), ptr(tk), ptr(match), C.byref(n)))
         return n.value, match, tk
 
+    def search_lists(self, mode, th_dist, qdesc, cand_start, cand_idx, kdesc, taken=None, ratio=None):
+        qdesc = np.ascontiguousarray(qdesc, np.uint8); kdesc = np.ascontiguousarray(kdesc, np.uint8)
+        cs = np.ascontiguousarray(cand_start, np.int32); ci = np.ascontiguousarray(cand_idx, np.int32)
+        nq, nk = len(qdesc), len(kdesc)
+        tk = np.full(nk, -1, np.int32) if taken is None else np.ascontiguousarray(taken, np.int32).copy()
+        match = np.full(nq, -1, np.int32); n = C.c_int()
+        check(lib().uvip_search_lists(self.h, int(mode), int(th_dist), float(self.mfNNratio if ratio is None else ratio), ptr(qdesc), nq,
+                                      ptr(cs), ptr(ci), ptr(kdesc), nk, ptr(tk), ptr(match), C.byref(n)))
+        return n.value, match, tk
+
+    def SearchByBoW(self, desc1, nodes1, angles1, desc2, nodes2, angles2, keyframe_pair=False):
+        """SearchByBoW (src/ORBmatcher.cc:155-284 / :715-850) over flat arrays: nodesX[i] = vocabulary node id of feature i
+        (what DBoW2's FeatureVector groups by).  Features of set 1 are the queries, visited node-major (ascending node id,
+        then feature index), matched inside the same node of set 2; TH_LOW, ratio, claims, rotation histogram."""
+        nodes1 = np.asarray(nodes1); nodes2 = np.asarray(nodes2)
+        order = np.lexsort((np.arange(len(nodes1)), nodes1))
+        common = np.intersect1d(nodes1, nodes2)
+        order = order[np.isin(nodes1[order], common)]
+        by_node = {n: np.nonzero(nodes2 == n)[0] for n in common}
+        lists = [by_node[nodes1[i]] for i in order]
+        cs = np.zeros(len(order) + 1, np.int32); cs[1:] = np.cumsum([len(l) for l in lists])
+        ci = np.concatenate(lists).astype(np.int32) if len(lists) else np.zeros(0, np.int32)
+        n, match, taken = self.search_lists(3 if keyframe_pair else 2, self.TH_LOW, np.asarray(desc1)[order], cs, ci, desc2)
+        full = np.full(len(nodes1), -1, np.int32); full[order] = match
+        if self.mbCheckOrientation:
+            full = self.rot_hist_filter(full, angles1, angles2)
+        return full
+
     def SearchByProjection(self, frame, map_points, th=1.0, taken=None):
         """SearchByProjection(FrameKTL&, const vector<MapPoint*>&, float th) (src/ORBmatcher.cc:49-125) over flat arrays.
         frame: dict(kx, ky, octave, kdesc, grid, scale_factors); map_points: dict(u, v, level, view_cos, desc)."""
