@@ -331,3 +331,32 @@ def test_search_by_bow_node_restricted_lists(gpu, oracle, synth):
     ofull = np.full(n1, -1, np.int32); ofull[order] = omatch
     assert np.array_equal(full, oracle.rot_hist_filter(ofull, a1, a2))
     assert 0 < (full >= 0).sum() <= (ofull >= 0).sum()
+
+
+def test_extract_parameter_sweep(gpu, oracle, synth):
+    """randomised sweep over shapes, level counts, scale factors, quotas and thresholds: keypoints (position, order,
+    response, octave) and descriptors must equal the oracle's for every draw"""
+    rng = np.random.default_rng(2024)
+    for trial in range(24):
+        W = int(rng.integers(160, 900)); H = int(rng.integers(140, 700))
+        if W < 0.55 * H:
+            continue
+        nlev = int(rng.integers(1, 9)); sf = float(rng.choice([1.1, 1.2, 1.2, 1.3, 1.5]))
+        while min(W, H) / sf ** (nlev - 1) < 70:
+            nlev -= 1
+        nf = int(rng.integers(50, 2500)); th = int(rng.choice([5, 7, 12, 20, 20, 30]))
+        img = synth.synth_frame(int(rng.integers(1, 1 << 30)), W, H)
+        if trial % 5 == 4:
+            img = (img // 4 + 90).astype(np.uint8)                # low contrast: many cells fall back to the retry threshold
+        ex = gpu.ORBextractor(nf, sf, nlev, 1, th, max_width=W, max_height=H)
+        oex = oracle.Extractor(nf, sf, nlev, 1, th)
+        kps, desc = ex(img, cap=nf + 8 * nlev + 4096)
+        okps, odesc = oex(img)
+        tag = (trial, W, H, nlev, sf, nf, th)
+        assert len(kps) == len(okps), tag
+        for fld in ('x', 'y', 'size', 'response', 'octave', 'class_id'):
+            assert np.array_equal(kps[fld], okps[fld]), (tag, fld)
+        if len(kps):
+            assert np.abs(kps['angle'] - okps['angle']).max() <= ANGLE_TOL_DEG, tag
+            assert 1.0 - np.unpackbits(desc ^ odesc).mean() >= DESC_BITS_MIN, tag
+        ex.close()
