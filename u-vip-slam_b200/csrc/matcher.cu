@@ -39,19 +39,24 @@ __global__ void __launch_bounds__(KNN_THREADS)
 k_knn2(const uint8_t* __restrict__ q_base, const int32_t* __restrict__ d_nq, size_t q_pitch,
        const uint8_t* __restrict__ t_base, const int32_t* __restrict__ d_nt, size_t t_pitch,
        int nq_fixed, int nt_fixed, int idx_base,
-       int32_t* __restrict__ idx2, int32_t* __restrict__ dist2, size_t res_pitch)
+       int32_t* __restrict__ idx2, int32_t* __restrict__ dist2, size_t res_pitch, int split_rows, size_t split_stride)
 {
     __shared__ __align__(128) uint8_t s_tile[2][KNN_STAGE_BYTES];
     __shared__ __align__(8) uint64_t s_bar[2];
 
     const int pair = blockIdx.y;
     const int nq = d_nq ? d_nq[pair] : nq_fixed;
-    const int nt = d_nt ? d_nt[pair] : nt_fixed;
-    if ((int)(blockIdx.x * KNN_THREADS) >= nq) return;          // uniform per block
+    int nt = d_nt ? d_nt[pair] : nt_fixed;
+    if ((int)(blockIdx.x * blockDim.x) >= nq) return;           // uniform per block
     const uint8_t* q = q_base + (size_t)pair * q_pitch;
     const uint8_t* t = t_base + (size_t)pair * t_pitch;
+    if (split_rows > 0) {                                       // blockIdx.z owns train rows [z*split_rows, (z+1)*split_rows)
+        const int z0 = blockIdx.z * split_rows;
+        t += (size_t)z0 * 32; idx_base += z0; nt = max(0, min(split_rows, nt - z0));
+        idx2 += (size_t)blockIdx.z * split_stride; dist2 += (size_t)blockIdx.z * split_stride;
+    }
     const int tid = threadIdx.x;
-    const int qi = blockIdx.x * KNN_THREADS + tid;
+    const int qi = blockIdx.x * blockDim.x + tid;
     const bool live = qi < nq;
 
     uint32_t a0 = 0, a1 = 0, a2 = 0, a3 = 0, a4 = 0, a5 = 0, a6 = 0, a7 = 0;
@@ -457,9 +462,30 @@ static int launch_knn2(uvip_matcher* m, const uint8_t* d_q, const int32_t* d_nq,
     UVIP_CHECK_ARG(((uintptr_t)d_q & 15) == 0 && ((uintptr_t)d_t & 15) == 0 && (q_pitch & 15) == 0 && (t_pitch & 15) == 0);
     UVIP_CHECK_ARG(((uintptr_t)d_idx2 & 7) == 0 && ((uintptr_t)d_dist2 & 7) == 0);
     if (npairs <= 0 || max_nq <= 0) return UVIP_OK;
-    dim3 grid(div_up(max_nq, KNN_THREADS), npairs);
-    k_knn2<<<grid, KNN_THREADS, 0, st>>>(d_q, d_nq, q_pitch, d_t, d_nt, t_pitch, nq_fixed, nt_fixed, idx_base,
-                                          d_idx2, d_dist2, res_pitch);
+    int sms = 148; cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, m->device);
+    const long long ctas = (long long)div_up(max_nq, KNN_THREADS) * npairs;
+    // mid-size single problems leave SMs short of warps: split the train rows over blockIdx.z and merge the partial top-2
+    int nz = 1;
+    if (npairs == 1 && !d_nt && ctas < 8LL * sms && nt_fixed >= 8192) {
+        nz = (int)((8LL * sms + ctas - 1) / ctas); if (nz > 16) nz = 16;
+        while (nz > 1 && nt_fixed / nz < 4096) nz--;
+    }
+    if (nz > 1) {
+        const size_t part = (size_t)max_nq * 2;
+        int rc;
+        if ((rc = m->misc2.reserve(part * nz * 4))) return rc;
+        if ((rc = m->misc3.reserve(part * nz * 4))) return rc;
+        const int rows = (int)align_up((size_t)div_up(nt_fixed, nz), 256);
+        dim3 grid(div_up(max_nq, KNN_THREADS), 1, div_up(nt_fixed, rows));
+        k_knn2<<<grid, KNN_THREADS, 0, st>>>(d_q, d_nq, q_pitch, d_t, d_nt, t_pitch, nq_fixed, nt_fixed, idx_base,
+                                              m->misc2.as<int32_t>(), m->misc3.as<int32_t>(), 0, rows, part);
+        m->launches++;
+        k_knn2_merge<<<div_up(max_nq, 256), 256, 0, st>>>(m->misc2.as<int32_t>(), m->misc3.as<int32_t>(), (int)grid.z, part, max_nq, d_idx2, d_dist2);
+    } else {
+        dim3 grid(div_up(max_nq, KNN_THREADS), npairs);
+        k_knn2<<<grid, KNN_THREADS, 0, st>>>(d_q, d_nq, q_pitch, d_t, d_nt, t_pitch, nq_fixed, nt_fixed, idx_base,
+                                              d_idx2, d_dist2, res_pitch, 0, 0);
+    }
     m->launches++;
     UVIP_CUDA(cudaGetLastError());
     return UVIP_OK;
