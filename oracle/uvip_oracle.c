@@ -184,8 +184,15 @@ static const int k_ring_dy[16] = {3, 3, 2, 1, 0, -1, -2, -3, -3, -3, -2, -1, 0, 
 
 static int fast_corner_score(const uint8_t* p, int stride, int th)  /* returns -1 if not a corner at th */
 {
+    /* OpenCV-style early outs first (a 9-arc holds one pixel of every opposite ring pair), so that this CPU baseline
+     * is not artificially slow; the decision and the score are those of the plain definition below. */
+    const int v = p[0], lo = v - th, hi = v + th;
+    int r, br, dk, b = 1, k_ = 1;
+#define PAIR(o1, o2) r = p[o1]; br = r > hi; dk = r < lo; r = p[o2]; br |= r > hi; dk |= r < lo; b &= br; k_ &= dk; if (!(b | k_)) return -1;
+    PAIR(3 * stride, -3 * stride) PAIR(3, -3) PAIR(2 * stride + 2, -2 * stride - 2) PAIR(-2 * stride + 2, 2 * stride - 2)
+    PAIR(3 * stride + 1, -3 * stride - 1) PAIR(stride + 3, -stride - 3) PAIR(-stride + 3, stride - 3) PAIR(-3 * stride + 1, 3 * stride - 1)
+#undef PAIR
     int d[25];
-    int v = p[0];
     for (int k = 0; k < 16; k++) d[k] = (int)p[k_ring_dy[k] * stride + k_ring_dx[k]] - v;
     for (int k = 16; k < 25; k++) d[k] = d[k - 16];
     int A = -256, B = -256;     /* A: best bright arc min(d); B: best dark arc min(-d) */
@@ -205,8 +212,10 @@ int uo_fast9(const uint8_t* img, int stride, int w, int h, int th, int nms,
 {
     int n = 0;
     if (w < 7 || h < 7) return 0;
-    uint8_t* sc = (uint8_t*)calloc((size_t)w * h, 1);
-    uint8_t* isc = (uint8_t*)calloc((size_t)w * h, 1);
+    static __thread uint8_t* scratch = NULL; static __thread size_t scratch_cap = 0;   /* per-thread, reused across the ~1000 cell calls of a frame */
+    if (scratch_cap < 2 * (size_t)w * h) { free(scratch); scratch_cap = 2 * (size_t)w * h; scratch = (uint8_t*)malloc(scratch_cap); }
+    uint8_t* sc = scratch; uint8_t* isc = scratch + (size_t)w * h;
+    memset(scratch, 0, 2 * (size_t)w * h);
     for (int y = 3; y < h - 3; y++)
         for (int x = 3; x < w - 3; x++) {
             int s = fast_corner_score(img + (size_t)y * stride + x, stride, th);
@@ -229,7 +238,6 @@ int uo_fast9(const uint8_t* img, int stride, int w, int h, int th, int nms,
                 n++;
             }
         }
-    free(sc); free(isc);
     return n;
 }
 
