@@ -25,6 +25,9 @@ void set_last_error(const char* fmt, ...) {
 // Running top-2 is kept as packed 32-bit keys (dist << 16 | row-in-supertile): unique keys give the
 // (distance, index) order, i.e. the reference's strict '<' scan where the first candidate wins ties.
 // =====================================================================================================
+#ifndef UVIP_KNN_CSA
+#define UVIP_KNN_CSA 1
+#endif
 constexpr int KNN_THREADS = 128;
 constexpr int KNN_TILE = 256;                      // train rows per stage
 constexpr int KNN_STAGE_BYTES = KNN_TILE * 32;
@@ -33,6 +36,26 @@ constexpr int KNN_SUPER = 256;                     // tiles per 16-bit index win
 __device__ __forceinline__ void top2_push(int d, int gi, int& d1, int& i1, int& d2, int& i2) {
     if (d < d1) { d2 = d1; i2 = i1; d1 = d; i1 = gi; }
     else if (d < d2) { d2 = d; i2 = gi; }
+}
+
+__device__ __forceinline__ int hamming8(uint32_t a0, uint32_t a1, uint32_t a2, uint32_t a3, uint32_t a4, uint32_t a5, uint32_t a6, uint32_t a7,
+                                        const uint4 u, const uint4 v)
+{
+#if UVIP_KNN_CSA
+    // Harley-Seal carry-save reduction: 8 XOR words -> ones/twos/fours/eights bit planes, 4 POPC instead of 8
+    const unsigned x0 = a0 ^ u.x, x1 = a1 ^ u.y, x2 = a2 ^ u.z, x3 = a3 ^ u.w, x4 = a4 ^ v.x, x5 = a5 ^ v.y, x6 = a6 ^ v.z, x7 = a7 ^ v.w;
+    const unsigned s1 = x0 ^ x1 ^ x2, c1 = (x0 & x1) | ((x0 ^ x1) & x2);
+    const unsigned s2 = x3 ^ x4 ^ x5, c2 = (x3 & x4) | ((x3 ^ x4) & x5);
+    const unsigned s3 = s1 ^ s2 ^ x6, c3 = (s1 & s2) | ((s1 ^ s2) & x6);
+    const unsigned ones = s3 ^ x7, c4 = s3 & x7;
+    const unsigned ts = c1 ^ c2 ^ c3, tc = (c1 & c2) | ((c1 ^ c2) & c3);
+    const unsigned twos = ts ^ c4, f2 = ts & c4;
+    const unsigned fours = tc ^ f2, eights = tc & f2;
+    return __popc(ones) + 2 * __popc(twos) + 4 * __popc(fours) + 8 * __popc(eights);
+#else
+    return (__popc(a0 ^ u.x) + __popc(a1 ^ u.y) + __popc(a2 ^ u.z)) + (__popc(a3 ^ u.w) + __popc(a4 ^ v.x) + __popc(a5 ^ v.y)) +
+           (__popc(a6 ^ v.z) + __popc(a7 ^ v.w));
+#endif
 }
 
 __global__ void __launch_bounds__(KNN_THREADS)
@@ -90,13 +113,21 @@ k_knn2(const uint8_t* __restrict__ q_base, const int32_t* __restrict__ d_nq, siz
         const int rows = min(KNN_TILE, nt - i * KNN_TILE);
         const uint4* T = reinterpret_cast<const uint4*>(s_tile[s]);
         uint32_t key = (uint32_t)((i & (KNN_SUPER - 1)) * KNN_TILE);
-#pragma unroll 4
-        for (int j = 0; j < rows; j++) {
-            const uint4 u = T[2 * j], v = T[2 * j + 1];
-            const int d = (__popc(a0 ^ u.x) + __popc(a1 ^ u.y) + __popc(a2 ^ u.z)) +
-                          (__popc(a3 ^ u.w) + __popc(a4 ^ v.x) + __popc(a5 ^ v.y)) +
-                          (__popc(a6 ^ v.z) + __popc(a7 ^ v.w));
-            const uint32_t k = ((uint32_t)d << 16) + key + (uint32_t)j;
+        // keys of 4 train rows at a time; the running top-2 is touched only when one of them beats the current second best
+        // (rare: a query's top-2 changes O(log n) times over a scan), which takes the 3 VIMNMX per pair off the ALU pipe
+        int j = 0;
+        for (; j + 4 <= rows; j += 4) {
+            uint32_t k4[4];
+#pragma unroll
+            for (int r = 0; r < 4; r++) k4[r] = ((uint32_t)hamming8(a0, a1, a2, a3, a4, a5, a6, a7, T[2 * (j + r)], T[2 * (j + r) + 1]) << 16) + key + (uint32_t)(j + r);
+            const uint32_t mn = min(__vimin3_u32(k4[0], k4[1], k4[2]), k4[3]);
+            if (mn < b2) {
+#pragma unroll
+                for (int r = 0; r < 4; r++) { const uint32_t lo = min(b1, k4[r]), hi = max(b1, k4[r]); b2 = min(b2, hi); b1 = lo; }
+            }
+        }
+        for (; j < rows; j++) {
+            const uint32_t k = ((uint32_t)hamming8(a0, a1, a2, a3, a4, a5, a6, a7, T[2 * j], T[2 * j + 1]) << 16) + key + (uint32_t)j;
             const uint32_t lo = min(b1, k), hi = max(b1, k);
             b2 = min(b2, hi);
             b1 = lo;
