@@ -491,7 +491,7 @@ k_fast(const CUtensorMap* __restrict__ tmaps, const unsigned* __restrict__ tile_
                 if (keep) {
                     const int o = base + __popc(bal & ((1u << lane) - 1));
                     if (o < L.raw_cap) gdst[o] = rec; else atomicOr(status, 1);
-                    atomicAdd(&s_surv[cell], 1);
+                    s_surv[cell] = 1;                      // only "any survivor" matters: plain store, every writer stores 1
                 }
             }
         }
