@@ -6,6 +6,7 @@
 //            [matcher] int32 nmatches ; nq int32 (keypoint index per map point or -1)
 #include <cstdio>
 #include <cstdlib>
+#include <map>
 #include <vector>
 #include "../../u-vip-slam_b200/host/ORBextractor.h"
 #include "../../u-vip-slam_b200/host/ORBmatcher.h"
@@ -16,9 +17,18 @@ struct MockMapPoint {
     bool isBad() const { return bad; }
     cv::Mat GetDescriptor() const { return desc; }
 };
+typedef std::map<unsigned, std::vector<unsigned> > FeatureVector;     // DBoW2::FeatureVector
 struct MockFrame {
-    std::vector<cv::KeyPoint> mvKeysUn; cv::Mat mDescriptors; std::vector<MockMapPoint*> mvpMapPoints; std::vector<float> mvScaleFactors;
+    std::vector<cv::KeyPoint> mvKeysUn, mvKeys; cv::Mat mDescriptors; std::vector<MockMapPoint*> mvpMapPoints; std::vector<float> mvScaleFactors;
     int mnMinX = 0, mnMinY = 0; float mfGridElementWidthInv = 0, mfGridElementHeightInv = 0;
+    FeatureVector mFeatVec;
+};
+struct MockKeyFrame {
+    std::vector<MockMapPoint*> mps; FeatureVector fv; cv::Mat desc; std::vector<cv::KeyPoint> keys;
+    std::vector<MockMapPoint*> GetMapPointMatches() { return mps; }
+    FeatureVector GetFeatureVector() { return fv; }
+    cv::Mat GetDescriptor(size_t i) { return desc.row((int)i); }
+    cv::KeyPoint GetKeyPointUn(size_t i) const { return keys[i]; }
 };
 
 static void put(FILE* f, const void* p, size_t n) { if (fwrite(p, 1, n, f) != n) { perror("write"); exit(2); } }
@@ -80,6 +90,25 @@ int main(int argc, char** argv)
         put(fo, owner.data(), (size_t)n * 4);
         int dd = USLAM::ORBmatcher::DescriptorDistance(desc.row(0), desc.row(n > 1 ? 1 : 0));
         put(fo, &dd, 4);
+        // 4. SearchByBoW(KeyFrame*, Frame&): the keyframe holds the same features; node id = (x / 64) + 16 * (y / 64) puts
+        //    ~30 features into a node, a few map points are missing / bad
+        MockKeyFrame KF; MockFrame F2;
+        KF.desc = desc; KF.keys = kps; F2.mDescriptors = desc; F2.mvKeys = kps; F2.mvpMapPoints.assign((size_t)n, nullptr);
+        std::vector<MockMapPoint> kfmps((size_t)n);
+        for (int i = 0; i < n; i++) {
+            const unsigned node = (unsigned)(kps[i].pt.x / 64) + 16u * (unsigned)(kps[i].pt.y / 64);
+            KF.fv[node].push_back((unsigned)i);
+            if (i % 17 != 3) F2.mFeatVec[node + (i % 29 == 0 ? 1000u : 0u)].push_back((unsigned)i);
+            kfmps[i].bad = (i % 19) == 0;
+            KF.mps.push_back((i % 7 == 0) ? nullptr : &kfmps[i]);
+        }
+        USLAM::ORBmatcher bow(0.9f, true);
+        std::vector<MockMapPoint*> vm;
+        const int nb = bow.SearchByBoW(&KF, F2, vm);
+        put(fo, &nb, 4);
+        std::vector<int> bowner((size_t)n, -1);
+        for (int i = 0; i < n; i++) if (vm[i]) bowner[i] = (int)(vm[i] - kfmps.data());
+        put(fo, bowner.data(), (size_t)n * 4);
     } catch (const std::exception& e) {
         fprintf(stderr, "shim error: %s\n", e.what());
         fclose(fo);

@@ -103,3 +103,27 @@ def test_shim_matches_oracle(pkg, oracle, synth, shim_exe, tmp_path):
     assert np.array_equal(owner, expect_owner)
     dd = int(take(np.int32, 1)[0])
     assert dd == oracle.descriptor_distance(odesc[0], odesc[1])
+    # 4. SearchByBoW(KeyFrame*, Frame&) through the shim: node-major query order, claims, TH_LOW, ratio 0.9, histogram
+    nb = int(take(np.int32, 1)[0]); bowner = take(np.int32, n)
+    node = (okps['x'] / np.float32(64)).astype(np.int64) + 16 * (okps['y'] / np.float32(64)).astype(np.int64)
+    fnode = {}
+    for k in range(n):
+        if k % 17 != 3:
+            fnode.setdefault(int(node[k]) + (1000 if k % 29 == 0 else 0), []).append(k)
+    queries, cs, ci = [], [0], []
+    for nd in sorted(set(node.tolist())):
+        if nd not in fnode:
+            continue
+        for k in np.nonzero(node == nd)[0]:
+            if k % 7 == 0 or k % 19 == 0:
+                continue                                          # no map point / bad map point
+            queries.append(int(k)); ci.extend(fnode[nd]); cs.append(len(ci))
+    queries = np.array(queries)
+    on, omatch, _ = oracle.search_lists(2, 50, np.float32(0.9), odesc[queries], np.array(cs, np.int32), np.array(ci, np.int32), odesc)
+    omatch = oracle.rot_hist_filter(omatch, okps['angle'][queries], okps['angle'])
+    expect = np.full(n, -1, np.int32)
+    for qi, k in enumerate(omatch):
+        if k >= 0:
+            expect[k] = queries[qi]
+    assert nb == int((omatch >= 0).sum()) and nb > 300
+    assert np.array_equal(bowner, expect)

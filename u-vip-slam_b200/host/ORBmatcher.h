@@ -4,7 +4,9 @@
 // SCATTERED back, so Tracking / LocalMapping / LoopClosing stay untouched.  The member templates accept
 // the reference's own FrameKTL / MapPoint types (they only use the members cited below), or mock types in tests.
 #pragma once
+#include <cmath>
 #include <cstring>
+#include <map>
 #include <stdexcept>
 #include <string>
 #include <vector>
@@ -80,6 +82,55 @@ public:
                                  kx.data(), ky.data(), oct.data(), kd.data(), nk, cs.data(), ci.data(), taken.data(), match.data(), &nmatches),
               "uvip_search_window");
         for (int q = 0; q < nq; q++) if (match[q] >= 0) F.mvpMapPoints[match[q]] = who[q];     // :119
+        return nmatches;
+    }
+
+    // SearchByBoW(KeyFrame*, FrameKTL&, vector<MapPoint*>&)  (src/ORBmatcher.cc:155-284): brute force restricted to features
+    // of the same vocabulary node, TH_LOW + ratio, claims in the reference's node-major order, rotation histogram.
+    // KeyFrameT needs: GetMapPointMatches(), GetFeatureVector() (a std::map<node id, vector<unsigned>>), GetDescriptor(i),
+    //                  GetKeyPointUn(i);  FrameT needs: mvpMapPoints, mFeatVec, mDescriptors, mvKeys
+    template <class KeyFrameT, class FrameT, class MapPointT>
+    int SearchByBoW(KeyFrameT* pKF, FrameT& F, std::vector<MapPointT*>& vpMapPointMatches)
+    {
+        ensure();
+        const std::vector<MapPointT*> vpMapPointsKF = pKF->GetMapPointMatches();
+        vpMapPointMatches = std::vector<MapPointT*>(F.mvpMapPoints.size(), static_cast<MapPointT*>(NULL));
+        const auto vFeatVecKF = pKF->GetFeatureVector();
+        std::vector<unsigned char> qd; std::vector<int32_t> cs(1, 0), ci; std::vector<unsigned> qidx;
+        auto KFit = vFeatVecKF.begin(); auto Fit = F.mFeatVec.begin();
+        while (KFit != vFeatVecKF.end() && Fit != F.mFeatVec.end()) {          // merge-join by node id (:176-252)
+            if (KFit->first == Fit->first) {
+                for (size_t iKF = 0; iKF < KFit->second.size(); iKF++) {
+                    const unsigned realIdxKF = KFit->second[iKF];
+                    MapPointT* pMP = vpMapPointsKF[realIdxKF];
+                    if (!pMP) continue;
+                    if (pMP->isBad()) continue;
+                    const cv::Mat dKF = pKF->GetDescriptor(realIdxKF);
+                    qd.insert(qd.end(), dKF.ptr(0), dKF.ptr(0) + 32);
+                    for (size_t iF = 0; iF < Fit->second.size(); iF++) ci.push_back((int32_t)Fit->second[iF]);
+                    cs.push_back((int32_t)ci.size());
+                    qidx.push_back(realIdxKF);
+                }
+                ++KFit; ++Fit;
+            } else if (KFit->first < Fit->first) KFit = vFeatVecKF.lower_bound(Fit->first);
+            else Fit = F.mFeatVec.lower_bound(KFit->first);
+        }
+        const int nq = (int)qidx.size(), nk = (int)F.mvpMapPoints.size();
+        if (nq == 0 || nk == 0) return 0;
+        std::vector<unsigned char> kd((size_t)nk * 32);
+        for (int i = 0; i < nk; i++) std::memcpy(&kd[(size_t)i * 32], F.mDescriptors.ptr(i), 32);
+        std::vector<int32_t> taken((size_t)nk, -1), match((size_t)nq);
+        int nmatches = 0;
+        if (ci.empty()) ci.push_back(0);
+        check(uvip_search_lists(handle_, 2, TH_LOW, mfNNratio, qd.data(), nq, cs.data(), ci.data(), kd.data(), nk, taken.data(), match.data(), &nmatches),
+              "uvip_search_lists");
+        if (mbCheckOrientation) {                                               // :227-241, :255-281
+            std::vector<float> a1((size_t)nq), a2((size_t)nk);
+            for (int q = 0; q < nq; q++) a1[q] = pKF->GetKeyPointUn(qidx[q]).angle;
+            for (int i = 0; i < nk; i++) a2[i] = F.mvKeys[i].angle;
+            check(uvip_rot_hist_filter(handle_, match.data(), nq, a1.data(), a2.data(), &nmatches), "uvip_rot_hist_filter");
+        }
+        for (int q = 0; q < nq; q++) if (match[q] >= 0) vpMapPointMatches[match[q]] = vpMapPointsKF[qidx[q]];
         return nmatches;
     }
 
