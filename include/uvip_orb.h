@@ -116,6 +116,14 @@ long long uvip_extractor_launch_count(const uvip_extractor* ex);
 int   uvip_extractor_profile(uvip_extractor* ex, int enable);
 int   uvip_extractor_stage_ms(uvip_extractor* ex, float* ms /* [UVIP_NUM_STAGES] */, int* ngroups);
 
+/* ---- next row N3: the step immediately before the path on every frame when `Enhance` is set ------------ */
+/* cv::createCLAHE(clip_limit, Size(tiles_x, tiles_y))->apply(src, dst) as called at src/Tracking.cc:425-431 (clip 4, 12 x 12
+ * tiles), 8-bit, bit-exact against OpenCV.  dst may alias src.  Host buffers / device-resident batch. */
+int   uvip_clahe(uvip_extractor* ex, const uint8_t* src, int w, int h, int stride, double clip_limit, int tiles_x, int tiles_y,
+                 uint8_t* dst, int dst_stride);
+int   uvip_clahe_batch_device(uvip_extractor* ex, const uint8_t* d_src, int nframes, int w, int h, int stride, size_t frame_pitch,
+                              double clip_limit, int tiles_x, int tiles_y, uint8_t* d_dst, int dst_stride, size_t dst_pitch, void* stream);
+
 /* ---- matcher: replaces the descriptor path of USLAM::ORBmatcher (include/ORBmatcher.h:41-94) ------------- */
 typedef struct uvip_matcher uvip_matcher;
 

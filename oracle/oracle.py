@@ -284,3 +284,11 @@ def search_lists(mode, th_dist, ratio, qdesc, cand_start, cand_idx, kdesc, taken
     match = np.zeros(nq, np.int32)
     n = lib().uo_search_lists(int(mode), int(th_dist), C.c_float(ratio), _p(qdesc), nq, _p(cs), _p(ci), _p(kdesc), nk, _p(tk), _p(match))
     return n, match, tk
+
+
+def clahe(img, clip_limit=4.0, tiles=(12, 12)):
+    img = np.ascontiguousarray(img, np.uint8)
+    h, w = img.shape
+    out = np.zeros_like(img)
+    lib().uo_clahe(_p(img), w, h, w, C.c_double(clip_limit), int(tiles[0]), int(tiles[1]), _p(out), w)
+    return out

@@ -907,3 +907,63 @@ int uo_search_lists(int mode, int th_dist, float ratio, const uint8_t* qdesc, in
     }
     return nmatches;
 }
+
+/* ================================================================ CLAHE (next row N3)
+ * cv::createCLAHE(clip, Size(tx,ty))->apply(im, im) as called at Tracking.cc:425-431 (clip 4, 12x12 tiles), restated from
+ * OpenCV imgproc/clahe.cpp (8-bit path): pad to a tile multiple with REFLECT_101, per-tile clipped + redistributed
+ * histogram -> LUT = saturate(cumsum * 255/tileArea), bilinear blend of the four neighbouring tile LUTs in float. */
+void uo_clahe(const uint8_t* src, int w, int h, int stride, double clip_limit, int tiles_x, int tiles_y, uint8_t* dst, int dstride)
+{
+    const int histSize = 256;
+    int ew = w, eh = h;
+    if (w % tiles_x != 0 || h % tiles_y != 0) { ew = w + (tiles_x - (w % tiles_x)); eh = h + (tiles_y - (h % tiles_y)); }
+    uint8_t* ext = (uint8_t*)malloc((size_t)ew * eh);
+    for (int y = 0; y < eh; y++) {
+        const int sy = y < h ? y : 2 * (h - 1) - y;
+        for (int x = 0; x < ew; x++) { const int sx = x < w ? x : 2 * (w - 1) - x; ext[(size_t)y * ew + x] = src[(size_t)sy * stride + sx]; }
+    }
+    const int tw = ew / tiles_x, th = eh / tiles_y;
+    const int tileSizeTotal = tw * th;
+    const float lutScale = (float)(histSize - 1) / tileSizeTotal;
+    int clipLimit = 0;
+    if (clip_limit > 0.0) { clipLimit = (int)(clip_limit * tileSizeTotal / histSize); if (clipLimit < 1) clipLimit = 1; }
+    uint8_t* lut = (uint8_t*)malloc((size_t)tiles_x * tiles_y * histSize);
+    for (int ty = 0; ty < tiles_y; ty++)
+        for (int tx = 0; tx < tiles_x; tx++) {
+            int hist[256]; memset(hist, 0, sizeof(hist));
+            for (int y = 0; y < th; y++) for (int x = 0; x < tw; x++) hist[ext[(size_t)(ty * th + y) * ew + tx * tw + x]]++;
+            if (clipLimit > 0) {
+                int clipped = 0;
+                for (int i = 0; i < histSize; i++) if (hist[i] > clipLimit) { clipped += hist[i] - clipLimit; hist[i] = clipLimit; }
+                int redistBatch = clipped / histSize, residual = clipped - redistBatch * histSize;
+                for (int i = 0; i < histSize; i++) hist[i] += redistBatch;
+                if (residual != 0) {
+                    int step = histSize / residual; if (step < 1) step = 1;
+                    for (int i = 0; i < histSize && residual > 0; i += step, residual--) hist[i]++;
+                }
+            }
+            uint8_t* tl = lut + (size_t)(ty * tiles_x + tx) * histSize;
+            int sum = 0;
+            for (int i = 0; i < histSize; i++) { sum += hist[i]; int v = cv_round_f((float)sum * lutScale); tl[i] = (uint8_t)(v < 0 ? 0 : v > 255 ? 255 : v); }
+        }
+    const float inv_tw = 1.0f / tw, inv_th = 1.0f / th;
+    for (int y = 0; y < h; y++) {
+        const float tyf = y * inv_th - 0.5f;
+        int ty1 = (int)floorf(tyf), ty2 = ty1 + 1;
+        const float ya = tyf - ty1, ya1 = 1.0f - ya;
+        if (ty1 < 0) ty1 = 0; if (ty2 > tiles_y - 1) ty2 = tiles_y - 1;
+        for (int x = 0; x < w; x++) {
+            const float txf = x * inv_tw - 0.5f;
+            int tx1 = (int)floorf(txf), tx2 = tx1 + 1;
+            const float xa = txf - tx1, xa1 = 1.0f - xa;
+            if (tx1 < 0) tx1 = 0; if (tx2 > tiles_x - 1) tx2 = tiles_x - 1;
+            const int v = src[(size_t)y * stride + x];
+            const float l11 = lut[(size_t)(ty1 * tiles_x + tx1) * histSize + v], l12 = lut[(size_t)(ty1 * tiles_x + tx2) * histSize + v];
+            const float l21 = lut[(size_t)(ty2 * tiles_x + tx1) * histSize + v], l22 = lut[(size_t)(ty2 * tiles_x + tx2) * histSize + v];
+            const float res = (l11 * xa1 + l12 * xa) * ya1 + (l21 * xa1 + l22 * xa) * ya;
+            int o = cv_round_f(res);
+            dst[(size_t)y * dstride + x] = (uint8_t)(o < 0 ? 0 : o > 255 ? 255 : o);
+        }
+    }
+    free(ext); free(lut);
+}

@@ -360,3 +360,22 @@ def test_extract_parameter_sweep(gpu, oracle, synth):
             assert np.abs(kps['angle'] - okps['angle']).max() <= ANGLE_TOL_DEG, tag
             assert 1.0 - np.unpackbits(desc ^ odesc).mean() >= DESC_BITS_MIN, tag
         ex.close()
+
+
+def test_clahe_preprocessing(gpu, oracle, synth, golden):
+    """next row N3: CLAHE (clip 4, 12x12 tiles) bit-exact against the oracle and the cv2 golden hashes, then the full
+    Enhance -> extract chain of Tracking::GrabImage (src/Tracking.cc:425-446)"""
+    ex = gpu.ORBextractor(1000, 1.2, 8, 1, 20, max_width=1280, max_height=1024)
+    for seed, W, H in ((1, 752, 480), (1000, 640, 512), (100000, 1280, 1024)):
+        img = synth.synth_frame(seed, W, H)
+        out = ex.clahe(img, 4.0, (12, 12))
+        assert sha(out) == str(golden['clahe_sha_%dx%d' % (W, H)])
+        assert np.array_equal(out, oracle.clahe(img, 4.0, (12, 12)))
+    assert np.array_equal(ex.clahe(synth.synth_frame(17, 97, 61), 2.0, (4, 3)), golden['clahe_small'])
+    for clip, tiles in ((2.0, (8, 8)), (40.0, (12, 12)), (0.0, (5, 7))):
+        img = synth.synth_frame(9, 401, 307)
+        assert np.array_equal(ex.clahe(img, clip, tiles), oracle.clahe(img, clip, tiles)), (clip, tiles)
+    img = synth.synth_frame(1, 752, 480)
+    kps, desc = ex(ex.clahe(img))
+    okps, odesc = oracle.Extractor(1000, 1.2, 8, 1, 20)(oracle.clahe(img))
+    assert np.array_equal(kps['x'], okps['x']) and np.array_equal(kps['y'], okps['y']) and np.array_equal(desc, odesc)

@@ -117,6 +117,10 @@ def main():
     # descriptor arithmetic can be pinned independently of the blur variant.
     g = cv2.getGaussianKernel(7, 2, cv2.CV_32F)
     G['orb_blurred_C'] = cv2.sepFilter2D(img, -1, g, g, borderType=cv2.BORDER_REFLECT_101)
+    # ---- CLAHE (next row N3): cv::createCLAHE(4, (12,12)) of src/Tracking.cc:425-431, plus a small explicit case
+    for (seed, W, H) in [(1, 752, 480), (1000, 640, 512), (100000, 1280, 1024)]:
+        G['clahe_sha_%dx%d' % (W, H)] = np.array(sha(cv2.createCLAHE(4.0, (12, 12)).apply(S.synth_frame(seed, W, H))))
+    G['clahe_small'] = cv2.createCLAHE(2.0, (4, 3)).apply(S.synth_frame(17, 97, 61))
     out = os.path.join(ROOT, 'tests', 'golden', 'cv2_golden.npz')
     np.savez_compressed(out, **G)
     print('wrote', out, os.path.getsize(out), 'bytes;', len(G), 'entries')

@@ -1043,6 +1043,82 @@ k_describe(const uint8_t* __restrict__ pyr, const uint8_t* __restrict__ blur, co
     }
 }
 
+// --------------------------------------------------------------------------------------------------------
+// N3: CLAHE pre-processing, cv::createCLAHE(4, Size(12,12))->apply(im, im) at src/Tracking.cc:425-431,
+// restated from OpenCV imgproc/clahe.cpp (8-bit path).  k_clahe_lut: one CTA per (tile, frame) — shared-memory histogram
+// of the tile (image padded to a tile multiple by reflect-101), clip + redistribute, cumulative LUT.  k_clahe_apply: four
+// LUT gathers per pixel and the float bilinear blend, every float op rounded separately like the x86 reference build.
+// --------------------------------------------------------------------------------------------------------
+__global__ void __launch_bounds__(256)
+k_clahe_lut(const uint8_t* __restrict__ src, int w, int h, int stride, size_t pitch, int tiles_x, int tw, int th, int clip_limit,
+            float lut_scale, uint8_t* __restrict__ lut)
+{
+    __shared__ int s_hist[256];
+    __shared__ int s_part[8];
+    __shared__ int s_clipped;
+    const int tile = blockIdx.x, f = blockIdx.y, tid = threadIdx.x;
+    const int tx = tile % tiles_x, ty = tile / tiles_x;
+    const uint8_t* img = src + (size_t)f * pitch;
+    s_hist[tid] = 0;
+    if (tid == 0) s_clipped = 0;
+    __syncthreads();
+    for (int i = tid; i < tw * th; i += 256) {
+        const int yy = i / tw, xx = i - yy * tw;
+        int x = tx * tw + xx, y = ty * th + yy;
+        if (x >= w) x = 2 * (w - 1) - x;                      // copyMakeBorder(..., BORDER_REFLECT_101) padding to a tile multiple
+        if (y >= h) y = 2 * (h - 1) - y;
+        atomicAdd(&s_hist[__ldg(img + (size_t)y * stride + x)], 1);
+    }
+    __syncthreads();
+    int v = s_hist[tid];
+    if (clip_limit > 0) {
+        if (v > clip_limit) { atomicAdd(&s_clipped, v - clip_limit); v = clip_limit; }
+        __syncthreads();
+        const int clipped = s_clipped;
+        const int batch = clipped / 256; int residual = clipped - batch * 256;
+        v += batch;
+        if (residual != 0) {
+            const int step = max(256 / residual, 1);
+            // bins 0, step, 2*step, ... get one more, at most `residual` of them
+            if (tid % step == 0 && tid / step < residual) v++;
+        }
+    }
+    // inclusive prefix sum over the 256 bins
+    int incl = v;
+    const int lane = tid & 31;
+#pragma unroll
+    for (int o = 1; o < 32; o <<= 1) { const int t = __shfl_up_sync(0xFFFFFFFFu, incl, o); if (lane >= o) incl += t; }
+    if (lane == 31) s_part[tid >> 5] = incl;
+    __syncthreads();
+    int off = 0;
+    for (int k = 0; k < (tid >> 5); k++) off += s_part[k];
+    const int sum = incl + off;
+    const int o = __float2int_rn(__fmul_rn((float)sum, lut_scale));
+    lut[((size_t)f * gridDim.x + tile) * 256 + tid] = (uint8_t)min(max(o, 0), 255);
+}
+
+__global__ void __launch_bounds__(256)
+k_clahe_apply(const uint8_t* __restrict__ src, int w, int h, int stride, size_t pitch, int tiles_x, int tiles_y, float inv_tw, float inv_th,
+              const uint8_t* __restrict__ lut, uint8_t* __restrict__ dst, int dstride, size_t dpitch)
+{
+    const int f = blockIdx.z;
+    const int x = blockIdx.x * 64 + (threadIdx.x & 63), y = blockIdx.y * 4 + (threadIdx.x >> 6);
+    if (x >= w || y >= h) return;
+    const float txf = __fsub_rn(__fmul_rn((float)x, inv_tw), 0.5f), tyf = __fsub_rn(__fmul_rn((float)y, inv_th), 0.5f);
+    int tx1 = (int)floorf(txf), ty1 = (int)floorf(tyf);
+    const float xa = __fsub_rn(txf, (float)tx1), ya = __fsub_rn(tyf, (float)ty1);
+    const float xa1 = __fsub_rn(1.0f, xa), ya1 = __fsub_rn(1.0f, ya);
+    int tx2 = min(tx1 + 1, tiles_x - 1), ty2 = min(ty1 + 1, tiles_y - 1);
+    tx1 = max(tx1, 0); ty1 = max(ty1, 0);
+    const int v = __ldg(src + (size_t)f * pitch + (size_t)y * stride + x);
+    const uint8_t* L = lut + (size_t)f * tiles_x * tiles_y * 256 + v;
+    const float l11 = (float)__ldg(L + (ty1 * tiles_x + tx1) * 256), l12 = (float)__ldg(L + (ty1 * tiles_x + tx2) * 256);
+    const float l21 = (float)__ldg(L + (ty2 * tiles_x + tx1) * 256), l22 = (float)__ldg(L + (ty2 * tiles_x + tx2) * 256);
+    const float res = __fadd_rn(__fmul_rn(__fadd_rn(__fmul_rn(l11, xa1), __fmul_rn(l12, xa)), ya1),
+                                __fmul_rn(__fadd_rn(__fmul_rn(l21, xa1), __fmul_rn(l22, xa)), ya));
+    dst[(size_t)f * dpitch + (size_t)y * dstride + x] = (uint8_t)min(max(__float2int_rn(res), 0), 255);
+}
+
 }  // namespace uvip
 
 // =====================================================================================================
@@ -1064,6 +1140,7 @@ struct uvip_extractor {
     size_t cap_frame_bytes = 0; int cap_cells = 0, cap_raw = 0, cap_kp = 0, cap_tab = 0;
     DevBuf pyr, blur, cand, labels, winners, counters, sel, nsel, tabs, status, grid, incoming, tmaps, pat_t;
     DevBuf in_frames, out_kps, out_desc, out_n;      // staging for the host-buffer entry points
+    DevBuf clahe_lut, clahe_io;                      // CLAHE LUTs and host-call staging
     DevBuf in2, kps2, desc2, n2;                     // second staging set: uvip_extract_batch double-buffers its chunks
     cudaStream_t h2d_stream = nullptr, d2h_stream = nullptr;
     cudaEvent_t ev_h2d[2] = {nullptr, nullptr}, ev_comp[2] = {nullptr, nullptr}, ev_d2h[2] = {nullptr, nullptr};
@@ -1444,7 +1521,7 @@ int uvip_extractor_destroy(uvip_extractor* ex)
     if (ex->stream) cudaStreamSynchronize(ex->stream);
     DevBuf* bufs[] = {&ex->pyr, &ex->blur, &ex->cand, &ex->labels, &ex->winners, &ex->counters, &ex->sel,
                       &ex->nsel, &ex->tabs, &ex->status, &ex->grid, &ex->incoming, &ex->tmaps, &ex->pat_t, &ex->in_frames, &ex->out_kps, &ex->out_desc, &ex->out_n,
-                      &ex->in2, &ex->kps2, &ex->desc2, &ex->n2};
+                      &ex->in2, &ex->kps2, &ex->desc2, &ex->n2, &ex->clahe_lut, &ex->clahe_io};
     for (DevBuf* b : bufs) b->release();
     for (cudaEvent_t e : ex->prof_ev) cudaEventDestroy(e);
     for (int i = 0; i < 2; i++) { if (ex->ev_h2d[i]) cudaEventDestroy(ex->ev_h2d[i]); if (ex->ev_comp[i]) cudaEventDestroy(ex->ev_comp[i]); if (ex->ev_d2h[i]) cudaEventDestroy(ex->ev_d2h[i]); }
@@ -1590,6 +1667,58 @@ int uvip_extract(uvip_extractor* ex, const uint8_t* image, int w, int h, int str
     if (!full_detect) UVIP_CUDA(cudaMemcpyAsync(grid, ex->grid.p, (size_t)grid_rows * grid_cols * 4, cudaMemcpyDeviceToHost, st));
     UVIP_CUDA(cudaStreamSynchronize(st));
     *n_inout = n;
+    return UVIP_OK;
+}
+
+// ---- CLAHE pre-processing (next row N3) ---------------------------------------------------------------
+static int enqueue_clahe(uvip_extractor* ex, const uint8_t* d_src, int nframes, int w, int h, int stride, size_t pitch, double clip, int tiles_x,
+                         int tiles_y, uint8_t* d_dst, int dstride, size_t dpitch, cudaStream_t st)
+{
+    int ew = w, eh = h;
+    if (w % tiles_x != 0 || h % tiles_y != 0) { ew = w + (tiles_x - (w % tiles_x)); eh = h + (tiles_y - (h % tiles_y)); }
+    const int tw = ew / tiles_x, th = eh / tiles_y;
+    UVIP_CHECK_ARG(tw >= 1 && th >= 1 && ew - w < w && eh - h < h);
+    const int total = tw * th;
+    const float lut_scale = (float)255 / total;
+    int clip_limit = 0;
+    if (clip > 0.0) { clip_limit = (int)(clip * total / 256); if (clip_limit < 1) clip_limit = 1; }
+    int rc;
+    if ((rc = ex->clahe_lut.reserve((size_t)nframes * tiles_x * tiles_y * 256))) return rc;
+    k_clahe_lut<<<dim3(tiles_x * tiles_y, nframes), 256, 0, st>>>(d_src, w, h, stride, pitch, tiles_x, tw, th, clip_limit, lut_scale, ex->clahe_lut.as<uint8_t>());
+    ex->launches++;
+    k_clahe_apply<<<dim3(div_up(w, 64), div_up(h, 4), nframes), 256, 0, st>>>(d_src, w, h, stride, pitch, tiles_x, tiles_y, 1.0f / tw, 1.0f / th,
+                                                                              ex->clahe_lut.as<uint8_t>(), d_dst, dstride, dpitch);
+    ex->launches++;
+    UVIP_CUDA(cudaGetLastError());
+    return UVIP_OK;
+}
+
+int uvip_clahe_batch_device(uvip_extractor* ex, const uint8_t* d_src, int nframes, int w, int h, int stride, size_t frame_pitch,
+                            double clip_limit, int tiles_x, int tiles_y, uint8_t* d_dst, int dst_stride, size_t dst_pitch, void* stream)
+{
+    UVIP_CHECK_ARG(ex && d_src && d_dst && nframes >= 1 && w > 0 && h > 0 && stride >= w && dst_stride >= w && tiles_x >= 1 && tiles_y >= 1);
+    DeviceGuard g(ex->device);
+    return enqueue_clahe(ex, d_src, nframes, w, h, stride, frame_pitch, clip_limit, tiles_x, tiles_y, d_dst, dst_stride, dst_pitch,
+                         stream ? (cudaStream_t)stream : ex->stream);
+}
+
+int uvip_clahe(uvip_extractor* ex, const uint8_t* src, int w, int h, int stride, double clip_limit, int tiles_x, int tiles_y,
+               uint8_t* dst, int dst_stride)
+{
+    UVIP_CHECK_ARG(ex && tiles_x >= 1 && tiles_y >= 1);
+    if (!src || w <= 0 || h <= 0) return UVIP_OK;
+    UVIP_CHECK_ARG(dst && stride >= w && dst_stride >= w);
+    std::lock_guard<std::mutex> lk(ex->mu);
+    DeviceGuard g(ex->device);
+    int rc;
+    const size_t bytes = (size_t)w * h;
+    if ((rc = ex->clahe_io.reserve(2 * bytes))) return rc;
+    uint8_t* d_in = ex->clahe_io.as<uint8_t>(); uint8_t* d_out = d_in + bytes;
+    cudaStream_t st = ex->stream;
+    UVIP_CUDA(cudaMemcpy2DAsync(d_in, w, src, stride, w, h, cudaMemcpyHostToDevice, st));
+    if ((rc = enqueue_clahe(ex, d_in, 1, w, h, w, bytes, clip_limit, tiles_x, tiles_y, d_out, w, bytes, st))) return rc;
+    UVIP_CUDA(cudaMemcpy2DAsync(dst, dst_stride, d_out, w, w, h, cudaMemcpyDeviceToHost, st));
+    UVIP_CUDA(cudaStreamSynchronize(st));
     return UVIP_OK;
 }
 

@@ -91,6 +91,14 @@ class ORBextractor:
         check(lib().uvip_extract_batch_device(self.h, ptr(d_frames), nframes, W, H, W, W * H, ptr(d_kps), ptr(d_n), cap,
                                               ptr(d_desc), C.c_void_p(stream) if stream else None))
 
+    def clahe(self, image, clip_limit=4.0, tiles=(12, 12)):
+        """cv::createCLAHE(clip_limit, tiles)->apply(im, im), the `Enhance` pre-processing of src/Tracking.cc:425-431"""
+        image = np.ascontiguousarray(image, np.uint8)
+        H, W = image.shape
+        out = np.zeros_like(image)
+        check(lib().uvip_clahe(self.h, ptr(image), W, H, W, float(clip_limit), int(tiles[0]), int(tiles[1]), ptr(out), W))
+        return out
+
     def status(self):
         check(lib().uvip_extractor_status(self.h))
 
