@@ -204,6 +204,22 @@ int   uvip_search_lists(uvip_matcher* m, int mode, int th_dist, float ratio, con
 /* ORBmatcher::RadiusByViewingCos (src/ORBmatcher.cc:127-133) */
 float uvip_radius_by_viewing_cos(float view_cos);
 
+/* ---- next row N2: DBoW2 vocabulary-tree descent ------------------------------------------------------ */
+/* ORBVocabulary::transform(features, BowVector&, FeatureVector&, levelsup) (src/FrameKTL.cc:439-446, src/KeyFrame.cc:203-210;
+ * Thirdparty/DBoW2/DBoW2/TemplatedVocabulary.h:1119-1195) = per descriptor a Hamming tree descent (:1218-1259) + host-side
+ * map bookkeeping.  The descent is the kernel; the caller (shim / Python mirror) loads the vocabulary text file, flattens
+ * the tree and accumulates the BowVector / FeatureVector from the per-feature results.
+ * Flat tree: children of node i = child_ids[child_start[i] .. child_start[i+1]) in file order; node 0 is the root; a node
+ * without children is a word (node_word = word id, else -1).  L = depth of the vocabulary (header of the text file). */
+typedef struct uvip_vocabulary uvip_vocabulary;
+int   uvip_vocabulary_create(int device, int nnodes, const int32_t* child_start, const int32_t* child_ids, const uint8_t* node_desc,
+                             const double* node_weight, const int32_t* node_word, int L, uvip_vocabulary** out);
+int   uvip_vocabulary_destroy(uvip_vocabulary* v);
+/* per feature: word id, weight of the word, and the node on the path at level L - levelsup (0 = root) */
+int   uvip_bow_transform(uvip_vocabulary* v, const uint8_t* desc, int n, int levelsup, int32_t* word_id, int32_t* node_id, double* weight);
+int   uvip_bow_transform_device(uvip_vocabulary* v, const uint8_t* d_desc, int n, int levelsup, int32_t* d_word_id, int32_t* d_node_id,
+                                double* d_weight, void* stream);
+
 /* ---- misc ---------------------------------------------------------------------------------------------- */
 int         uvip_abi_version(void);
 const char* uvip_last_error(void);          /* thread-local text of the last failure */

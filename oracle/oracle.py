@@ -292,3 +292,15 @@ def clahe(img, clip_limit=4.0, tiles=(12, 12)):
     out = np.zeros_like(img)
     lib().uo_clahe(_p(img), w, h, w, C.c_double(clip_limit), int(tiles[0]), int(tiles[1]), _p(out), w)
     return out
+
+
+def bow_transform(voc, desc, levelsup=4):
+    """voc: dict(child_start, child_ids, desc, weight, word, L) flat vocabulary tree"""
+    desc = np.ascontiguousarray(desc, np.uint8)
+    n = len(desc)
+    wid = np.zeros(n, np.int32); nid = np.zeros(n, np.int32); w = np.zeros(n, np.float64)
+    cs = np.ascontiguousarray(voc['child_start'], np.int32); ci = np.ascontiguousarray(voc['child_ids'], np.int32)
+    nd = np.ascontiguousarray(voc['desc'], np.uint8); nw = np.ascontiguousarray(voc['weight'], np.float64)
+    word = np.ascontiguousarray(voc['word'], np.int32)
+    lib().uo_bow_transform(_p(cs), _p(ci), _p(nd), _p(nw), _p(word), int(voc['L']), _p(desc), n, int(levelsup), _p(wid), _p(nid), _p(w))
+    return wid, nid, w

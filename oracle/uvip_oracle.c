@@ -967,3 +967,33 @@ void uo_clahe(const uint8_t* src, int w, int h, int stride, double clip_limit, i
     }
     free(ext); free(lut);
 }
+
+/* ================================================================ DBoW2 tree descent (next row N2)
+ * TemplatedVocabulary::transform(feature, word_id, weight, nid, levelsup), Thirdparty/DBoW2/DBoW2/TemplatedVocabulary.h:1218-1259,
+ * with FORB::distance (FORB.cpp:80-101) = 256-bit Hamming.  The tree is flat: children of node i are
+ * child_ids[child_start[i] .. child_start[i+1]) in file order; a node without children is a leaf (word).  Strict '<':
+ * the first child wins ties.  node_id = the node on the path at level L - levelsup (0 = root if that level is <= 0, and
+ * also if the leaf is reached earlier - the reference leaves *nid unset there). */
+void uo_bow_transform(const int32_t* child_start, const int32_t* child_ids, const uint8_t* node_desc, const double* node_weight,
+                      const int32_t* node_word, int L, const uint8_t* desc, int n, int levelsup,
+                      int32_t* word_id, int32_t* node_id, double* weight)
+{
+    const int nid_level = L - levelsup;
+    for (int f = 0; f < n; f++) {
+        const uint8_t* d = desc + (size_t)f * 32;
+        int final_id = 0, level = 0, nid = 0;
+        do {
+            ++level;
+            const int b = child_start[final_id], e = child_start[final_id + 1];
+            final_id = child_ids[b];
+            int best = uo_descriptor_distance(d, node_desc + (size_t)final_id * 32);
+            for (int c = b + 1; c < e; c++) {
+                const int id = child_ids[c];
+                const int dd = uo_descriptor_distance(d, node_desc + (size_t)id * 32);
+                if (dd < best) { best = dd; final_id = id; }
+            }
+            if (level == nid_level) nid = final_id;
+        } while (child_start[final_id + 1] > child_start[final_id]);
+        word_id[f] = node_word[final_id]; weight[f] = node_weight[final_id]; node_id[f] = nid;
+    }
+}

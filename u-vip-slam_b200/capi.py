@@ -89,6 +89,10 @@ def lib():
         L.uvip_search_window.argtypes = [vp, C.POINTER(SearchParams), vp, vp, vp, vp, vp, vp, i,
                                          vp, vp, vp, vp, i, vp, vp, vp, vp, C.POINTER(i)]
         L.uvip_search_lists.argtypes = [vp, i, i, C.c_float, vp, i, vp, vp, vp, i, vp, vp, C.POINTER(i)]
+        L.uvip_vocabulary_create.argtypes = [i, i, vp, vp, vp, vp, vp, i, C.POINTER(vp)]
+        L.uvip_vocabulary_destroy.argtypes = [vp]
+        L.uvip_bow_transform.argtypes = [vp, vp, i, i, vp, vp, vp]
+        L.uvip_bow_transform_device.argtypes = [vp, vp, i, i, vp, vp, vp, vp]
         L.uvip_popc_peak.argtypes = [i, i, C.POINTER(C.c_double)]
         _LIB = L
     return _LIB

@@ -417,6 +417,43 @@ k_search_window(SearchCtx c, int nq, int nk, int32_t* __restrict__ taken, int32_
     if (threadIdx.x == 0) { out_counts[0] = s_n; out_counts[1] = rounds; }
 }
 
+// N2: DBoW2 vocabulary-tree descent, TemplatedVocabulary::transform (Thirdparty/DBoW2/DBoW2/TemplatedVocabulary.h:1218-1259)
+// with FORB::distance = 256-bit Hamming.  One warp per descriptor: at every level lane c scores child c (k <= 32 per pass),
+// the warp takes the minimum of (distance << 8 | child position) — strict '<', first child wins ties — and descends.
+__global__ void __launch_bounds__(256)
+k_bow_transform(const int32_t* __restrict__ child_start, const int32_t* __restrict__ child_ids, const uint8_t* __restrict__ node_desc,
+                const double* __restrict__ node_weight, const int32_t* __restrict__ node_word, int L,
+                const uint8_t* __restrict__ desc, int n, int levelsup,
+                int32_t* __restrict__ word_id, int32_t* __restrict__ node_id, double* __restrict__ weight)
+{
+    const int f = blockIdx.x * 8 + (threadIdx.x >> 5), lane = threadIdx.x & 31;
+    if (f >= n) return;
+    const uint4 u = __ldg(reinterpret_cast<const uint4*>(desc + (size_t)f * 32)), v = __ldg(reinterpret_cast<const uint4*>(desc + (size_t)f * 32) + 1);
+    const int nid_level = L - levelsup;
+    int final_id = 0, level = 0, nid = 0;
+    for (;;) {
+        const int b = __ldg(child_start + final_id), e = __ldg(child_start + final_id + 1);
+        if (e <= b && level > 0) break;                                   // leaf reached
+        if (e <= b) break;                                                 // malformed: root without children
+        ++level;
+        unsigned best = 0xFFFFFFFFu;
+        for (int c0 = b; c0 < e; c0 += 32) {
+            const int c = c0 + lane;
+            unsigned key = 0xFFFFFFFFu;
+            if (c < e) {
+                const int id = __ldg(child_ids + c);
+                key = ((unsigned)hamming256(u, v, node_desc + (size_t)id * 32) << 20) | (unsigned)(c - b);
+            }
+#pragma unroll
+            for (int o = 16; o > 0; o >>= 1) key = min(key, __shfl_xor_sync(0xFFFFFFFFu, key, o));
+            best = min(best, key);
+        }
+        final_id = __ldg(child_ids + b + (int)(best & 0xFFFFFu));
+        if (level == nid_level) nid = final_id;
+    }
+    if (lane == 0) { word_id[f] = __ldg(node_word + final_id); weight[f] = __ldg(node_weight + final_id); node_id[f] = nid; }
+}
+
 // popc-pipe microbenchmark (roofline denominator for K9): 8 independent popc chains per thread
 __global__ void k_popc_peak(int iters, uint32_t seed, uint32_t* __restrict__ out)
 {
@@ -861,6 +898,95 @@ int uvip_popc_peak(int device, int iters, double* popc_per_s)
     }
     cudaEventDestroy(e0); cudaEventDestroy(e1); cudaFree(d_out);
     *popc_per_s = (double)blocks * threads * 8.0 * iters / (best * 1e-3);
+    return UVIP_OK;
+}
+
+}  // extern "C"
+
+// ---- DBoW2 vocabulary (next row N2) ----------------------------------------------------------------------
+struct uvip_vocabulary {
+    int device = 0, nnodes = 0, L = 0;
+    cudaStream_t stream = nullptr;
+    DevBuf child_start, child_ids, desc, weight, word, io;
+    long long launches = 0;
+    std::mutex mu;
+};
+
+extern "C" {
+
+int uvip_vocabulary_create(int device, int nnodes, const int32_t* child_start, const int32_t* child_ids, const uint8_t* node_desc,
+                           const double* node_weight, const int32_t* node_word, int L, uvip_vocabulary** out)
+{
+    UVIP_CHECK_ARG(out && nnodes >= 2 && child_start && child_ids && node_desc && node_weight && node_word && L >= 1);
+    *out = nullptr;
+    int ndev = 0;
+    if (cudaGetDeviceCount(&ndev) != cudaSuccess || ndev == 0) { set_last_error("no CUDA device available; libuvip_orb has no CPU fallback"); return UVIP_ERR_NO_DEVICE; }
+    UVIP_CHECK_ARG(device >= 0 && device < ndev);
+    UVIP_CHECK_ARG(child_start[0] == 0 && child_start[1] > 0);
+    const int nchild = child_start[nnodes];
+    for (int i = 0; i < nnodes; i++) UVIP_CHECK_ARG(child_start[i + 1] >= child_start[i]);
+    for (int i = 0; i < nchild; i++) UVIP_CHECK_ARG(child_ids[i] > 0 && child_ids[i] < nnodes);
+    DeviceGuard g(device);
+    uvip_vocabulary* v = new uvip_vocabulary();
+    v->device = device; v->nnodes = nnodes; v->L = L;
+    int rc = 0;
+    rc |= v->child_start.reserve((size_t)(nnodes + 1) * 4); rc |= v->child_ids.reserve((size_t)(nchild > 0 ? nchild : 1) * 4);
+    rc |= v->desc.reserve((size_t)nnodes * 32); rc |= v->weight.reserve((size_t)nnodes * 8); rc |= v->word.reserve((size_t)nnodes * 4);
+    if (rc || cudaStreamCreateWithFlags(&v->stream, cudaStreamNonBlocking) != cudaSuccess) { uvip_vocabulary_destroy(v); return UVIP_ERR_CUDA; }
+    cudaMemcpy(v->child_start.p, child_start, (size_t)(nnodes + 1) * 4, cudaMemcpyHostToDevice);
+    cudaMemcpy(v->child_ids.p, child_ids, (size_t)nchild * 4, cudaMemcpyHostToDevice);
+    cudaMemcpy(v->desc.p, node_desc, (size_t)nnodes * 32, cudaMemcpyHostToDevice);
+    cudaMemcpy(v->weight.p, node_weight, (size_t)nnodes * 8, cudaMemcpyHostToDevice);
+    cudaMemcpy(v->word.p, node_word, (size_t)nnodes * 4, cudaMemcpyHostToDevice);
+    UVIP_CUDA(cudaGetLastError());
+    *out = v;
+    return UVIP_OK;
+}
+
+int uvip_vocabulary_destroy(uvip_vocabulary* v)
+{
+    if (!v) return UVIP_OK;
+    DeviceGuard g(v->device);
+    if (v->stream) { cudaStreamSynchronize(v->stream); cudaStreamDestroy(v->stream); }
+    DevBuf* bufs[] = {&v->child_start, &v->child_ids, &v->desc, &v->weight, &v->word, &v->io};
+    for (DevBuf* b : bufs) b->release();
+    delete v;
+    return UVIP_OK;
+}
+
+int uvip_bow_transform_device(uvip_vocabulary* v, const uint8_t* d_desc, int n, int levelsup, int32_t* d_word_id, int32_t* d_node_id,
+                              double* d_weight, void* stream)
+{
+    UVIP_CHECK_ARG(v && n >= 0 && levelsup >= 0);
+    if (n == 0) return UVIP_OK;
+    UVIP_CHECK_ARG(d_desc && d_word_id && d_node_id && d_weight && ((uintptr_t)d_desc & 15) == 0);
+    DeviceGuard g(v->device);
+    cudaStream_t st = stream ? (cudaStream_t)stream : v->stream;
+    k_bow_transform<<<div_up(n, 8), 256, 0, st>>>(v->child_start.as<int32_t>(), v->child_ids.as<int32_t>(), v->desc.as<uint8_t>(),
+                                                   v->weight.as<double>(), v->word.as<int32_t>(), v->L, d_desc, n, levelsup, d_word_id, d_node_id, d_weight);
+    v->launches++;
+    UVIP_CUDA(cudaGetLastError());
+    return UVIP_OK;
+}
+
+int uvip_bow_transform(uvip_vocabulary* v, const uint8_t* desc, int n, int levelsup, int32_t* word_id, int32_t* node_id, double* weight)
+{
+    UVIP_CHECK_ARG(v && n >= 0);
+    if (n == 0) return UVIP_OK;
+    UVIP_CHECK_ARG(desc && word_id && node_id && weight);
+    std::lock_guard<std::mutex> lk(v->mu);
+    DeviceGuard g(v->device);
+    int rc;
+    const size_t o_w = align_up((size_t)n * 32, 256), o_n = o_w + align_up((size_t)n * 8, 256), o_i = o_n + align_up((size_t)n * 4, 256);
+    if ((rc = v->io.reserve(o_i + (size_t)n * 4))) return rc;
+    uint8_t* base = v->io.as<uint8_t>();
+    UVIP_CUDA(cudaMemcpyAsync(base, desc, (size_t)n * 32, cudaMemcpyHostToDevice, v->stream));
+    rc = uvip_bow_transform_device(v, base, n, levelsup, (int32_t*)(base + o_i), (int32_t*)(base + o_n), (double*)(base + o_w), v->stream);
+    if (rc) return rc;
+    UVIP_CUDA(cudaMemcpyAsync(word_id, base + o_i, (size_t)n * 4, cudaMemcpyDeviceToHost, v->stream));
+    UVIP_CUDA(cudaMemcpyAsync(node_id, base + o_n, (size_t)n * 4, cudaMemcpyDeviceToHost, v->stream));
+    UVIP_CUDA(cudaMemcpyAsync(weight, base + o_w, (size_t)n * 8, cudaMemcpyDeviceToHost, v->stream));
+    UVIP_CUDA(cudaStreamSynchronize(v->stream));
     return UVIP_OK;
 }
 

@@ -265,3 +265,117 @@ class ORBmatcher:
         r = (r * sf[lvl]).astype(np.float32)
         return self.search_window(0, self.TH_HIGH, map_points['u'], map_points['v'], r, lvl - 1, lvl, map_points['desc'],
                                   frame['kx'], frame['ky'], frame['octave'], frame['kdesc'], frame['grid'], taken)
+
+
+class ORBVocabulary:
+    """DBoW2 ORB vocabulary (include/ORBVocabulary.h = TemplatedVocabulary<FORB::TDescriptor, FORB>), next row N2.
+
+    The tree is kept flat (see uvip_vocabulary_create); `transform` sends the descriptors through the CUDA tree descent and
+    builds BowVector / FeatureVector on the host exactly like TemplatedVocabulary::transform (:1119-1195): feature order,
+    double accumulation, weighting (TF_IDF/TF/IDF/BINARY) and scoring-dependent normalisation."""
+    TF_IDF, TF, IDF, BINARY = 0, 1, 2, 3
+    L1_NORM, L2_NORM, CHI_SQUARE, KL, BHATTACHARYYA, DOT_PRODUCT = range(6)
+
+    def __init__(self, tree=None, device=0):
+        self.h = C.c_void_p()
+        self.device = device
+        if tree is not None:
+            self._set(tree)
+
+    def _set(self, tree):
+        self.tree = tree
+        self.k, self.L = int(tree['k']), int(tree['L'])
+        self.scoring, self.weighting = int(tree.get('scoring', 0)), int(tree.get('weighting', 0))
+        cs = np.ascontiguousarray(tree['child_start'], np.int32); ci = np.ascontiguousarray(tree['child_ids'], np.int32)
+        nd = np.ascontiguousarray(tree['desc'], np.uint8); nw = np.ascontiguousarray(tree['weight'], np.float64)
+        word = np.ascontiguousarray(tree['word'], np.int32)
+        self.close()
+        check(lib().uvip_vocabulary_create(self.device, len(word), ptr(cs), ptr(ci), ptr(nd), ptr(nw), ptr(word), self.L, C.byref(self.h)))
+
+    def close(self):
+        if getattr(self, 'h', None) is not None and self.h:
+            lib().uvip_vocabulary_destroy(self.h)
+            self.h = C.c_void_p()
+
+    def __del__(self):
+        try:
+            self.close()
+        except Exception:
+            pass
+
+    @staticmethod
+    def parse_text(path):
+        """loadFromTextFile (TemplatedVocabulary.h:1338-1420): 'k L scoring weighting' then one line per node:
+        'parent isLeaf b0 .. b31 weight' (node ids are 1.. in file order, 0 is the root)"""
+        with open(path) as f:
+            k, L, n1, n2 = [int(v) for v in f.readline().split()[:4]]
+            if k < 0 or k > 20 or L < 1 or L > 10 or n1 < 0 or n1 > 5 or n2 < 0 or n2 > 3:
+                raise ValueError('Vocabulary loading failure: This is not a correct text file!')
+            parent, leaf, desc, weight = [0], [0], [np.zeros(32, np.uint8)], [0.0]
+            for line in f:
+                t = line.split()
+                if len(t) < 35:
+                    continue
+                parent.append(int(t[0])); leaf.append(int(t[1]))
+                desc.append(np.array([int(v) for v in t[2:34]], np.uint8)); weight.append(float(t[34]))
+        n = len(parent)
+        children = [[] for _ in range(n)]
+        for i in range(1, n):
+            children[parent[i]].append(i)
+        cs = np.zeros(n + 1, np.int32); cs[1:] = np.cumsum([len(c) for c in children])
+        ci = np.array([c for ch in children for c in ch], np.int32)
+        word = np.full(n, -1, np.int32); w = 0
+        for i in range(1, n):
+            if leaf[i] > 0:
+                word[i] = w; w += 1
+        return dict(k=k, L=L, scoring=n1, weighting=n2, child_start=cs, child_ids=ci, desc=np.stack(desc), weight=np.array(weight, np.float64),
+                    word=word)
+
+    def loadFromTextFile(self, path):
+        self._set(self.parse_text(path))
+        return True
+
+    def descend(self, desc, levelsup=4):
+        desc = np.ascontiguousarray(desc, np.uint8).reshape(-1, 32)
+        n = len(desc)
+        wid = np.zeros(n, np.int32); nid = np.zeros(n, np.int32); w = np.zeros(n, np.float64)
+        check(lib().uvip_bow_transform(self.h, ptr(desc), n, int(levelsup), ptr(wid), ptr(nid), ptr(w)))
+        return wid, nid, w
+
+    @staticmethod
+    def accumulate(wid, nid, w, weighting, scoring):
+        """BowVector / FeatureVector bookkeeping of TemplatedVocabulary::transform(features, v, fv, levelsup)"""
+        bow, fv = {}, {}
+        tf = weighting in (ORBVocabulary.TF_IDF, ORBVocabulary.TF)
+        for i in range(len(wid)):
+            if w[i] > 0:                                   # not stopped
+                k = int(wid[i])
+                if tf:
+                    bow[k] = bow.get(k, 0.0) + float(w[i])
+                elif k not in bow:
+                    bow[k] = float(w[i])
+                fv.setdefault(int(nid[i]), []).append(i)
+        must = scoring != ORBVocabulary.DOT_PRODUCT
+        if tf and bow and not must:
+            nd = float(len(bow))
+            for k in bow:
+                bow[k] /= nd
+        if must:
+            keys = sorted(bow)
+            if scoring == ORBVocabulary.L2_NORM:
+                norm = 0.0
+                for k in keys:
+                    norm += bow[k] * bow[k]
+                norm = float(np.sqrt(norm))
+            else:
+                norm = 0.0
+                for k in keys:
+                    norm += abs(bow[k])
+            if norm > 0.0:
+                for k in keys:
+                    bow[k] /= norm
+        return bow, fv
+
+    def transform(self, desc, levelsup=4):
+        wid, nid, w = self.descend(desc, levelsup)
+        return self.accumulate(wid, nid, w, self.weighting, self.scoring)

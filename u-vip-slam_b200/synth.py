@@ -128,3 +128,39 @@ def projection_case(seed_f=3, seed_p=4, nk=2000, nq=10000, W=752, H=480):
     return dict(kx=kx.astype(np.float32), ky=ky.astype(np.float32), octave=octave, kangle=kangle, kdesc=kdesc,
                 u=u, v=v, level=lvl, qangle=qangle, qdesc=qdesc, view_cos=view_cos,
                 bounds=(0.0, float(W), 0.0, float(H)))
+
+
+def synthetic_vocabulary(k=10, L=3, seed=77, ragged=False):
+    """a DBoW2-shaped vocabulary tree with random 256-bit node descriptors (children = parent with ~40 bit flips, so that
+    descents are meaningful) and idf-like weights; ragged=True drops some children and ends some branches early.
+    Returns the flat tree (see frontend.ORBVocabulary) and the lines of the equivalent DBoW2 text file."""
+    rng = np.random.default_rng(seed)
+    parent, level, desc = [0], [0], [rng.integers(0, 256, 32, dtype=np.uint8)]
+    frontier = [0]
+    for lv in range(1, L + 1):
+        nxt = []
+        for p in frontier:
+            nk = k if not ragged else int(rng.integers(max(1, k // 2), k + 1))
+            if ragged and lv > 1 and rng.random() < 0.15:
+                continue                                   # this branch ends early: p stays a leaf
+            for _ in range(nk):
+                d = desc[p].copy()
+                for b in rng.integers(0, 256, 40):
+                    d[b >> 3] ^= np.uint8(1 << (b & 7))
+                parent.append(p); level.append(lv); desc.append(d); nxt.append(len(parent) - 1)
+        frontier = nxt
+    n = len(parent)
+    children = [[] for _ in range(n)]
+    for i in range(1, n):
+        children[parent[i]].append(i)
+    cs = np.zeros(n + 1, np.int32); cs[1:] = np.cumsum([len(c) for c in children])
+    ci = np.array([c for ch in children for c in ch], np.int32)
+    leaf = np.array([len(c) == 0 for c in children]); leaf[0] = False
+    word = np.full(n, -1, np.int32); word[leaf] = np.arange(int(leaf.sum()))
+    weight = np.where(leaf, np.round(rng.uniform(0.0, 9.0, n), 5), 0.0)
+    weight[leaf & (rng.random(n) < 0.03)] = 0.0               # a few stopped words
+    lines = ['%d %d 0 0' % (k, L)]
+    for i in range(1, n):
+        lines.append('%d %d %s %s' % (parent[i], int(leaf[i]), ' '.join(str(int(v)) for v in desc[i]), repr(float(weight[i]))))
+    tree = dict(k=k, L=L, scoring=0, weighting=0, child_start=cs, child_ids=ci, desc=np.stack(desc), weight=weight.astype(np.float64), word=word)
+    return tree, lines
