@@ -220,6 +220,22 @@ int   uvip_bow_transform(uvip_vocabulary* v, const uint8_t* desc, int n, int lev
 int   uvip_bow_transform_device(uvip_vocabulary* v, const uint8_t* d_desc, int n, int levelsup, int32_t* d_word_id, int32_t* d_node_id,
                                 double* d_weight, void* stream);
 
+/* ---- next row N1: KLT front end ------------------------------------------------------------------------ */
+/* cv::buildOpticalFlowPyramid(im, pyr, Size(win,win), max_level) with derivatives (src/FrameKTL.cc:76) and
+ * cv::calcOpticalFlowPyrLK(pyr0, pyr1, pts0, pts1, status, err, Size(win,win), max_level, criteria, flags)
+ * (src/Tracking.cc:1044-1047).  A handle owns `nslots` device pyramids (a frame's pyramid is built once and serves as
+ * "next" for one call and "prev" for the following one).  pyrDown / Scharr / window interpolation are bit-exact against
+ * OpenCV; tracked positions agree within ~1e-3 px (float reduction order), status flags are identical.
+ * flags: 4 = OPTFLOW_USE_INITIAL_FLOW, 8 = OPTFLOW_LK_GET_MIN_EIGENVALS (the reference passes both). */
+typedef struct uvip_klt uvip_klt;
+int   uvip_klt_create(int device, int max_width, int max_height, int win, int max_level, int nslots, uvip_klt** out);
+int   uvip_klt_destroy(uvip_klt* k);
+int   uvip_klt_build_pyramid(uvip_klt* k, int slot, const uint8_t* image, int w, int h, int stride, int* nlevels);
+int   uvip_klt_get_level(uvip_klt* k, int slot, int level, uint8_t* img, int16_t* der_xy, int* w, int* h);   /* debug tap */
+int   uvip_klt_track(uvip_klt* k, int slot_prev, int slot_next, const float* prev_pts, float* next_pts_inout, int n, int max_level,
+                     int max_iter, double epsilon, int flags, double min_eig_threshold, uint8_t* status, float* err);
+long long uvip_klt_launch_count(const uvip_klt* k);
+
 /* ---- misc ---------------------------------------------------------------------------------------------- */
 int         uvip_abi_version(void);
 const char* uvip_last_error(void);          /* thread-local text of the last failure */

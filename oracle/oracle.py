@@ -304,3 +304,57 @@ def bow_transform(voc, desc, levelsup=4):
     word = np.ascontiguousarray(voc['word'], np.int32)
     lib().uo_bow_transform(_p(cs), _p(ci), _p(nd), _p(nw), _p(word), int(voc['L']), _p(desc), n, int(levelsup), _p(wid), _p(nid), _p(w))
     return wid, nid, w
+
+
+class LKPyramid:
+    """cv::buildOpticalFlowPyramid(img, pyr, Size(win,win), max_level) with derivatives (FrameKTL.cc:76)"""
+
+    def __init__(self, img, win=21, max_level=5):
+        img = np.ascontiguousarray(img, np.uint8)
+        h, w = img.shape
+        L = lib()
+        L.uo_lk_pyramid_build.restype = C.c_void_p
+        self.p = C.c_void_p(L.uo_lk_pyramid_build(_p(img), w, h, w, int(win), int(max_level)))
+        self.win = win
+
+    def __del__(self):
+        try:
+            lib().uo_lk_pyramid_free(self.p)
+        except Exception:
+            pass
+
+    def levels(self):
+        return lib().uo_lk_pyramid_levels(self.p)
+
+    def level(self, l):
+        w = C.c_int(); h = C.c_int()
+        lib().uo_lk_pyramid_get(self.p, l, C.byref(w), C.byref(h), None, None)
+        img = np.zeros((h.value, w.value), np.uint8); der = np.zeros((h.value, w.value, 2), np.int16)
+        lib().uo_lk_pyramid_get(self.p, l, C.byref(w), C.byref(h), _p(img), _p(der))
+        return img, der
+
+
+def lk_track(pyr0, pyr1, prev_pts, next_pts, win=21, max_level=5, max_iter=30, eps=0.01, flags=12, min_eig_thr=1e-4):
+    prev_pts = np.ascontiguousarray(prev_pts, np.float32).reshape(-1, 2)
+    nxt = np.ascontiguousarray(next_pts, np.float32).reshape(-1, 2).copy()
+    n = len(prev_pts)
+    status = np.zeros(n, np.uint8); err = np.zeros(n, np.float32)
+    lib().uo_lk_track(pyr0.p, pyr1.p, _p(prev_pts), _p(nxt), n, int(win), int(max_level), int(max_iter), C.c_double(eps), int(flags),
+                      C.c_double(min_eig_thr), _p(status), _p(err))
+    return nxt, status, err
+
+
+def pyr_down(img):
+    img = np.ascontiguousarray(img, np.uint8)
+    h, w = img.shape
+    out = np.zeros(((h + 1) // 2, (w + 1) // 2), np.uint8)
+    lib().uo_pyr_down(_p(img), w, h, w, _p(out), out.shape[1])
+    return out
+
+
+def scharr(img):
+    img = np.ascontiguousarray(img, np.uint8)
+    h, w = img.shape
+    out = np.zeros((h, w, 2), np.int16)
+    lib().uo_scharr(_p(img), w, h, w, _p(out))
+    return out

@@ -997,3 +997,158 @@ void uo_bow_transform(const int32_t* child_start, const int32_t* child_ids, cons
         word_id[f] = node_word[final_id]; weight[f] = node_weight[final_id]; node_id[f] = nid;
     }
 }
+
+/* ================================================================ KLT front end (next row N1)
+ * cv::buildOpticalFlowPyramid (FrameKTL.cc:76) + cv::calcOpticalFlowPyrLK (Tracking.cc:1044-1047: win 21x21, 5 levels, 30 it,
+ * eps 0.01, USE_INITIAL_FLOW | LK_GET_MIN_EIGENVALS), restated from OpenCV video/lkpyramid.cpp + imgproc/pyramids.cpp.
+ * Integer stages (pyrDown, Scharr derivatives, fixed-point window interpolation) are exact; the float accumulations use the
+ * scalar (row-major) order, which differs from OpenCV's SIMD lane order in the last bits -> positions agree to ~1e-3 px. */
+void uo_pyr_down(const uint8_t* src, int sw, int sh, int sstride, uint8_t* dst, int dstride)
+{
+    const int dw = (sw + 1) / 2, dh = (sh + 1) / 2;
+    int* rows = (int*)malloc(sizeof(int) * 5 * dw);
+    for (int y = 0; y < dh; y++) {
+        for (int k = 0; k < 5; k++) {
+            const int sy = reflect101(2 * y - 2 + k, sh);
+            const uint8_t* S = src + (size_t)sy * sstride;
+            int* R = rows + k * dw;
+            for (int x = 0; x < dw; x++) {
+                const int x0 = reflect101(2 * x - 2, sw), x1 = reflect101(2 * x - 1, sw), x2 = reflect101(2 * x, sw), x3 = reflect101(2 * x + 1, sw), x4 = reflect101(2 * x + 2, sw);
+                R[x] = S[x2] * 6 + (S[x1] + S[x3]) * 4 + S[x0] + S[x4];
+            }
+        }
+        for (int x = 0; x < dw; x++) {
+            const int v = rows[2 * dw + x] * 6 + (rows[dw + x] + rows[3 * dw + x]) * 4 + rows[x] + rows[4 * dw + x];
+            dst[(size_t)y * dstride + x] = (uint8_t)((v + 128) >> 8);
+        }
+    }
+    free(rows);
+}
+
+void uo_scharr(const uint8_t* src, int w, int h, int stride, int16_t* dxy /* w*h*2: Ix, Iy interleaved */)
+{
+    int* t0 = (int*)malloc(sizeof(int) * (w + 2)); int* t1 = (int*)malloc(sizeof(int) * (w + 2));
+    for (int y = 0; y < h; y++) {
+        const uint8_t* r0 = src + (size_t)(y > 0 ? y - 1 : (h > 1 ? 1 : 0)) * stride;
+        const uint8_t* r1 = src + (size_t)y * stride;
+        const uint8_t* r2 = src + (size_t)(y < h - 1 ? y + 1 : (h > 1 ? h - 2 : 0)) * stride;
+        for (int x = 0; x < w; x++) { t0[x + 1] = (r0[x] + r2[x]) * 3 + r1[x] * 10; t1[x + 1] = r2[x] - r0[x]; }
+        const int xl = w > 1 ? 1 : 0, xr = w > 1 ? w - 2 : 0;
+        t0[0] = t0[xl + 1]; t0[w + 1] = t0[xr + 1]; t1[0] = t1[xl + 1]; t1[w + 1] = t1[xr + 1];
+        for (int x = 0; x < w; x++) {
+            dxy[((size_t)y * w + x) * 2] = (int16_t)(t0[x + 2] - t0[x]);
+            dxy[((size_t)y * w + x) * 2 + 1] = (int16_t)((t1[x + 2] + t1[x]) * 3 + t1[x + 1] * 10);
+        }
+    }
+    free(t0); free(t1);
+}
+
+#define LK_MAXLEV 10
+typedef struct { int nlevels; int w[LK_MAXLEV], h[LK_MAXLEV]; uint8_t* img[LK_MAXLEV]; int16_t* der[LK_MAXLEV]; } uo_lkpyr;
+
+void* uo_lk_pyramid_build(const uint8_t* img, int w, int h, int stride, int win, int max_level)
+{
+    uo_lkpyr* P = (uo_lkpyr*)calloc(1, sizeof(*P));
+    if (max_level > LK_MAXLEV - 1) max_level = LK_MAXLEV - 1;
+    P->w[0] = w; P->h[0] = h; P->img[0] = (uint8_t*)malloc((size_t)w * h);
+    for (int y = 0; y < h; y++) memcpy(P->img[0] + (size_t)y * w, img + (size_t)y * stride, (size_t)w);
+    P->nlevels = 1;
+    for (int l = 1; l <= max_level; l++) {
+        const int dw = (P->w[l - 1] + 1) / 2, dh = (P->h[l - 1] + 1) / 2;
+        if (dw <= win || dh <= win) break;                       /* lkpyramid.cpp: stop when the level is not larger than the window */
+        P->w[l] = dw; P->h[l] = dh; P->img[l] = (uint8_t*)malloc((size_t)dw * dh);
+        uo_pyr_down(P->img[l - 1], P->w[l - 1], P->h[l - 1], P->w[l - 1], P->img[l], dw);
+        P->nlevels = l + 1;
+    }
+    for (int l = 0; l < P->nlevels; l++) { P->der[l] = (int16_t*)malloc(sizeof(int16_t) * 2 * (size_t)P->w[l] * P->h[l]); uo_scharr(P->img[l], P->w[l], P->h[l], P->w[l], P->der[l]); }
+    return P;
+}
+void uo_lk_pyramid_free(void* P_) { uo_lkpyr* P = (uo_lkpyr*)P_; if (!P) return; for (int l = 0; l < P->nlevels; l++) { free(P->img[l]); free(P->der[l]); } free(P); }
+int  uo_lk_pyramid_levels(const void* P) { return ((const uo_lkpyr*)P)->nlevels; }
+void uo_lk_pyramid_get(const void* P_, int l, int* w, int* h, uint8_t* img, int16_t* der)
+{
+    const uo_lkpyr* P = (const uo_lkpyr*)P_;
+    *w = P->w[l]; *h = P->h[l];
+    if (img) memcpy(img, P->img[l], (size_t)P->w[l] * P->h[l]);
+    if (der) memcpy(der, P->der[l], sizeof(int16_t) * 2 * (size_t)P->w[l] * P->h[l]);
+}
+
+static inline int lk_img(const uo_lkpyr* P, int l, int x, int y) { return P->img[l][(size_t)reflect101(y, P->h[l]) * P->w[l] + reflect101(x, P->w[l])]; }
+static inline int lk_der(const uo_lkpyr* P, int l, int x, int y, int c)
+{ return (x < 0 || y < 0 || x >= P->w[l] || y >= P->h[l]) ? 0 : P->der[l][((size_t)y * P->w[l] + x) * 2 + c]; }
+#define LK_DESCALE(x, n) (((x) + (1 << ((n) - 1))) >> (n))
+
+/* calcOpticalFlowPyrLK over two prebuilt pyramids.  next_pts is in/out (initial flow).  flags: 4 = USE_INITIAL_FLOW, 8 = GET_MIN_EIGENVALS */
+void uo_lk_track(const void* P0_, const void* P1_, const float* prev_pts, float* next_pts, int n, int win, int max_level,
+                 int max_iter, double eps, int flags, double min_eig_thr, uint8_t* status, float* err)
+{
+    const uo_lkpyr* P0 = (const uo_lkpyr*)P0_; const uo_lkpyr* P1 = (const uo_lkpyr*)P1_;
+    if (max_iter < 0) max_iter = 0; if (max_iter > 100) max_iter = 100;
+    if (eps < 0) eps = 0; if (eps > 10) eps = 10;
+    eps *= eps;
+    int levels = P0->nlevels < P1->nlevels ? P0->nlevels : P1->nlevels;
+    if (max_level > levels - 1) max_level = levels - 1;
+    const int W_BITS = 14;
+    const float FLT_SCALE = 1.f / (1 << 20);
+    const float half = (win - 1) * 0.5f;
+    short* Iw = (short*)malloc(sizeof(short) * win * win); short* dIw = (short*)malloc(sizeof(short) * 2 * win * win);
+    for (int i = 0; i < n; i++) { status[i] = 1; if (err) err[i] = 0; }
+    for (int level = max_level; level >= 0; level--) {
+        const int cols = P0->w[level], rows = P0->h[level];
+        for (int i = 0; i < n; i++) {
+            float px = prev_pts[2 * i] * (float)(1. / (1 << level)), py = prev_pts[2 * i + 1] * (float)(1. / (1 << level));
+            float nx, ny;
+            if (level == max_level) {
+                if (flags & 4) { nx = next_pts[2 * i] * (float)(1. / (1 << level)); ny = next_pts[2 * i + 1] * (float)(1. / (1 << level)); }
+                else { nx = px; ny = py; }
+            } else { nx = next_pts[2 * i] * 2.f; ny = next_pts[2 * i + 1] * 2.f; }
+            next_pts[2 * i] = nx; next_pts[2 * i + 1] = ny;
+            px -= half; py -= half;
+            int ipx = (int)floorf(px), ipy = (int)floorf(py);
+            if (ipx < -win || ipx >= cols || ipy < -win || ipy >= rows) { if (level == 0) { status[i] = 0; if (err) err[i] = 0; } continue; }
+            float a = px - ipx, b = py - ipy;
+            int iw00 = cv_round_f((1.f - a) * (1.f - b) * (1 << W_BITS)), iw01 = cv_round_f(a * (1.f - b) * (1 << W_BITS));
+            int iw10 = cv_round_f((1.f - a) * b * (1 << W_BITS)), iw11 = (1 << W_BITS) - iw00 - iw01 - iw10;
+            float iA11 = 0, iA12 = 0, iA22 = 0;
+            for (int y = 0; y < win; y++)
+                for (int x = 0; x < win; x++) {
+                    const int X = ipx + x, Y = ipy + y;
+                    const int ival = LK_DESCALE(lk_img(P0, level, X, Y) * iw00 + lk_img(P0, level, X + 1, Y) * iw01 + lk_img(P0, level, X, Y + 1) * iw10 + lk_img(P0, level, X + 1, Y + 1) * iw11, W_BITS - 5);
+                    const int ixval = LK_DESCALE(lk_der(P0, level, X, Y, 0) * iw00 + lk_der(P0, level, X + 1, Y, 0) * iw01 + lk_der(P0, level, X, Y + 1, 0) * iw10 + lk_der(P0, level, X + 1, Y + 1, 0) * iw11, W_BITS);
+                    const int iyval = LK_DESCALE(lk_der(P0, level, X, Y, 1) * iw00 + lk_der(P0, level, X + 1, Y, 1) * iw01 + lk_der(P0, level, X, Y + 1, 1) * iw10 + lk_der(P0, level, X + 1, Y + 1, 1) * iw11, W_BITS);
+                    Iw[y * win + x] = (short)ival; dIw[2 * (y * win + x)] = (short)ixval; dIw[2 * (y * win + x) + 1] = (short)iyval;
+                    iA11 += (float)(ixval * ixval); iA12 += (float)(ixval * iyval); iA22 += (float)(iyval * iyval);
+                }
+            const float A11 = iA11 * FLT_SCALE, A12 = iA12 * FLT_SCALE, A22 = iA22 * FLT_SCALE;
+            float D = A11 * A22 - A12 * A12;
+            const float minEig = (A22 + A11 - sqrtf((A11 - A22) * (A11 - A22) + 4.f * A12 * A12)) / (2 * win * win);
+            if (err && (flags & 8)) err[i] = minEig;
+            if (minEig < min_eig_thr || D < FLT_EPSILON) { if (level == 0) status[i] = 0; continue; }
+            D = 1.f / D;
+            nx -= half; ny -= half;
+            float pdx = 0, pdy = 0;
+            for (int j = 0; j < max_iter; j++) {
+                const int inx = (int)floorf(nx), iny = (int)floorf(ny);
+                if (inx < -win || inx >= P1->w[level] || iny < -win || iny >= P1->h[level]) { if (level == 0) status[i] = 0; break; }
+                a = nx - inx; b = ny - iny;
+                iw00 = cv_round_f((1.f - a) * (1.f - b) * (1 << W_BITS)); iw01 = cv_round_f(a * (1.f - b) * (1 << W_BITS));
+                iw10 = cv_round_f((1.f - a) * b * (1 << W_BITS)); iw11 = (1 << W_BITS) - iw00 - iw01 - iw10;
+                float ib1 = 0, ib2 = 0;
+                for (int y = 0; y < win; y++)
+                    for (int x = 0; x < win; x++) {
+                        const int X = inx + x, Y = iny + y;
+                        const int diff = LK_DESCALE(lk_img(P1, level, X, Y) * iw00 + lk_img(P1, level, X + 1, Y) * iw01 + lk_img(P1, level, X, Y + 1) * iw10 + lk_img(P1, level, X + 1, Y + 1) * iw11, W_BITS - 5) - Iw[y * win + x];
+                        ib1 += (float)(diff * dIw[2 * (y * win + x)]); ib2 += (float)(diff * dIw[2 * (y * win + x) + 1]);
+                    }
+                const float b1 = ib1 * FLT_SCALE, b2 = ib2 * FLT_SCALE;
+                const float dx = (float)((A12 * b2 - A22 * b1) * D), dy = (float)((A12 * b1 - A11 * b2) * D);
+                nx += dx; ny += dy;
+                next_pts[2 * i] = nx + half; next_pts[2 * i + 1] = ny + half;
+                if ((double)dx * dx + (double)dy * dy <= eps) break;
+                if (j > 0 && fabsf(dx + pdx) < 0.01 && fabsf(dy + pdy) < 0.01) { next_pts[2 * i] -= dx * 0.5f; next_pts[2 * i + 1] -= dy * 0.5f; break; }
+                pdx = dx; pdy = dy;
+            }
+        }
+    }
+    free(Iw); free(dIw);
+}

@@ -32,6 +32,14 @@ def level_sizes(W, H, n=8):
     return [(int(np.rint(np.float32(W) * s)), int(np.rint(np.float32(H) * s))) for s in inv]
 
 
+def klt_points(S, n, W, H):
+    """deterministic sub-pixel points, a few of them close to / outside the image border"""
+    k = np.arange(1, n + 1, dtype=np.uint64)
+    x = (S.draw(71, k) % np.uint64((W + 20) * 100)).astype(np.float32) / np.float32(100) - np.float32(10)
+    y = (S.draw(72, k) % np.uint64((H + 20) * 100)).astype(np.float32) / np.float32(100) - np.float32(10)
+    return np.stack([x, y], 1).astype(np.float32)
+
+
 def main():
     cv2.setNumThreads(1)
     G = {'cv2_version': np.array(cv2.__version__)}
@@ -121,6 +129,17 @@ def main():
     for (seed, W, H) in [(1, 752, 480), (1000, 640, 512), (100000, 1280, 1024)]:
         G['clahe_sha_%dx%d' % (W, H)] = np.array(sha(cv2.createCLAHE(4.0, (12, 12)).apply(S.synth_frame(seed, W, H))))
     G['clahe_small'] = cv2.createCLAHE(2.0, (4, 3)).apply(S.synth_frame(17, 97, 61))
+    # ---- KLT (next row N1): cv::calcOpticalFlowPyrLK on the config-1 frame pair with the reference's parameters
+    a = S.synth_frame(1, 752, 480); b = S.synth_frame(1, 752, 480, dx=5, dy=3, noise_seed=2)
+    G['klt_pyrdown_sha'] = np.array(sha(cv2.pyrDown(a)))
+    G['klt_scharr_sha'] = np.array(sha(np.stack([cv2.Scharr(a, cv2.CV_16S, 1, 0, borderType=cv2.BORDER_REFLECT_101),
+                                                 cv2.Scharr(a, cv2.CV_16S, 0, 1, borderType=cv2.BORDER_REFLECT_101)], 2)))
+    p0 = klt_points(S, 500, 752, 480)
+    for win, lev in ((21, 5), (9, 3)):
+        crit = (cv2.TERM_CRITERIA_COUNT + cv2.TERM_CRITERIA_EPS, 30, 0.01)
+        p1, st, err = cv2.calcOpticalFlowPyrLK(a, b, p0.copy(), (p0 + np.float32([2.0, 1.5])).copy(), winSize=(win, win), maxLevel=lev, criteria=crit,
+                                               flags=cv2.OPTFLOW_USE_INITIAL_FLOW + cv2.OPTFLOW_LK_GET_MIN_EIGENVALS)
+        G['klt_p1_w%d' % win] = p1.astype(np.float32); G['klt_st_w%d' % win] = st.ravel().astype(np.uint8); G['klt_err_w%d' % win] = err.ravel().astype(np.float32)
     out = os.path.join(ROOT, 'tests', 'golden', 'cv2_golden.npz')
     np.savez_compressed(out, **G)
     print('wrote', out, os.path.getsize(out), 'bytes;', len(G), 'entries')

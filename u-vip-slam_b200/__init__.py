@@ -13,4 +13,4 @@ from . import build  # noqa: F401
 from . import capi  # noqa: F401
 from . import frontend  # noqa: F401
 from . import sharding  # noqa: F401
-from .frontend import ORBextractor, ORBmatcher, ORBVocabulary  # noqa: F401
+from .frontend import ORBextractor, ORBmatcher, ORBVocabulary, KLTTracker  # noqa: F401

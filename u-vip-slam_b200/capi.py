@@ -93,6 +93,13 @@ def lib():
         L.uvip_vocabulary_destroy.argtypes = [vp]
         L.uvip_bow_transform.argtypes = [vp, vp, i, i, vp, vp, vp]
         L.uvip_bow_transform_device.argtypes = [vp, vp, i, i, vp, vp, vp, vp]
+        L.uvip_klt_create.argtypes = [i, i, i, i, i, i, C.POINTER(vp)]
+        L.uvip_klt_destroy.argtypes = [vp]
+        L.uvip_klt_build_pyramid.argtypes = [vp, i, vp, i, i, i, C.POINTER(i)]
+        L.uvip_klt_get_level.argtypes = [vp, i, i, vp, vp, C.POINTER(i), C.POINTER(i)]
+        L.uvip_klt_track.argtypes = [vp, i, i, vp, vp, i, i, i, C.c_double, i, C.c_double, vp, vp]
+        L.uvip_klt_launch_count.argtypes = [vp]
+        L.uvip_klt_launch_count.restype = C.c_longlong
         L.uvip_popc_peak.argtypes = [i, i, C.POINTER(C.c_double)]
         _LIB = L
     return _LIB

@@ -1,0 +1,325 @@
+// klt.cu — next row N1: the KLT front end that associates features frame to frame in this fork:
+// cv::buildOpticalFlowPyramid (src/FrameKTL.cc:76) and cv::calcOpticalFlowPyrLK (src/Tracking.cc:1044-1047; 21x21 window,
+// 5 levels, 30 iterations, eps 0.01, USE_INITIAL_FLOW | LK_GET_MIN_EIGENVALS).  Semantics restated from OpenCV
+// video/lkpyramid.cpp and imgproc/pyramids.cpp (never its code).  Integer stages (pyrDown, Scharr, fixed-point window
+// interpolation) are bit-exact; the float reductions run in warp-shuffle order, so positions agree with OpenCV to ~1e-3 px.
+// C-ABI: include/uvip_orb.h.
+#include "common.cuh"
+#include <float.h>
+#include <math.h>
+#include <vector>
+
+namespace uvip {
+
+constexpr int KLT_MAXLEV = 10;
+
+struct KltLevel {
+    int w, h;            // interior size
+    int B;               // border (win + 2): image planes hold reflect-101 pixels there, derivative planes zeros
+    int istride;         // padded image row stride (bytes)
+    int dstride;         // padded derivative row stride (short2 elements)
+    size_t ioff, doff;   // offsets of the padded origins inside a slot (bytes / short2 elements)
+};
+struct KltPlan { int nlevels, win; KltLevel lv[KLT_MAXLEV]; };
+
+__device__ __forceinline__ int refl(int p, int n) { return p < 0 ? -p : (p >= n ? 2 * (n - 1) - p : p); }
+
+// level 0: padded copy of the input frame (reflect-101 border of win + 2 pixels)
+__global__ void __launch_bounds__(256)
+k_klt_import(const uint8_t* __restrict__ src, int stride, uint8_t* __restrict__ img, const __grid_constant__ KltPlan P)
+{
+    const KltLevel& L = P.lv[0];
+    const int pw = L.w + 2 * L.B, ph = L.h + 2 * L.B;
+    const int i = blockIdx.x * 256 + threadIdx.x;
+    if (i >= pw * ph) return;
+    const int y = i / pw, x = i - y * pw;
+    img[L.ioff + (size_t)y * L.istride + x] = __ldg(src + (size_t)refl(y - L.B, L.h) * stride + refl(x - L.B, L.w));
+}
+
+// level l from level l-1: cv::pyrDown (5x5 binomial, (sum + 128) >> 8, REFLECT_101), written for every padded position
+__global__ void __launch_bounds__(256)
+k_klt_pyrdown(uint8_t* __restrict__ img, int level, const __grid_constant__ KltPlan P)
+{
+    const KltLevel& D = P.lv[level]; const KltLevel& S = P.lv[level - 1];
+    const int pw = D.w + 2 * D.B, ph = D.h + 2 * D.B;
+    const int i = blockIdx.x * 256 + threadIdx.x;
+    if (i >= pw * ph) return;
+    const int py = i / pw, px = i - py * pw;
+    const int x = refl(px - D.B, D.w), y = refl(py - D.B, D.h);          // interior pixel this padded position mirrors
+    const uint8_t* s = img + S.ioff + (size_t)(2 * y - 2 + S.B) * S.istride + (2 * x - 2 + S.B);   // source border >= 2 is reflect-101
+    int acc = 0;
+#pragma unroll
+    for (int r = 0; r < 5; r++) {
+        const int kr = (r == 0 || r == 4) ? 1 : (r == 2 ? 6 : 4);
+        const uint8_t* q = s + (size_t)r * S.istride;
+        acc += kr * (q[2] * 6 + (q[1] + q[3]) * 4 + q[0] + q[4]);
+    }
+    img[D.ioff + (size_t)py * D.istride + px] = (uint8_t)((acc + 128) >> 8);
+}
+
+// Scharr derivatives (calcSharrDeriv): Ix = [3 10 3]^T x [-1 0 1], Iy = [-1 0 1]^T x [3 10 3], int16, interior only
+__global__ void __launch_bounds__(256)
+k_klt_scharr(const uint8_t* __restrict__ img, short2* __restrict__ der, int level, const __grid_constant__ KltPlan P)
+{
+    const KltLevel& L = P.lv[level];
+    const int i = blockIdx.x * 256 + threadIdx.x;
+    if (i >= L.w * L.h) return;
+    const int y = i / L.w, x = i - y * L.w;
+    const uint8_t* p = img + L.ioff + (size_t)(y + L.B) * L.istride + (x + L.B);
+    const int s = L.istride;
+    const int a00 = p[-s - 1], a01 = p[-s], a02 = p[-s + 1], a10 = p[-1], a12 = p[1], a20 = p[s - 1], a21 = p[s], a22 = p[s + 1];
+    const int ix = ((a02 + a22) * 3 + a12 * 10) - ((a00 + a20) * 3 + a10 * 10);
+    const int iy = ((a20 - a00) + (a22 - a02)) * 3 + (a21 - a01) * 10;
+    der[L.doff + (size_t)(y + L.B) * L.dstride + (x + L.B)] = make_short2((short)ix, (short)iy);
+}
+
+#define KLT_DESCALE(x, n) (((x) + (1 << ((n) - 1))) >> (n))
+
+// LKTrackerInvoker: one warp per point, coarse to fine inside the kernel.  The window of the first image (interpolated
+// intensities and derivatives, int16) lives in shared memory; every iteration the lanes interpolate the second image over
+// the window, accumulate the mismatch vector in float and reduce it with shuffles.
+__global__ void __launch_bounds__(256)
+k_klt_track(const uint8_t* __restrict__ img0, const short2* __restrict__ der0, const uint8_t* __restrict__ img1,
+            const float2* __restrict__ prev_pts, float2* __restrict__ next_pts, int n, int max_level, int max_iter, double eps2,
+            int flags, double min_eig_thr, uint8_t* __restrict__ status, float* __restrict__ err, const __grid_constant__ KltPlan P)
+{
+    extern __shared__ short s_win[];                   // per warp: win*win intensities, then win*win (Ix, Iy)
+    const int lane = threadIdx.x & 31, wib = threadIdx.x >> 5;
+    const int pt = blockIdx.x * 8 + wib;
+    if (pt >= n) return;
+    const int win = P.win, npx = win * win;
+    const int npx_pad = (npx + 1) & ~1;                   // keeps the short2 part 4-byte aligned
+    short* Iw = s_win + (size_t)wib * 3 * npx_pad;
+    short2* dIw = reinterpret_cast<short2*>(Iw + npx_pad);
+    const unsigned rcpw = 0xFFFFFFFFu / (unsigned)win + 1u;
+    const float half = (win - 1) * 0.5f;
+    const float FLT_SCALE = 1.f / (1 << 20);
+    const float2 pp = prev_pts[pt];
+    float2 np = next_pts[pt];
+    bool ok = true;
+    float errv = 0.f;
+    for (int level = max_level; level >= 0; level--) {
+        const KltLevel& L = P.lv[level];
+        const float sc = (float)(1. / (1 << level));
+        float px = pp.x * sc, py = pp.y * sc, nx, ny;
+        if (level == max_level) {
+            if (flags & 4) { nx = np.x * sc; ny = np.y * sc; } else { nx = px; ny = py; }
+        } else { nx = np.x * 2.f; ny = np.y * 2.f; }
+        np = make_float2(nx, ny);
+        px -= half; py -= half;
+        const int ipx = (int)floorf(px), ipy = (int)floorf(py);
+        if (ipx < -win || ipx >= L.w || ipy < -win || ipy >= L.h) { if (level == 0) { ok = false; errv = 0.f; } continue; }
+        float a = px - ipx, b = py - ipy;
+        int iw00 = __float2int_rn((1.f - a) * (1.f - b) * 16384.f), iw01 = __float2int_rn(a * (1.f - b) * 16384.f);
+        int iw10 = __float2int_rn((1.f - a) * b * 16384.f), iw11 = 16384 - iw00 - iw01 - iw10;
+        const uint8_t* I0 = img0 + L.ioff + (size_t)(ipy + L.B) * L.istride + (ipx + L.B);
+        const short2* D0 = der0 + L.doff + (size_t)(ipy + L.B) * L.dstride + (ipx + L.B);
+        float A11 = 0.f, A12 = 0.f, A22 = 0.f;
+        __syncwarp();
+        for (int i = lane; i < npx; i += 32) {
+            const int y = __umulhi((unsigned)i, rcpw), x = i - y * win;
+            const uint8_t* p = I0 + (size_t)y * L.istride + x;
+            const short2* q = D0 + (size_t)y * L.dstride + x;
+            const int ival = KLT_DESCALE(p[0] * iw00 + p[1] * iw01 + p[L.istride] * iw10 + p[L.istride + 1] * iw11, 9);
+            const short2 d00 = q[0], d01 = q[1], d10 = q[L.dstride], d11 = q[L.dstride + 1];
+            const int ixval = KLT_DESCALE(d00.x * iw00 + d01.x * iw01 + d10.x * iw10 + d11.x * iw11, 14);
+            const int iyval = KLT_DESCALE(d00.y * iw00 + d01.y * iw01 + d10.y * iw10 + d11.y * iw11, 14);
+            Iw[i] = (short)ival; dIw[i] = make_short2((short)ixval, (short)iyval);
+            A11 += (float)(ixval * ixval); A12 += (float)(ixval * iyval); A22 += (float)(iyval * iyval);
+        }
+#pragma unroll
+        for (int o = 16; o > 0; o >>= 1) {
+            A11 += __shfl_xor_sync(0xFFFFFFFFu, A11, o); A12 += __shfl_xor_sync(0xFFFFFFFFu, A12, o); A22 += __shfl_xor_sync(0xFFFFFFFFu, A22, o);
+        }
+        __syncwarp();
+        A11 *= FLT_SCALE; A12 *= FLT_SCALE; A22 *= FLT_SCALE;
+        float D = A11 * A22 - A12 * A12;
+        const float minEig = (A22 + A11 - sqrtf((A11 - A22) * (A11 - A22) + 4.f * A12 * A12)) / (float)(2 * win * win);
+        if (flags & 8) errv = minEig;
+        if (minEig < min_eig_thr || D < FLT_EPSILON) { if (level == 0) ok = false; continue; }
+        D = 1.f / D;
+        nx -= half; ny -= half;
+        float pdx = 0.f, pdy = 0.f;
+        for (int j = 0; j < max_iter; j++) {
+            const int inx = (int)floorf(nx), iny = (int)floorf(ny);
+            if (inx < -win || inx >= L.w || iny < -win || iny >= L.h) { if (level == 0) ok = false; break; }
+            a = nx - inx; b = ny - iny;
+            iw00 = __float2int_rn((1.f - a) * (1.f - b) * 16384.f); iw01 = __float2int_rn(a * (1.f - b) * 16384.f);
+            iw10 = __float2int_rn((1.f - a) * b * 16384.f); iw11 = 16384 - iw00 - iw01 - iw10;
+            const uint8_t* J = img1 + L.ioff + (size_t)(iny + L.B) * L.istride + (inx + L.B);
+            float b1 = 0.f, b2 = 0.f;
+            for (int i = lane; i < npx; i += 32) {
+                const int y = __umulhi((unsigned)i, rcpw), x = i - y * win;
+                const uint8_t* p = J + (size_t)y * L.istride + x;
+                const int diff = KLT_DESCALE(p[0] * iw00 + p[1] * iw01 + p[L.istride] * iw10 + p[L.istride + 1] * iw11, 9) - Iw[i];
+                const short2 d = dIw[i];
+                b1 += (float)(diff * d.x); b2 += (float)(diff * d.y);
+            }
+#pragma unroll
+            for (int o = 16; o > 0; o >>= 1) { b1 += __shfl_xor_sync(0xFFFFFFFFu, b1, o); b2 += __shfl_xor_sync(0xFFFFFFFFu, b2, o); }
+            b1 *= FLT_SCALE; b2 *= FLT_SCALE;
+            const float dx = (A12 * b2 - A22 * b1) * D, dy = (A12 * b1 - A11 * b2) * D;
+            nx += dx; ny += dy;
+            np = make_float2(nx + half, ny + half);
+            if ((double)dx * dx + (double)dy * dy <= eps2) break;
+            if (j > 0 && fabsf(dx + pdx) < 0.01 && fabsf(dy + pdy) < 0.01) { np.x -= dx * 0.5f; np.y -= dy * 0.5f; break; }
+            pdx = dx; pdy = dy;
+        }
+    }
+    if (lane == 0) { next_pts[pt] = np; status[pt] = ok ? 1 : 0; if (err) err[pt] = errv; }
+}
+
+}  // namespace uvip
+
+using namespace uvip;
+
+struct uvip_klt {
+    int device = 0, max_w = 0, max_h = 0, max_level = 0, win = 0, nslots = 0;
+    int w = 0, h = 0;                                   // geometry of the current plan
+    KltPlan plan;
+    size_t img_bytes = 0, der_elems = 0;
+    cudaStream_t stream = nullptr;
+    DevBuf img, der, stage, pts;
+    long long launches = 0;
+    std::mutex mu;
+};
+
+static void klt_make_plan(uvip_klt* k, int w, int h)
+{
+    KltPlan& P = k->plan; memset(&P, 0, sizeof(P));
+    P.win = k->win;
+    size_t ioff = 0, doff = 0;
+    int lw = w, lh = h, n = 0;
+    for (int l = 0; l <= k->max_level && l < KLT_MAXLEV; l++) {
+        if (l > 0) {
+            lw = (lw + 1) / 2; lh = (lh + 1) / 2;
+            if (lw <= k->win || lh <= k->win) break;          // lkpyramid.cpp: stop when a level is not larger than the window
+        }
+        KltLevel& L = P.lv[l];
+        L.w = lw; L.h = lh; L.B = k->win + 2;
+        L.istride = (int)align_up((size_t)lw + 2 * L.B, 16); L.dstride = (int)align_up((size_t)lw + 2 * L.B, 4);
+        L.ioff = ioff; L.doff = doff;
+        ioff += align_up((size_t)L.istride * (lh + 2 * L.B), 256);
+        doff += align_up((size_t)L.dstride * (lh + 2 * L.B), 64);
+        n = l + 1;
+    }
+    P.nlevels = n;
+    k->img_bytes = ioff; k->der_elems = doff; k->w = w; k->h = h;
+}
+
+extern "C" {
+
+int uvip_klt_create(int device, int max_width, int max_height, int win, int max_level, int nslots, uvip_klt** out)
+{
+    UVIP_CHECK_ARG(out && max_width > 0 && max_height > 0 && win >= 3 && win <= 63 && max_level >= 0 && nslots >= 2 && nslots <= 64);
+    *out = nullptr;
+    int ndev = 0;
+    if (cudaGetDeviceCount(&ndev) != cudaSuccess || ndev == 0) { set_last_error("no CUDA device available; libuvip_orb has no CPU fallback"); return UVIP_ERR_NO_DEVICE; }
+    UVIP_CHECK_ARG(device >= 0 && device < ndev);
+    DeviceGuard g(device);
+    uvip_klt* k = new uvip_klt();
+    k->device = device; k->max_w = max_width; k->max_h = max_height; k->win = win; k->max_level = max_level; k->nslots = nslots;
+    klt_make_plan(k, max_width, max_height);
+    const size_t ib = k->img_bytes, de = k->der_elems;
+    int rc = k->img.reserve(ib * nslots) | k->der.reserve(de * sizeof(short2) * nslots) | k->stage.reserve((size_t)max_width * max_height);
+    if (rc || cudaStreamCreateWithFlags(&k->stream, cudaStreamNonBlocking) != cudaSuccess) { uvip_klt_destroy(k); return UVIP_ERR_CUDA; }
+    cudaMemset(k->der.p, 0, k->der.cap);                 // derivative borders are BORDER_CONSTANT 0 and are never written
+    k->w = k->h = 0;
+    *out = k;
+    return UVIP_OK;
+}
+
+int uvip_klt_destroy(uvip_klt* k)
+{
+    if (!k) return UVIP_OK;
+    DeviceGuard g(k->device);
+    if (k->stream) { cudaStreamSynchronize(k->stream); cudaStreamDestroy(k->stream); }
+    k->img.release(); k->der.release(); k->stage.release(); k->pts.release();
+    delete k;
+    return UVIP_OK;
+}
+
+int uvip_klt_build_pyramid(uvip_klt* k, int slot, const uint8_t* image, int w, int h, int stride, int* nlevels)
+{
+    UVIP_CHECK_ARG(k && image && slot >= 0 && slot < k->nslots && w > 0 && h > 0 && stride >= w && w <= k->max_w && h <= k->max_h);
+    std::lock_guard<std::mutex> lk(k->mu);
+    DeviceGuard g(k->device);
+    cudaStream_t st = k->stream;
+    if (w != k->w || h != k->h) {
+        const size_t ib = k->img_bytes, de = k->der_elems;     // slot strides stay those of the maximal frame
+        klt_make_plan(k, w, h);
+        k->img_bytes = ib; k->der_elems = de;
+        UVIP_CUDA(cudaMemsetAsync(k->der.p, 0, k->der.cap, st));
+    }
+    const KltPlan& P = k->plan;
+    uint8_t* img = k->img.as<uint8_t>() + (size_t)slot * k->img_bytes;
+    short2* der = k->der.as<short2>() + (size_t)slot * k->der_elems;
+    UVIP_CUDA(cudaMemcpy2DAsync(k->stage.p, w, image, stride, w, h, cudaMemcpyHostToDevice, st));
+    { const KltLevel& L = P.lv[0]; k_klt_import<<<div_up((L.w + 2 * L.B) * (L.h + 2 * L.B), 256), 256, 0, st>>>(k->stage.as<uint8_t>(), w, img, P); k->launches++; }
+    for (int l = 1; l < P.nlevels; l++) {
+        const KltLevel& L = P.lv[l];
+        k_klt_pyrdown<<<div_up((L.w + 2 * L.B) * (L.h + 2 * L.B), 256), 256, 0, st>>>(img, l, P); k->launches++;
+    }
+    for (int l = 0; l < P.nlevels; l++) {
+        const KltLevel& L = P.lv[l];
+        k_klt_scharr<<<div_up(L.w * L.h, 256), 256, 0, st>>>(img, der, l, P); k->launches++;
+    }
+    UVIP_CUDA(cudaGetLastError());
+    UVIP_CUDA(cudaStreamSynchronize(st));
+    if (nlevels) *nlevels = P.nlevels;
+    return UVIP_OK;
+}
+
+int uvip_klt_get_level(uvip_klt* k, int slot, int level, uint8_t* img, int16_t* der, int* w, int* h)
+{
+    UVIP_CHECK_ARG(k && slot >= 0 && slot < k->nslots && k->w > 0 && level >= 0 && level < k->plan.nlevels);
+    const KltLevel& L = k->plan.lv[level];
+    if (w) *w = L.w; if (h) *h = L.h;
+    DeviceGuard g(k->device);
+    UVIP_CUDA(cudaDeviceSynchronize());
+    if (img) UVIP_CUDA(cudaMemcpy2D(img, L.w, k->img.as<uint8_t>() + (size_t)slot * k->img_bytes + L.ioff + (size_t)L.B * L.istride + L.B, L.istride,
+                                    L.w, L.h, cudaMemcpyDeviceToHost));
+    if (der) UVIP_CUDA(cudaMemcpy2D(der, (size_t)L.w * 4, k->der.as<short2>() + (size_t)slot * k->der_elems + L.doff + (size_t)L.B * L.dstride + L.B,
+                                    (size_t)L.dstride * 4, (size_t)L.w * 4, L.h, cudaMemcpyDeviceToHost));
+    return UVIP_OK;
+}
+
+int uvip_klt_track(uvip_klt* k, int slot_prev, int slot_next, const float* prev_pts, float* next_pts, int n, int max_level,
+                   int max_iter, double epsilon, int flags, double min_eig_threshold, uint8_t* status, float* err)
+{
+    UVIP_CHECK_ARG(k && n >= 0 && slot_prev >= 0 && slot_prev < k->nslots && slot_next >= 0 && slot_next < k->nslots && k->w > 0);
+    if (n == 0) return UVIP_OK;
+    UVIP_CHECK_ARG(prev_pts && next_pts && status);
+    std::lock_guard<std::mutex> lk(k->mu);
+    DeviceGuard g(k->device);
+    if (max_iter < 0) max_iter = 0; if (max_iter > 100) max_iter = 100;            // calcOpticalFlowPyrLK clamps the criteria
+    if (epsilon < 0) epsilon = 0; if (epsilon > 10) epsilon = 10;
+    const double eps2 = epsilon * epsilon;
+    const KltPlan& P = k->plan;
+    if (max_level > P.nlevels - 1) max_level = P.nlevels - 1;
+    if (max_level < 0) max_level = 0;
+    int rc;
+    const size_t o_next = align_up((size_t)n * 8, 256), o_st = 2 * o_next, o_err = o_st + align_up((size_t)n, 256);
+    if ((rc = k->pts.reserve(o_err + (size_t)n * 4))) return rc;
+    uint8_t* base = k->pts.as<uint8_t>();
+    cudaStream_t st = k->stream;
+    UVIP_CUDA(cudaMemcpyAsync(base, prev_pts, (size_t)n * 8, cudaMemcpyHostToDevice, st));
+    UVIP_CUDA(cudaMemcpyAsync(base + o_next, next_pts, (size_t)n * 8, cudaMemcpyHostToDevice, st));
+    const int npx = P.win * P.win;
+    const size_t smem = (size_t)8 * 3 * ((npx + 1) & ~1) * sizeof(short);
+    UVIP_CUDA(cudaFuncSetAttribute(k_klt_track, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+    k_klt_track<<<div_up(n, 8), 256, smem, st>>>(k->img.as<uint8_t>() + (size_t)slot_prev * k->img_bytes, k->der.as<short2>() + (size_t)slot_prev * k->der_elems,
+                                                k->img.as<uint8_t>() + (size_t)slot_next * k->img_bytes, (const float2*)base, (float2*)(base + o_next), n,
+                                                max_level, max_iter, eps2, flags, min_eig_threshold, base + o_st, (float*)(base + o_err), P);
+    k->launches++;
+    UVIP_CUDA(cudaGetLastError());
+    UVIP_CUDA(cudaMemcpyAsync(next_pts, base + o_next, (size_t)n * 8, cudaMemcpyDeviceToHost, st));
+    UVIP_CUDA(cudaMemcpyAsync(status, base + o_st, (size_t)n, cudaMemcpyDeviceToHost, st));
+    if (err) UVIP_CUDA(cudaMemcpyAsync(err, base + o_err, (size_t)n * 4, cudaMemcpyDeviceToHost, st));
+    UVIP_CUDA(cudaStreamSynchronize(st));
+    return UVIP_OK;
+}
+
+long long uvip_klt_launch_count(const uvip_klt* k) { return k ? k->launches : 0; }
+
+}  // extern "C"

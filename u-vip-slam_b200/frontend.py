@@ -379,3 +379,48 @@ class ORBVocabulary:
     def transform(self, desc, levelsup=4):
         wid, nid, w = self.descend(desc, levelsup)
         return self.accumulate(wid, nid, w, self.weighting, self.scoring)
+
+
+class KLTTracker:
+    """cv::buildOpticalFlowPyramid + cv::calcOpticalFlowPyrLK as used by FrameKTL / Tracking::perform_matching
+    (src/FrameKTL.cc:76, src/Tracking.cc:1044-1047), next row N1."""
+    USE_INITIAL_FLOW, GET_MIN_EIGENVALS = 4, 8
+
+    def __init__(self, max_width, max_height, win=21, max_level=5, nslots=2, device=0):
+        self.h = C.c_void_p()
+        self.win, self.max_level = win, max_level
+        check(lib().uvip_klt_create(device, max_width, max_height, win, max_level, nslots, C.byref(self.h)))
+
+    def close(self):
+        if getattr(self, 'h', None) is not None and self.h:
+            lib().uvip_klt_destroy(self.h)
+            self.h = C.c_void_p()
+
+    def __del__(self):
+        try:
+            self.close()
+        except Exception:
+            pass
+
+    def build_pyramid(self, slot, image):
+        image = np.ascontiguousarray(image, np.uint8)
+        H, W = image.shape
+        n = C.c_int()
+        check(lib().uvip_klt_build_pyramid(self.h, slot, ptr(image), W, H, W, C.byref(n)))
+        return n.value
+
+    def level(self, slot, l):
+        w = C.c_int(); h = C.c_int()
+        check(lib().uvip_klt_get_level(self.h, slot, l, None, None, C.byref(w), C.byref(h)))
+        img = np.zeros((h.value, w.value), np.uint8); der = np.zeros((h.value, w.value, 2), np.int16)
+        check(lib().uvip_klt_get_level(self.h, slot, l, ptr(img), ptr(der), C.byref(w), C.byref(h)))
+        return img, der
+
+    def track(self, slot_prev, slot_next, prev_pts, next_pts, max_iter=30, eps=0.01, flags=12, min_eig_thr=1e-4):
+        prev_pts = np.ascontiguousarray(prev_pts, np.float32).reshape(-1, 2)
+        nxt = np.ascontiguousarray(next_pts, np.float32).reshape(-1, 2).copy()
+        n = len(prev_pts)
+        status = np.zeros(n, np.uint8); err = np.zeros(n, np.float32)
+        check(lib().uvip_klt_track(self.h, slot_prev, slot_next, ptr(prev_pts), ptr(nxt), n, self.max_level, int(max_iter), float(eps), int(flags),
+                                   float(min_eig_thr), ptr(status), ptr(err)))
+        return nxt, status, err
