@@ -36,7 +36,7 @@ def parse():
     ap.add_argument('--batch', type=int, default=256, help='frames per step and per GPU')
     ap.add_argument('--ref-frames', type=int, default=0, help='frames per step of the reference arm (0 = 4 x cores)')
     ap.add_argument('--no-extras', action='store_true', help='skip the Hamming-only and cpu_baseline legs')
-    ap.add_argument('--workload', default='frames', choices=['frames', 'knn'],
+    ap.add_argument('--workload', default='frames', choices=['frames', 'knn', 'next'],
                     help="'frames' = the headline metric; 'knn' = BASELINE config 4: database-sharded brute-force kNN2 with NCCL top-2 merge")
     ap.add_argument('--knn-n', type=int, default=262144, help='rows of the query and train sets for --workload knn (config 4 is 1048576)')
     return ap.parse_args()
@@ -402,8 +402,74 @@ def run_knn(args):
     return 0
 
 
+def run_next(args):
+    """the SURVEY 8f rows built so far (CLAHE, DBoW2 descent, KLT), each timed next to its oracle on the host cores"""
+    import ctypes as C
+    import numpy as np
+    import torch
+    import __graft_entry__ as ge
+    pkg = ge.load_package()
+    from oracle import oracle as O
+    dev = torch.device('cuda', 0); torch.cuda.set_device(0)
+    L = pkg.capi.lib(); chk = pkg.capi.check
+    stream = torch.cuda.Stream(dev); torch.cuda.set_stream(stream)
+    sp = C.c_void_p(stream.cuda_stream)
+    K = args.steps
+    out = {'metric': 'next rows (SURVEY 8f)', 'n_gpus': 1, 'steps': K, 'data': 'synthetic'}
+
+    def timed(fn):
+        for _ in range(3):
+            fn()
+        torch.cuda.synchronize(dev)
+        a = torch.cuda.Event(enable_timing=True); b = torch.cuda.Event(enable_timing=True)
+        a.record(stream)
+        for _ in range(K):
+            fn()
+        b.record(stream); torch.cuda.synchronize(dev)
+        return a.elapsed_time(b) / K
+
+    # CLAHE: 256 frames resident in HBM, in place
+    B = 256
+    frames = make_frames(pkg.synth, B, 1)
+    d = torch.from_numpy(frames).to(dev)
+    ex = pkg.ORBextractor(NFEAT, SCALE, NLEVELS, 1, FAST_TH, device=0, max_width=W, max_height=H, max_batch=1)
+    ms = timed(lambda: chk(L.uvip_clahe_batch_device(ex.h, C.c_void_p(d.data_ptr()), B, W, H, W, W * H, 4.0, 12, 12, C.c_void_p(d.data_ptr()), W, W * H, sp)))
+    t0 = time.perf_counter(); [O.clahe(f) for f in frames[:32]]; tc = (time.perf_counter() - t0) / 32
+    peak, _ = hbm_peak()
+    out['clahe'] = {'frames_per_s': B / (ms * 1e-3), 'ms_per_256_frames': ms, 'hbm_frac_of_measured': (2.0 * W * H * B / (ms * 1e-3) / 1e9) / peak,
+                    'cpu_oracle_frames_per_s_1thread': 1.0 / tc}
+    # DBoW2 descent: k=10, L=5 synthetic vocabulary (111k nodes), 256 x 1000 descriptors
+    tree, _ = pkg.synth.synthetic_vocabulary(10, 5, seed=3)
+    voc = pkg.ORBVocabulary(tree)
+    nd = 256000
+    desc = torch.from_numpy(pkg.synth.random_descriptors(5, nd)).to(dev)
+    wid = torch.empty(nd, dtype=torch.int32, device=dev); nid = torch.empty_like(wid); wt = torch.empty(nd, dtype=torch.float64, device=dev)
+    ms = timed(lambda: chk(L.uvip_bow_transform_device(voc.h, C.c_void_p(desc.data_ptr()), nd, 4, C.c_void_p(wid.data_ptr()), C.c_void_p(nid.data_ptr()),
+                                                       C.c_void_p(wt.data_ptr()), sp)))
+    hd = desc[:20000].cpu().numpy()
+    t0 = time.perf_counter(); O.bow_transform(tree, hd, 4); tc = time.perf_counter() - t0
+    out['bow_descent'] = {'descriptors_per_s': nd / (ms * 1e-3), 'ms_per_256k': ms, 'distances_per_descriptor': 10 * 5,
+                          'cpu_oracle_descriptors_per_s_1thread': 20000 / tc}
+    # KLT: 1000 points, 21x21, 5 levels, through the host-buffer calls (copies inside)
+    a_img = pkg.synth.synth_frame(1, W, H); b_img = pkg.synth.synth_frame(1, W, H, dx=5, dy=3, noise_seed=2)
+    kps, _ = ex(a_img)
+    p0 = np.stack([kps['x'], kps['y']], 1).astype(np.float32)[:1000]
+    klt = pkg.KLTTracker(W, H, 21, 5)
+    t0 = time.perf_counter()
+    for _ in range(K):
+        klt.build_pyramid(0, a_img); klt.build_pyramid(1, b_img)
+        p1, st, err = klt.track(0, 1, p0, p0)
+    tg = (time.perf_counter() - t0) / K
+    t0 = time.perf_counter()
+    P0 = O.LKPyramid(a_img, 21, 5); P1 = O.LKPyramid(b_img, 21, 5); O.lk_track(P0, P1, p0, p0, 21, 5, 30, 0.01, 8)
+    tc = time.perf_counter() - t0
+    out['klt'] = {'frame_pairs_per_s_e2e': 1.0 / tg, 'points': len(p0), 'tracked': int(st.sum()), 'cpu_oracle_frame_pairs_per_s_1thread': 1.0 / tc}
+    print(json.dumps(out), flush=True)
+    return 0
+
+
 if __name__ == '__main__':
     a = parse()
     if a.impl == 'reference':
         sys.exit(run_reference(a))
-    sys.exit(run_knn(a) if a.workload == 'knn' else run_ours(a))
+    sys.exit(run_knn(a) if a.workload == 'knn' else run_next(a) if a.workload == 'next' else run_ours(a))
