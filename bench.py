@@ -35,6 +35,7 @@ def parse():
     ap.add_argument('--impl', default='ours', choices=['ours', 'reference'])
     ap.add_argument('--batch', type=int, default=256, help='frames per step and per GPU')
     ap.add_argument('--ref-frames', type=int, default=0, help='frames per step of the reference arm (0 = 4 x cores)')
+    ap.add_argument('--e2e-chunk', type=int, default=0, help='frames per pipeline chunk of the host-buffer entry point (0 = batch/2)')
     ap.add_argument('--no-extras', action='store_true', help='skip the Hamming-only and cpu_baseline legs')
     ap.add_argument('--workload', default='frames', choices=['frames', 'knn', 'next'],
                     help="'frames' = the headline metric; 'knn' = BASELINE config 4: database-sharded brute-force kNN2 with NCCL top-2 merge")
@@ -245,27 +246,41 @@ def run_ours(args):
         ms = float(tt.item())
     fps = world * B * K / (ms * 1e-3)
 
-    # ---- end to end through the host-buffer C-ABI (pinned host memory in, host memory out), copies inside the timed region
-    host_k = torch.zeros((B, cap, 28), dtype=torch.uint8).pin_memory(); host_d = torch.zeros((B, cap, 32), dtype=torch.uint8).pin_memory()
-    host_n = torch.zeros(B, dtype=torch.int32).pin_memory()
-    host_i = torch.zeros((B, cap, 2), dtype=torch.int32).pin_memory(); host_dd = torch.zeros_like(host_i).pin_memory()
+    # ---- end to end through the host-buffer C-ABI (pinned host memory in, host memory out), copies inside the timed region.
+    # Each step uploads its own 256 frames and downloads keypoints, descriptors and kNN results; steps are issued through
+    # uvip_extract_batch_submit / _wait so that the upload of step i+1 overlaps the kernels of step i (two host buffer sets).
     hp = lambda t: C.c_void_p(t.data_ptr())
-
-    # the host-buffer entry point pipelines chunks of max_batch frames (H2D | kernels | D2H on three streams)
+    hb = []
+    for j in range(2):
+        hb.append(dict(inp=(host_in if j == 0 else torch.roll(host_in, 1, 0).pin_memory()),
+                       k=torch.zeros((B, cap, 28), dtype=torch.uint8).pin_memory(), d=torch.zeros((B, cap, 32), dtype=torch.uint8).pin_memory(),
+                       n=torch.zeros(B, dtype=torch.int32).pin_memory(), i=torch.zeros((B, cap, 2), dtype=torch.int32).pin_memory(),
+                       dd=torch.zeros((B, cap, 2), dtype=torch.int32).pin_memory()))
     ex_e2e = pkg.ORBextractor(NFEAT, SCALE, NLEVELS, pkg.ORBextractor.FAST_SCORE, FAST_TH, device=local, max_width=W, max_height=H,
-                              max_batch=max(1, B // 8))
+                              max_batch=args.e2e_chunk or max(1, B // 2))
 
-    def e2e_step():
-        chk(L.uvip_extract_batch(ex_e2e.h, hp(host_in), B, W, H, W, W * H, hp(host_k), hp(host_n), cap, hp(host_d)))
-        chk(L.uvip_knn2_batch(m.h, hp(host_d), hp(host_n), cap * 32, C.c_void_p(host_d.data_ptr() + cap * 32),
-                              C.c_void_p(host_n.data_ptr() + 4), cap * 32, B - 1, cap, hp(host_i), hp(host_dd), cap))
+    def submit(j):
+        t = C.c_int(-1)
+        chk(L.uvip_extract_batch_submit(ex_e2e.h, hp(hb[j]['inp']), B, W, H, W, W * H, hp(hb[j]['k']), hp(hb[j]['n']), cap, hp(hb[j]['d']), C.byref(t)))
+        return t.value
+
+    def finish(j, t):
+        chk(L.uvip_extract_batch_wait(ex_e2e.h, t))
+        chk(L.uvip_knn2_batch(m.h, hp(hb[j]['d']), hp(hb[j]['n']), cap * 32, C.c_void_p(hb[j]['d'].data_ptr() + cap * 32),
+                              C.c_void_p(hb[j]['n'].data_ptr() + 4), cap * 32, B - 1, cap, hp(hb[j]['i']), hp(hb[j]['dd']), cap))
+
+    def e2e_run(nsteps):
+        t = submit(0)
+        for i in range(nsteps):
+            tn = submit((i + 1) & 1) if i + 1 < nsteps else None
+            finish(i & 1, t)
+            t = tn
 
     Ke = max(3, min(K, 10))
-    e2e_step(); e2e_step()
+    e2e_run(2)
     barrier()
     te = time.perf_counter()
-    for _ in range(Ke):
-        e2e_step()
+    e2e_run(Ke)
     barrier()
     e2e_s = time.perf_counter() - te
     if world > 1:
@@ -274,6 +289,16 @@ def run_ours(args):
         e2e_s = float(tt.item())
     e2e_fps = world * B * Ke / e2e_s
     h2d = B * W * H + B * cap * 32 + 2 * (B - 1) * 4
+    # single-frame latency of the reference-shaped call (uvip_extract = operator(), host image in, host keypoints out)
+    one_k = np.zeros((cap, 7), np.float32); one_d = np.zeros((cap, 32), np.uint8)
+    lat = []
+    for i in range(40):
+        nn = C.c_int(0)
+        tl = time.perf_counter()
+        chk(L.uvip_extract(ex_e2e.h, C.c_void_p(host_in[i % B].data_ptr()), W, H, W, C.c_void_p(one_k.ctypes.data), C.byref(nn), cap,
+                           C.c_void_p(one_d.ctypes.data), None, 0, 0, 0, 1, 0))
+        lat.append(time.perf_counter() - tl)
+    lat_ms = float(np.median(lat[8:]) * 1e3)
     d2h = B * cap * 60 + B * 4 + 2 * (B - 1) * cap * 8
 
     # ---- roofline of the dominant extraction kernel (algorithmic bytes of SURVEY 8(d) / its measured duration)
@@ -296,7 +321,8 @@ def run_ours(args):
                    'l2': 'inputs alternate between two 92 MB batches and each step streams a 0.7 GB pyramid working set (> 126 MB L2)',
                    'parallelism': 'frames sharded over %d GPU(s), no collective' % world},
         'clocks': clk,
-        'e2e': {'value': e2e_fps, 'unit': 'frames/s', 'h2d_bytes_per_step': h2d, 'd2h_bytes_per_step': d2h, 'steps': Ke},
+        'e2e': {'value': e2e_fps, 'unit': 'frames/s', 'h2d_bytes_per_step': h2d, 'd2h_bytes_per_step': d2h, 'steps': Ke,
+                'chunk_frames': args.e2e_chunk or max(1, B // 2), 'pipeline': 'submit/wait, 2 batches in flight', 'single_frame_latency_ms': lat_ms},
         'gpu_launches': int(launches),
         'roofline': roofline,
         'hamming': {'pairs_per_s_in_step': pairs_step * K / (knn_ms * 1e-3) if knn_ms > 0 else None, 'pairs_per_step': pairs_step},

@@ -91,6 +91,14 @@ int   uvip_extract(uvip_extractor* ex, const uint8_t* image, int w, int h, int s
  * n_out[f] keypoints at kps + f*cap and desc + f*cap*32.  Host buffers (copies are inside the call). */
 int   uvip_extract_batch(uvip_extractor* ex, const uint8_t* frames, int nframes, int w, int h, int stride,
                          size_t frame_pitch, uvip_keypoint* kps, int32_t* n_out, int cap, uint8_t* desc);
+/* The two halves of uvip_extract_batch for callers that stream a sequence: submit enqueues the copies and kernels of one
+ * batch and returns a ticket (0 or 1) without waiting; wait blocks until that batch's outputs are in the host buffers
+ * and returns its status.  At most two batches are in flight per handle, so the H2D copy of batch i+1 overlaps the
+ * kernels of batch i and the D2H copy of batch i-1.  The host buffers must stay valid (and should be pinned) until the
+ * wait returns; uvip_extract on the same handle is refused while a ticket is outstanding. */
+int   uvip_extract_batch_submit(uvip_extractor* ex, const uint8_t* frames, int nframes, int w, int h, int stride,
+                                size_t frame_pitch, uvip_keypoint* kps, int32_t* n_out, int cap, uint8_t* desc, int* ticket);
+int   uvip_extract_batch_wait(uvip_extractor* ex, int ticket);
 /* Device-resident variant: all pointers are device memory; asynchronous on `stream`.
  * uvip_extractor_status() after synchronising reports capacity overflow of the launch group. */
 int   uvip_extract_batch_device(uvip_extractor* ex, const uint8_t* d_frames, int nframes, int w, int h, int stride,

@@ -155,6 +155,26 @@ def test_extract_batch_matches_single_frames(gpu, oracle, synth):
     # size-independent property: a batch is order-equivariant
     kps2, n2, desc2 = ex.extract_batch(frames[::-1].copy())
     assert np.array_equal(n2, n[::-1]) and np.array_equal(desc2[0, :n2[0]], desc[nfr - 1, :n[nfr - 1]])
+    # submit/wait: two batches in flight give the same bytes as the synchronous call; a third submit and a single-frame
+    # call are refused while tickets are outstanding
+    cap = kps.shape[1]
+    fa, fb = frames[:5].copy(), frames[1:].copy()
+    outs = [(np.zeros((5, cap), gpu.KP_DTYPE), np.zeros(5, np.int32), np.zeros((5, cap, 32), np.uint8)) for _ in range(2)]
+    ta = ex.extract_batch_submit(fa, *outs[0]); tb = ex.extract_batch_submit(fb, *outs[1])
+    assert {ta, tb} == {0, 1}
+    with pytest.raises(gpu.UvipError):
+        ex.extract_batch_submit(fa, *outs[0])
+    with pytest.raises(gpu.UvipError):
+        ex(frames[0])
+    ex.extract_batch_wait(tb); ex.extract_batch_wait(ta)
+    with pytest.raises(gpu.UvipError):
+        ex.extract_batch_wait(ta)
+    for (k_, n_, d_), lo in ((outs[0], 0), (outs[1], 1)):
+        assert np.array_equal(n_, n[lo:lo + 5])
+        for f in range(5):
+            assert np.array_equal(k_[f, :n_[f]], kps[lo + f, :n_[f]]) and np.array_equal(d_[f, :n_[f]], desc[lo + f, :n_[f]])
+    k1, d1 = ex(frames[0])                                   # the single-frame path works again once the tickets are back
+    assert np.array_equal(d1, desc[0, :n[0]])
 
 
 def test_capacity_overflow_is_loud(gpu, synth):

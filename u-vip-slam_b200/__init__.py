@@ -13,4 +13,5 @@ from . import build  # noqa: F401
 from . import capi  # noqa: F401
 from . import frontend  # noqa: F401
 from . import sharding  # noqa: F401
+from .capi import UvipError, KP_DTYPE  # noqa: F401
 from .frontend import ORBextractor, ORBmatcher, ORBVocabulary, KLTTracker  # noqa: F401

@@ -1144,6 +1144,11 @@ struct uvip_extractor {
     DevBuf in2, kps2, desc2, n2;                     // second staging set: uvip_extract_batch double-buffers its chunks
     cudaStream_t h2d_stream = nullptr, d2h_stream = nullptr;
     cudaEvent_t ev_h2d[2] = {nullptr, nullptr}, ev_comp[2] = {nullptr, nullptr}, ev_d2h[2] = {nullptr, nullptr};
+    cudaEvent_t ev_done[2] = {nullptr, nullptr};       // one per ticket of uvip_extract_batch_submit
+    int* h_status = nullptr;                           // pinned, one word per ticket
+    long long chunk_seq = 0, ticket_seq = 0;
+    int inflight = 0;
+    bool ticket_busy[2] = {false, false};
     int sel_cap = 0;
     int last_frames = 0;
     long long launches = 0;
@@ -1525,6 +1530,8 @@ int uvip_extractor_destroy(uvip_extractor* ex)
     for (DevBuf* b : bufs) b->release();
     for (cudaEvent_t e : ex->prof_ev) cudaEventDestroy(e);
     for (int i = 0; i < 2; i++) { if (ex->ev_h2d[i]) cudaEventDestroy(ex->ev_h2d[i]); if (ex->ev_comp[i]) cudaEventDestroy(ex->ev_comp[i]); if (ex->ev_d2h[i]) cudaEventDestroy(ex->ev_d2h[i]); }
+    for (int i = 0; i < 2; i++) if (ex->ev_done[i]) cudaEventDestroy(ex->ev_done[i]);
+    if (ex->h_status) cudaFreeHost(ex->h_status);
     if (ex->h2d_stream) cudaStreamDestroy(ex->h2d_stream);
     if (ex->d2h_stream) cudaStreamDestroy(ex->d2h_stream);
     if (ex->stream) cudaStreamDestroy(ex->stream);
@@ -1568,27 +1575,37 @@ int uvip_extractor_status(uvip_extractor* ex)
     return read_status(ex, ex->stream);
 }
 
-int uvip_extract_batch(uvip_extractor* ex, const uint8_t* frames, int nframes, int w, int h, int stride,
-                       size_t frame_pitch, uvip_keypoint* kps, int32_t* n_out, int cap, uint8_t* desc)
+// Chunks of max_batch frames flow through a 3-stream pipeline: H2D of chunk c+1 and D2H of chunk c-1 overlap the kernels of
+// chunk c (two staging sets; pinned host memory is needed for the copies to be truly asynchronous).  The chunk counter
+// and the guard events live in the handle, so that two submitted batches overlap in the same way across calls.
+static int submit_batch(uvip_extractor* ex, const uint8_t* frames, int nframes, int w, int h, int stride,
+                        size_t frame_pitch, uvip_keypoint* kps, int32_t* n_out, int cap, uint8_t* desc, int* ticket_out)
 {
-    UVIP_CHECK_ARG(ex && frames && kps && n_out && desc && nframes >= 1 && w > 0 && h > 0 && stride >= w && cap >= 1);
-    UVIP_CHECK_ARG(frame_pitch >= (size_t)stride * (h - 1) + w);
-    std::lock_guard<std::mutex> lk(ex->mu);
+    if (ex->inflight >= 2) { set_last_error("two batches are already in flight: wait for a ticket first"); return UVIP_ERR_ARG; }
     DeviceGuard g(ex->device);
     int rc = ensure_plan(ex, w, h);
     if (rc) return rc;
-    // Chunks of max_batch frames flow through a 3-stream pipeline: H2D of chunk c+1 and D2H of chunk c-1 overlap the
-    // kernels of chunk c (two staging sets; pinned host memory is needed for the copies to be truly asynchronous).
     const int B = ex->prm.max_batch;
     const size_t fbytes = (size_t)stride * h;
     DevBuf* in[2] = {&ex->in_frames, &ex->in2}; DevBuf* ok[2] = {&ex->out_kps, &ex->kps2};
     DevBuf* od[2] = {&ex->out_desc, &ex->desc2}; DevBuf* on[2] = {&ex->out_n, &ex->n2};
     const int nchunks = (nframes + B - 1) / B;
-    for (int s = 0; s < (nchunks > 1 ? 2 : 1); s++) {
-        if ((rc = in[s]->reserve((size_t)B * fbytes))) return rc;
-        if ((rc = ok[s]->reserve((size_t)B * cap * sizeof(uvip_keypoint)))) return rc;
-        if ((rc = od[s]->reserve((size_t)B * cap * 32))) return rc;
-        if ((rc = on[s]->reserve((size_t)B * 4))) return rc;
+    cudaStream_t st = ex->stream;
+    bool grew = false;
+    for (int s = 0; s < 2; s++) {
+        const size_t need[4] = {(size_t)B * fbytes, (size_t)B * cap * sizeof(uvip_keypoint), (size_t)B * cap * 32, (size_t)B * 4};
+        DevBuf* b[4] = {in[s], ok[s], od[s], on[s]};
+        for (int i = 0; i < 4; i++) if (b[i]->cap < need[i]) grew = true;
+    }
+    if (grew) {                                                  // reallocation: nothing may still be using the old staging sets
+        if (ex->inflight) { set_last_error("staging buffers must grow while a batch is in flight: wait first"); return UVIP_ERR_ARG; }
+        UVIP_CUDA(cudaDeviceSynchronize());
+        for (int s = 0; s < 2; s++) {
+            if ((rc = in[s]->reserve((size_t)B * fbytes))) return rc;
+            if ((rc = ok[s]->reserve((size_t)B * cap * sizeof(uvip_keypoint)))) return rc;
+            if ((rc = od[s]->reserve((size_t)B * cap * 32))) return rc;
+            if ((rc = on[s]->reserve((size_t)B * 4))) return rc;
+        }
     }
     if (!ex->h2d_stream) {
         UVIP_CUDA(cudaStreamCreateWithFlags(&ex->h2d_stream, cudaStreamNonBlocking));
@@ -1597,19 +1614,30 @@ int uvip_extract_batch(uvip_extractor* ex, const uint8_t* frames, int nframes, i
             UVIP_CUDA(cudaEventCreateWithFlags(&ex->ev_h2d[i], cudaEventDisableTiming));
             UVIP_CUDA(cudaEventCreateWithFlags(&ex->ev_comp[i], cudaEventDisableTiming));
             UVIP_CUDA(cudaEventCreateWithFlags(&ex->ev_d2h[i], cudaEventDisableTiming));
+            UVIP_CUDA(cudaEventCreateWithFlags(&ex->ev_done[i], cudaEventDisableTiming));
         }
+        UVIP_CUDA(cudaHostAlloc((void**)&ex->h_status, 2 * sizeof(int), cudaHostAllocDefault));
+        ex->chunk_seq = 0;
     }
-    cudaStream_t st = ex->stream, sh = ex->h2d_stream, sd = ex->d2h_stream;
-    UVIP_CUDA(cudaMemsetAsync(ex->status.p, 0, sizeof(int), st));
-    for (int c = 0; c < nchunks; c++) {
-        const int s = c & 1, f0 = c * B;
+    cudaStream_t sh = ex->h2d_stream, sd = ex->d2h_stream;
+    if (ex->inflight == 0) {
+        UVIP_CUDA(cudaMemsetAsync(ex->status.p, 0, sizeof(int), st));
+        // the single-frame entry point shares in_frames / out_* on the compute stream: order the copy streams behind it
+        UVIP_CUDA(cudaEventRecord(ex->ev_done[0], st));
+        UVIP_CUDA(cudaStreamWaitEvent(sh, ex->ev_done[0], 0));
+        UVIP_CUDA(cudaStreamWaitEvent(sd, ex->ev_done[0], 0));
+    }
+    int s = 0;
+    for (int c = 0; c < nchunks; c++, ex->chunk_seq++) {
+        s = (int)(ex->chunk_seq & 1);
+        const int f0 = c * B;
         const int nb = nframes - f0 < B ? nframes - f0 : B;
-        if (c >= 2) UVIP_CUDA(cudaStreamWaitEvent(sh, ex->ev_comp[s], 0));          // kernels of chunk c-2 are done with in[s]
+        if (ex->chunk_seq >= 2) UVIP_CUDA(cudaStreamWaitEvent(sh, ex->ev_comp[s], 0));   // kernels of chunk c-2 are done with in[s]
         if (frame_pitch == fbytes) UVIP_CUDA(cudaMemcpyAsync(in[s]->p, frames + (size_t)f0 * frame_pitch, (size_t)nb * fbytes, cudaMemcpyHostToDevice, sh));
         else UVIP_CUDA(cudaMemcpy2DAsync(in[s]->p, fbytes, frames + (size_t)f0 * frame_pitch, frame_pitch, fbytes - (stride - w), nb, cudaMemcpyHostToDevice, sh));
         UVIP_CUDA(cudaEventRecord(ex->ev_h2d[s], sh));
         UVIP_CUDA(cudaStreamWaitEvent(st, ex->ev_h2d[s], 0));
-        if (c >= 2) UVIP_CUDA(cudaStreamWaitEvent(st, ex->ev_d2h[s], 0));           // results of chunk c-2 have left out[s]
+        if (ex->chunk_seq >= 2) UVIP_CUDA(cudaStreamWaitEvent(st, ex->ev_d2h[s], 0));    // results of chunk c-2 have left out[s]
         rc = enqueue_group(ex, in[s]->as<uint8_t>(), nb, stride, fbytes, ok[s]->as<uvip_keypoint>(), on[s]->as<int32_t>(),
                            cap, od[s]->as<uint8_t>(), 1, 0, 1, 1, 1, 0, st, false);
         if (rc) return rc;
@@ -1620,8 +1648,54 @@ int uvip_extract_batch(uvip_extractor* ex, const uint8_t* frames, int nframes, i
         UVIP_CUDA(cudaMemcpyAsync(desc + (size_t)f0 * cap * 32, od[s]->p, (size_t)nb * cap * 32, cudaMemcpyDeviceToHost, sd));
         UVIP_CUDA(cudaEventRecord(ex->ev_d2h[s], sd));
     }
-    UVIP_CUDA(cudaStreamSynchronize(sd));
-    return read_status(ex, st);
+    const int t = ex->ticket_busy[0] ? 1 : 0;
+    UVIP_CUDA(cudaMemcpyAsync(ex->h_status + t, ex->status.p, sizeof(int), cudaMemcpyDeviceToHost, sd));   // sd is behind the last chunk's kernels
+    UVIP_CUDA(cudaEventRecord(ex->ev_done[t], sd));
+    ex->ticket_busy[t] = true; ex->inflight++;
+    *ticket_out = t;
+    return UVIP_OK;
+}
+
+static int wait_batch(uvip_extractor* ex, int ticket)
+{
+    if (ticket < 0 || ticket > 1 || !ex->ticket_busy[ticket]) { set_last_error("ticket %d is not in flight", ticket); return UVIP_ERR_ARG; }
+    DeviceGuard g(ex->device);
+    UVIP_CUDA(cudaEventSynchronize(ex->ev_done[ticket]));
+    ex->ticket_busy[ticket] = false; ex->inflight--;
+    const int s = ex->h_status[ticket];
+    if (s) {       // flags are sticky on the device until every batch in flight has reported them
+        set_last_error("device capacity overflow, flags 0x%x (1 FAST candidates, 2 quadtree nodes, 4 winners, 8 output rows)", s);
+        return UVIP_ERR_CAPACITY;
+    }
+    return UVIP_OK;
+}
+
+int uvip_extract_batch_submit(uvip_extractor* ex, const uint8_t* frames, int nframes, int w, int h, int stride,
+                              size_t frame_pitch, uvip_keypoint* kps, int32_t* n_out, int cap, uint8_t* desc, int* ticket)
+{
+    UVIP_CHECK_ARG(ex && frames && kps && n_out && desc && ticket && nframes >= 1 && w > 0 && h > 0 && stride >= w && cap >= 1);
+    UVIP_CHECK_ARG(frame_pitch >= (size_t)stride * (h - 1) + w);
+    std::lock_guard<std::mutex> lk(ex->mu);
+    return submit_batch(ex, frames, nframes, w, h, stride, frame_pitch, kps, n_out, cap, desc, ticket);
+}
+
+int uvip_extract_batch_wait(uvip_extractor* ex, int ticket)
+{
+    UVIP_CHECK_ARG(ex);
+    std::lock_guard<std::mutex> lk(ex->mu);
+    return wait_batch(ex, ticket);
+}
+
+int uvip_extract_batch(uvip_extractor* ex, const uint8_t* frames, int nframes, int w, int h, int stride,
+                       size_t frame_pitch, uvip_keypoint* kps, int32_t* n_out, int cap, uint8_t* desc)
+{
+    UVIP_CHECK_ARG(ex && frames && kps && n_out && desc && nframes >= 1 && w > 0 && h > 0 && stride >= w && cap >= 1);
+    UVIP_CHECK_ARG(frame_pitch >= (size_t)stride * (h - 1) + w);
+    std::lock_guard<std::mutex> lk(ex->mu);
+    int t = 0;
+    int rc = submit_batch(ex, frames, nframes, w, h, stride, frame_pitch, kps, n_out, cap, desc, &t);
+    if (rc) return rc;
+    return wait_batch(ex, t);
 }
 
 int uvip_extract(uvip_extractor* ex, const uint8_t* image, int w, int h, int stride,
@@ -1635,6 +1709,7 @@ int uvip_extract(uvip_extractor* ex, const uint8_t* image, int w, int h, int str
     UVIP_CHECK_ARG(n_in <= 4096 && n_in <= cap);
     if (!full_detect) UVIP_CHECK_ARG(grid && grid_rows > 0 && grid_cols > 0 && min_px_dist > 0);
     std::lock_guard<std::mutex> lk(ex->mu);
+    if (ex->inflight) { set_last_error("a submitted batch is in flight on this handle: wait for its ticket first"); return UVIP_ERR_ARG; }
     DeviceGuard g(ex->device);
     int rc = ensure_plan(ex, w, h);
     if (rc) return rc;

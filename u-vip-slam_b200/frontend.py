@@ -86,6 +86,18 @@ class ORBextractor:
         check(lib().uvip_extract_batch(self.h, ptr(frames), nf, W, H, W, W * H, ptr(kps), ptr(n), cap, ptr(desc)))
         return kps, n, desc
 
+    def extract_batch_submit(self, frames, kps, n, desc):
+        """enqueue one batch (caller-owned, ideally pinned, arrays: frames (nf,H,W) u8, kps (nf,cap) KP_DTYPE, n (nf,) i32,
+        desc (nf,cap,32) u8) and return its ticket; the arrays are filled when extract_batch_wait(ticket) returns"""
+        nf, H, W = frames.shape
+        cap = kps.shape[1]
+        t = C.c_int(-1)
+        check(lib().uvip_extract_batch_submit(self.h, ptr(frames), nf, W, H, W, W * H, ptr(kps), ptr(n), cap, ptr(desc), C.byref(t)))
+        return t.value
+
+    def extract_batch_wait(self, ticket):
+        check(lib().uvip_extract_batch_wait(self.h, int(ticket)))
+
     def extract_batch_device(self, d_frames, nframes, W, H, d_kps, d_n, cap, d_desc, stream=0):
         """all pointers are integers (device addresses, e.g. torch tensor.data_ptr()); asynchronous"""
         check(lib().uvip_extract_batch_device(self.h, ptr(d_frames), nframes, W, H, W, W * H, ptr(d_kps), ptr(d_n), cap,
