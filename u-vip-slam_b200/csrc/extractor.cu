@@ -51,8 +51,9 @@ struct Plan {
     int ftiles, btiles, tile_tab_off;
     int node_cap;             // quadtree node capacity (power of two)
     unsigned rcp_cpr;         // ceil(2^32 / chunks-per-row) for the import kernel
+    unsigned f_rcp_srow;      // ceil(2^32 / f_srow)
     int rs_boxw, rs_boxh;     // resize: TMA box of the source level
-    int f_irow, f_irows, f_srow, f_srows, f_gcap, f_qcap;   // FAST shared-memory carve-up (largest tile over all levels)
+    int f_irow, f_irows, f_srow, f_srows, f_gw;   // FAST shared-memory carve-up (largest tile over all levels)
     unsigned long long frame_bytes;
     LevelInfo lv[MAXLEV];
 };
@@ -209,14 +210,17 @@ k_resize(const CUtensorMap* __restrict__ tmaps, uint8_t* __restrict__ pyr, const
 //   B1  SWAR pre-test, 4 pixels per thread per step, all groups: |ring - v| > t on the compass pairs (0,8),(4,12)
 //       via VABSDIFF4 + a per-byte carry trick; a 9-arc contains one pixel of every opposite pair, so groups where
 //       no pixel passes are dropped (85 % on the benchmark frame).  Survivors are compacted (warp ballot) so that
-//   B2  the full test runs on dense warps: ring pixel k of 4 neighbouring pixels is one funnel-shifted 32-bit word,
-//       "brighter than v+t" / "darker than v-t" are 3 ALU ops per word each, opposite pairs are AND-ed progressively,
-//       then the 9-contiguity AND-chains; corner pixels are queued
-//   C   exact score s = max_arc min_k |ring_k - v| - 1 (== OpenCV cornerScore) for the queued corners (DPX min3/max3)
+//   B2  the groups are tested on dense warps at the 8 even ring positions (ring pixel k of 4 neighbouring pixels is one
+//       funnel-shifted 32-bit word; "brighter than v+t" / "darker than v-t" are 3 ALU ops per word each): a 9-arc
+//       contains 4 consecutive even positions, so pixels without such a run are dropped; the rest are queued
+//   C   exact score s = max_arc min_k |ring_k - v| - 1 (== OpenCV cornerScore, DPX min3/max3) of every queued pixel;
+//       s >= t  <=>  the pixel is a FAST-9 corner at t, so this is also the exact corner decision; corners are
+//       compacted once more
 //   D   3x3 strict NMS inside the cell, survivors appended to the (frame, level) raw-corner list (warp-aggregated)
 // Pass 2 repeats B..D at the retry threshold for the cells of the tile that produced no survivor.
 // --------------------------------------------------------------------------------------------------------
 constexpr int FAST_CW = 4, FAST_CH = 2;      // cells per tile
+constexpr int FAST_WARPS = 8;
 
 __device__ __forceinline__ unsigned swar_gt(unsigned a, unsigned b, unsigned nb7)
 {   // bit 7 of every byte: a > b (unsigned bytes); nb7 = ~b & 0x7f7f7f7f precomputed
@@ -248,63 +252,51 @@ __device__ __forceinline__ unsigned fast_pre4(const unsigned* __restrict__ W, in
     return p08 & (g4 | g12) & 0x80808080u;
 }
 
-// B2: corner flags (bit 7 per byte) of the 4 pixels whose centre word is W[0]; rs = row stride in words
-__device__ __forceinline__ unsigned fast_swar4(const unsigned* __restrict__ W, int rs, unsigned t4, unsigned valid)
+// B2: candidate flags (bit 7 per byte) of the 4 pixels whose centre word is W[0]; rs = row stride in words.
+// Only the 8 even ring positions are examined: a 9-arc of the 16-ring always contains 4 consecutive even positions, so
+// "4 consecutive even positions all brighter than v+t (or all darker than v-t)" is necessary for a corner.  The exact
+// decision is left to the score stage (score >= t  <=>  corner at t), which runs on dense warps of single pixels.
+__device__ __forceinline__ unsigned fast_even8(const unsigned* __restrict__ W, int rs, unsigned t4, unsigned valid)
 {
     const unsigned v = W[0];
     const unsigned hi = __vaddus4(v, t4), lo = __vsubus4(v, t4);
     const unsigned nhi7 = ~hi & 0x7f7f7f7fu, lo7 = lo & 0x7f7f7f7fu;
-    unsigned b[16], d[16];
+    unsigned b[8], d[8];
 #define RING(k, word) do { const unsigned r_ = (word); b[k] = swar_gt(r_, hi, nhi7); d[k] = swar_lt(r_, lo, lo7); } while (0)
     RING(0, W[3 * rs]);
-    RING(8, W[-3 * rs]);
+    RING(4, W[-3 * rs]);
     {
         const unsigned l = W[-1], r = W[1];
-        RING(4, __funnelshift_r(v, r, 24));
-        RING(12, __funnelshift_r(l, v, 8));
+        RING(2, __funnelshift_r(v, r, 24));
+        RING(6, __funnelshift_r(l, v, 8));
     }
-    unsigned pb = (b[0] | b[8]) & (b[4] | b[12]), pd = (d[0] | d[8]) & (d[4] | d[12]);
+    // two adjacent compass points of one polarity are necessary: (0|8)&(4|12) in ring numbering
+    unsigned pb = (b[0] | b[4]) & (b[2] | b[6]), pd = (d[0] | d[4]) & (d[2] | d[6]);
     if (((pb | pd) & valid) == 0) return 0;
     {
         const unsigned* p = W + 2 * rs; const unsigned* q = W - 2 * rs;
-        RING(2, __funnelshift_r(p[0], p[1], 16));
-        RING(14, __funnelshift_r(p[-1], p[0], 16));
-        RING(6, __funnelshift_r(q[0], q[1], 16));
-        RING(10, __funnelshift_r(q[-1], q[0], 16));
-    }
-    pb &= (b[2] | b[10]) & (b[6] | b[14]); pd &= (d[2] | d[10]) & (d[6] | d[14]);
-    if (((pb | pd) & valid) == 0) return 0;
-    {
-        const unsigned* p = W + 3 * rs; const unsigned* q = W - 3 * rs;
-        RING(1, __funnelshift_r(p[0], p[1], 8));
-        RING(15, __funnelshift_r(p[-1], p[0], 24));
-        RING(7, __funnelshift_r(q[0], q[1], 8));
-        RING(9, __funnelshift_r(q[-1], q[0], 24));
-        p = W + rs; q = W - rs;
-        RING(3, __funnelshift_r(p[0], p[1], 24));
-        RING(13, __funnelshift_r(p[-1], p[0], 8));
-        RING(5, __funnelshift_r(q[0], q[1], 24));
-        RING(11, __funnelshift_r(q[-1], q[0], 8));
+        RING(1, __funnelshift_r(p[0], p[1], 16));
+        RING(7, __funnelshift_r(p[-1], p[0], 16));
+        RING(3, __funnelshift_r(q[0], q[1], 16));
+        RING(5, __funnelshift_r(q[-1], q[0], 16));
     }
 #undef RING
-    pb &= (b[1] | b[9]) & (b[3] | b[11]) & (b[5] | b[13]) & (b[7] | b[15]);
-    pd &= (d[1] | d[9]) & (d[3] | d[11]) & (d[5] | d[13]) & (d[7] | d[15]);
     unsigned out = 0;
-    if (pb & valid) {
-        unsigned c3[16];
+    {
+        unsigned p2[8];
 #pragma unroll
-        for (int k = 0; k < 16; k++) c3[k] = b[k] & b[(k + 1) & 15] & b[(k + 2) & 15];
+        for (int k = 0; k < 8; k++) p2[k] = b[k] & b[(k + 1) & 7];
 #pragma unroll
-        for (int k = 0; k < 16; k++) out |= c3[k] & c3[(k + 3) & 15] & c3[(k + 6) & 15];
+        for (int k = 0; k < 8; k++) out |= p2[k] & p2[(k + 2) & 7];
     }
-    if (pd & valid) {
-        unsigned c3[16];
+    {
+        unsigned p2[8];
 #pragma unroll
-        for (int k = 0; k < 16; k++) c3[k] = d[k] & d[(k + 1) & 15] & d[(k + 2) & 15];
+        for (int k = 0; k < 8; k++) p2[k] = d[k] & d[(k + 1) & 7];
 #pragma unroll
-        for (int k = 0; k < 16; k++) out |= c3[k] & c3[(k + 3) & 15] & c3[(k + 6) & 15];
+        for (int k = 0; k < 8; k++) out |= p2[k] & p2[(k + 2) & 7];
     }
-    return out & valid;
+    return out & valid & 0x80808080u;
 }
 
 __global__ void __launch_bounds__(256)
@@ -315,13 +307,13 @@ k_fast(const CUtensorMap* __restrict__ tmaps, const unsigned* __restrict__ tile_
     __shared__ __align__(8) uint64_t s_mbar;
     __shared__ unsigned s_colvalid[FAST_CH][64];
     __shared__ unsigned char s_xcell[FAST_CW * 64 + 8];       // cell column of every pixel column of the tile
-    __shared__ int s_ng, s_nq, s_surv[FAST_CW * FAST_CH];
-    __shared__ unsigned char s_rowact[2][8];     // [cell row][cell col] evaluated in this pass
+    __shared__ int s_surv[FAST_CW * FAST_CH];
+    __shared__ unsigned s_rcpg;
 
     const unsigned te = __ldg(tile_tab + blockIdx.x);     // level | cy0 << 4 | cx0 << 16
     const int level = te & 15, cy0 = (te >> 4) & 0xFFF, cx0 = te >> 16;
     const LevelInfo& L = P.lv[level];
-    const int f = blockIdx.y, tid = threadIdx.x, lane = tid & 31;
+    const int f = blockIdx.y, tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
     const int ncx = min(FAST_CW, L.ncols - cx0), ncy = min(FAST_CH, L.nrows - cy0);
     const int xend = L.w - EDGE, yend = L.h - EDGE;
     const int X0 = EDGE + cx0 * L.wcell, X1 = min(EDGE + (cx0 + ncx) * L.wcell, xend);
@@ -330,8 +322,9 @@ k_fast(const CUtensorMap* __restrict__ tmaps, const unsigned* __restrict__ tile_
     const int irow = P.f_irow, srow = P.f_srow;           // shared-memory strides (bytes) from the plan
     unsigned* s_img = reinterpret_cast<unsigned*>(s_fast);
     uint8_t* s_score = s_fast + (size_t)irow * P.f_irows;
-    unsigned short* s_gq = reinterpret_cast<unsigned short*>(s_score + (size_t)srow * P.f_srows);
-    unsigned short* s_queue = s_gq + P.f_gcap;
+    // per-warp queues: every warp filters its own share of the tile through B1 -> B2 -> C without a CTA barrier
+    unsigned short* gq = reinterpret_cast<unsigned short*>(s_score + (size_t)srow * P.f_srows) + warp * P.f_gw;   // groups, later corners
+    unsigned short* pq = reinterpret_cast<unsigned short*>(s_score + (size_t)srow * P.f_srows) + FAST_WARPS * P.f_gw + warp * 4 * P.f_gw;   // candidate pixels
 
     const int gx0 = X0 & ~3, gxe = (X1 - 1) & ~3;         // first / last 4-pixel group (image coords)
     const int ngx = ((gxe - gx0) >> 2) + 1;
@@ -339,23 +332,30 @@ k_fast(const CUtensorMap* __restrict__ tmaps, const unsigned* __restrict__ tile_
     const int ay0 = Y0 - 3;
     const int cofs = (gx0 - 4 - ax0) >> 2;                // word column of the first group's left neighbour
     const int rsw = irow >> 2;
+    const int wc = L.wcell, hc = L.hcell;
     if (tid < FAST_CW * FAST_CH) s_surv[tid] = 0;
-    for (int i = tid; i < X1 - X0; i += 256) s_xcell[i] = (unsigned char)min(i / L.wcell, FAST_CW - 1);
+    for (int i = tid; i < X1 - X0; i += 256) s_xcell[i] = (unsigned char)((i >= wc) + (i >= 2 * wc) + (i >= 3 * wc));
+    static_assert(FAST_CW == 4 && FAST_CH == 2, "the cell arithmetic below is written for 4 x 2 cells");
     // A: stage the tile with one TMA box load (zero-filled outside the padded plane); the box is the plan's
     //    largest tile, so every CTA issues the same shape
     if (tid == 0) { mbar_init(&s_mbar, 1); mbar_fence_init(); }
+    if (tid == 32) s_rcpg = 0xFFFFFFFFu / (unsigned)ngx + 1u;     // one division per CTA, not per thread
     __syncthreads();
     if (tid == 0) {
         mbar_arrive_expect_tx(&s_mbar, (unsigned)(irow * P.f_irows));
         tma_load_3d(s_img, tmaps + level, ax0 + EDGE, ay0 + EDGE, f, &s_mbar);
     }
+    // score map: pixel (x, y) of cell (ci, cj) lives at row (y - Y0) + 1 + ci, column (x - X0) + 1 + cj, i.e. cells are
+    // separated by one row / column that stays 0, so the cell-local NMS reads its 8 neighbours unconditionally
     for (int i = tid; i < (srow * P.f_srows) >> 2; i += 256) reinterpret_cast<unsigned*>(s_score)[i] = 0;
     mbar_wait(&s_mbar, 0);
     const int nrows = Y1 - Y0, ngroups = ngx * nrows;
-    const unsigned rcpg = 0xFFFFFFFFu / (unsigned)ngx + 1u;
-    const unsigned rcps = 0xFFFFFFFFu / (unsigned)srow + 1u;
+    const unsigned rcpg = s_rcpg;
+    const unsigned rcps = P.f_rcp_srow;
+    const unsigned ltmask = (1u << lane) - 1u;
     int* gcount = cand_count + (size_t)f * P.nlevels + level;
     unsigned* gdst = cand + (size_t)f * P.raw_per_frame + L.raw_off;
+    const uint8_t* img8 = reinterpret_cast<const uint8_t*>(s_img) + 3 * irow + (X0 - ax0);    // pixel (X0, Y0)
 
     for (int pass = 0; pass < 2; pass++) {
         const int t = pass ? P.t2 : P.t1;
@@ -366,22 +366,24 @@ k_fast(const CUtensorMap* __restrict__ tmaps, const unsigned* __restrict__ tile_
             mine = i < ncy && j < ncx && (pass == 0 || s_surv[tid] == 0);
         }
         if (!__syncthreads_or(mine)) break;                // also orders staging / the previous pass (uniform exit)
-        if (tid < FAST_CW * FAST_CH) s_rowact[tid / FAST_CW][tid % FAST_CW] = mine ? 1 : 0;
-        if (tid == 0) { s_ng = 0; s_nq = 0; }
-        __syncthreads();
         if (tid < FAST_CH * 64) {                           // byte masks per (cell row, group column): inside [X0,X1) and cell active
             const int ci = tid >> 6, c = tid & 63;
             unsigned m = 0;
-            if (c < ngx)
+            if (c < ngx && ci < ncy)
                 for (int bb = 0; bb < 4; bb++) {
                     const int x = gx0 + 4 * c + bb;
-                    if (x >= X0 && x < X1 && s_rowact[ci][s_xcell[x - X0]]) m |= 0x80u << (8 * bb);
+                    if (x >= X0 && x < X1) {
+                        const int cj = s_xcell[x - X0];
+                        if (pass == 0 || s_surv[ci * FAST_CW + cj] == 0) m |= 0x80u << (8 * bb);
+                    }
                 }
             s_colvalid[ci][c] = m;
         }
-        // B1: compass pre-test over all groups, survivors compacted into s_gq
+        __syncthreads();
+        // B1: compass pre-test over this warp's groups, survivors compacted into gq
         const bool t_low = t < 128;
         const unsigned k7 = (unsigned)(0x7f - (t & 0x7f)) * 0x01010101u;
+        int ngw = 0;
         for (int g0 = 0; g0 < ngroups; g0 += 256) {
             const int g = g0 + tid;
             unsigned pf = 0;
@@ -390,97 +392,112 @@ k_fast(const CUtensorMap* __restrict__ tmaps, const unsigned* __restrict__ tile_
                 pf = fast_pre4(s_img + (r + 3) * rsw + (cofs + c + 1), rsw, k7, t_low);
             }
             const unsigned bal = __ballot_sync(0xFFFFFFFFu, pf != 0);
-            if (bal) {
-                int base = 0;
-                if (lane == 0) base = atomicAdd(&s_ng, __popc(bal));
-                base = __shfl_sync(0xFFFFFFFFu, base, 0);
-                if (pf) s_gq[base + __popc(bal & ((1u << lane) - 1))] = (unsigned short)g;
-            }
+            if (pf) gq[ngw + __popc(bal & ltmask)] = (unsigned short)g;
+            ngw += __popc(bal);
         }
-        __syncthreads();
-        const int ng = s_ng;
-        // B2: full SWAR test on the compacted groups
+        __syncwarp();
+        // B2: even-position candidate test on the compacted groups; candidate pixels go to pq as (y - Y0) * srow + (x - X0)
         const unsigned t4 = (unsigned)t * 0x01010101u;
-        for (int g0 = 0; g0 < ng; g0 += 256) {
-            const int gi = g0 + tid;
-            const int g = gi < ng ? s_gq[gi] : 0;
+        int npw = 0;
+        for (int i0 = 0; i0 < ngw; i0 += 32) {
+            const int gi = i0 + lane;
+            const int g = gi < ngw ? gq[gi] : 0;
             const int r = __umulhi((unsigned)g, rcpg), c = g - r * ngx;
-            const unsigned valid = gi < ng ? s_colvalid[(r >= L.hcell) ? 1 : 0][c] : 0u;
-            unsigned cf = valid ? fast_swar4(s_img + (r + 3) * rsw + (cofs + c + 1), rsw, t4, valid) : 0u;
-            // warp-aggregated append of the corner pixels (<= 4 per lane): inclusive scan of the per-lane counts
+            const unsigned valid = gi < ngw ? s_colvalid[(r >= hc) ? 1 : 0][c] : 0u;
+            unsigned cf = valid ? fast_even8(s_img + (r + 3) * rsw + (cofs + c + 1), rsw, t4, valid) : 0u;
+            // warp-aggregated append of the candidate pixels (<= 4 per lane): inclusive scan of the per-lane counts
             const int cnt = __popc(cf);
             int incl = cnt;
 #pragma unroll
             for (int o = 1; o < 32; o <<= 1) { const int v = __shfl_up_sync(0xFFFFFFFFu, incl, o); if (lane >= o) incl += v; }
             const int total = __shfl_sync(0xFFFFFFFFu, incl, 31);
-            if (total) {
-                int base = 0;
-                if (lane == 31) base = atomicAdd(&s_nq, total);
-                base = __shfl_sync(0xFFFFFFFFu, base, 31) + incl - cnt;
-                const int p0 = (r + 1) * srow + (gx0 + 4 * c - X0 + 1);
-                while (cf) {
-                    const int bb = (__ffs(cf) - 1) >> 3;
-                    cf &= cf - 1;
-                    s_queue[base++] = (unsigned short)(p0 + bb);
-                }
+            int base = npw + incl - cnt;
+            const int q0 = r * srow + (gx0 + 4 * c - X0);
+            while (cf) {
+                const int bb = (__ffs(cf) - 1) >> 3;
+                cf &= cf - 1;
+                pq[base++] = (unsigned short)(q0 + bb);
             }
+            npw += total;
         }
-        __syncthreads();
-        const int nq = s_nq;
-        // C: exact score
-        for (int qi = tid; qi < nq; qi += 256) {
-            const int pos = s_queue[qi];
-            const int sy = __umulhi((unsigned)pos, rcps), sx = pos - sy * srow;
-            const uint8_t* pc = reinterpret_cast<const uint8_t*>(s_img) + (sy - 1 + 3) * irow + (sx - 1 + X0 - ax0);
-            const int v = pc[0];
-            int d[16];
-            d[0] = pc[3 * irow] - v;       d[1] = pc[3 * irow + 1] - v;   d[2] = pc[2 * irow + 2] - v;   d[3] = pc[irow + 3] - v;
-            d[4] = pc[3] - v;              d[5] = pc[-irow + 3] - v;      d[6] = pc[-2 * irow + 2] - v;  d[7] = pc[-3 * irow + 1] - v;
-            d[8] = pc[-3 * irow] - v;      d[9] = pc[-3 * irow - 1] - v;  d[10] = pc[-2 * irow - 2] - v; d[11] = pc[-irow - 3] - v;
-            d[12] = pc[-3] - v;            d[13] = pc[irow - 3] - v;      d[14] = pc[2 * irow - 2] - v;  d[15] = pc[3 * irow - 1] - v;
-            int mn3[16], mx3[16];
+        __syncwarp();
+        // C: exact score s = max_arc min_k |ring_k - v| - 1 (== OpenCV cornerScore); the pixel is a corner at t  <=>
+        //    s >= t.  Two queued pixels per lane: their ring values are packed as 16x2 and the arc min / max trees
+        //    run on the DPX three-input SIMD min / max.  Corners are compacted into gq (score-map positions) while they
+        //    fit; pq is rewritten in place (position or 0xFFFF) as the fallback list for a denser warp.
+        int ncw = 0;
+        for (int i0 = 0; i0 < npw; i0 += 64) {
+            const int i = i0 + 2 * lane;
+            const bool h0 = i < npw, h1 = i + 1 < npw;
+            const int qa = h0 ? pq[i] : 0, qb = h1 ? pq[i + 1] : qa;
+            const int rya = __umulhi((unsigned)qa, rcps), rxa = qa - rya * srow;
+            const int ryb = __umulhi((unsigned)qb, rcps), rxb = qb - ryb * srow;
+            const uint8_t* pa = img8 + rya * irow + rxa;
+            const uint8_t* pb = img8 + ryb * irow + rxb;
+            const int va = pa[0], vb = pb[0];
+            unsigned w[16];
+#define PK(k, o) w[k] = (unsigned)pa[o] | ((unsigned)pb[o] << 16)
+            PK(0, 3 * irow);      PK(1, 3 * irow + 1);   PK(2, 2 * irow + 2);   PK(3, irow + 3);
+            PK(4, 3);             PK(5, -irow + 3);      PK(6, -2 * irow + 2);  PK(7, -3 * irow + 1);
+            PK(8, -3 * irow);     PK(9, -3 * irow - 1);  PK(10, -2 * irow - 2); PK(11, -irow - 3);
+            PK(12, -3);           PK(13, irow - 3);      PK(14, 2 * irow - 2);  PK(15, 3 * irow - 1);
+#undef PK
+            unsigned A, Bm;
+            {
+                unsigned m3[16];
 #pragma unroll
-            for (int k = 0; k < 16; k++) {
-                mn3[k] = __vimin3_s32(d[k], d[(k + 1) & 15], d[(k + 2) & 15]);
-                mx3[k] = __vimax3_s32(d[k], d[(k + 1) & 15], d[(k + 2) & 15]);
-            }
-            int A = -256, Bn = 256;
+                for (int k = 0; k < 16; k++) m3[k] = __vimin3_u16x2(w[k], w[(k + 1) & 15], w[(k + 2) & 15]);
+                unsigned m9[16];
 #pragma unroll
-            for (int k = 0; k < 16; k++) {
-                A = max(A, __vimin3_s32(mn3[k], mn3[(k + 3) & 15], mn3[(k + 6) & 15]));
-                Bn = min(Bn, __vimax3_s32(mx3[k], mx3[(k + 3) & 15], mx3[(k + 6) & 15]));
+                for (int k = 0; k < 16; k++) m9[k] = __vimin3_u16x2(m3[k], m3[(k + 3) & 15], m3[(k + 6) & 15]);
+                A = __vimax3_u16x2(m9[0], m9[1], m9[2]);
+#pragma unroll
+                for (int k = 3; k < 15; k += 2) A = __vimax3_u16x2(A, m9[k], m9[k + 1]);
+                A = __vmaxu2(A, m9[15]);
             }
-            s_score[pos] = (uint8_t)(max(A, -Bn) - 1);     // >= t >= 1 for a corner at t
+            {
+                unsigned m3[16];
+#pragma unroll
+                for (int k = 0; k < 16; k++) m3[k] = __vimax3_u16x2(w[k], w[(k + 1) & 15], w[(k + 2) & 15]);
+                unsigned m9[16];
+#pragma unroll
+                for (int k = 0; k < 16; k++) m9[k] = __vimax3_u16x2(m3[k], m3[(k + 3) & 15], m3[(k + 6) & 15]);
+                Bm = __vimin3_u16x2(m9[0], m9[1], m9[2]);
+#pragma unroll
+                for (int k = 3; k < 15; k += 2) Bm = __vimin3_u16x2(Bm, m9[k], m9[k + 1]);
+                Bm = __vminu2(Bm, m9[15]);
+            }
+            const int sca = max((int)(A & 0xFFFFu) - va, va - (int)(Bm & 0xFFFFu)) - 1;
+            const int scb = max((int)(A >> 16) - vb, vb - (int)(Bm >> 16)) - 1;
+            const bool ca = h0 && sca >= t, cb = h1 && scb >= t;
+            // score-map positions (cells separated by the zero row / column)
+            const int posa = qa + (1 + (rya >= hc)) * srow + 1 + (rxa >= wc) + (rxa >= 2 * wc) + (rxa >= 3 * wc);
+            const int posb = qb + (1 + (ryb >= hc)) * srow + 1 + (rxb >= wc) + (rxb >= 2 * wc) + (rxb >= 3 * wc);
+            if (h0) { s_score[posa] = (uint8_t)(ca ? sca : 0); pq[i] = (unsigned short)(ca ? posa : 0xFFFF); }
+            if (h1) { s_score[posb] = (uint8_t)(cb ? scb : 0); pq[i + 1] = (unsigned short)(cb ? posb : 0xFFFF); }
+            const unsigned bala = __ballot_sync(0xFFFFFFFFu, ca), balb = __ballot_sync(0xFFFFFFFFu, cb);
+            const int ia = ncw + __popc(bala & ltmask), ib = ncw + __popc(bala) + __popc(balb & ltmask);
+            if (ca && ia < P.f_gw) gq[ia] = (unsigned short)posa;
+            if (cb && ib < P.f_gw) gq[ib] = (unsigned short)posb;
+            ncw += __popc(bala) + __popc(balb);
         }
-        __syncthreads();
-        // D: strict 3x3 NMS inside the cell (positions outside the cell interior count as 0); append survivors
-        for (int q0 = 0; q0 < nq; q0 += 256) {
-            const int qi = q0 + tid;
+        __syncthreads();                                   // every warp's scores are in the map
+        // D: strict 3x3 NMS inside the cell; append survivors to the (frame, level) raw-corner list
+        const bool fits = ncw <= P.f_gw;                   // warp-uniform
+        const unsigned short* dq = fits ? gq : pq;
+        const int nd = fits ? ncw : npw;
+        for (int i0 = 0; i0 < nd; i0 += 32) {
+            const int i = i0 + lane;
+            const int pos = i < nd ? dq[i] : 0xFFFF;
             bool keep = false; unsigned rec = 0; int cell = 0;
-            if (qi < nq) {
-                const int pos = s_queue[qi];
-                const int sy = __umulhi((unsigned)pos, rcps), sx = pos - sy * srow;
-                const int x = X0 + sx - 1, y = Y0 + sy - 1;
-                const int cj = s_xcell[x - X0], ci = (y - Y0 >= L.hcell) ? 1 : 0;
-                const int cxa = X0 + cj * L.wcell, cxb = min(cxa + L.wcell, X1);
-                const int cya = Y0 + ci * L.hcell, cyb = min(cya + L.hcell, Y1);
-                const int s = s_score[pos];
-                const bool hasL = x > cxa, hasR = x + 1 < cxb, hasU = y > cya, hasD = y + 1 < cyb;
+            if (pos != 0xFFFF) {
                 const uint8_t* sp = s_score + pos;
-                keep = true;
-                if (hasL) keep &= s > sp[-1];
-                if (hasR) keep &= s > sp[1];
-                if (hasU) {
-                    keep &= s > sp[-srow];
-                    if (hasL) keep &= s > sp[-srow - 1];
-                    if (hasR) keep &= s > sp[-srow + 1];
-                }
-                if (hasD) {
-                    keep &= s > sp[srow];
-                    if (hasL) keep &= s > sp[srow - 1];
-                    if (hasR) keep &= s > sp[srow + 1];
-                }
-                rec = (unsigned)x | ((unsigned)y << 12) | ((unsigned)s << 24);
+                const int s = sp[0];
+                keep = s > sp[-1] && s > sp[1] && s > sp[-srow - 1] && s > sp[-srow] && s > sp[-srow + 1] &&
+                       s > sp[srow - 1] && s > sp[srow] && s > sp[srow + 1];
+                const int sy = __umulhi((unsigned)pos, rcps), sx = pos - sy * srow;
+                const int ci = sy > hc + 1, cj = (sx > wc + 1) + (sx > 2 * wc + 2) + (sx > 3 * wc + 3);
+                rec = (unsigned)(X0 + sx - 1 - cj) | ((unsigned)(Y0 + sy - 1 - ci) << 12) | ((unsigned)s << 24);
                 cell = ci * FAST_CW + cj;
             }
             const unsigned bal = __ballot_sync(0xFFFFFFFFu, keep);
@@ -489,7 +506,7 @@ k_fast(const CUtensorMap* __restrict__ tmaps, const unsigned* __restrict__ tile_
                 if (lane == 0) base = atomicAdd(gcount, __popc(bal));
                 base = __shfl_sync(0xFFFFFFFFu, base, 0);
                 if (keep) {
-                    const int o = base + __popc(bal & ((1u << lane) - 1));
+                    const int o = base + __popc(bal & ltmask);
                     if (o < L.raw_cap) gdst[o] = rec; else atomicOr(status, 1);
                     s_surv[cell] = 1;                      // only "any survivor" matters: plain store, every writer stores 1
                 }
@@ -1239,8 +1256,10 @@ static int make_plan(const uvip_extractor* ex, int w, int h, Plan* out, std::vec
     {
         const int ngx_max = (max_tw + 2) / 4 + 1;
         P.f_irow = (int)align_up((size_t)4 * (ngx_max + 2) + 12, 16); P.f_irows = max_th + 6;   // TMA box: 16-byte aligned start and extent
-        P.f_srow = (int)align_up((size_t)max_tw + 2, 4); P.f_srows = max_th + 2;
-        P.f_gcap = (ngx_max * max_th + 1) & ~1; P.f_qcap = (max_tw * max_th + 1) & ~1;
+        P.f_srow = (int)align_up((size_t)max_tw + 2 + FAST_CW, 4); P.f_srows = max_th + 2 + FAST_CH;   // one zero row / column between cells
+        P.f_rcp_srow = 0xFFFFFFFFu / (unsigned)P.f_srow + 1u;
+        P.f_gw = 32 * div_up(ngx_max * max_th, 32 * FAST_WARPS);           // groups one warp can meet
+        if ((size_t)P.f_srow * P.f_srows >= 0xFFFFu) { set_last_error("FAST tile does not fit 16-bit positions"); return UVIP_ERR_UNSUPPORTED; }
     }
     P.rcp_cpr = 0xFFFFFFFFu / (unsigned)((P.lv[0].w + 15) >> 4) + 1u;
     {
@@ -1287,7 +1306,7 @@ static int make_plan(const uvip_extractor* ex, int w, int h, Plan* out, std::vec
     return UVIP_OK;
 }
 
-static size_t fast_smem_bytes(const Plan& P) { return (size_t)P.f_irow * P.f_irows + (size_t)P.f_srow * P.f_srows + 2 * (size_t)P.f_gcap + 2 * (size_t)P.f_qcap + 128; }
+static size_t fast_smem_bytes(const Plan& P) { return (size_t)P.f_irow * P.f_irows + (size_t)P.f_srow * P.f_srows + 2 * (size_t)FAST_WARPS * 5 * P.f_gw + 128; }
 static size_t qt_smem_bytes(int cap) { return (size_t)(4 * cap * 2 + cap * 2 + 4 * cap + cap + cap + (cap + 1) + cap + 4 * cap + cap + cap + cap) * 4; }
 
 static int ensure_plan(uvip_extractor* ex, int w, int h)
