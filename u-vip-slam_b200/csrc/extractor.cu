@@ -982,7 +982,10 @@ __device__ __forceinline__ void sincos_as_float(float xf, float* s_out, float* c
 }
 
 constexpr int DESC_WARPS = 8, DESC_KPW = 4;           // warps per CTA, keypoints per warp
-__global__ void __launch_bounds__(DESC_WARPS * 32)
+#ifndef DESC_MINB
+#define DESC_MINB 4          // 64 registers: four CTAs per SM (the kernel is latency-bound; measured 0.37 -> 0.27 ms at batch 256)
+#endif
+__global__ void __launch_bounds__(DESC_WARPS * 32, DESC_MINB)
 k_describe(const uint8_t* __restrict__ pyr, const uint8_t* __restrict__ blur, const unsigned* __restrict__ winners,
            const unsigned* __restrict__ sel, const int* __restrict__ nsel, int sel_cap,
            const uvip_keypoint* __restrict__ incoming, const float2* __restrict__ pat_t,
@@ -994,11 +997,13 @@ k_describe(const uint8_t* __restrict__ pyr, const uint8_t* __restrict__ blur, co
     const int n = nsel[f];
     if (blockIdx.x == 0 && threadIdx.x == 0) { n_out[f] = n; if (n > out_cap) atomicOr(status, 8); }
     const int slot0 = (blockIdx.x * DESC_WARPS + (threadIdx.x >> 5)) * DESC_KPW;
+    if ((int)(blockIdx.x * DESC_WARPS * DESC_KPW) >= n) return;          // whole CTA idle (uniform)
+    // pattern in shared memory, transposed [k][lane]: lane reads its 16 points (descriptor byte `lane`) conflict-free,
+    // which keeps the kernel at 64 registers (occupancy matters more than the 16 LDS: the kernel is latency-bound)
+    __shared__ float2 s_pat[512];
+    for (int i = threadIdx.x; i < 512; i += DESC_WARPS * 32) s_pat[i] = __ldg(pat_t + i);
+    __syncthreads();
     if (slot0 >= n) return;
-    // this lane's 16 pattern points (descriptor byte `lane`), transposed table [k][lane] -> coalesced loads, kept in registers
-    float px[16], py[16];
-#pragma unroll
-    for (int k = 0; k < 16; k++) { const float2 p = __ldg(pat_t + k * 32 + lane); px[k] = p.x; py[k] = p.y; }
     const int u = lane - HALF_PATCH;
     const int vm = lane < 31 ? c_umax[u < 0 ? -u : u] : -1;       // disc rows |v| <= vm belong to column u (umax is symmetric)
 #pragma unroll 1
@@ -1045,7 +1050,8 @@ k_describe(const uint8_t* __restrict__ pyr, const uint8_t* __restrict__ blur, co
         unsigned val = 0;
 #pragma unroll
         for (int k = 0; k < 8; k++) {
-            const float x0 = px[2 * k], y0 = py[2 * k], x1 = px[2 * k + 1], y1 = py[2 * k + 1];
+            const float2 p0 = s_pat[(2 * k) * 32 + lane], p1 = s_pat[(2 * k + 1) * 32 + lane];
+            const float x0 = p0.x, y0 = p0.y, x1 = p1.x, y1 = p1.y;
             const int r0 = __float2int_rn(__fadd_rn(__fmul_rn(x0, b), __fmul_rn(y0, a))), q0 = __float2int_rn(__fsub_rn(__fmul_rn(x0, a), __fmul_rn(y0, b)));
             const int r1 = __float2int_rn(__fadd_rn(__fmul_rn(x1, b), __fmul_rn(y1, a))), q1 = __float2int_rn(__fsub_rn(__fmul_rn(x1, a), __fmul_rn(y1, b)));
             const int t0 = __ldg(cb + (r0 * ps + q0)), t1 = __ldg(cb + (r1 * ps + q1));
