@@ -490,6 +490,22 @@ def run_next(args):
     P0 = O.LKPyramid(a_img, 21, 5); P1 = O.LKPyramid(b_img, 21, 5); O.lk_track(P0, P1, p0, p0, 21, 5, 30, 0.01, 8)
     tc = time.perf_counter() - t0
     out['klt'] = {'frame_pairs_per_s_e2e': 1.0 / tg, 'points': len(p0), 'tracked': int(st.sum()), 'cpu_oracle_frame_pairs_per_s_1thread': 1.0 / tc}
+    # ---- N4 (descriptor half): batched MapPoint::ComputeDistinctiveDescriptors, 100k map points with 2..30 observations
+    rng = np.random.default_rng(4)
+    sizes = rng.integers(2, 31, 100000)
+    start = np.zeros(len(sizes) + 1, np.int32); start[1:] = np.cumsum(sizes)
+    dd = pkg.synth.random_descriptors(8, int(start[-1]))
+    mm = pkg.ORBmatcher(0.6, True, device=0)
+    mm.distinctive_descriptors(dd, start)
+    tg = time.perf_counter()
+    for _ in range(K):
+        bi, _ = mm.distinctive_descriptors(dd, start)
+    tg = (time.perf_counter() - tg) / K
+    ns = 5000
+    tc = time.perf_counter(); obi, _ = O.distinctive_descriptors(dd[:start[ns]], start[:ns + 1]); tc = time.perf_counter() - tc
+    assert np.array_equal(bi[:ns], obi)
+    out['distinctive_descriptors'] = {'map_points_per_s_e2e': len(sizes) / tg, 'observations': int(start[-1]),
+                                      'cpu_oracle_map_points_per_s_1thread': ns / tc}
     print(json.dumps(out), flush=True)
     return 0
 

@@ -209,6 +209,13 @@ int   uvip_search_window(uvip_matcher* m, const uvip_search_params* sp,
 int   uvip_search_lists(uvip_matcher* m, int mode, int th_dist, float ratio, const uint8_t* qdesc, int nq,
                         const int32_t* cand_start, const int32_t* cand_idx, const uint8_t* kdesc, int nk,
                         int32_t* taken, int32_t* match, int* nmatches);
+/* next row N4, the descriptor half: MapPoint::ComputeDistinctiveDescriptors (src/MapPoint.cc:197-270) for a
+ * batch of map points.  The observed descriptors of point p are rows start[p] .. start[p+1]-1 of desc (start[0] == 0).
+ * best_idx[p] = index inside the point's own list of the descriptor with the least median Hamming distance to the
+ * others (sorted row element floor((N-1)/2), diagonal included; first index on ties, :250-264), best_median[p] that
+ * median (may be NULL); both -1 for a point without descriptors.  Host buffers. */
+int   uvip_distinctive_descriptors(uvip_matcher* m, const uint8_t* desc, const int32_t* start, int npoints,
+                                   int32_t* best_idx, int32_t* best_median);
 /* ORBmatcher::RadiusByViewingCos (src/ORBmatcher.cc:127-133) */
 float uvip_radius_by_viewing_cos(float view_cos);
 

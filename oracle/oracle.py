@@ -216,6 +216,15 @@ def descriptor_distance(a, b):
     return int(lib().uo_descriptor_distance(_p(a), _p(b)))
 
 
+def distinctive_descriptors(desc, start):
+    """MapPoint::ComputeDistinctiveDescriptors over ragged lists (rows start[p]..start[p+1]-1) -> (best_idx, best_median)"""
+    desc = np.ascontiguousarray(desc, np.uint8).reshape(-1, 32); start = np.ascontiguousarray(start, np.int32)
+    n = len(start) - 1
+    bi = np.zeros(n, np.int32); bm = np.zeros(n, np.int32)
+    lib().uo_distinctive_descriptors(_p(desc), _p(start), n, _p(bi), _p(bm))
+    return bi, bm
+
+
 def knn2(q, t, threads=0):
     q = np.ascontiguousarray(q, np.uint8); t = np.ascontiguousarray(t, np.uint8)
     nq, nt = len(q), len(t)

@@ -1152,3 +1152,25 @@ void uo_lk_track(const void* P0_, const void* P1_, const float* prev_pts, float*
     }
     free(Iw); free(dIw);
 }
+
+/* MapPoint::ComputeDistinctiveDescriptors, src/MapPoint.cc:236-264: N x N distances, per row the sorted row's element
+ * (size_t)(0.5*(N-1)), the row with the least median wins (strict <, so the first).  scratch-free, O(N^2 log N). */
+static int cmp_int(const void* a, const void* b) { return *(const int*)a - *(const int*)b; }
+void uo_distinctive_descriptors(const uint8_t* desc, const int32_t* start, int npoints, int32_t* best_idx, int32_t* best_median)
+{
+    for (int p = 0; p < npoints; p++) {
+        const int N = start[p + 1] - start[p];
+        const uint8_t* D = desc + (size_t)start[p] * 32;
+        if (N <= 0) { best_idx[p] = -1; if (best_median) best_median[p] = -1; continue; }
+        int* row = (int*)malloc(sizeof(int) * (size_t)N);
+        int BestMedian = 0x7fffffff, BestIdx = 0;
+        for (int i = 0; i < N; i++) {
+            for (int j = 0; j < N; j++) row[j] = (i == j) ? 0 : uo_descriptor_distance(D + (size_t)i * 32, D + (size_t)j * 32);
+            qsort(row, (size_t)N, sizeof(int), cmp_int);
+            const int median = row[(size_t)(0.5 * (N - 1))];
+            if (median < BestMedian) { BestMedian = median; BestIdx = i; }
+        }
+        free(row);
+        best_idx[p] = BestIdx; if (best_median) best_median[p] = BestMedian;
+    }
+}

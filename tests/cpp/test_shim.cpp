@@ -109,6 +109,15 @@ int main(int argc, char** argv)
         std::vector<int> bowner((size_t)n, -1);
         for (int i = 0; i < n; i++) if (vm[i]) bowner[i] = (int)(vm[i] - kfmps.data());
         put(fo, bowner.data(), (size_t)n * 4);
+        // 5. MapPoint::ComputeDistinctiveDescriptors batched: list p = descriptor rows p, p+7, p+14, ... (1 + p % 9 of them)
+        const int np = n < 64 ? n : 64;
+        std::vector<std::vector<cv::Mat> > lists((size_t)np);
+        for (int p = 0; p < np; p++)
+            for (int j = 0; j < 1 + p % 9; j++) lists[(size_t)p].push_back(desc.row((p + 7 * j) % n));
+        std::vector<int> best;
+        bow.ComputeDistinctiveDescriptors(lists, best);
+        put(fo, &np, 4);
+        put(fo, best.data(), (size_t)np * 4);
     } catch (const std::exception& e) {
         fprintf(stderr, "shim error: %s\n", e.what());
         fclose(fo);

@@ -127,3 +127,10 @@ def test_shim_matches_oracle(pkg, oracle, synth, shim_exe, tmp_path):
             expect[k] = queries[qi]
     assert nb == int((omatch >= 0).sum()) and nb > 300
     assert np.array_equal(bowner, expect)
+    # 5. ComputeDistinctiveDescriptors batched through the shim (uses the shim's own descriptors, 99.9 % equal to the oracle's)
+    npnt = int(take(np.int32, 1)[0]); best = take(np.int32, npnt)
+    sizes = [1 + p % 9 for p in range(npnt)]
+    start = np.zeros(npnt + 1, np.int32); start[1:] = np.cumsum(sizes)
+    rows = np.concatenate([desc[[(p + 7 * j) % n for j in range(sizes[p])]] for p in range(npnt)])
+    obest, _ = oracle.distinctive_descriptors(rows, start)
+    assert npnt == 64 and np.array_equal(best, obest)

@@ -399,3 +399,38 @@ def test_clahe_preprocessing(gpu, oracle, synth, golden):
     kps, desc = ex(ex.clahe(img))
     okps, odesc = oracle.Extractor(1000, 1.2, 8, 1, 20)(oracle.clahe(img))
     assert np.array_equal(kps['x'], okps['x']) and np.array_equal(kps['y'], okps['y']) and np.array_equal(desc, odesc)
+
+
+def _distinctive_case(synth, seed=5):
+    """ragged map-point observation lists: N = 0, 1, 2, 3, ... incl. > 32 and > 64, clustered descriptors + exact duplicates"""
+    rng = np.random.default_rng(seed)
+    sizes = [0, 1, 2, 3, 4, 5, 7, 8, 16, 31, 32, 33, 40, 64, 65, 100, 2, 6] + list(rng.integers(1, 20, 200))
+    start = np.zeros(len(sizes) + 1, np.int32); start[1:] = np.cumsum(sizes)
+    base = synth.random_descriptors(seed, len(sizes))
+    rows = []
+    for p, n in enumerate(sizes):
+        if n == 0:
+            continue
+        d = np.repeat(base[p:p + 1], n, 0)
+        d = synth.flip_bits(d, seed * 1000 + p, [int(v) for v in rng.integers(0, 60, n)])
+        if n >= 4:
+            d[n - 1] = d[0]                                  # exact duplicates -> zero distances and median ties
+        rows.append(d)
+    return np.concatenate(rows), start
+
+
+def test_distinctive_descriptors_batch(gpu, oracle, synth):
+    """next row N4 (descriptor half): MapPoint::ComputeDistinctiveDescriptors, src/MapPoint.cc:197-270; bit-exact"""
+    desc, start = _distinctive_case(synth)
+    m = gpu.ORBmatcher(0.6, True)
+    bi, bm = m.distinctive_descriptors(desc, start)
+    obi, obm = oracle.distinctive_descriptors(desc, start)
+    assert np.array_equal(bi, obi) and np.array_equal(bm, obm)
+    assert bi[0] == -1 and bi[1] == 0 and bm[1] == 0
+    # size-independent property: the least median does not depend on the order of a point's observations
+    p = 15                                                   # N = 100
+    sl = slice(start[p], start[p + 1])
+    perm = np.random.default_rng(1).permutation(100)
+    d2 = desc.copy(); d2[sl] = desc[sl][perm]
+    bi2, bm2 = m.distinctive_descriptors(d2, start)
+    assert bm2[p] == bm[p] and np.array_equal(np.delete(bm2, p), np.delete(bm, p))

@@ -64,6 +64,7 @@ def lib():
         L.uvip_extractor_tables.argtypes = [vp, vp, vp, vp, vp]
         L.uvip_extract.argtypes = [vp, vp, i, i, i, vp, C.POINTER(i), i, vp, vp, i, i, i, i, i]
         L.uvip_extract_batch.argtypes = [vp, vp, i, i, i, i, sz, vp, vp, i, vp]
+        L.uvip_distinctive_descriptors.argtypes = [vp, vp, vp, i, vp, vp]
         L.uvip_extract_batch_submit.argtypes = [vp, vp, i, i, i, i, sz, vp, vp, i, vp, C.POINTER(i)]
         L.uvip_extract_batch_wait.argtypes = [vp, i]
         L.uvip_extract_batch_device.argtypes = [vp, vp, i, i, i, i, sz, vp, vp, i, vp, vp]

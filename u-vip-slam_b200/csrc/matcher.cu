@@ -188,6 +188,45 @@ __global__ void k_descriptor_distance(const uint8_t* __restrict__ a, const uint8
              __popc(v.x ^ y.x) + __popc(v.y ^ y.y) + __popc(v.z ^ y.z) + __popc(v.w ^ y.w);
 }
 
+// N4: MapPoint::ComputeDistinctiveDescriptors (src/MapPoint.cc:236-264) for a batch of map points, one warp per point.
+// Lane i owns row i of the N x N distance matrix; its median (sorted row, element floor((N-1)/2), the diagonal 0
+// included) is found by a 9-step bisection on the distance value, every step recounting the row (row j is a broadcast
+// load for the whole warp), so no N-sized storage exists and N is unbounded.  Winner = least median, first on ties.
+__global__ void k_distinctive(const uint8_t* __restrict__ desc, const int32_t* __restrict__ start, int npoints,
+                              int32_t* __restrict__ best_idx, int32_t* __restrict__ best_median)
+{
+    const int p = (int)((blockIdx.x * (size_t)blockDim.x + threadIdx.x) >> 5), lane = threadIdx.x & 31;
+    if (p >= npoints) return;
+    const int s0 = start[p], N = start[p + 1] - s0;
+    if (N <= 0) { if (lane == 0) { best_idx[p] = -1; best_median[p] = -1; } return; }
+    const int k1 = ((N - 1) >> 1) + 1;                     // the median has at least k1 row elements <= it
+    const uint4* rows = reinterpret_cast<const uint4*>(desc + (size_t)s0 * 32);
+    unsigned bestkey = 0xFFFFFFFFu;
+    for (int i0 = 0; i0 < N; i0 += 32) {
+        const int i = i0 + lane;
+        const bool act = i < N;
+        const uint4 a0 = __ldg(rows + 2 * (act ? i : 0)), a1 = __ldg(rows + 2 * (act ? i : 0) + 1);
+        int lo = 0, hi = 256;
+#pragma unroll 1
+        for (int it = 0; it < 9; it++) {
+            const int mid = (lo + hi) >> 1;
+            int cnt = 0;
+            for (int j = 0; j < N; j++) {
+                const uint4 b0 = __ldg(rows + 2 * j), b1 = __ldg(rows + 2 * j + 1);
+                const int d = __popc(a0.x ^ b0.x) + __popc(a0.y ^ b0.y) + __popc(a0.z ^ b0.z) + __popc(a0.w ^ b0.w) +
+                              __popc(a1.x ^ b1.x) + __popc(a1.y ^ b1.y) + __popc(a1.z ^ b1.z) + __popc(a1.w ^ b1.w);
+                cnt += d <= mid;
+            }
+            if (cnt >= k1) hi = mid; else lo = mid + 1;
+        }
+        const unsigned key = act ? ((unsigned)lo << 16 | (unsigned)i) : 0xFFFFFFFFu;
+        bestkey = min(bestkey, key);
+    }
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) bestkey = min(bestkey, __shfl_xor_sync(0xFFFFFFFFu, bestkey, o));
+    if (lane == 0) { best_idx[p] = (int)(bestkey & 0xFFFFu); best_median[p] = (int)(bestkey >> 16); }
+}
+
 // ratio test, include/utils.h:104-108 (float distances, double ratio)
 __global__ void k_ratio_filter(const int32_t* __restrict__ idx2, const int32_t* __restrict__ dist2, int nq, double ratio,
                                int32_t* __restrict__ match, int* __restrict__ nmatches)
@@ -674,6 +713,33 @@ int uvip_descriptor_distance(uvip_matcher* m, const uint8_t* a, const uint8_t* b
     m->launches++;
     UVIP_CUDA(cudaGetLastError());
     UVIP_CUDA(cudaMemcpyAsync(out, m->idx.p, (size_t)n * 4, cudaMemcpyDeviceToHost, m->stream));
+    UVIP_CUDA(cudaStreamSynchronize(m->stream));
+    return UVIP_OK;
+}
+
+int uvip_distinctive_descriptors(uvip_matcher* m, const uint8_t* desc, const int32_t* start, int npoints,
+                                 int32_t* best_idx, int32_t* best_median)
+{
+    UVIP_CHECK_ARG(m && npoints >= 0);
+    if (npoints == 0) return UVIP_OK;
+    UVIP_CHECK_ARG(start && best_idx);
+    const int total = start[npoints];
+    UVIP_CHECK_ARG(start[0] == 0 && total >= 0 && (total == 0 || desc));
+    for (int p = 0; p < npoints; p++) UVIP_CHECK_ARG(start[p + 1] >= start[p] && start[p + 1] - start[p] <= 65535);
+    std::lock_guard<std::mutex> lk(m->mu);
+    DeviceGuard g(m->device);
+    int rc;
+    if ((rc = m->t.reserve((size_t)total * 32 + 32))) return rc;
+    if ((rc = m->idx.reserve((size_t)(npoints + 1) * 4))) return rc;
+    if ((rc = m->dist.reserve((size_t)npoints * 8))) return rc;
+    if (total) UVIP_CUDA(cudaMemcpyAsync(m->t.p, desc, (size_t)total * 32, cudaMemcpyHostToDevice, m->stream));
+    UVIP_CUDA(cudaMemcpyAsync(m->idx.p, start, (size_t)(npoints + 1) * 4, cudaMemcpyHostToDevice, m->stream));
+    int32_t* d_best = m->dist.as<int32_t>();
+    k_distinctive<<<div_up(npoints, 4), 128, 0, m->stream>>>(m->t.as<uint8_t>(), m->idx.as<int32_t>(), npoints, d_best, d_best + npoints);
+    m->launches++;
+    UVIP_CUDA(cudaGetLastError());
+    UVIP_CUDA(cudaMemcpyAsync(best_idx, d_best, (size_t)npoints * 4, cudaMemcpyDeviceToHost, m->stream));
+    if (best_median) UVIP_CUDA(cudaMemcpyAsync(best_median, d_best + npoints, (size_t)npoints * 4, cudaMemcpyDeviceToHost, m->stream));
     UVIP_CUDA(cudaStreamSynchronize(m->stream));
     return UVIP_OK;
 }

@@ -189,6 +189,15 @@ class ORBmatcher:
         check(lib().uvip_knn2(self.h, ptr(q), len(q), ptr(t), len(t), ptr(idx), ptr(dist)))
         return idx, dist
 
+    def distinctive_descriptors(self, desc, start):
+        """MapPoint::ComputeDistinctiveDescriptors (src/MapPoint.cc:197-270) for a batch of map points: the observed
+        descriptors of point p are rows start[p]..start[p+1]-1 of desc.  Returns (best index inside each list, its median)"""
+        desc = np.ascontiguousarray(desc, np.uint8).reshape(-1, 32); start = np.ascontiguousarray(start, np.int32)
+        n = len(start) - 1
+        bi = np.zeros(n, np.int32); bm = np.zeros(n, np.int32)
+        check(lib().uvip_distinctive_descriptors(self.h, ptr(desc), ptr(start), n, ptr(bi), ptr(bm)))
+        return bi, bm
+
     def ratio_filter(self, idx, dist, ratio=None):
         idx = np.ascontiguousarray(idx, np.int32); dist = np.ascontiguousarray(dist, np.int32)
         m = np.zeros(len(idx), np.int32); n = C.c_int()

@@ -152,6 +152,26 @@ public:
         return n;
     }
 
+    // MapPoint::ComputeDistinctiveDescriptors (src/MapPoint.cc:197-270) for a batch of map points: lists[p] holds the
+    // observed descriptors (1 x 32 CV_8U rows) of point p; best[p] = index of the descriptor the reference would keep
+    // as mDescriptor (-1 for an empty list).  LocalMapping / LoopClosing call it once per touched map point; gathering
+    // the touched points of a keyframe insertion into one call is the batched form.
+    void ComputeDistinctiveDescriptors(const std::vector<std::vector<cv::Mat> >& lists, std::vector<int>& best)
+    {
+        ensure();
+        const int np = (int)lists.size();
+        best.assign((size_t)np, -1);
+        if (np == 0) return;
+        std::vector<int32_t> start((size_t)np + 1, 0);
+        for (int p = 0; p < np; p++) start[(size_t)p + 1] = start[(size_t)p] + (int)lists[(size_t)p].size();
+        std::vector<unsigned char> d((size_t)start[(size_t)np] * 32 + 32);
+        for (int p = 0; p < np; p++)
+            for (size_t i = 0; i < lists[(size_t)p].size(); i++) std::memcpy(&d[((size_t)start[(size_t)p] + i) * 32], lists[(size_t)p][i].ptr(0), 32);
+        std::vector<int32_t> bi((size_t)np);
+        check(uvip_distinctive_descriptors(handle_, d.data(), start.data(), np, bi.data(), 0), "uvip_distinctive_descriptors");
+        for (int p = 0; p < np; p++) best[(size_t)p] = bi[(size_t)p];
+    }
+
     // rotation-consistency histogram (src/ORBmatcher.cc:232-241, :263-281, :1748-1789) over an index match list
     int CheckOrientation(std::vector<int>& match, const std::vector<float>& angles1, const std::vector<float>& angles2)
     {
