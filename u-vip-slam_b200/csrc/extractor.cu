@@ -1077,22 +1077,33 @@ k_clahe_lut(const uint8_t* __restrict__ src, int w, int h, int stride, size_t pi
             float lut_scale, uint8_t* __restrict__ lut)
 {
     __shared__ int s_hist[256];
+    __shared__ int s_wh[8][256];                              // one histogram per warp: atomics only collide inside a warp
     __shared__ int s_part[8];
     __shared__ int s_clipped;
-    const int tile = blockIdx.x, f = blockIdx.y, tid = threadIdx.x;
+    const int tile = blockIdx.x, f = blockIdx.y, tid = threadIdx.x, warp = tid >> 5;
     const int tx = tile % tiles_x, ty = tile / tiles_x;
     const uint8_t* img = src + (size_t)f * pitch;
-    s_hist[tid] = 0;
+#pragma unroll
+    for (int k = 0; k < 8; k++) s_wh[k][tid] = 0;
     if (tid == 0) s_clipped = 0;
     __syncthreads();
-    for (int i = tid; i < tw * th; i += 256) {
-        const int yy = i / tw, xx = i - yy * tw;
-        int x = tx * tw + xx, y = ty * th + yy;
-        if (x >= w) x = 2 * (w - 1) - x;                      // copyMakeBorder(..., BORDER_REFLECT_101) padding to a tile multiple
-        if (y >= h) y = 2 * (h - 1) - y;
-        atomicAdd(&s_hist[__ldg(img + (size_t)y * stride + x)], 1);
+    for (int yy = warp; yy < th; yy += 8) {
+        int y = ty * th + yy;
+        if (y >= h) y = 2 * (h - 1) - y;                      // copyMakeBorder(..., BORDER_REFLECT_101) padding to a tile multiple
+        const uint8_t* row = img + (size_t)y * stride;
+        for (int xx = tid & 31; xx < tw; xx += 32) {
+            int x = tx * tw + xx;
+            if (x >= w) x = 2 * (w - 1) - x;
+            atomicAdd(&s_wh[warp][__ldg(row + x)], 1);
+        }
     }
     __syncthreads();
+    {
+        int t = 0;
+#pragma unroll
+        for (int k = 0; k < 8; k++) t += s_wh[k][tid];
+        s_hist[tid] = t;
+    }
     int v = s_hist[tid];
     if (clip_limit > 0) {
         if (v > clip_limit) { atomicAdd(&s_clipped, v - clip_limit); v = clip_limit; }
@@ -1120,9 +1131,12 @@ k_clahe_lut(const uint8_t* __restrict__ src, int w, int h, int stride, size_t pi
     lut[((size_t)f * gridDim.x + tile) * 256 + tid] = (uint8_t)min(max(o, 0), 255);
 }
 
+constexpr int CL_W = 64, CL_H = 32, CL_MAXT = 4;           // pixel rectangle of one CTA; tables it may touch per axis
+
+// generic path (any tile size): one pixel per thread, tables read through L1
 __global__ void __launch_bounds__(256)
-k_clahe_apply(const uint8_t* __restrict__ src, int w, int h, int stride, size_t pitch, int tiles_x, int tiles_y, float inv_tw, float inv_th,
-              const uint8_t* __restrict__ lut, uint8_t* __restrict__ dst, int dstride, size_t dpitch)
+k_clahe_apply_generic(const uint8_t* __restrict__ src, int w, int h, int stride, size_t pitch, int tiles_x, int tiles_y, float inv_tw, float inv_th,
+                      const uint8_t* __restrict__ lut, uint8_t* __restrict__ dst, int dstride, size_t dpitch)
 {
     const int f = blockIdx.z;
     const int x = blockIdx.x * 64 + (threadIdx.x & 63), y = blockIdx.y * 4 + (threadIdx.x >> 6);
@@ -1140,6 +1154,70 @@ k_clahe_apply(const uint8_t* __restrict__ src, int w, int h, int stride, size_t 
     const float res = __fadd_rn(__fmul_rn(__fadd_rn(__fmul_rn(l11, xa1), __fmul_rn(l12, xa)), ya1),
                                 __fmul_rn(__fadd_rn(__fmul_rn(l21, xa1), __fmul_rn(l22, xa)), ya));
     dst[(size_t)f * dpitch + (size_t)y * dstride + x] = (uint8_t)min(max(__float2int_rn(res), 0), 255);
+}
+
+
+__global__ void __launch_bounds__(256)
+k_clahe_apply(const uint8_t* __restrict__ src, int w, int h, int stride, size_t pitch, int tiles_x, int tiles_y, float inv_tw, float inv_th,
+              const uint8_t* __restrict__ lut, uint8_t* __restrict__ dst, int dstride, size_t dpitch)
+{
+    // one CTA per CL_W x CL_H pixel rectangle; the look-up tables of every tile its pixels interpolate between are staged in
+    // shared memory first (at most CL_MAXT x CL_MAXT of them, checked by the host), so the 4 look-ups per pixel are LDS.
+    // The interpolation arithmetic is OpenCV's CLAHE_Interpolation_Body float sequence, one rounding per operation.
+    __shared__ __align__(16) uint8_t s_lut[CL_MAXT * CL_MAXT][256];
+    const int f = blockIdx.z, tid = threadIdx.x;
+    const int x0 = blockIdx.x * CL_W, y0 = blockIdx.y * CL_H;
+    const int x1 = min(x0 + CL_W, w) - 1, y1 = min(y0 + CL_H, h) - 1;
+    const int txb = max((int)floorf(__fsub_rn(__fmul_rn((float)x0, inv_tw), 0.5f)), 0);
+    const int tyb = max((int)floorf(__fsub_rn(__fmul_rn((float)y0, inv_th), 0.5f)), 0);
+    const int txe = min((int)floorf(__fsub_rn(__fmul_rn((float)x1, inv_tw), 0.5f)) + 1, tiles_x - 1);
+    const int tye = min((int)floorf(__fsub_rn(__fmul_rn((float)y1, inv_th), 0.5f)) + 1, tiles_y - 1);
+    const int ntx = txe - txb + 1, nty = tye - tyb + 1;
+    const uint8_t* Lf = lut + (size_t)f * tiles_x * tiles_y * 256;
+    for (int i = tid; i < ntx * nty * 64; i += 256) {          // 64 words per table
+        const int t = i >> 6, wd = i & 63;
+        const int tyy = t / ntx, txx = t - tyy * ntx;
+        reinterpret_cast<unsigned*>(s_lut[tyy * CL_MAXT + txx])[wd] =
+            __ldg(reinterpret_cast<const unsigned*>(Lf + ((size_t)(tyb + tyy) * tiles_x + (txb + txx)) * 256) + wd);
+    }
+    __syncthreads();
+    // thread = 4 consecutive columns x (CL_H / 16) rows; the column terms are computed once
+    const int cx = x0 + 4 * (tid & (CL_W / 4 - 1)), ry = tid / (CL_W / 4);
+    if (cx >= w) return;
+    int t1[4], t2[4]; float xa[4], xa1[4];
+#pragma unroll
+    for (int k = 0; k < 4; k++) {
+        const float txf = __fsub_rn(__fmul_rn((float)(cx + k), inv_tw), 0.5f);
+        const int a1 = (int)floorf(txf);
+        xa[k] = __fsub_rn(txf, (float)a1); xa1[k] = __fsub_rn(1.0f, xa[k]);
+        t2[k] = min(a1 + 1, tiles_x - 1) - txb; t1[k] = max(a1, 0) - txb;
+    }
+    const bool vec = ((cx + 3) < w) && (((size_t)src | (size_t)dst | (size_t)stride | (size_t)dstride | pitch | dpitch) & 3) == 0;
+    for (int y = y0 + ry; y <= y1; y += 256 / (CL_W / 4)) {
+        const float tyf = __fsub_rn(__fmul_rn((float)y, inv_th), 0.5f);
+        const int b1 = (int)floorf(tyf);
+        const float ya = __fsub_rn(tyf, (float)b1), ya1 = __fsub_rn(1.0f, ya);
+        const int r2 = (min(b1 + 1, tiles_y - 1) - tyb) * CL_MAXT, r1 = (max(b1, 0) - tyb) * CL_MAXT;
+        const uint8_t* sp = src + (size_t)f * pitch + (size_t)y * stride + cx;
+        uint8_t* dp = dst + (size_t)f * dpitch + (size_t)y * dstride + cx;
+        unsigned in4 = 0;
+        if (vec) in4 = __ldg(reinterpret_cast<const unsigned*>(sp));
+        else
+            for (int k = 0; k < 4; k++) if (cx + k < w) in4 |= (unsigned)__ldg(sp + k) << (8 * k);
+        unsigned out4 = 0;
+#pragma unroll
+        for (int k = 0; k < 4; k++) {
+            const int v = (in4 >> (8 * k)) & 255;
+            const float l11 = (float)s_lut[r1 + t1[k]][v], l12 = (float)s_lut[r1 + t2[k]][v];
+            const float l21 = (float)s_lut[r2 + t1[k]][v], l22 = (float)s_lut[r2 + t2[k]][v];
+            const float res = __fadd_rn(__fmul_rn(__fadd_rn(__fmul_rn(l11, xa1[k]), __fmul_rn(l12, xa[k])), ya1),
+                                        __fmul_rn(__fadd_rn(__fmul_rn(l21, xa1[k]), __fmul_rn(l22, xa[k])), ya));
+            out4 |= (unsigned)min(max(__float2int_rn(res), 0), 255) << (8 * k);
+        }
+        if (vec) *reinterpret_cast<unsigned*>(dp) = out4;
+        else
+            for (int k = 0; k < 4; k++) if (cx + k < w) dp[k] = (uint8_t)(out4 >> (8 * k));
+    }
 }
 
 }  // namespace uvip
@@ -1786,7 +1864,12 @@ static int enqueue_clahe(uvip_extractor* ex, const uint8_t* d_src, int nframes, 
     if ((rc = ex->clahe_lut.reserve((size_t)nframes * tiles_x * tiles_y * 256))) return rc;
     k_clahe_lut<<<dim3(tiles_x * tiles_y, nframes), 256, 0, st>>>(d_src, w, h, stride, pitch, tiles_x, tw, th, clip_limit, lut_scale, ex->clahe_lut.as<uint8_t>());
     ex->launches++;
-    k_clahe_apply<<<dim3(div_up(w, 64), div_up(h, 4), nframes), 256, 0, st>>>(d_src, w, h, stride, pitch, tiles_x, tiles_y, 1.0f / tw, 1.0f / th,
+    // a CL_W x CL_H rectangle touches at most (CL_W-1)/tw + 3 tile columns; smaller tiles take the generic kernel
+    if ((CL_W - 1) / tw + 3 > CL_MAXT || (CL_H - 1) / th + 3 > CL_MAXT)
+        k_clahe_apply_generic<<<dim3(div_up(w, 64), div_up(h, 4), nframes), 256, 0, st>>>(d_src, w, h, stride, pitch, tiles_x, tiles_y, 1.0f / tw, 1.0f / th,
+                                                                                          ex->clahe_lut.as<uint8_t>(), d_dst, dstride, dpitch);
+    else
+    k_clahe_apply<<<dim3(div_up(w, CL_W), div_up(h, CL_H), nframes), 256, 0, st>>>(d_src, w, h, stride, pitch, tiles_x, tiles_y, 1.0f / tw, 1.0f / th,
                                                                               ex->clahe_lut.as<uint8_t>(), d_dst, dstride, dpitch);
     ex->launches++;
     UVIP_CUDA(cudaGetLastError());
