@@ -39,8 +39,27 @@ def parse():
     ap.add_argument('--no-extras', action='store_true', help='skip the Hamming-only and cpu_baseline legs')
     ap.add_argument('--workload', default='frames', choices=['frames', 'knn', 'next'],
                     help="'frames' = the headline metric; 'knn' = BASELINE config 4: database-sharded brute-force kNN2 with NCCL top-2 merge")
+    ap.add_argument('--shape', default='euroc', choices=['euroc', 'aqualoc', 'hd'],
+                    help='frame shape of --workload frames: euroc 752x480/1000 kp (the metric, config 1 shape), aqualoc 640x512/1500 kp (config 2), '
+                         'hd 1280x1024/2000 kp (config 5)')
     ap.add_argument('--knn-n', type=int, default=262144, help='rows of the query and train sets for --workload knn (config 4 is 1048576)')
     return ap.parse_args()
+
+
+SHAPES = {'euroc': (752, 480, 1000), 'aqualoc': (640, 512, 1500), 'hd': (1280, 1024, 2000)}
+
+
+def set_shape(name):
+    """select the frame shape; algorithmic bytes per frame = input + pyramid levels 1..7 written once + 60 B per keypoint"""
+    global W, H, NFEAT, B_FRAME_BYTES
+    import numpy as np
+    W, H, NFEAT = SHAPES[name]
+    inv, isf, tot = np.float32(1), np.float32(1.0 / np.float64(np.float32(SCALE))), 0
+    for _ in range(1, NLEVELS):
+        inv = np.float32(inv * isf)
+        tot += int(np.rint(np.float32(W) * inv)) * int(np.rint(np.float32(H) * inv))
+    B_FRAME_BYTES = W * H + tot + NFEAT * 60
+    return 'ORBextractor %dx%d / %d kp / 8 levels / 1.2 / FAST 20-7' % (W, H, NFEAT)
 
 
 def make_frames(synth, n, seed0):
@@ -148,8 +167,8 @@ def run_reference(args):
         'impl': 'reference', 'metric': METRIC, 'value': fps, 'unit': 'frames/s', 'n_gpus': args.gpus, 'steps': args.steps,
         'warmup': args.warmup, 'ms_per_step': 1e3 * t / args.steps, 'higher_is_better': True, 'scaling': 'weak',
         'vs_baseline': None, 'dtype': 'u8', 'data': 'synthetic',
-        'config': {'workload': 'ORBextractor 752x480 / 1000 kp / 8 levels / 1.2 / FAST 20-7 + brute-force Hamming kNN2 of consecutive '
-                               'frames (BASELINE config 1 shape, batched)', 'frames_per_step': nfr, 'keypoints': NFEAT},
+        'config': {'workload': set_shape(args.shape) + ' + brute-force Hamming kNN2 of consecutive '
+                               'frames (BASELINE %s shape, batched)' % {'euroc': 'config 1', 'aqualoc': 'config 2', 'hd': 'config 5'}[args.shape], 'frames_per_step': nfr, 'keypoints': NFEAT},
         'cpu_baseline': {'value': fps, 'unit': 'frames/s', 'cores': cores, 'kind': 'port',
                          'sample': '%d frames per step, OpenMP over frames; the reference itself cannot be built here '
                                    '(needs OpenCV 3.4 C++/ROS/Eigen), so this is the C oracle restating it' % nfr},
@@ -316,9 +335,9 @@ def run_ours(args):
     line = {
         'metric': METRIC, 'value': fps, 'unit': 'frames/s', 'n_gpus': world, 'steps': K, 'warmup': Wm, 'ms_per_step': ms / K,
         'higher_is_better': True, 'scaling': 'weak', 'vs_baseline': None, 'dtype': 'u8', 'data': 'synthetic',
-        'config': {'workload': 'ORBextractor 752x480 / 1000 kp / 8 levels / 1.2 / FAST 20-7 + brute-force Hamming kNN2 of consecutive '
-                               'frames (BASELINE config 1 shape, batched)', 'frames_per_step_per_gpu': B, 'keypoints': NFEAT,
-                   'l2': 'inputs alternate between two 92 MB batches and each step streams a 0.7 GB pyramid working set (> 126 MB L2)',
+        'config': {'workload': set_shape(args.shape) + ' + brute-force Hamming kNN2 of consecutive '
+                               'frames (BASELINE %s shape, batched)' % {'euroc': 'config 1', 'aqualoc': 'config 2', 'hd': 'config 5'}[args.shape], 'frames_per_step_per_gpu': B, 'keypoints': NFEAT,
+                   'l2': 'inputs alternate between two %d MB batches and each step streams a %.1f GB pyramid working set (> 126 MB L2)' % (B * W * H >> 20, 2.0 * B * B_FRAME_BYTES / 1e9),
                    'parallelism': 'frames sharded over %d GPU(s), no collective' % world},
         'clocks': clk,
         'e2e': {'value': e2e_fps, 'unit': 'frames/s', 'h2d_bytes_per_step': h2d, 'd2h_bytes_per_step': d2h, 'steps': Ke,
@@ -512,6 +531,8 @@ def run_next(args):
 
 if __name__ == '__main__':
     a = parse()
+    set_shape(a.shape)
+    assert a.shape != 'euroc' or B_FRAME_BYTES == 1177367
     if a.impl == 'reference':
         sys.exit(run_reference(a))
     sys.exit(run_knn(a) if a.workload == 'knn' else run_next(a) if a.workload == 'next' else run_ours(a))
