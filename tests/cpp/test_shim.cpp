@@ -7,6 +7,7 @@
 #include <cstdio>
 #include <cstdlib>
 #include <map>
+#include <set>
 #include <vector>
 #include "../../u-vip-slam_b200/host/ORBextractor.h"
 #include "../../u-vip-slam_b200/host/ORBmatcher.h"
@@ -14,14 +15,20 @@
 struct MockMapPoint {
     bool mbTrackInView = true; int mnTrackScaleLevel = 0; float mTrackViewCos = 0.9f, mTrackProjX = 0, mTrackProjY = 0;
     cv::Mat desc; bool bad = false;
+    float pos[3] = {0, 0, 1}, minDist = 1.0f;
     bool isBad() const { return bad; }
     cv::Mat GetDescriptor() const { return desc; }
+    cv::Mat GetWorldPos() { return cv::Mat(3, 4, CV_8UC1, pos, 4); }              // 3x1 float viewed through the 8-bit stand-in (ptr<float>(r)[0])
+    float GetMinDistanceInvariance() const { return minDist; }
 };
 typedef std::map<unsigned, std::vector<unsigned> > FeatureVector;     // DBoW2::FeatureVector
 struct MockFrame {
     std::vector<cv::KeyPoint> mvKeysUn, mvKeys; cv::Mat mDescriptors; std::vector<MockMapPoint*> mvpMapPoints; std::vector<float> mvScaleFactors;
-    int mnMinX = 0, mnMinY = 0; float mfGridElementWidthInv = 0, mfGridElementHeightInv = 0;
+    int mnMinX = 0, mnMinY = 0, mnMaxX = 0, mnMaxY = 0, mnScaleLevels = 8; float mfGridElementWidthInv = 0, mfGridElementHeightInv = 0;
     FeatureVector mFeatVec;
+    float pose[16] = {1, 0, 0, 0, 0, 1, 0, 0, 0, 0, 1, 0, 0, 0, 0, 1}; float fx = 1, fy = 1, cx = 0, cy = 0;
+    cv::Mat mTcw;                                                                 // 4x4 float viewed through the 8-bit stand-in
+    MockFrame() : mTcw(4, 16, CV_8UC1, pose, 16) {}
 };
 struct MockKeyFrame {
     std::vector<MockMapPoint*> mps; FeatureVector fv; cv::Mat desc; std::vector<cv::KeyPoint> keys;
@@ -109,6 +116,34 @@ int main(int argc, char** argv)
         std::vector<int> bowner((size_t)n, -1);
         for (int i = 0; i < n; i++) if (vm[i]) bowner[i] = (int)(vm[i] - kfmps.data());
         put(fo, bowner.data(), (size_t)n * 4);
+        // 6 (written after 5 below). SearchByProjection(CurrentFrame, KeyFrame*, sAlreadyFound, th, ORBdist): relocalisation
+        // geometry.  The keyframe's map point i is keypoint i back-projected at depth 2 + (i % 7) * 0.5 through the camera,
+        // then seen by a slightly rotated / translated current pose.
+        MockFrame F3;
+        F3.mvKeysUn = kps; F3.mvKeys = kps; F3.mDescriptors = desc; F3.mvpMapPoints.assign((size_t)n, nullptr);
+        F3.mvScaleFactors = F.mvScaleFactors; F3.mfGridElementWidthInv = F.mfGridElementWidthInv; F3.mfGridElementHeightInv = F.mfGridElementHeightInv;
+        F3.mnMaxX = w; F3.mnMaxY = h; F3.fx = 458.0f; F3.fy = 457.0f; F3.cx = 367.0f; F3.cy = 248.0f;
+        {
+            const float c = 0.99995f, sn = 0.0099998f;                            // ~0.573 degrees about the optical axis
+            const float P[16] = {c, -sn, 0, 0.01f, sn, c, 0, -0.02f, 0, 0, 1, 0.03f, 0, 0, 0, 1};
+            for (int i = 0; i < 16; i++) F3.pose[i] = P[i];
+        }
+        std::vector<MockMapPoint> mps3((size_t)n);
+        MockKeyFrame KF3; KF3.desc = desc; KF3.keys = kps;
+        std::set<MockMapPoint*> found;
+        for (int i = 0; i < n; i++) {
+            const float z = 2.0f + (float)(i % 7) * 0.5f;
+            mps3[i].pos[0] = (kps[i].pt.x - F3.cx) / F3.fx * z; mps3[i].pos[1] = (kps[i].pt.y - F3.cy) / F3.fy * z; mps3[i].pos[2] = z;
+            mps3[i].minDist = z / F3.mvScaleFactors[(size_t)kps[i].octave] * 1.05f;
+            mps3[i].desc = desc.row(i); mps3[i].bad = (i % 23) == 0;
+            KF3.mps.push_back((i % 9 == 0) ? nullptr : &mps3[i]);
+            if (i % 10 == 1) found.insert(&mps3[i]);
+            if (i % 31 == 5) F3.mvpMapPoints[i] = &mps3[0];                        // keypoints that already carry a map point
+        }
+        USLAM::ORBmatcher reloc(0.9f, true);
+        const int nr = reloc.SearchByProjection(F3, &KF3, found, 10.0f, 100);
+        std::vector<int> rowner((size_t)n, -1);
+        for (int i = 0; i < n; i++) if (F3.mvpMapPoints[i]) rowner[i] = (int)(F3.mvpMapPoints[i] - mps3.data());
         // 5. MapPoint::ComputeDistinctiveDescriptors batched: list p = descriptor rows p, p+7, p+14, ... (1 + p % 9 of them)
         const int np = n < 64 ? n : 64;
         std::vector<std::vector<cv::Mat> > lists((size_t)np);
@@ -118,6 +153,8 @@ int main(int argc, char** argv)
         bow.ComputeDistinctiveDescriptors(lists, best);
         put(fo, &np, 4);
         put(fo, best.data(), (size_t)np * 4);
+        put(fo, &nr, 4);
+        put(fo, rowner.data(), (size_t)n * 4);
     } catch (const std::exception& e) {
         fprintf(stderr, "shim error: %s\n", e.what());
         fclose(fo);

@@ -134,3 +134,52 @@ def test_shim_matches_oracle(pkg, oracle, synth, shim_exe, tmp_path):
     rows = np.concatenate([desc[[(p + 7 * j) % n for j in range(sizes[p])]] for p in range(npnt)])
     obest, _ = oracle.distinctive_descriptors(rows, start)
     assert npnt == 64 and np.array_equal(best, obest)
+    # 6. SearchByProjection(CurrentFrame, KeyFrame*, sAlreadyFound, th=10, ORBdist=100) through the shim: projection with the
+    #    current pose (double accumulation of float products, as cv::Mat products do), predicted level by lower_bound on the
+    #    scale factors, window levels [l-1, l+1], best-only + claims, rotation histogram rollback (src/ORBmatcher.cc:1622-1746)
+    nr = int(take(np.int32, 1)[0]); rowner = take(np.int32, n)
+    f32 = np.float32
+    fx, fy, cx, cy = f32(458.0), f32(457.0), f32(367.0), f32(248.0)
+    c_, s_ = f32(0.99995), f32(0.0099998)
+    P = np.array([[c_, -s_, 0, f32(0.01)], [s_, c_, 0, f32(-0.02)], [0, 0, 1, f32(0.03)]], np.float32)
+    Rm, tv = P[:, :3], P[:, 3]
+    Ow = np.zeros(3, np.float32)
+    for c in range(3):
+        acc = 0.0
+        for r in range(3):
+            acc += float(Rm[r, c]) * float(tv[r])
+        Ow[c] = f32(-1.0 * acc)
+    # the shim used ITS OWN keypoints / descriptors (kps, desc): identical to the oracle's except for the angle / descriptor tolerance
+    qu, qv, qr, qlo, qhi, qa, who = [], [], [], [], [], [], []
+    for i in range(n):
+        if i % 9 == 0 or i % 23 == 0 or i % 10 == 1:
+            continue
+        z = f32(2.0) + f32(i % 7) * f32(0.5)
+        X = np.array([(kps['x'][i] - cx) / fx * z, (kps['y'][i] - cy) / fy * z, z], np.float32)
+        xc3 = np.zeros(3, np.float32)
+        for r in range(3):
+            acc = 0.0
+            for c in range(3):
+                acc += float(Rm[r, c]) * float(X[c])
+            xc3[r] = f32(acc + float(tv[r]))
+        invz = f32(1.0 / float(xc3[2]))
+        u_ = fx * xc3[0] * invz + cx; v_ = fy * xc3[1] * invz + cy
+        if u_ < 0 or u_ > W or v_ < 0 or v_ > H:
+            continue
+        po = X - Ow
+        d3 = f32(np.sqrt(float(po[0]) * float(po[0]) + float(po[1]) * float(po[1]) + float(po[2]) * float(po[2])))
+        mind = z / sf[kps['octave'][i]] * f32(1.05)
+        ratio = d3 / mind
+        lv = min(int(np.searchsorted(sf, ratio, side='left')), 7)
+        qu.append(u_); qv.append(v_); qr.append(f32(10.0) * sf[lv]); qlo.append(lv - 1); qhi.append(lv + 1); qa.append(kps['angle'][i]); who.append(i)
+    taken0 = np.where(np.arange(n) % 31 == 5, -2, -1).astype(np.int32)
+    start3, items3 = oracle.grid_build(kps['x'], kps['y'], 0.0, 0.0, float(inv_w), float(inv_h))
+    on3, om3, _ = oracle.search_window(1, 100, np.float32(0.9), qu, qv, qr, qlo, qhi, desc[who], kps['x'], kps['y'], kps['octave'].astype(np.int32),
+                                       desc, start3, items3, 0.0, 0.0, float(inv_w), float(inv_h), taken=taken0)
+    kept = oracle.rot_hist_filter(om3, np.array(qa, np.float32), kps['angle'])
+    expect3 = np.where(np.arange(n) % 31 == 5, 0, -1).astype(np.int32)
+    for qi, k in enumerate(kept):
+        if k >= 0:
+            expect3[k] = who[qi]
+    assert nr == int((kept >= 0).sum()) and nr > 300, (nr, int((kept >= 0).sum()))
+    assert np.array_equal(rowner, expect3)

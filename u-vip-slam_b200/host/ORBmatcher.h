@@ -6,7 +6,9 @@
 #pragma once
 #include <cmath>
 #include <cstring>
+#include <algorithm>
 #include <map>
+#include <set>
 #include <stdexcept>
 #include <string>
 #include <vector>
@@ -82,6 +84,90 @@ public:
                                  kx.data(), ky.data(), oct.data(), kd.data(), nk, cs.data(), ci.data(), taken.data(), match.data(), &nmatches),
               "uvip_search_window");
         for (int q = 0; q < nq; q++) if (match[q] >= 0) F.mvpMapPoints[match[q]] = who[q];     // :119
+        return nmatches;
+    }
+
+    // SearchByProjection(FrameKTL& CurrentFrame, KeyFrame* pKF, const set<MapPoint*>& sAlreadyFound, th, ORBdist)
+    // (src/ORBmatcher.cc:1622-1746; relocalisation and keyframe tracking, src/Tracking.cc:2480,2494,3020,3026).  The host
+    // side projects the keyframe's map points with the current pose exactly as :1650-1678 does (cv::Mat products
+    // accumulate float products in double and round once, cv::norm likewise), the window search + claims run in
+    // uvip_search_window mode 1 and the rotation histogram in uvip_rot_hist_filter.
+    // FrameT needs: mTcw (4x4 CV_32F), fx, fy, cx, cy, mnMinX/MaxX/MinY/MaxY, mvScaleFactors, mnScaleLevels, mvKeysUn,
+    //               mDescriptors, mvpMapPoints, mfGridElement{Width,Height}Inv;  KeyFrameT: GetMapPointMatches(),
+    //               GetKeyPointUn(i);  MapPointT: isBad(), GetWorldPos() (3x1 CV_32F), GetMinDistanceInvariance(), GetDescriptor()
+    template <class FrameT, class KeyFrameT, class MapPointT>
+    int SearchByProjection(FrameT& CurrentFrame, KeyFrameT* pKF, const std::set<MapPointT*>& sAlreadyFound, const float th, const int ORBdist)
+    {
+        ensure();
+        float R[3][3], t[3], Ow[3];
+        for (int r = 0; r < 3; r++) {
+            const float* row = CurrentFrame.mTcw.template ptr<float>(r);
+            for (int c = 0; c < 3; c++) R[r][c] = row[c];
+            t[r] = row[3];
+        }
+        for (int c = 0; c < 3; c++) {                                              // Ow = -Rcw.t()*tcw  (:1628)
+            double s = 0; for (int r = 0; r < 3; r++) s += (double)R[r][c] * (double)t[r];
+            Ow[c] = (float)(-1.0 * s);
+        }
+        const std::vector<MapPointT*> vpMPs = pKF->GetMapPointMatches();
+        std::vector<float> qu, qv, qr, qa; std::vector<int32_t> qmin, qmax; std::vector<unsigned char> qd; std::vector<MapPointT*> who;
+        for (size_t i = 0; i < vpMPs.size(); i++) {
+            MapPointT* pMP = vpMPs[i];
+            if (!pMP) continue;
+            if (pMP->isBad() || sAlreadyFound.count(pMP)) continue;
+            const cv::Mat x3Dw = pMP->GetWorldPos();
+            float X[3], xc3[3];
+            for (int r = 0; r < 3; r++) X[r] = x3Dw.template ptr<float>(r)[0];
+            for (int r = 0; r < 3; r++) {                                          // x3Dc = Rcw*x3Dw+tcw  (:1651)
+                double s = 0; for (int c = 0; c < 3; c++) s += (double)R[r][c] * (double)X[c];
+                xc3[r] = (float)(s + (double)t[r]);
+            }
+            const float xc = xc3[0], yc = xc3[1];
+            const float invzc = (float)(1.0 / xc3[2]);
+            const float u = CurrentFrame.fx * xc * invzc + CurrentFrame.cx;
+            const float v = CurrentFrame.fy * yc * invzc + CurrentFrame.cy;
+            if (u < CurrentFrame.mnMinX || u > CurrentFrame.mnMaxX) continue;
+            if (v < CurrentFrame.mnMinY || v > CurrentFrame.mnMaxY) continue;
+            const float minDistance = pMP->GetMinDistanceInvariance();              // predicted scale level (:1666-1672)
+            double n2 = 0; for (int r = 0; r < 3; r++) { const float po = X[r] - Ow[r]; n2 += (double)po * (double)po; }
+            const float dist3D = (float)std::sqrt(n2);
+            const float ratio = dist3D / minDistance;
+            const std::vector<float>& sf = CurrentFrame.mvScaleFactors;
+            const int lvl = std::min((int)(std::lower_bound(sf.begin(), sf.end(), ratio) - sf.begin()), (int)CurrentFrame.mnScaleLevels - 1);
+            qu.push_back(u); qv.push_back(v); qr.push_back(th * sf[(size_t)lvl]);
+            qmin.push_back(lvl - 1); qmax.push_back(lvl + 1);
+            const cv::Mat d = pMP->GetDescriptor();
+            qd.insert(qd.end(), d.ptr(0), d.ptr(0) + 32);
+            qa.push_back(pKF->GetKeyPointUn(i).angle);
+            who.push_back(pMP);
+        }
+        const int nq = (int)who.size(), nk = (int)CurrentFrame.mvKeysUn.size();
+        if (nq == 0 || nk == 0) return 0;
+        std::vector<float> kx((size_t)nk), ky((size_t)nk), ka((size_t)nk); std::vector<int32_t> oct((size_t)nk), taken((size_t)nk);
+        std::vector<unsigned char> kd((size_t)nk * 32);
+        for (int i = 0; i < nk; i++) {
+            kx[i] = CurrentFrame.mvKeysUn[i].pt.x; ky[i] = CurrentFrame.mvKeysUn[i].pt.y; oct[i] = CurrentFrame.mvKeysUn[i].octave;
+            ka[i] = CurrentFrame.mvKeysUn[i].angle;
+            taken[i] = CurrentFrame.mvpMapPoints[i] ? -2 : -1;
+            std::memcpy(&kd[(size_t)i * 32], CurrentFrame.mDescriptors.ptr(i), 32);
+        }
+        uvip_search_params sp;
+        sp.mode = 1; sp.th_dist = ORBdist; sp.ratio = mfNNratio;
+        sp.min_x = (float)CurrentFrame.mnMinX; sp.min_y = (float)CurrentFrame.mnMinY;
+        sp.inv_w = CurrentFrame.mfGridElementWidthInv; sp.inv_h = CurrentFrame.mfGridElementHeightInv;
+        sp.cols = 64; sp.rows = 48;
+        std::vector<int32_t> cs(64 * 48 + 1), ci((size_t)nk), match((size_t)nq);
+        check(uvip_grid_build(handle_, kx.data(), ky.data(), nk, sp.min_x, sp.min_y, sp.inv_w, sp.inv_h, 64, 48, cs.data(), ci.data()), "uvip_grid_build");
+        int nmatches = 0;
+        check(uvip_search_window(handle_, &sp, qu.data(), qv.data(), qr.data(), qmin.data(), qmax.data(), qd.data(), nq,
+                                 kx.data(), ky.data(), oct.data(), kd.data(), nk, cs.data(), ci.data(), taken.data(), match.data(), &nmatches),
+              "uvip_search_window");
+        for (int q = 0; q < nq; q++) if (match[q] >= 0) CurrentFrame.mvpMapPoints[match[q]] = who[q];      // :1698
+        if (mbCheckOrientation) {                                                                          // :1701-1743
+            std::vector<int32_t> kept(match);
+            check(uvip_rot_hist_filter(handle_, kept.data(), nq, qa.data(), ka.data(), &nmatches), "uvip_rot_hist_filter");
+            for (int q = 0; q < nq; q++) if (match[q] >= 0 && kept[q] < 0) CurrentFrame.mvpMapPoints[match[q]] = static_cast<MapPointT*>(NULL);
+        }
         return nmatches;
     }
 
