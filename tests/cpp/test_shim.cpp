@@ -36,6 +36,8 @@ struct MockKeyFrame {
     FeatureVector GetFeatureVector() { return fv; }
     cv::Mat GetDescriptor(size_t i) { return desc.row((int)i); }
     cv::KeyPoint GetKeyPointUn(size_t i) const { return keys[i]; }
+    std::vector<cv::KeyPoint> GetKeyPointsUn() const { return keys; }
+    cv::Mat GetDescriptors() const { return desc; }
 };
 
 static void put(FILE* f, const void* p, size_t n) { if (fwrite(p, 1, n, f) != n) { perror("write"); exit(2); } }
@@ -155,6 +157,21 @@ int main(int argc, char** argv)
         put(fo, best.data(), (size_t)np * 4);
         put(fo, &nr, 4);
         put(fo, rowner.data(), (size_t)n * 4);
+        // 7. SearchByBoW(KeyFrame*, KeyFrame*): KF (section 4) against a second keyframe with the same features, other gaps
+        MockKeyFrame KFb; KFb.desc = desc; KFb.keys = kps;
+        std::vector<MockMapPoint> mpsb((size_t)n);
+        for (int i = 0; i < n; i++) {
+            const unsigned node = (unsigned)(kps[i].pt.x / 64) + 16u * (unsigned)(kps[i].pt.y / 64);
+            if (i % 15 != 4) KFb.fv[node + (i % 37 == 0 ? 2000u : 0u)].push_back((unsigned)i);
+            mpsb[i].bad = (i % 21) == 2;
+            KFb.mps.push_back((i % 6 == 1) ? nullptr : &mpsb[i]);
+        }
+        std::vector<MockMapPoint*> m12;
+        const int nkk = bow.SearchByBoW(&KF, &KFb, m12);
+        put(fo, &nkk, 4);
+        std::vector<int> o12((size_t)n, -1);
+        for (int i = 0; i < n; i++) if (m12[i]) o12[i] = (int)(m12[i] - mpsb.data());
+        put(fo, o12.data(), (size_t)n * 4);
     } catch (const std::exception& e) {
         fprintf(stderr, "shim error: %s\n", e.what());
         fclose(fo);

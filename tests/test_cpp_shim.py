@@ -183,3 +183,26 @@ def test_shim_matches_oracle(pkg, oracle, synth, shim_exe, tmp_path):
             expect3[k] = who[qi]
     assert nr == int((kept >= 0).sum()) and nr > 300, (nr, int((kept >= 0).sum()))
     assert np.array_equal(rowner, expect3)
+    # 7. SearchByBoW(KeyFrame*, KeyFrame*) through the shim (src/ORBmatcher.cc:715-850): strict best < TH_LOW, ratio 0.9, claims
+    #    on the second keyframe, candidates without a good map point dropped, histogram rollback
+    nkk = int(take(np.int32, 1)[0]); o12 = take(np.int32, n)
+    node_s = (kps['x'] / np.float32(64)).astype(np.int64) + 16 * (kps['y'] / np.float32(64)).astype(np.int64)
+    anode, bnode = {}, {}
+    for k in range(n):
+        anode.setdefault(int(node_s[k]), []).append(k)
+        if k % 15 != 4:
+            bnode.setdefault(int(node_s[k]) + (2000 if k % 37 == 0 else 0), []).append(k)
+    q7, cs7, ci7 = [], [0], []
+    for nd in sorted(anode):
+        if nd not in bnode:
+            continue
+        for k in anode[nd]:
+            if k % 7 == 0 or k % 19 == 0:
+                continue
+            q7.append(k); ci7.extend(j for j in bnode[nd] if j % 6 != 1 and j % 21 != 2); cs7.append(len(ci7))
+    q7 = np.array(q7)
+    on7, om7, _ = oracle.search_lists(3, 50, np.float32(0.9), desc[q7], np.array(cs7, np.int32), np.array(ci7 or [0], np.int32), desc)
+    om7 = oracle.rot_hist_filter(om7, kps['angle'][q7], kps['angle'])
+    e12 = np.full(n, -1, np.int32); e12[q7[om7 >= 0]] = om7[om7 >= 0]
+    assert nkk == int((om7 >= 0).sum()) and nkk > 200, (nkk, int((om7 >= 0).sum()))
+    assert np.array_equal(o12, e12)

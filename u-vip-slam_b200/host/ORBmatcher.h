@@ -220,6 +220,61 @@ public:
         return nmatches;
     }
 
+    // SearchByBoW(KeyFrame* pKF1, KeyFrame* pKF2, vector<MapPoint*>& vpMatches12)  (src/ORBmatcher.cc:715-850, loop closing
+    // src/LoopClosing.cc:399): same node-restricted top-2 as above between two keyframes, strict best < TH_LOW, ratio, claims on
+    // the second keyframe's features, rotation histogram.  Candidates without a (good) map point are dropped while the
+    // lists are built (:766-772).  KeyFrameT needs: GetKeyPointsUn(), GetFeatureVector(), GetMapPointMatches(), GetDescriptors()
+    template <class KeyFrameT, class MapPointT>
+    int SearchByBoW(KeyFrameT* pKF1, KeyFrameT* pKF2, std::vector<MapPointT*>& vpMatches12)
+    {
+        ensure();
+        const std::vector<cv::KeyPoint> vKeysUn1 = pKF1->GetKeyPointsUn(), vKeysUn2 = pKF2->GetKeyPointsUn();
+        const auto vFeatVec1 = pKF1->GetFeatureVector(); const auto vFeatVec2 = pKF2->GetFeatureVector();
+        const std::vector<MapPointT*> vpMapPoints1 = pKF1->GetMapPointMatches(), vpMapPoints2 = pKF2->GetMapPointMatches();
+        const cv::Mat Descriptors1 = pKF1->GetDescriptors(), Descriptors2 = pKF2->GetDescriptors();
+        vpMatches12 = std::vector<MapPointT*>(vpMapPoints1.size(), static_cast<MapPointT*>(NULL));
+        std::vector<unsigned char> qd; std::vector<int32_t> cs(1, 0), ci; std::vector<unsigned> qidx;
+        auto f1it = vFeatVec1.begin(); auto f2it = vFeatVec2.begin();
+        while (f1it != vFeatVec1.end() && f2it != vFeatVec2.end()) {
+            if (f1it->first == f2it->first) {
+                for (size_t i1 = 0; i1 < f1it->second.size(); i1++) {
+                    const unsigned idx1 = f1it->second[i1];
+                    MapPointT* pMP1 = vpMapPoints1[idx1];
+                    if (!pMP1) continue;
+                    if (pMP1->isBad()) continue;
+                    qd.insert(qd.end(), Descriptors1.ptr((int)idx1), Descriptors1.ptr((int)idx1) + 32);
+                    for (size_t i2 = 0; i2 < f2it->second.size(); i2++) {
+                        const unsigned idx2 = f2it->second[i2];
+                        MapPointT* pMP2 = vpMapPoints2[idx2];
+                        if (!pMP2 || pMP2->isBad()) continue;
+                        ci.push_back((int32_t)idx2);
+                    }
+                    cs.push_back((int32_t)ci.size());
+                    qidx.push_back(idx1);
+                }
+                ++f1it; ++f2it;
+            } else if (f1it->first < f2it->first) f1it = vFeatVec1.lower_bound(f2it->first);
+            else f2it = vFeatVec2.lower_bound(f1it->first);
+        }
+        const int nq = (int)qidx.size(), nk = (int)vpMapPoints2.size();
+        if (nq == 0 || nk == 0) return 0;
+        std::vector<unsigned char> kd((size_t)nk * 32);
+        for (int i = 0; i < nk; i++) std::memcpy(&kd[(size_t)i * 32], Descriptors2.ptr(i), 32);
+        std::vector<int32_t> taken((size_t)nk, -1), match((size_t)nq);
+        int nmatches = 0;
+        if (ci.empty()) ci.push_back(0);
+        check(uvip_search_lists(handle_, 3, TH_LOW, mfNNratio, qd.data(), nq, cs.data(), ci.data(), kd.data(), nk, taken.data(), match.data(), &nmatches),
+              "uvip_search_lists");
+        if (mbCheckOrientation) {
+            std::vector<float> a1((size_t)nq), a2((size_t)nk);
+            for (int q = 0; q < nq; q++) a1[q] = vKeysUn1[qidx[q]].angle;
+            for (int i = 0; i < nk; i++) a2[i] = vKeysUn2[(size_t)i].angle;
+            check(uvip_rot_hist_filter(handle_, match.data(), nq, a1.data(), a2.data(), &nmatches), "uvip_rot_hist_filter");
+        }
+        for (int q = 0; q < nq; q++) if (match[q] >= 0) vpMatches12[qidx[q]] = vpMapPoints2[(size_t)match[q]];
+        return nmatches;
+    }
+
     // haloc::Utils::ratioMatching (include/utils.h:81-111): brute-force k=2 + ratio test; match[i] = train row or -1
     int RatioMatching(const cv::Mat& descriptors1, const cv::Mat& descriptors2, double ratio, std::vector<int>& match)
     {
