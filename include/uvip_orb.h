@@ -182,13 +182,17 @@ int   uvip_grid_build(uvip_matcher* m, const float* kx, const float* ky, int n,
 
 /* Grid-windowed search with claims: ORBmatcher::SearchByProjection(FrameKTL&, vector<MapPoint*>&, th)
  * (src/ORBmatcher.cc:49-125) when mode == 0, and the search loop of SearchByProjection(FrameKTL&, KeyFrame*, ...)
- * (src/ORBmatcher.cc:1683-1715) when mode == 1; candidates come from FrameKTL::GetFeaturesInArea
- * (src/FrameKTL.cc:359-424).  The caller (shim) projects the map points and supplies per query
+ * (src/ORBmatcher.cc:1683-1715) when mode == 1 — which is also the loop of SearchByProjection(KeyFrame*, Scw, ...)
+ * (:372-399, taken = vpMatched) — and the loop of Fuse (:1075-1100) when mode == 4; candidates come from
+ * FrameKTL::GetFeaturesInArea (src/FrameKTL.cc:359-424) = KeyFrame::GetFeaturesInArea (src/KeyFrame.cc:952-992, same
+ * cells and the same inclusive |dx| <= r test) followed by the explicit level test [l-1, l] of the keyframe-side loops.  The caller (shim) projects the map points and supplies per query
  * (u, v, radius, minLevel, maxLevel, descriptor).  taken[] (nk): -1 = free, anything else = keypoint already has a
  * map point; on return claimed keypoints hold the claiming query index.  match[q] = keypoint index or -1.
  * The sequential claim order of the reference is reproduced exactly. */
 typedef struct uvip_search_params {
-    int32_t mode;        /* 0: top-2 with same-level ratio rule; 1: best only */
+    int32_t mode;        /* 0: top-2 with same-level ratio rule; 1: best only; 4: best only without claims (Fuse,
+                          * src/ORBmatcher.cc:1075-1100: taken[] is neither read nor written, several queries may return
+                          * the same keypoint and the caller replays Replace / AddObservation in query order) */
     int32_t th_dist;     /* UVIP_TH_HIGH for mode 0, ORBdist for mode 1 */
     float   ratio;       /* mfNNratio */
     float   min_x, min_y, inv_w, inv_h;   /* FrameKTL::mnMinX, mnMinY, mfGridElementWidthInv, mfGridElementHeightInv */

@@ -863,14 +863,15 @@ int uo_search_window(const uo_search_params* sp,
                 taken[bestIdx] = q; match_of_query[q] = bestIdx; nmatches++;
             }
         } else {
+            /* mode 1: src/ORBmatcher.cc:1683-1715 / :372-399 (claims);  mode 4: Fuse :1075-1100 (no claims: taken[] untouched) */
             int bestDist = 2147483647, bestIdx = -1;
             for (int c = 0; c < nc; c++) {
                 int idx = cand[c];
-                if (taken[idx] != -1) continue;
+                if (sp->mode != 4 && taken[idx] != -1) continue;
                 int dist = uo_descriptor_distance(d, kdesc + (size_t)idx * 32);
                 if (dist < bestDist) { bestDist = dist; bestIdx = idx; }
             }
-            if (bestDist <= sp->th_dist) { taken[bestIdx] = q; match_of_query[q] = bestIdx; nmatches++; }
+            if (bestDist <= sp->th_dist) { if (sp->mode != 4) taken[bestIdx] = q; match_of_query[q] = bestIdx; nmatches++; }
         }
     }
     free(cand);

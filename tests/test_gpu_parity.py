@@ -299,6 +299,18 @@ def test_grid_and_search_by_projection_cfg3(gpu, oracle, synth):
     g = m.rot_hist_filter(match, c['qangle'], c['kangle'])
     o = oracle.rot_hist_filter(omatch, c['qangle'], c['kangle'])
     assert np.array_equal(g, o) and (g >= 0).sum() < (match >= 0).sum()
+    # M8 Fuse semantics (src/ORBmatcher.cc:1075-1100): th=2.5 window, levels [l-1, l], best only, TH_LOW, NO claims: taken[] is
+    # neither read nor written and several map points may land on the same keypoint
+    r = (np.float32(2.5) * sf[lvl]).astype(np.float32)
+    n4, match4, taken4 = m.search_window(4, 50, c['u'], c['v'], r, lvl - 1, lvl, c['qdesc'], c['kx'], c['ky'], c['octave'],
+                                         c['kdesc'], grid, taken=pre)
+    on4, omatch4, otaken4 = oracle.search_window(4, 50, 0.8, c['u'], c['v'], r, lvl - 1, lvl, c['qdesc'], c['kx'], c['ky'],
+                                                 c['octave'], c['kdesc'], ostart, oitems, grid['minX'], grid['minY'],
+                                                 grid['inv_w'], grid['inv_h'], taken=pre)
+    assert n4 == on4 == int((match4 >= 0).sum()) and np.array_equal(match4, omatch4)
+    assert np.array_equal(taken4, pre) and np.array_equal(otaken4, pre)
+    hit = match4[match4 >= 0]
+    assert len(np.unique(hit)) < len(hit) and (hit % 7 == 0).any()   # shared keypoints, pre-taken ones included
 
 
 def test_search_window_claim_chain(gpu, oracle, synth):

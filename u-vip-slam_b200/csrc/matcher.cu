@@ -421,17 +421,18 @@ k_search_window(SearchCtx c, int nq, int nk, int32_t* __restrict__ taken, int32_
 {
     __shared__ int s_changed, s_n;
     int* prev = ownerA; int* cur = ownerB;
-    for (int i = threadIdx.x; i < nk; i += blockDim.x) prev[i] = (taken[i] != -1) ? -2 : INT_MAX;
+    const bool claims = c.sp.mode != 4;                    // mode 4 (Fuse): every query is independent, taken[] is not consulted
+    for (int i = threadIdx.x; i < nk; i += blockDim.x) prev[i] = (claims && taken[i] != -1) ? -2 : INT_MAX;
     __syncthreads();
     int rounds = 0;
     for (;;) {
-        for (int i = threadIdx.x; i < nk; i += blockDim.x) cur[i] = (taken[i] != -1) ? -2 : INT_MAX;
+        for (int i = threadIdx.x; i < nk; i += blockDim.x) cur[i] = (claims && taken[i] != -1) ? -2 : INT_MAX;
         if (threadIdx.x == 0) s_changed = 0;
         __syncthreads();
         for (int q = threadIdx.x; q < nq; q += blockDim.x) {
             const int r = c.cand_start ? search_one_list(c, q, prev) : search_one(c, q, prev);
             match[q] = r;
-            if (r >= 0) atomicMin(&cur[r], q);
+            if (r >= 0 && claims) atomicMin(&cur[r], q);
         }
         __syncthreads();
         int ch = 0;
@@ -447,9 +448,13 @@ k_search_window(SearchCtx c, int nq, int nk, int32_t* __restrict__ taken, int32_
     if (threadIdx.x == 0) s_n = 0;
     __syncthreads();
     int n = 0;
-    for (int i = threadIdx.x; i < nk; i += blockDim.x) {
-        const int o = prev[i];
-        if (o >= 0 && o != INT_MAX) { taken[i] = o; n++; }
+    if (claims) {
+        for (int i = threadIdx.x; i < nk; i += blockDim.x) {
+            const int o = prev[i];
+            if (o >= 0 && o != INT_MAX) { taken[i] = o; n++; }
+        }
+    } else {
+        for (int q = threadIdx.x; q < nq; q += blockDim.x) n += match[q] >= 0;
     }
     if (n) atomicAdd(&s_n, n);
     __syncthreads();
