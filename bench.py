@@ -30,7 +30,7 @@ FALLBACK_HBM_GBS = 6650.0        # B200_PROFILING.md fallback when MEASURED_PEAK
 def parse():
     ap = argparse.ArgumentParser()
     ap.add_argument('--gpus', type=int, default=1)
-    ap.add_argument('--steps', type=int, default=20)
+    ap.add_argument('--steps', type=int, default=200)
     ap.add_argument('--warmup', type=int, default=3)
     ap.add_argument('--impl', default='ours', choices=['ours', 'reference'])
     ap.add_argument('--batch', type=int, default=256, help='frames per step and per GPU')
@@ -72,29 +72,74 @@ def make_frames(synth, n, seed0):
 
 
 class ClockSampler:
-    """nvidia-smi clocks + throttle reasons sampled DURING the timed region (B200_PROFILING.md recipe)"""
+    """SM clock + throttle reasons sampled DURING the timed region (B200_PROFILING.md recipe).  NVML is polled in-process
+    every few milliseconds (the timed region of a default run is well under a second, too short for `nvidia-smi -lms`
+    to deliver a sample); nvidia-smi is the fallback when NVML cannot be loaded."""
     Q = ('index,clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.hw_slowdown,'
          'clocks_event_reasons.hw_thermal_slowdown,clocks_event_reasons.sw_thermal_slowdown,clocks_event_reasons.sw_power_cap')
 
-    def __init__(self, index):
-        self.index, self.proc, self.lines = index, None, []
+    def __init__(self, index, period_s=0.004):
+        self.index, self.period, self.proc, self.lines = index, period_s, None, []
+        self.sm, self.mx, self.reasons, self.stop_flag, self.th, self.nvml = [], None, set(), False, None, None
+
+    def _physical_index(self):
+        vis = os.environ.get('CUDA_VISIBLE_DEVICES')
+        if vis:
+            try:
+                return int(vis.split(',')[self.index])
+            except Exception:
+                pass
+        return self.index
 
     def start(self):
         try:
-            self.proc = subprocess.Popen(['nvidia-smi', '-i', str(self.index), '--query-gpu=' + self.Q, '--format=csv,noheader,nounits',
-                                          '-lms', '100'], stdout=subprocess.PIPE, stderr=subprocess.DEVNULL, text=True)
+            import pynvml as N
+            N.nvmlInit()
+            self.h = N.nvmlDeviceGetHandleByIndex(self._physical_index())
+            self.mx = float(N.nvmlDeviceGetMaxClockInfo(self.h, N.NVML_CLOCK_SM))
+            self.nvml = N
+            self.th = threading.Thread(target=self._poll, daemon=True)
+            self.th.start()
+            return
+        except Exception:
+            self.nvml = None
+        try:
+            self.proc = subprocess.Popen(['nvidia-smi', '-i', str(self._physical_index()), '--query-gpu=' + self.Q,
+                                          '--format=csv,noheader,nounits', '-lms', '20'], stdout=subprocess.PIPE,
+                                         stderr=subprocess.DEVNULL, text=True)
             self.th = threading.Thread(target=self._read, daemon=True)
             self.th.start()
         except Exception:
             self.proc = None
+
+    def _poll(self):
+        N = self.nvml
+        names = (('hw_slowdown', N.nvmlClocksEventReasonHwSlowdown), ('hw_thermal_slowdown', N.nvmlClocksEventReasonHwThermalSlowdown),
+                 ('sw_thermal_slowdown', N.nvmlClocksEventReasonSwThermalSlowdown), ('sw_power_cap', N.nvmlClocksEventReasonSwPowerCap))
+        while not self.stop_flag:
+            try:
+                self.sm.append(float(N.nvmlDeviceGetClockInfo(self.h, N.NVML_CLOCK_SM)))
+                r = N.nvmlDeviceGetCurrentClocksEventReasons(self.h)
+                for name, bit in names:
+                    if r & bit:
+                        self.reasons.add(name)
+            except Exception:
+                pass
+            time.sleep(self.period)
 
     def _read(self):
         for line in self.proc.stdout:
             self.lines.append(line.strip())
 
     def stop(self):
+        if self.nvml is not None:
+            self.stop_flag = True
+            self.th.join(timeout=2)
+            sm = sorted(self.sm)
+            return {'sm_mhz': sm[len(sm) // 2] if sm else None, 'sm_max_mhz': self.mx, 'reasons': sorted(self.reasons),
+                    'samples': len(sm), 'source': 'nvml'}
         if not self.proc:
-            return {'sm_mhz': None, 'sm_max_mhz': None, 'reasons': ['nvidia-smi unavailable']}
+            return {'sm_mhz': None, 'sm_max_mhz': None, 'reasons': ['nvml and nvidia-smi unavailable'], 'samples': 0}
         self.proc.terminate()
         try:
             self.proc.wait(timeout=5)
@@ -114,7 +159,7 @@ class ClockSampler:
                     reasons.add(name)
         sm.sort()
         return {'sm_mhz': sm[len(sm) // 2] if sm else None, 'sm_max_mhz': max(mx) if mx else None,
-                'reasons': sorted(reasons), 'samples': len(sm)}
+                'reasons': sorted(reasons), 'samples': len(sm), 'source': 'nvidia-smi'}
 
 
 def hbm_peak():
@@ -133,13 +178,30 @@ def ncu_traffic():
 
 
 # ------------------------------------------------------------------------------------------------ reference arm
+def cpu_kind():
+    """'reference' when oracle/_ref (the reference's own ORBextractor.cc, compiled in the build container) is present,
+    else 'port' (the C oracle restating it)"""
+    from oracle import reference as R
+    return 'reference' if os.path.exists(R.SO) else 'port'
+
+
+CPU_KIND_NOTE = {
+    'reference': "extraction = the reference's own src/ORBextractor.cc (oracle/_ref, OpenCV primitives through stand-ins backed by the C "
+                 "oracle); kNN2 = the C oracle's BFMatcher restatement (the reference's matcher needs its whole map/ROS stack)",
+    'port': 'the C oracle restating the reference (oracle/_ref absent)'}
+
+
 def cpu_reference(frames, threads, want_knn=True):
-    """the reference's CPU path for one batch: oracle ORBextractor over all frames (OpenMP over frames) + brute-force
-    kNN2 between consecutive frames.  Returns seconds."""
+    """the reference's CPU path for one batch: ORBextractor over all frames (OpenMP over frames, one extractor per
+    thread) + brute-force kNN2 between consecutive frames.  Returns seconds."""
     import numpy as np
     from oracle import oracle as O
+    from oracle import reference as R
     t0 = time.perf_counter()
-    kps, n, desc = O.extract_batch(frames, NFEAT, SCALE, NLEVELS, FAST_TH, threads=threads)
+    if os.path.exists(R.SO):
+        kps, n, desc = R.extract_batch(frames, NFEAT, SCALE, NLEVELS, FAST_TH, threads=threads)
+    else:
+        kps, n, desc = O.extract_batch(frames, NFEAT, SCALE, NLEVELS, FAST_TH, threads=threads)
     if want_knn:
         for f in range(len(frames) - 1):
             O.knn2(desc[f, :n[f]], desc[f + 1, :n[f + 1]], threads=threads)
@@ -169,9 +231,8 @@ def run_reference(args):
         'vs_baseline': None, 'dtype': 'u8', 'data': 'synthetic',
         'config': {'workload': set_shape(args.shape) + ' + brute-force Hamming kNN2 of consecutive '
                                'frames (BASELINE %s shape, batched)' % {'euroc': 'config 1', 'aqualoc': 'config 2', 'hd': 'config 5'}[args.shape], 'frames_per_step': nfr, 'keypoints': NFEAT},
-        'cpu_baseline': {'value': fps, 'unit': 'frames/s', 'cores': cores, 'kind': 'port',
-                         'sample': '%d frames per step, OpenMP over frames; the reference itself cannot be built here '
-                                   '(needs OpenCV 3.4 C++/ROS/Eigen), so this is the C oracle restating it' % nfr},
+        'cpu_baseline': {'value': fps, 'unit': 'frames/s', 'cores': cores, 'kind': cpu_kind(),
+                         'sample': '%d frames per step, OpenMP over frames; %s' % (nfr, CPU_KIND_NOTE[cpu_kind()])},
         'e2e': {'value': fps, 'unit': 'frames/s', 'h2d_bytes_per_step': 0, 'd2h_bytes_per_step': 0},
     }
     print(json.dumps(line), flush=True)
@@ -295,7 +356,7 @@ def run_ours(args):
             finish(i & 1, t)
             t = tn
 
-    Ke = max(3, min(K, 10))
+    Ke = max(3, min(K, 40))
     e2e_run(2)
     barrier()
     te = time.perf_counter()
@@ -372,14 +433,19 @@ def run_ours(args):
         if world == 1:
             # cpu_baseline: the oracle on this box's host cores, bounded sample of the same workload
             cores = os.cpu_count() or 1
-            ns = max(16, 4 * cores)
-            sample = frames[:ns] if ns <= B else make_frames(pkg.synth, ns, 1)
+            ns = min(B, max(16, 8 * cores))
+            sample = frames[:ns]
             cpu_reference(sample[:max(2, cores)], cores)
             tc = cpu_reference(sample, cores)
-            t1c = cpu_reference(sample[:max(4, ns // 8)], 1)
-            line['cpu_baseline'] = {'value': len(sample) / tc, 'unit': 'frames/s', 'cores': cores, 'kind': 'port',
-                                    'sample': '%d frames of the same workload (extraction + consecutive-frame kNN2), OpenMP over frames' % len(sample),
-                                    'single_thread_frames_per_s': max(4, ns // 8) / t1c}
+            reps = max(1, min(40, int(10.0 / max(tc, 1e-3))))          # ~10 s of all-core CPU work in total
+            for _ in range(reps - 1):
+                tc += cpu_reference(sample, cores)
+            n1 = max(4, min(ns, 128))
+            t1c = cpu_reference(sample[:n1], 1)
+            line['cpu_baseline'] = {'value': reps * len(sample) / tc, 'unit': 'frames/s', 'cores': cores, 'kind': cpu_kind(), 'what': CPU_KIND_NOTE[cpu_kind()],
+                                    'sample': '%d passes over %d frames of the same workload (extraction + consecutive-frame kNN2), OpenMP over '
+                                              'frames on all host cores; single-thread figure on %d frames' % (reps, len(sample), n1),
+                                    'single_thread_frames_per_s': n1 / t1c}
     if rank == 0:
         print(json.dumps(line), flush=True)
     if world > 1:
