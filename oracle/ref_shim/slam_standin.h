@@ -1,0 +1,125 @@
+// slam_standin.h — TEST INFRASTRUCTURE.  Stand-ins for the reference's FrameKTL / KeyFrame / MapPoint classes with
+// exactly the members src/ORBmatcher.cc touches, so that the UNMODIFIED reference matcher can be compiled here
+// (oracle/Makefile target `ref`: the real include/MapPoint.h, KeyFrame.h and FrameKTL.h pull in g2o, DBoW2, Boost, PCL
+// and ROS, so their include guards are pre-defined and this header is force-included instead).  Plain data holders:
+// the test driver (ref_matcher_driver.cpp) fills them; all matching logic that runs is the reference's.
+// GetFeaturesInArea (src/FrameKTL.cc:359-424, src/KeyFrame.cc:952-992 — not compilable here) forwards to the C oracle's
+// restatement.
+#ifndef UVIP_SLAM_STANDIN_H
+#define UVIP_SLAM_STANDIN_H
+#include <limits.h>
+#include <map>
+#include <set>
+#include <vector>
+#include "uvip_cv_standin.hpp"
+#include "Thirdparty/DBoW2/DBoW2/FeatureVector.h"
+
+using namespace std;        // the reference headers rely on it (include/ORBmatcher.h:71 uses an unqualified `pair`)
+
+#define FRAME_GRID_ROWS 48
+#define FRAME_GRID_COLS 64
+
+namespace USLAM {
+
+class KeyFrame;
+class FrameKTL;
+
+class MapPoint {
+public:
+    MapPoint() : mbTrackInView(false), mnTrackScaleLevel(0), mTrackProjX(0), mTrackProjY(0), mTrackViewCos(0), mnLastFrameSeen(0), mnId(0),
+                 bad(false), minDist(0), maxDist(0), nObs(1), replaced(0) {}
+    // tracking fields written by FrameKTL::isInFrustum (include/MapPoint.h:96-101)
+    bool mbTrackInView; int mnTrackScaleLevel; float mTrackProjX, mTrackProjY, mTrackViewCos;
+    long unsigned int mnLastFrameSeen, mnId;
+    bool isBad() { return bad; }
+    cv::Mat GetDescriptor() { return desc.clone(); }
+    cv::Mat GetWorldPos() { return pos.clone(); }
+    cv::Mat GetNormal() { return normal.clone(); }
+    float GetMinDistanceInvariance() { return minDist; }
+    float GetMaxDistanceInvariance() { return maxDist; }
+    int Observations() { return nObs; }
+    bool IsInKeyFrame(KeyFrame* kf) { return obs.count(kf) != 0; }
+    int GetIndexInKeyFrame(KeyFrame* kf) { return obs.count(kf) ? (int)obs[kf] : -1; }
+    void AddObservation(KeyFrame* kf, size_t idx) { if (!obs.count(kf)) { obs[kf] = idx; nObs++; } }
+    void Replace(MapPoint* p) { replaced = p; bad = true; }
+    void ComputeDistinctiveDescriptors() {}
+    // data
+    bool bad; float minDist, maxDist; int nObs; MapPoint* replaced;
+    cv::Mat desc, pos, normal;
+    std::map<KeyFrame*, size_t> obs;
+};
+
+// the frame grid shared by the two stand-ins: CSR over cols*rows cells as the oracle builds it
+struct GridStandin {
+    std::vector<float> kx, ky; std::vector<int32_t> octave, cell_start, cell_items;
+    float minX, minY, inv_w, inv_h; int cols, rows;
+    void build(const std::vector<cv::KeyPoint>& k, float mnMinX, float mnMaxX, float mnMinY, float mnMaxY)
+    {
+        cols = FRAME_GRID_COLS; rows = FRAME_GRID_ROWS; minX = mnMinX; minY = mnMinY;
+        inv_w = (float)cols / (mnMaxX - mnMinX); inv_h = (float)rows / (mnMaxY - mnMinY);       // src/FrameKTL.cc:150-151
+        const int n = (int)k.size();
+        kx.resize(n); ky.resize(n); octave.resize(n); cell_start.assign(cols * rows + 1, 0); cell_items.assign(n ? n : 1, 0);
+        for (int i = 0; i < n; i++) { kx[i] = k[i].pt.x; ky[i] = k[i].pt.y; octave[i] = k[i].octave; }
+        uo_grid_build(kx.data(), ky.data(), n, minX, minY, inv_w, inv_h, cols, rows, cell_start.data(), cell_items.data());
+    }
+    std::vector<size_t> area(float x, float y, float r, int minLevel, int maxLevel) const
+    {
+        std::vector<int32_t> out(kx.size() ? kx.size() : 1);
+        const int n = uo_features_in_area(kx.data(), ky.data(), octave.data(), cell_start.data(), cell_items.data(), minX, minY, inv_w, inv_h,
+                                          cols, rows, x, y, r, minLevel, maxLevel, out.data(), (int)out.size());
+        return std::vector<size_t>(out.begin(), out.begin() + n);
+    }
+};
+
+class FrameKTL {
+public:
+    FrameKTL() : fx(0), fy(0), cx(0), cy(0), mnMinX(0), mnMaxX(0), mnMinY(0), mnMaxY(0), mnScaleLevels(0), mnId(0) {}
+    std::vector<cv::KeyPoint> mvKeys, mvKeysUn;
+    cv::Mat mDescriptors, mTcw;
+    std::vector<MapPoint*> mvpMapPoints;
+    std::vector<bool> mvbOutlier;
+    std::vector<float> mvScaleFactors;
+    DBoW2::FeatureVector mFeatVec;
+    float fx, fy, cx, cy;
+    float mnMinX, mnMaxX, mnMinY, mnMaxY;       // static members in the reference (include/FrameKTL.h:173-176)
+    int mnScaleLevels; long unsigned int mnId;
+    GridStandin grid;
+    std::vector<size_t> GetFeaturesInArea(const float& x, const float& y, const float& r, const int minLevel = -1, const int maxLevel = -1) const
+    { return grid.area(x, y, r, minLevel, maxLevel); }
+};
+
+class KeyFrame {
+public:
+    KeyFrame() : fx(0), fy(0), cx(0), cy(0), mnId(0) {}
+    std::vector<cv::KeyPoint> keysUn;
+    cv::Mat descriptors, Rcw, tcw, Ow;
+    std::vector<MapPoint*> mapPoints;
+    std::vector<float> scaleFactors, levelSigma2;
+    DBoW2::FeatureVector featVec;
+    float fx, fy, cx, cy; long unsigned int mnId;
+    float minX, maxX, minY, maxY;
+    GridStandin grid;
+    std::vector<MapPoint*> GetMapPointMatches() { return mapPoints; }
+    MapPoint* GetMapPoint(const size_t& idx) { return mapPoints[idx]; }
+    std::set<MapPoint*> GetMapPoints() { std::set<MapPoint*> s; for (MapPoint* p : mapPoints) if (p && !p->isBad()) s.insert(p); return s; }
+    void AddMapPoint(MapPoint* p, const size_t& idx) { mapPoints[idx] = p; }
+    DBoW2::FeatureVector GetFeatureVector() { return featVec; }
+    cv::Mat GetDescriptor(const size_t& idx) { return descriptors.row((int)idx).clone(); }
+    cv::Mat GetDescriptors() { return descriptors.clone(); }
+    std::vector<cv::KeyPoint> GetKeyPointsUn() const { return keysUn; }
+    cv::KeyPoint GetKeyPointUn(const size_t& idx) const { return keysUn[idx]; }
+    int GetKeyPointScaleLevel(const size_t& idx) const { return keysUn[idx].octave; }
+    std::vector<float> GetScaleFactors() const { return scaleFactors; }
+    float GetScaleFactor(int level = 1) const { return scaleFactors[level]; }
+    int GetScaleLevels() const { return (int)scaleFactors.size(); }
+    float GetSigma2(int level = 1) const { return levelSigma2[level]; }
+    cv::Mat GetRotation() { return Rcw.clone(); }
+    cv::Mat GetTranslation() { return tcw.clone(); }
+    cv::Mat GetCameraCenter() { return Ow.clone(); }
+    bool IsInImage(const float& x, const float& y) const { return x >= minX && x < maxX && y >= minY && y < maxY; }     // src/KeyFrame.cc:994-997
+    // src/KeyFrame.cc:952-992: no level filter
+    std::vector<size_t> GetFeaturesInArea(const float& x, const float& y, const float& r) const { return grid.area(x, y, r, -1, -1); }
+};
+
+}  // namespace USLAM
+#endif

@@ -19,6 +19,8 @@
 typedef unsigned char uchar;
 #define CV_8U 0
 #define CV_8UC1 0
+#define CV_32F 5
+#define CV_32FC1 5
 #define CV_PI 3.1415926535897932384626433832795
 #define CV_Assert(expr) assert(expr)
 
@@ -61,46 +63,51 @@ enum { BORDER_CONSTANT = 0, BORDER_REFLECT_101 = 4, BORDER_ISOLATED = 16 };
 
 struct MatZeros { int rows, cols, type; };
 
-// 8-bit single-channel matrix header over a shared, reference-counted buffer (ROI views share the buffer).  The
-// buffer and its counter come from malloc, never from operator new, so that the driver's arena (ref_driver.cpp) only
-// ever sees the reference's own allocations.
+// Single-channel matrix header (CV_8U or CV_32F) over a shared, reference-counted buffer (ROI views share the
+// buffer).  The buffer and its counter come from malloc, never from operator new, so that the driver's arena
+// (ref_driver.cpp) only ever sees the reference's own allocations.
+struct MatT;
 class Mat {
 public:
     struct Step { size_t v; Step() : v(0) {} operator size_t() const { return v; } };
     uchar* data; int rows, cols; Step step;
-    Mat() : data(0), rows(0), cols(0), buf(0) {}
-    Mat(Size sz, int type) : data(0), rows(0), cols(0), buf(0) { create(sz.height, sz.width, type); }
-    Mat(int r, int c, int type) : data(0), rows(0), cols(0), buf(0) { create(r, c, type); }
-    Mat(int r, int c, int type, void* ext, size_t st) : data((uchar*)ext), rows(r), cols(c), buf(0) { (void)type; step.v = st; }
-    Mat(const Mat& m) : data(m.data), rows(m.rows), cols(m.cols), step(m.step), buf(m.buf) { retain(); }
-    Mat(const Mat& m, const Rect& r) : data(m.data + (size_t)r.y * m.step.v + r.x), rows(r.height), cols(r.width), step(m.step), buf(m.buf)
+    Mat() : data(0), rows(0), cols(0), tp(CV_8UC1), buf(0) {}
+    Mat(Size sz, int type) : data(0), rows(0), cols(0), tp(CV_8UC1), buf(0) { create(sz.height, sz.width, type); }
+    Mat(int r, int c, int type) : data(0), rows(0), cols(0), tp(CV_8UC1), buf(0) { create(r, c, type); }
+    Mat(int r, int c, int type, void* ext, size_t st = 0) : data((uchar*)ext), rows(r), cols(c), tp(type), buf(0) { step.v = st ? st : (size_t)c * esz(type); }
+    Mat(const Mat& m) : data(m.data), rows(m.rows), cols(m.cols), step(m.step), tp(m.tp), buf(m.buf) { retain(); }
+    Mat(const Mat& m, const Rect& r) : data(m.data + (size_t)r.y * m.step.v + (size_t)r.x * esz(m.tp)), rows(r.height), cols(r.width), step(m.step), tp(m.tp), buf(m.buf)
     { assert(r.x >= 0 && r.y >= 0 && r.x + r.width <= m.cols && r.y + r.height <= m.rows); retain(); }
-    Mat(const MatZeros& z) : data(0), rows(0), cols(0), buf(0) { *this = z; }
+    Mat(const MatZeros& z) : data(0), rows(0), cols(0), tp(CV_8UC1), buf(0) { *this = z; }
+    inline Mat(const MatT& e);
     ~Mat() { drop(); }
     Mat& operator=(const Mat& m)
     {
-        if (this != &m) { if (m.buf) ++*m.buf; drop(); data = m.data; rows = m.rows; cols = m.cols; step = m.step; buf = m.buf; }
+        if (this != &m) { if (m.buf) ++*m.buf; drop(); data = m.data; rows = m.rows; cols = m.cols; step = m.step; tp = m.tp; buf = m.buf; }
         return *this;
     }
     static MatZeros zeros(int r, int c, int type) { MatZeros z = {r, c, type}; return z; }
     // assigning Mat::zeros to a matrix of the same shape clears it in place (cv::Mat::operator=(const MatExpr&) -> create + setTo)
-    Mat& operator=(const MatZeros& z) { create(z.rows, z.cols, z.type); for (int y = 0; y < rows; y++) memset(data + (size_t)y * step.v, 0, (size_t)cols); return *this; }
+    Mat& operator=(const MatZeros& z) { create(z.rows, z.cols, z.type); for (int y = 0; y < rows; y++) memset(data + (size_t)y * step.v, 0, (size_t)cols * esz(tp)); return *this; }
     void create(int r, int c, int type)
     {
-        assert(type == CV_8UC1);
-        if (data && r == rows && c == cols) return;
+        assert(type == CV_8UC1 || type == CV_32F);
+        if (data && r == rows && c == cols && type == tp) return;
         drop();
-        buf = (int*)malloc(64 + (size_t)r * c + 64);
+        buf = (int*)malloc(64 + (size_t)r * c * esz(type) + 64);
         *buf = 1;
-        data = (uchar*)buf + 64; rows = r; cols = c; step.v = (size_t)c;
+        data = (uchar*)buf + 64; rows = r; cols = c; tp = type; step.v = (size_t)c * esz(type);
     }
     void release() { drop(); data = 0; rows = cols = 0; step.v = 0; }
     bool empty() const { return data == 0 || rows == 0 || cols == 0; }
-    int type() const { return CV_8UC1; }
-    size_t elemSize1() const { return 1; }
-    size_t step1() const { return step.v; }
+    int type() const { return tp; }
+    size_t elemSize() const { return esz(tp); }
+    size_t elemSize1() const { return esz(tp); }
+    size_t step1() const { return step.v / esz(tp); }
     Mat rowRange(int a, int b) const { return Mat(*this, Rect(0, a, cols, b - a)); }
     Mat colRange(int a, int b) const { return Mat(*this, Rect(a, 0, b - a, rows)); }
+    Mat row(int y) const { return Mat(*this, Rect(0, y, cols, 1)); }
+    Mat col(int x) const { return Mat(*this, Rect(x, 0, 1, rows)); }
     Mat operator()(const Rect& r) const { return Mat(*this, r); }
     template <typename T> T* ptr(int y = 0) { return (T*)(data + (size_t)y * step.v); }
     template <typename T> const T* ptr(int y = 0) const { return (const T*)(data + (size_t)y * step.v); }
@@ -108,12 +115,98 @@ public:
     const uchar* ptr(int y = 0) const { return data + (size_t)y * step.v; }
     template <typename T> T& at(int y, int x) { return ((T*)(data + (size_t)y * step.v))[x]; }
     template <typename T> const T& at(int y, int x) const { return ((const T*)(data + (size_t)y * step.v))[x]; }
-    Mat clone() const { Mat m(rows, cols, CV_8UC1); for (int y = 0; y < rows; y++) memcpy(m.ptr(y), ptr(y), (size_t)cols); return m; }
+    // single-index access to a row or column vector
+    template <typename T> T& at(int i) { return rows == 1 ? at<T>(0, i) : at<T>(i, 0); }
+    template <typename T> const T& at(int i) const { return rows == 1 ? at<T>(0, i) : at<T>(i, 0); }
+    Mat clone() const { Mat m(rows, cols, tp); for (int y = 0; y < rows; y++) memcpy(m.ptr(y), ptr(y), (size_t)cols * esz(tp)); return m; }
+    void copyTo(Mat& m) const { m.create(rows, cols, tp); for (int y = 0; y < rows; y++) memcpy(m.ptr(y), ptr(y), (size_t)cols * esz(tp)); }
+    // ---- CV_32F algebra (what src/ORBmatcher.cc needs); products and sums in float, left to right, like cv::gemm's
+    //      small-matrix path
+    inline struct MatT t() const;       // lazy alpha * A^T, see below
+    double dot(const Mat& o) const
+    {
+        assert(tp == CV_32F && o.tp == CV_32F && rows * cols == o.rows * o.cols);
+        double s = 0; const int n = rows * cols;      // cv::Mat::dot accumulates float products in double
+        for (int i = 0; i < n; i++) s += (double)lin(i) * (double)o.lin(i);
+        return s;
+    }
+    float lin(int i) const { return at<float>(i / cols, i % cols); }
 private:
+    int tp;
     int* buf;                       // reference counter at the head of the malloc'ed block, 0 for external data
+    static size_t esz(int type) { return type == CV_32F ? 4 : 1; }
     void retain() { if (buf) ++*buf; }
     void drop() { if (buf && --*buf == 0) free(buf); buf = 0; }
 };
+
+// cv::Mat products as OpenCV 3.4 evaluates them (core/src/matmul.cpp).  A*B (+C) without transposition and with inner
+// size 2..4 takes gemm's small-matrix path: products and sums in float, left to right, then (float)(t*alpha + c*beta) in
+// double.  Anything with a transposed operand (e.g. -R.t()*t) takes the generic path, which accumulates in double.
+struct MatProd { Mat a, b; inline operator Mat() const; };
+struct MatT { Mat a; double alpha; };
+inline MatT Mat::t() const { assert(tp == CV_32F); MatT e = {*this, 1.0}; return e; }
+inline Mat::Mat(const MatT& e) : data(0), rows(0), cols(0), tp(CV_8UC1), buf(0)
+{   // transpose, then scale through convertTo (double product, one rounding)
+    create(e.a.cols, e.a.rows, CV_32F);
+    for (int y = 0; y < e.a.rows; y++) for (int x = 0; x < e.a.cols; x++)
+        at<float>(x, y) = e.alpha == 1.0 ? e.a.at<float>(y, x) : (float)((double)e.a.at<float>(y, x) * e.alpha);
+}
+static inline Mat gemm_small(const Mat& a, const Mat& b, const Mat* c)
+{
+    assert(a.type() == CV_32F && b.type() == CV_32F && a.cols == b.rows);
+    Mat m(a.rows, b.cols, CV_32F);
+    const bool small = a.cols >= 2 && a.cols <= 4;
+    for (int y = 0; y < a.rows; y++) for (int x = 0; x < b.cols; x++) {
+        const double cc = c ? (double)c->at<float>(y, x) : 0.0;
+        if (small) {
+            float t = a.at<float>(y, 0) * b.at<float>(0, x);
+            for (int k = 1; k < a.cols; k++) t = t + a.at<float>(y, k) * b.at<float>(k, x);
+            m.at<float>(y, x) = (float)((double)t * 1.0 + cc * 1.0);
+        } else {
+            double sacc = 0;
+            for (int k = 0; k < a.cols; k++) sacc += (double)a.at<float>(y, k) * (double)b.at<float>(k, x);
+            m.at<float>(y, x) = (float)(sacc + cc);
+        }
+    }
+    return m;
+}
+inline MatProd::operator Mat() const { return gemm_small(a, b, 0); }
+static inline MatProd operator*(const Mat& a, const Mat& b) { MatProd p = {a, b}; return p; }
+static inline Mat operator+(const MatProd& p, const Mat& c) { return gemm_small(p.a, p.b, &c); }
+static inline MatT operator-(const MatT& e) { MatT r = {e.a, -e.alpha}; return r; }
+static inline MatT operator*(double s, const MatT& e) { MatT r = {e.a, e.alpha * s}; return r; }
+static inline Mat operator*(const MatT& e, const Mat& b)
+{   // alpha * A^T * B: generic gemm, double accumulation
+    assert(e.a.type() == CV_32F && b.type() == CV_32F && e.a.rows == b.rows);
+    Mat m(e.a.cols, b.cols, CV_32F);
+    for (int y = 0; y < e.a.cols; y++) for (int x = 0; x < b.cols; x++) {
+        double sacc = 0;
+        for (int k = 0; k < e.a.rows; k++) sacc += (double)e.a.at<float>(k, y) * (double)b.at<float>(k, x);
+        m.at<float>(y, x) = (float)(sacc * e.alpha);
+    }
+    return m;
+}
+static inline Mat mat_map2(const Mat& a, const Mat& b, float sb)
+{
+    assert(a.type() == CV_32F && b.type() == CV_32F && a.rows == b.rows && a.cols == b.cols);
+    Mat m(a.rows, a.cols, CV_32F);
+    for (int y = 0; y < a.rows; y++) for (int x = 0; x < a.cols; x++) m.at<float>(y, x) = a.at<float>(y, x) + sb * b.at<float>(y, x);
+    return m;
+}
+static inline Mat mat_scale(const Mat& a, double s)
+{   // cv::Mat * scalar / scalar go through convertTo(alpha): the product is formed in double and rounded to float once
+    assert(a.type() == CV_32F);
+    Mat m(a.rows, a.cols, CV_32F);
+    for (int y = 0; y < a.rows; y++) for (int x = 0; x < a.cols; x++) m.at<float>(y, x) = (float)((double)a.at<float>(y, x) * s);
+    return m;
+}
+static inline Mat operator+(const Mat& a, const Mat& b) { return mat_map2(a, b, 1.f); }
+static inline Mat operator-(const Mat& a, const Mat& b) { return mat_map2(a, b, -1.f); }
+static inline Mat operator-(const Mat& a) { return mat_scale(a, -1.0); }
+static inline Mat operator*(const Mat& a, double s) { return mat_scale(a, s); }
+static inline Mat operator*(double s, const Mat& a) { return mat_scale(a, s); }
+static inline Mat operator/(const Mat& a, double s) { return mat_scale(a, 1.0 / s); }
+static inline double norm(const Mat& a) { return sqrt(a.dot(a)); }
 
 class _InputArray {
 public:

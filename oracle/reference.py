@@ -103,3 +103,101 @@ def extract_batch(frames, nfeatures=1000, scale_factor=1.2, nlevels=8, fast_th=2
     if rc != 0:
         raise RuntimeError('ref_extract_batch failed: %d' % rc)
     return kps, n, desc
+
+
+# ------------------------------------------------------------------------------------------------ matcher
+MATCHER_SO = os.path.join(_HERE, '_ref', 'libref_orbmatcher.so')
+_MLIB = None
+
+
+def matcher_available():
+    return os.path.exists(MATCHER_SO) or os.path.exists('/root/reference/src/ORBmatcher.cc')
+
+
+def mlib():
+    """oracle/_ref/libref_orbmatcher.so: the reference's own src/ORBmatcher.cc over stand-in FrameKTL/KeyFrame/MapPoint types"""
+    global _MLIB
+    if _MLIB is None:
+        build()
+        if not os.path.exists(MATCHER_SO):
+            raise RuntimeError('oracle/_ref/libref_orbmatcher.so is not built and /root/reference is absent')
+        _MLIB = C.CDLL(MATCHER_SO)
+    return _MLIB
+
+
+def _f32(a):
+    return np.ascontiguousarray(a, np.float32)
+
+
+def _i32(a):
+    return np.ascontiguousarray(a, np.int32)
+
+
+def _u8(a):
+    return np.ascontiguousarray(a, np.uint8)
+
+
+def descriptor_distance(a, b):
+    return int(mlib().refm_descriptor_distance(_p(_u8(a)), _p(_u8(b))))
+
+
+def search_by_projection_mps(kx, ky, octave, kdesc, bounds, scale_factors, u, v, level, view_cos, qdesc, th, nnratio, taken=None,
+                             in_view=None, bad=None):
+    """ORBmatcher::SearchByProjection(FrameKTL&, vector<MapPoint*>&, th) -> (nmatches, owner[nk])"""
+    kx, ky, octave, kdesc = _f32(kx), _f32(ky), _i32(octave), _u8(kdesc)
+    nk, nq = len(kx), len(u)
+    owner = np.zeros(nk, np.int32)
+    tk = None if taken is None else _i32(taken)
+    iv = None if in_view is None else _u8(in_view)
+    bd = None if bad is None else _u8(bad)
+    sf = _f32(scale_factors)
+    n = mlib().refm_search_by_projection_mps(nk, _p(kx), _p(ky), _p(octave), _p(kdesc), _p(_f32(bounds)), len(sf), _p(sf), _p(tk),
+                                             nq, _p(_f32(u)), _p(_f32(v)), _p(_i32(level)), _p(_f32(view_cos)), _p(iv), _p(bd), _p(_u8(qdesc)),
+                                             C.c_float(th), C.c_float(nnratio), _p(owner))
+    return n, owner
+
+
+def search_by_projection_kf(kx, ky, octave, kangle, kdesc, bounds, scale_factors, Tcw, intr, has_mp, bad, found, pos, min_dist, pdesc, pangle,
+                            th, orb_dist, nnratio, check_ori=True, taken=None):
+    """ORBmatcher::SearchByProjection(FrameKTL&, KeyFrame*, sAlreadyFound, th, ORBdist) -> (nmatches, owner[nk])"""
+    kx, ky = _f32(kx), _f32(ky)
+    nk, npnt = len(kx), len(has_mp)
+    owner = np.zeros(nk, np.int32)
+    tk = None if taken is None else _i32(taken)
+    sf = _f32(scale_factors)
+    n = mlib().refm_search_by_projection_kf(nk, _p(kx), _p(ky), _p(_i32(octave)), _p(_f32(kangle)), _p(_u8(kdesc)), _p(_f32(bounds)), len(sf), _p(sf),
+                                            _p(tk), _p(_f32(Tcw)), _p(_f32(intr)), npnt, _p(_u8(has_mp)), _p(_u8(bad)), _p(_u8(found)), _p(_f32(pos)),
+                                            _p(_f32(min_dist)), _p(_u8(pdesc)), _p(_f32(pangle)), C.c_float(th), int(orb_dist), C.c_float(nnratio),
+                                            int(bool(check_ori)), _p(owner))
+    return n, owner
+
+
+def _featvec(fv):
+    """dict node id -> list of feature indices  ->  (ids, start, idx) flat arrays in ascending node order"""
+    ids = sorted(fv)
+    start = np.zeros(len(ids) + 1, np.int32)
+    idx = []
+    for i, k in enumerate(ids):
+        idx.extend(fv[k]); start[i + 1] = len(idx)
+    return _i32(ids), start, _i32(idx if idx else [0])
+
+
+def search_by_bow_kf_frame(kf_desc, kf_angle, has_mp, bad, kf_featvec, f_desc, f_angle, f_featvec, nnratio, check_ori=True):
+    """ORBmatcher::SearchByBoW(KeyFrame*, FrameKTL&, matches) -> (nmatches, keyframe slot per frame keypoint or -1)"""
+    ki, ks, kx = _featvec(kf_featvec); fi, fs, fx = _featvec(f_featvec)
+    nk = len(f_desc)
+    out = np.zeros(nk, np.int32)
+    n = mlib().refm_search_by_bow_kf_frame(len(kf_desc), _p(_u8(kf_desc)), _p(_f32(kf_angle)), _p(_u8(has_mp)), _p(_u8(bad)), len(ki), _p(ki), _p(ks), _p(kx),
+                                           nk, _p(_u8(f_desc)), _p(_f32(f_angle)), len(fi), _p(fi), _p(fs), _p(fx), C.c_float(nnratio),
+                                           int(bool(check_ori)), _p(out))
+    return n, out
+
+
+def search_by_bow_kf_kf(desc1, angle1, has1, bad1, fv1, desc2, angle2, has2, bad2, fv2, nnratio, check_ori=True):
+    """ORBmatcher::SearchByBoW(KeyFrame*, KeyFrame*, matches12) -> (nmatches, slot of keyframe 2 per slot of keyframe 1 or -1)"""
+    i1, s1, x1 = _featvec(fv1); i2, s2, x2 = _featvec(fv2)
+    out = np.zeros(len(desc1), np.int32)
+    n = mlib().refm_search_by_bow_kf_kf(len(desc1), _p(_u8(desc1)), _p(_f32(angle1)), _p(_u8(has1)), _p(_u8(bad1)), len(i1), _p(i1), _p(s1), _p(x1),
+                                        len(desc2), _p(_u8(desc2)), _p(_f32(angle2)), _p(_u8(has2)), _p(_u8(bad2)), len(i2), _p(i2), _p(s2), _p(x2),
+                                        C.c_float(nnratio), int(bool(check_ori)), _p(out))
+    return n, out

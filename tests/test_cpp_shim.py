@@ -135,7 +135,7 @@ def test_shim_matches_oracle(pkg, oracle, synth, shim_exe, tmp_path):
     obest, _ = oracle.distinctive_descriptors(rows, start)
     assert npnt == 64 and np.array_equal(best, obest)
     # 6. SearchByProjection(CurrentFrame, KeyFrame*, sAlreadyFound, th=10, ORBdist=100) through the shim: projection with the
-    #    current pose (double accumulation of float products, as cv::Mat products do), predicted level by lower_bound on the
+    #    current pose (cv::gemm small-matrix float path for R*x+t, double accumulation for -R.t()*t and cv::norm), predicted level by lower_bound on the
     #    scale factors, window levels [l-1, l+1], best-only + claims, rotation histogram rollback (src/ORBmatcher.cc:1622-1746)
     nr = int(take(np.int32, 1)[0]); rowner = take(np.int32, n)
     f32 = np.float32
@@ -157,11 +157,9 @@ def test_shim_matches_oracle(pkg, oracle, synth, shim_exe, tmp_path):
         z = f32(2.0) + f32(i % 7) * f32(0.5)
         X = np.array([(kps['x'][i] - cx) / fx * z, (kps['y'][i] - cy) / fy * z, z], np.float32)
         xc3 = np.zeros(3, np.float32)
-        for r in range(3):
-            acc = 0.0
-            for c in range(3):
-                acc += float(Rm[r, c]) * float(X[c])
-            xc3[r] = f32(acc + float(tv[r]))
+        for r in range(3):                  # cv::gemm 3x3 path: float products and sums, (float)(t + c) in double
+            t_ = f32(Rm[r, 0] * X[0]); t_ = f32(t_ + f32(Rm[r, 1] * X[1])); t_ = f32(t_ + f32(Rm[r, 2] * X[2]))
+            xc3[r] = f32(float(t_) + float(tv[r]))
         invz = f32(1.0 / float(xc3[2]))
         u_ = fx * xc3[0] * invz + cx; v_ = fy * xc3[1] * invz + cy
         if u_ < 0 or u_ > W or v_ < 0 or v_ > H:

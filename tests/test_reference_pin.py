@@ -152,3 +152,275 @@ def test_cuda_equals_reference_occupancy_grid(gpu, synth):
         rk, rd = rex(img, keypoints=inc, grid=g_r, min_px_dist=mpd, full_detect=False, num_needed=need)
         assert_cuda_matches(gk, gd, rk, rd, step)
         assert np.array_equal(g_g, g_r), step
+
+
+# ---------------------------------------------------------------------------------------------------- matcher
+# oracle/_ref/libref_orbmatcher.so = the reference's own src/ORBmatcher.cc over stand-in FrameKTL/KeyFrame/MapPoint data
+# holders (oracle/ref_shim/slam_standin.h).  The oracle's matcher restatement must give the same claims.
+needs_mref = pytest.mark.skipif(not R.matcher_available(), reason='oracle/_ref matcher not built and /root/reference absent')
+
+
+def scale_factors(n=8, s=1.2):
+    sf = [np.float32(1)]
+    for _ in range(n - 1):
+        sf.append(np.float32(sf[-1] * np.float32(s)))
+    return np.array(sf, np.float32)
+
+
+@needs_mref
+def test_descriptor_distance_equals_reference(oracle):
+    rng = np.random.default_rng(1)
+    for i in range(200):
+        a = rng.integers(0, 256, 32, dtype=np.uint8); b = rng.integers(0, 256, 32, dtype=np.uint8)
+        if i == 0:
+            b = a.copy()
+        if i == 1:
+            b = ~a
+        assert R.descriptor_distance(a, b) == oracle.descriptor_distance(a, b) == int(np.unpackbits(a ^ b).sum())
+
+
+def m4_oracle(oracle, c, th, ratio, W, H, taken=None, use=None):
+    sf = scale_factors()
+    rad = np.array([oracle.lib().uo_radius_by_viewing_cos(float(x)) for x in c['view_cos']], np.float32)
+    if th != 1.0:
+        rad = rad * np.float32(th)
+    r_ = (rad * sf[c['level']]).astype(np.float32)
+    inv_w = np.float32(64.0) / np.float32(W); inv_h = np.float32(48.0) / np.float32(H)
+    start, items = oracle.grid_build(c['kx'], c['ky'], 0.0, 0.0, float(inv_w), float(inv_h))
+    q = np.arange(len(c['u'])) if use is None else np.nonzero(use)[0]
+    n, match, tk = oracle.search_window(0, 100, np.float32(ratio), c['u'][q], c['v'][q], r_[q], c['level'][q] - 1, c['level'][q], c['qdesc'][q],
+                                        c['kx'], c['ky'], c['octave'], c['kdesc'], start, items, 0.0, 0.0, float(inv_w), float(inv_h), taken=taken)
+    owner = np.where(tk >= 0, q[np.clip(tk, 0, len(q) - 1)], tk).astype(np.int32)
+    return n, owner
+
+
+@needs_mref
+@pytest.mark.parametrize('th,ratio', [(1.0, 0.8), (3.0, 0.8), (5.0, 0.6), (1.0, 0.95)])
+def test_search_by_projection_cfg3_equals_reference(oracle, synth, th, ratio):
+    """BASELINE config 3: 10 000 projected map points vs a 2000-keypoint frame (src/ORBmatcher.cc:49-125)."""
+    W, H = 752, 480
+    c = synth.projection_case()
+    nq, nk = len(c['u']), len(c['kx'])
+    in_view = (np.arange(nq) % 17 != 3); bad = (np.arange(nq) % 29 == 7)
+    taken = np.where(np.arange(nk) % 13 == 2, -2, -1).astype(np.int32)
+    on, oowner = m4_oracle(oracle, c, th, ratio, W, H, taken=taken, use=in_view & ~bad)
+    rn, rowner = R.search_by_projection_mps(c['kx'], c['ky'], c['octave'], c['kdesc'], [0, W, 0, H], scale_factors(), c['u'], c['v'], c['level'],
+                                            c['view_cos'], c['qdesc'], th, ratio, taken=taken, in_view=in_view, bad=bad)
+    assert on == rn and rn > 1000
+    assert np.array_equal(oowner, rowner)
+
+
+def frame_for_matching(oracle, synth, seed=1, W=752, H=480):
+    img = synth.synth_frame(seed, W, H)
+    return oracle.Extractor(1000, 1.2, 8, 1, 20)(img)
+
+
+def m5_scene(kps, W, H, sf):
+    """keyframe map points that project near the frame's own keypoints under a small pose change; replay of
+    src/ORBmatcher.cc:1626-1672 with cv::Mat arithmetic as OpenCV 3.4 evaluates it (R*x+t: float products and sums;
+    -R.t()*t and cv::norm: double accumulation)"""
+    f32 = np.float32
+    n = len(kps)
+    fx, fy, cx, cy = f32(458.0), f32(457.0), f32(367.0), f32(248.0)
+    c_, s_ = f32(0.99995), f32(0.0099998)
+    T = np.array([[c_, -s_, 0, f32(0.01)], [s_, c_, 0, f32(-0.02)], [0, 0, 1, f32(0.03)], [0, 0, 0, 1]], np.float32)
+    Rm, tv = T[:3, :3], T[:3, 3]
+    Ow = np.array([f32(-1.0 * sum(float(Rm[r, c]) * float(tv[r]) for r in range(3))) for c in range(3)], np.float32)
+    has_mp = (np.arange(n) % 9 != 0); bad = (np.arange(n) % 23 == 0); found = (np.arange(n) % 10 == 1)
+    pos = np.zeros((n, 3), np.float32); min_dist = np.ones(n, np.float32)
+    q = dict(u=[], v=[], r=[], lo=[], hi=[], who=[])
+    for i in range(n):
+        z = f32(2.0) + f32(i % 7) * f32(0.5)
+        X = np.array([(kps['x'][i] - cx) / fx * z, (kps['y'][i] - cy) / fy * z, z], np.float32)
+        pos[i] = X
+        min_dist[i] = z / sf[kps['octave'][i]] * f32(1.05)
+        if not has_mp[i] or bad[i] or found[i]:
+            continue
+        xc3 = np.zeros(3, np.float32)
+        for r in range(3):
+            t = f32(Rm[r, 0] * X[0])
+            t = f32(t + f32(Rm[r, 1] * X[1])); t = f32(t + f32(Rm[r, 2] * X[2]))
+            xc3[r] = f32(float(t) + float(tv[r]))
+        invz = f32(1.0 / float(xc3[2]))
+        u_ = f32(f32(f32(fx * xc3[0]) * invz) + cx); v_ = f32(f32(f32(fy * xc3[1]) * invz) + cy)
+        if u_ < 0 or u_ > W or v_ < 0 or v_ > H:
+            continue
+        po = (X - Ow).astype(np.float32)
+        d3 = f32(np.sqrt(sum(float(p) * float(p) for p in po)))
+        ratio = f32(d3 / min_dist[i])
+        lv = min(int(np.searchsorted(sf, ratio, side='left')), len(sf) - 1)
+        q['u'].append(u_); q['v'].append(v_); q['lo'].append(lv - 1); q['hi'].append(lv + 1); q['who'].append(i); q['r'].append(lv)
+    return dict(T=T, intr=[fx, fy, cx, cy], has_mp=has_mp, bad=bad, found=found, pos=pos, min_dist=min_dist, q=q)
+
+
+@needs_mref
+@pytest.mark.parametrize('th,orb_dist,check_ori', [(10.0, 100, True), (3.0, 64, True), (10.0, 100, False)])
+def test_search_by_projection_keyframe_equals_reference(oracle, synth, th, orb_dist, check_ori):
+    """src/ORBmatcher.cc:1622-1746: pose projection, lower_bound level prediction, levels [l-1, l+1], best-only, claims,
+    rotation histogram (ComputeThreeMaxima :1748-1789)."""
+    W, H = 752, 480
+    kps, desc = frame_for_matching(oracle, synth)
+    n = len(kps); sf = scale_factors()
+    S = m5_scene(kps, W, H, sf); q = S['q']; who = np.array(q['who'])
+    taken0 = np.where(np.arange(n) % 31 == 5, -2, -1).astype(np.int32)
+    inv_w = np.float32(64.0) / np.float32(W); inv_h = np.float32(48.0) / np.float32(H)
+    start, items = oracle.grid_build(kps['x'], kps['y'], 0.0, 0.0, float(inv_w), float(inv_h))
+    qr = (np.float32(th) * sf[np.array(q['r'])]).astype(np.float32)
+    on, om, _ = oracle.search_window(1, orb_dist, np.float32(0.9), q['u'], q['v'], qr, q['lo'], q['hi'], desc[who], kps['x'], kps['y'],
+                                     kps['octave'].astype(np.int32), desc, start, items, 0.0, 0.0, float(inv_w), float(inv_h), taken=taken0)
+    kept = oracle.rot_hist_filter(om, kps['angle'][who], kps['angle']) if check_ori else om
+    expect = np.where(np.arange(n) % 31 == 5, -2, -1).astype(np.int32)
+    for qi, k in enumerate(kept):
+        if k >= 0:
+            expect[k] = who[qi]
+    rn, rowner = R.search_by_projection_kf(kps['x'], kps['y'], kps['octave'], kps['angle'], desc, [0, W, 0, H], sf, S['T'], S['intr'], S['has_mp'],
+                                           S['bad'], S['found'], S['pos'], S['min_dist'], desc, kps['angle'], th, orb_dist, 0.9, check_ori, taken=taken0)
+    assert rn == int((kept >= 0).sum()) and rn > 100
+    assert np.array_equal(rowner, expect)
+
+
+def bow_scene(kps, n):
+    node = (kps['x'] / np.float32(64)).astype(np.int64) + 16 * (kps['y'] / np.float32(64)).astype(np.int64)
+    return node
+
+
+@needs_mref
+@pytest.mark.parametrize('ratio,check_ori', [(0.9, True), (0.7, True), (0.9, False)])
+def test_search_by_bow_keyframe_frame_equals_reference(oracle, synth, ratio, check_ori):
+    """src/ORBmatcher.cc:155-284: merge-join of the two FeatureVectors, top-2 inside a node, TH_LOW, ratio, claims, histogram."""
+    kps, desc = frame_for_matching(oracle, synth)
+    kps2, desc2 = frame_for_matching(oracle, synth, seed=1)       # same scene: the frame's descriptors with a few bits flipped
+    n = len(kps)
+    rng = np.random.default_rng(3)
+    fdesc = desc.copy()
+    flip = rng.integers(0, 256, (n, 12))
+    for j in range(12):
+        sel = rng.random(n) < 0.7
+        fdesc[sel, flip[sel, j] >> 3] ^= (1 << (flip[sel, j] & 7)).astype(np.uint8)
+    fangle = np.mod(kps['angle'] + rng.normal(0, 8, n).astype(np.float32) + np.where(rng.random(n) < 0.2, 90, 0), 360).astype(np.float32)
+    node = bow_scene(kps, n)
+    kf_fv, f_fv = {}, {}
+    for k in range(n):
+        kf_fv.setdefault(int(node[k]), []).append(k)
+        if k % 17 != 3:
+            f_fv.setdefault(int(node[k]) + (1000 if k % 29 == 0 else 0), []).append(k)
+    has_mp = (np.arange(n) % 7 != 0); bad = (np.arange(n) % 19 == 0)
+    queries, cs, ci = [], [0], []
+    for nd in sorted(kf_fv):
+        if nd not in f_fv:
+            continue
+        for k in kf_fv[nd]:
+            if not has_mp[k] or bad[k]:
+                continue
+            queries.append(k); ci.extend(f_fv[nd]); cs.append(len(ci))
+    queries = np.array(queries)
+    on, om, _ = oracle.search_lists(2, 50, np.float32(ratio), desc[queries], np.array(cs, np.int32), np.array(ci, np.int32), fdesc)
+    if check_ori:
+        om = oracle.rot_hist_filter(om, kps['angle'][queries], fangle)
+    expect = np.full(n, -1, np.int32)
+    for qi, k in enumerate(om):
+        if k >= 0:
+            expect[k] = queries[qi]
+    rn, rmatch = R.search_by_bow_kf_frame(desc, kps['angle'], has_mp, bad, kf_fv, fdesc, fangle, f_fv, ratio, check_ori)
+    assert rn == int((om >= 0).sum()) and rn > 200
+    assert np.array_equal(rmatch, expect)
+
+
+@needs_mref
+@pytest.mark.parametrize('ratio,check_ori', [(0.9, True), (0.75, False)])
+def test_search_by_bow_keyframe_keyframe_equals_reference(oracle, synth, ratio, check_ori):
+    """src/ORBmatcher.cc:715-850: strict best < TH_LOW, ratio, claims on the second keyframe, candidates without a map point
+    dropped, histogram rollback."""
+    kps, desc = frame_for_matching(oracle, synth)
+    n = len(kps)
+    rng = np.random.default_rng(4)
+    d2 = desc.copy()
+    flip = rng.integers(0, 256, (n, 10))
+    for j in range(10):
+        sel = rng.random(n) < 0.6
+        d2[sel, flip[sel, j] >> 3] ^= (1 << (flip[sel, j] & 7)).astype(np.uint8)
+    a2 = np.mod(kps['angle'] + rng.normal(0, 6, n).astype(np.float32) + np.where(rng.random(n) < 0.15, 120, 0), 360).astype(np.float32)
+    node = bow_scene(kps, n)
+    fv1, fv2 = {}, {}
+    for k in range(n):
+        fv1.setdefault(int(node[k]), []).append(k)
+        if k % 15 != 4:
+            fv2.setdefault(int(node[k]) + (2000 if k % 37 == 0 else 0), []).append(k)
+    has1 = (np.arange(n) % 7 != 0); bad1 = (np.arange(n) % 19 == 0)
+    has2 = (np.arange(n) % 6 != 1); bad2 = (np.arange(n) % 21 == 2)
+    q, cs, ci = [], [0], []
+    for nd in sorted(fv1):
+        if nd not in fv2:
+            continue
+        for k in fv1[nd]:
+            if not has1[k] or bad1[k]:
+                continue
+            q.append(k); ci.extend(j for j in fv2[nd] if has2[j] and not bad2[j]); cs.append(len(ci))
+    q = np.array(q)
+    on, om, _ = oracle.search_lists(3, 50, np.float32(ratio), desc[q], np.array(cs, np.int32), np.array(ci or [0], np.int32), d2)
+    if check_ori:
+        om = oracle.rot_hist_filter(om, kps['angle'][q], a2)
+    expect = np.full(n, -1, np.int32); expect[q[om >= 0]] = om[om >= 0]
+    rn, r12 = R.search_by_bow_kf_kf(desc, kps['angle'], has1, bad1, fv1, d2, a2, has2, bad2, fv2, ratio, check_ori)
+    assert rn == int((om >= 0).sum()) and rn > 150
+    assert np.array_equal(r12, expect)
+
+
+@needs_mref
+@pytest.mark.gpu
+@pytest.mark.parametrize('th', [1.0, 3.0])
+def test_cuda_search_by_projection_cfg3_equals_reference(gpu, synth, th):
+    """BASELINE config 3 on the GPU (k_grid_build + k_search_window through the C-ABI) against the reference's compiled
+    ORBmatcher::SearchByProjection(FrameKTL&, vector<MapPoint*>&, th)."""
+    W, H = 752, 480
+    c = synth.projection_case()
+    m = gpu.ORBmatcher(0.8, True)
+    grid = m.grid_build(c['kx'], c['ky'], c['bounds'])
+    sf = scale_factors()
+    frame = dict(kx=c['kx'], ky=c['ky'], octave=c['octave'], kdesc=c['kdesc'], grid=grid, scale_factors=sf)
+    mps = dict(u=c['u'], v=c['v'], level=c['level'], view_cos=c['view_cos'], desc=c['qdesc'])
+    n, match, taken = m.SearchByProjection(frame, mps, th)
+    rn, rowner = R.search_by_projection_mps(c['kx'], c['ky'], c['octave'], c['kdesc'], [0, W, 0, H], sf, c['u'], c['v'], c['level'],
+                                            c['view_cos'], c['qdesc'], th, 0.8)
+    assert n == rn and n > 1000
+    assert np.array_equal(taken, rowner)
+
+
+@needs_mref
+@pytest.mark.gpu
+def test_cuda_search_by_bow_lists_equals_reference(gpu, oracle, synth):
+    """uvip_search_lists mode 2 + uvip_rot_hist_filter on the GPU against the reference's compiled SearchByBoW(KeyFrame*, FrameKTL&)."""
+    kps, desc = frame_for_matching(oracle, synth)
+    n = len(kps)
+    rng = np.random.default_rng(3)
+    fdesc = desc.copy()
+    flip = rng.integers(0, 256, (n, 12))
+    for j in range(12):
+        sel = rng.random(n) < 0.7
+        fdesc[sel, flip[sel, j] >> 3] ^= (1 << (flip[sel, j] & 7)).astype(np.uint8)
+    fangle = np.mod(kps['angle'] + rng.normal(0, 8, n).astype(np.float32), 360).astype(np.float32)
+    node = bow_scene(kps, n)
+    kf_fv, f_fv = {}, {}
+    for k in range(n):
+        kf_fv.setdefault(int(node[k]), []).append(k)
+        if k % 17 != 3:
+            f_fv.setdefault(int(node[k]), []).append(k)
+    has_mp = (np.arange(n) % 7 != 0); bad = (np.arange(n) % 19 == 0)
+    queries, cs, ci = [], [0], []
+    for nd in sorted(kf_fv):
+        if nd not in f_fv:
+            continue
+        for k in kf_fv[nd]:
+            if has_mp[k] and not bad[k]:
+                queries.append(k); ci.extend(f_fv[nd]); cs.append(len(ci))
+    queries = np.array(queries)
+    m = gpu.ORBmatcher(0.9, True)
+    gn, gm, _ = m.search_lists(2, 50, desc[queries], np.array(cs, np.int32), np.array(ci, np.int32), fdesc)
+    gm = m.rot_hist_filter(gm, kps['angle'][queries], fangle)
+    expect = np.full(n, -1, np.int32)
+    for qi, k in enumerate(gm):
+        if k >= 0:
+            expect[k] = queries[qi]
+    rn, rmatch = R.search_by_bow_kf_frame(desc, kps['angle'], has_mp, bad, kf_fv, fdesc, fangle, f_fv, 0.9, True)
+    assert rn == int((gm >= 0).sum()) and rn > 200
+    assert np.array_equal(rmatch, expect)

@@ -89,8 +89,8 @@ public:
 
     // SearchByProjection(FrameKTL& CurrentFrame, KeyFrame* pKF, const set<MapPoint*>& sAlreadyFound, th, ORBdist)
     // (src/ORBmatcher.cc:1622-1746; relocalisation and keyframe tracking, src/Tracking.cc:2480,2494,3020,3026).  The host
-    // side projects the keyframe's map points with the current pose exactly as :1650-1678 does (cv::Mat products
-    // accumulate float products in double and round once, cv::norm likewise), the window search + claims run in
+    // side projects the keyframe's map points with the current pose exactly as :1650-1678 does (Rcw*x+tcw through
+    // cv::gemm's small-matrix float path; -Rcw.t()*tcw and cv::norm accumulate in double), the window search + claims run in
     // uvip_search_window mode 1 and the rotation histogram in uvip_rot_hist_filter.
     // FrameT needs: mTcw (4x4 CV_32F), fx, fy, cx, cy, mnMinX/MaxX/MinY/MaxY, mvScaleFactors, mnScaleLevels, mvKeysUn,
     //               mDescriptors, mvpMapPoints, mfGridElement{Width,Height}Inv;  KeyFrameT: GetMapPointMatches(),
@@ -119,8 +119,11 @@ public:
             float X[3], xc3[3];
             for (int r = 0; r < 3; r++) X[r] = x3Dw.template ptr<float>(r)[0];
             for (int r = 0; r < 3; r++) {                                          // x3Dc = Rcw*x3Dw+tcw  (:1651)
-                double s = 0; for (int c = 0; c < 3; c++) s += (double)R[r][c] * (double)X[c];
-                xc3[r] = (float)(s + (double)t[r]);
+                // cv::gemm's 3x3 path (core/src/matmul.cpp): float products and sums, then (float)(t*alpha + c*beta) in double
+                float s = R[r][0] * X[0];
+                s = s + R[r][1] * X[1];
+                s = s + R[r][2] * X[2];
+                xc3[r] = (float)((double)s + (double)t[r]);
             }
             const float xc = xc3[0], yc = xc3[1];
             const float invzc = (float)(1.0 / xc3[2]);
