@@ -187,4 +187,49 @@ int refm_search_by_bow_kf_kf(int n1, const uint8_t* desc1, const float* angle1, 
     return n;
 }
 
+// ORBmatcher::Fuse(KeyFrame*, vector<MapPoint*>&, th)  (src/ORBmatcher.cc:1016-1134).  Keyframe: keypoints, descriptors, pose
+// (Rcw 3x3 row-major, tcw, Ow), intrinsics, image bounds, scale factors, kf_has_mp/kf_bad per slot.  Map points: world
+// position, normal, min/max distance, descriptor, null/bad/in-keyframe flags.
+// action[i]: 0 = nothing, 1 = replaced by the keyframe's map point at slot target[i], 2 = added to the keyframe at slot
+// target[i], 3 = hit a slot whose map point is bad (counted, nothing done).  Returns nFused.
+int refm_fuse(int nk, const float* kx, const float* ky, const int32_t* octave, const uint8_t* kdesc, const float* bounds, int nlevels,
+              const float* sf, const float* Rcw, const float* tcw, const float* Ow, const float* intr, const uint8_t* kf_has_mp,
+              const uint8_t* kf_bad, int np, const uint8_t* is_null, const uint8_t* bad, const uint8_t* in_kf, const float* pos,
+              const float* normal, const float* min_dist, const float* max_dist, const uint8_t* pdesc, float th, int32_t* action,
+              int32_t* target)
+{
+    KeyFrame KF;
+    fill_keys(KF.keysUn, nk, kx, ky, octave, 0);
+    KF.descriptors = desc_mat(kdesc, nk);
+    KF.minX = bounds[0]; KF.maxX = bounds[1]; KF.minY = bounds[2]; KF.maxY = bounds[3];
+    KF.grid.build(KF.keysUn, KF.minX, KF.maxX, KF.minY, KF.maxY);
+    KF.scaleFactors.assign(sf, sf + nlevels);
+    KF.Rcw = cv::Mat(3, 3, CV_32F); memcpy(KF.Rcw.data, Rcw, 36);
+    KF.tcw = vec3(tcw); KF.Ow = vec3(Ow);
+    KF.fx = intr[0]; KF.fy = intr[1]; KF.cx = intr[2]; KF.cy = intr[3];
+    std::vector<MapPoint> kfmp(nk), mps(np);
+    KF.mapPoints.assign(nk, (MapPoint*)0);
+    for (int i = 0; i < nk; i++) if (kf_has_mp[i]) { kfmp[i].bad = kf_bad[i] != 0; KF.mapPoints[i] = &kfmp[i]; }
+    std::vector<MapPoint*> vp(np, (MapPoint*)0);
+    for (int i = 0; i < np; i++) {
+        if (is_null[i]) continue;
+        MapPoint& m = mps[i];
+        m.bad = bad[i] != 0; m.pos = vec3(pos + 3 * (size_t)i); m.normal = vec3(normal + 3 * (size_t)i);
+        m.minDist = min_dist[i]; m.maxDist = max_dist[i]; m.desc = desc_mat(pdesc + (size_t)i * 32, 1);
+        if (in_kf[i]) m.obs[&KF] = 0;
+        vp[i] = &m;
+    }
+    std::vector<MapPoint*> before(KF.mapPoints);
+    ORBmatcher matcher(0.6f, true);
+    const int n = matcher.Fuse(&KF, vp, th);
+    for (int i = 0; i < np; i++) {
+        action[i] = 0; target[i] = -1;
+        if (is_null[i]) continue;
+        MapPoint& m = mps[i];
+        if (m.replaced) { action[i] = 1; target[i] = (int32_t)(m.replaced - &kfmp[0]); if (m.replaced >= &mps[0] && m.replaced < &mps[0] + np) target[i] = -2 - (int32_t)(m.replaced - &mps[0]); }
+        else if (!in_kf[i] && m.obs.count(&KF)) { action[i] = 2; target[i] = (int32_t)m.obs[&KF]; }
+    }
+    return n;
+}
+
 }  // extern "C"

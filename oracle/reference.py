@@ -201,3 +201,16 @@ def search_by_bow_kf_kf(desc1, angle1, has1, bad1, fv1, desc2, angle2, has2, bad
                                         len(desc2), _p(_u8(desc2)), _p(_f32(angle2)), _p(_u8(has2)), _p(_u8(bad2)), len(i2), _p(i2), _p(s2), _p(x2),
                                         C.c_float(nnratio), int(bool(check_ori)), _p(out))
     return n, out
+
+
+def fuse(kx, ky, octave, kdesc, bounds, scale_factors, Rcw, tcw, Ow, intr, kf_has_mp, kf_bad, is_null, bad, in_kf, pos, normal, min_dist,
+         max_dist, pdesc, th):
+    """ORBmatcher::Fuse(KeyFrame*, vector<MapPoint*>&, th) -> (nFused, action[np], target[np]); see ref_matcher_driver.cpp"""
+    nk, npnt = len(kx), len(is_null)
+    sf = _f32(scale_factors)
+    action = np.zeros(npnt, np.int32); target = np.zeros(npnt, np.int32)
+    n = mlib().refm_fuse(nk, _p(_f32(kx)), _p(_f32(ky)), _p(_i32(octave)), _p(_u8(kdesc)), _p(_f32(bounds)), len(sf), _p(sf), _p(_f32(Rcw)),
+                         _p(_f32(tcw)), _p(_f32(Ow)), _p(_f32(intr)), _p(_u8(kf_has_mp)), _p(_u8(kf_bad)), npnt, _p(_u8(is_null)), _p(_u8(bad)),
+                         _p(_u8(in_kf)), _p(_f32(pos)), _p(_f32(normal)), _p(_f32(min_dist)), _p(_f32(max_dist)), _p(_u8(pdesc)), C.c_float(th),
+                         _p(action), _p(target))
+    return n, action, target

@@ -424,3 +424,101 @@ def test_cuda_search_by_bow_lists_equals_reference(gpu, oracle, synth):
     rn, rmatch = R.search_by_bow_kf_frame(desc, kps['angle'], has_mp, bad, kf_fv, fdesc, fangle, f_fv, 0.9, True)
     assert rn == int((gm >= 0).sum()) and rn > 200
     assert np.array_equal(rmatch, expect)
+
+
+def fuse_scene(oracle, kps, desc, W, H, sf, th):
+    """map points that project near the keyframe's keypoints; numpy replay of the geometry of src/ORBmatcher.cc:1036-1086 and
+    the oracle's best-only search without claims (mode 4) for :1088-1113"""
+    f32 = np.float32
+    n = len(kps)
+    fx, fy, cx, cy = f32(458.0), f32(457.0), f32(367.0), f32(248.0)
+    c_, s_ = f32(0.99995), f32(0.0099998)
+    Rm = np.array([[c_, -s_, 0], [s_, c_, 0], [0, 0, 1]], np.float32); tv = np.array([0.01, -0.02, 0.03], np.float32)
+    Ow = np.array([f32(-1.0 * sum(float(Rm[r, c]) * float(tv[r]) for r in range(3))) for c in range(3)], np.float32)
+    npnt = 2 * n
+    src = np.arange(npnt) % n
+    rng = np.random.default_rng(11)
+    is_null = (np.arange(npnt) % 14 == 3); bad = (np.arange(npnt) % 25 == 6); in_kf = (np.arange(npnt) % 9 == 2)
+    pos = np.zeros((npnt, 3), np.float32); normal = np.zeros((npnt, 3), np.float32)
+    min_dist = np.ones(npnt, np.float32); max_dist = np.ones(npnt, np.float32)
+    pdesc = desc[src].copy()
+    flip = rng.integers(0, 256, (npnt, 14))
+    for j in range(14):
+        sel = rng.random(npnt) < 0.6
+        pdesc[sel, flip[sel, j] >> 3] ^= (1 << (flip[sel, j] & 7)).astype(np.uint8)
+    q = dict(u=[], v=[], r=[], lo=[], hi=[], who=[])
+    for i in range(npnt):
+        k = src[i]
+        z = f32(2.0) + f32(i % 7) * f32(0.5)
+        if i % 41 == 0:
+            z = f32(-1.0)                                  # behind the camera
+        jx = f32(((i * 7) % 5) - 2) * f32(0.8); jy = f32(((i * 3) % 5) - 2) * f32(0.6)
+        X = np.array([(kps['x'][k] + jx - cx) / fx * z, (kps['y'][k] + jy - cy) / fy * z, z], np.float32)
+        pos[i] = X
+        min_dist[i] = abs(z) / sf[kps['octave'][k]] * f32(1.05) * (f32(3.0) if i % 37 == 1 else f32(1.0))     # some too close
+        max_dist[i] = abs(z) * f32(1.4) * (f32(0.5) if i % 43 == 2 else f32(1.0))                                # some too far
+        nrm = X - Ow
+        if i % 31 == 4:
+            nrm = np.array([1, 0, 0], np.float32) * np.linalg.norm(nrm)                                        # viewed from the side
+        normal[i] = (nrm / np.linalg.norm(nrm)).astype(np.float32)
+        if is_null[i] or bad[i] or in_kf[i]:
+            continue
+        xc3 = np.zeros(3, np.float32)
+        for r in range(3):
+            t = f32(Rm[r, 0] * X[0]); t = f32(t + f32(Rm[r, 1] * X[1])); t = f32(t + f32(Rm[r, 2] * X[2]))
+            xc3[r] = f32(float(t) + float(tv[r]))
+        if xc3[2] < 0:
+            continue
+        invz = f32(f32(1) / xc3[2])
+        x_ = f32(xc3[0] * invz); y_ = f32(xc3[1] * invz)
+        u_ = f32(f32(fx * x_) + cx); v_ = f32(f32(fy * y_) + cy)
+        if not (u_ >= 0 and u_ < W and v_ >= 0 and v_ < H):
+            continue
+        po = (X - Ow).astype(np.float32)
+        d3 = f32(np.sqrt(sum(float(p) * float(p) for p in po)))
+        if d3 < min_dist[i] or d3 > max_dist[i]:
+            continue
+        if sum(float(a) * float(b) for a, b in zip(po, normal[i])) < 0.5 * float(d3):
+            continue
+        ratio = f32(d3 / min_dist[i])
+        lv = min(int(np.searchsorted(sf, ratio, side='left')), len(sf) - 1)
+        q['u'].append(u_); q['v'].append(v_); q['r'].append(f32(f32(th) * sf[lv])); q['lo'].append(lv - 1); q['hi'].append(lv); q['who'].append(i)
+    return dict(Rm=Rm, tv=tv, Ow=Ow, intr=[fx, fy, cx, cy], is_null=is_null, bad=bad, in_kf=in_kf, pos=pos, normal=normal,
+                min_dist=min_dist, max_dist=max_dist, pdesc=pdesc, q=q)
+
+
+@needs_mref
+@pytest.mark.parametrize('th', [2.5, 4.0])
+def test_fuse_equals_reference(oracle, synth, th):
+    """M8: ORBmatcher::Fuse(KeyFrame*, vector<MapPoint*>&, th) (src/ORBmatcher.cc:1016-1134) — frustum / distance / viewing-angle
+    gates, level prediction, KeyFrame::GetFeaturesInArea window, levels [l-1, l], best-only at TH_LOW WITHOUT claims (the
+    oracle's / kernel's mode 4), then the host-side Replace / AddObservation bookkeeping in map-point order."""
+    W, H = 752, 480
+    kps, desc = frame_for_matching(oracle, synth)
+    n = len(kps); sf = scale_factors()
+    S = fuse_scene(oracle, kps, desc, W, H, sf, th); q = S['q']; who = np.array(q['who'])
+    inv_w = np.float32(64.0) / np.float32(W); inv_h = np.float32(48.0) / np.float32(H)
+    start, items = oracle.grid_build(kps['x'], kps['y'], 0.0, 0.0, float(inv_w), float(inv_h))
+    on, om, _ = oracle.search_window(4, 50, np.float32(0.6), q['u'], q['v'], q['r'], q['lo'], q['hi'], S['pdesc'][who], kps['x'], kps['y'],
+                                     kps['octave'].astype(np.int32), desc, start, items, 0.0, 0.0, float(inv_w), float(inv_h))
+    kf_has = (np.arange(n) % 3 != 0); kf_bad = (np.arange(n) % 16 == 5)
+    slot = [(-1 if not kf_has[k] else k) for k in range(n)]          # k = the keyframe's own map point, -2-j = map point j added by Fuse
+    slot_bad = [bool(kf_bad[k]) for k in range(n)]
+    e_action = np.zeros(len(S['is_null']), np.int32); e_target = np.full(len(S['is_null']), -1, np.int32)
+    fused = 0
+    for qi, k in enumerate(om):
+        if k < 0:
+            continue
+        i = who[qi]
+        fused += 1
+        if slot[k] != -1:
+            if not slot_bad[k]:
+                e_action[i] = 1; e_target[i] = slot[k]
+        else:
+            e_action[i] = 2; e_target[i] = k
+            slot[k] = -2 - i; slot_bad[k] = False
+    rn, action, target = R.fuse(kps['x'], kps['y'], kps['octave'], desc, [0, W, 0, H], sf, S['Rm'], S['tv'], S['Ow'], S['intr'], kf_has, kf_bad,
+                                S['is_null'], S['bad'], S['in_kf'], S['pos'], S['normal'], S['min_dist'], S['max_dist'], S['pdesc'], th)
+    assert rn == fused == on and rn > 300
+    assert (e_action == 1).sum() > 50 and (e_action == 2).sum() > 50 and (e_target < -1).sum() > 0     # every branch exercised
+    assert np.array_equal(action, e_action) and np.array_equal(target, e_target)
