@@ -11,12 +11,13 @@ so = sys.argv[4] if len(sys.argv) > 4 else os.path.join(os.path.dirname(os.path.
 out = subprocess.run(['ncu', '-i', rep, '--page', 'source', '--csv', '--kernel-name', 'regex:' + kern],
                      capture_output=True, text=True).stdout
 rows = list(csv.reader(io.StringIO(out)))
-hdr = None; data = []
+hdr = None; data = []; nth = int(os.environ.get('NTH', '0')); seen = -1     # NTH = which matching launch (default: the first)
 for r in rows:
     if r and r[0] == 'Address' and 'Source' in r:
-        if hdr is not None:
-            break                      # first matching launch only
-        hdr = r; continue
+        seen += 1
+        if seen > nth:
+            break
+        hdr = r; data = []; continue
     if hdr and len(r) == len(hdr):
         data.append(r)
 iS = hdr.index('Source'); iI = hdr.index('Instructions Executed'); iT = hdr.index('Thread Instructions Executed'); iN = hdr.index('# Samples')

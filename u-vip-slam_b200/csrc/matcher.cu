@@ -18,16 +18,23 @@ void set_last_error(const char* fmt, ...) {
 }
 
 // =====================================================================================================
-// K9: tiled Hamming top-2.  One thread per query (descriptor in 8 registers); train rows stream through
-// shared memory in 8 KB stages filled by the TMA engine (cp.async.bulk + mbarrier), every lane reads the
-// same train row (LDS.128 broadcast), so per descriptor pair the SM executes 8 LOP3 + 8 POPC + 4 IADD3/LEA
-// + 3 VIMNMX.  POPC issues at 16 lanes/clk/SM -> 2 pairs/clk/SM is the roofline.
+// K9: tiled Hamming top-2.  One thread per query; train rows stream through shared memory in 8 KB stages filled by
+// the TMA engine (cp.async.bulk + mbarrier); every lane reads the same train row (LDS.128 broadcast).
+//
+// Per descriptor pair the naive count is 8 XOR + 8 POPC.  POPC issues at 16 lanes/clk/SM, LOP3 on the ALU pipe at 64.
+// A carry-save (Harley-Seal) reduction of the 8 XOR words x_i = a_i ^ b_i trades POPCs for LOP3s:
+//      (s1, c1) = CSA(x0, x1, x2)   (s2, c2) = CSA(x3, x4, x5)   (s3, c3) = CSA(s1, s2, x6)   (ts, tc) = CSA(c1, c2, c3)
+//      distance = popc(s3) + popc(x7) + 2 popc(ts) + 4 popc(tc)                                        -> 4 POPC
+// The SUM outputs of a CSA are linear in the inputs: s1 = (a0^a1^a2) ^ (b0^b1^b2), and the CARRY of a CSA is a function of
+// two inputs and the sum (the third input is their XOR with the sum).  So with the query-side XORs kept in registers and
+// the train-side XORs B012 = b0^b1^b2, B345, B06 = b0^..^b6 stored WITH THE ROW, the words x2, x5, x6 are never formed:
+//      x0, x1, s1 = A012^B012, c1 = f(x0, x1, s1),  x3, x4, s2, c2,  s3 = A06^B06, c3 = f(s1, s2, s3),  x7,  ts, tc
+// = 13 LOP3 + 4 POPC per pair (was 8 + 14 LOP3), which makes the kernel POPC-bound at 4 POPC per pair instead of ALU-bound.
+// Each stage is rewritten in place after it lands: row = {b0, b1, b3, b4 | b7, B012, B345, B06} (one thread per row,
+// b2, b5, b6 are not needed any more), so the inner loop still reads two LDS.128 per pair.
 // Running top-2 is kept as packed 32-bit keys (dist << 16 | row-in-supertile): unique keys give the
 // (distance, index) order, i.e. the reference's strict '<' scan where the first candidate wins ties.
 // =====================================================================================================
-#ifndef UVIP_KNN_CSA
-#define UVIP_KNN_CSA 1
-#endif
 constexpr int KNN_THREADS = 128;
 constexpr int KNN_TILE = 256;                      // train rows per stage
 constexpr int KNN_STAGE_BYTES = KNN_TILE * 32;
@@ -38,24 +45,31 @@ __device__ __forceinline__ void top2_push(int d, int gi, int& d1, int& i1, int& 
     else if (d < d2) { d2 = d; i2 = gi; }
 }
 
-__device__ __forceinline__ int hamming8(uint32_t a0, uint32_t a1, uint32_t a2, uint32_t a3, uint32_t a4, uint32_t a5, uint32_t a6, uint32_t a7,
-                                        const uint4 u, const uint4 v)
+// carry of CSA(x, y, z) given x, y and the sum s = x^y^z: one LOP3
+__device__ __forceinline__ unsigned csa_carry(unsigned x, unsigned y, unsigned s) { const unsigned xy = x ^ y; return (x & y) | (xy & (xy ^ s)); }
+
+struct KnnQuery { unsigned a0, a1, a3, a4, a7, A012, A345, A06; };
+
+// u = {b0, b1, b3, b4}, v = {b7, B012, B345, B06} (the in-place rewritten train row)
+__device__ __forceinline__ unsigned hamming8(const KnnQuery& q, const uint4 u, const uint4 v)
 {
-#if UVIP_KNN_CSA
-    // Harley-Seal carry-save reduction: 8 XOR words -> ones/twos/fours/eights bit planes, 4 POPC instead of 8
-    const unsigned x0 = a0 ^ u.x, x1 = a1 ^ u.y, x2 = a2 ^ u.z, x3 = a3 ^ u.w, x4 = a4 ^ v.x, x5 = a5 ^ v.y, x6 = a6 ^ v.z, x7 = a7 ^ v.w;
-    const unsigned s1 = x0 ^ x1 ^ x2, c1 = (x0 & x1) | ((x0 ^ x1) & x2);
-    const unsigned s2 = x3 ^ x4 ^ x5, c2 = (x3 & x4) | ((x3 ^ x4) & x5);
-    const unsigned s3 = s1 ^ s2 ^ x6, c3 = (s1 & s2) | ((s1 ^ s2) & x6);
-    const unsigned ones = s3 ^ x7, c4 = s3 & x7;
+    const unsigned x0 = q.a0 ^ u.x, x1 = q.a1 ^ u.y, s1 = q.A012 ^ v.y, c1 = csa_carry(x0, x1, s1);
+    const unsigned x3 = q.a3 ^ u.z, x4 = q.a4 ^ u.w, s2 = q.A345 ^ v.z, c2 = csa_carry(x3, x4, s2);
+    const unsigned s3 = q.A06 ^ v.w, c3 = csa_carry(s1, s2, s3);
+    const unsigned x7 = q.a7 ^ v.x;
     const unsigned ts = c1 ^ c2 ^ c3, tc = (c1 & c2) | ((c1 ^ c2) & c3);
-    const unsigned twos = ts ^ c4, f2 = ts & c4;
-    const unsigned fours = tc ^ f2, eights = tc & f2;
-    return __popc(ones) + 2 * __popc(twos) + 4 * __popc(fours) + 8 * __popc(eights);
-#else
-    return (__popc(a0 ^ u.x) + __popc(a1 ^ u.y) + __popc(a2 ^ u.z)) + (__popc(a3 ^ u.w) + __popc(a4 ^ v.x) + __popc(a5 ^ v.y)) +
-           (__popc(a6 ^ v.z) + __popc(a7 ^ v.w));
-#endif
+    return (unsigned)__popc(s3) + (unsigned)__popc(x7) + 2u * (unsigned)__popc(ts) + 4u * (unsigned)__popc(tc);
+}
+
+// rewrite the rows [first, first + count) of a landed stage in place (see above); one thread per row
+__device__ __forceinline__ void knn_prepare_rows(uint4* T, int rows, int tid)
+{
+    for (int r = tid; r < rows; r += KNN_THREADS) {
+        const uint4 u = T[2 * r], v = T[2 * r + 1];
+        const unsigned B012 = u.x ^ u.y ^ u.z, B345 = u.w ^ v.x ^ v.y;
+        T[2 * r] = make_uint4(u.x, u.y, u.w, v.x);
+        T[2 * r + 1] = make_uint4(v.w, B012, B345, B012 ^ B345 ^ v.z);
+    }
 }
 
 __global__ void __launch_bounds__(KNN_THREADS)
@@ -82,11 +96,12 @@ k_knn2(const uint8_t* __restrict__ q_base, const int32_t* __restrict__ d_nq, siz
     const int qi = blockIdx.x * blockDim.x + tid;
     const bool live = qi < nq;
 
-    uint32_t a0 = 0, a1 = 0, a2 = 0, a3 = 0, a4 = 0, a5 = 0, a6 = 0, a7 = 0;
+    KnnQuery Q = {0, 0, 0, 0, 0, 0, 0, 0};
     if (live) {
         const uint4* qp = reinterpret_cast<const uint4*>(q + (size_t)qi * 32);
-        uint4 u = __ldg(qp), v = __ldg(qp + 1);
-        a0 = u.x; a1 = u.y; a2 = u.z; a3 = u.w; a4 = v.x; a5 = v.y; a6 = v.z; a7 = v.w;
+        const uint4 u = __ldg(qp), v = __ldg(qp + 1);
+        Q.a0 = u.x; Q.a1 = u.y; Q.a3 = u.w; Q.a4 = v.x; Q.a7 = v.w;
+        Q.A012 = u.x ^ u.y ^ u.z; Q.A345 = u.w ^ v.x ^ v.y; Q.A06 = Q.A012 ^ Q.A345 ^ v.z;
     }
 
     const int ntiles = (nt + KNN_TILE - 1) / KNN_TILE;
@@ -107,9 +122,13 @@ k_knn2(const uint8_t* __restrict__ q_base, const int32_t* __restrict__ d_nq, siz
     int g1d = 257, g2d = 257, g1i = -1, g2i = -1;
     uint32_t b1 = 0xFFFFFFFFu, b2 = 0xFFFFFFFFu;
 
+    if (ntiles > 0) {                                              // stage 0: wait, rewrite in place, publish
+        mbar_wait(&s_bar[0], 0);
+        knn_prepare_rows(reinterpret_cast<uint4*>(s_tile[0]), min(KNN_TILE, nt), tid);
+        __syncthreads();
+    }
     for (int i = 0; i < ntiles; i++) {
         const int s = i & 1;
-        mbar_wait(&s_bar[s], (i >> 1) & 1);
         const int rows = min(KNN_TILE, nt - i * KNN_TILE);
         const uint4* T = reinterpret_cast<const uint4*>(s_tile[s]);
         uint32_t key = (uint32_t)((i & (KNN_SUPER - 1)) * KNN_TILE);
@@ -119,7 +138,7 @@ k_knn2(const uint8_t* __restrict__ q_base, const int32_t* __restrict__ d_nq, siz
         for (; j + 4 <= rows; j += 4) {
             uint32_t k4[4];
 #pragma unroll
-            for (int r = 0; r < 4; r++) k4[r] = ((uint32_t)hamming8(a0, a1, a2, a3, a4, a5, a6, a7, T[2 * (j + r)], T[2 * (j + r) + 1]) << 16) + key + (uint32_t)(j + r);
+            for (int r = 0; r < 4; r++) k4[r] = (hamming8(Q, T[2 * (j + r)], T[2 * (j + r) + 1]) << 16) + key + (uint32_t)(j + r);
             const uint32_t mn = min(__vimin3_u32(k4[0], k4[1], k4[2]), k4[3]);
             if (mn < b2) {
 #pragma unroll
@@ -127,14 +146,19 @@ k_knn2(const uint8_t* __restrict__ q_base, const int32_t* __restrict__ d_nq, siz
             }
         }
         for (; j < rows; j++) {
-            const uint32_t k = ((uint32_t)hamming8(a0, a1, a2, a3, a4, a5, a6, a7, T[2 * j], T[2 * j + 1]) << 16) + key + (uint32_t)j;
+            const uint32_t k = (hamming8(Q, T[2 * j], T[2 * j + 1]) << 16) + key + (uint32_t)j;
             const uint32_t lo = min(b1, k), hi = max(b1, k);
             b2 = min(b2, hi);
             b1 = lo;
         }
-        __syncthreads();                                           // stage s fully consumed
+        if (i + 1 < ntiles) {                                      // the next stage landed long ago: rewrite it while this one drains
+            mbar_wait(&s_bar[s ^ 1], ((i + 1) >> 1) & 1);
+            knn_prepare_rows(reinterpret_cast<uint4*>(s_tile[s ^ 1]), min(KNN_TILE, nt - (i + 1) * KNN_TILE), tid);
+        }
+        __syncthreads();                                           // stage s fully consumed, stage s^1 rewritten
         if (tid == 0 && i + 2 < ntiles) {
             const int r2 = min(KNN_TILE, nt - (i + 2) * KNN_TILE);
+            fence_proxy_async_smem();                              // the stage was rewritten through the generic proxy
             mbar_arrive_expect_tx(&s_bar[s], r2 * 32);
             bulk_g2s(s_tile[s], t + (size_t)(i + 2) * KNN_STAGE_BYTES, r2 * 32, &s_bar[s]);
         }
