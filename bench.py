@@ -37,8 +37,8 @@ def parse():
     ap.add_argument('--ref-frames', type=int, default=0, help='frames per step of the reference arm (0 = 4 x cores)')
     ap.add_argument('--e2e-chunk', type=int, default=0, help='frames per pipeline chunk of the host-buffer entry point (0 = batch/2)')
     ap.add_argument('--no-extras', action='store_true', help='skip the Hamming-only and cpu_baseline legs')
-    ap.add_argument('--workload', default='frames', choices=['frames', 'knn', 'next'],
-                    help="'frames' = the headline metric; 'knn' = BASELINE config 4: database-sharded brute-force kNN2 with NCCL top-2 merge")
+    ap.add_argument('--workload', default='frames', choices=['frames', 'knn', 'search', 'next'],
+                    help="'frames' = the headline metric; 'knn' = BASELINE config 4: database-sharded brute-force kNN2 with NCCL top-2 merge; 'search' = BASELINE config 3: batched grid-windowed SearchByProjection")
     ap.add_argument('--shape', default='euroc', choices=['euroc', 'aqualoc', 'hd'],
                     help='frame shape of --workload frames: euroc 752x480/1000 kp (the metric, config 1 shape), aqualoc 640x512/1500 kp (config 2), '
                          'hd 1280x1024/2000 kp (config 5)')
@@ -513,6 +513,140 @@ def run_knn(args):
     return 0
 
 
+def run_search(args):
+    """BASELINE config 3 as a throughput workload: SearchByProjection-style grid-windowed matching, 10 000 projected map points
+    against a 2000-keypoint frame (radius search on the 64 x 48 frame grid, top-2 + ratio, claims), `--batch` frames per step in
+    one launch pair (grid build + search), frames sharded over the GPUs with no collective.  value = map points per second."""
+    import ctypes as C
+    import numpy as np
+    import torch
+    import __graft_entry__ as ge
+    pkg = ge.load_package()
+    rank = int(os.environ.get('RANK', '0')); world = int(os.environ.get('WORLD_SIZE', '1')); local = int(os.environ.get('LOCAL_RANK', '0'))
+    torch.cuda.set_device(local)
+    dev = torch.device('cuda', local)
+    dist = None
+    if world > 1:
+        import torch.distributed as dist
+        dist.init_process_group('nccl', device_id=dev)
+    Wf, Hf, NQ, NK = 752, 480, 10000, 2000
+    F, K, Wm = args.batch, args.steps, max(args.warmup, 3)
+    ndistinct = min(F, 16)
+    cases = [pkg.synth.projection_case(seed_f=3 + 10 * i + 1000 * rank, seed_p=4 + 10 * i + 1000 * rank) for i in range(ndistinct)]
+    m = pkg.ORBmatcher(0.8, True, device=local)
+    sf = pkg.ORBextractor(1000, 1.2, 8, 1, 20, device=local, max_width=Wf, max_height=Hf).tables()[0]
+    rad = [m.projection_radius(c['view_cos'], c['level'], sf, 1.0) for c in cases]
+    pick = [i % ndistinct for i in range(F)]
+    stack = lambda fn, dt: torch.from_numpy(np.ascontiguousarray(np.stack([fn(i) for i in pick]), dt)).to(dev)
+    t = dict(u=stack(lambda i: cases[i]['u'], np.float32), v=stack(lambda i: cases[i]['v'], np.float32), r=stack(lambda i: rad[i], np.float32),
+             lo=stack(lambda i: cases[i]['level'] - 1, np.int32), hi=stack(lambda i: cases[i]['level'], np.int32),
+             qd=stack(lambda i: cases[i]['qdesc'], np.uint8), x=stack(lambda i: cases[i]['kx'], np.float32),
+             y=stack(lambda i: cases[i]['ky'], np.float32), o=stack(lambda i: cases[i]['octave'], np.int32),
+             kd=stack(lambda i: cases[i]['kdesc'], np.uint8),
+             nq=torch.full((F,), NQ, dtype=torch.int32, device=dev), nk=torch.full((F,), NK, dtype=torch.int32, device=dev),
+             taken=torch.full((F, NK), -1, dtype=torch.int32, device=dev), match=torch.zeros((F, NQ), dtype=torch.int32, device=dev),
+             counts=torch.zeros((F, 2), dtype=torch.int32, device=dev))
+    P = lambda k: t[k].data_ptr()
+    stream = torch.cuda.Stream(dev); torch.cuda.set_stream(stream)
+
+    def step():
+        t['taken'].fill_(-1)                                 # every step starts from a frame without map points
+        m.search_window_batch_device(0, 100, (0, Wf, 0, Hf), F, (P('u'), P('v'), P('r'), P('lo'), P('hi'), P('qd')), P('nq'), NQ,
+                                     (P('x'), P('y'), P('o'), P('kd')), P('nk'), NK, P('taken'), P('match'), P('counts'), stream.cuda_stream)
+    for _ in range(Wm):
+        step()
+    torch.cuda.synchronize(dev)
+    if world > 1:
+        dist.barrier()
+    launches0 = m.launch_count()
+    clocks = ClockSampler(local); clocks.start()
+    e0 = torch.cuda.Event(enable_timing=True); e1 = torch.cuda.Event(enable_timing=True)
+    e0.record(stream)
+    for _ in range(K):
+        step()
+    e1.record(stream)
+    torch.cuda.synchronize(dev)
+    if world > 1:
+        dist.barrier()
+    ms = e0.elapsed_time(e1)
+    clk = clocks.stop()
+    launches = m.launch_count() - launches0 + K              # + the fill kernel of every step
+    if world > 1:
+        tt = torch.tensor([ms], dtype=torch.float64, device=dev); dist.all_reduce(tt, op=dist.ReduceOp.MAX); ms = float(tt.item())
+    mps = float(world) * F * NQ * K / (ms * 1e-3)
+    counts = t['counts'].cpu().numpy()
+    # ---- end to end: the single-frame host-buffer call (uvip_grid_build + uvip_search_window, H2D + D2H inside), one frame after another
+    c0 = cases[0]
+    te = time.perf_counter(); ne = 0
+    while ne < 20 or time.perf_counter() - te < 0.5:
+        c = cases[ne % ndistinct]
+        grid = m.grid_build(c['kx'], c['ky'], c['bounds'])
+        n1, match1, taken1 = m.search_window(0, 100, c['u'], c['v'], rad[ne % ndistinct], c['level'] - 1, c['level'], c['qdesc'], c['kx'], c['ky'],
+                                             c['octave'], c['kdesc'], grid)
+        ne += 1
+    e2e_s = time.perf_counter() - te
+    if world > 1:
+        tt = torch.tensor([e2e_s / ne], dtype=torch.float64, device=dev); dist.all_reduce(tt, op=dist.ReduceOp.MAX); e2e_s = float(tt.item()) * ne
+    line = None
+    if rank == 0:
+        from oracle import oracle as O
+        # candidate pairs per frame (one 8-popc distance each) from the oracle's GetFeaturesInArea on the distinct frames
+        inv_w = np.float32(64.0) / np.float32(Wf); inv_h = np.float32(48.0) / np.float32(Hf)
+        c = cases[0]
+        start, items = O.grid_build(c['kx'], c['ky'], 0.0, 0.0, float(inv_w), float(inv_h))
+        ncand = sum(len(O.features_in_area(c['kx'], c['ky'], c['octave'], start, items, 0.0, 0.0, float(inv_w), float(inv_h), float(c['u'][q]),
+                                           float(c['v'][q]), float(rad[0][q]), int(c['level'][q]) - 1, int(c['level'][q]))) for q in range(NQ))
+        on, om, otk = O.search_window(0, 100, 0.8, c['u'], c['v'], rad[0], c['level'] - 1, c['level'], c['qdesc'], c['kx'], c['ky'], c['octave'],
+                                      c['kdesc'], start, items, 0.0, 0.0, float(inv_w), float(inv_h))
+        ok = bool(np.array_equal(t['match'][0].cpu().numpy(), om) and counts[0, 0] == on and n1 >= 0)
+        # algorithmic bytes (SURVEY 8d): per query 32 + 16 read, 16 written; per frame 2000 x 44 B + grid CSR
+        bytes_frame = NQ * (32 + 16 + 16) + NK * 44 + (64 * 48 + 1) * 4 + NK * 4
+        peak, peak_kind = hbm_peak()
+        achieved = bytes_frame * F * K / (ms * 1e-3) / 1e9
+        popc = C.c_double(); pkg.capi.check(pkg.capi.lib().uvip_popc_peak(local, 4096, C.byref(popc)))
+        line = {'metric': 'SearchByProjection map points/s (BASELINE config 3: 10k projected map points vs 2000-kp frame)', 'value': mps,
+                'unit': 'map points/s', 'n_gpus': world, 'steps': K, 'warmup': Wm, 'ms_per_step': ms / K, 'higher_is_better': True, 'scaling': 'weak',
+                'vs_baseline': None, 'dtype': 'f32 geometry + u32 popc', 'data': 'synthetic',
+                'config': {'workload': 'BASELINE config 3: grid-windowed SearchByProjection, 10000 map points x 2000 keypoints per frame, th=1, ratio 0.8',
+                           'frames_per_step_per_gpu': F, 'distinct_frames': ndistinct, 'l2': 'the batch (%.0f MB) exceeds nothing: this stage is latency-bound, '
+                           'not bandwidth-bound; inputs stay L2-resident by design' % (F * (NQ * 56 + NK * 48) / 1e6)},
+                'clocks': clk, 'gpu_launches': int(launches),
+                'e2e': {'value': world * NQ * ne / e2e_s, 'unit': 'map points/s', 'h2d_bytes_per_step': NQ * 52 + NK * 48 + (64 * 48 + 1) * 4 + NK * 8,
+                        'd2h_bytes_per_step': NQ * 4 + NK * 4 + (64 * 48 + 1) * 4 + NK * 4 + 8, 'what': 'single-frame host-buffer calls uvip_grid_build + '
+                        'uvip_search_window, one frame after another (the shape of the reference call)', 'frames': ne, 'ms_per_frame': 1e3 * e2e_s / ne},
+                'roofline': {'bound': 'hbm', 'achieved': achieved, 'peak': peak, 'unit': 'GB/s', 'frac': achieved / peak, 'traffic': None,
+                             'peak_source': peak_kind, 'algorithmic_bytes_per_launch': bytes_frame * F,
+                             'candidate_pairs_per_s': float(world) * ncand * F * K / (ms * 1e-3), 'candidate_pairs_per_frame': ncand,
+                             'popc_frac_8_per_pair': float(ncand) * F * K / (ms * 1e-3) * 8 / popc.value,
+                             'claim_rounds_per_frame': float(counts[:, 1].mean()), 'note': 'latency-bound gather: one CTA per frame, queries re-run until '
+                             'the claim table is a fixed point'},
+                'matches_oracle_frame0': ok}
+        # cpu_baseline: the reference's own compiled ORBmatcher::SearchByProjection (oracle/_ref), single thread as the reference runs it
+        from oracle import reference as R
+        if R.matcher_available():
+            sfl = [float(x) for x in sf]
+            tot = 0.0; nfr = 0
+            while tot < 1.0 or nfr < 8:
+                c = cases[nfr % ndistinct]
+                R.search_by_projection_mps(c['kx'], c['ky'], c['octave'], c['kdesc'], [0, Wf, 0, Hf], sfl, c['u'], c['v'], c['level'], c['view_cos'],
+                                           c['qdesc'], 1.0, 0.8)
+                tot += R.last_call_seconds(); nfr += 1
+            line['cpu_baseline'] = {'value': NQ * nfr / tot, 'unit': 'map points/s', 'cores': 1, 'kind': 'reference',
+                                    'sample': "%d frames through the reference's own compiled ORBmatcher::SearchByProjection (oracle/_ref, scene "
+                                              'construction excluded); the reference runs this on one Tracking thread' % nfr}
+        else:
+            tc = time.perf_counter(); nfr = 0
+            while time.perf_counter() - tc < 1.0:
+                O.search_window(0, 100, 0.8, c['u'], c['v'], rad[0], c['level'] - 1, c['level'], c['qdesc'], c['kx'], c['ky'], c['octave'], c['kdesc'],
+                                start, items, 0.0, 0.0, float(inv_w), float(inv_h)); nfr += 1
+            line['cpu_baseline'] = {'value': NQ * nfr / (time.perf_counter() - tc), 'unit': 'map points/s', 'cores': 1, 'kind': 'port',
+                                    'sample': '%d frames through the C oracle' % nfr}
+        print(json.dumps(line), flush=True)
+    if world > 1:
+        dist.destroy_process_group()
+    return 0
+
+
 def run_next(args):
     """the SURVEY 8f rows built so far (CLAHE, DBoW2 descent, KLT), each timed next to its oracle on the host cores"""
     import ctypes as C
@@ -601,4 +735,4 @@ if __name__ == '__main__':
     assert a.shape != 'euroc' or B_FRAME_BYTES == 1177367
     if a.impl == 'reference':
         sys.exit(run_reference(a))
-    sys.exit(run_knn(a) if a.workload == 'knn' else run_next(a) if a.workload == 'next' else run_ours(a))
+    sys.exit(run_knn(a) if a.workload == 'knn' else run_next(a) if a.workload == 'next' else run_search(a) if a.workload == 'search' else run_ours(a))

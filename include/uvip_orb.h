@@ -204,6 +204,17 @@ int   uvip_search_window(uvip_matcher* m, const uvip_search_params* sp,
                          const float* kx, const float* ky, const int32_t* octave, const uint8_t* kdesc, int nk,
                          const int32_t* cell_start, const int32_t* cell_items,
                          int32_t* taken, int32_t* match, int* nmatches);
+/* The same search for a batch of device-resident frames (BASELINE config 3 as a throughput workload; frames shard with no
+ * exchange because claims never cross frames).  Frame f owns queries [f*q_stride, f*q_stride + d_nq[f]) and keypoints
+ * [f*k_stride, f*k_stride + d_nk[f]) of every array; the frame grids (src/FrameKTL.cc:250-264) are built on the device by the
+ * same call.  d_taken (nframes x k_stride) in/out and d_match (nframes x q_stride) as above; d_counts[2f] = matches of
+ * frame f, d_counts[2f+1] = claim rounds it took.  Asynchronous on `stream` (NULL = the handle's stream). */
+int   uvip_search_window_batch_device(uvip_matcher* m, const uvip_search_params* sp, int nframes,
+                                      const float* d_qu, const float* d_qv, const float* d_qr, const int32_t* d_qmin_level,
+                                      const int32_t* d_qmax_level, const uint8_t* d_qdesc, const int32_t* d_nq, int q_stride,
+                                      const float* d_kx, const float* d_ky, const int32_t* d_octave, const uint8_t* d_kdesc,
+                                      const int32_t* d_nk, int k_stride,
+                                      int32_t* d_taken, int32_t* d_match, int32_t* d_counts, void* stream);
 /* Node-restricted search with claims over explicit candidate lists (CSR: cand_start[nq+1], cand_idx[]): the inner
  * loops of SearchByBoW(KeyFrame*, FrameKTL&, ...) (src/ORBmatcher.cc:186-245; mode 2: best <= th and
  * (float)best < ratio*(float)best2) and SearchByBoW(KeyFrame*, KeyFrame*, ...) (:751-811; mode 3: best < th, same

@@ -5,6 +5,7 @@
 // matcher restatement (and through it the CUDA kernels and the C++ shim) against the reference's compiled code.
 #include <stdint.h>
 #include <string.h>
+#include <time.h>
 #include <memory>
 #include <set>
 #include <vector>
@@ -13,6 +14,14 @@
 using namespace USLAM;
 
 namespace {
+
+// wall time of the last reference member call alone (scene construction excluded), for the CPU-baseline legs of bench.py
+thread_local double g_call_seconds = 0.0;
+struct CallTimer {
+    timespec t0;
+    CallTimer() { clock_gettime(CLOCK_MONOTONIC, &t0); }
+    ~CallTimer() { timespec t1; clock_gettime(CLOCK_MONOTONIC, &t1); g_call_seconds = (double)(t1.tv_sec - t0.tv_sec) + 1e-9 * (double)(t1.tv_nsec - t0.tv_nsec); }
+};
 
 cv::Mat desc_mat(const uint8_t* d, int n) { cv::Mat m(n > 0 ? n : 1, 32, CV_8UC1); if (n > 0) memcpy(m.data, d, (size_t)n * 32); return m; }
 cv::Mat vec3(const float* p) { cv::Mat m(3, 1, CV_32F); for (int i = 0; i < 3; i++) m.at<float>(i) = p[i]; return m; }
@@ -54,6 +63,8 @@ struct FrameScene {
 
 extern "C" {
 
+double refm_last_call_seconds(void) { return g_call_seconds; }
+
 // ORBmatcher::DescriptorDistance (src/ORBmatcher.cc:1794-1810)
 int refm_descriptor_distance(const uint8_t* a, const uint8_t* b)
 {
@@ -82,7 +93,8 @@ int refm_search_by_projection_mps(int nk, const float* kx, const float* ky, cons
         vp[i] = &m;
     }
     ORBmatcher matcher(nnratio, true);
-    const int n = matcher.SearchByProjection(S.F, vp, th);
+    int n;
+    { CallTimer timer; n = matcher.SearchByProjection(S.F, vp, th); }
     for (int k = 0; k < nk; k++) {
         MapPoint* p = S.F.mvpMapPoints[k];
         owner[k] = !p ? -1 : (p >= &mps[0] && p < &mps[0] + nq ? (int32_t)(p - &mps[0]) : -2);

@@ -122,7 +122,13 @@ def mlib():
         if not os.path.exists(MATCHER_SO):
             raise RuntimeError('oracle/_ref/libref_orbmatcher.so is not built and /root/reference is absent')
         _MLIB = C.CDLL(MATCHER_SO)
+        _MLIB.refm_last_call_seconds.restype = C.c_double
     return _MLIB
+
+
+def last_call_seconds():
+    """wall time of the reference member function inside the last matcher entry point (scene construction excluded)"""
+    return float(mlib().refm_last_call_seconds())
 
 
 def _f32(a):

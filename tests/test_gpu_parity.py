@@ -446,3 +446,44 @@ def test_distinctive_descriptors_batch(gpu, oracle, synth):
     d2 = desc.copy(); d2[sl] = desc[sl][perm]
     bi2, bm2 = m.distinctive_descriptors(d2, start)
     assert bm2[p] == bm[p] and np.array_equal(np.delete(bm2, p), np.delete(bm, p))
+
+
+def test_search_by_projection_batch_device(gpu, oracle, synth):
+    """config 3 as a batch: several frames (ragged sizes) searched by one launch, each identical to the sequential oracle."""
+    import torch
+    dev = torch.device('cuda', 0)
+    W, H = 752, 480
+    cases = [synth.projection_case(seed_f=3 + 10 * i, seed_p=4 + 10 * i, nk=2000 - 150 * i, nq=10000 - 900 * i) for i in range(5)]
+    m = gpu.ORBmatcher(0.8, True)
+    sf = gpu.ORBextractor(1000, 1.2, 8, 1, 20, max_width=W, max_height=H).tables()[0]
+    QS, KS, F = 10000, 2000, len(cases)
+    qf = {k: np.zeros((F, QS), np.float32) for k in ('u', 'v', 'r')}; qi = {k: np.zeros((F, QS), np.int32) for k in ('lo', 'hi')}
+    qd = np.zeros((F, QS, 32), np.uint8)
+    kf = {k: np.zeros((F, KS), np.float32) for k in ('x', 'y')}; ko = np.zeros((F, KS), np.int32); kd = np.zeros((F, KS, 32), np.uint8)
+    nq = np.zeros(F, np.int32); nk = np.zeros(F, np.int32)
+    taken = np.full((F, KS), -1, np.int32)
+    for f, c in enumerate(cases):
+        a, b = len(c['u']), len(c['kx'])
+        nq[f], nk[f] = a, b
+        qf['u'][f, :a] = c['u']; qf['v'][f, :a] = c['v']; qf['r'][f, :a] = m.projection_radius(c['view_cos'], c['level'], sf, 1.0)
+        qi['lo'][f, :a] = c['level'] - 1; qi['hi'][f, :a] = c['level']; qd[f, :a] = c['qdesc']
+        kf['x'][f, :b] = c['kx']; kf['y'][f, :b] = c['ky']; ko[f, :b] = c['octave']; kd[f, :b] = c['kdesc']
+        taken[f, :b:9] = -2
+    T = lambda a: torch.from_numpy(a).to(dev)
+    t = dict(u=T(qf['u']), v=T(qf['v']), r=T(qf['r']), lo=T(qi['lo']), hi=T(qi['hi']), qd=T(qd), x=T(kf['x']), y=T(kf['y']), o=T(ko), kd=T(kd),
+             nq=T(nq), nk=T(nk), taken=T(taken), match=torch.full((F, QS), -7, dtype=torch.int32, device=dev),
+             counts=torch.zeros((F, 2), dtype=torch.int32, device=dev))
+    P = lambda k: t[k].data_ptr()
+    m.search_window_batch_device(0, 100, (0, W, 0, H), F, (P('u'), P('v'), P('r'), P('lo'), P('hi'), P('qd')), P('nq'), QS,
+                                 (P('x'), P('y'), P('o'), P('kd')), P('nk'), KS, P('taken'), P('match'), P('counts'))
+    torch.cuda.synchronize()
+    g_match = t['match'].cpu().numpy(); g_taken = t['taken'].cpu().numpy(); g_counts = t['counts'].cpu().numpy()
+    inv_w = np.float32(64.0) / np.float32(W); inv_h = np.float32(48.0) / np.float32(H)
+    for f, c in enumerate(cases):
+        a, b = nq[f], nk[f]
+        start, items = oracle.grid_build(c['kx'], c['ky'], 0.0, 0.0, float(inv_w), float(inv_h))
+        on, om, otk = oracle.search_window(0, 100, 0.8, c['u'], c['v'], qf['r'][f, :a], c['level'] - 1, c['level'], c['qdesc'], c['kx'], c['ky'],
+                                           c['octave'], c['kdesc'], start, items, 0.0, 0.0, float(inv_w), float(inv_h), taken=taken[f, :b])
+        assert g_counts[f, 0] == on and on > 500, f
+        assert np.array_equal(g_match[f, :a], om) and np.array_equal(g_taken[f, :b], otk), f
+        assert (g_match[f, a:] == -7).all()                       # nothing written beyond the frame's own queries

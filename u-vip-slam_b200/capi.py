@@ -89,6 +89,7 @@ def lib():
         L.uvip_ratio_filter.argtypes = [vp, vp, vp, i, C.c_double, vp, C.POINTER(i)]
         L.uvip_rot_hist_filter.argtypes = [vp, vp, i, vp, vp, C.POINTER(i)]
         L.uvip_grid_build.argtypes = [vp, vp, vp, i, C.c_float, C.c_float, C.c_float, C.c_float, i, i, vp, vp]
+        L.uvip_search_window_batch_device.argtypes = [vp, C.POINTER(SearchParams), i] + [vp] * 7 + [i] + [vp] * 5 + [i] + [vp] * 4
         L.uvip_search_window.argtypes = [vp, C.POINTER(SearchParams), vp, vp, vp, vp, vp, vp, i,
                                          vp, vp, vp, vp, i, vp, vp, vp, vp, C.POINTER(i)]
         L.uvip_search_lists.argtypes = [vp, i, i, C.c_float, vp, i, vp, vp, vp, i, vp, vp, C.POINTER(i)]

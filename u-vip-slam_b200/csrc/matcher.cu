@@ -316,10 +316,16 @@ __global__ void k_rot_hist(int32_t* __restrict__ match, int n, const float* __re
 // frame grid: FrameKTL.cc:250-264 + PosInGrid :426-436.  Single CTA; counts/cursors in dynamic smem.
 __global__ void k_grid_build(const float* __restrict__ kx, const float* __restrict__ ky, int n,
                              float min_x, float min_y, float inv_w, float inv_h, int cols, int rows,
-                             int32_t* __restrict__ cell_start, int32_t* __restrict__ cell_items, int32_t* __restrict__ cell_of)
+                             int32_t* __restrict__ cell_start, int32_t* __restrict__ cell_items, int32_t* __restrict__ cell_of,
+                             const int32_t* __restrict__ d_n, int k_stride)
 {
     extern __shared__ int s_cnt[];      // ncell + 1 counts, then ncell cursors
     const int ncell = cols * rows;
+    {   // batched form: blockIdx.x = frame, per-frame arrays k_stride apart, per-frame sizes in d_n
+        const size_t f = blockIdx.x;
+        kx += f * k_stride; ky += f * k_stride; cell_items += f * k_stride; cell_of += f * k_stride; cell_start += f * (ncell + 1);
+        if (d_n) n = d_n[f];
+    }
     int* s_cur = s_cnt + ncell + 1;
     for (int c = threadIdx.x; c <= ncell; c += blockDim.x) s_cnt[c] = 0;
     for (int c = threadIdx.x; c < ncell; c += blockDim.x) s_cur[c] = 0;
@@ -441,9 +447,20 @@ __device__ int search_one_list(const SearchCtx& c, int q, const int* __restrict_
 // is exactly the sequential result ("claims").
 __global__ void __launch_bounds__(1024)
 k_search_window(SearchCtx c, int nq, int nk, int32_t* __restrict__ taken, int32_t* __restrict__ match,
-                int* __restrict__ ownerA, int* __restrict__ ownerB, int* __restrict__ out_counts)
+                int* __restrict__ ownerA, int* __restrict__ ownerB, int* __restrict__ out_counts,
+                const int32_t* __restrict__ d_nq, const int32_t* __restrict__ d_nk, int q_stride, int k_stride)
 {
     __shared__ int s_changed, s_n;
+    {   // batched form (frames shard trivially: claims never cross frames): blockIdx.x = frame
+        const size_t f = blockIdx.x;
+        const size_t qo = f * q_stride, ko = f * k_stride;
+        c.qu += qo; c.qv += qo; c.qr += qo; c.qminL += qo; c.qmaxL += qo; c.qdesc += qo * 32;
+        c.kx += ko; c.ky += ko; c.octave += ko; c.kdesc += ko * 32;
+        c.cell_start += f * (size_t)(c.sp.cols * c.sp.rows + 1); c.cell_items += ko;
+        taken += ko; match += qo; ownerA += ko; ownerB += ko; out_counts += 2 * f;
+        if (d_nq) nq = d_nq[f];
+        if (d_nk) nk = d_nk[f];
+    }
     int* prev = ownerA; int* cur = ownerB;
     const bool claims = c.sp.mode != 4;                    // mode 4 (Fuse): every query is independent, taken[] is not consulted
     for (int i = threadIdx.x; i < nk; i += blockDim.x) prev[i] = (claims && taken[i] != -1) ? -2 : INT_MAX;
@@ -857,7 +874,7 @@ int uvip_grid_build(uvip_matcher* m, const float* kx, const float* ky, int n,
     int32_t* d_items = m->misc4.as<int32_t>();
     int32_t* d_cellof = d_items + nn;
     k_grid_build<<<1, 1024, smem, m->stream>>>(m->misc.as<float>(), m->misc2.as<float>(), n, min_x, min_y, inv_w, inv_h,
-                                                cols, rows, m->misc3.as<int32_t>(), d_items, d_cellof);
+                                                cols, rows, m->misc3.as<int32_t>(), d_items, d_cellof, nullptr, 0);
     m->launches++;
     UVIP_CUDA(cudaGetLastError());
     UVIP_CUDA(cudaMemcpyAsync(cell_start, m->misc3.p, (size_t)(ncell + 1) * 4, cudaMemcpyDeviceToHost, m->stream));
@@ -911,7 +928,7 @@ int uvip_search_window(uvip_matcher* m, const uvip_search_params* sp,
     c.kx = (const float*)(base + o_kx); c.ky = (const float*)(base + o_ky); c.octave = (const int32_t*)(base + o_oct);
     c.kdesc = base + o_kd; c.cell_start = (const int32_t*)(base + o_cs); c.cell_items = (const int32_t*)(base + o_ci);
     k_search_window<<<1, 1024, 0, st>>>(c, nq, nk, (int32_t*)(base + o_taken), (int32_t*)(base + o_match),
-                                         (int*)(base + o_oa), (int*)(base + o_ob), (int*)(base + o_cnt));
+                                         (int*)(base + o_oa), (int*)(base + o_ob), (int*)(base + o_cnt), nullptr, nullptr, 0, 0);
     m->launches++;
     UVIP_CUDA(cudaGetLastError());
     int counts[2] = {0, 0};
@@ -954,7 +971,7 @@ int uvip_search_lists(uvip_matcher* m, int mode, int th_dist, float ratio, const
     c.qdesc = base + o_qd; c.kdesc = base + o_kd;
     c.cand_start = (const int32_t*)(base + o_cs); c.cand_idx = (const int32_t*)(base + o_ci);
     k_search_window<<<1, 1024, 0, st>>>(c, nq, nk, (int32_t*)(base + o_taken), (int32_t*)(base + o_match),
-                                         (int*)(base + o_oa), (int*)(base + o_ob), (int*)(base + o_cnt));
+                                         (int*)(base + o_oa), (int*)(base + o_ob), (int*)(base + o_cnt), nullptr, nullptr, 0, 0);
     m->launches++;
     UVIP_CUDA(cudaGetLastError());
     int counts[2] = {0, 0};
@@ -963,6 +980,49 @@ int uvip_search_lists(uvip_matcher* m, int mode, int th_dist, float ratio, const
     UVIP_CUDA(cudaMemcpyAsync(counts, base + o_cnt, 8, cudaMemcpyDeviceToHost, st));
     UVIP_CUDA(cudaStreamSynchronize(st));
     if (nmatches) *nmatches = counts[0];
+    return UVIP_OK;
+}
+
+// Batched grid-windowed search over device-resident frames (BASELINE config 3 as a throughput workload): frame f owns
+// queries [f*q_stride, f*q_stride + nq[f]) and keypoints [f*k_stride, f*k_stride + nk[f]).  One launch builds all frame
+// grids, one launch runs all searches (one CTA per frame: the claims of a frame are sequentially consistent inside its CTA
+// and never cross frames, so frames shard with no exchange).  Nothing is copied or synchronised here.
+int uvip_search_window_batch_device(uvip_matcher* m, const uvip_search_params* sp, int nframes,
+                                    const float* d_qu, const float* d_qv, const float* d_qr, const int32_t* d_qmin_level,
+                                    const int32_t* d_qmax_level, const uint8_t* d_qdesc, const int32_t* d_nq, int q_stride,
+                                    const float* d_kx, const float* d_ky, const int32_t* d_octave, const uint8_t* d_kdesc,
+                                    const int32_t* d_nk, int k_stride,
+                                    int32_t* d_taken, int32_t* d_match, int32_t* d_counts, void* stream)
+{
+    UVIP_CHECK_ARG(m && sp && nframes >= 0 && q_stride > 0 && k_stride > 0 && sp->cols > 0 && sp->rows > 0);
+    UVIP_CHECK_ARG(sp->mode == 0 || sp->mode == 1 || sp->mode == 4);
+    if (nframes == 0) return UVIP_OK;
+    UVIP_CHECK_ARG(d_qu && d_qv && d_qr && d_qmin_level && d_qmax_level && d_qdesc && d_nq && d_kx && d_ky && d_octave && d_kdesc && d_nk &&
+                   d_taken && d_match && d_counts);
+    const int ncell = sp->cols * sp->rows;
+    UVIP_CHECK_ARG((size_t)(2 * ncell + 1) * 4 <= 200 * 1024);
+    std::lock_guard<std::mutex> lk(m->mu);
+    DeviceGuard g(m->device);
+    cudaStream_t st = stream ? (cudaStream_t)stream : m->stream;
+    int rc;
+    const size_t nk_all = (size_t)nframes * k_stride;
+    if ((rc = m->misc2.reserve((size_t)nframes * (ncell + 1) * 4))) return rc;      // cell_start
+    if ((rc = m->misc3.reserve(nk_all * 4 * 2))) return rc;                         // cell_items, cell_of
+    if ((rc = m->misc4.reserve(nk_all * 4 * 2))) return rc;                         // owner tables A, B
+    int32_t* cs = m->misc2.as<int32_t>();
+    int32_t* ci = m->misc3.as<int32_t>();
+    int32_t* cof = ci + nk_all;
+    const size_t smem = (size_t)(2 * ncell + 1) * 4;
+    UVIP_CUDA(cudaFuncSetAttribute(k_grid_build, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+    k_grid_build<<<nframes, 1024, smem, st>>>(d_kx, d_ky, 0, sp->min_x, sp->min_y, sp->inv_w, sp->inv_h, sp->cols, sp->rows, cs, ci, cof, d_nk, k_stride);
+    SearchCtx c; memset(&c, 0, sizeof(c));
+    c.sp = *sp;
+    c.qu = d_qu; c.qv = d_qv; c.qr = d_qr; c.qminL = d_qmin_level; c.qmaxL = d_qmax_level; c.qdesc = d_qdesc;
+    c.kx = d_kx; c.ky = d_ky; c.octave = d_octave; c.kdesc = d_kdesc; c.cell_start = cs; c.cell_items = ci;
+    k_search_window<<<nframes, 1024, 0, st>>>(c, 0, 0, d_taken, d_match, m->misc4.as<int>(), m->misc4.as<int>() + nk_all, d_counts,
+                                               d_nq, d_nk, q_stride, k_stride);
+    m->launches += 2;
+    UVIP_CUDA(cudaGetLastError());
     return UVIP_OK;
 }
 

@@ -247,6 +247,25 @@ class ORBmatcher:
                                        ptr(i32(grid['items'])), ptr(tk), ptr(match), C.byref(n)))
         return n.value, match, tk
 
+    def projection_radius(self, view_cos, level, scale_factors, th=1.0):
+        """r = RadiusByViewingCos(viewCos) [* th] * mvScaleFactors[level]  (src/ORBmatcher.cc:68-76,127-133), float by float"""
+        r = np.array([lib().uvip_radius_by_viewing_cos(float(c)) for c in view_cos], np.float32)
+        if th != 1.0:
+            r = (r * np.float32(th)).astype(np.float32)
+        return (r * np.asarray(scale_factors, np.float32)[np.asarray(level, np.int32)]).astype(np.float32)
+
+    def search_window_batch_device(self, mode, th_dist, bounds, nframes, q_ptrs, d_nq, q_stride, k_ptrs, d_nk, k_stride,
+                                   d_taken, d_match, d_counts, stream=None, cols=64, rows=48):
+        """uvip_search_window_batch_device over raw device pointers (ints): q_ptrs = (qu, qv, qr, qminL, qmaxL, qdesc),
+        k_ptrs = (kx, ky, octave, kdesc); frame f owns [f*stride, f*stride + n[f]).  Asynchronous."""
+        minX, maxX, minY, maxY = bounds
+        inv_w = np.float32(cols) / np.float32(maxX - minX); inv_h = np.float32(rows) / np.float32(maxY - minY)
+        sp = SearchParams(mode, th_dist, self.mfNNratio, float(minX), float(minY), float(inv_w), float(inv_h), cols, rows)
+        vp = C.c_void_p
+        check(lib().uvip_search_window_batch_device(self.h, C.byref(sp), int(nframes), *[vp(p) for p in q_ptrs], vp(d_nq), int(q_stride),
+                                                    *[vp(p) for p in k_ptrs], vp(d_nk), int(k_stride), vp(d_taken), vp(d_match), vp(d_counts),
+                                                    vp(stream) if stream else None))
+
     def search_lists(self, mode, th_dist, qdesc, cand_start, cand_idx, kdesc, taken=None, ratio=None):
         qdesc = np.ascontiguousarray(qdesc, np.uint8); kdesc = np.ascontiguousarray(kdesc, np.uint8)
         cs = np.ascontiguousarray(cand_start, np.int32); ci = np.ascontiguousarray(cand_idx, np.int32)
@@ -278,12 +297,8 @@ class ORBmatcher:
     def SearchByProjection(self, frame, map_points, th=1.0, taken=None):
         """SearchByProjection(FrameKTL&, const vector<MapPoint*>&, float th) (src/ORBmatcher.cc:49-125) over flat arrays.
         frame: dict(kx, ky, octave, kdesc, grid, scale_factors); map_points: dict(u, v, level, view_cos, desc)."""
-        sf = np.asarray(frame['scale_factors'], np.float32)
         lvl = np.asarray(map_points['level'], np.int32)
-        r = np.array([lib().uvip_radius_by_viewing_cos(float(c)) for c in map_points['view_cos']], np.float32)
-        if th != 1.0:
-            r = (r * np.float32(th)).astype(np.float32)
-        r = (r * sf[lvl]).astype(np.float32)
+        r = self.projection_radius(map_points['view_cos'], lvl, frame['scale_factors'], th)
         return self.search_window(0, self.TH_HIGH, map_points['u'], map_points['v'], r, lvl - 1, lvl, map_points['desc'],
                                   frame['kx'], frame['ky'], frame['octave'], frame['kdesc'], frame['grid'], taken)
 
