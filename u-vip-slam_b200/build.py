@@ -28,15 +28,16 @@ def _deps():
     return out
 
 
-def build_cuda(force=False, verbose=False, extra=()):
+def build_cuda(force=False, verbose=False, extra=(), out=None):
+    """out: alternative output path (A/B variants built with extra -D flags; selected at run time with UVIP_LIB)"""
     srcs = [os.path.join(CSRC, s) for s in SOURCES if os.path.exists(os.path.join(CSRC, s))]
-    if not force and os.path.exists(SO) and all(os.path.getmtime(d) <= os.path.getmtime(SO) for d in _deps()):
+    if out is None and not force and os.path.exists(SO) and all(os.path.getmtime(d) <= os.path.getmtime(SO) for d in _deps()):
         return SO
     env = dict(os.environ)
     env.pop('CC', None); env.pop('CXX', None)
     cmd = [nvcc_path()] + NVCC_FLAGS + ['-ccbin', '/usr/bin/g++' if os.path.exists('/usr/bin/g++') else 'g++'] + \
-        list(extra) + ['-o', SO] + srcs
+        list(extra) + ['-o', out or SO] + srcs
     if verbose:
         print(' '.join(cmd), flush=True)
     subprocess.check_call(cmd, env=env)
-    return SO
+    return out or SO

@@ -46,7 +46,7 @@ def declared_symbols():
 def lib():
     global _LIB
     if _LIB is None:
-        so = _build.SO
+        so = os.environ.get('UVIP_LIB') or _build.SO          # UVIP_LIB: A/B builds of the same library while tuning kernels
         if not os.path.exists(so):
             so = _build.build_cuda()
         L = C.CDLL(so)

@@ -981,7 +981,10 @@ __device__ __forceinline__ void sincos_as_float(float xf, float* s_out, float* c
     *c_out = (float)(((n + 1) & 2) ? -c : c);
 }
 
-constexpr int DESC_WARPS = 8, DESC_KPW = 4;           // warps per CTA, keypoints per warp
+#ifndef DESC_KPW_
+#define DESC_KPW_ 4
+#endif
+constexpr int DESC_WARPS = 8, DESC_KPW = DESC_KPW_;           // warps per CTA, keypoints per warp
 #ifndef DESC_MINB
 #define DESC_MINB 4          // 64 registers: four CTAs per SM (the kernel is latency-bound; measured 0.37 -> 0.27 ms at batch 256)
 #endif
