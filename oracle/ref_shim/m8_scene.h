@@ -1,0 +1,163 @@
+// m8_scene.h — TEST INFRASTRUCTURE.  One scene description and one driver routine for the keyframe-side searches of
+// SURVEY 8a row M8, compiled TWICE with the same stand-in FrameKTL / KeyFrame / MapPoint types (slam_standin.h):
+//   * against the reference's own USLAM::ORBmatcher (src/ORBmatcher.cc, oracle/_ref/libref_orbmatcher.so, entry refm_m8_run)
+//   * against the drop-in shim's USLAM::ORBmatcher (u-vip-slam_b200/host/ORBmatcher.h -> C-ABI -> CUDA; tests/cpp/test_shim_m8.cpp)
+// Both read the same array bundle written by tests/test_reference_pin.py and dump the same result bundle, so the test is a
+// byte comparison of what the two matchers did to identical scenes through identical call signatures.
+#ifndef UVIP_M8_SCENE_H
+#define UVIP_M8_SCENE_H
+#include <stdio.h>
+#include <stdint.h>
+#include <string.h>
+#include <vector>
+
+namespace m8 {
+
+// bundle file: int32 count, then per array: int32 nbytes + payload
+struct Bundle {
+    std::vector<std::vector<char> > a;
+    bool load(const char* path)
+    {
+        FILE* f = fopen(path, "rb"); if (!f) return false;
+        int32_t n = 0; if (fread(&n, 4, 1, f) != 1) { fclose(f); return false; }
+        a.resize((size_t)n);
+        for (int i = 0; i < n; i++) {
+            int32_t nb = 0; if (fread(&nb, 4, 1, f) != 1) { fclose(f); return false; }
+            a[(size_t)i].resize((size_t)nb);
+            if (nb && fread(a[(size_t)i].data(), 1, (size_t)nb, f) != (size_t)nb) { fclose(f); return false; }
+        }
+        fclose(f); return true;
+    }
+    bool save(const char* path) const
+    {
+        FILE* f = fopen(path, "wb"); if (!f) return false;
+        int32_t n = (int32_t)a.size(); fwrite(&n, 4, 1, f);
+        for (size_t i = 0; i < a.size(); i++) { int32_t nb = (int32_t)a[i].size(); fwrite(&nb, 4, 1, f); if (nb) fwrite(a[i].data(), 1, (size_t)nb, f); }
+        fclose(f); return true;
+    }
+    template <class T> const T* get(int i) const { return (const T*)a[(size_t)i].data(); }
+    template <class T> int count(int i) const { return (int)(a[(size_t)i].size() / sizeof(T)); }
+    template <class T> void put(const std::vector<T>& v) { a.push_back(std::vector<char>((const char*)v.data(), (const char*)v.data() + v.size() * sizeof(T))); }
+};
+
+inline cv::Mat mat_f32(const float* p, int r, int c) { cv::Mat m(r, c, CV_32F); memcpy(m.data, p, sizeof(float) * (size_t)r * c); return m; }
+inline cv::Mat mat_desc(const uint8_t* d, int n) { cv::Mat m(n > 0 ? n : 1, 32, CV_8UC1); if (n > 0) memcpy(m.data, d, (size_t)n * 32); return m; }
+
+// array order of the scene bundle (written by tests/test_reference_pin.py::m8_bundle)
+enum { A_PARAMS = 0,      // float: th, s12, nnratio
+       A_SF,              // float[nlevels] scale factors (both keyframes)
+       A_INTR,            // float[4] fx fy cx cy
+       A_BOUNDS,          // int32[4] minX maxX minY maxY
+       A_SCW,             // float[16]
+       A_R12, A_T12,      // float[9], float[3]
+       K1_XYOA,           // float[nk1*4]: x, y, octave, angle
+       K1_DESC,           // uint8[nk1*32]
+       K1_POSE,           // float[15]: Rcw(9) tcw(3) Ow(3)
+       K1_MP,             // int32[nk1*3]: has map point, bad, pre-matched slot in K2 for SearchBySim3 (-1 none)
+       K1_MPGEO,          // float[nk1*8]: pos(3) normal(3) minDist maxDist of the slot's map point
+       K2_XYOA, K2_DESC, K2_POSE, K2_MP, K2_MPGEO,
+       P_FLAGS,           // int32[np*4]: null, bad, already observed in K1 (Fuse) / already matched (Scw searches), -
+       P_GEO,             // float[np*8]
+       P_DESC,            // uint8[np*32]
+       K1_MATCHED,        // int32[nk1]: vpMatched for SearchByProjection(KF,Scw): index into the point list or -1
+       A_COUNT };
+
+struct Scene {
+    USLAM::KeyFrame K[2];
+    std::vector<USLAM::MapPoint> kmp[2], pts;
+    std::vector<USLAM::MapPoint*> vp;
+    cv::Mat Scw, R12, t12; float th, s12, nnratio;
+    int nk[2], np;
+
+    void fill_point(USLAM::MapPoint& m, const float* geo, const uint8_t* desc, bool bad)
+    {
+        m.bad = bad; m.pos = mat_f32(geo, 3, 1); m.normal = mat_f32(geo + 3, 3, 1); m.minDist = geo[6]; m.maxDist = geo[7];
+        m.desc = mat_desc(desc, 1);
+    }
+    void build(const Bundle& B)
+    {
+        const float* prm = B.get<float>(A_PARAMS); th = prm[0]; s12 = prm[1]; nnratio = prm[2];
+        const int nl = B.count<float>(A_SF);
+        const float* intr = B.get<float>(A_INTR); const int32_t* bd = B.get<int32_t>(A_BOUNDS);
+        Scw = mat_f32(B.get<float>(A_SCW), 4, 4); R12 = mat_f32(B.get<float>(A_R12), 3, 3); t12 = mat_f32(B.get<float>(A_T12), 3, 1);
+        for (int k = 0; k < 2; k++) {
+            const int o = k ? K2_XYOA : K1_XYOA;
+            USLAM::KeyFrame& KF = K[k];
+            nk[k] = B.count<float>(o) / 4;
+            const float* xyoa = B.get<float>(o);
+            KF.keysUn.resize((size_t)nk[k]);
+            for (int i = 0; i < nk[k]; i++) KF.keysUn[(size_t)i] = cv::KeyPoint(xyoa[4 * i], xyoa[4 * i + 1], 31.f, xyoa[4 * i + 3], 0.f, (int)xyoa[4 * i + 2], -1);
+            KF.descriptors = mat_desc(B.get<uint8_t>(o + 1), nk[k]);
+            const float* pose = B.get<float>(o + 2);
+            KF.Rcw = mat_f32(pose, 3, 3); KF.tcw = mat_f32(pose + 9, 3, 1); KF.Ow = mat_f32(pose + 12, 3, 1);
+            KF.fx = intr[0]; KF.fy = intr[1]; KF.cx = intr[2]; KF.cy = intr[3];
+            KF.scaleFactors.assign(B.get<float>(A_SF), B.get<float>(A_SF) + nl);
+            KF.mnId = (unsigned long)k;
+            KF.set_bounds(bd[0], bd[1], bd[2], bd[3]);
+            const int32_t* mp = B.get<int32_t>(o + 3); const float* geo = B.get<float>(o + 4);
+            kmp[k].resize((size_t)nk[k]);
+            KF.mapPoints.assign((size_t)nk[k], (USLAM::MapPoint*)0);
+            for (int i = 0; i < nk[k]; i++)
+                if (mp[3 * i]) { fill_point(kmp[k][(size_t)i], geo + 8 * i, B.get<uint8_t>(o + 1) + 32 * (size_t)i, mp[3 * i + 1] != 0); kmp[k][(size_t)i].obs[&KF] = (size_t)i; KF.mapPoints[(size_t)i] = &kmp[k][(size_t)i]; }
+        }
+        np = B.count<int32_t>(P_FLAGS) / 4;
+        pts.resize((size_t)np); vp.assign((size_t)np, (USLAM::MapPoint*)0);
+        const int32_t* pf = B.get<int32_t>(P_FLAGS); const float* pg = B.get<float>(P_GEO);
+        for (int i = 0; i < np; i++) {
+            if (pf[4 * i]) continue;
+            fill_point(pts[(size_t)i], pg + 8 * i, B.get<uint8_t>(P_DESC) + 32 * (size_t)i, pf[4 * i + 1] != 0);
+            vp[(size_t)i] = &pts[(size_t)i];
+        }
+    }
+    // identity of a map point: keyframe-1 slot k -> k, keyframe-2 slot k -> 100000 + k, list point i -> 200000 + i, none -> -1
+    int id_of(const USLAM::MapPoint* p) const
+    {
+        if (!p) return -1;
+        if (!kmp[0].empty() && p >= &kmp[0][0] && p < &kmp[0][0] + nk[0]) return (int)(p - &kmp[0][0]);
+        if (!kmp[1].empty() && p >= &kmp[1][0] && p < &kmp[1][0] + nk[1]) return 100000 + (int)(p - &kmp[1][0]);
+        if (!pts.empty() && p >= &pts[0] && p < &pts[0] + np) return 200000 + (int)(p - &pts[0]);
+        return -2;
+    }
+};
+
+// which: 0 Fuse(KF, MPs, th)   1 Fuse(KF, Scw, MPs, th)   2 SearchByProjection(KF, Scw, MPs, vpMatched, th)   3 SearchBySim3
+template <class Matcher>
+int run(int which, const Bundle& in, Bundle& out)
+{
+    Scene S; S.build(in);
+    Matcher matcher(S.nnratio, true);
+    const int32_t* pf = in.get<int32_t>(P_FLAGS);
+    std::vector<int32_t> ret(1, 0), slot_owner, replaced, obs_slot;
+    USLAM::KeyFrame* pKF = &S.K[0];
+    if (which == 0 || which == 1) {
+        std::vector<USLAM::MapPoint*> vp;
+        for (int i = 0; i < S.np; i++) {
+            if (which == 1 && !S.vp[(size_t)i]) continue;            // Fuse(KF,Scw) dereferences every entry: no NULLs in its list
+            if (S.vp[(size_t)i] && pf[4 * i + 2] && which == 0) S.pts[(size_t)i].obs[pKF] = 0;     // IsInKeyFrame(pKF)
+            vp.push_back(S.vp[(size_t)i]);
+        }
+        ret[0] = which == 0 ? matcher.Fuse(pKF, vp, S.th) : matcher.Fuse(pKF, S.Scw, vp, S.th);
+        for (int k = 0; k < S.nk[0]; k++) slot_owner.push_back(S.id_of(pKF->mapPoints[(size_t)k]));
+        for (int k = 0; k < S.nk[0]; k++) replaced.push_back(S.id_of(S.kmp[0][(size_t)k].replaced));
+        for (int i = 0; i < S.np; i++) replaced.push_back(S.id_of(S.pts[(size_t)i].replaced));
+        for (int i = 0; i < S.np; i++) obs_slot.push_back(S.pts[(size_t)i].obs.count(pKF) && !(which == 0 && pf[4 * i + 2]) ? (int32_t)S.pts[(size_t)i].obs[pKF] : -1);
+    } else if (which == 2) {
+        std::vector<USLAM::MapPoint*> vp, matched((size_t)S.nk[0], (USLAM::MapPoint*)0);
+        for (int i = 0; i < S.np; i++) if (S.vp[(size_t)i]) vp.push_back(S.vp[(size_t)i]);
+        const int32_t* km = in.get<int32_t>(K1_MATCHED);
+        for (int k = 0; k < S.nk[0]; k++) if (km[k] >= 0 && S.vp[(size_t)km[k]]) matched[(size_t)k] = S.vp[(size_t)km[k]];
+        ret[0] = matcher.SearchByProjection(pKF, S.Scw, vp, matched, (int)S.th);
+        for (int k = 0; k < S.nk[0]; k++) slot_owner.push_back(S.id_of(matched[(size_t)k]));
+    } else {
+        const int32_t* mp1 = in.get<int32_t>(K1_MP);
+        std::vector<USLAM::MapPoint*> m12((size_t)S.nk[0], (USLAM::MapPoint*)0);
+        for (int k = 0; k < S.nk[0]; k++) if (mp1[3 * k + 2] >= 0 && S.K[1].mapPoints[(size_t)mp1[3 * k + 2]]) m12[(size_t)k] = S.K[1].mapPoints[(size_t)mp1[3 * k + 2]];
+        ret[0] = matcher.SearchBySim3(&S.K[0], &S.K[1], m12, S.s12, S.R12, S.t12, S.th);
+        for (int k = 0; k < S.nk[0]; k++) slot_owner.push_back(S.id_of(m12[(size_t)k]));
+    }
+    out.put(ret); out.put(slot_owner); out.put(replaced); out.put(obs_slot);
+    return ret[0];
+}
+
+}  // namespace m8
+#endif

@@ -10,6 +10,7 @@
 #include <set>
 #include <vector>
 #include "ORBmatcher.h"
+#include "m8_scene.h"
 
 using namespace USLAM;
 
@@ -213,8 +214,7 @@ int refm_fuse(int nk, const float* kx, const float* ky, const int32_t* octave, c
     KeyFrame KF;
     fill_keys(KF.keysUn, nk, kx, ky, octave, 0);
     KF.descriptors = desc_mat(kdesc, nk);
-    KF.minX = bounds[0]; KF.maxX = bounds[1]; KF.minY = bounds[2]; KF.maxY = bounds[3];
-    KF.grid.build(KF.keysUn, KF.minX, KF.maxX, KF.minY, KF.maxY);
+    KF.set_bounds((int)bounds[0], (int)bounds[1], (int)bounds[2], (int)bounds[3]);
     KF.scaleFactors.assign(sf, sf + nlevels);
     KF.Rcw = cv::Mat(3, 3, CV_32F); memcpy(KF.Rcw.data, Rcw, 36);
     KF.tcw = vec3(tcw); KF.Ow = vec3(Ow);
@@ -242,6 +242,16 @@ int refm_fuse(int nk, const float* kx, const float* ky, const int32_t* octave, c
         else if (!in_kf[i] && m.obs.count(&KF)) { action[i] = 2; target[i] = (int32_t)m.obs[&KF]; }
     }
     return n;
+}
+
+// the keyframe-side searches of row M8 on a scene bundle (m8_scene.h): 0 Fuse(KF,MPs)  1 Fuse(KF,Scw)  2 SearchByProjection(KF,Scw)
+// 3 SearchBySim3.  Returns the reference's return value, or -1000 on I/O failure.
+int refm_m8_run(const char* scene_path, const char* out_path, int which)
+{
+    m8::Bundle in, out;
+    if (!in.load(scene_path) || (int)in.a.size() < m8::A_COUNT) return -1000;
+    const int r = m8::run<ORBmatcher>(which, in, out);
+    return out.save(out_path) ? r : -1000;
 }
 
 }  // extern "C"

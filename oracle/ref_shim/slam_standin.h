@@ -90,15 +90,26 @@ public:
 
 class KeyFrame {
 public:
-    KeyFrame() : fx(0), fy(0), cx(0), cy(0), mnId(0) {}
+    KeyFrame() : mnGridCols(FRAME_GRID_COLS), mnGridRows(FRAME_GRID_ROWS), mfGridElementWidthInv(0), mfGridElementHeightInv(0), fx(0), fy(0), cx(0), cy(0),
+                 mnId(0), mnMinX(0), mnMinY(0), mnMaxX(0), mnMaxY(0) {}
+    // public members of the reference class (include/KeyFrame.h:186-246)
+    int mnGridCols, mnGridRows; float mfGridElementWidthInv, mfGridElementHeightInv;
+    float fx, fy, cx, cy; long unsigned int mnId;
+    // protected in the reference (include/KeyFrame.h:260-263); the shim needs mnMinX / mnMinY
+    int mnMinX, mnMinY, mnMaxX, mnMaxY;
+    // data
     std::vector<cv::KeyPoint> keysUn;
     cv::Mat descriptors, Rcw, tcw, Ow;
     std::vector<MapPoint*> mapPoints;
     std::vector<float> scaleFactors, levelSigma2;
     DBoW2::FeatureVector featVec;
-    float fx, fy, cx, cy; long unsigned int mnId;
-    float minX, maxX, minY, maxY;
     GridStandin grid;
+    void set_bounds(int minX, int maxX, int minY, int maxY)
+    {
+        mnMinX = minX; mnMaxX = maxX; mnMinY = minY; mnMaxY = maxY;
+        mfGridElementWidthInv = (float)mnGridCols / (float)(maxX - minX); mfGridElementHeightInv = (float)mnGridRows / (float)(maxY - minY);
+        grid.build(keysUn, (float)minX, (float)maxX, (float)minY, (float)maxY);
+    }
     std::vector<MapPoint*> GetMapPointMatches() { return mapPoints; }
     MapPoint* GetMapPoint(const size_t& idx) { return mapPoints[idx]; }
     std::set<MapPoint*> GetMapPoints() { std::set<MapPoint*> s; for (MapPoint* p : mapPoints) if (p && !p->isBad()) s.insert(p); return s; }
@@ -116,7 +127,7 @@ public:
     cv::Mat GetRotation() { return Rcw.clone(); }
     cv::Mat GetTranslation() { return tcw.clone(); }
     cv::Mat GetCameraCenter() { return Ow.clone(); }
-    bool IsInImage(const float& x, const float& y) const { return x >= minX && x < maxX && y >= minY && y < maxY; }     // src/KeyFrame.cc:994-997
+    bool IsInImage(const float& x, const float& y) const { return x >= mnMinX && x < mnMaxX && y >= mnMinY && y < mnMaxY; }     // src/KeyFrame.cc:994-997
     // src/KeyFrame.cc:952-992: no level filter
     std::vector<size_t> GetFeaturesInArea(const float& x, const float& y, const float& r) const { return grid.area(x, y, r, -1, -1); }
 };

@@ -146,10 +146,10 @@ struct MatProd { Mat a, b; inline operator Mat() const; };
 struct MatT { Mat a; double alpha; };
 inline MatT Mat::t() const { assert(tp == CV_32F); MatT e = {*this, 1.0}; return e; }
 inline Mat::Mat(const MatT& e) : data(0), rows(0), cols(0), tp(CV_8UC1), buf(0)
-{   // transpose, then scale through convertTo (double product, one rounding)
+{   // transpose, then scale through convertTo (float product, see mat_scale)
     create(e.a.cols, e.a.rows, CV_32F);
     for (int y = 0; y < e.a.rows; y++) for (int x = 0; x < e.a.cols; x++)
-        at<float>(x, y) = e.alpha == 1.0 ? e.a.at<float>(y, x) : (float)((double)e.a.at<float>(y, x) * e.alpha);
+        at<float>(x, y) = e.alpha == 1.0 ? e.a.at<float>(y, x) : e.a.at<float>(y, x) * (float)e.alpha;
 }
 static inline Mat gemm_small(const Mat& a, const Mat& b, const Mat* c)
 {
@@ -194,10 +194,12 @@ static inline Mat mat_map2(const Mat& a, const Mat& b, float sb)
     return m;
 }
 static inline Mat mat_scale(const Mat& a, double s)
-{   // cv::Mat * scalar / scalar go through convertTo(alpha): the product is formed in double and rounded to float once
+{   // cv::Mat * scalar / scalar go through convertTo(alpha); for 32f -> 32f OpenCV 3.4's cvtScale works in float
+    // (core/src/convert.cpp, DEF_CVT_SCALE_FUNC(32f, float, float, float)): dst = src * (float)alpha
     assert(a.type() == CV_32F);
     Mat m(a.rows, a.cols, CV_32F);
-    for (int y = 0; y < a.rows; y++) for (int x = 0; x < a.cols; x++) m.at<float>(y, x) = (float)((double)a.at<float>(y, x) * s);
+    const float sf = (float)s;
+    for (int y = 0; y < a.rows; y++) for (int x = 0; x < a.cols; x++) m.at<float>(y, x) = a.at<float>(y, x) * sf;
     return m;
 }
 static inline Mat operator+(const Mat& a, const Mat& b) { return mat_map2(a, b, 1.f); }

@@ -220,3 +220,34 @@ def fuse(kx, ky, octave, kdesc, bounds, scale_factors, Rcw, tcw, Ow, intr, kf_ha
                          _p(_u8(in_kf)), _p(_f32(pos)), _p(_f32(normal)), _p(_f32(min_dist)), _p(_f32(max_dist)), _p(_u8(pdesc)), C.c_float(th),
                          _p(action), _p(target))
     return n, action, target
+
+
+M8_EXE = os.path.join(_HERE, '_ref', 'test_shim_m8')
+
+
+def write_bundle(path, arrays):
+    """array bundle of oracle/ref_shim/m8_scene.h: int32 count, then int32 nbytes + payload per array"""
+    import struct
+    with open(path, 'wb') as f:
+        f.write(struct.pack('i', len(arrays)))
+        for a in arrays:
+            b = np.ascontiguousarray(a).tobytes()
+            f.write(struct.pack('i', len(b))); f.write(b)
+
+
+def read_bundle(path):
+    import struct
+    buf = open(path, 'rb').read()
+    n = struct.unpack_from('i', buf, 0)[0]; off = 4; out = []
+    for _ in range(n):
+        nb = struct.unpack_from('i', buf, off)[0]; off += 4
+        out.append(np.frombuffer(buf, np.int32, nb // 4, off).copy()); off += nb
+    return out
+
+
+def m8_run(scene_path, out_path, which):
+    """the reference's own Fuse / Fuse(Scw) / SearchByProjection(KF,Scw) / SearchBySim3 (which = 0..3) on a scene bundle"""
+    r = mlib().refm_m8_run(scene_path.encode(), out_path.encode(), int(which))
+    if r == -1000:
+        raise RuntimeError('refm_m8_run: I/O failure')
+    return r, read_bundle(out_path)

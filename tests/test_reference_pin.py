@@ -522,3 +522,125 @@ def test_fuse_equals_reference(oracle, synth, th):
     assert rn == fused == on and rn > 300
     assert (e_action == 1).sum() > 50 and (e_action == 2).sum() > 50 and (e_target < -1).sum() > 0     # every branch exercised
     assert np.array_equal(action, e_action) and np.array_equal(target, e_target)
+
+
+# ---------------------------------------------------------------------------------------------------- row M8 through the shim
+def m8_bundle(oracle, synth, which):
+    """scene for the keyframe-side searches (array order: oracle/ref_shim/m8_scene.h)"""
+    f32 = np.float32
+    W, H = 752, 480
+    kps, desc = frame_for_matching(oracle, synth)
+    n = len(kps); sf = scale_factors()
+    rng = np.random.default_rng(100 + which)
+    fx, fy, cx, cy = f32(458.0), f32(457.0), f32(367.0), f32(248.0)
+
+    def rot(ax, ay, az):
+        cxr, sxr, cyr, syr, czr, szr = np.cos(ax), np.sin(ax), np.cos(ay), np.sin(ay), np.cos(az), np.sin(az)
+        Rx = np.array([[1, 0, 0], [0, cxr, -sxr], [0, sxr, cxr]]); Ry = np.array([[cyr, 0, syr], [0, 1, 0], [-syr, 0, cyr]])
+        Rz = np.array([[czr, -szr, 0], [szr, czr, 0], [0, 0, 1]])
+        return (Rz @ Ry @ Rx).astype(np.float32)
+    R1, t1 = rot(0.004, -0.003, 0.01), np.array([0.01, -0.02, 0.03], np.float32)
+    R2, t2 = rot(-0.002, 0.006, 0.004), np.array([-0.04, 0.01, 0.02], np.float32)
+    ow = lambda R, t: (-(R.astype(np.float64).T @ t.astype(np.float64))).astype(np.float32)
+    O1, O2 = ow(R1, t1), ow(R2, t2)
+    z = (2.0 + (np.arange(n) % 7) * 0.5).astype(np.float32)
+    Xc = np.stack([(kps['x'] - cx) / fx * z, (kps['y'] - cy) / fy * z, z], 1).astype(np.float64)
+    Xw = ((Xc - t1.astype(np.float64)) @ R1.astype(np.float64)).astype(np.float32)           # R1^T (Xc - t1)
+
+    def geo(X, Ocam, octave, i):
+        d = np.linalg.norm((X - Ocam).astype(np.float64), axis=1)
+        mind = (d / (sf[octave] * 0.98)).astype(np.float32)
+        maxd = (mind * sf[-1] * 1.3).astype(np.float32)
+        nrm = ((X - Ocam) / d[:, None]).astype(np.float32)
+        mind = np.where(i % 37 == 1, mind * 3, mind).astype(np.float32)                      # some too close
+        maxd = np.where(i % 43 == 2, mind * 0.5, maxd).astype(np.float32)                    # some too far
+        nrm[i % 31 == 4] = np.array([1, 0, 0], np.float32)                                   # some seen from the side
+        return np.concatenate([X, nrm, mind[:, None], maxd[:, None]], 1).astype(np.float32)
+
+    def flips(d, k, p):
+        out = d.copy()
+        pos = rng.integers(0, 256, (len(d), k))
+        for j in range(k):
+            sel = rng.random(len(d)) < p
+            out[sel, pos[sel, j] >> 3] ^= (1 << (pos[sel, j] & 7)).astype(np.uint8)
+        return out
+
+    idx = np.arange(n)
+    k1_xyoa = np.stack([kps['x'], kps['y'], kps['octave'].astype(np.float32), kps['angle']], 1).astype(np.float32)
+    k1_mp = np.stack([(idx % 3 != 0), (idx % 16 == 5), np.where(idx % 13 == 6, idx, -1)], 1).astype(np.int32)
+    k1_geo = geo(Xw, O1, kps['octave'], idx)
+    # keyframe 2 sees the same 3-D points from a slightly different pose
+    Xc2 = (Xw.astype(np.float64) @ R2.astype(np.float64).T + t2.astype(np.float64))
+    u2 = (fx * Xc2[:, 0] / Xc2[:, 2] + cx + rng.normal(0, 0.6, n)).astype(np.float32)
+    v2 = (fy * Xc2[:, 1] / Xc2[:, 2] + cy + rng.normal(0, 0.6, n)).astype(np.float32)
+    k2_xyoa = np.stack([u2, v2, kps['octave'].astype(np.float32), np.mod(kps['angle'] + rng.normal(0, 5, n), 360).astype(np.float32)], 1).astype(np.float32)
+    k2_desc = flips(desc, 10, 0.6)
+    k2_mp = np.stack([(idx % 4 != 1), (idx % 18 == 7), np.full(n, -1)], 1).astype(np.int32)
+    k2_geo = geo(Xw, O2, kps['octave'], idx + 5)
+    # candidate map points: two per keypoint, jittered around the keypoint's 3-D point
+    npnt = 2 * n
+    pi = np.arange(npnt); src = pi % n
+    jit = np.stack([((pi * 7) % 5 - 2) * 0.004, ((pi * 3) % 5 - 2) * 0.003, np.zeros(npnt)], 1)
+    Pw = (Xw[src].astype(np.float64) + jit * z[src, None]).astype(np.float32)
+    Pw[pi % 41 == 0] = (O1 - (Xw[src][pi % 41 == 0] - O1)).astype(np.float32)                # behind the camera
+    p_flags = np.stack([(pi % 14 == 3), (pi % 25 == 6), (pi % 9 == 2), np.zeros(npnt)], 1).astype(np.int32)
+    p_geo = geo(Pw, O1, kps['octave'][src], pi + 11)
+    p_desc = flips(desc[src], 14, 0.6)
+    k1_matched = np.where(idx % 11 == 4, (idx * 2 + 1) % npnt, -1).astype(np.int32)
+    # Sim3 between the cameras (s12 = 1): p1 = R12 p2 + t12;  Scw = 1.7 * [R1 | t1]
+    R12 = (R1.astype(np.float64) @ R2.astype(np.float64).T).astype(np.float32)
+    t12 = (t1.astype(np.float64) - R12.astype(np.float64) @ t2.astype(np.float64)).astype(np.float32)
+    Scw = np.eye(4, dtype=np.float32); Scw[:3, :3] = f32(1.7) * R1; Scw[:3, 3] = f32(1.7) * t1
+    th = [3.0, 4.0, 10.0, 7.5][which]
+    pose = lambda R, t, O: np.concatenate([R.ravel(), t, O]).astype(np.float32)
+    return [np.array([th, 1.0, 0.6], np.float32), sf, np.array([fx, fy, cx, cy], np.float32), np.array([0, W, 0, H], np.int32), Scw, R12, t12,
+            k1_xyoa, desc, pose(R1, t1, O1), k1_mp, k1_geo, k2_xyoa, k2_desc, pose(R2, t2, O2), k2_mp, k2_geo, p_flags, p_geo, p_desc, k1_matched]
+
+
+M8_NAMES = ['Fuse(KF, MPs, th)', 'Fuse(KF, Scw, MPs, th)', 'SearchByProjection(KF, Scw, MPs, vpMatched, th)', 'SearchBySim3']
+
+
+@needs_mref
+@pytest.mark.parametrize('which', [0, 1, 2, 3])
+def test_m8_reference_runs_every_branch(oracle, synth, which, tmp_path):
+    """the scenes must exercise the reference's code paths (otherwise the GPU comparison below proves little)"""
+    R.write_bundle(str(tmp_path / 's.bin'), m8_bundle(oracle, synth, which))
+    r, (ret, slot_owner, replaced, obs_slot) = R.m8_run(str(tmp_path / 's.bin'), str(tmp_path / 'o.bin'), which)
+    assert ret[0] == r and r > 150, (M8_NAMES[which], r)
+    if which in (0, 1):
+        assert (replaced >= 0).sum() > 30 and (obs_slot >= 0).sum() > 30          # both bookkeeping branches
+        assert (slot_owner >= 200000).sum() == (obs_slot >= 0).sum()              # added points sit in the keyframe's slots
+        if which == 1:
+            assert (replaced[:len(slot_owner)] >= 200000).sum() > 30              # Fuse(Scw) replaces the KEYFRAME's points
+    elif which == 2:
+        assert (slot_owner >= 200000).sum() >= r
+    else:
+        assert (slot_owner >= 100000).sum() >= r
+
+
+@needs_mref
+def test_shim_m8_driver_refuses_without_device(pkg, oracle, synth, tmp_path):
+    import os, subprocess
+    if pkg.capi.lib().uvip_device_count() > 0 or not os.path.exists(R.M8_EXE):
+        pytest.skip('a CUDA device is present, or the prebuilt driver is missing')
+    R.write_bundle(str(tmp_path / 's.bin'), m8_bundle(oracle, synth, 0))
+    p = subprocess.run([R.M8_EXE, str(tmp_path / 's.bin'), str(tmp_path / 'o.bin'), '0'], capture_output=True, text=True)
+    assert p.returncode == 3 and 'no CPU fallback' in p.stderr
+
+
+@needs_mref
+@pytest.mark.gpu
+@pytest.mark.parametrize('which', [0, 1, 2, 3])
+def test_shim_m8_equals_reference(gpu, oracle, synth, which, tmp_path):
+    """row M8 end to end: the drop-in shim (host geometry + uvip_search_window on the GPU) against the reference's compiled
+    ORBmatcher, same scene code, same stand-in SLAM types, same call signatures; result bundles must be identical."""
+    import os, subprocess
+    assert os.path.exists(R.M8_EXE), 'oracle/_ref/test_shim_m8 is prebuilt by `make -C oracle ref` in the build container'
+    R.write_bundle(str(tmp_path / 's.bin'), m8_bundle(oracle, synth, which))
+    r, ref = R.m8_run(str(tmp_path / 's.bin'), str(tmp_path / 'ref.bin'), which)
+    p = subprocess.run([R.M8_EXE, str(tmp_path / 's.bin'), str(tmp_path / 'shim.bin'), str(which)], capture_output=True, text=True)
+    assert p.returncode == 0, p.stderr
+    shim = R.read_bundle(str(tmp_path / 'shim.bin'))
+    assert int(p.stdout.strip()) == r and r > 150, (M8_NAMES[which], p.stdout, r)
+    for a, b, name in zip(shim, ref, ('return', 'slot owner', 'replaced', 'observation')):
+        assert np.array_equal(a, b), (M8_NAMES[which], name, int((a != b).sum()))

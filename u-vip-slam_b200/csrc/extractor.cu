@@ -526,7 +526,10 @@ k_fast(const CUtensorMap* __restrict__ tmaps, const unsigned* __restrict__ tile_
 // the sorted order finds that stopping point.  The sort tie on node POINTER (:1151) is pinned to creation order
 // (later-created = nearer the list front = first), same as the oracle.
 // --------------------------------------------------------------------------------------------------------
-constexpr int QT_THREADS = 256;
+#ifndef QT_THREADS_
+#define QT_THREADS_ 256
+#endif
+constexpr int QT_THREADS = QT_THREADS_;
 
 struct QtShared {          // laid out in dynamic shared memory, all arrays node_cap long unless noted
     int* box[2];           // 4 ints per node: x0,y0,x1,y1

@@ -278,6 +278,268 @@ public:
         return nmatches;
     }
 
+    // ------------------------------------------------------------------------------------------------------------------
+    // Keyframe-side searches (LocalMapping / LoopClosing threads).  The host side keeps the reference's
+    // geometry — projection, depth / image / distance / viewing-angle gates, lower_bound level prediction — with cv::Mat
+    // arithmetic as OpenCV 3.4 evaluates it (R*x+t: gemm's small-matrix float path; anything transposed and cv::norm / dot:
+    // double accumulation; Mat*scalar: float product with the scalar rounded to float), and hands the window search to uvip_search_window:
+    // KeyFrame::GetFeaturesInArea (src/KeyFrame.cc:952-992) + levels [l-1, l] + best-only, with claims (mode 1) or without
+    // (mode 4).  KeyFrameT needs: fx, fy, cx, cy, mnMinX, mnMinY (protected in the reference: add `friend class ORBmatcher;`
+    // or two getters), mfGridElementWidthInv, mfGridElementHeightInv, GetKeyPointsUn(), GetDescriptors(),
+    // GetScaleFactors(), GetScaleLevels(), IsInImage(u, v), GetMapPoint(i), AddMapPoint(p, i), GetMapPoints(),
+    // GetMapPointMatches(), GetRotation(), GetTranslation(), GetCameraCenter();  MapPointT: isBad(), IsInKeyFrame(kf),
+    // GetWorldPos(), GetNormal(), GetMin/MaxDistanceInvariance(), GetDescriptor(), Replace(p), AddObservation(kf, i),
+    // GetIndexInKeyFrame(kf).
+    // ------------------------------------------------------------------------------------------------------------------
+protected:
+    struct Pose3 { float R[3][3], t[3], Ow[3]; };
+    static void read3x3(const cv::Mat& m, float R[3][3]) { for (int r = 0; r < 3; r++) for (int c = 0; c < 3; c++) R[r][c] = m.template ptr<float>(r)[c]; }
+    static void read3(const cv::Mat& m, float v[3]) { for (int r = 0; r < 3; r++) v[r] = m.template ptr<float>(r)[0]; }
+    // Scw -> Rcw, tcw, Ow  (src/ORBmatcher.cc:298-302, :1145-1149)
+    static void decompose_sim3(const cv::Mat& Scw, Pose3& P)
+    {
+        float s[3][4];
+        for (int r = 0; r < 3; r++) for (int c = 0; c < 4; c++) s[r][c] = Scw.template ptr<float>(r)[c];
+        double d = 0; for (int c = 0; c < 3; c++) d += (double)s[0][c] * (double)s[0][c];       // sRcw.row(0).dot(sRcw.row(0))
+        const float scw = (float)std::sqrt(d);
+        const float inv = (float)(1.0 / scw);                        // Mat / scalar = convertTo(alpha = 1/scalar): float product for 32f (convert.cpp)
+        for (int r = 0; r < 3; r++) { for (int c = 0; c < 3; c++) P.R[r][c] = s[r][c] * inv; P.t[r] = s[r][3] * inv; }
+        camera_center(P);
+    }
+    static void camera_center(Pose3& P)                                                          // Ow = -Rcw.t()*tcw: generic gemm, double
+    {
+        for (int c = 0; c < 3; c++) { double a = 0; for (int r = 0; r < 3; r++) a += (double)P.R[r][c] * (double)P.t[r]; P.Ow[c] = (float)(a * -1.0); }
+    }
+    static void mul_add3(const float R[3][3], const float x[3], const float t[3], float out[3])  // R*x + t, gemm small-matrix path
+    {
+        for (int r = 0; r < 3; r++) { float a = R[r][0] * x[0]; a = a + R[r][1] * x[1]; a = a + R[r][2] * x[2]; out[r] = (float)((double)a + (double)t[r]); }
+    }
+    static float norm3(const float v[3]) { double a = 0; for (int r = 0; r < 3; r++) a += (double)v[r] * (double)v[r]; return (float)std::sqrt(a); }
+
+    struct KfQueries {
+        std::vector<float> u, v, r; std::vector<int32_t> lo, hi; std::vector<unsigned char> d; std::vector<int> who;
+        void push(float u_, float v_, float r_, int lvl, const cv::Mat& desc, int index)
+        { u.push_back(u_); v.push_back(v_); r.push_back(r_); lo.push_back(lvl - 1); hi.push_back(lvl); d.insert(d.end(), desc.ptr(0), desc.ptr(0) + 32); who.push_back(index); }
+    };
+    // the shared tail of :1036-1086 / :324-362 / :1173-1215: image, distance and viewing-angle gates, level, radius
+    template <class KeyFrameT, class MapPointT>
+    static bool gate_and_level(KeyFrameT* pKF, MapPointT* pMP, const float p3Dw[3], const float Ow[3], float u, float v, const std::vector<float>& sf,
+                               bool normal_gate, float dist3D_given, bool use_given, int& level)
+    {
+        if (!pKF->IsInImage(u, v)) return false;
+        const float maxDistance = pMP->GetMaxDistanceInvariance(), minDistance = pMP->GetMinDistanceInvariance();
+        float PO[3] = {p3Dw[0] - Ow[0], p3Dw[1] - Ow[1], p3Dw[2] - Ow[2]};
+        const float dist3D = use_given ? dist3D_given : norm3(PO);
+        if (dist3D < minDistance || dist3D > maxDistance) return false;
+        if (normal_gate) {
+            float Pn[3]; read3(pMP->GetNormal(), Pn);
+            double dot = 0; for (int r = 0; r < 3; r++) dot += (double)PO[r] * (double)Pn[r];
+            if (dot < 0.5 * dist3D) return false;
+        }
+        const float ratio = dist3D / minDistance;
+        level = std::min((int)(std::lower_bound(sf.begin(), sf.end(), ratio) - sf.begin()), (int)sf.size() - 1);
+        return true;
+    }
+    // KeyFrame::GetFeaturesInArea window + levels [l-1, l] + best-only over a flattened keyframe; match[q] = keypoint or -1
+    template <class KeyFrameT>
+    int keyframe_window_search(KeyFrameT* pKF, int mode, int th_dist, const KfQueries& Q, std::vector<int32_t>& taken, std::vector<int32_t>& match)
+    {
+        const std::vector<cv::KeyPoint> keys = pKF->GetKeyPointsUn();
+        const cv::Mat D = pKF->GetDescriptors();
+        const int nk = (int)keys.size(), nq = (int)Q.who.size();
+        match.assign((size_t)nq, -1);
+        if (nq == 0 || nk == 0) return 0;
+        std::vector<float> kx((size_t)nk), ky((size_t)nk); std::vector<int32_t> oct((size_t)nk); std::vector<unsigned char> kd((size_t)nk * 32);
+        for (int i = 0; i < nk; i++) { kx[i] = keys[i].pt.x; ky[i] = keys[i].pt.y; oct[i] = keys[i].octave; std::memcpy(&kd[(size_t)i * 32], D.ptr(i), 32); }
+        if (taken.size() != (size_t)nk) taken.assign((size_t)nk, -1);
+        uvip_search_params sp;
+        sp.mode = mode; sp.th_dist = th_dist; sp.ratio = mfNNratio;
+        sp.min_x = (float)pKF->mnMinX; sp.min_y = (float)pKF->mnMinY; sp.inv_w = pKF->mfGridElementWidthInv; sp.inv_h = pKF->mfGridElementHeightInv;
+        sp.cols = 64; sp.rows = 48;
+        std::vector<int32_t> cs(64 * 48 + 1), ci((size_t)nk);
+        check(uvip_grid_build(handle_, kx.data(), ky.data(), nk, sp.min_x, sp.min_y, sp.inv_w, sp.inv_h, 64, 48, cs.data(), ci.data()), "uvip_grid_build");
+        int n = 0;
+        check(uvip_search_window(handle_, &sp, Q.u.data(), Q.v.data(), Q.r.data(), Q.lo.data(), Q.hi.data(), Q.d.data(), nq, kx.data(), ky.data(), oct.data(),
+                                 kd.data(), nk, cs.data(), ci.data(), taken.data(), match.data(), &n), "uvip_search_window");
+        return n;
+    }
+
+public:
+    // Fuse(KeyFrame* pKF, vector<MapPoint*>& vpMapPoints, float th)  (src/ORBmatcher.cc:1016-1134; src/LocalMapping.cc:1236,1261)
+    template <class KeyFrameT, class MapPointT>
+    int Fuse(KeyFrameT* pKF, std::vector<MapPointT*>& vpMapPoints, const float th = 3.0f)
+    {
+        ensure();
+        Pose3 P; read3x3(pKF->GetRotation(), P.R); read3(pKF->GetTranslation(), P.t); read3(pKF->GetCameraCenter(), P.Ow);
+        const float fx = pKF->fx, fy = pKF->fy, cx = pKF->cx, cy = pKF->cy;
+        const std::vector<float> sf = pKF->GetScaleFactors();
+        KfQueries Q;
+        for (size_t i = 0; i < vpMapPoints.size(); i++) {
+            MapPointT* pMP = vpMapPoints[i];
+            if (!pMP) continue;
+            if (pMP->isBad() || pMP->IsInKeyFrame(pKF)) continue;
+            float X[3], c3[3]; read3(pMP->GetWorldPos(), X); mul_add3(P.R, X, P.t, c3);
+            if (c3[2] < 0.0f) continue;
+            const float invz = 1 / c3[2], x = c3[0] * invz, y = c3[1] * invz;
+            const float u = fx * x + cx, v = fy * y + cy;
+            int lvl;
+            if (!gate_and_level(pKF, pMP, X, P.Ow, u, v, sf, true, 0.f, false, lvl)) continue;
+            Q.push(u, v, th * sf[(size_t)lvl], lvl, pMP->GetDescriptor(), (int)i);
+        }
+        std::vector<int32_t> taken, match;
+        keyframe_window_search(pKF, 4, TH_LOW, Q, taken, match);
+        int nFused = 0;
+        for (size_t q = 0; q < match.size(); q++) {                            // :1115-1129, in map-point order
+            if (match[q] < 0) continue;
+            MapPointT* pMP = vpMapPoints[(size_t)Q.who[q]];
+            MapPointT* pMPinKF = pKF->GetMapPoint((size_t)match[q]);
+            if (pMPinKF) { if (!pMPinKF->isBad()) pMP->Replace(pMPinKF); }
+            else { pMP->AddObservation(pKF, (size_t)match[q]); pKF->AddMapPoint(pMP, (size_t)match[q]); }
+            nFused++;
+        }
+        return nFused;
+    }
+
+    // Fuse(KeyFrame* pKF, cv::Mat Scw, const vector<MapPoint*>& vpPoints, float th)  (src/ORBmatcher.cc:1136-1265; src/LoopClosing.cc:704)
+    template <class KeyFrameT, class MapPointT>
+    int Fuse(KeyFrameT* pKF, cv::Mat Scw, const std::vector<MapPointT*>& vpPoints, float th = 2.5f)
+    {
+        ensure();
+        Pose3 P; decompose_sim3(Scw, P);
+        const float fx = pKF->fx, fy = pKF->fy, cx = pKF->cx, cy = pKF->cy;
+        const std::set<MapPointT*> spAlreadyFound = pKF->GetMapPoints();
+        const std::vector<float> sf = pKF->GetScaleFactors();
+        KfQueries Q;
+        for (size_t i = 0; i < vpPoints.size(); i++) {
+            MapPointT* pMP = vpPoints[i];
+            if (pMP->isBad() || spAlreadyFound.count(pMP)) continue;
+            float X[3], c3[3]; read3(pMP->GetWorldPos(), X); mul_add3(P.R, X, P.t, c3);
+            if (c3[2] < 0.0f) continue;
+            const float invz = (float)(1.0 / c3[2]), x = c3[0] * invz, y = c3[1] * invz;          // :1180 `1.0/`
+            const float u = fx * x + cx, v = fy * y + cy;
+            int lvl;
+            if (!gate_and_level(pKF, pMP, X, P.Ow, u, v, sf, true, 0.f, false, lvl)) continue;
+            Q.push(u, v, th * sf[(size_t)lvl], lvl, pMP->GetDescriptor(), (int)i);
+        }
+        std::vector<int32_t> taken, match;
+        keyframe_window_search(pKF, 4, TH_LOW, Q, taken, match);
+        int nFused = 0;
+        for (size_t q = 0; q < match.size(); q++) {                            // :1246-1260: here the KEYFRAME's point is replaced
+            if (match[q] < 0) continue;
+            MapPointT* pMP = vpPoints[(size_t)Q.who[q]];
+            MapPointT* pMPinKF = pKF->GetMapPoint((size_t)match[q]);
+            if (pMPinKF) { if (!pMPinKF->isBad()) pMPinKF->Replace(pMP); }
+            else { pMP->AddObservation(pKF, (size_t)match[q]); pKF->AddMapPoint(pMP, (size_t)match[q]); }
+            nFused++;
+        }
+        return nFused;
+    }
+
+    // SearchByProjection(KeyFrame* pKF, cv::Mat Scw, const vector<MapPoint*>& vpPoints, vector<MapPoint*>& vpMatched, int th)
+    // (src/ORBmatcher.cc:286-407; src/LoopClosing.cc:512): claims on vpMatched, so later points skip taken keypoints (mode 1)
+    template <class KeyFrameT, class MapPointT>
+    int SearchByProjection(KeyFrameT* pKF, cv::Mat Scw, const std::vector<MapPointT*>& vpPoints, std::vector<MapPointT*>& vpMatched, int th)
+    {
+        ensure();
+        Pose3 P; decompose_sim3(Scw, P);
+        const float fx = pKF->fx, fy = pKF->fy, cx = pKF->cx, cy = pKF->cy;
+        std::set<MapPointT*> spAlreadyFound(vpMatched.begin(), vpMatched.end());
+        spAlreadyFound.erase(static_cast<MapPointT*>(NULL));
+        const std::vector<float> sf = pKF->GetScaleFactors();
+        KfQueries Q;
+        for (size_t i = 0; i < vpPoints.size(); i++) {
+            MapPointT* pMP = vpPoints[i];
+            if (pMP->isBad() || spAlreadyFound.count(pMP)) continue;
+            float X[3], c3[3]; read3(pMP->GetWorldPos(), X); mul_add3(P.R, X, P.t, c3);
+            if (c3[2] < 0.0) continue;
+            const float invz = 1 / c3[2], x = c3[0] * invz, y = c3[1] * invz;
+            const float u = fx * x + cx, v = fy * y + cy;
+            int lvl;
+            if (!gate_and_level(pKF, pMP, X, P.Ow, u, v, sf, true, 0.f, false, lvl)) continue;
+            Q.push(u, v, th * sf[(size_t)lvl], lvl, pMP->GetDescriptor(), (int)i);
+        }
+        std::vector<int32_t> taken(vpMatched.size()), match;
+        for (size_t k = 0; k < vpMatched.size(); k++) taken[k] = vpMatched[k] ? -2 : -1;
+        const int nmatches = keyframe_window_search(pKF, 1, TH_LOW, Q, taken, match);
+        for (size_t q = 0; q < match.size(); q++) if (match[q] >= 0) vpMatched[(size_t)match[q]] = vpPoints[(size_t)Q.who[q]];
+        return nmatches;
+    }
+
+    // SearchBySim3(KeyFrame* pKF1, KeyFrame* pKF2, vector<MapPoint*>& vpMatches12, s12, R12, t12, th)
+    // (src/ORBmatcher.cc:1267-1505; src/LoopClosing.cc:458): two best-only projection searches (TH_HIGH, no claims) and
+    // the mutual-agreement check
+    template <class KeyFrameT, class MapPointT>
+    int SearchBySim3(KeyFrameT* pKF1, KeyFrameT* pKF2, std::vector<MapPointT*>& vpMatches12, const float& s12, const cv::Mat& R12, const cv::Mat& t12,
+                     const float th)
+    {
+        ensure();
+        const float fx = pKF1->fx, fy = pKF1->fy, cx = pKF1->cx, cy = pKF1->cy;
+        float R1w[3][3], t1w[3], R2w[3][3], t2w[3], r12[3][3], T12[3], sR12[3][3], sR21[3][3], t21[3];
+        read3x3(pKF1->GetRotation(), R1w); read3(pKF1->GetTranslation(), t1w);
+        read3x3(pKF2->GetRotation(), R2w); read3(pKF2->GetTranslation(), t2w);
+        read3x3(R12, r12); read3(t12, T12);
+        for (int r = 0; r < 3; r++) for (int c = 0; c < 3; c++) {
+            sR12[r][c] = r12[r][c] * s12;                                                        // s12*R12
+            sR21[r][c] = r12[c][r] * (float)(1.0 / s12);                                         // (1.0/s12)*R12.t(): transpose, then float scale
+        }
+        {   // t21 = -sR21*t12: the negated matrix times t12 through the small-matrix float path
+            const float zero[3] = {0.f, 0.f, 0.f}; float neg[3][3];
+            for (int r = 0; r < 3; r++) for (int c = 0; c < 3; c++) neg[r][c] = -sR21[r][c];
+            mul_add3(neg, T12, zero, t21);
+        }
+        const std::vector<float> sf1 = pKF1->GetScaleFactors(), sf2 = pKF2->GetScaleFactors();
+        const std::vector<MapPointT*> vpMapPoints1 = pKF1->GetMapPointMatches(), vpMapPoints2 = pKF2->GetMapPointMatches();
+        const int N1 = (int)vpMapPoints1.size(), N2 = (int)vpMapPoints2.size();
+        std::vector<bool> vbAlreadyMatched1((size_t)N1, false), vbAlreadyMatched2((size_t)N2, false);
+        for (int i = 0; i < N1; i++) {
+            MapPointT* pMP = vpMatches12[(size_t)i];
+            if (pMP) {
+                vbAlreadyMatched1[(size_t)i] = true;
+                const int idx2 = pMP->GetIndexInKeyFrame(pKF2);
+                if (idx2 >= 0 && idx2 < N2) vbAlreadyMatched2[(size_t)idx2] = true;
+            }
+        }
+        const float origin[3] = {0.f, 0.f, 0.f};
+        KfQueries Q12, Q21;
+        for (int i1 = 0; i1 < N1; i1++) {                                      // KF1's points into KF2 (:1316-1395)
+            MapPointT* pMP = vpMapPoints1[(size_t)i1];
+            if (!pMP || vbAlreadyMatched1[(size_t)i1]) continue;
+            if (pMP->isBad()) continue;
+            float X[3], c1[3], c2[3]; read3(pMP->GetWorldPos(), X); mul_add3(R1w, X, t1w, c1); mul_add3(sR21, c1, t21, c2);
+            if (c2[2] < 0.0) continue;
+            const float invz = (float)(1.0 / c2[2]), x = c2[0] * invz, y = c2[1] * invz;
+            const float u = fx * x + cx, v = fy * y + cy;
+            int lvl;
+            if (!gate_and_level(pKF2, pMP, c2, origin, u, v, sf2, false, norm3(c2), true, lvl)) continue;
+            Q12.push(u, v, th * sf2[(size_t)lvl], lvl, pMP->GetDescriptor(), i1);
+        }
+        for (int i2 = 0; i2 < N2; i2++) {                                      // KF2's points into KF1 (:1398-1476)
+            MapPointT* pMP = vpMapPoints2[(size_t)i2];
+            if (!pMP || vbAlreadyMatched2[(size_t)i2]) continue;
+            if (pMP->isBad()) continue;
+            float X[3], c2[3], c1[3]; read3(pMP->GetWorldPos(), X); mul_add3(R2w, X, t2w, c2); mul_add3(sR12, c2, T12, c1);
+            if (c1[2] < 0.0) continue;
+            const float invz = (float)(1.0 / c1[2]), x = c1[0] * invz, y = c1[1] * invz;
+            const float u = fx * x + cx, v = fy * y + cy;
+            int lvl;
+            if (!gate_and_level(pKF1, pMP, c1, origin, u, v, sf1, false, norm3(c1), true, lvl)) continue;
+            Q21.push(u, v, th * sf1[(size_t)lvl], lvl, pMP->GetDescriptor(), i2);
+        }
+        std::vector<int32_t> taken, m12, m21;
+        keyframe_window_search(pKF2, 4, TH_HIGH, Q12, taken, m12);
+        taken.clear();
+        keyframe_window_search(pKF1, 4, TH_HIGH, Q21, taken, m21);
+        std::vector<int> vnMatch1((size_t)N1, -1), vnMatch2((size_t)N2, -1);
+        for (size_t q = 0; q < m12.size(); q++) if (m12[q] >= 0) vnMatch1[(size_t)Q12.who[q]] = m12[q];
+        for (size_t q = 0; q < m21.size(); q++) if (m21[q] >= 0) vnMatch2[(size_t)Q21.who[q]] = m21[q];
+        int nFound = 0;
+        for (int i1 = 0; i1 < N1; i1++) {                                      // agreement (:1479-1502)
+            const int idx2 = vnMatch1[(size_t)i1];
+            if (idx2 >= 0 && vnMatch2[(size_t)idx2] == i1) { vpMatches12[(size_t)i1] = vpMapPoints2[(size_t)idx2]; nFound++; }
+        }
+        return nFound;
+    }
+
     // haloc::Utils::ratioMatching (include/utils.h:81-111): brute-force k=2 + ratio test; match[i] = train row or -1
     int RatioMatching(const cv::Mat& descriptors1, const cv::Mat& descriptors2, double ratio, std::vector<int>& match)
     {
