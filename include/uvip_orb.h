@@ -204,6 +204,15 @@ int   uvip_search_window(uvip_matcher* m, const uvip_search_params* sp,
                          const float* kx, const float* ky, const int32_t* octave, const uint8_t* kdesc, int nk,
                          const int32_t* cell_start, const int32_t* cell_items,
                          int32_t* taken, int32_t* match, int* nmatches);
+/* The matching core of SearchForTriangulation (src/ORBmatcher.cc:893-952 with CheckDistEpipolarLine :136-153): per query
+ * (a keypoint of keyframe 1 without a map point) the candidates of the same vocabulary node (CSR lists, caller-filtered to
+ * keypoints of keyframe 2 without a map point) with distance <= th_dist are ordered by (distance, index); among those within
+ * round(2 * best distance) the first whose squared distance to the epipolar line is below kthr[idx] = 3.84 * sigma2(octave)
+ * is matched and claimed (taken[] as in uvip_search_window).  qline[q] = (a, b, c, a*a + b*b) of x1' F12 in float, as :139-146
+ * computes them; kx, ky = keypoint coordinates of keyframe 2.  Queries in array order = the reference's node-major order. */
+int   uvip_search_lists_epipolar(uvip_matcher* m, int th_dist, const uint8_t* qdesc, const float* qline, int nq,
+                                 const int32_t* cand_start, const int32_t* cand_idx, const uint8_t* kdesc, const float* kx, const float* ky,
+                                 const double* kthr, int nk, int32_t* taken, int32_t* match, int* nmatches);
 /* The same search for a batch of device-resident frames (BASELINE config 3 as a throughput workload; frames shard with no
  * exchange because claims never cross frames).  Frame f owns queries [f*q_stride, f*q_stride + d_nq[f]) and keypoints
  * [f*k_stride, f*k_stride + d_nk[f]) of every array; the frame grids (src/FrameKTL.cc:250-264) are built on the device by the

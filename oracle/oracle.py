@@ -295,6 +295,17 @@ def search_lists(mode, th_dist, ratio, qdesc, cand_start, cand_idx, kdesc, taken
     return n, match, tk
 
 
+def search_lists_epipolar(th_dist, qdesc, qline, cand_start, cand_idx, kdesc, kx, ky, kthr, taken=None):
+    qdesc = np.ascontiguousarray(qdesc, np.uint8); kdesc = np.ascontiguousarray(kdesc, np.uint8)
+    ql = np.ascontiguousarray(qline, np.float32); cs = np.ascontiguousarray(cand_start, np.int32); ci = np.ascontiguousarray(cand_idx, np.int32)
+    kx = np.ascontiguousarray(kx, np.float32); ky = np.ascontiguousarray(ky, np.float32); kt = np.ascontiguousarray(kthr, np.float64)
+    nq, nk = len(qdesc), len(kdesc)
+    tk = np.full(nk, -1, np.int32) if taken is None else np.ascontiguousarray(taken, np.int32).copy()
+    match = np.zeros(nq, np.int32)
+    n = lib().uo_search_lists_epipolar(int(th_dist), _p(qdesc), _p(ql), nq, _p(cs), _p(ci), _p(kdesc), _p(kx), _p(ky), _p(kt), nk, _p(tk), _p(match))
+    return n, match, tk
+
+
 def clahe(img, clip_limit=4.0, tiles=(12, 12)):
     img = np.ascontiguousarray(img, np.uint8)
     h, w = img.shape

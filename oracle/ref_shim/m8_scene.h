@@ -60,13 +60,15 @@ enum { A_PARAMS = 0,      // float: th, s12, nnratio
        P_GEO,             // float[np*8]
        P_DESC,            // uint8[np*32]
        K1_MATCHED,        // int32[nk1]: vpMatched for SearchByProjection(KF,Scw): index into the point list or -1
+       A_F12,             // float[9] fundamental matrix for SearchForTriangulation
+       K1_NODE, K2_NODE,  // int32[nk]: vocabulary node of every keypoint (FeatureVector), -1 = none
        A_COUNT };
 
 struct Scene {
     USLAM::KeyFrame K[2];
     std::vector<USLAM::MapPoint> kmp[2], pts;
     std::vector<USLAM::MapPoint*> vp;
-    cv::Mat Scw, R12, t12; float th, s12, nnratio;
+    cv::Mat Scw, R12, t12, F12; float th, s12, nnratio;
     int nk[2], np;
 
     void fill_point(USLAM::MapPoint& m, const float* geo, const uint8_t* desc, bool bad)
@@ -80,6 +82,7 @@ struct Scene {
         const int nl = B.count<float>(A_SF);
         const float* intr = B.get<float>(A_INTR); const int32_t* bd = B.get<int32_t>(A_BOUNDS);
         Scw = mat_f32(B.get<float>(A_SCW), 4, 4); R12 = mat_f32(B.get<float>(A_R12), 3, 3); t12 = mat_f32(B.get<float>(A_T12), 3, 1);
+        F12 = mat_f32(B.get<float>(A_F12), 3, 3);
         for (int k = 0; k < 2; k++) {
             const int o = k ? K2_XYOA : K1_XYOA;
             USLAM::KeyFrame& KF = K[k];
@@ -92,6 +95,10 @@ struct Scene {
             KF.Rcw = mat_f32(pose, 3, 3); KF.tcw = mat_f32(pose + 9, 3, 1); KF.Ow = mat_f32(pose + 12, 3, 1);
             KF.fx = intr[0]; KF.fy = intr[1]; KF.cx = intr[2]; KF.cy = intr[3];
             KF.scaleFactors.assign(B.get<float>(A_SF), B.get<float>(A_SF) + nl);
+            KF.levelSigma2.resize((size_t)nl);
+            for (int l = 0; l < nl; l++) KF.levelSigma2[(size_t)l] = KF.scaleFactors[(size_t)l] * KF.scaleFactors[(size_t)l];     // src/FrameKTL.cc: mvLevelSigma2
+            const int32_t* node = B.get<int32_t>(k ? K2_NODE : K1_NODE);
+            for (int i = 0; i < nk[k]; i++) if (node[i] >= 0) KF.featVec[(DBoW2::NodeId)node[i]].push_back((unsigned)i);
             KF.mnId = (unsigned long)k;
             KF.set_bounds(bd[0], bd[1], bd[2], bd[3]);
             const int32_t* mp = B.get<int32_t>(o + 3); const float* geo = B.get<float>(o + 4);
@@ -121,6 +128,7 @@ struct Scene {
 };
 
 // which: 0 Fuse(KF, MPs, th)   1 Fuse(KF, Scw, MPs, th)   2 SearchByProjection(KF, Scw, MPs, vpMatched, th)   3 SearchBySim3
+//        4 SearchForTriangulation(KF1, KF2, F12, keys1, keys2, pairs)
 template <class Matcher>
 int run(int which, const Bundle& in, Bundle& out)
 {
@@ -148,6 +156,16 @@ int run(int which, const Bundle& in, Bundle& out)
         for (int k = 0; k < S.nk[0]; k++) if (km[k] >= 0 && S.vp[(size_t)km[k]]) matched[(size_t)k] = S.vp[(size_t)km[k]];
         ret[0] = matcher.SearchByProjection(pKF, S.Scw, vp, matched, (int)S.th);
         for (int k = 0; k < S.nk[0]; k++) slot_owner.push_back(S.id_of(matched[(size_t)k]));
+    } else if (which == 4) {
+        std::vector<cv::KeyPoint> mk1, mk2; std::vector<std::pair<size_t, size_t> > pairs;
+        ret[0] = matcher.SearchForTriangulation(&S.K[0], &S.K[1], S.F12, mk1, mk2, pairs);
+        slot_owner.assign((size_t)S.nk[0], -1);
+        for (size_t i = 0; i < pairs.size(); i++) {
+            slot_owner[pairs[i].first] = (int32_t)pairs[i].second;
+            replaced.push_back((int32_t)pairs[i].first); replaced.push_back((int32_t)pairs[i].second);
+            // the returned keypoints must be the ones the pairs name
+            obs_slot.push_back(mk1[i].pt.x == S.K[0].keysUn[pairs[i].first].pt.x && mk2[i].pt.y == S.K[1].keysUn[pairs[i].second].pt.y ? 1 : 0);
+        }
     } else {
         const int32_t* mp1 = in.get<int32_t>(K1_MP);
         std::vector<USLAM::MapPoint*> m12((size_t)S.nk[0], (USLAM::MapPoint*)0);

@@ -909,6 +909,46 @@ int uo_search_lists(int mode, int th_dist, float ratio, const uint8_t* qdesc, in
     return nmatches;
 }
 
+/* SearchForTriangulation's matching core, ORBmatcher.cc:893-952 + CheckDistEpipolarLine :136-153.  qline = (a, b, c, den) per
+ * query in float; kthr = 3.84 * sigma2(octave) per keypoint.  Sequential, claims through taken[]. */
+typedef struct { int dist; int idx; } uo_di;
+static int uo_di_cmp(const void* a, const void* b)
+{
+    const uo_di* x = (const uo_di*)a; const uo_di* y = (const uo_di*)b;
+    if (x->dist != y->dist) return x->dist < y->dist ? -1 : 1;
+    return x->idx < y->idx ? -1 : (x->idx > y->idx);
+}
+int uo_search_lists_epipolar(int th_dist, const uint8_t* qdesc, const float* qline, int nq, const int32_t* cand_start, const int32_t* cand_idx,
+                             const uint8_t* kdesc, const float* kx, const float* ky, const double* kthr, int nk, int32_t* taken, int32_t* match_of_query)
+{
+    int nmatches = 0;
+    uo_di* v = (uo_di*)malloc(sizeof(uo_di) * (size_t)(nk + 1));
+    for (int q = 0; q < nq; q++) {
+        match_of_query[q] = -1;
+        int n = 0;
+        for (int c = cand_start[q]; c < cand_start[q + 1]; c++) {
+            const int idx = cand_idx[c];
+            if (taken[idx] != -1) continue;
+            const int dist = uo_descriptor_distance(qdesc + (size_t)q * 32, kdesc + (size_t)idx * 32);
+            if (dist > th_dist) continue;
+            v[n].dist = dist; v[n].idx = idx; n++;
+        }
+        if (n == 0) continue;
+        qsort(v, (size_t)n, sizeof(uo_di), uo_di_cmp);
+        const int distTh = (int)round(2 * v[0].dist);
+        const float a = qline[4 * q], b = qline[4 * q + 1], cc = qline[4 * q + 2], den = qline[4 * q + 3];
+        for (int i = 0; i < n; i++) {
+            if (v[i].dist > distTh) break;
+            if (den == 0) continue;
+            const float num = a * kx[v[i].idx] + b * ky[v[i].idx] + cc;
+            const float dsqr = num * num / den;
+            if ((double)dsqr < kthr[v[i].idx]) { taken[v[i].idx] = q; match_of_query[q] = v[i].idx; nmatches++; break; }
+        }
+    }
+    free(v);
+    return nmatches;
+}
+
 /* ================================================================ CLAHE (next row N3)
  * cv::createCLAHE(clip, Size(tx,ty))->apply(im, im) as called at Tracking.cc:425-431 (clip 4, 12x12 tiles), restated from
  * OpenCV imgproc/clahe.cpp (8-bit path): pad to a tile multiple with REFLECT_101, per-tile clipped + redistributed

@@ -591,23 +591,34 @@ def m8_bundle(oracle, synth, which):
     R12 = (R1.astype(np.float64) @ R2.astype(np.float64).T).astype(np.float32)
     t12 = (t1.astype(np.float64) - R12.astype(np.float64) @ t2.astype(np.float64)).astype(np.float32)
     Scw = np.eye(4, dtype=np.float32); Scw[:3, :3] = f32(1.7) * R1; Scw[:3, 3] = f32(1.7) * t1
-    th = [3.0, 4.0, 10.0, 7.5][which]
+    th = [3.0, 4.0, 10.0, 7.5, 0.0][which]
     pose = lambda R, t, O: np.concatenate([R.ravel(), t, O]).astype(np.float32)
+    # fundamental matrix of the pair, F12 = K^-T [t12]x R12 K^-1 (src/LocalMapping.cc ComputeF12), and vocabulary nodes
+    Kinv = np.linalg.inv(np.array([[fx, 0, cx], [0, fy, cy], [0, 0, 1]], np.float64))
+    tx = np.array([[0, -t12[2], t12[1]], [t12[2], 0, -t12[0]], [-t12[1], t12[0], 0]], np.float64)
+    F12 = (Kinv.T @ tx @ R12.astype(np.float64) @ Kinv).astype(np.float32)
+    node1 = ((kps['x'] / 64).astype(np.int32) + 16 * (kps['y'] / 64).astype(np.int32)).astype(np.int32)
+    node2 = np.where(idx % 15 == 4, -1, node1 + np.where(idx % 37 == 0, 2000, 0)).astype(np.int32)
     return [np.array([th, 1.0, 0.6], np.float32), sf, np.array([fx, fy, cx, cy], np.float32), np.array([0, W, 0, H], np.int32), Scw, R12, t12,
-            k1_xyoa, desc, pose(R1, t1, O1), k1_mp, k1_geo, k2_xyoa, k2_desc, pose(R2, t2, O2), k2_mp, k2_geo, p_flags, p_geo, p_desc, k1_matched]
+            k1_xyoa, desc, pose(R1, t1, O1), k1_mp, k1_geo, k2_xyoa, k2_desc, pose(R2, t2, O2), k2_mp, k2_geo, p_flags, p_geo, p_desc, k1_matched,
+            F12, node1, node2]
 
 
-M8_NAMES = ['Fuse(KF, MPs, th)', 'Fuse(KF, Scw, MPs, th)', 'SearchByProjection(KF, Scw, MPs, vpMatched, th)', 'SearchBySim3']
+M8_NAMES = ['Fuse(KF, MPs, th)', 'Fuse(KF, Scw, MPs, th)', 'SearchByProjection(KF, Scw, MPs, vpMatched, th)', 'SearchBySim3', 'SearchForTriangulation']
+M8_MIN = [150, 150, 150, 150, 25]
 
 
 @needs_mref
-@pytest.mark.parametrize('which', [0, 1, 2, 3])
+@pytest.mark.parametrize('which', [0, 1, 2, 3, 4])
 def test_m8_reference_runs_every_branch(oracle, synth, which, tmp_path):
     """the scenes must exercise the reference's code paths (otherwise the GPU comparison below proves little)"""
     R.write_bundle(str(tmp_path / 's.bin'), m8_bundle(oracle, synth, which))
     r, (ret, slot_owner, replaced, obs_slot) = R.m8_run(str(tmp_path / 's.bin'), str(tmp_path / 'o.bin'), which)
-    assert ret[0] == r and r > 150, (M8_NAMES[which], r)
-    if which in (0, 1):
+    assert ret[0] == r and r > M8_MIN[which], (M8_NAMES[which], r)
+    if which == 4:
+        assert (slot_owner >= 0).sum() == r and len(replaced) == 2 * r and obs_slot.all()
+        assert (np.diff(replaced[0::2]) > 0).all()                                # pairs come out in ascending order of the first index
+    elif which in (0, 1):
         assert (replaced >= 0).sum() > 30 and (obs_slot >= 0).sum() > 30          # both bookkeeping branches
         assert (slot_owner >= 200000).sum() == (obs_slot >= 0).sum()              # added points sit in the keyframe's slots
         if which == 1:
@@ -630,7 +641,7 @@ def test_shim_m8_driver_refuses_without_device(pkg, oracle, synth, tmp_path):
 
 @needs_mref
 @pytest.mark.gpu
-@pytest.mark.parametrize('which', [0, 1, 2, 3])
+@pytest.mark.parametrize('which', [0, 1, 2, 3, 4])
 def test_shim_m8_equals_reference(gpu, oracle, synth, which, tmp_path):
     """row M8 end to end: the drop-in shim (host geometry + uvip_search_window on the GPU) against the reference's compiled
     ORBmatcher, same scene code, same stand-in SLAM types, same call signatures; result bundles must be identical."""
@@ -641,6 +652,41 @@ def test_shim_m8_equals_reference(gpu, oracle, synth, which, tmp_path):
     p = subprocess.run([R.M8_EXE, str(tmp_path / 's.bin'), str(tmp_path / 'shim.bin'), str(which)], capture_output=True, text=True)
     assert p.returncode == 0, p.stderr
     shim = R.read_bundle(str(tmp_path / 'shim.bin'))
-    assert int(p.stdout.strip()) == r and r > 150, (M8_NAMES[which], p.stdout, r)
+    assert int(p.stdout.strip()) == r and r > M8_MIN[which], (M8_NAMES[which], p.stdout, r)
     for a, b, name in zip(shim, ref, ('return', 'slot owner', 'replaced', 'observation')):
         assert np.array_equal(a, b), (M8_NAMES[which], name, int((a != b).sum()))
+
+
+@needs_mref
+def test_search_for_triangulation_core_equals_reference(oracle, synth, tmp_path):
+    """the oracle's restatement of SearchForTriangulation's matching core (src/ORBmatcher.cc:893-952, :136-153) against the
+    reference's compiled function on the M8 scene: same pairs, histogram applied afterwards"""
+    B = m8_bundle(oracle, synth, 4)
+    R.write_bundle(str(tmp_path / 's.bin'), B)
+    r, (ret, slot_owner, replaced, obs_slot) = R.m8_run(str(tmp_path / 's.bin'), str(tmp_path / 'o.bin'), 4)
+    k1_xyoa, d1, k1_mp, k2_xyoa, d2, k2_mp, F12, node1, node2, sf = B[7], B[8], B[10], B[12], B[13], B[15], B[21], B[22], B[23], B[1]
+    f32 = np.float32
+    q, ql, cs, ci = [], [], [0], []
+    by2 = {}
+    for k in range(len(node2)):
+        if node2[k] >= 0:
+            by2.setdefault(int(node2[k]), []).append(k)
+    for nd in sorted(set(node1.tolist())):
+        if nd not in by2:
+            continue
+        for k in np.nonzero(node1 == nd)[0]:
+            if k1_mp[k, 0]:
+                continue
+            x, y = k1_xyoa[k, 0], k1_xyoa[k, 1]
+            a = f32(f32(f32(x * F12[0, 0]) + f32(y * F12[1, 0])) + F12[2, 0]); b = f32(f32(f32(x * F12[0, 1]) + f32(y * F12[1, 1])) + F12[2, 1])
+            c = f32(f32(f32(x * F12[0, 2]) + f32(y * F12[1, 2])) + F12[2, 2])
+            q.append(k); ql.append([a, b, c, f32(f32(a * a) + f32(b * b))])
+            ci.extend(j for j in by2[nd] if not k2_mp[j, 0]); cs.append(len(ci))
+    q = np.array(q)
+    sig2 = (sf * sf).astype(np.float32)
+    kthr = 3.84 * sig2[k2_xyoa[:, 2].astype(np.int32)].astype(np.float64)
+    on, om, _ = oracle.search_lists_epipolar(50, d1[q], np.array(ql, np.float32), np.array(cs, np.int32), np.array(ci or [0], np.int32), d2,
+                                             k2_xyoa[:, 0], k2_xyoa[:, 1], kthr)
+    om = oracle.rot_hist_filter(om, k1_xyoa[q, 3], k2_xyoa[:, 3])
+    expect = np.full(len(node1), -1, np.int32); expect[q[om >= 0]] = om[om >= 0]
+    assert r == int((om >= 0).sum()) and np.array_equal(slot_owner, expect)

@@ -365,6 +365,8 @@ struct SearchCtx {
     const float *kx, *ky; const int32_t* octave; const uint8_t* kdesc;
     const int32_t *cell_start, *cell_items;
     const int32_t *cand_start, *cand_idx;          // explicit candidate lists (node-restricted searches); NULL = grid window
+    const float* qline;                            // mode 5: epipolar line (a, b, c, a*a+b*b) per query
+    const double* kthr;                            // mode 5: 3.84 * sigma2(octave) per keypoint
 };
 
 __device__ __forceinline__ int hamming256(const uint4& u, const uint4& v, const uint8_t* __restrict__ row)
@@ -433,12 +435,42 @@ __device__ int search_one_list(const SearchCtx& c, int q, const int* __restrict_
         if (dist < best1) { best2 = best1; best1 = dist; bestIdx = id; }
         else if (dist < best2) best2 = dist;
     }
+    if (sp.mode == 5) return -1;                                       // handled by search_one_epipolar
     if (bestIdx < 0) return -1;
     bool ok;
     if (sp.mode == 1) ok = best1 <= sp.th_dist;
     else if (sp.mode == 2) ok = best1 <= sp.th_dist && (float)best1 < __fmul_rn(sp.ratio, (float)best2);
     else ok = best1 < sp.th_dist && (float)best1 < __fmul_rn(sp.ratio, (float)best2);
     return ok ? bestIdx : -1;
+}
+
+// SearchForTriangulation's inner loops (src/ORBmatcher.cc:893-952 + CheckDistEpipolarLine :136-153): candidates of the same
+// vocabulary node with dist <= TH_LOW, sorted by (dist, index); among those with dist <= round(2 * best dist) the first one whose
+// distance to the epipolar line passes the chi-square test is taken and claimed.  One pass: the best (dist, index) key over all
+// candidates gives the bound, the best key over the epipolar-consistent ones the match.
+__device__ int search_one_epipolar(const SearchCtx& c, int q, const int* __restrict__ owner)
+{
+    const uvip_search_params& sp = c.sp;
+    const uint4 u = __ldg(reinterpret_cast<const uint4*>(c.qdesc + (size_t)q * 32));
+    const uint4 v = __ldg(reinterpret_cast<const uint4*>(c.qdesc + (size_t)q * 32) + 1);
+    const float4 L = __ldg(reinterpret_cast<const float4*>(c.qline) + q);       // a, b, c, den
+    unsigned bestAll = 0xFFFFFFFFu, bestEpi = 0xFFFFFFFFu;
+    const int e = c.cand_start[q + 1];
+    for (int j = c.cand_start[q]; j < e; j++) {
+        const int id = c.cand_idx[j];
+        if (owner[id] < q) continue;                                            // vbMatched2[idx2]
+        const int dist = hamming256(u, v, c.kdesc + (size_t)id * 32);
+        if (dist > sp.th_dist) continue;
+        const unsigned key = ((unsigned)dist << 20) | (unsigned)id;
+        bestAll = min(bestAll, key);
+        if (L.w == 0.f) continue;                                               // den == 0 -> false
+        const float num = __fadd_rn(__fadd_rn(__fmul_rn(L.x, c.kx[id]), __fmul_rn(L.y, c.ky[id])), L.z);
+        const float dsqr = __fdiv_rn(__fmul_rn(num, num), L.w);
+        if ((double)dsqr < c.kthr[id]) bestEpi = min(bestEpi, key);
+    }
+    if (bestEpi == 0xFFFFFFFFu) return -1;
+    const int distTh = (int)round(2.0 * (double)(bestAll >> 20));               // int DistTh = round(2*BestDist)
+    return (int)(bestEpi >> 20) <= distTh ? (int)(bestEpi & 0xFFFFFu) : -1;
 }
 
 // The reference loop is sequential: a query skips keypoints claimed by EARLIER queries.  Here every query
@@ -471,7 +503,7 @@ k_search_window(SearchCtx c, int nq, int nk, int32_t* __restrict__ taken, int32_
         if (threadIdx.x == 0) s_changed = 0;
         __syncthreads();
         for (int q = threadIdx.x; q < nq; q += blockDim.x) {
-            const int r = c.cand_start ? search_one_list(c, q, prev) : search_one(c, q, prev);
+            const int r = c.cand_start ? (c.sp.mode == 5 ? search_one_epipolar(c, q, prev) : search_one_list(c, q, prev)) : search_one(c, q, prev);
             match[q] = r;
             if (r >= 0 && claims) atomicMin(&cur[r], q);
         }
@@ -970,6 +1002,51 @@ int uvip_search_lists(uvip_matcher* m, int mode, int th_dist, float ratio, const
     c.sp.mode = mode; c.sp.th_dist = th_dist; c.sp.ratio = ratio;
     c.qdesc = base + o_qd; c.kdesc = base + o_kd;
     c.cand_start = (const int32_t*)(base + o_cs); c.cand_idx = (const int32_t*)(base + o_ci);
+    k_search_window<<<1, 1024, 0, st>>>(c, nq, nk, (int32_t*)(base + o_taken), (int32_t*)(base + o_match),
+                                         (int*)(base + o_oa), (int*)(base + o_ob), (int*)(base + o_cnt), nullptr, nullptr, 0, 0);
+    m->launches++;
+    UVIP_CUDA(cudaGetLastError());
+    int counts[2] = {0, 0};
+    UVIP_CUDA(cudaMemcpyAsync(match, base + o_match, (size_t)nq * 4, cudaMemcpyDeviceToHost, st));
+    if (nk) UVIP_CUDA(cudaMemcpyAsync(taken, base + o_taken, (size_t)nk * 4, cudaMemcpyDeviceToHost, st));
+    UVIP_CUDA(cudaMemcpyAsync(counts, base + o_cnt, 8, cudaMemcpyDeviceToHost, st));
+    UVIP_CUDA(cudaStreamSynchronize(st));
+    if (nmatches) *nmatches = counts[0];
+    return UVIP_OK;
+}
+
+// SearchForTriangulation's matching core (src/ORBmatcher.cc:893-952): see search_one_epipolar
+int uvip_search_lists_epipolar(uvip_matcher* m, int th_dist, const uint8_t* qdesc, const float* qline, int nq,
+                               const int32_t* cand_start, const int32_t* cand_idx, const uint8_t* kdesc, const float* kx, const float* ky,
+                               const double* kthr, int nk, int32_t* taken, int32_t* match, int* nmatches)
+{
+    UVIP_CHECK_ARG(m && nq >= 0 && nk >= 0 && nk < (1 << 20));
+    if (nmatches) *nmatches = 0;
+    if (nq == 0) return UVIP_OK;
+    UVIP_CHECK_ARG(qdesc && qline && cand_start && match && (nk == 0 || (kdesc && kx && ky && kthr && taken)));
+    const int ncand = cand_start[nq];
+    UVIP_CHECK_ARG(ncand >= 0 && (ncand == 0 || cand_idx));
+    for (int i = 0; i < ncand; i++) UVIP_CHECK_ARG(cand_idx[i] >= 0 && cand_idx[i] < nk);
+    std::lock_guard<std::mutex> lk(m->mu);
+    DeviceGuard g(m->device);
+    size_t off = 0;
+    auto sect = [&](size_t bytes) { size_t o = off; off = align_up(off + bytes, 32); return o; };
+    const size_t nkk = nk > 0 ? nk : 1;
+    const size_t o_qd = sect((size_t)nq * 32), o_ql = sect((size_t)nq * 16), o_kd = sect(nkk * 32), o_kx = sect(nkk * 4), o_ky = sect(nkk * 4), o_kt = sect(nkk * 8);
+    const size_t o_cs = sect((size_t)(nq + 1) * 4), o_ci = sect((size_t)(ncand > 0 ? ncand : 1) * 4);
+    const size_t o_taken = sect(nkk * 4), o_match = sect((size_t)nq * 4), o_oa = sect(nkk * 4), o_ob = sect(nkk * 4), o_cnt = sect(16);
+    int rc;
+    if ((rc = m->misc.reserve(off))) return rc;
+    uint8_t* base = m->misc.as<uint8_t>();
+    cudaStream_t st = m->stream;
+#define UP(o, src, bytes) if ((bytes) > 0) UVIP_CUDA(cudaMemcpyAsync(base + (o), (src), (bytes), cudaMemcpyHostToDevice, st))
+    UP(o_qd, qdesc, (size_t)nq * 32); UP(o_ql, qline, (size_t)nq * 16); UP(o_kd, kdesc, (size_t)nk * 32); UP(o_kx, kx, (size_t)nk * 4); UP(o_ky, ky, (size_t)nk * 4);
+    UP(o_kt, kthr, (size_t)nk * 8); UP(o_cs, cand_start, (size_t)(nq + 1) * 4); UP(o_ci, cand_idx, (size_t)ncand * 4); UP(o_taken, taken, (size_t)nk * 4);
+#undef UP
+    SearchCtx c; memset(&c, 0, sizeof(c));
+    c.sp.mode = 5; c.sp.th_dist = th_dist;
+    c.qdesc = base + o_qd; c.qline = (const float*)(base + o_ql); c.kdesc = base + o_kd; c.kx = (const float*)(base + o_kx); c.ky = (const float*)(base + o_ky);
+    c.kthr = (const double*)(base + o_kt); c.cand_start = (const int32_t*)(base + o_cs); c.cand_idx = (const int32_t*)(base + o_ci);
     k_search_window<<<1, 1024, 0, st>>>(c, nq, nk, (int32_t*)(base + o_taken), (int32_t*)(base + o_match),
                                          (int*)(base + o_oa), (int*)(base + o_ob), (int*)(base + o_cnt), nullptr, nullptr, 0, 0);
     m->launches++;

@@ -540,6 +540,72 @@ public:
         return nFound;
     }
 
+    // SearchForTriangulation(KeyFrame* pKF1, KeyFrame* pKF2, cv::Mat F12, keys1, keys2, pairs)  (src/ORBmatcher.cc:852-1014;
+    // src/LocalMapping.cc:1080): keypoints without a map point, same vocabulary node, dist <= TH_LOW, sorted by (dist, index),
+    // first epipolar-consistent candidate within round(2 * best) wins and is claimed; rotation histogram; outputs in ascending
+    // order of the first keyframe's index.  The epipolar lines x1' F12 are formed here in float as :139-141 does; the per-pair
+    // chi-square test runs inside uvip_search_lists_epipolar.  KeyFrameT additionally needs GetFeatureVector(), GetSigma2(l).
+    template <class KeyFrameT>
+    int SearchForTriangulation(KeyFrameT* pKF1, KeyFrameT* pKF2, cv::Mat F12, std::vector<cv::KeyPoint>& vMatchedKeys1,
+                               std::vector<cv::KeyPoint>& vMatchedKeys2, std::vector<std::pair<size_t, size_t> >& vMatchedPairs)
+    {
+        ensure();
+        const auto vpMapPoints1 = pKF1->GetMapPointMatches(); const auto vpMapPoints2 = pKF2->GetMapPointMatches();
+        const std::vector<cv::KeyPoint> vKeysUn1 = pKF1->GetKeyPointsUn(), vKeysUn2 = pKF2->GetKeyPointsUn();
+        const cv::Mat Descriptors1 = pKF1->GetDescriptors(), Descriptors2 = pKF2->GetDescriptors();
+        const auto vFeatVec1 = pKF1->GetFeatureVector(); const auto vFeatVec2 = pKF2->GetFeatureVector();
+        float F[3][3]; read3x3(F12, F);
+        std::vector<unsigned char> qd; std::vector<float> ql; std::vector<int32_t> cs(1, 0), ci; std::vector<unsigned> qidx;
+        auto f1it = vFeatVec1.begin(); auto f2it = vFeatVec2.begin();
+        while (f1it != vFeatVec1.end() && f2it != vFeatVec2.end()) {
+            if (f1it->first == f2it->first) {
+                for (size_t i1 = 0; i1 < f1it->second.size(); i1++) {
+                    const size_t idx1 = f1it->second[i1];
+                    if (vpMapPoints1[idx1]) continue;                                           // already a map point (:897-899)
+                    const cv::KeyPoint& kp1 = vKeysUn1[idx1];
+                    const float a = kp1.pt.x * F[0][0] + kp1.pt.y * F[1][0] + F[2][0];
+                    const float b = kp1.pt.x * F[0][1] + kp1.pt.y * F[1][1] + F[2][1];
+                    const float c = kp1.pt.x * F[0][2] + kp1.pt.y * F[1][2] + F[2][2];
+                    const float den = a * a + b * b;
+                    qd.insert(qd.end(), Descriptors1.ptr((int)idx1), Descriptors1.ptr((int)idx1) + 32);
+                    ql.push_back(a); ql.push_back(b); ql.push_back(c); ql.push_back(den);
+                    for (size_t i2 = 0; i2 < f2it->second.size(); i2++) { const size_t idx2 = f2it->second[i2]; if (!vpMapPoints2[idx2]) ci.push_back((int32_t)idx2); }
+                    cs.push_back((int32_t)ci.size());
+                    qidx.push_back((unsigned)idx1);
+                }
+                ++f1it; ++f2it;
+            } else if (f1it->first < f2it->first) f1it = vFeatVec1.lower_bound(f2it->first);
+            else f2it = vFeatVec2.lower_bound(f1it->first);
+        }
+        vMatchedKeys1.clear(); vMatchedKeys2.clear(); vMatchedPairs.clear();
+        const int nq = (int)qidx.size(), nk = (int)vKeysUn2.size();
+        if (nq == 0 || nk == 0) return 0;
+        std::vector<unsigned char> kd((size_t)nk * 32); std::vector<float> kx((size_t)nk), ky((size_t)nk), a2((size_t)nk); std::vector<double> kthr((size_t)nk);
+        for (int i = 0; i < nk; i++) {
+            std::memcpy(&kd[(size_t)i * 32], Descriptors2.ptr(i), 32);
+            kx[i] = vKeysUn2[(size_t)i].pt.x; ky[i] = vKeysUn2[(size_t)i].pt.y; a2[i] = vKeysUn2[(size_t)i].angle;
+            kthr[i] = 3.84 * pKF2->GetSigma2(vKeysUn2[(size_t)i].octave);                       // :152
+        }
+        std::vector<int32_t> taken((size_t)nk, -1), match((size_t)nq);
+        if (ci.empty()) ci.push_back(0);
+        int nmatches = 0;
+        check(uvip_search_lists_epipolar(handle_, TH_LOW, qd.data(), ql.data(), nq, cs.data(), ci.data(), kd.data(), kx.data(), ky.data(), kthr.data(), nk,
+                                         taken.data(), match.data(), &nmatches), "uvip_search_lists_epipolar");
+        if (mbCheckOrientation) {
+            std::vector<float> a1((size_t)nq);
+            for (int q = 0; q < nq; q++) a1[q] = vKeysUn1[qidx[q]].angle;
+            check(uvip_rot_hist_filter(handle_, match.data(), nq, a1.data(), a2.data(), &nmatches), "uvip_rot_hist_filter");
+        }
+        std::vector<int> vMatches12(vKeysUn1.size(), -1);
+        for (int q = 0; q < nq; q++) if (match[q] >= 0) vMatches12[qidx[q]] = match[q];
+        for (size_t i = 0; i < vMatches12.size(); i++) {
+            if (vMatches12[i] < 0) continue;
+            vMatchedKeys1.push_back(vKeysUn1[i]); vMatchedKeys2.push_back(vKeysUn2[(size_t)vMatches12[i]]);
+            vMatchedPairs.push_back(std::make_pair(i, (size_t)vMatches12[i]));
+        }
+        return nmatches;
+    }
+
     // haloc::Utils::ratioMatching (include/utils.h:81-111): brute-force k=2 + ratio test; match[i] = train row or -1
     int RatioMatching(const cv::Mat& descriptors1, const cv::Mat& descriptors2, double ratio, std::vector<int>& match)
     {
