@@ -1263,6 +1263,12 @@ struct uvip_extractor {
     bool prof = false;
     std::vector<cudaEvent_t> prof_ev;      // PROF_RING * (UVIP_NUM_STAGES + 1)
     long long prof_groups = 0;
+    // single-frame call (uvip_extract = operator()): the memsets + 13 kernels of one frame are captured once per call shape
+    // into a CUDA graph and replayed (the call is launch-bound: a frame's kernels are tiny), results come back through one
+    // pinned staging block with a single synchronisation
+    struct GraphKey { int w, h, stride, cap, full, n_in, gr, gc, mpd, need; const void *in, *kps, *desc, *n, *grid, *incoming, *pyr; };
+    GraphKey gkey; bool ghave = false; cudaGraphExec_t gexec = nullptr; long long glaunches = 0;
+    uint8_t* h_stage = nullptr; size_t h_stage_bytes = 0;      // pinned: [n, status | keypoints cap x 28 | descriptors cap x 32]
     std::mutex mu;
 };
 constexpr int PROF_RING = 256;
@@ -1641,6 +1647,8 @@ int uvip_extractor_destroy(uvip_extractor* ex)
     for (int i = 0; i < 2; i++) { if (ex->ev_h2d[i]) cudaEventDestroy(ex->ev_h2d[i]); if (ex->ev_comp[i]) cudaEventDestroy(ex->ev_comp[i]); if (ex->ev_d2h[i]) cudaEventDestroy(ex->ev_d2h[i]); }
     for (int i = 0; i < 2; i++) if (ex->ev_done[i]) cudaEventDestroy(ex->ev_done[i]);
     if (ex->h_status) cudaFreeHost(ex->h_status);
+    if (ex->gexec) cudaGraphExecDestroy(ex->gexec);
+    if (ex->h_stage) cudaFreeHost(ex->h_stage);
     if (ex->h2d_stream) cudaStreamDestroy(ex->h2d_stream);
     if (ex->d2h_stream) cudaStreamDestroy(ex->d2h_stream);
     if (ex->stream) cudaStreamDestroy(ex->stream);
@@ -1837,19 +1845,64 @@ int uvip_extract(uvip_extractor* ex, const uint8_t* image, int w, int h, int str
             UVIP_CUDA(cudaMemcpyAsync(ex->incoming.p, kps, (size_t)n_in * sizeof(uvip_keypoint), cudaMemcpyHostToDevice, st));
         }
     }
-    rc = enqueue_group(ex, ex->in_frames.as<uint8_t>(), 1, stride, fbytes, ex->out_kps.as<uvip_keypoint>(), ex->out_n.as<int32_t>(),
-                       cap, ex->out_desc.as<uint8_t>(), full_detect ? 1 : 0, n_in, grid_rows, grid_cols, min_px_dist, num_needed, st);
-    if (rc) return rc;
-    int n = 0;
-    UVIP_CUDA(cudaMemcpyAsync(&n, ex->out_n.p, 4, cudaMemcpyDeviceToHost, st));
-    if ((rc = read_status(ex, st))) return rc;
+    if (ex->prof) {                                            // per-stage event timing wants plain launches
+        rc = enqueue_group(ex, ex->in_frames.as<uint8_t>(), 1, stride, fbytes, ex->out_kps.as<uvip_keypoint>(), ex->out_n.as<int32_t>(),
+                           cap, ex->out_desc.as<uint8_t>(), full_detect ? 1 : 0, n_in, grid_rows, grid_cols, min_px_dist, num_needed, st);
+        if (rc) return rc;
+    } else {
+        uvip_extractor::GraphKey key;
+        memset(&key, 0, sizeof(key));
+        key.w = w; key.h = h; key.stride = stride; key.cap = cap; key.full = full_detect ? 1 : 0; key.n_in = n_in;
+        key.gr = full_detect ? 0 : grid_rows; key.gc = full_detect ? 0 : grid_cols; key.mpd = full_detect ? 0 : min_px_dist; key.need = full_detect ? 0 : num_needed;
+        key.in = ex->in_frames.p; key.kps = ex->out_kps.p; key.desc = ex->out_desc.p; key.n = ex->out_n.p; key.grid = ex->grid.p;
+        key.incoming = ex->incoming.p; key.pyr = ex->pyr.p;
+        if (!ex->ghave || memcmp(&key, &ex->gkey, sizeof(key)) != 0) {
+            if (ex->gexec) { cudaGraphExecDestroy(ex->gexec); ex->gexec = nullptr; }
+            ex->ghave = false;
+            cudaGraph_t graph = nullptr;
+            const long long l0 = ex->launches;
+            UVIP_CUDA(cudaStreamBeginCapture(st, cudaStreamCaptureModeThreadLocal));
+            rc = enqueue_group(ex, ex->in_frames.as<uint8_t>(), 1, stride, fbytes, ex->out_kps.as<uvip_keypoint>(), ex->out_n.as<int32_t>(),
+                               cap, ex->out_desc.as<uint8_t>(), full_detect ? 1 : 0, n_in, grid_rows, grid_cols, min_px_dist, num_needed, st);
+            const cudaError_t ce = cudaStreamEndCapture(st, &graph);
+            ex->glaunches = ex->launches - l0; ex->launches = l0;
+            if (rc) { if (graph) cudaGraphDestroy(graph); return rc; }
+            UVIP_CUDA(ce);
+            const cudaError_t ci = cudaGraphInstantiate(&ex->gexec, graph, 0);
+            cudaGraphDestroy(graph);
+            UVIP_CUDA(ci);
+            ex->gkey = key; ex->ghave = true;
+        }
+        UVIP_CUDA(cudaGraphLaunch(ex->gexec, st));
+        ex->launches += ex->glaunches;
+    }
+    // one pinned staging block, one synchronisation: [n, status | cap keypoints | cap descriptors]
+    const size_t o_kps = 64, o_desc = o_kps + align_up((size_t)cap * sizeof(uvip_keypoint), 64), need_bytes = o_desc + (size_t)cap * 32;
+    if (ex->h_stage_bytes < need_bytes) {
+        if (ex->h_stage) { cudaFreeHost(ex->h_stage); ex->h_stage = nullptr; ex->h_stage_bytes = 0; }
+        UVIP_CUDA(cudaMallocHost((void**)&ex->h_stage, need_bytes));
+        ex->h_stage_bytes = need_bytes;
+    }
+    UVIP_CUDA(cudaMemcpyAsync(ex->h_stage, ex->out_n.p, 4, cudaMemcpyDeviceToHost, st));
+    UVIP_CUDA(cudaMemcpyAsync(ex->h_stage + 4, ex->status.p, 4, cudaMemcpyDeviceToHost, st));
+    UVIP_CUDA(cudaMemcpyAsync(ex->h_stage + o_kps, ex->out_kps.p, (size_t)cap * sizeof(uvip_keypoint), cudaMemcpyDeviceToHost, st));
+    UVIP_CUDA(cudaMemcpyAsync(ex->h_stage + o_desc, ex->out_desc.p, (size_t)cap * 32, cudaMemcpyDeviceToHost, st));
+    UVIP_CUDA(cudaStreamSynchronize(st));
+    int n = 0, flags = 0;
+    memcpy(&n, ex->h_stage, 4); memcpy(&flags, ex->h_stage + 4, 4);
+    if (flags) {
+        set_last_error("device capacity overflow, flags 0x%x (1 FAST candidates, 2 quadtree nodes, 4 winners, 8 output rows)", flags);
+        return UVIP_ERR_CAPACITY;
+    }
     if (n > cap) { set_last_error("%d keypoints do not fit cap %d", n, cap); return UVIP_ERR_CAPACITY; }
     if (n) {
-        UVIP_CUDA(cudaMemcpyAsync(kps, ex->out_kps.p, (size_t)n * sizeof(uvip_keypoint), cudaMemcpyDeviceToHost, st));
-        UVIP_CUDA(cudaMemcpyAsync(desc, ex->out_desc.p, (size_t)n * 32, cudaMemcpyDeviceToHost, st));
+        memcpy(kps, ex->h_stage + o_kps, (size_t)n * sizeof(uvip_keypoint));
+        memcpy(desc, ex->h_stage + o_desc, (size_t)n * 32);
     }
-    if (!full_detect) UVIP_CUDA(cudaMemcpyAsync(grid, ex->grid.p, (size_t)grid_rows * grid_cols * 4, cudaMemcpyDeviceToHost, st));
-    UVIP_CUDA(cudaStreamSynchronize(st));
+    if (!full_detect) {                                        // the caller's occupancy grid comes back only on success
+        UVIP_CUDA(cudaMemcpyAsync(grid, ex->grid.p, (size_t)grid_rows * grid_cols * 4, cudaMemcpyDeviceToHost, st));
+        UVIP_CUDA(cudaStreamSynchronize(st));
+    }
     *n_inout = n;
     return UVIP_OK;
 }
