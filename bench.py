@@ -169,6 +169,14 @@ def hbm_peak():
         return FALLBACK_HBM_GBS, 'fallback'
 
 
+def ncu_pipes():
+    """per-kernel issue-slot / ALU-pipe utilisation from the committed ncu launch list (static evidence, not measured live)"""
+    try:
+        return json.load(open(os.path.join(ROOT, 'profiles', 'kernel_pipes.json')))
+    except Exception:
+        return {}
+
+
 def ncu_traffic():
     """dram bytes per launch of the dominant kernel from the committed ncu --set full capture, if any"""
     try:
@@ -392,6 +400,11 @@ def run_ours(args):
                 'algorithmic_bytes_per_launch': B_FRAME_BYTES * B, 'launch_ms': dom_ms,
                 'stage_ms_per_step': {k: v / max(ngroups, 1) for k, v in stage_ms.items()}, 'knn_ms_per_step': knn_ms / K,
                 'whole_step_frac': (B_FRAME_BYTES * B * K / (ms * 1e-3) / 1e9) / peak}
+    pipes = ncu_pipes()
+    if dom in pipes:           # the extraction kernels are instruction-bound, so the ALU pipe is reported next to HBM
+        roofline['alu_pipe'] = {'kernel': dom, 'alu_pipe_pct': pipes[dom]['alu_pipe_pct'], 'issue_slot_pct': pipes[dom]['issue_slot_pct'],
+                                'thread_instructions_per_pyramid_pixel': pipes[dom]['warp_instructions'] * 32.0 / (256 * 1117367.0),
+                                'source': 'profiles/kernel_pipes.json (ncu launch list of this command at batch 256, euroc shape)'}
 
     line = {
         'metric': METRIC, 'value': fps, 'unit': 'frames/s', 'n_gpus': world, 'steps': K, 'warmup': Wm, 'ms_per_step': ms / K,
