@@ -115,6 +115,11 @@ int   uvip_get_raw_corners(uvip_extractor* ex, int frame, int level,
 int   uvip_get_level_keypoints(uvip_extractor* ex, int frame, int level,
                                int32_t* xs, int32_t* ys, int32_t* scores, int cap, int* n); /* quadtree winners, level coords,
                                                                                 list order (src/ORBextractor.cc:817-831) */
+/* HarrisResponses (src/ORBextractor.cc:80-121: blockSize 7, k = 0.04 at its only call site :663) at n points (level
+ * coordinates) of the UNBLURRED pyramid level of a frame of the last extract call.  This is the scoring half of the reference's
+ * dead detector path ComputeKeyPoints (:536-746); the quota-cell distribution around it is not built. */
+int   uvip_harris_responses(uvip_extractor* ex, int frame, int level, const float* xs, const float* ys, int n, int block_size,
+                            float harris_k, float* out);
 /* how many of this library's kernels the handle has launched so far (bench.py's gpu_launches) */
 long long uvip_extractor_launch_count(const uvip_extractor* ex);
 /* per-stage device time (CUDA events recorded between the stage kernels on the launching stream), summed over

@@ -202,6 +202,15 @@ def descriptor(padded, x, y, angle_deg):
     return d
 
 
+def harris_responses(level_img, xs, ys, block_size=7, k=0.04):
+    """HarrisResponses (src/ORBextractor.cc:80-121) on a level image (points at least block_size//2 + 2 px from its edge)"""
+    img = np.ascontiguousarray(level_img, np.uint8)
+    xs = np.ascontiguousarray(xs, np.float32); ys = np.ascontiguousarray(ys, np.float32)
+    out = np.zeros(len(xs), np.float32)
+    lib().uo_harris_responses(_p(img), img.shape[1], _p(xs), _p(ys), len(xs), int(block_size), C.c_float(k), _p(out))
+    return out
+
+
 def distribute_octtree(x, y, resp, minX, maxX, minY, maxY, N):
     x = np.ascontiguousarray(x, np.float32); y = np.ascontiguousarray(y, np.float32)
     resp = np.ascontiguousarray(resp, np.float32)

@@ -119,4 +119,31 @@ int ref_extract_batch(int nfeatures, float scale_factor, int nlevels, int score_
     return bad ? -2 : 0;
 }
 
+// The reference's dead detector path (src/ORBextractor.cc:536-746), reached through a subclass because ComputeKeyPoints and
+// ComputePyramid are protected and no caller uses them: returns the keypoints ComputeKeyPoints leaves on `level` (level
+// coordinates, response = HarrisResponses when the extractor was created with HARRIS_SCORE).  The SELECTION among equal
+// responses depends on std::nth_element (KeyPointsFilter::retainBest), i.e. on the C++ library; the responses do not.
+struct DeadPathProbe : public USLAM::ORBextractor {
+    static int run(USLAM::ORBextractor* ex, const cv::Mat& image, int level, ref_keypoint* out, int cap)
+    {
+        DeadPathProbe* p = static_cast<DeadPathProbe*>(ex);
+        p->ComputePyramid(image);
+        std::vector<std::vector<cv::KeyPoint> > all;
+        p->ComputeKeyPoints(all);
+        if (level < 0 || level >= (int)all.size()) return -1;
+        const int n = (int)all[(size_t)level].size();
+        for (int i = 0; i < n && i < cap; i++) {
+            const cv::KeyPoint& k = all[(size_t)level][(size_t)i];
+            ref_keypoint o = {k.pt.x, k.pt.y, k.size, k.angle, k.response, k.octave, k.class_id};
+            out[i] = o;
+        }
+        return n;
+    }
+};
+int ref_dead_path_keypoints(void* h, const uint8_t* img, int w, int h_, int stride, int level, ref_keypoint* out, int cap)
+{
+    cv::Mat image(h_, w, CV_8UC1, (void*)img, (size_t)stride);
+    return DeadPathProbe::run((USLAM::ORBextractor*)h, image, level, out, cap);
+}
+
 }  // extern "C"

@@ -86,6 +86,18 @@ class Extractor:
         return kps[:n.value].copy(), desc[:n.value].copy()
 
 
+def dead_path_keypoints(extractor, image, level, cap=20000):
+    """keypoints the reference's dead ComputeKeyPoints path (src/ORBextractor.cc:536-746) leaves on `level` (HarrisResponses as
+    response when the extractor was created with score_type 0)"""
+    img = np.ascontiguousarray(image, np.uint8)
+    H, W = img.shape
+    out = np.zeros(cap, KP_DTYPE)
+    n = lib().ref_dead_path_keypoints(extractor.h, _p(img), W, H, W, int(level), _p(out), cap)
+    if n < 0 or n > cap:
+        raise RuntimeError('ref_dead_path_keypoints: %d' % n)
+    return out[:n].copy()
+
+
 def extract_batch(frames, nfeatures=1000, scale_factor=1.2, nlevels=8, fast_th=20, threads=0, cap=None, arena_mb=256):
     """frame-parallel batch over the reference extractor (one instance per OpenMP thread), same shape as oracle.extract_batch.
     arena_mb >= 0 (default): per-thread bump arena = pinned quadtree tie-break, and also the fastest way to run it (glibc

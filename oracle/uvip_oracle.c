@@ -289,6 +289,28 @@ float uo_fast_atan2(float y, float x)
 }
 
 /* IC_Angle: ORBextractor.cc:125-152 */
+/* HarrisResponses, ORBextractor.cc:80-121 (only reachable from the dead ComputeKeyPoints path :536-746).  img = pixel (0,0)
+ * of the level (unblurred), points in level coordinates. */
+void uo_harris_responses(const uint8_t* img, int step, const float* xs, const float* ys, int n, int blockSize, float harris_k, float* out)
+{
+    const int r = blockSize / 2;
+    float scale = (1 << 2) * blockSize * 255.0f;
+    scale = 1.0f / scale;
+    const float scale_sq_sq = scale * scale * scale * scale;
+    for (int i = 0; i < n; i++) {
+        const int x0 = cv_round_f(xs[i] - r), y0 = cv_round_f(ys[i] - r);
+        const uint8_t* ptr0 = img + (ptrdiff_t)y0 * step + x0;
+        int a = 0, b = 0, c = 0;
+        for (int k = 0; k < blockSize * blockSize; k++) {
+            const uint8_t* ptr = ptr0 + (k / blockSize) * step + (k % blockSize);
+            const int Ix = (ptr[1] - ptr[-1]) * 2 + (ptr[-step + 1] - ptr[-step - 1]) + (ptr[step + 1] - ptr[step - 1]);
+            const int Iy = (ptr[step] - ptr[-step]) * 2 + (ptr[step - 1] - ptr[-step - 1]) + (ptr[step + 1] - ptr[-step + 1]);
+            a += Ix * Ix; b += Iy * Iy; c += Ix * Iy;
+        }
+        out[i] = ((float)a * b - (float)c * c - harris_k * ((float)a + b) * ((float)a + b)) * scale_sq_sq;
+    }
+}
+
 float uo_ic_angle(const uint8_t* center, int step, const int* umax)
 {
     int m_01 = 0, m_10 = 0;

@@ -690,3 +690,33 @@ def test_search_for_triangulation_core_equals_reference(oracle, synth, tmp_path)
     om = oracle.rot_hist_filter(om, k1_xyoa[q, 3], k2_xyoa[:, 3])
     expect = np.full(len(node1), -1, np.int32); expect[q[om >= 0]] = om[om >= 0]
     assert r == int((om >= 0).sum()) and np.array_equal(slot_owner, expect)
+
+
+# ---------------------------------------------------------------------------------------------------- row E8, scoring half
+@needs_ref
+def test_harris_responses_equal_reference_dead_path(oracle, synth):
+    """HarrisResponses (src/ORBextractor.cc:80-121) is only reachable from the dead ComputeKeyPoints path (:536-746); the
+    reference's compiled code is driven into it through a subclass and the responses it leaves must be reproduced bit for bit"""
+    for seed, W, H in ((1, 752, 480), (1000, 640, 512)):
+        img = synth.synth_frame(seed, W, H)
+        rex = R.Extractor(1000, 1.2, 8, 0, 20)              # HARRIS_SCORE
+        oex = oracle.Extractor(1000, 1.2, 8, 0, 20); oex(img)
+        total = 0
+        for l in range(8):
+            k = R.dead_path_keypoints(rex, img, l)
+            assert len(k) > 20 and (k['octave'] == l).all()
+            assert np.array_equal(oracle.harris_responses(oex.level(l), k['x'], k['y']), k['response']), (seed, l)
+            total += len(k)
+        assert total > 800
+
+
+@needs_ref
+@pytest.mark.gpu
+def test_cuda_harris_responses_equal_reference_dead_path(gpu, synth):
+    img = synth.synth_frame(1, 752, 480)
+    ex = gpu.ORBextractor(1000, 1.2, 8, 0, 20, max_width=752, max_height=480)
+    ex(img)
+    rex = R.Extractor(1000, 1.2, 8, 0, 20)
+    for l in range(8):
+        k = R.dead_path_keypoints(rex, img, l)
+        assert np.array_equal(ex.harris_responses(l, k['x'], k['y']), k['response']), l

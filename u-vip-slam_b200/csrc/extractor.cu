@@ -1073,6 +1073,39 @@ k_describe(const uint8_t* __restrict__ pyr, const uint8_t* __restrict__ blur, co
 }
 
 // --------------------------------------------------------------------------------------------------------
+// E8 (scoring half): HarrisResponses (src/ORBextractor.cc:80-121) on the unblurred level for a list of points: integer
+// Sobel-like gradients over a blockSize x blockSize window, a = sum Ix^2, b = sum Iy^2, c = sum IxIy, response =
+// ((float)a*b - (float)c*c - k*((float)a+b)*((float)a+b)) * scale^4 with every float operation rounded separately.
+// One thread per point (lists are short); the quota-cell distribution around it (:536-746) is dead code in the reference.
+// --------------------------------------------------------------------------------------------------------
+__global__ void __launch_bounds__(128)
+k_harris(const uint8_t* __restrict__ pyr, int frame, int level, const float* __restrict__ xs, const float* __restrict__ ys, int n,
+         int block_size, float harris_k, float* __restrict__ out, const __grid_constant__ Plan P)
+{
+    const int i = blockIdx.x * 128 + threadIdx.x;
+    if (i >= n) return;
+    const LevelInfo& L = P.lv[level];
+    const int ps = L.pstride;
+    const uint8_t* img = pyr + (size_t)frame * P.frame_bytes + L.poff + (size_t)EDGE * ps + EDGE;
+    const int r = block_size / 2;
+    const int x0 = __float2int_rn(__fsub_rn(xs[i], (float)r)), y0 = __float2int_rn(__fsub_rn(ys[i], (float)r));      // cvRound(pt - r)
+    int a = 0, b = 0, c = 0;
+    for (int dy = 0; dy < block_size; dy++)
+        for (int dx = 0; dx < block_size; dx++) {
+            const uint8_t* p = img + (ptrdiff_t)(y0 + dy) * ps + (x0 + dx);
+            const int Ix = ((int)p[1] - (int)p[-1]) * 2 + ((int)p[-ps + 1] - (int)p[-ps - 1]) + ((int)p[ps + 1] - (int)p[ps - 1]);
+            const int Iy = ((int)p[ps] - (int)p[-ps]) * 2 + ((int)p[ps - 1] - (int)p[-ps - 1]) + ((int)p[ps + 1] - (int)p[-ps + 1]);
+            a += Ix * Ix; b += Iy * Iy; c += Ix * Iy;
+        }
+    float scale = __fmul_rn((float)((1 << 2) * block_size), 255.0f);
+    scale = __fdiv_rn(1.0f, scale);
+    const float s4 = __fmul_rn(__fmul_rn(__fmul_rn(scale, scale), scale), scale);
+    const float fa = (float)a, fb = (float)b, fc = (float)c, ab = __fadd_rn(fa, fb);
+    const float v = __fsub_rn(__fsub_rn(__fmul_rn(fa, fb), __fmul_rn(fc, fc)), __fmul_rn(__fmul_rn(harris_k, ab), ab));
+    out[i] = __fmul_rn(v, s4);
+}
+
+// --------------------------------------------------------------------------------------------------------
 // N3: CLAHE pre-processing, cv::createCLAHE(4, Size(12,12))->apply(im, im) at src/Tracking.cc:425-431,
 // restated from OpenCV imgproc/clahe.cpp (8-bit path).  k_clahe_lut: one CTA per (tile, frame) — shared-memory histogram
 // of the tile (image padded to a tile multiple by reflect-101), clip + redistribute, cumulative LUT.  k_clahe_apply: four
@@ -2067,6 +2100,34 @@ int uvip_get_level_keypoints(uvip_extractor* ex, int frame, int level, int32_t* 
         if (ys) ys[i] = (int)((v[i] >> 12) & 0xFFF);
         if (scores) scores[i] = (int)(v[i] >> 24);
     }
+    return UVIP_OK;
+}
+
+// HarrisResponses (src/ORBextractor.cc:80-121) at n points of pyramid level `level` of frame `frame` of the last extract call
+int uvip_harris_responses(uvip_extractor* ex, int frame, int level, const float* xs, const float* ys, int n, int block_size, float harris_k,
+                          float* out)
+{
+    UVIP_CHECK_ARG(ex && ex->plan.W > 0 && frame >= 0 && frame < ex->last_frames && level >= 0 && level < ex->prm.nlevels && n >= 0);
+    UVIP_CHECK_ARG(block_size >= 1 && block_size * block_size <= 2048);
+    if (n == 0) return UVIP_OK;
+    UVIP_CHECK_ARG(xs && ys && out);
+    const LevelInfo& L = ex->plan.lv[level];
+    const int r = block_size / 2, reach = block_size - r;        // the window plus its gradient neighbours must stay inside the materialised ring
+    for (int i = 0; i < n; i++)
+        UVIP_CHECK_ARG(xs[i] - r - 1 >= -BORDER_W && xs[i] + reach + 1 <= L.w + BORDER_W && ys[i] - r - 1 >= -BORDER_W && ys[i] + reach + 1 <= L.h + BORDER_W);
+    std::lock_guard<std::mutex> lk(ex->mu);
+    DeviceGuard g(ex->device);
+    int rc;
+    if ((rc = ex->clahe_io.reserve((size_t)n * 12))) return rc;
+    float* d = ex->clahe_io.as<float>();
+    cudaStream_t st = ex->stream;
+    UVIP_CUDA(cudaMemcpyAsync(d, xs, (size_t)n * 4, cudaMemcpyHostToDevice, st));
+    UVIP_CUDA(cudaMemcpyAsync(d + n, ys, (size_t)n * 4, cudaMemcpyHostToDevice, st));
+    k_harris<<<div_up(n, 128), 128, 0, st>>>(ex->pyr.as<uint8_t>(), frame, level, d, d + n, n, block_size, harris_k, d + 2 * (size_t)n, ex->plan);
+    ex->launches++;
+    UVIP_CUDA(cudaGetLastError());
+    UVIP_CUDA(cudaMemcpyAsync(out, d + 2 * (size_t)n, (size_t)n * 4, cudaMemcpyDeviceToHost, st));
+    UVIP_CUDA(cudaStreamSynchronize(st));
     return UVIP_OK;
 }
 

@@ -148,6 +148,13 @@ class ORBextractor:
     def level_keypoints(self, l, frame=0):
         return self._list(lib().uvip_get_level_keypoints, l, frame)
 
+    def harris_responses(self, l, xs, ys, block_size=7, k=0.04, frame=0):
+        """HarrisResponses (src/ORBextractor.cc:80-121) at points of pyramid level l of the last extracted frame"""
+        xs = np.ascontiguousarray(xs, np.float32); ys = np.ascontiguousarray(ys, np.float32)
+        out = np.zeros(len(xs), np.float32)
+        check(lib().uvip_harris_responses(self.h, int(frame), int(l), ptr(xs), ptr(ys), len(xs), int(block_size), float(k), ptr(out)))
+        return out
+
 
 class ORBmatcher:
     TH_HIGH = 100
