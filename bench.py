@@ -588,14 +588,13 @@ def run_search(args):
         tt = torch.tensor([ms], dtype=torch.float64, device=dev); dist.all_reduce(tt, op=dist.ReduceOp.MAX); ms = float(tt.item())
     mps = float(world) * F * NQ * K / (ms * 1e-3)
     counts = t['counts'].cpu().numpy()
-    # ---- end to end: the single-frame host-buffer call (uvip_grid_build + uvip_search_window, H2D + D2H inside), one frame after another
+    # ---- end to end: the single-frame host-buffer call (uvip_search_frame, H2D + D2H inside), one frame after another
     c0 = cases[0]
     te = time.perf_counter(); ne = 0
     while ne < 20 or time.perf_counter() - te < 0.5:
         c = cases[ne % ndistinct]
-        grid = m.grid_build(c['kx'], c['ky'], c['bounds'])
-        n1, match1, taken1 = m.search_window(0, 100, c['u'], c['v'], rad[ne % ndistinct], c['level'] - 1, c['level'], c['qdesc'], c['kx'], c['ky'],
-                                             c['octave'], c['kdesc'], grid)
+        n1, match1, taken1 = m.search_frame(0, 100, c['u'], c['v'], rad[ne % ndistinct], c['level'] - 1, c['level'], c['qdesc'], c['kx'], c['ky'],
+                                            c['octave'], c['kdesc'], c['bounds'])
         ne += 1
     e2e_s = time.perf_counter() - te
     if world > 1:
@@ -625,8 +624,8 @@ def run_search(args):
                            'not bandwidth-bound; inputs stay L2-resident by design' % (F * (NQ * 56 + NK * 48) / 1e6)},
                 'clocks': clk, 'gpu_launches': int(launches),
                 'e2e': {'value': world * NQ * ne / e2e_s, 'unit': 'map points/s', 'h2d_bytes_per_step': NQ * 52 + NK * 48 + (64 * 48 + 1) * 4 + NK * 8,
-                        'd2h_bytes_per_step': NQ * 4 + NK * 4 + (64 * 48 + 1) * 4 + NK * 4 + 8, 'what': 'single-frame host-buffer calls uvip_grid_build + '
-                        'uvip_search_window, one frame after another (the shape of the reference call)', 'frames': ne, 'ms_per_frame': 1e3 * e2e_s / ne},
+                        'd2h_bytes_per_step': NQ * 4 + NK * 4 + (64 * 48 + 1) * 4 + NK * 4 + 8, 'what': 'single-frame host-buffer call uvip_search_frame '
+                        '(grid + search on the device), one frame after another (the shape of the reference call)', 'frames': ne, 'ms_per_frame': 1e3 * e2e_s / ne},
                 'roofline': {'bound': 'hbm', 'achieved': achieved, 'peak': peak, 'unit': 'GB/s', 'frac': achieved / peak, 'traffic': None,
                              'peak_source': peak_kind, 'algorithmic_bytes_per_launch': bytes_frame * F,
                              'candidate_pairs_per_s': float(world) * ncand * F * K / (ms * 1e-3), 'candidate_pairs_per_frame': ncand,

@@ -218,6 +218,14 @@ int   uvip_search_window(uvip_matcher* m, const uvip_search_params* sp,
 int   uvip_search_lists_epipolar(uvip_matcher* m, int th_dist, const uint8_t* qdesc, const float* qline, int nq,
                                  const int32_t* cand_start, const int32_t* cand_idx, const uint8_t* kdesc, const float* kx, const float* ky,
                                  const double* kthr, int nk, int32_t* taken, int32_t* match, int* nmatches);
+/* uvip_search_window for one frame WITHOUT a caller-side grid: one upload, frame grid + search on the device, one download,
+ * one synchronisation.  This is what the shim's per-frame searches call (e.g. SearchByProjection(F, local map points, th),
+ * src/Tracking.cc:2228); uvip_grid_build + uvip_search_window remain for callers that keep a frame's grid. */
+int   uvip_search_frame(uvip_matcher* m, const uvip_search_params* sp,
+                        const float* qu, const float* qv, const float* qr, const int32_t* qmin_level,
+                        const int32_t* qmax_level, const uint8_t* qdesc, int nq,
+                        const float* kx, const float* ky, const int32_t* octave, const uint8_t* kdesc, int nk,
+                        int32_t* taken, int32_t* match, int* nmatches);
 /* The same search for a batch of device-resident frames (BASELINE config 3 as a throughput workload; frames shard with no
  * exchange because claims never cross frames).  Frame f owns queries [f*q_stride, f*q_stride + d_nq[f]) and keypoints
  * [f*k_stride, f*k_stride + d_nk[f]) of every array; the frame grids (src/FrameKTL.cc:250-264) are built on the device by the

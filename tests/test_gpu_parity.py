@@ -285,6 +285,9 @@ def test_grid_and_search_by_projection_cfg3(gpu, oracle, synth):
                                                   grid['minX'], grid['minY'], grid['inv_w'], grid['inv_h'])
         assert n == on and n > 500
         assert np.array_equal(match, omatch) and np.array_equal(taken, otaken)
+        n2, match2, taken2 = m.search_frame(0, 100, c['u'], c['v'], r, c['level'] - 1, c['level'], c['qdesc'], c['kx'], c['ky'], c['octave'],
+                                            c['kdesc'], c['bounds'])                     # grid built on the device by the same call
+        assert n2 == on and np.array_equal(match2, omatch) and np.array_equal(taken2, otaken)
     # M5 semantics: th=10 window, levels [l-1, l+1], best only, ORBdist 100, pre-taken keypoints, then the histogram
     lvl = c['level']
     r = (np.float32(10) * sf[lvl]).astype(np.float32)

@@ -596,6 +596,7 @@ struct uvip_matcher {
     cudaStream_t stream = nullptr;
     DevBuf q, t, idx, dist, misc, misc2, misc3, misc4;
     long long launches = 0;
+    uint8_t* h_stage = nullptr; size_t h_stage_bytes = 0;      // pinned mirror of the upload / download block of uvip_search_frame
     std::mutex mu;
 };
 
@@ -632,6 +633,7 @@ int uvip_matcher_destroy(uvip_matcher* m)
     cudaStreamSynchronize(m->stream);
     m->q.release(); m->t.release(); m->idx.release(); m->dist.release();
     m->misc.release(); m->misc2.release(); m->misc3.release(); m->misc4.release();
+    if (m->h_stage) cudaFreeHost(m->h_stage);
     cudaStreamDestroy(m->stream);
     delete m;
     return UVIP_OK;
@@ -1011,6 +1013,74 @@ int uvip_search_lists(uvip_matcher* m, int mode, int th_dist, float ratio, const
     if (nk) UVIP_CUDA(cudaMemcpyAsync(taken, base + o_taken, (size_t)nk * 4, cudaMemcpyDeviceToHost, st));
     UVIP_CUDA(cudaMemcpyAsync(counts, base + o_cnt, 8, cudaMemcpyDeviceToHost, st));
     UVIP_CUDA(cudaStreamSynchronize(st));
+    if (nmatches) *nmatches = counts[0];
+    return UVIP_OK;
+}
+
+// uvip_search_window without the caller-side grid: one upload, grid build + search on the device, one download and a single
+// synchronisation.  This is the per-frame call of the Tracking thread (SearchByProjection(F, local map points, th)).
+int uvip_search_frame(uvip_matcher* m, const uvip_search_params* sp,
+                      const float* qu, const float* qv, const float* qr, const int32_t* qmin_level,
+                      const int32_t* qmax_level, const uint8_t* qdesc, int nq,
+                      const float* kx, const float* ky, const int32_t* octave, const uint8_t* kdesc, int nk,
+                      int32_t* taken, int32_t* match, int* nmatches)
+{
+    UVIP_CHECK_ARG(m && sp && nq >= 0 && nk >= 0 && sp->cols > 0 && sp->rows > 0);
+    UVIP_CHECK_ARG(sp->mode == 0 || sp->mode == 1 || sp->mode == 4);
+    if (nmatches) *nmatches = 0;
+    if (nq == 0) return UVIP_OK;
+    UVIP_CHECK_ARG(qu && qv && qr && qmin_level && qmax_level && qdesc && match);
+    UVIP_CHECK_ARG(nk == 0 || (kx && ky && octave && kdesc && taken));
+    const int ncell = sp->cols * sp->rows;
+    UVIP_CHECK_ARG((size_t)(2 * ncell + 1) * 4 <= 200 * 1024);
+    std::lock_guard<std::mutex> lk(m->mu);
+    DeviceGuard g(m->device);
+    size_t off = 0;
+    auto sect = [&](size_t bytes) { size_t o = off; off = align_up(off + bytes, 32); return o; };
+    const size_t nkk = nk > 0 ? nk : 1;
+    // host-visible part first (one contiguous upload from a pinned mirror), device-only scratch after it
+    const size_t o_qu = sect((size_t)nq * 4), o_qv = sect((size_t)nq * 4), o_qr = sect((size_t)nq * 4);
+    const size_t o_qmin = sect((size_t)nq * 4), o_qmax = sect((size_t)nq * 4), o_qd = sect((size_t)nq * 32);
+    const size_t o_kx = sect(nkk * 4), o_ky = sect(nkk * 4), o_oct = sect(nkk * 4), o_kd = sect(nkk * 32), o_taken = sect(nkk * 4);
+    const size_t up_bytes = off;
+    const size_t o_match = sect((size_t)nq * 4), o_cnt = sect(16);
+    const size_t down_bytes = off - o_taken;
+    const size_t o_cs = sect((size_t)(ncell + 1) * 4), o_ci = sect(nkk * 4), o_cof = sect(nkk * 4), o_oa = sect(nkk * 4), o_ob = sect(nkk * 4);
+    int rc;
+    if ((rc = m->misc.reserve(off))) return rc;
+    if (m->h_stage_bytes < o_cs) {
+        if (m->h_stage) { cudaFreeHost(m->h_stage); m->h_stage = nullptr; m->h_stage_bytes = 0; }
+        UVIP_CUDA(cudaMallocHost((void**)&m->h_stage, o_cs));
+        m->h_stage_bytes = o_cs;
+    }
+    uint8_t* hs = m->h_stage; uint8_t* base = m->misc.as<uint8_t>();
+    memcpy(hs + o_qu, qu, (size_t)nq * 4); memcpy(hs + o_qv, qv, (size_t)nq * 4); memcpy(hs + o_qr, qr, (size_t)nq * 4);
+    memcpy(hs + o_qmin, qmin_level, (size_t)nq * 4); memcpy(hs + o_qmax, qmax_level, (size_t)nq * 4); memcpy(hs + o_qd, qdesc, (size_t)nq * 32);
+    if (nk) {
+        memcpy(hs + o_kx, kx, (size_t)nk * 4); memcpy(hs + o_ky, ky, (size_t)nk * 4); memcpy(hs + o_oct, octave, (size_t)nk * 4);
+        memcpy(hs + o_kd, kdesc, (size_t)nk * 32); memcpy(hs + o_taken, taken, (size_t)nk * 4);
+    }
+    cudaStream_t st = m->stream;
+    UVIP_CUDA(cudaMemcpyAsync(base, hs, up_bytes, cudaMemcpyHostToDevice, st));
+    const size_t smem = (size_t)(2 * ncell + 1) * 4;
+    UVIP_CUDA(cudaFuncSetAttribute(k_grid_build, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+    k_grid_build<<<1, 1024, smem, st>>>((const float*)(base + o_kx), (const float*)(base + o_ky), nk, sp->min_x, sp->min_y, sp->inv_w, sp->inv_h,
+                                         sp->cols, sp->rows, (int32_t*)(base + o_cs), (int32_t*)(base + o_ci), (int32_t*)(base + o_cof), nullptr, 0);
+    SearchCtx c; memset(&c, 0, sizeof(c));
+    c.sp = *sp;
+    c.qu = (const float*)(base + o_qu); c.qv = (const float*)(base + o_qv); c.qr = (const float*)(base + o_qr);
+    c.qminL = (const int32_t*)(base + o_qmin); c.qmaxL = (const int32_t*)(base + o_qmax); c.qdesc = base + o_qd;
+    c.kx = (const float*)(base + o_kx); c.ky = (const float*)(base + o_ky); c.octave = (const int32_t*)(base + o_oct);
+    c.kdesc = base + o_kd; c.cell_start = (const int32_t*)(base + o_cs); c.cell_items = (const int32_t*)(base + o_ci);
+    k_search_window<<<1, 1024, 0, st>>>(c, nq, nk, (int32_t*)(base + o_taken), (int32_t*)(base + o_match),
+                                         (int*)(base + o_oa), (int*)(base + o_ob), (int*)(base + o_cnt), nullptr, nullptr, 0, 0);
+    m->launches += 2;
+    UVIP_CUDA(cudaGetLastError());
+    UVIP_CUDA(cudaMemcpyAsync(hs + o_taken, base + o_taken, down_bytes, cudaMemcpyDeviceToHost, st));      // taken | match | counts
+    UVIP_CUDA(cudaStreamSynchronize(st));
+    memcpy(match, hs + o_match, (size_t)nq * 4);
+    if (nk) memcpy(taken, hs + o_taken, (size_t)nk * 4);
+    int counts[2]; memcpy(counts, hs + o_cnt, 8);
     if (nmatches) *nmatches = counts[0];
     return UVIP_OK;
 }

@@ -254,6 +254,24 @@ class ORBmatcher:
                                        ptr(i32(grid['items'])), ptr(tk), ptr(match), C.byref(n)))
         return n.value, match, tk
 
+    def search_frame(self, mode, th_dist, qu, qv, qr, qminL, qmaxL, qdesc, kx, ky, octave, kdesc, bounds, taken=None, cols=64, rows=48):
+        """uvip_search_frame: uvip_search_window with the frame grid built on the device by the same call"""
+        f32 = lambda a: np.ascontiguousarray(a, np.float32)
+        i32 = lambda a: np.ascontiguousarray(a, np.int32)
+        qu, qv, qr, kx, ky = f32(qu), f32(qv), f32(qr), f32(kx), f32(ky)
+        qminL, qmaxL, octave = i32(qminL), i32(qmaxL), i32(octave)
+        qdesc = np.ascontiguousarray(qdesc, np.uint8); kdesc = np.ascontiguousarray(kdesc, np.uint8)
+        nq, nk = len(qu), len(kx)
+        tk = np.full(nk, -1, np.int32) if taken is None else i32(taken).copy()
+        match = np.full(nq, -1, np.int32)
+        minX, maxX, minY, maxY = bounds
+        inv_w = np.float32(cols) / np.float32(maxX - minX); inv_h = np.float32(rows) / np.float32(maxY - minY)
+        sp = SearchParams(mode, th_dist, self.mfNNratio, float(minX), float(minY), float(inv_w), float(inv_h), cols, rows)
+        n = C.c_int()
+        check(lib().uvip_search_frame(self.h, C.byref(sp), ptr(qu), ptr(qv), ptr(qr), ptr(qminL), ptr(qmaxL), ptr(qdesc), nq,
+                                      ptr(kx), ptr(ky), ptr(octave), ptr(kdesc), nk, ptr(tk), ptr(match), C.byref(n)))
+        return n.value, match, tk
+
     def projection_radius(self, view_cos, level, scale_factors, th=1.0):
         """r = RadiusByViewingCos(viewCos) [* th] * mvScaleFactors[level]  (src/ORBmatcher.cc:68-76,127-133), float by float"""
         r = np.array([lib().uvip_radius_by_viewing_cos(float(c)) for c in view_cos], np.float32)

@@ -77,12 +77,10 @@ public:
         sp.mode = 0; sp.th_dist = TH_HIGH; sp.ratio = mfNNratio;
         sp.min_x = (float)F.mnMinX; sp.min_y = (float)F.mnMinY; sp.inv_w = F.mfGridElementWidthInv; sp.inv_h = F.mfGridElementHeightInv;
         sp.cols = 64; sp.rows = 48;
-        std::vector<int32_t> cs(64 * 48 + 1), ci((size_t)(nk > 0 ? nk : 1)), match((size_t)nq);
-        check(uvip_grid_build(handle_, kx.data(), ky.data(), nk, sp.min_x, sp.min_y, sp.inv_w, sp.inv_h, 64, 48, cs.data(), ci.data()), "uvip_grid_build");
+        std::vector<int32_t> match((size_t)nq);
         int nmatches = 0;
-        check(uvip_search_window(handle_, &sp, qu.data(), qv.data(), qr.data(), qmin.data(), qmax.data(), qd.data(), nq,
-                                 kx.data(), ky.data(), oct.data(), kd.data(), nk, cs.data(), ci.data(), taken.data(), match.data(), &nmatches),
-              "uvip_search_window");
+        check(uvip_search_frame(handle_, &sp, qu.data(), qv.data(), qr.data(), qmin.data(), qmax.data(), qd.data(), nq,
+                                kx.data(), ky.data(), oct.data(), kd.data(), nk, taken.data(), match.data(), &nmatches), "uvip_search_frame");
         for (int q = 0; q < nq; q++) if (match[q] >= 0) F.mvpMapPoints[match[q]] = who[q];     // :119
         return nmatches;
     }
@@ -159,12 +157,10 @@ public:
         sp.min_x = (float)CurrentFrame.mnMinX; sp.min_y = (float)CurrentFrame.mnMinY;
         sp.inv_w = CurrentFrame.mfGridElementWidthInv; sp.inv_h = CurrentFrame.mfGridElementHeightInv;
         sp.cols = 64; sp.rows = 48;
-        std::vector<int32_t> cs(64 * 48 + 1), ci((size_t)nk), match((size_t)nq);
-        check(uvip_grid_build(handle_, kx.data(), ky.data(), nk, sp.min_x, sp.min_y, sp.inv_w, sp.inv_h, 64, 48, cs.data(), ci.data()), "uvip_grid_build");
+        std::vector<int32_t> match((size_t)nq);
         int nmatches = 0;
-        check(uvip_search_window(handle_, &sp, qu.data(), qv.data(), qr.data(), qmin.data(), qmax.data(), qd.data(), nq,
-                                 kx.data(), ky.data(), oct.data(), kd.data(), nk, cs.data(), ci.data(), taken.data(), match.data(), &nmatches),
-              "uvip_search_window");
+        check(uvip_search_frame(handle_, &sp, qu.data(), qv.data(), qr.data(), qmin.data(), qmax.data(), qd.data(), nq,
+                                kx.data(), ky.data(), oct.data(), kd.data(), nk, taken.data(), match.data(), &nmatches), "uvip_search_frame");
         for (int q = 0; q < nq; q++) if (match[q] >= 0) CurrentFrame.mvpMapPoints[match[q]] = who[q];      // :1698
         if (mbCheckOrientation) {                                                                          // :1701-1743
             std::vector<int32_t> kept(match);
@@ -356,11 +352,9 @@ protected:
         sp.mode = mode; sp.th_dist = th_dist; sp.ratio = mfNNratio;
         sp.min_x = (float)pKF->mnMinX; sp.min_y = (float)pKF->mnMinY; sp.inv_w = pKF->mfGridElementWidthInv; sp.inv_h = pKF->mfGridElementHeightInv;
         sp.cols = 64; sp.rows = 48;
-        std::vector<int32_t> cs(64 * 48 + 1), ci((size_t)nk);
-        check(uvip_grid_build(handle_, kx.data(), ky.data(), nk, sp.min_x, sp.min_y, sp.inv_w, sp.inv_h, 64, 48, cs.data(), ci.data()), "uvip_grid_build");
         int n = 0;
-        check(uvip_search_window(handle_, &sp, Q.u.data(), Q.v.data(), Q.r.data(), Q.lo.data(), Q.hi.data(), Q.d.data(), nq, kx.data(), ky.data(), oct.data(),
-                                 kd.data(), nk, cs.data(), ci.data(), taken.data(), match.data(), &n), "uvip_search_window");
+        check(uvip_search_frame(handle_, &sp, Q.u.data(), Q.v.data(), Q.r.data(), Q.lo.data(), Q.hi.data(), Q.d.data(), nq, kx.data(), ky.data(), oct.data(),
+                                kd.data(), nk, taken.data(), match.data(), &n), "uvip_search_frame");
         return n;
     }
 
