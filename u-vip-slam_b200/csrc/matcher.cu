@@ -5,8 +5,11 @@
 // Reference semantics restated here (never its code): src/ORBmatcher.cc:40-133,1748-1810,
 // src/FrameKTL.cc:250-264,359-436, include/utils.h:81-111.
 #include "common.cuh"
+#include <cooperative_groups.h>
 #include <stdarg.h>
 #include <limits.h>
+
+namespace cg = cooperative_groups;
 
 namespace uvip {
 
@@ -376,7 +379,7 @@ __device__ __forceinline__ int hamming256(const uint4& u, const uint4& v, const 
            __popc(v.x ^ y.x) + __popc(v.y ^ y.y) + __popc(v.z ^ y.z) + __popc(v.w ^ y.w);
 }
 
-__device__ int search_one(const SearchCtx& c, int q, const int* __restrict__ owner)
+__device__ int search_one(const SearchCtx& c, int q, const int* owner)
 {
     const uvip_search_params& sp = c.sp;
     const float x = c.qu[q], y = c.qv[q], r = c.qr[q];
@@ -421,7 +424,7 @@ __device__ int search_one(const SearchCtx& c, int q, const int* __restrict__ own
 }
 
 // node-restricted search (SearchByBoW inner loops, src/ORBmatcher.cc:186-245 and :751-811; mode 1 = best-only lists)
-__device__ int search_one_list(const SearchCtx& c, int q, const int* __restrict__ owner)
+__device__ int search_one_list(const SearchCtx& c, int q, const int* owner)
 {
     const uvip_search_params& sp = c.sp;
     const uint4 u = __ldg(reinterpret_cast<const uint4*>(c.qdesc + (size_t)q * 32));
@@ -448,7 +451,7 @@ __device__ int search_one_list(const SearchCtx& c, int q, const int* __restrict_
 // vocabulary node with dist <= TH_LOW, sorted by (dist, index); among those with dist <= round(2 * best dist) the first one whose
 // distance to the epipolar line passes the chi-square test is taken and claimed.  One pass: the best (dist, index) key over all
 // candidates gives the bound, the best key over the epipolar-consistent ones the match.
-__device__ int search_one_epipolar(const SearchCtx& c, int q, const int* __restrict__ owner)
+__device__ int search_one_epipolar(const SearchCtx& c, int q, const int* owner)
 {
     const uvip_search_params& sp = c.sp;
     const uint4 u = __ldg(reinterpret_cast<const uint4*>(c.qdesc + (size_t)q * 32));
@@ -477,61 +480,86 @@ __device__ int search_one_epipolar(const SearchCtx& c, int q, const int* __restr
 // runs in parallel against the claims of the previous round (owner[idx] = lowest query index that claimed idx)
 // and rounds repeat until the claim table is a fixed point; by induction over the query index the fixed point
 // is exactly the sequential result ("claims").
-__global__ void __launch_bounds__(1024)
+// One thread-block CLUSTER per frame (hardware cluster barrier between the phases of
+// a round), so that a single frame's 10 000 queries spread over several SMs instead of one.  Claim tables live in global
+// memory (L2), the "anything changed" flag of a round in a small per-frame rotating triple.  The cluster barrier has
+// release / acquire semantics at cluster scope (the acquire side invalidates L1), so the tables are read with plain cached loads:
+// within a round `prev` is read-only and `cur` only receives atomics.
+// Launch shapes (measured on B200, config 3): a lone frame wants its queries on many SMs (8 CTAs x 512 threads: 0.26 ms per
+// host call against 0.60 ms with one 1024-thread CTA); a large batch already fills the GPU with frames and prefers few fat
+// CTAs (2 x 1024: 1.06 ms per 256 frames against 1.44 ms).  The kernel reads its shape at run time.
+constexpr int SW_THREADS = 1024;
+__global__ void __launch_bounds__(SW_THREADS)
 k_search_window(SearchCtx c, int nq, int nk, int32_t* __restrict__ taken, int32_t* __restrict__ match,
-                int* __restrict__ ownerA, int* __restrict__ ownerB, int* __restrict__ out_counts,
-                const int32_t* __restrict__ d_nq, const int32_t* __restrict__ d_nk, int q_stride, int k_stride)
+                int* ownerA, int* ownerB, int* __restrict__ out_counts,
+                const int32_t* __restrict__ d_nq, const int32_t* __restrict__ d_nk, int q_stride, int k_stride, int* flags)
 {
-    __shared__ int s_changed, s_n;
-    {   // batched form (frames shard trivially: claims never cross frames): blockIdx.x = frame
-        const size_t f = blockIdx.x;
+    cg::cluster_group cl = cg::this_cluster();
+    const int CL = (int)cl.num_blocks(), rank = (int)cl.block_rank();
+    const int T = CL * (int)blockDim.x, t0 = rank * (int)blockDim.x + (int)threadIdx.x;
+    {   // batched form (frames shard trivially: claims never cross frames): one cluster per frame
+        const size_t f = blockIdx.x / CL;
         const size_t qo = f * q_stride, ko = f * k_stride;
         c.qu += qo; c.qv += qo; c.qr += qo; c.qminL += qo; c.qmaxL += qo; c.qdesc += qo * 32;
         c.kx += ko; c.ky += ko; c.octave += ko; c.kdesc += ko * 32;
         c.cell_start += f * (size_t)(c.sp.cols * c.sp.rows + 1); c.cell_items += ko;
-        taken += ko; match += qo; ownerA += ko; ownerB += ko; out_counts += 2 * f;
+        taken += ko; match += qo; ownerA += ko; ownerB += ko; out_counts += 2 * f; flags += 4 * f;
         if (d_nq) nq = d_nq[f];
         if (d_nk) nk = d_nk[f];
     }
     int* prev = ownerA; int* cur = ownerB;
     const bool claims = c.sp.mode != 4;                    // mode 4 (Fuse): every query is independent, taken[] is not consulted
-    for (int i = threadIdx.x; i < nk; i += blockDim.x) prev[i] = (claims && taken[i] != -1) ? -2 : INT_MAX;
-    __syncthreads();
+    for (int i = t0; i < nk; i += T) prev[i] = (claims && taken[i] != -1) ? -2 : INT_MAX;
+    if (t0 == 0) { flags[0] = flags[1] = flags[2] = 0; out_counts[0] = 0; }
+    cl.sync();
     int rounds = 0;
     for (;;) {
-        for (int i = threadIdx.x; i < nk; i += blockDim.x) cur[i] = (claims && taken[i] != -1) ? -2 : INT_MAX;
-        if (threadIdx.x == 0) s_changed = 0;
-        __syncthreads();
-        for (int q = threadIdx.x; q < nq; q += blockDim.x) {
+        int* flag = flags + rounds % 3;
+        for (int i = t0; i < nk; i += T) cur[i] = (claims && taken[i] != -1) ? -2 : INT_MAX;
+        if (t0 == 0) flags[(rounds + 1) % 3] = 0;          // next round's flag: nobody reads or writes it during this round
+        cl.sync();
+        for (int q = t0; q < nq; q += T) {
             const int r = c.cand_start ? (c.sp.mode == 5 ? search_one_epipolar(c, q, prev) : search_one_list(c, q, prev)) : search_one(c, q, prev);
             match[q] = r;
             if (r >= 0 && claims) atomicMin(&cur[r], q);
         }
-        __syncthreads();
+        cl.sync();
         int ch = 0;
-        for (int i = threadIdx.x; i < nk; i += blockDim.x) ch |= (cur[i] != prev[i]);
-        if (ch) s_changed = 1;
-        __syncthreads();
+        for (int i = t0; i < nk; i += T) ch |= (cur[i] != prev[i]);
+        if (__any_sync(0xFFFFFFFFu, ch) && (threadIdx.x & 31) == 0) atomicOr(flag, 1);
+        cl.sync();
         rounds++;
-        const int changed = s_changed;
+        const int changed = __ldcg(flag);
         int* tmp = prev; prev = cur; cur = tmp;
-        __syncthreads();
-        if (!changed) break;
+        if (!changed) break;                               // uniform over the cluster: every CTA read the same flag after the barrier
     }
-    if (threadIdx.x == 0) s_n = 0;
-    __syncthreads();
     int n = 0;
     if (claims) {
-        for (int i = threadIdx.x; i < nk; i += blockDim.x) {
+        for (int i = t0; i < nk; i += T) {
             const int o = prev[i];
             if (o >= 0 && o != INT_MAX) { taken[i] = o; n++; }
         }
     } else {
-        for (int q = threadIdx.x; q < nq; q += blockDim.x) n += match[q] >= 0;
+        for (int q = t0; q < nq; q += T) n += match[q] >= 0;
     }
-    if (n) atomicAdd(&s_n, n);
-    __syncthreads();
-    if (threadIdx.x == 0) { out_counts[0] = s_n; out_counts[1] = rounds; }
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) n += __shfl_xor_sync(0xFFFFFFFFu, n, o);
+    if ((threadIdx.x & 31) == 0 && n) atomicAdd(&out_counts[0], n);
+    if (t0 == 0) out_counts[1] = rounds;
+}
+
+// launches the search for nframes frames: one cluster per frame
+static cudaError_t launch_search(cudaStream_t st, int nframes, const SearchCtx& c, int nq, int nk, int32_t* taken, int32_t* match, int* oa, int* ob,
+                                 int* counts, const int32_t* d_nq, const int32_t* d_nk, int q_stride, int k_stride, int* flags)
+{
+    const int cluster = nframes <= 32 ? 8 : 2, threads = nframes <= 32 ? 512 : 1024;
+    cudaLaunchConfig_t cfg = {};
+    cfg.gridDim = dim3((unsigned)(nframes * cluster)); cfg.blockDim = dim3((unsigned)threads); cfg.dynamicSmemBytes = 0; cfg.stream = st;
+    cudaLaunchAttribute at[1];
+    at[0].id = cudaLaunchAttributeClusterDimension;
+    at[0].val.clusterDim.x = (unsigned)cluster; at[0].val.clusterDim.y = 1; at[0].val.clusterDim.z = 1;
+    cfg.attrs = at; cfg.numAttrs = 1;
+    return cudaLaunchKernelEx(&cfg, k_search_window, c, nq, nk, taken, match, oa, ob, counts, d_nq, d_nk, q_stride, k_stride, flags);
 }
 
 // N2: DBoW2 vocabulary-tree descent, TemplatedVocabulary::transform (Thirdparty/DBoW2/DBoW2/TemplatedVocabulary.h:1218-1259)
@@ -943,7 +971,7 @@ int uvip_search_window(uvip_matcher* m, const uvip_search_params* sp,
     const size_t o_kx = sect(nkk * 4), o_ky = sect(nkk * 4), o_oct = sect(nkk * 4), o_kd = sect(nkk * 32);
     const size_t o_cs = sect((size_t)(ncell + 1) * 4), o_ci = sect((size_t)(nitems > 0 ? nitems : 1) * 4);
     const size_t o_taken = sect(nkk * 4), o_match = sect((size_t)nq * 4), o_oa = sect(nkk * 4), o_ob = sect(nkk * 4);
-    const size_t o_cnt = sect(16);
+    const size_t o_cnt = sect(32);
     int rc;
     if ((rc = m->misc.reserve(off))) return rc;
     uint8_t* base = m->misc.as<uint8_t>();
@@ -961,8 +989,8 @@ int uvip_search_window(uvip_matcher* m, const uvip_search_params* sp,
     c.qminL = (const int32_t*)(base + o_qmin); c.qmaxL = (const int32_t*)(base + o_qmax); c.qdesc = base + o_qd;
     c.kx = (const float*)(base + o_kx); c.ky = (const float*)(base + o_ky); c.octave = (const int32_t*)(base + o_oct);
     c.kdesc = base + o_kd; c.cell_start = (const int32_t*)(base + o_cs); c.cell_items = (const int32_t*)(base + o_ci);
-    k_search_window<<<1, 1024, 0, st>>>(c, nq, nk, (int32_t*)(base + o_taken), (int32_t*)(base + o_match),
-                                         (int*)(base + o_oa), (int*)(base + o_ob), (int*)(base + o_cnt), nullptr, nullptr, 0, 0);
+    UVIP_CUDA(launch_search(st, 1, c, nq, nk, (int32_t*)(base + o_taken), (int32_t*)(base + o_match), (int*)(base + o_oa), (int*)(base + o_ob),
+                            (int*)(base + o_cnt), nullptr, nullptr, 0, 0, (int*)(base + o_cnt) + 4));
     m->launches++;
     UVIP_CUDA(cudaGetLastError());
     int counts[2] = {0, 0};
@@ -991,7 +1019,7 @@ int uvip_search_lists(uvip_matcher* m, int mode, int th_dist, float ratio, const
     auto sect = [&](size_t bytes) { size_t o = off; off = align_up(off + bytes, 32); return o; };
     const size_t nkk = nk > 0 ? nk : 1;
     const size_t o_qd = sect((size_t)nq * 32), o_kd = sect(nkk * 32), o_cs = sect((size_t)(nq + 1) * 4), o_ci = sect((size_t)(ncand > 0 ? ncand : 1) * 4);
-    const size_t o_taken = sect(nkk * 4), o_match = sect((size_t)nq * 4), o_oa = sect(nkk * 4), o_ob = sect(nkk * 4), o_cnt = sect(16);
+    const size_t o_taken = sect(nkk * 4), o_match = sect((size_t)nq * 4), o_oa = sect(nkk * 4), o_ob = sect(nkk * 4), o_cnt = sect(32);
     int rc;
     if ((rc = m->misc.reserve(off))) return rc;
     uint8_t* base = m->misc.as<uint8_t>();
@@ -1004,8 +1032,8 @@ int uvip_search_lists(uvip_matcher* m, int mode, int th_dist, float ratio, const
     c.sp.mode = mode; c.sp.th_dist = th_dist; c.sp.ratio = ratio;
     c.qdesc = base + o_qd; c.kdesc = base + o_kd;
     c.cand_start = (const int32_t*)(base + o_cs); c.cand_idx = (const int32_t*)(base + o_ci);
-    k_search_window<<<1, 1024, 0, st>>>(c, nq, nk, (int32_t*)(base + o_taken), (int32_t*)(base + o_match),
-                                         (int*)(base + o_oa), (int*)(base + o_ob), (int*)(base + o_cnt), nullptr, nullptr, 0, 0);
+    UVIP_CUDA(launch_search(st, 1, c, nq, nk, (int32_t*)(base + o_taken), (int32_t*)(base + o_match), (int*)(base + o_oa), (int*)(base + o_ob),
+                            (int*)(base + o_cnt), nullptr, nullptr, 0, 0, (int*)(base + o_cnt) + 4));
     m->launches++;
     UVIP_CUDA(cudaGetLastError());
     int counts[2] = {0, 0};
@@ -1043,7 +1071,7 @@ int uvip_search_frame(uvip_matcher* m, const uvip_search_params* sp,
     const size_t o_qmin = sect((size_t)nq * 4), o_qmax = sect((size_t)nq * 4), o_qd = sect((size_t)nq * 32);
     const size_t o_kx = sect(nkk * 4), o_ky = sect(nkk * 4), o_oct = sect(nkk * 4), o_kd = sect(nkk * 32), o_taken = sect(nkk * 4);
     const size_t up_bytes = off;
-    const size_t o_match = sect((size_t)nq * 4), o_cnt = sect(16);
+    const size_t o_match = sect((size_t)nq * 4), o_cnt = sect(32);
     const size_t down_bytes = off - o_taken;
     const size_t o_cs = sect((size_t)(ncell + 1) * 4), o_ci = sect(nkk * 4), o_cof = sect(nkk * 4), o_oa = sect(nkk * 4), o_ob = sect(nkk * 4);
     int rc;
@@ -1072,8 +1100,8 @@ int uvip_search_frame(uvip_matcher* m, const uvip_search_params* sp,
     c.qminL = (const int32_t*)(base + o_qmin); c.qmaxL = (const int32_t*)(base + o_qmax); c.qdesc = base + o_qd;
     c.kx = (const float*)(base + o_kx); c.ky = (const float*)(base + o_ky); c.octave = (const int32_t*)(base + o_oct);
     c.kdesc = base + o_kd; c.cell_start = (const int32_t*)(base + o_cs); c.cell_items = (const int32_t*)(base + o_ci);
-    k_search_window<<<1, 1024, 0, st>>>(c, nq, nk, (int32_t*)(base + o_taken), (int32_t*)(base + o_match),
-                                         (int*)(base + o_oa), (int*)(base + o_ob), (int*)(base + o_cnt), nullptr, nullptr, 0, 0);
+    UVIP_CUDA(launch_search(st, 1, c, nq, nk, (int32_t*)(base + o_taken), (int32_t*)(base + o_match), (int*)(base + o_oa), (int*)(base + o_ob),
+                            (int*)(base + o_cnt), nullptr, nullptr, 0, 0, (int*)(base + o_cnt) + 4));
     m->launches += 2;
     UVIP_CUDA(cudaGetLastError());
     UVIP_CUDA(cudaMemcpyAsync(hs + o_taken, base + o_taken, down_bytes, cudaMemcpyDeviceToHost, st));      // taken | match | counts
@@ -1104,7 +1132,7 @@ int uvip_search_lists_epipolar(uvip_matcher* m, int th_dist, const uint8_t* qdes
     const size_t nkk = nk > 0 ? nk : 1;
     const size_t o_qd = sect((size_t)nq * 32), o_ql = sect((size_t)nq * 16), o_kd = sect(nkk * 32), o_kx = sect(nkk * 4), o_ky = sect(nkk * 4), o_kt = sect(nkk * 8);
     const size_t o_cs = sect((size_t)(nq + 1) * 4), o_ci = sect((size_t)(ncand > 0 ? ncand : 1) * 4);
-    const size_t o_taken = sect(nkk * 4), o_match = sect((size_t)nq * 4), o_oa = sect(nkk * 4), o_ob = sect(nkk * 4), o_cnt = sect(16);
+    const size_t o_taken = sect(nkk * 4), o_match = sect((size_t)nq * 4), o_oa = sect(nkk * 4), o_ob = sect(nkk * 4), o_cnt = sect(32);
     int rc;
     if ((rc = m->misc.reserve(off))) return rc;
     uint8_t* base = m->misc.as<uint8_t>();
@@ -1117,8 +1145,8 @@ int uvip_search_lists_epipolar(uvip_matcher* m, int th_dist, const uint8_t* qdes
     c.sp.mode = 5; c.sp.th_dist = th_dist;
     c.qdesc = base + o_qd; c.qline = (const float*)(base + o_ql); c.kdesc = base + o_kd; c.kx = (const float*)(base + o_kx); c.ky = (const float*)(base + o_ky);
     c.kthr = (const double*)(base + o_kt); c.cand_start = (const int32_t*)(base + o_cs); c.cand_idx = (const int32_t*)(base + o_ci);
-    k_search_window<<<1, 1024, 0, st>>>(c, nq, nk, (int32_t*)(base + o_taken), (int32_t*)(base + o_match),
-                                         (int*)(base + o_oa), (int*)(base + o_ob), (int*)(base + o_cnt), nullptr, nullptr, 0, 0);
+    UVIP_CUDA(launch_search(st, 1, c, nq, nk, (int32_t*)(base + o_taken), (int32_t*)(base + o_match), (int*)(base + o_oa), (int*)(base + o_ob),
+                            (int*)(base + o_cnt), nullptr, nullptr, 0, 0, (int*)(base + o_cnt) + 4));
     m->launches++;
     UVIP_CUDA(cudaGetLastError());
     int counts[2] = {0, 0};
@@ -1155,7 +1183,7 @@ int uvip_search_window_batch_device(uvip_matcher* m, const uvip_search_params* s
     const size_t nk_all = (size_t)nframes * k_stride;
     if ((rc = m->misc2.reserve((size_t)nframes * (ncell + 1) * 4))) return rc;      // cell_start
     if ((rc = m->misc3.reserve(nk_all * 4 * 2))) return rc;                         // cell_items, cell_of
-    if ((rc = m->misc4.reserve(nk_all * 4 * 2))) return rc;                         // owner tables A, B
+    if ((rc = m->misc4.reserve(nk_all * 4 * 2 + (size_t)nframes * 16))) return rc;   // owner tables A, B, round flags
     int32_t* cs = m->misc2.as<int32_t>();
     int32_t* ci = m->misc3.as<int32_t>();
     int32_t* cof = ci + nk_all;
@@ -1166,8 +1194,8 @@ int uvip_search_window_batch_device(uvip_matcher* m, const uvip_search_params* s
     c.sp = *sp;
     c.qu = d_qu; c.qv = d_qv; c.qr = d_qr; c.qminL = d_qmin_level; c.qmaxL = d_qmax_level; c.qdesc = d_qdesc;
     c.kx = d_kx; c.ky = d_ky; c.octave = d_octave; c.kdesc = d_kdesc; c.cell_start = cs; c.cell_items = ci;
-    k_search_window<<<nframes, 1024, 0, st>>>(c, 0, 0, d_taken, d_match, m->misc4.as<int>(), m->misc4.as<int>() + nk_all, d_counts,
-                                               d_nq, d_nk, q_stride, k_stride);
+    UVIP_CUDA(launch_search(st, nframes, c, 0, 0, d_taken, d_match, m->misc4.as<int>(), m->misc4.as<int>() + nk_all, d_counts, d_nq, d_nk, q_stride, k_stride,
+                            m->misc4.as<int>() + 2 * nk_all));
     m->launches += 2;
     UVIP_CUDA(cudaGetLastError());
     return UVIP_OK;
