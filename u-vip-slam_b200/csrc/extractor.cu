@@ -119,13 +119,16 @@ k_import(const uint8_t* __restrict__ frames, int stride, size_t frame_pitch, int
 
 // --------------------------------------------------------------------------------------------------------
 // K1b: level l from level l-1, cv::resize INTER_LINEAR 8-bit fixed point (11-bit coefficients), cascaded
-// (src/ORBextractor.cc:982).  One CTA per 128x64 output tile; the source region arrives as one TMA box.  A thread
-// owns 4 output columns (source offsets and coefficient pairs live in registers) and walks down 8 rows; the
+// (src/ORBextractor.cc:982).  One CTA per 128x96 output tile; the source region arrives as one TMA box.  A thread
+// owns 4 output columns (source offsets and coefficient pairs live in registers) and walks down 12 rows; the
 // horizontal pass of a source row is one IDP.2A per pixel on a funnel-shifted word and is reused by the next output
 // row whenever that row's upper source row is this row's lower one (5 rows out of 6 at scale 1.2).
 // tables (host-built, per level): xofs[w] int32, xcoef[w] {a0,a1} int16x2, yofs[h], ycoef[h]
 // --------------------------------------------------------------------------------------------------------
-constexpr int RS_W = 128, RS_H = 64, RS_R = 8;
+#ifndef RS_R_
+#define RS_R_ 12
+#endif
+constexpr int RS_W = 128, RS_R = RS_R_, RS_H = 8 * RS_R;
 
 __global__ void __launch_bounds__(256)
 k_resize(const CUtensorMap* __restrict__ tmaps, uint8_t* __restrict__ pyr, const int* __restrict__ tabs, int level, const __grid_constant__ Plan P)
@@ -802,11 +805,15 @@ k_quadtree(const unsigned* __restrict__ cand, const int* __restrict__ cand_count
 // K6: GaussianBlur 7x7 sigma 2, fixed point [18,34,48,56,48,34,18]/256 per axis, out = (sum + 2^15) >> 16
 // (SURVEY A.6 variant A).  The blurred plane keeps the layout of the pyramid plane; its 4-px border ring holds the
 // UNBLURRED reflect-101 border, which is what the reference's in-place ROI blur leaves there.
-// One CTA per 128x64 tile: the tile + halo arrives as one TMA box; each thread owns 4 adjacent columns and walks
-// down 8 rows with a 7-row register window of horizontal sums (2 IDP4A per pixel), so the vertical pass never
+// One CTA per 128x128 tile: the tile + halo arrives as one TMA box; each thread owns 4 adjacent columns and walks
+// down 16 rows (measured: 8 rows 0.290 ms, 16 rows 0.256 ms per 256 frames — the 6 halo rows of the horizontal pass are
+// amortised over twice as many outputs) with a 7-row register window of horizontal sums (2 IDP4A per pixel), so the vertical pass never
 // touches shared memory.  The last tile entry of every level copies the border ring.
 // --------------------------------------------------------------------------------------------------------
-constexpr int BL_W = 128, BL_H = 64, BL_R = 8;          // tile, rows per warp
+#ifndef BL_R_
+#define BL_R_ 16
+#endif
+constexpr int BL_W = 128, BL_R = BL_R_, BL_H = 8 * BL_R;   // tile, rows per warp
 constexpr int BL_BOXW = BL_W + 32, BL_BOXH = BL_H + 6;  // TMA box: 16 B aligned start, 16 px slack left and right
 
 __global__ void __launch_bounds__(256)
