@@ -170,6 +170,8 @@ k_resize(const CUtensorMap* __restrict__ tmaps, uint8_t* __restrict__ pyr, const
     uint8_t* inner = pyr + (size_t)f * P.frame_bytes + D.poff + (size_t)EDGE * D.pstride + EDGE;
     if (live) {
     int prev_sy = -100, h1[4] = {0, 0, 0, 0};
+    uint8_t* dst = inner + (size_t)yw * D.pstride + x;          // one row down per iteration
+    const bool fullw = x + 3 < D.w;
 #pragma unroll 2
     for (int j = 0; j < RS_R; j++) {
         const int y = yw + j;
@@ -194,9 +196,9 @@ k_resize(const CUtensorMap* __restrict__ tmaps, uint8_t* __restrict__ pyr, const
             const int v = (((b0 * (h0[k] >> 4)) >> 16) + ((b1 * (h1[k] >> 4)) >> 16) + 2) >> 2;
             o |= (unsigned)v << (8 * k);
         }
-        uint8_t* dst = inner + (size_t)y * D.pstride + x;
-        if (x + 3 < D.w) *reinterpret_cast<unsigned*>(dst) = o;
+        if (fullw) *reinterpret_cast<unsigned*>(dst) = o;
         else for (int k = 0; k < 4; k++) if (x + k < D.w) dst[k] = (uint8_t)(o >> (8 * k));
+        dst += D.pstride;
     }
     }
     // reflect-101 ring: every ring pixel whose source lies in this tile, after the tile is complete
@@ -860,6 +862,9 @@ k_blur(const CUtensorMap* __restrict__ tmaps, const uint8_t* __restrict__ pyr, u
     const unsigned K1 = 48u | (34u << 8) | (18u << 16);                   // taps for bytes x+1..x+3
     const unsigned* S = s_in + (BL_R * warp) * (BL_BOXW / 4) + 4 + lane;  // row yw-3, centre word
     int h[7][4];
+    uint8_t* dst = out + (ptrdiff_t)yw * L.pstride + x;      // walks down one row per output: no per-row 64-bit address arithmetic
+    const int nrow = min(BL_R, L.h - yw);                  // rows of this warp inside the image (>= 1)
+    const bool full = x + 3 < L.w;
 #pragma unroll
     for (int r = 0; r < BL_R + 6; r++) {
         const unsigned l = S[r * (BL_BOXW / 4) - 1], m = S[r * (BL_BOXW / 4)], n = S[r * (BL_BOXW / 4) + 1];
@@ -870,8 +875,7 @@ k_blur(const CUtensorMap* __restrict__ tmaps, const uint8_t* __restrict__ pyr, u
         hr[3] = __dp4a(m, K0, __dp4a(n, K1, 0u));
         if (r >= 6) {
             const int j = r - 6;                          // output row yw + j uses window rows j..j+6
-            const int y = yw + j;
-            if (y < L.h) {
+            if (j < nrow) {
                 unsigned o = 0;
 #pragma unroll
                 for (int k = 0; k < 4; k++) {
@@ -879,9 +883,9 @@ k_blur(const CUtensorMap* __restrict__ tmaps, const uint8_t* __restrict__ pyr, u
                                   48 * (h[(j + 2) % 7][k] + h[(j + 4) % 7][k]) + 56 * h[(j + 3) % 7][k];
                     o |= (unsigned)((a + 32768) >> 16) << (8 * k);
                 }
-                uint8_t* dst = out + (ptrdiff_t)y * L.pstride + x;
-                if (x + 3 < L.w) *reinterpret_cast<unsigned*>(dst) = o;
+                if (full) *reinterpret_cast<unsigned*>(dst) = o;
                 else for (int k = 0; k < 4; k++) if (x + k < L.w) dst[k] = (uint8_t)(o >> (8 * k));
+                dst += L.pstride;
             }
         }
     }
