@@ -254,6 +254,15 @@ int   uvip_search_lists(uvip_matcher* m, int mode, int th_dist, float ratio, con
 int   uvip_distinctive_descriptors(uvip_matcher* m, const uint8_t* desc, const int32_t* start, int npoints,
                                    int32_t* best_idx, int32_t* best_median);
 /* ORBmatcher::RadiusByViewingCos (src/ORBmatcher.cc:127-133) */
+/* haloc hash (next row N4, second half): haloc::Hash::getHash (src/hash.cpp:57-85; called at src/KeyFrame.cc:322,328 and
+ * src/LoopClosing.cc:136) for nsets descriptor sets, rows start[s]..start[s+1]-1 of desc (CSR).  proj = the caller's num_proj
+ * projection vectors of proj_len floats (the reference's r_, drawn from rand() seeded with time(NULL), :95-147 — which is why
+ * they are an input here); hash = nsets x (num_proj * 32) floats, products and running sums in float in row order, exactly
+ * as :70-79.  uvip_haloc_match = haloc::Hash::match (:190-206) of one query against n stored hashes
+ * (KeyFrameDatabase::DetectLoopCandidatesHaloc, src/KeyFrameDatabase.cc:98-118). */
+int   uvip_haloc_hash(uvip_matcher* m, const uint8_t* desc, const int32_t* start, int nsets, const float* proj, int num_proj,
+                      int proj_len, float* hash);
+int   uvip_haloc_match(uvip_matcher* m, const float* query, const float* table, int n, int len, float* score);
 float uvip_radius_by_viewing_cos(float view_cos);
 
 /* ---- next row N2: DBoW2 vocabulary-tree descent ------------------------------------------------------ */

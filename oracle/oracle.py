@@ -315,6 +315,19 @@ def search_lists_epipolar(th_dist, qdesc, qline, cand_start, cand_idx, kdesc, kx
     return n, match, tk
 
 
+def haloc_hash(desc, proj):
+    desc = np.ascontiguousarray(desc, np.uint8).reshape(-1, 32); proj = np.ascontiguousarray(proj, np.float32)
+    out = np.zeros(proj.shape[0] * 32, np.float32)
+    lib().uo_haloc_hash(_p(desc), len(desc), _p(proj), proj.shape[0], proj.shape[1], _p(out))
+    return out
+
+
+def haloc_match(a, b):
+    a = np.ascontiguousarray(a, np.float32); b = np.ascontiguousarray(b, np.float32)
+    L = lib(); L.uo_haloc_match.restype = C.c_float
+    return float(L.uo_haloc_match(_p(a), _p(b), len(a)))
+
+
 def clahe(img, clip_limit=4.0, tiles=(12, 12)):
     img = np.ascontiguousarray(img, np.uint8)
     h, w = img.shape

@@ -1,2 +1,5 @@
-// stand-in for <ros/ros.h>: src/ORBextractor.cc includes it but uses nothing from it
+// stand-in for <ros/ros.h>: the compiled reference files include it for logging / assertions only
+#include <iostream>
+#include <cstdlib>
+#include <cmath>
 #define ROS_ASSERT(x) ((void)0)

@@ -263,3 +263,59 @@ def m8_run(scene_path, out_path, which):
     if r == -1000:
         raise RuntimeError('refm_m8_run: I/O failure')
     return r, read_bundle(out_path)
+
+
+# ------------------------------------------------------------------------------------------------ haloc hash (next row N4)
+HASH_SO = os.path.join(_HERE, '_ref', 'libref_hash.so')
+_HLIB = None
+
+
+def hash_available():
+    return os.path.exists(HASH_SO) or os.path.exists('/root/reference/src/hash.cpp')
+
+
+def hlib():
+    global _HLIB
+    if _HLIB is None:
+        build()
+        _HLIB = C.CDLL(HASH_SO)
+        _HLIB.refh_create.restype = C.c_void_p
+        _HLIB.refh_destroy.argtypes = [C.c_void_p]
+        _HLIB.refh_get_hash.argtypes = [C.c_void_p, C.c_void_p, C.c_int, C.c_void_p]
+        _HLIB.refh_projection_length.argtypes = [C.c_void_p]
+        _HLIB.refh_get_projections.argtypes = [C.c_void_p, C.c_void_p]
+        _HLIB.refh_match.restype = C.c_float
+        _HLIB.refh_match.argtypes = [C.c_void_p, C.c_void_p, C.c_void_p, C.c_int]
+    return _HLIB
+
+
+class HalocHash:
+    """the reference's own haloc::Hash (src/hash.cpp); its time(NULL)-seeded projection vectors are made reproducible by
+    interposing time() inside the library and can be read out with projections()"""
+
+    def __init__(self, num_proj=3):
+        self.num_proj = num_proj
+        self.h = C.c_void_p(hlib().refh_create(num_proj))
+
+    def __del__(self):
+        try:
+            hlib().refh_destroy(self.h)
+        except Exception:
+            pass
+
+    def get_hash(self, desc):
+        desc = np.ascontiguousarray(desc, np.uint8).reshape(-1, 32)
+        out = np.zeros(self.num_proj * 32, np.float32)
+        n = hlib().refh_get_hash(self.h, _p(desc), len(desc), _p(out))
+        assert n == len(out), n
+        return out
+
+    def projections(self):
+        n = hlib().refh_projection_length(self.h)
+        out = np.zeros((self.num_proj, n), np.float32)
+        hlib().refh_get_projections(self.h, _p(out))
+        return out
+
+    def match(self, a, b):
+        a = np.ascontiguousarray(a, np.float32); b = np.ascontiguousarray(b, np.float32)
+        return float(hlib().refh_match(self.h, _p(a), _p(b), len(a)))

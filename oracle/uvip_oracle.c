@@ -971,6 +971,24 @@ int uo_search_lists_epipolar(int th_dist, const uint8_t* qdesc, const float* qli
     return nmatches;
 }
 
+/* haloc::Hash::getHash (hash.cpp:57-85) on one descriptor set and haloc::Hash::match (:190-206) */
+void uo_haloc_hash(const uint8_t* desc, int rows, const float* proj, int num_proj, int proj_len, float* hash)
+{
+    int k = 0;
+    for (int i = 0; i < num_proj; i++)
+        for (int n = 0; n < 32; n++) {
+            float desc_sum = 0.0f;
+            for (int m = 0; m < rows; m++) desc_sum += proj[(size_t)i * proj_len + m] * (float)desc[(size_t)m * 32 + n];
+            hash[k++] = rows > 0 ? desc_sum / (float)rows : 0.0f;
+        }
+}
+float uo_haloc_match(const float* a, const float* b, int n)
+{
+    float sum = 0.0f;
+    for (int i = 0; i < n; i++) sum += fabsf(a[i] - b[i]);
+    return sum;
+}
+
 /* ================================================================ CLAHE (next row N3)
  * cv::createCLAHE(clip, Size(tx,ty))->apply(im, im) as called at Tracking.cc:425-431 (clip 4, 12x12 tiles), restated from
  * OpenCV imgproc/clahe.cpp (8-bit path): pad to a tile multiple with REFLECT_101, per-tile clipped + redistributed

@@ -720,3 +720,45 @@ def test_cuda_harris_responses_equal_reference_dead_path(gpu, synth):
     for l in range(8):
         k = R.dead_path_keypoints(rex, img, l)
         assert np.array_equal(ex.harris_responses(l, k['x'], k['y']), k['response']), l
+
+
+# ---------------------------------------------------------------------------------------------------- next row N4: haloc hash
+needs_href = pytest.mark.skipif(not R.hash_available(), reason='oracle/_ref hash not built and /root/reference absent')
+
+
+def haloc_sets(oracle, synth):
+    sets = [frame_for_matching(oracle, synth, seed=s)[1] for s in (1, 2, 3)]
+    sets.append(sets[0][:1]); sets.append(sets[1][:137])
+    return sets
+
+
+@needs_href
+def test_haloc_hash_and_match_equal_reference(oracle, synth):
+    """haloc::Hash::getHash / match (src/hash.cpp:57-85, :190-206) of the reference's compiled code on its own projection vectors"""
+    rh = R.HalocHash(3)
+    sets = haloc_sets(oracle, synth)
+    ref = [rh.get_hash(d) for d in sets]
+    proj = rh.projections()
+    assert proj.shape == (3, 6000) and abs(float((proj[0].astype(np.float64) ** 2).sum()) - 1.0) < 1e-3      # unit vectors
+    assert abs(float((proj[0].astype(np.float64) * proj[1].astype(np.float64)).sum())) < 1e-3                 # orthogonalised (:112-146)
+    ours = [oracle.haloc_hash(d, proj) for d in sets]
+    for a, b in zip(ours, ref):
+        assert np.array_equal(a, b)
+    for i in range(len(sets)):
+        for j in range(len(sets)):
+            assert oracle.haloc_match(ours[i], ours[j]) == rh.match(ref[i], ref[j])
+
+
+@needs_href
+@pytest.mark.gpu
+def test_cuda_haloc_hash_and_match_equal_reference(gpu, oracle, synth):
+    rh = R.HalocHash(3)
+    sets = haloc_sets(oracle, synth)
+    ref = np.stack([rh.get_hash(d) for d in sets])
+    proj = rh.projections()
+    start = np.zeros(len(sets) + 1, np.int32); start[1:] = np.cumsum([len(d) for d in sets])
+    m = gpu.ORBmatcher(0.6, True)
+    got = m.haloc_hash(np.concatenate(sets), start, proj)
+    assert np.array_equal(got, ref)
+    scores = m.haloc_match(ref[0], ref)
+    assert np.array_equal(scores, np.array([rh.match(ref[0], r) for r in ref], np.float32))

@@ -93,6 +93,8 @@ def lib():
         L.uvip_search_window_batch_device.argtypes = [vp, C.POINTER(SearchParams), i] + [vp] * 7 + [i] + [vp] * 5 + [i] + [vp] * 4
         L.uvip_search_window.argtypes = [vp, C.POINTER(SearchParams), vp, vp, vp, vp, vp, vp, i,
                                          vp, vp, vp, vp, i, vp, vp, vp, vp, C.POINTER(i)]
+        L.uvip_haloc_hash.argtypes = [vp, vp, vp, i, vp, i, i, vp]
+        L.uvip_haloc_match.argtypes = [vp, vp, vp, i, i, vp]
         L.uvip_search_frame.argtypes = [vp, C.POINTER(SearchParams), vp, vp, vp, vp, vp, vp, i, vp, vp, vp, vp, i, vp, vp, C.POINTER(i)]
         L.uvip_search_lists_epipolar.argtypes = [vp, i, vp, vp, i, vp, vp, vp, vp, vp, vp, i, vp, vp, C.POINTER(i)]
         L.uvip_search_lists.argtypes = [vp, i, i, C.c_float, vp, i, vp, vp, vp, i, vp, vp, C.POINTER(i)]

@@ -203,6 +203,33 @@ __global__ void k_knn2_merge(const int32_t* __restrict__ idx_parts, const int32_
     *reinterpret_cast<int2*>(dist2 + 2 * (size_t)qi) = make_int2(d1, d2);
 }
 
+// N4, second half: haloc::Hash::getHash (src/hash.cpp:57-85) for a batch of descriptor sets and haloc::Hash::match (:190-206)
+// of one query hash against a table.  hash[i*32 + n] = (sum_m r_i[m] * (float)desc[m][n]) / rows with the products and
+// the running sum in float, in row order (one thread per output element walks its column); match = sum |a - b| in order.
+__global__ void __launch_bounds__(128)
+k_haloc_hash(const uint8_t* __restrict__ desc, const int32_t* __restrict__ start, const float* __restrict__ proj, int num_proj, int proj_len,
+             float* __restrict__ hash)
+{
+    const int s = blockIdx.x, b = start[s], rows = start[s + 1] - b;
+    for (int o = threadIdx.x; o < num_proj * 32; o += blockDim.x) {
+        const int i = o >> 5, n = o & 31;
+        const float* r = proj + (size_t)i * proj_len;
+        const uint8_t* d = desc + (size_t)b * 32 + n;
+        float sum = 0.0f;
+        for (int m = 0; m < rows; m++) sum = __fadd_rn(sum, __fmul_rn(__ldg(r + m), (float)d[(size_t)m * 32]));
+        hash[(size_t)s * num_proj * 32 + o] = rows > 0 ? __fdiv_rn(sum, (float)rows) : 0.0f;
+    }
+}
+__global__ void k_haloc_match(const float* __restrict__ query, const float* __restrict__ table, int n, int len, float* __restrict__ score)
+{
+    const int t = blockIdx.x * blockDim.x + threadIdx.x;
+    if (t >= n) return;
+    const float* h = table + (size_t)t * len;
+    float sum = 0.0f;
+    for (int i = 0; i < len; i++) sum = __fadd_rn(sum, fabsf(__fsub_rn(query[i], h[i])));
+    score[t] = sum;
+}
+
 // M1: DescriptorDistance for n row pairs
 __global__ void k_descriptor_distance(const uint8_t* __restrict__ a, const uint8_t* __restrict__ b, int n, int32_t* __restrict__ out)
 {
@@ -1110,6 +1137,62 @@ int uvip_search_frame(uvip_matcher* m, const uvip_search_params* sp,
     if (nk) memcpy(taken, hs + o_taken, (size_t)nk * 4);
     int counts[2]; memcpy(counts, hs + o_cnt, 8);
     if (nmatches) *nmatches = counts[0];
+    return UVIP_OK;
+}
+
+// haloc::Hash::getHash for nsets descriptor sets (rows start[s]..start[s+1]-1 of desc); proj = the caller's num_proj random
+// projection vectors of proj_len floats each (the reference draws them from rand() seeded with time(NULL), src/hash.cpp:95)
+int uvip_haloc_hash(uvip_matcher* m, const uint8_t* desc, const int32_t* start, int nsets, const float* proj, int num_proj, int proj_len, float* hash)
+{
+    UVIP_CHECK_ARG(m && nsets >= 0 && num_proj > 0 && proj_len > 0);
+    if (nsets == 0) return UVIP_OK;
+    UVIP_CHECK_ARG(start && proj && hash);
+    const int nrows = start[nsets];
+    UVIP_CHECK_ARG(nrows >= 0 && (nrows == 0 || desc));
+    for (int s2 = 0; s2 < nsets; s2++) UVIP_CHECK_ARG(start[s2 + 1] >= start[s2] && start[s2 + 1] - start[s2] <= proj_len);
+    std::lock_guard<std::mutex> lk(m->mu);
+    DeviceGuard g(m->device);
+    size_t off = 0;
+    auto sect = [&](size_t bytes) { size_t o = off; off = align_up(off + bytes, 32); return o; };
+    const size_t o_d = sect((size_t)(nrows > 0 ? nrows : 1) * 32), o_s = sect((size_t)(nsets + 1) * 4), o_p = sect((size_t)num_proj * proj_len * 4);
+    const size_t o_h = sect((size_t)nsets * num_proj * 32 * 4);
+    int rc;
+    if ((rc = m->misc.reserve(off))) return rc;
+    uint8_t* base = m->misc.as<uint8_t>();
+    cudaStream_t st = m->stream;
+    if (nrows) UVIP_CUDA(cudaMemcpyAsync(base + o_d, desc, (size_t)nrows * 32, cudaMemcpyHostToDevice, st));
+    UVIP_CUDA(cudaMemcpyAsync(base + o_s, start, (size_t)(nsets + 1) * 4, cudaMemcpyHostToDevice, st));
+    UVIP_CUDA(cudaMemcpyAsync(base + o_p, proj, (size_t)num_proj * proj_len * 4, cudaMemcpyHostToDevice, st));
+    k_haloc_hash<<<nsets, 128, 0, st>>>(base + o_d, (const int32_t*)(base + o_s), (const float*)(base + o_p), num_proj, proj_len, (float*)(base + o_h));
+    m->launches++;
+    UVIP_CUDA(cudaGetLastError());
+    UVIP_CUDA(cudaMemcpyAsync(hash, base + o_h, (size_t)nsets * num_proj * 32 * 4, cudaMemcpyDeviceToHost, st));
+    UVIP_CUDA(cudaStreamSynchronize(st));
+    return UVIP_OK;
+}
+
+// haloc::Hash::match of one query hash against n stored hashes of `len` floats (KeyFrameDatabase::DetectLoopCandidatesHaloc)
+int uvip_haloc_match(uvip_matcher* m, const float* query, const float* table, int n, int len, float* score)
+{
+    UVIP_CHECK_ARG(m && n >= 0 && len > 0);
+    if (n == 0) return UVIP_OK;
+    UVIP_CHECK_ARG(query && table && score);
+    std::lock_guard<std::mutex> lk(m->mu);
+    DeviceGuard g(m->device);
+    size_t off = 0;
+    auto sect = [&](size_t bytes) { size_t o = off; off = align_up(off + bytes, 32); return o; };
+    const size_t o_q = sect((size_t)len * 4), o_t = sect((size_t)n * len * 4), o_s = sect((size_t)n * 4);
+    int rc;
+    if ((rc = m->misc.reserve(off))) return rc;
+    uint8_t* base = m->misc.as<uint8_t>();
+    cudaStream_t st = m->stream;
+    UVIP_CUDA(cudaMemcpyAsync(base + o_q, query, (size_t)len * 4, cudaMemcpyHostToDevice, st));
+    UVIP_CUDA(cudaMemcpyAsync(base + o_t, table, (size_t)n * len * 4, cudaMemcpyHostToDevice, st));
+    k_haloc_match<<<div_up(n, 128), 128, 0, st>>>((const float*)(base + o_q), (const float*)(base + o_t), n, len, (float*)(base + o_s));
+    m->launches++;
+    UVIP_CUDA(cudaGetLastError());
+    UVIP_CUDA(cudaMemcpyAsync(score, base + o_s, (size_t)n * 4, cudaMemcpyDeviceToHost, st));
+    UVIP_CUDA(cudaStreamSynchronize(st));
     return UVIP_OK;
 }
 

@@ -272,6 +272,22 @@ class ORBmatcher:
                                       ptr(kx), ptr(ky), ptr(octave), ptr(kdesc), nk, ptr(tk), ptr(match), C.byref(n)))
         return n.value, match, tk
 
+    def haloc_hash(self, desc, start, proj):
+        """haloc::Hash::getHash (src/hash.cpp:57-85) for CSR descriptor sets; proj = (num_proj, proj_len) float32 -> (nsets, num_proj*32)"""
+        desc = np.ascontiguousarray(desc, np.uint8).reshape(-1, 32); start = np.ascontiguousarray(start, np.int32)
+        proj = np.ascontiguousarray(proj, np.float32)
+        nsets = len(start) - 1
+        out = np.zeros((nsets, proj.shape[0] * 32), np.float32)
+        check(lib().uvip_haloc_hash(self.h, ptr(desc), ptr(start), nsets, ptr(proj), proj.shape[0], proj.shape[1], ptr(out)))
+        return out
+
+    def haloc_match(self, query, table):
+        """haloc::Hash::match (src/hash.cpp:190-206) of one hash against a table of hashes"""
+        query = np.ascontiguousarray(query, np.float32); table = np.ascontiguousarray(table, np.float32).reshape(-1, len(query))
+        out = np.zeros(len(table), np.float32)
+        check(lib().uvip_haloc_match(self.h, ptr(query), ptr(table), len(table), len(query), ptr(out)))
+        return out
+
     def projection_radius(self, view_cos, level, scale_factors, th=1.0):
         """r = RadiusByViewingCos(viewCos) [* th] * mvScaleFactors[level]  (src/ORBmatcher.cc:68-76,127-133), float by float"""
         r = np.array([lib().uvip_radius_by_viewing_cos(float(c)) for c in view_cos], np.float32)
