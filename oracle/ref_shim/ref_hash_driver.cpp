@@ -5,6 +5,8 @@
 #include <stdint.h>
 #include <string.h>
 #include <time.h>
+#include "uvip_cv_standin.hpp"  // everything hash.h pulls in, before the access override below
+#include <Eigen/Dense>
 #define private public          // r_ (the projection vectors) is private in include/hash.h
 #include "hash.h"
 #undef private

@@ -13,6 +13,10 @@
 #include <string.h>
 #include <assert.h>
 #include <algorithm>
+#include <fstream>
+#include <iostream>
+#include <sstream>
+#include <string>
 #include <vector>
 #include "../uvip_oracle.h"
 
@@ -311,6 +315,29 @@ struct KeyPointsFilter {
             kps.resize(e - kps.begin());
         }
     }
+};
+
+// cv::FileStorage / cv::FileNode: DBoW2's TemplatedVocabulary has virtual YAML save / load members that must COMPILE
+// (virtual members are instantiated with the class); the tests only use its text loader, so these throw when reached.
+struct FileNode {
+    FileNode operator[](const char*) const { fail(); return FileNode(); }
+    FileNode operator[](const std::string&) const { fail(); return FileNode(); }
+    FileNode operator[](int) const { fail(); return FileNode(); }
+    size_t size() const { fail(); return 0; }
+    operator int() const { fail(); return 0; }
+    operator double() const { fail(); return 0; }
+    operator std::string() const { fail(); return std::string(); }
+    static void fail() { throw std::string("cv::FileStorage is a stand-in: YAML vocabularies are not supported by oracle/ref_shim"); }
+};
+struct FileStorage {
+    enum { READ = 0, WRITE = 1 };
+    FileStorage() {}
+    FileStorage(const char*, int) {}
+    FileStorage(const std::string&, int) {}
+    bool isOpened() const { return false; }
+    FileNode operator[](const char*) const { FileNode::fail(); return FileNode(); }
+    FileNode operator[](const std::string&) const { FileNode::fail(); return FileNode(); }
+    template <class T> FileStorage& operator<<(const T&) { FileNode::fail(); return *this; }
 };
 
 }  // namespace cv

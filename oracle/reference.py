@@ -319,3 +319,58 @@ class HalocHash:
     def match(self, a, b):
         a = np.ascontiguousarray(a, np.float32); b = np.ascontiguousarray(b, np.float32)
         return float(hlib().refh_match(self.h, _p(a), _p(b), len(a)))
+
+
+# ------------------------------------------------------------------------------------------------ DBoW2 (next row N2)
+DBOW_SO = os.path.join(_HERE, '_ref', 'libref_dbow.so')
+_VLIB = None
+
+
+def dbow_available():
+    return os.path.exists(DBOW_SO) or os.path.exists('/root/reference/Thirdparty/DBoW2/DBoW2/TemplatedVocabulary.h')
+
+
+def vlib():
+    global _VLIB
+    if _VLIB is None:
+        build()
+        _VLIB = C.CDLL(DBOW_SO)
+        _VLIB.refv_load.restype = C.c_void_p
+        _VLIB.refv_load.argtypes = [C.c_char_p]
+        _VLIB.refv_destroy.argtypes = [C.c_void_p]
+        _VLIB.refv_size.argtypes = [C.c_void_p]
+    return _VLIB
+
+
+class Vocabulary:
+    """the reference's own ORBVocabulary (DBoW2 TemplatedVocabulary<FORB>) loaded from a text file"""
+
+    def __init__(self, path):
+        h = vlib().refv_load(str(path).encode())
+        if not h:
+            raise RuntimeError('loadFromTextFile failed: %s' % path)
+        self.h = C.c_void_p(h)
+
+    def __del__(self):
+        try:
+            vlib().refv_destroy(self.h)
+        except Exception:
+            pass
+
+    def size(self):
+        return vlib().refv_size(self.h)
+
+    def transform(self, desc, levelsup=4):
+        """-> (BowVector as {word: value}, FeatureVector as {node: [feature indices]})"""
+        desc = np.ascontiguousarray(desc, np.uint8).reshape(-1, 32)
+        n = len(desc)
+        bw = np.zeros(n + 1, np.int32); bv = np.zeros(n + 1, np.float64); fn = np.zeros(n + 1, np.int32); ff = np.zeros(n + 1, np.int32)
+        nb = C.c_int(); nf = C.c_int()
+        rc = vlib().refv_transform(self.h, _p(desc), n, int(levelsup), _p(bw), _p(bv), C.byref(nb), n + 1, _p(fn), _p(ff), C.byref(nf), n + 1)
+        if rc != 0:
+            raise RuntimeError('refv_transform: %d' % rc)
+        bow = {int(w): float(v) for w, v in zip(bw[:nb.value], bv[:nb.value])}
+        fv = {}
+        for node, f in zip(fn[:nf.value], ff[:nf.value]):
+            fv.setdefault(int(node), []).append(int(f))
+        return bow, fv

@@ -762,3 +762,54 @@ def test_cuda_haloc_hash_and_match_equal_reference(gpu, oracle, synth):
     assert np.array_equal(got, ref)
     scores = m.haloc_match(ref[0], ref)
     assert np.array_equal(scores, np.array([rh.match(ref[0], r) for r in ref], np.float32))
+
+
+# ---------------------------------------------------------------------------------------------------- next row N2: DBoW2
+needs_vref = pytest.mark.skipif(not R.dbow_available(), reason='oracle/_ref DBoW2 not built and /root/reference absent')
+
+
+def voc_case(synth, k, L, ragged, seed, n):
+    tree, lines = synth.synthetic_vocabulary(k, L, seed=seed, ragged=ragged)
+    desc = synth.random_descriptors(19 + seed, n)
+    src = np.random.default_rng(2).integers(1, len(tree['word']), n // 2)
+    desc[:n // 2] = synth.flip_bits(tree['desc'][src], 44, np.random.default_rng(3).integers(0, 60, n // 2).tolist())
+    return tree, lines, desc
+
+
+@needs_vref
+@pytest.mark.parametrize('k,L,ragged', [(10, 3, False), (6, 4, True), (10, 5, False)])
+def test_vocabulary_transform_equals_reference_dbow2(pkg, oracle, synth, tmp_path, k, L, ragged):
+    """the reference's own DBoW2 (text loader :1338-1420, transform :1175-1259, L1-normalised TF-IDF) against the oracle descent
+    + the host-side BowVector / FeatureVector bookkeeping of frontend.ORBVocabulary"""
+    tree, lines, desc = voc_case(synth, k, L, ragged, 5 + k, 600)
+    path = tmp_path / 'voc.txt'
+    # no trailing newline: the reference's loader (`while(!f.eof())`, :1376) turns a final empty line into one more child of the
+    # root whose leaf flag is an uninitialised variable — undefined behaviour, not a target (DESIGN.md)
+    path.write_text('\n'.join(lines))
+    rv = R.Vocabulary(path)
+    assert rv.size() == int((tree['word'] >= 0).sum())
+    parsed = pkg.ORBVocabulary.parse_text(str(path))
+    # ragged trees: a descent that ends above level L - levelsup never writes `nid` in the reference (:1230-1253), whose caller
+    # then files the feature under an uninitialised variable (:1152) — undefined behaviour, so only levels every descent reaches
+    for levelsup in ((0, 2, 4, L, L + 3) if not ragged else (L - 1, L, L + 3)):
+        rbow, rfv = rv.transform(desc, levelsup)
+        wid, nid, w = oracle.bow_transform(parsed, desc, levelsup)
+        bow, fv = pkg.ORBVocabulary.accumulate(wid, nid, w, parsed['weighting'], parsed['scoring'])
+        assert sorted(bow) == sorted(rbow) and all(bow[x] == rbow[x] for x in bow), (k, L, levelsup)      # values bit-identical (double)
+        assert {a: list(b) for a, b in fv.items()} == rfv, (k, L, levelsup)
+
+
+@needs_vref
+@pytest.mark.gpu
+def test_cuda_vocabulary_transform_equals_reference_dbow2(gpu, synth, tmp_path):
+    tree, lines, desc = voc_case(synth, 10, 5, False, 15, 3000)
+    path = tmp_path / 'voc.txt'
+    path.write_text('\n'.join(lines))
+    rv = R.Vocabulary(path)
+    voc = gpu.ORBVocabulary(); voc.loadFromTextFile(str(path))
+    for levelsup in (4, 2):
+        bow, fv = voc.transform(desc, levelsup)
+        rbow, rfv = rv.transform(desc, levelsup)
+        assert sorted(bow) == sorted(rbow) and all(bow[x] == rbow[x] for x in bow)
+        assert {a: list(b) for a, b in fv.items()} == rfv
+    voc.close()
