@@ -374,3 +374,23 @@ class Vocabulary:
         for node, f in zip(fn[:nf.value], ff[:nf.value]):
             fv.setdefault(int(node), []).append(int(f))
         return bow, fv
+
+
+# ------------------------------------------------------------------------------------------------ MapPoint (next row N4, first half)
+MAPPOINT_SO = os.path.join(_HERE, '_ref', 'libref_mappoint.so')
+
+
+def mappoint_available():
+    return os.path.exists(MAPPOINT_SO) or os.path.exists('/root/reference/src/MapPoint.cc')
+
+
+def distinctive_descriptors(desc, start):
+    """the reference's real MapPoint::ComputeDistinctiveDescriptors (src/MapPoint.cc:197-270) on ragged observation lists:
+    -> (chosen descriptor per list [n, 32], chosen flag per list)"""
+    build()
+    L = C.CDLL(MAPPOINT_SO)
+    desc = np.ascontiguousarray(desc, np.uint8).reshape(-1, 32); start = np.ascontiguousarray(start, np.int32)
+    n = len(start) - 1
+    out = np.zeros((n, 32), np.uint8); chosen = np.zeros(n, np.int32)
+    L.refp_distinctive_descriptors(_p(desc), _p(start), n, _p(out), _p(chosen))
+    return out, chosen

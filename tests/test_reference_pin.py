@@ -813,3 +813,46 @@ def test_cuda_vocabulary_transform_equals_reference_dbow2(gpu, synth, tmp_path):
         assert sorted(bow) == sorted(rbow) and all(bow[x] == rbow[x] for x in bow)
         assert {a: list(b) for a, b in fv.items()} == rfv
     voc.close()
+
+
+# ---------------------------------------------------------------------------------------------------- next row N4, first half
+needs_pref = pytest.mark.skipif(not R.mappoint_available(), reason='oracle/_ref MapPoint not built and /root/reference absent')
+
+
+def distinctive_case(synth):
+    rng = np.random.default_rng(8)
+    sizes = [0, 1, 2, 3, 4, 5, 7, 8, 9, 16, 33, 64, 100] + rng.integers(1, 40, 120).tolist()
+    start = np.zeros(len(sizes) + 1, np.int32); start[1:] = np.cumsum(sizes)
+    base = synth.random_descriptors(123, len(sizes))
+    rows = []
+    for p, n in enumerate(sizes):                       # observations of one map point: its descriptor with a few bits flipped, some exact duplicates
+        d = np.repeat(base[p:p + 1], n, 0)
+        d = synth.flip_bits(d, 1000 + p, rng.integers(0, 25, n).tolist()) if n else d
+        if n > 3:
+            d[n - 1] = d[0]
+        rows.append(d)
+    return np.concatenate(rows), start, sizes
+
+
+@needs_pref
+def test_distinctive_descriptors_equal_reference_mappoint(oracle, synth):
+    """the reference's REAL MapPoint class (src/MapPoint.cc compiled over stand-in KeyFrame / Map): the descriptor
+    ComputeDistinctiveDescriptors (:197-270) keeps must be the one the oracle's best index names"""
+    desc, start, sizes = distinctive_case(synth)
+    rdesc, chosen = R.distinctive_descriptors(desc, start)
+    best, med = oracle.distinctive_descriptors(desc, start)
+    for p, n in enumerate(sizes):
+        assert chosen[p] == (1 if n else 0)
+        if n:
+            assert np.array_equal(rdesc[p], desc[start[p] + best[p]]), (p, n)
+
+
+@needs_pref
+@pytest.mark.gpu
+def test_cuda_distinctive_descriptors_equal_reference_mappoint(gpu, synth):
+    desc, start, sizes = distinctive_case(synth)
+    rdesc, chosen = R.distinctive_descriptors(desc, start)
+    best, med = gpu.ORBmatcher(0.6, True).distinctive_descriptors(desc, start)
+    for p, n in enumerate(sizes):
+        if n:
+            assert np.array_equal(rdesc[p], desc[start[p] + best[p]]), (p, n)
