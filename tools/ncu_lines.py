@@ -8,10 +8,11 @@ rep, kern = sys.argv[1], sys.argv[2]
 top = int(sys.argv[3]) if len(sys.argv) > 3 else 40
 so = sys.argv[4] if len(sys.argv) > 4 else os.path.join(os.path.dirname(os.path.dirname(os.path.abspath(__file__))),
                                                         'u-vip-slam_b200', 'libuvip_orb.so')
-out = subprocess.run(['ncu', '-i', rep, '--page', 'source', '--csv', '--kernel-name', 'regex:' + kern],
+nth_args = ['--launch-skip', os.environ['NTH'], '--launch-count', '1'] if os.environ.get('NTH') else []       # NTH = which matching launch
+out = subprocess.run(['ncu', '-i', rep, '--page', 'source', '--csv', '--kernel-name', 'regex:' + kern] + nth_args,
                      capture_output=True, text=True).stdout
 rows = list(csv.reader(io.StringIO(out)))
-hdr = None; data = []; nth = int(os.environ.get('NTH', '0')); seen = -1     # NTH = which matching launch (default: the first)
+hdr = None; data = []; nth = 0; seen = -1
 for r in rows:
     if r and r[0] == 'Address' and 'Source' in r:
         seen += 1
