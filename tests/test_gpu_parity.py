@@ -490,3 +490,60 @@ def test_search_by_projection_batch_device(gpu, oracle, synth):
         assert g_counts[f, 0] == on and on > 500, f
         assert np.array_equal(g_match[f, :a], om) and np.array_equal(g_taken[f, :b], otk), f
         assert (g_match[f, a:] == -7).all()                       # nothing written beyond the frame's own queries
+
+
+def test_new_entry_points_edge_cases(gpu, oracle, synth):
+    """empty and degenerate inputs of the entry points added late in round 1: nothing crashes, nothing is written out of bounds,
+    results equal the oracle's on the same degenerate input"""
+    import ctypes as C
+    L = gpu.capi.lib()
+    m = gpu.ORBmatcher(0.8, True)
+    c = synth.projection_case(nk=50, nq=80)
+    r = m.projection_radius(c['view_cos'], c['level'], [1.0, 1.2, 1.44, 1.728, 2.0736, 2.48832, 2.985984, 3.5831808], 1.0)
+    # uvip_search_frame: no queries, no keypoints, all keypoints pre-taken, queries far outside the image
+    n, match, taken = m.search_frame(0, 100, [], [], [], [], [], np.zeros((0, 32), np.uint8), c['kx'], c['ky'], c['octave'], c['kdesc'], c['bounds'])
+    assert n == 0 and len(match) == 0 and (taken == -1).all()
+    n, match, taken = m.search_frame(0, 100, c['u'], c['v'], r, c['level'] - 1, c['level'], c['qdesc'], [], [], [], np.zeros((0, 32), np.uint8), c['bounds'])
+    assert n == 0 and (match == -1).all()
+    n, match, taken = m.search_frame(0, 100, c['u'], c['v'], r, c['level'] - 1, c['level'], c['qdesc'], c['kx'], c['ky'], c['octave'], c['kdesc'], c['bounds'],
+                                     taken=np.full(50, -2, np.int32))
+    assert n == 0 and (match == -1).all() and (taken == -2).all()
+    n, match, taken = m.search_frame(1, 256, c['u'] + 5000, c['v'] - 5000, r, c['level'] - 1, c['level'], c['qdesc'], c['kx'], c['ky'], c['octave'], c['kdesc'],
+                                     c['bounds'])
+    assert n == 0 and (match == -1).all()
+    # one query, one keypoint, identical position: found in every mode
+    for mode in (0, 1, 4):
+        n, match, taken = m.search_frame(mode, 256, c['kx'][:1], c['ky'][:1], [3.0], [-1], [-1], c['kdesc'][:1], c['kx'][:1], c['ky'][:1], c['octave'][:1], c['kdesc'][:1],
+                                         c['bounds'])
+        assert n == 1 and match[0] == 0 and taken[0] == (0 if mode != 4 else -1)
+    # epipolar list search: empty lists, a degenerate line (den == 0), threshold 0
+    qd = c['qdesc'][:4]; kd = c['kdesc'][:6]
+    kthr = np.full(6, 3.84, np.float64)
+    cs = np.array([0, 0, 2, 4, 6], np.int32); ci = np.array([0, 1, 2, 3, 4, 5], np.int32)
+    ql = np.array([[0, 1, -c['ky'][0], 1], [0, 0, 0, 0], [0, 1, -c['ky'][2], 1], [1, 0, -c['kx'][4], 1]], np.float32)
+    for th in (256, 0):
+        on, om, otk = oracle.search_lists_epipolar(th, qd, ql, cs, ci, kd, c['kx'][:6], c['ky'][:6], kthr)
+        match = np.full(4, -7, np.int32); taken = np.full(6, -1, np.int32); nn = C.c_int(-1)
+        gpu.capi.check(L.uvip_search_lists_epipolar(m.h, th, qd.ctypes.data, ql.ctypes.data, 4, cs.ctypes.data, ci.ctypes.data, kd.ctypes.data,
+                                                    np.ascontiguousarray(c['kx'][:6]).ctypes.data, np.ascontiguousarray(c['ky'][:6]).ctypes.data, kthr.ctypes.data, 6,
+                                                    taken.ctypes.data, match.ctypes.data, C.byref(nn)))
+        assert nn.value == on and np.array_equal(match, om) and np.array_equal(taken, otk), th
+    assert om[0] == -1 and om[1] == -1                     # empty list, degenerate line
+    # haloc hash: an empty set among non-empty ones; match against an empty table
+    proj = (np.arange(3 * 64, dtype=np.float32).reshape(3, 64) % 7 - 3) / np.float32(8)
+    start = np.array([0, 0, 5, 5, 9], np.int32)
+    h = m.haloc_hash(c['kdesc'][:9], start, proj)
+    assert (h[0] == 0).all() and (h[2] == 0).all()
+    assert np.array_equal(h[1], oracle.haloc_hash(c['kdesc'][:5], proj)) and np.array_equal(h[3], oracle.haloc_hash(c['kdesc'][5:9], proj))
+    assert len(m.haloc_match(h[1], np.zeros((0, 96), np.float32))) == 0
+    with pytest.raises(gpu.capi.UvipError):               # more rows than projection entries: loud, not truncated
+        m.haloc_hash(c['kdesc'][:9], np.array([0, 9], np.int32), proj[:, :4])
+    # Harris: a point too close to the level's edge is refused, not read out of bounds
+    ex = gpu.ORBextractor(300, 1.2, 4, 0, 20, max_width=320, max_height=240)
+    ex(synth.synth_frame(2, 320, 240))
+    assert len(ex.harris_responses(1, [], [])) == 0
+    with pytest.raises(gpu.capi.UvipError):
+        ex.harris_responses(0, [-1.0], [100.0])               # the 4-px reflect-101 ring covers x >= 0, not x = -1
+    assert np.isfinite(ex.harris_responses(3, [20.0], [20.0])).all()
+    # batched search with zero frames
+    m.search_window_batch_device(0, 100, (0, 752, 0, 480), 0, (0, 0, 0, 0, 0, 0), 0, 1, (0, 0, 0, 0), 0, 1, 0, 0, 0)
