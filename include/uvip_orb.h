@@ -120,6 +120,13 @@ int   uvip_get_level_keypoints(uvip_extractor* ex, int frame, int level,
  * dead detector path ComputeKeyPoints (:536-746); the quota-cell distribution around it is not built. */
 int   uvip_harris_responses(uvip_extractor* ex, int frame, int level, const float* xs, const float* ys, int n, int block_size,
                             float harris_k, float* out);
+/* OPTIONAL mode: the reference's dead detector path ORBextractor::ComputeKeyPoints (src/ORBextractor.cc:536-746, SURVEY 8a row
+ * E8; no caller reaches it in the reference) on the pyramid of a frame of the last extract call: quota cells (:547-561),
+ * cv::FAST per cell + retry at threshold 5 when <= 3 corners (:645-652), HarrisResponses when the extractor was created with
+ * HARRIS_SCORE (:655-659), quota redistribution (:683-709), KeyPointsFilter::retainBest per cell and per level (:718-741),
+ * orientation (:744-745).  kps = [nlevels][cap_per_level] in level coordinates (= allKeypoints[level]).  Which keypoints of
+ * EQUAL response survive a cut is decided by std::nth_element here as in the reference (OpenCV's retainBest calls it). */
+int   uvip_compute_keypoints_quota(uvip_extractor* ex, int frame, uvip_keypoint* kps, int32_t* n_per_level, int cap_per_level);
 /* how many of this library's kernels the handle has launched so far (bench.py's gpu_launches) */
 long long uvip_extractor_launch_count(const uvip_extractor* ex);
 /* per-stage device time (CUDA events recorded between the stage kernels on the launching stream), summed over

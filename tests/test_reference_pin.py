@@ -856,3 +856,27 @@ def test_cuda_distinctive_descriptors_equal_reference_mappoint(gpu, synth):
     for p, n in enumerate(sizes):
         if n:
             assert np.array_equal(rdesc[p], desc[start[p] + best[p]]), (p, n)
+
+
+@needs_ref
+@pytest.mark.gpu
+@pytest.mark.parametrize('score_type,seed,W,H,nf', [(0, 1, 752, 480, 1000), (1, 1, 752, 480, 1000), (0, 1000, 640, 512, 1500), (1, 7, 320, 240, 500)])
+def test_cuda_quota_detector_equals_reference_dead_path(gpu, synth, score_type, seed, W, H, nf):
+    """row E8 as an optional mode: uvip_compute_keypoints_quota against the reference's compiled ComputeKeyPoints
+    (src/ORBextractor.cc:536-746, reached through a subclass): quota cells, FAST + retry at 5, Harris / FAST responses, quota
+    redistribution, retainBest per cell and per level (std::nth_element on both sides), orientation — same keypoints, same order"""
+    img = synth.synth_frame(seed, W, H)
+    ex = gpu.ORBextractor(nf, 1.2, 8, score_type, 20, max_width=W, max_height=H)
+    ex(img)
+    got = ex.compute_keypoints_quota()
+    rex = R.Extractor(nf, 1.2, 8, score_type, 20)
+    total = 0
+    for l in range(8):
+        ref = R.dead_path_keypoints(rex, img, l)
+        assert len(got[l]) == len(ref), (l, len(got[l]), len(ref))
+        for f in ('x', 'y', 'size', 'response', 'octave', 'class_id'):
+            assert np.array_equal(got[l][f], ref[f]), (l, f)
+        assert np.abs(got[l]['angle'] - ref['angle']).max() <= ANGLE_TOL_DEG, l
+        assert np.array_equal(got[l]['angle'], ref['angle']), l
+        total += len(ref)
+    assert total > 0.8 * nf

@@ -77,6 +77,7 @@ def lib():
         L.uvip_extractor_stage_ms.argtypes = [vp, vp, C.POINTER(i)]
         L.uvip_clahe.argtypes = [vp, vp, i, i, i, C.c_double, i, i, vp, i]
         L.uvip_clahe_batch_device.argtypes = [vp, vp, i, i, i, i, sz, C.c_double, i, i, vp, i, sz, vp]
+        L.uvip_compute_keypoints_quota.argtypes = [vp, i, vp, vp, i]
         L.uvip_harris_responses.argtypes = [vp, i, i, vp, vp, i, i, C.c_float, vp]
         L.uvip_matcher_create.argtypes = [i, C.POINTER(vp)]
         L.uvip_matcher_destroy.argtypes = [vp]

@@ -1117,6 +1117,138 @@ k_harris(const uint8_t* __restrict__ pyr, int frame, int level, const float* __r
 }
 
 // --------------------------------------------------------------------------------------------------------
+// E8 (detector half, optional mode): the reference's dead ComputeKeyPoints path (src/ORBextractor.cc:536-746).  Its cells are
+// large quota cells (e.g. 144 x 64 px on level 0), each run through cv::FAST(fastTh, nms) on the cell + 3 px and again at
+// threshold 5 when it yields <= 3 corners.  k_fast_roi does exactly that for one cell per CTA, unoptimised on purpose (no
+// caller reaches this path in the reference): exact score of every pixel (s >= t <=> FAST-9 corner at t), strict 3x3 NMS inside
+// the ROI, survivors written in cv::FAST's row-major order.  The quota logic and KeyPointsFilter::retainBest stay on the host.
+// --------------------------------------------------------------------------------------------------------
+struct RoiCell { int level, x0, y0, w, h; };          // ROI origin in level coordinates (inside the padded plane)
+
+__device__ __forceinline__ int fast_score_exact(const uint8_t* p, int st)
+{
+    const int v = p[0];
+    int r[16] = {p[3 * st], p[3 * st + 1], p[2 * st + 2], p[st + 3], p[3], p[-st + 3], p[-2 * st + 2], p[-3 * st + 1],
+                 p[-3 * st], p[-3 * st - 1], p[-2 * st - 2], p[-st - 3], p[-3], p[st - 3], p[2 * st - 2], p[3 * st - 1]};
+    int A = 0, B = 255;
+#pragma unroll
+    for (int k = 0; k < 16; k++) {
+        int mn = r[k], mx = r[k];
+#pragma unroll
+        for (int j = 1; j < 9; j++) { mn = min(mn, r[(k + j) & 15]); mx = max(mx, r[(k + j) & 15]); }
+        A = max(A, mn); B = min(B, mx);
+    }
+    return max(A - v, v - B) - 1;
+}
+
+__global__ void __launch_bounds__(256)
+k_fast_roi(const uint8_t* __restrict__ pyr, int frame, const RoiCell* __restrict__ cells, int t1, int t2, int cap_cell,
+           unsigned* __restrict__ lists, int* __restrict__ counts, int* __restrict__ status, const __grid_constant__ Plan P)
+{
+    extern __shared__ __align__(16) unsigned char s_roi[];
+    __shared__ int s_rowcnt[512];
+    __shared__ int s_total;
+    const RoiCell c = cells[blockIdx.x];
+    const LevelInfo& L = P.lv[c.level];
+    const int ps = L.pstride, w = c.w, h = c.h, tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+    const uint8_t* img = pyr + (size_t)frame * P.frame_bytes + L.poff + (size_t)(EDGE + c.y0) * ps + (EDGE + c.x0);
+    uint8_t* s_img = s_roi; uint8_t* s_sc = s_roi + (size_t)w * h; uint8_t* s_keep = s_sc + (size_t)w * h;
+    for (int i = tid; i < w * h; i += 256) s_img[i] = img[(size_t)(i / w) * ps + (i % w)];
+    __syncthreads();
+    unsigned* out = lists + (size_t)blockIdx.x * cap_cell;
+    for (int pass = 0; pass < 2; pass++) {
+        const int t = pass ? t2 : t1;
+        for (int i = tid; i < w * h; i += 256) {
+            const int y = i / w, x = i - y * w;
+            int s = 0;
+            if (x >= 3 && x < w - 3 && y >= 3 && y < h - 3) { s = fast_score_exact(s_img + i, w); s = s >= t ? s : 0; }
+            s_sc[i] = (uint8_t)s;
+        }
+        if (tid == 0) s_total = 0;
+        for (int i = tid; i < h; i += 256) s_rowcnt[i] = 0;
+        __syncthreads();
+        for (int i = tid; i < w * h; i += 256) {
+            const int y = i / w, x = i - y * w;
+            const int s = s_sc[i];
+            bool keep = false;
+            if (s > 0 && x >= 3 && x < w - 3 && y >= 3 && y < h - 3)
+                keep = s > s_sc[i - 1] && s > s_sc[i + 1] && s > s_sc[i - w - 1] && s > s_sc[i - w] && s > s_sc[i - w + 1] &&
+                       s > s_sc[i + w - 1] && s > s_sc[i + w] && s > s_sc[i + w + 1];
+            s_keep[i] = keep ? 1 : 0;
+            if (keep) atomicAdd(&s_rowcnt[y], 1);
+        }
+        __syncthreads();
+        if (tid == 0) { int acc = 0; for (int y = 0; y < h; y++) { const int n = s_rowcnt[y]; s_rowcnt[y] = acc; acc += n; } s_total = acc; }
+        __syncthreads();
+        const int total = s_total;
+        if (pass == 0 && total <= 3) { __syncthreads(); continue; }            // cv::FAST again at threshold 5 (:646-652), uniform
+        if (total > cap_cell) { if (tid == 0) { atomicOr(status, 1); counts[blockIdx.x] = 0; } return; }
+        for (int y = warp; y < h; y += 8) {                                    // one warp writes one row, in x order
+            int base = s_rowcnt[y];
+            for (int x0 = 0; x0 < w; x0 += 32) {
+                const int x = x0 + lane;
+                const bool k = x < w && s_keep[y * w + x];
+                const unsigned bal = __ballot_sync(0xFFFFFFFFu, k);
+                if (k) out[base + __popc(bal & ((1u << lane) - 1u))] = (unsigned)x | ((unsigned)y << 12) | ((unsigned)s_sc[y * w + x] << 24);
+                base += __popc(bal);
+            }
+        }
+        if (tid == 0) counts[blockIdx.x] = total;
+        return;
+    }
+}
+
+// HarrisResponses (:80-121) for every entry of the cell lists (cell-relative coordinates), blockSize 7
+__global__ void __launch_bounds__(128)
+k_harris_cells(const uint8_t* __restrict__ pyr, int frame, const RoiCell* __restrict__ cells, int cap_cell, const unsigned* __restrict__ lists,
+               const int* __restrict__ counts, float harris_k, float* __restrict__ resp, const __grid_constant__ Plan P)
+{
+    const RoiCell c = cells[blockIdx.x];
+    const LevelInfo& L = P.lv[c.level];
+    const int ps = L.pstride;
+    const uint8_t* img = pyr + (size_t)frame * P.frame_bytes + L.poff + (size_t)(EDGE + c.y0) * ps + (EDGE + c.x0);
+    const int n = counts[blockIdx.x];
+    float scale = __fmul_rn((float)((1 << 2) * 7), 255.0f);
+    scale = __fdiv_rn(1.0f, scale);
+    const float s4 = __fmul_rn(__fmul_rn(__fmul_rn(scale, scale), scale), scale);
+    for (int i = threadIdx.x; i < n; i += 128) {
+        const unsigned e = lists[(size_t)blockIdx.x * cap_cell + i];
+        const int x0 = (int)(e & 0xFFF) - 3, y0 = (int)((e >> 12) & 0xFFF) - 3;
+        int a = 0, b = 0, cc = 0;
+        for (int dy = 0; dy < 7; dy++)
+            for (int dx = 0; dx < 7; dx++) {
+                const uint8_t* p = img + (ptrdiff_t)(y0 + dy) * ps + (x0 + dx);
+                const int Ix = ((int)p[1] - (int)p[-1]) * 2 + ((int)p[-ps + 1] - (int)p[-ps - 1]) + ((int)p[ps + 1] - (int)p[ps - 1]);
+                const int Iy = ((int)p[ps] - (int)p[-ps]) * 2 + ((int)p[ps - 1] - (int)p[-ps - 1]) + ((int)p[ps + 1] - (int)p[-ps + 1]);
+                a += Ix * Ix; b += Iy * Iy; cc += Ix * Iy;
+            }
+        const float fa = (float)a, fb = (float)b, fc = (float)cc, ab = __fadd_rn(fa, fb);
+        const float v = __fsub_rn(__fsub_rn(__fmul_rn(fa, fb), __fmul_rn(fc, fc)), __fmul_rn(__fmul_rn(harris_k, ab), ab));
+        resp[(size_t)blockIdx.x * cap_cell + i] = __fmul_rn(v, s4);
+    }
+}
+
+// IC_Angle (:125-152) for a list of (level, x, y): one warp per keypoint, as in k_describe
+__global__ void __launch_bounds__(256)
+k_angle_list(const uint8_t* __restrict__ pyr, int frame, const int* __restrict__ lxy, int n, float* __restrict__ angle, const __grid_constant__ Plan P)
+{
+    const int i = blockIdx.x * 8 + (threadIdx.x >> 5), lane = threadIdx.x & 31;
+    if (i >= n) return;
+    const int level = lxy[3 * i], cx = lxy[3 * i + 1], cy = lxy[3 * i + 2];
+    const LevelInfo& L = P.lv[level];
+    const int ps = L.pstride;
+    const int u = lane - HALF_PATCH;
+    const int vm = lane < 31 ? c_umax[u < 0 ? -u : u] : -1;
+    const uint8_t* p = pyr + (size_t)frame * P.frame_bytes + L.poff + (size_t)(EDGE + cy - HALF_PATCH) * ps + (EDGE + cx + u);
+    int colsum = 0, m01 = 0;
+    for (int v = -HALF_PATCH; v <= HALF_PATCH; v++) { const int val = ((v < 0 ? -v : v) <= vm) ? (int)p[0] : 0; colsum += val; m01 += v * val; p += ps; }
+    int m10 = u * colsum;
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) { m10 += __shfl_xor_sync(0xFFFFFFFFu, m10, o); m01 += __shfl_xor_sync(0xFFFFFFFFu, m01, o); }
+    if (lane == 0) angle[i] = fast_atan2_deg((float)m01, (float)m10);
+}
+
+// --------------------------------------------------------------------------------------------------------
 // N3: CLAHE pre-processing, cv::createCLAHE(4, Size(12,12))->apply(im, im) at src/Tracking.cc:425-431,
 // restated from OpenCV imgproc/clahe.cpp (8-bit path).  k_clahe_lut: one CTA per (tile, frame) — shared-memory histogram
 // of the tile (image padded to a tile multiple by reflect-101), clip + redistribute, cumulative LUT.  k_clahe_apply: four
@@ -2139,6 +2271,171 @@ int uvip_harris_responses(uvip_extractor* ex, int frame, int level, const float*
     UVIP_CUDA(cudaGetLastError());
     UVIP_CUDA(cudaMemcpyAsync(out, d + 2 * (size_t)n, (size_t)n * 4, cudaMemcpyDeviceToHost, st));
     UVIP_CUDA(cudaStreamSynchronize(st));
+    return UVIP_OK;
+}
+
+// The reference's dead detector path ComputeKeyPoints (src/ORBextractor.cc:536-746) as an OPTIONAL mode, on the pyramid of a
+// frame of the last extract call: quota cells, cv::FAST per cell (+ retry at 5 when <= 3 corners), HarrisResponses when the
+// extractor was created with HARRIS_SCORE, quota redistribution, KeyPointsFilter::retainBest per cell and per level,
+// orientation.  kps = [nlevels][cap_per_level], level coordinates like allKeypoints[level] of the reference.
+// Detection, scoring and orientation run on the GPU; the quota bookkeeping and retainBest (std::nth_element + std::partition,
+// exactly as OpenCV's KeyPointsFilter) on the host — which of several keypoints with EQUAL response survive a cut is decided
+// by std::nth_element in the reference too, i.e. by the C++ library.
+namespace {
+struct QuotaKP { float x, y, response; };
+void retain_best(std::vector<QuotaKP>& k, int n)            // cv::KeyPointsFilter::retainBest (features2d/keypoint.cpp)
+{
+    if (n >= 0 && k.size() > (size_t)n) {
+        if (n == 0) { k.clear(); return; }
+        std::nth_element(k.begin(), k.begin() + n - 1, k.end(), [](const QuotaKP& a, const QuotaKP& b) { return a.response > b.response; });
+        const float amb = k[(size_t)n - 1].response;
+        auto e = std::partition(k.begin() + n, k.end(), [amb](const QuotaKP& q) { return q.response >= amb; });
+        k.resize((size_t)(e - k.begin()));
+    }
+}
+}
+
+int uvip_compute_keypoints_quota(uvip_extractor* ex, int frame, uvip_keypoint* kps, int32_t* n_per_level, int cap_per_level)
+{
+    UVIP_CHECK_ARG(ex && kps && n_per_level && cap_per_level > 0 && ex->plan.W > 0 && frame >= 0 && frame < ex->last_frames);
+    std::lock_guard<std::mutex> lk(ex->mu);
+    DeviceGuard g(ex->device);
+    const Plan& P = ex->plan;
+    const int nlevels = P.nlevels;
+    const float imageRatio = (float)P.lv[0].w / P.lv[0].h;                             // :541
+    struct LevelCells { int cols, rows, cellW, cellH, nfeaturesCell, first; std::vector<int> iniX, iniY; std::vector<char> skipped; };
+    std::vector<LevelCells> LC((size_t)nlevels);
+    std::vector<RoiCell> cells;
+    size_t max_area = 1;
+    for (int level = 0; level < nlevels; level++) {
+        const LevelInfo& L = P.lv[level];
+        LevelCells& C = LC[(size_t)level];
+        const int nDesired = ex->quota[level];
+        C.cols = (int)sqrtf((float)nDesired / (5 * imageRatio));                     // :547-548
+        C.rows = (int)(imageRatio * C.cols);
+        if (C.cols < 1 || C.rows < 1) { set_last_error("quota detector: level %d has no cell grid (the reference divides by zero here)", level); return UVIP_ERR_UNSUPPORTED; }
+        const int minB = EDGE, maxBX = L.w - EDGE, maxBY = L.h - EDGE, W = maxBX - minB, H = maxBY - minB;
+        C.cellW = (int)ceilf((float)W / C.cols); C.cellH = (int)ceilf((float)H / C.rows);
+        C.nfeaturesCell = (int)ceilf((float)nDesired / (C.rows * C.cols));
+        C.first = (int)cells.size();
+        C.iniX.assign((size_t)C.cols, 0); C.iniY.assign((size_t)C.rows, 0); C.skipped.assign((size_t)C.rows * C.cols, 1);
+        float hY = (float)(C.cellH + 6);
+        for (int i = 0; i < C.rows; i++) {                                           // :574-611
+            const float iniY = (float)(minB + i * C.cellH - 3);
+            C.iniY[(size_t)i] = (int)iniY;
+            if (i == C.rows - 1) { hY = maxBY + 3 - iniY; if (hY <= 0) { for (int j = 0; j < C.cols; j++) cells.push_back(RoiCell{level, 0, 0, 0, 0}); continue; } }
+            float hX = (float)(C.cellW + 6);
+            for (int j = 0; j < C.cols; j++) {
+                float iniX;
+                if (i == 0) { iniX = (float)(minB + j * C.cellW - 3); C.iniX[(size_t)j] = (int)iniX; } else iniX = (float)C.iniX[(size_t)j];
+                if (j == C.cols - 1) { hX = maxBX + 3 - iniX; if (hX <= 0) { cells.push_back(RoiCell{level, 0, 0, 0, 0}); continue; } }
+                RoiCell rc; rc.level = level; rc.x0 = (int)iniX; rc.y0 = (int)iniY; rc.w = (int)(iniX + hX) - (int)iniX; rc.h = (int)(iniY + hY) - (int)iniY;
+                UVIP_CHECK_ARG(rc.w >= 0 && rc.h >= 0 && rc.h <= 512 && rc.w < 4096 && rc.x0 + rc.w <= L.w + 3 && rc.y0 + rc.h <= L.h + 3);
+                C.skipped[(size_t)i * C.cols + j] = 0;
+                cells.push_back(rc);
+                if ((size_t)rc.w * rc.h > max_area) max_area = (size_t)rc.w * rc.h;
+            }
+        }
+    }
+    const int ncells = (int)cells.size(), cap_cell = 4096;
+    const size_t smem = 3 * max_area + 16;
+    if (smem > 200 * 1024) { set_last_error("quota detector: a %zu-pixel cell does not fit shared memory", max_area); return UVIP_ERR_UNSUPPORTED; }
+    int rc;
+    size_t off = 0;
+    auto sect = [&](size_t bytes) { size_t o = off; off = align_up(off + bytes, 256); return o; };
+    const size_t o_cells = sect((size_t)ncells * sizeof(RoiCell)), o_cnt = sect((size_t)ncells * 4), o_list = sect((size_t)ncells * cap_cell * 4),
+                 o_resp = sect((size_t)ncells * cap_cell * 4);
+    if ((rc = ex->clahe_io.reserve(off))) return rc;
+    uint8_t* base = ex->clahe_io.as<uint8_t>();
+    cudaStream_t st = ex->stream;
+    UVIP_CUDA(cudaStreamSynchronize(st));
+    UVIP_CUDA(cudaMemcpyAsync(base + o_cells, cells.data(), (size_t)ncells * sizeof(RoiCell), cudaMemcpyHostToDevice, st));
+    UVIP_CUDA(cudaMemsetAsync(base + o_cnt, 0, (size_t)ncells * 4, st));
+    UVIP_CUDA(cudaMemsetAsync(ex->status.p, 0, sizeof(int), st));
+    UVIP_CUDA(cudaFuncSetAttribute(k_fast_roi, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+    k_fast_roi<<<ncells, 256, smem, st>>>(ex->pyr.as<uint8_t>(), frame, (const RoiCell*)(base + o_cells), ex->prm.fast_th, 5, cap_cell,
+                                          (unsigned*)(base + o_list), (int*)(base + o_cnt), ex->status.as<int>(), P);
+    const bool harris = ex->prm.score_type == 0;                                    // ORBextractor::HARRIS_SCORE (include/ORBextractor.h:49)
+    if (harris)
+        k_harris_cells<<<ncells, 128, 0, st>>>(ex->pyr.as<uint8_t>(), frame, (const RoiCell*)(base + o_cells), cap_cell, (const unsigned*)(base + o_list),
+                                               (const int*)(base + o_cnt), 0.04f, (float*)(base + o_resp), P);
+    ex->launches += harris ? 2 : 1;
+    UVIP_CUDA(cudaGetLastError());
+    std::vector<int> counts((size_t)ncells);
+    UVIP_CUDA(cudaMemcpyAsync(counts.data(), base + o_cnt, (size_t)ncells * 4, cudaMemcpyDeviceToHost, st));
+    if ((rc = read_status(ex, st))) return rc;
+    std::vector<unsigned> lists((size_t)ncells * cap_cell); std::vector<float> resp;
+    UVIP_CUDA(cudaMemcpyAsync(lists.data(), base + o_list, lists.size() * 4, cudaMemcpyDeviceToHost, st));
+    if (harris) { resp.resize(lists.size()); UVIP_CUDA(cudaMemcpyAsync(resp.data(), base + o_resp, resp.size() * 4, cudaMemcpyDeviceToHost, st)); }
+    UVIP_CUDA(cudaStreamSynchronize(st));
+    // ---- host: quotas and retainBest (:653-745)
+    std::vector<std::vector<QuotaKP> > all((size_t)nlevels);
+    for (int level = 0; level < nlevels; level++) {
+        const LevelCells& C = LC[(size_t)level];
+        const int nDesired = ex->quota[level], nCells = C.rows * C.cols;
+        std::vector<std::vector<QuotaKP> > cellK((size_t)nCells);
+        std::vector<int> nToRetain((size_t)nCells, 0), nTotal((size_t)nCells, 0); std::vector<char> bNoMore((size_t)nCells, 0);
+        int nNoMore = 0, nToDistribute = 0;
+        for (int ci = 0; ci < nCells; ci++) {
+            if (C.skipped[(size_t)ci]) continue;                                      // `continue` of :584 / :604: the cell keeps its zeros
+            const int gi = C.first + ci, n = counts[(size_t)gi];
+            std::vector<QuotaKP>& v = cellK[(size_t)ci];
+            v.resize((size_t)n);
+            for (int k = 0; k < n; k++) {
+                const unsigned e = lists[(size_t)gi * cap_cell + k];
+                v[(size_t)k].x = (float)(e & 0xFFF); v[(size_t)k].y = (float)((e >> 12) & 0xFFF);
+                v[(size_t)k].response = harris ? resp[(size_t)gi * cap_cell + k] : (float)(e >> 24);
+            }
+            nTotal[(size_t)ci] = n;
+            if (n > C.nfeaturesCell) { nToRetain[(size_t)ci] = C.nfeaturesCell; bNoMore[(size_t)ci] = 0; }
+            else { nToRetain[(size_t)ci] = n; nToDistribute += C.nfeaturesCell - n; bNoMore[(size_t)ci] = 1; nNoMore++; }
+        }
+        while (nToDistribute > 0 && nNoMore < nCells) {                               // :685-710
+            const int nNew = C.nfeaturesCell + (int)ceilf((float)nToDistribute / (nCells - nNoMore));
+            nToDistribute = 0;
+            for (int ci = 0; ci < nCells; ci++) {
+                if (bNoMore[(size_t)ci]) continue;
+                if (nTotal[(size_t)ci] > nNew) { nToRetain[(size_t)ci] = nNew; bNoMore[(size_t)ci] = 0; }
+                else { nToRetain[(size_t)ci] = nTotal[(size_t)ci]; nToDistribute += nNew - nTotal[(size_t)ci]; bNoMore[(size_t)ci] = 1; nNoMore++; }
+            }
+        }
+        std::vector<QuotaKP>& keypoints = all[(size_t)level];
+        for (int i = 0; i < C.rows; i++)
+            for (int j = 0; j < C.cols; j++) {                                        // :718-735
+                std::vector<QuotaKP>& v = cellK[(size_t)i * C.cols + j];
+                retain_best(v, nToRetain[(size_t)i * C.cols + j]);
+                if ((int)v.size() > nToRetain[(size_t)i * C.cols + j]) v.resize((size_t)nToRetain[(size_t)i * C.cols + j]);
+                for (size_t k = 0; k < v.size(); k++) { v[k].x += (float)C.iniX[(size_t)j]; v[k].y += (float)C.iniY[(size_t)i]; keypoints.push_back(v[k]); }
+            }
+        if ((int)keypoints.size() > nDesired) { retain_best(keypoints, nDesired); keypoints.resize((size_t)nDesired); }     // :737-741
+        if ((int)keypoints.size() > cap_per_level) { set_last_error("level %d: %zu keypoints do not fit cap %d", level, keypoints.size(), cap_per_level); return UVIP_ERR_CAPACITY; }
+    }
+    // ---- orientation (:744-745)
+    std::vector<int> lxy; std::vector<float> angle;
+    for (int level = 0; level < nlevels; level++)
+        for (const QuotaKP& k : all[(size_t)level]) { lxy.push_back(level); lxy.push_back((int)lrintf(k.x)); lxy.push_back((int)lrintf(k.y)); }
+    const int ntot = (int)(lxy.size() / 3);
+    angle.assign((size_t)ntot, 0.f);
+    if (ntot) {
+        if ((rc = ex->clahe_io.reserve((size_t)ntot * 16))) return rc;
+        int* d_lxy = ex->clahe_io.as<int>(); float* d_ang = (float*)(d_lxy + 3 * (size_t)ntot);
+        UVIP_CUDA(cudaMemcpyAsync(d_lxy, lxy.data(), (size_t)ntot * 12, cudaMemcpyHostToDevice, st));
+        k_angle_list<<<div_up(ntot, 8), 256, 0, st>>>(ex->pyr.as<uint8_t>(), frame, d_lxy, ntot, d_ang, P);
+        ex->launches++;
+        UVIP_CUDA(cudaGetLastError());
+        UVIP_CUDA(cudaMemcpyAsync(angle.data(), d_ang, (size_t)ntot * 4, cudaMemcpyDeviceToHost, st));
+        UVIP_CUDA(cudaStreamSynchronize(st));
+    }
+    size_t a = 0;
+    for (int level = 0; level < nlevels; level++) {
+        const float size = (float)(int)(31 * ex->scale[level]);                      // scaledPatchSize (:713)
+        n_per_level[level] = (int)all[(size_t)level].size();
+        for (size_t k = 0; k < all[(size_t)level].size(); k++, a++) {
+            uvip_keypoint& o = kps[(size_t)level * cap_per_level + k];
+            o.x = all[(size_t)level][k].x; o.y = all[(size_t)level][k].y; o.size = size; o.angle = angle[a];
+            o.response = all[(size_t)level][k].response; o.octave = level; o.class_id = -1;
+        }
+    }
     return UVIP_OK;
 }
 

@@ -148,6 +148,14 @@ class ORBextractor:
     def level_keypoints(self, l, frame=0):
         return self._list(lib().uvip_get_level_keypoints, l, frame)
 
+    def compute_keypoints_quota(self, frame=0, cap_per_level=4096):
+        """optional mode: the reference's dead ComputeKeyPoints path (src/ORBextractor.cc:536-746) on the last extracted frame
+        -> list of per-level keypoint arrays (level coordinates)"""
+        nl = self.GetLevels()
+        kps = np.zeros((nl, cap_per_level), KP_DTYPE); n = np.zeros(nl, np.int32)
+        check(lib().uvip_compute_keypoints_quota(self.h, int(frame), ptr(kps), ptr(n), int(cap_per_level)))
+        return [kps[l, :n[l]].copy() for l in range(nl)]
+
     def harris_responses(self, l, xs, ys, block_size=7, k=0.04, frame=0):
         """HarrisResponses (src/ORBextractor.cc:80-121) at points of pyramid level l of the last extracted frame"""
         xs = np.ascontiguousarray(xs, np.float32); ys = np.ascontiguousarray(ys, np.float32)
