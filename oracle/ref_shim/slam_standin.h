@@ -13,6 +13,7 @@
 #include <vector>
 #include "uvip_cv_standin.hpp"
 #include "Thirdparty/DBoW2/DBoW2/FeatureVector.h"
+#include "grid_standin.h"
 
 using namespace std;        // the reference headers rely on it (include/ORBmatcher.h:71 uses an unqualified `pair`)
 
@@ -47,28 +48,6 @@ public:
     bool bad; float minDist, maxDist; int nObs; MapPoint* replaced;
     cv::Mat desc, pos, normal;
     std::map<KeyFrame*, size_t> obs;
-};
-
-// the frame grid shared by the two stand-ins: CSR over cols*rows cells as the oracle builds it
-struct GridStandin {
-    std::vector<float> kx, ky; std::vector<int32_t> octave, cell_start, cell_items;
-    float minX, minY, inv_w, inv_h; int cols, rows;
-    void build(const std::vector<cv::KeyPoint>& k, float mnMinX, float mnMaxX, float mnMinY, float mnMaxY)
-    {
-        cols = FRAME_GRID_COLS; rows = FRAME_GRID_ROWS; minX = mnMinX; minY = mnMinY;
-        inv_w = (float)cols / (mnMaxX - mnMinX); inv_h = (float)rows / (mnMaxY - mnMinY);       // src/FrameKTL.cc:150-151
-        const int n = (int)k.size();
-        kx.resize(n); ky.resize(n); octave.resize(n); cell_start.assign(cols * rows + 1, 0); cell_items.assign(n ? n : 1, 0);
-        for (int i = 0; i < n; i++) { kx[i] = k[i].pt.x; ky[i] = k[i].pt.y; octave[i] = k[i].octave; }
-        uo_grid_build(kx.data(), ky.data(), n, minX, minY, inv_w, inv_h, cols, rows, cell_start.data(), cell_items.data());
-    }
-    std::vector<size_t> area(float x, float y, float r, int minLevel, int maxLevel) const
-    {
-        std::vector<int32_t> out(kx.size() ? kx.size() : 1);
-        const int n = uo_features_in_area(kx.data(), ky.data(), octave.data(), cell_start.data(), cell_items.data(), minX, minY, inv_w, inv_h,
-                                          cols, rows, x, y, r, minLevel, maxLevel, out.data(), (int)out.size());
-        return std::vector<size_t>(out.begin(), out.begin() + n);
-    }
 };
 
 class FrameKTL {

@@ -91,6 +91,8 @@ public:
         return *this;
     }
     static MatZeros zeros(int r, int c, int type) { MatZeros z = {r, c, type}; return z; }
+    static Mat eye(int r, int c, int type) { Mat m(r, c, type); for (int y = 0; y < r; y++) { memset(m.ptr(y), 0, (size_t)c * esz(type)); if (y < c && type == CV_32F) m.at<float>(y, y) = 1.f; } return m; }
+    Mat reshape(int) const { return *this; }      // only named by FrameKTL::ComputeImageBounds' distortion branch, which the tests never take
     // assigning Mat::zeros to a matrix of the same shape clears it in place (cv::Mat::operator=(const MatExpr&) -> create + setTo)
     Mat& operator=(const MatZeros& z) { create(z.rows, z.cols, z.type); for (int y = 0; y < rows; y++) memset(data + (size_t)y * step.v, 0, (size_t)cols * esz(tp)); return *this; }
     void create(int r, int c, int type)
@@ -124,6 +126,7 @@ public:
     template <typename T> const T& at(int i) const { return rows == 1 ? at<T>(0, i) : at<T>(i, 0); }
     Mat clone() const { Mat m(rows, cols, tp); for (int y = 0; y < rows; y++) memcpy(m.ptr(y), ptr(y), (size_t)cols * esz(tp)); return m; }
     void copyTo(Mat& m) const { m.create(rows, cols, tp); for (int y = 0; y < rows; y++) memcpy(m.ptr(y), ptr(y), (size_t)cols * esz(tp)); }
+    void copyTo(const Mat& view) const { assert(view.rows == rows && view.cols == cols && view.tp == tp); for (int y = 0; y < rows; y++) memcpy(const_cast<Mat&>(view).ptr(y), ptr(y), (size_t)cols * esz(tp)); }   // into a temporary ROI view
     // ---- CV_32F algebra (what src/ORBmatcher.cc needs); products and sums in float, left to right, like cv::gemm's
     //      small-matrix path
     inline struct MatT t() const;       // lazy alpha * A^T, see below
@@ -146,7 +149,7 @@ private:
 // cv::Mat products as OpenCV 3.4 evaluates them (core/src/matmul.cpp).  A*B (+C) without transposition and with inner
 // size 2..4 takes gemm's small-matrix path: products and sums in float, left to right, then (float)(t*alpha + c*beta) in
 // double.  Anything with a transposed operand (e.g. -R.t()*t) takes the generic path, which accumulates in double.
-struct MatProd { Mat a, b; inline operator Mat() const; };
+struct MatProd { Mat a, b; inline operator Mat() const; inline MatT t() const; };
 struct MatT { Mat a; double alpha; };
 inline MatT Mat::t() const { assert(tp == CV_32F); MatT e = {*this, 1.0}; return e; }
 inline Mat::Mat(const MatT& e) : data(0), rows(0), cols(0), tp(CV_8UC1), buf(0)
@@ -175,6 +178,7 @@ static inline Mat gemm_small(const Mat& a, const Mat& b, const Mat* c)
     return m;
 }
 inline MatProd::operator Mat() const { return gemm_small(a, b, 0); }
+inline MatT MatProd::t() const { MatT e = {gemm_small(a, b, 0), 1.0}; return e; }
 static inline MatProd operator*(const Mat& a, const Mat& b) { MatProd p = {a, b}; return p; }
 static inline Mat operator+(const MatProd& p, const Mat& c) { return gemm_small(p.a, p.b, &c); }
 static inline MatT operator-(const MatT& e) { MatT r = {e.a, -e.alpha}; return r; }

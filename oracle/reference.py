@@ -394,3 +394,32 @@ def distinctive_descriptors(desc, start):
     out = np.zeros((n, 32), np.uint8); chosen = np.zeros(n, np.int32)
     L.refp_distinctive_descriptors(_p(desc), _p(start), n, _p(out), _p(chosen))
     return out, chosen
+
+
+# ------------------------------------------------------------------------------------------------ mini front-end (real FrameKTL)
+FRONTEND_SO = os.path.join(_HERE, '_ref', 'libref_frontend.so')
+
+
+def frontend_available():
+    return os.path.exists(FRONTEND_SO) or os.path.exists('/root/reference/src/FrameKTL.cc')
+
+
+def search_local_points(kxyoa, kdesc, bounds, intr, nlevels, scale_factor, Tcw, pos, obs_level, ref_Ow, pdesc, th, nnratio, cos_limit=0.5):
+    """the reference's REAL FrameKTL + MapPoint + ORBmatcher replaying Tracking::SearchLocalPoints for one frame
+    -> dict(n, inview, u, v, level, viewcos, owner, cell_start, cell_items)"""
+    build()
+    L = C.CDLL(FRONTEND_SO)
+    kxyoa = np.ascontiguousarray(kxyoa, np.float32); kdesc = np.ascontiguousarray(kdesc, np.uint8)
+    pos = np.ascontiguousarray(pos, np.float32); pdesc = np.ascontiguousarray(pdesc, np.uint8)
+    nk, npnt = len(kxyoa), len(pos)
+    out = dict(inview=np.zeros(npnt, np.int32), u=np.zeros(npnt, np.float32), v=np.zeros(npnt, np.float32), level=np.zeros(npnt, np.int32),
+               viewcos=np.zeros(npnt, np.float32), owner=np.zeros(nk, np.int32), cell_start=np.zeros(64 * 48 + 1, np.int32),
+               cell_items=np.zeros(max(nk, 1), np.int32))
+    L.reff_search_local_points.argtypes = [C.c_int, C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p, C.c_int, C.c_float, C.c_void_p, C.c_int, C.c_void_p,
+                                           C.c_void_p, C.c_void_p, C.c_void_p, C.c_float, C.c_float, C.c_float] + [C.c_void_p] * 8
+    out['n'] = L.reff_search_local_points(nk, _p(kxyoa), _p(kdesc), _p(_i32(bounds)), _p(_f32(intr)), int(nlevels), float(scale_factor), _p(_f32(Tcw)),
+                                          npnt, _p(pos), _p(_i32(obs_level)), _p(_f32(ref_Ow)), _p(pdesc), float(th), float(nnratio), float(cos_limit),
+                                          _p(out['inview']), _p(out['u']), _p(out['v']), _p(out['level']), _p(out['viewcos']), _p(out['owner']),
+                                          _p(out['cell_start']), _p(out['cell_items']))
+    out['cell_items'] = out['cell_items'][:out['cell_start'][-1]].copy()
+    return out

@@ -880,3 +880,90 @@ def test_cuda_quota_detector_equals_reference_dead_path(gpu, synth, score_type, 
         assert np.array_equal(got[l]['angle'], ref['angle']), l
         total += len(ref)
     assert total > 0.8 * nf
+
+
+# ---------------------------------------------------------------------------------------------------- the frame grid, for real
+needs_fref = pytest.mark.skipif(not R.frontend_available(), reason='oracle/_ref mini front-end not built and /root/reference absent')
+
+
+def local_points_scene(oracle, synth, th):
+    f32 = np.float32
+    W, H = 752, 480
+    kps, desc = frame_for_matching(oracle, synth)
+    n = len(kps)
+    # keypoints away from integer grid lines too: undistorted coordinates are not integers in the reference
+    rng = np.random.default_rng(17)
+    kx = (kps['x'] + rng.uniform(-0.49, 0.49, n)).astype(np.float32); ky = (kps['y'] + rng.uniform(-0.49, 0.49, n)).astype(np.float32)
+    kxyoa = np.stack([kx, ky, kps['octave'].astype(np.float32), kps['angle']], 1).astype(np.float32)
+    fx, fy, cx, cy = f32(458.0), f32(457.0), f32(367.0), f32(248.0)
+    c_, s_ = f32(0.99995), f32(0.0099998)
+    T = np.array([[c_, -s_, 0, 0.01], [s_, c_, 0, -0.02], [0, 0, 1, 0.03], [0, 0, 0, 1]], np.float32)
+    R1, t1 = T[:3, :3].astype(np.float64), T[:3, 3].astype(np.float64)
+    O1 = (-(R1.T @ t1)).astype(np.float32)
+    npnt = 3 * n
+    pi = np.arange(npnt); src = pi % n
+    z = (2.0 + (pi % 7) * 0.5)
+    jit = np.stack([((pi * 7) % 5 - 2) * 0.9, ((pi * 3) % 5 - 2) * 0.7], 1)
+    Xc = np.stack([(kx[src] + jit[:, 0] - cx) / fx * z, (ky[src] + jit[:, 1] - cy) / fy * z, z], 1).astype(np.float64)
+    Xw = ((Xc - t1) @ R1).astype(np.float32)
+    Xw[pi % 41 == 0] = (O1 - (Xw[pi % 41 == 0] - O1)).astype(np.float32)                 # behind the camera
+    Xw[pi % 53 == 1] += np.array([40, 0, 0], np.float32)                                 # outside the image
+    ref_Ow = (O1 + np.array([0.3, -0.1, 0.05], np.float32)).astype(np.float32)           # the observing keyframe sits elsewhere
+    obs_level = np.clip(kps['octave'][src] + (pi % 3) - 1, 0, 7).astype(np.int32)
+    pdesc = desc[src].copy()
+    flip = rng.integers(0, 256, (npnt, 16))
+    for j in range(16):
+        sel = rng.random(npnt) < 0.6
+        pdesc[sel, flip[sel, j] >> 3] ^= (1 << (flip[sel, j] & 7)).astype(np.uint8)
+    return dict(W=W, H=H, kxyoa=kxyoa, kdesc=desc, intr=[fx, fy, cx, cy], T=T, pos=Xw, obs_level=obs_level, ref_Ow=ref_Ow, pdesc=pdesc, th=th)
+
+
+def replay_local_points(oracle, S, ref, search):
+    """grid + search of the product / oracle on what the reference's isInFrustum produced"""
+    W, H = S['W'], S['H']
+    sf = scale_factors()
+    inv = np.nonzero(ref['inview'])[0]
+    rad = np.array([oracle.lib().uo_radius_by_viewing_cos(float(c)) for c in ref['viewcos'][inv]], np.float32)
+    if S['th'] != 1.0:
+        rad = rad * np.float32(S['th'])
+    r = (rad * sf[ref['level'][inv]]).astype(np.float32)
+    n, match, taken = search(ref['u'][inv], ref['v'][inv], r, ref['level'][inv] - 1, ref['level'][inv], S['pdesc'][inv])
+    owner = np.where(taken >= 0, inv[np.clip(taken, 0, len(inv) - 1)], -1).astype(np.int32)
+    return n, owner
+
+
+@needs_fref
+@pytest.mark.parametrize('th', [1.0, 3.0])
+def test_frame_grid_and_search_local_points_equal_real_frontend(oracle, synth, th):
+    """FrameKTL::PosInGrid + grid fill (src/FrameKTL.cc:250-264,426-436), GetFeaturesInArea (:359-424), isInFrustum (:299-357) and
+    ORBmatcher::SearchByProjection (:49-125) of the reference's REAL classes compiled together, against the oracle's grid and
+    window search on the same frame"""
+    S = local_points_scene(oracle, synth, th)
+    ref = R.search_local_points(S['kxyoa'], S['kdesc'], [0, S['W'], 0, S['H']], S['intr'], 8, 1.2, S['T'], S['pos'], S['obs_level'], S['ref_Ow'],
+                                S['pdesc'], th, 0.8)
+    assert ref['inview'].sum() > 1500 and (ref['inview'] == 0).sum() > 100
+    kx, ky, octave = S['kxyoa'][:, 0], S['kxyoa'][:, 1], S['kxyoa'][:, 2].astype(np.int32)
+    inv_w = np.float32(64.0) / np.float32(S['W']); inv_h = np.float32(48.0) / np.float32(S['H'])
+    start, items = oracle.grid_build(kx, ky, 0.0, 0.0, float(inv_w), float(inv_h))
+    assert np.array_equal(start, ref['cell_start']) and np.array_equal(items, ref['cell_items'])      # the grid itself, cell by cell
+    search = lambda u, v, r, lo, hi, d: oracle.search_window(0, 100, np.float32(0.8), u, v, r, lo, hi, d, kx, ky, octave, S['kdesc'], start, items,
+                                                             0.0, 0.0, float(inv_w), float(inv_h))
+    n, owner = replay_local_points(oracle, S, ref, search)
+    assert n == ref['n'] and n > 500
+    assert np.array_equal(owner, ref['owner'])
+
+
+@needs_fref
+@pytest.mark.gpu
+@pytest.mark.parametrize('th', [1.0, 3.0])
+def test_cuda_grid_and_search_equal_real_frontend(gpu, oracle, synth, th):
+    S = local_points_scene(oracle, synth, th)
+    ref = R.search_local_points(S['kxyoa'], S['kdesc'], [0, S['W'], 0, S['H']], S['intr'], 8, 1.2, S['T'], S['pos'], S['obs_level'], S['ref_Ow'],
+                                S['pdesc'], th, 0.8)
+    kx, ky, octave = S['kxyoa'][:, 0], S['kxyoa'][:, 1], S['kxyoa'][:, 2].astype(np.int32)
+    m = gpu.ORBmatcher(0.8, True)
+    grid = m.grid_build(kx, ky, (0, S['W'], 0, S['H']))
+    assert np.array_equal(grid['start'], ref['cell_start']) and np.array_equal(grid['items'], ref['cell_items'])
+    search = lambda u, v, r, lo, hi, d: m.search_frame(0, 100, u, v, r, lo, hi, d, kx, ky, octave, S['kdesc'], (0, S['W'], 0, S['H']))
+    n, owner = replay_local_points(oracle, S, ref, search)
+    assert n == ref['n'] and np.array_equal(owner, ref['owner'])
