@@ -216,8 +216,8 @@ k_resize(const CUtensorMap* __restrict__ tmaps, uint8_t* __restrict__ pyr, const
 //       via VABSDIFF4 + a per-byte carry trick; a 9-arc contains one pixel of every opposite pair, so groups where
 //       no pixel passes are dropped (85 % on the benchmark frame).  Survivors are compacted (warp ballot) so that
 //   B2  the groups are tested on dense warps at the 8 even ring positions (ring pixel k of 4 neighbouring pixels is one
-//       funnel-shifted 32-bit word; "brighter than v+t" / "darker than v-t" are 3 ALU ops per word each): a 9-arc
-//       contains 4 consecutive even positions, so pixels without such a run are dropped; the rest are queued
+//       funnel-shifted 32-bit word; |ring - v| > t is one VABSDIFF4 + 3 ALU ops per word): a 9-arc contains 4 consecutive
+//       even positions, so pixels without such a run are dropped; the rest are queued
 //   C   exact score s = max_arc min_k |ring_k - v| - 1 (== OpenCV cornerScore, DPX min3/max3) of every queued pixel;
 //       s >= t  <=>  the pixel is a FAST-9 corner at t, so this is also the exact corner decision; corners are
 //       compacted once more
@@ -227,16 +227,6 @@ k_resize(const CUtensorMap* __restrict__ tmaps, uint8_t* __restrict__ pyr, const
 constexpr int FAST_CW = 4, FAST_CH = 2;      // cells per tile
 constexpr int FAST_WARPS = 8;
 
-__device__ __forceinline__ unsigned swar_gt(unsigned a, unsigned b, unsigned nb7)
-{   // bit 7 of every byte: a > b (unsigned bytes); nb7 = ~b & 0x7f7f7f7f precomputed
-    const unsigned s = (a & 0x7f7f7f7fu) + nb7;
-    return (a & ~b) | (~(a ^ b) & s);
-}
-__device__ __forceinline__ unsigned swar_lt(unsigned a, unsigned b, unsigned b7)
-{   // bit 7 of every byte: a < b; b7 = b & 0x7f7f7f7f precomputed
-    const unsigned s = b7 + (~a & 0x7f7f7f7fu);
-    return (b & ~a) | (~(a ^ b) & s);
-}
 // bit 7 of every byte: a > t for a constant threshold; k7 = (0x7f - (t & 0x7f)) * 0x01010101
 __device__ __forceinline__ unsigned swar_gt_const(unsigned a, unsigned k7, bool t_low)
 {
@@ -258,49 +248,36 @@ __device__ __forceinline__ unsigned fast_pre4(const unsigned* __restrict__ W, in
 }
 
 // B2: candidate flags (bit 7 per byte) of the 4 pixels whose centre word is W[0]; rs = row stride in words.
-// Only the 8 even ring positions are examined: a 9-arc of the 16-ring always contains 4 consecutive even positions, so
-// "4 consecutive even positions all brighter than v+t (or all darker than v-t)" is necessary for a corner.  The exact
+// Only the 8 even ring positions are examined, and without polarity: a 9-arc of the 16-ring always contains 4 consecutive
+// even positions, all on one side of v, so "4 consecutive even positions all differ from v by more than t" is necessary for a
+// corner.  One VABSDIFF4 + 3 ops per ring word; 13.5 % of the benchmark frame's pixels pass (a polarity-aware version of the
+// same test passes 11.9 % at twice the ALU cost: measured 0.846 -> 0.820 ms per 256 frames in favour of this one).  The exact
 // decision is left to the score stage (score >= t  <=>  corner at t), which runs on dense warps of single pixels.
-__device__ __forceinline__ unsigned fast_even8(const unsigned* __restrict__ W, int rs, unsigned t4, unsigned valid)
+__device__ __forceinline__ unsigned fast_even8(const unsigned* __restrict__ W, int rs, unsigned k7, bool t_low, unsigned valid)
 {
     const unsigned v = W[0];
-    const unsigned hi = __vaddus4(v, t4), lo = __vsubus4(v, t4);
-    const unsigned nhi7 = ~hi & 0x7f7f7f7fu, lo7 = lo & 0x7f7f7f7fu;
-    unsigned b[8], d[8];
-#define RING(k, word) do { const unsigned r_ = (word); b[k] = swar_gt(r_, hi, nhi7); d[k] = swar_lt(r_, lo, lo7); } while (0)
-    RING(0, W[3 * rs]);
-    RING(4, W[-3 * rs]);
+    unsigned f[8];
+#define RINGA(k, word) f[k] = swar_gt_const(__vabsdiffu4((word), v), k7, t_low)
+    RINGA(0, W[3 * rs]);
+    RINGA(4, W[-3 * rs]);
     {
         const unsigned l = W[-1], r = W[1];
-        RING(2, __funnelshift_r(v, r, 24));
-        RING(6, __funnelshift_r(l, v, 8));
+        RINGA(2, __funnelshift_r(v, r, 24));
+        RINGA(6, __funnelshift_r(l, v, 8));
     }
-    // two adjacent compass points of one polarity are necessary: (0|8)&(4|12) in ring numbering
-    unsigned pb = (b[0] | b[4]) & (b[2] | b[6]), pd = (d[0] | d[4]) & (d[2] | d[6]);
-    if (((pb | pd) & valid) == 0) return 0;
     {
         const unsigned* p = W + 2 * rs; const unsigned* q = W - 2 * rs;
-        RING(1, __funnelshift_r(p[0], p[1], 16));
-        RING(7, __funnelshift_r(p[-1], p[0], 16));
-        RING(3, __funnelshift_r(q[0], q[1], 16));
-        RING(5, __funnelshift_r(q[-1], q[0], 16));
+        RINGA(1, __funnelshift_r(p[0], p[1], 16));
+        RINGA(7, __funnelshift_r(p[-1], p[0], 16));
+        RINGA(3, __funnelshift_r(q[0], q[1], 16));
+        RINGA(5, __funnelshift_r(q[-1], q[0], 16));
     }
-#undef RING
-    unsigned out = 0;
-    {
-        unsigned p2[8];
+#undef RINGA
+    unsigned p2[8], out = 0;
 #pragma unroll
-        for (int k = 0; k < 8; k++) p2[k] = b[k] & b[(k + 1) & 7];
+    for (int k = 0; k < 8; k++) p2[k] = f[k] & f[(k + 1) & 7];
 #pragma unroll
-        for (int k = 0; k < 8; k++) out |= p2[k] & p2[(k + 2) & 7];
-    }
-    {
-        unsigned p2[8];
-#pragma unroll
-        for (int k = 0; k < 8; k++) p2[k] = d[k] & d[(k + 1) & 7];
-#pragma unroll
-        for (int k = 0; k < 8; k++) out |= p2[k] & p2[(k + 2) & 7];
-    }
+    for (int k = 0; k < 8; k++) out |= p2[k] & p2[(k + 2) & 7];
     return out & valid & 0x80808080u;
 }
 
@@ -402,14 +379,13 @@ k_fast(const CUtensorMap* __restrict__ tmaps, const unsigned* __restrict__ tile_
         }
         __syncwarp();
         // B2: even-position candidate test on the compacted groups; candidate pixels go to pq as (y - Y0) * srow + (x - X0)
-        const unsigned t4 = (unsigned)t * 0x01010101u;
         int npw = 0;
         for (int i0 = 0; i0 < ngw; i0 += 32) {
             const int gi = i0 + lane;
             const int g = gi < ngw ? gq[gi] : 0;
             const int r = __umulhi((unsigned)g, rcpg), c = g - r * ngx;
             const unsigned valid = gi < ngw ? s_colvalid[(r >= hc) ? 1 : 0][c] : 0u;
-            unsigned cf = valid ? fast_even8(s_img + (r + 3) * rsw + (cofs + c + 1), rsw, t4, valid) : 0u;
+            unsigned cf = valid ? fast_even8(s_img + (r + 3) * rsw + (cofs + c + 1), rsw, k7, t_low, valid) : 0u;
             // warp-aggregated append of the candidate pixels (<= 4 per lane): inclusive scan of the per-lane counts
             const int cnt = __popc(cf);
             int incl = cnt;
