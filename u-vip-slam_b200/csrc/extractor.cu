@@ -288,7 +288,6 @@ k_fast(const CUtensorMap* __restrict__ tmaps, const unsigned* __restrict__ tile_
     extern __shared__ __align__(128) unsigned char s_fast[];
     __shared__ __align__(8) uint64_t s_mbar;
     __shared__ unsigned s_colvalid[FAST_CH][64];
-    __shared__ unsigned char s_xcell[FAST_CW * 64 + 8];       // cell column of every pixel column of the tile
     __shared__ int s_surv[FAST_CW * FAST_CH];
     __shared__ unsigned s_rcpg;
 
@@ -316,20 +315,38 @@ k_fast(const CUtensorMap* __restrict__ tmaps, const unsigned* __restrict__ tile_
     const int rsw = irow >> 2;
     const int wc = L.wcell, hc = L.hcell;
     if (tid < FAST_CW * FAST_CH) s_surv[tid] = 0;
-    for (int i = tid; i < X1 - X0; i += 256) s_xcell[i] = (unsigned char)((i >= wc) + (i >= 2 * wc) + (i >= 3 * wc));
     static_assert(FAST_CW == 4 && FAST_CH == 2, "the cell arithmetic below is written for 4 x 2 cells");
     // A: stage the tile with one TMA box load (zero-filled outside the padded plane); the box is the plan's
-    //    largest tile, so every CTA issues the same shape
-    if (tid == 0) { mbar_init(&s_mbar, 1); mbar_fence_init(); }
-    if (tid == 32) s_rcpg = 0xFFFFFFFFu / (unsigned)ngx + 1u;     // one division per CTA, not per thread
-    __syncthreads();
+    //    largest tile, so every CTA issues the same shape.  The issuing thread initialises the barrier itself; the other
+    //    threads only touch it after the CTA barrier below.
     if (tid == 0) {
+        mbar_init(&s_mbar, 1); mbar_fence_init();
         mbar_arrive_expect_tx(&s_mbar, (unsigned)(irow * P.f_irows));
         tma_load_3d(s_img, tmaps + level, ax0 + EDGE, ay0 + EDGE, f, &s_mbar);
     }
+    if (tid == 32) s_rcpg = 0xFFFFFFFFu / (unsigned)ngx + 1u;     // one division per CTA, not per thread
+    // byte masks per (cell row, group column): pixel inside [X0, X1) and its cell active in this pass (pass 0: every cell)
+    auto col_masks = [&](int pass) {
+        if (tid < FAST_CH * 64) {
+            const int ci = tid >> 6, c = tid & 63;
+            unsigned m = 0;
+            if (c < ngx && ci < ncy)
+                for (int bb = 0; bb < 4; bb++) {
+                    const int x = gx0 + 4 * c + bb;
+                    if (x >= X0 && x < X1) {
+                        const int xr = x - X0, cj = (xr >= wc) + (xr >= 2 * wc) + (xr >= 3 * wc);
+                        if (pass == 0 || s_surv[ci * FAST_CW + cj] == 0) m |= 0x80u << (8 * bb);
+                    }
+                }
+            s_colvalid[ci][c] = m;
+        }
+    };
+    col_masks(0);
     // score map: pixel (x, y) of cell (ci, cj) lives at row (y - Y0) + 1 + ci, column (x - X0) + 1 + cj, i.e. cells are
     // separated by one row / column that stays 0, so the cell-local NMS reads its 8 neighbours unconditionally
-    for (int i = tid; i < (srow * P.f_srows) >> 2; i += 256) reinterpret_cast<unsigned*>(s_score)[i] = 0;
+    // (128-bit stores; the last one may run a few bytes into the queues behind the map, which nobody has written yet)
+    for (int i = tid; i < (srow * P.f_srows + 15) >> 4; i += 256) reinterpret_cast<uint4*>(s_score)[i] = make_uint4(0u, 0u, 0u, 0u);
+    __syncthreads();                                       // s_surv, s_rcpg, masks, zeroed map, initialised barrier
     mbar_wait(&s_mbar, 0);
     const int nrows = Y1 - Y0, ngroups = ngx * nrows;
     const unsigned rcpg = s_rcpg;
@@ -341,27 +358,16 @@ k_fast(const CUtensorMap* __restrict__ tmaps, const unsigned* __restrict__ tile_
 
     for (int pass = 0; pass < 2; pass++) {
         const int t = pass ? P.t2 : P.t1;
-        if (pass && P.t2 >= P.t1) break;                   // the retry cannot add anything (uniform)
-        bool mine = false;                                 // is "my" cell (tid < 8) evaluated in this pass?
-        if (tid < FAST_CW * FAST_CH) {
-            const int i = tid / FAST_CW, j = tid % FAST_CW;
-            mine = i < ncy && j < ncx && (pass == 0 || s_surv[tid] == 0);
+        if (pass) {
+            if (P.t2 >= P.t1) break;                       // the retry cannot add anything (uniform)
+            // every thread reads the 8 survivor flags itself (complete: barrier after stage D), so the decision needs no vote
+            bool retry = false;
+#pragma unroll
+            for (int cell = 0; cell < FAST_CW * FAST_CH; cell++) retry |= (cell / FAST_CW) < ncy && (cell % FAST_CW) < ncx && s_surv[cell] == 0;
+            if (!retry) break;                             // uniform
+            col_masks(1);
+            __syncthreads();
         }
-        if (!__syncthreads_or(mine)) break;                // also orders staging / the previous pass (uniform exit)
-        if (tid < FAST_CH * 64) {                           // byte masks per (cell row, group column): inside [X0,X1) and cell active
-            const int ci = tid >> 6, c = tid & 63;
-            unsigned m = 0;
-            if (c < ngx && ci < ncy)
-                for (int bb = 0; bb < 4; bb++) {
-                    const int x = gx0 + 4 * c + bb;
-                    if (x >= X0 && x < X1) {
-                        const int cj = s_xcell[x - X0];
-                        if (pass == 0 || s_surv[ci * FAST_CW + cj] == 0) m |= 0x80u << (8 * bb);
-                    }
-                }
-            s_colvalid[ci][c] = m;
-        }
-        __syncthreads();
         // B1: compass pre-test over this warp's groups, survivors compacted into gq
         const bool t_low = t < 128;
         const unsigned k7 = (unsigned)(0x7f - (t & 0x7f)) * 0x01010101u;
@@ -464,33 +470,46 @@ k_fast(const CUtensorMap* __restrict__ tmaps, const unsigned* __restrict__ tile_
         }
         __syncthreads();                                   // every warp's scores are in the map
         // D: strict 3x3 NMS inside the cell; append survivors to the (frame, level) raw-corner list
+        //    Two sweeps over the warp's corner list so that the warp makes ONE reservation in the global list (a global atomic
+        //    per 32 corners kept the warps waiting on its latency): sweep 1 decides NMS and strikes the losers out of the list
+        //    in place, sweep 2 writes the survivors.
         const bool fits = ncw <= P.f_gw;                   // warp-uniform
-        const unsigned short* dq = fits ? gq : pq;
+        unsigned short* dq = fits ? gq : pq;
         const int nd = fits ? ncw : npw;
+        int nkeep = 0;
         for (int i0 = 0; i0 < nd; i0 += 32) {
             const int i = i0 + lane;
             const int pos = i < nd ? dq[i] : 0xFFFF;
-            bool keep = false; unsigned rec = 0; int cell = 0;
+            bool keep = false;
             if (pos != 0xFFFF) {
                 const uint8_t* sp = s_score + pos;
                 const int s = sp[0];
-                keep = s > sp[-1] && s > sp[1] && s > sp[-srow - 1] && s > sp[-srow] && s > sp[-srow + 1] &&
-                       s > sp[srow - 1] && s > sp[srow] && s > sp[srow + 1];
-                const int sy = __umulhi((unsigned)pos, rcps), sx = pos - sy * srow;
-                const int ci = sy > hc + 1, cj = (sx > wc + 1) + (sx > 2 * wc + 2) + (sx > 3 * wc + 3);
-                rec = (unsigned)(X0 + sx - 1 - cj) | ((unsigned)(Y0 + sy - 1 - ci) << 12) | ((unsigned)s << 24);
-                cell = ci * FAST_CW + cj;
+                const int m = max(max(max((int)sp[-1], (int)sp[1]), max((int)sp[-srow - 1], (int)sp[-srow])),
+                                  max(max((int)sp[-srow + 1], (int)sp[srow - 1]), max((int)sp[srow], (int)sp[srow + 1])));
+                keep = s > m;                              // strict maximum of its 8 neighbours, no short-circuit branches
+                if (!keep) dq[i] = 0xFFFF;
             }
-            const unsigned bal = __ballot_sync(0xFFFFFFFFu, keep);
-            if (bal) {
-                int base = 0;
-                if (lane == 0) base = atomicAdd(gcount, __popc(bal));
-                base = __shfl_sync(0xFFFFFFFFu, base, 0);
+            nkeep += __popc(__ballot_sync(0xFFFFFFFFu, keep));
+        }
+        if (nkeep) {                                       // warp-uniform
+            int base = 0;
+            if (lane == 0) base = atomicAdd(gcount, nkeep);
+            base = __shfl_sync(0xFFFFFFFFu, base, 0);
+            __syncwarp();
+            for (int i0 = 0; i0 < nd; i0 += 32) {
+                const int i = i0 + lane;
+                const int pos = i < nd ? dq[i] : 0xFFFF;
+                const bool keep = pos != 0xFFFF;
+                const unsigned bal = __ballot_sync(0xFFFFFFFFu, keep);
                 if (keep) {
+                    const int sy = __umulhi((unsigned)pos, rcps), sx = pos - sy * srow;
+                    const int ci = sy > hc + 1, cj = (sx > wc + 1) + (sx > 2 * wc + 2) + (sx > 3 * wc + 3);
+                    const unsigned rec = (unsigned)(X0 + sx - 1 - cj) | ((unsigned)(Y0 + sy - 1 - ci) << 12) | ((unsigned)s_score[pos] << 24);
                     const int o = base + __popc(bal & ltmask);
                     if (o < L.raw_cap) gdst[o] = rec; else atomicOr(status, 1);
-                    s_surv[cell] = 1;                      // only "any survivor" matters: plain store, every writer stores 1
+                    s_surv[ci * FAST_CW + cj] = 1;         // only "any survivor" matters: plain store, every writer stores 1
                 }
+                base += __popc(bal);
             }
         }
         __syncthreads();                                   // s_surv complete before the retry pass reads it
