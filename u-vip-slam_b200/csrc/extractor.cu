@@ -392,18 +392,16 @@ k_fast(const CUtensorMap* __restrict__ tmaps, const unsigned* __restrict__ tile_
             const int r = __umulhi((unsigned)g, rcpg), c = g - r * ngx;
             const unsigned valid = gi < ngw ? s_colvalid[(r >= hc) ? 1 : 0][c] : 0u;
             unsigned cf = valid ? fast_even8(s_img + (r + 3) * rsw + (cofs + c + 1), rsw, k7, t_low, valid) : 0u;
-            // warp-aggregated append of the candidate pixels (<= 4 per lane): inclusive scan of the per-lane counts
-            const int cnt = __popc(cf);
-            int incl = cnt;
-#pragma unroll
-            for (int o = 1; o < 32; o <<= 1) { const int v = __shfl_up_sync(0xFFFFFFFFu, incl, o); if (lane >= o) incl += v; }
-            const int total = __shfl_sync(0xFFFFFFFFu, incl, 31);
-            int base = npw + incl - cnt;
+            // warp-aggregated append of the candidate pixels (<= 4 per lane), one ballot per byte position: no scan, no
+            // data-dependent loop (the order inside pq does not matter)
             const int q0 = r * srow + (gx0 + 4 * c - X0);
-            while (cf) {
-                const int bb = (__ffs(cf) - 1) >> 3;
-                cf &= cf - 1;
-                pq[base++] = (unsigned short)(q0 + bb);
+            int total = 0;
+#pragma unroll
+            for (int bb = 0; bb < 4; bb++) {
+                const bool on = (cf >> (8 * bb + 7)) & 1u;
+                const unsigned bal = __ballot_sync(0xFFFFFFFFu, on);
+                if (on) pq[npw + total + __popc(bal & ltmask)] = (unsigned short)(q0 + bb);
+                total += __popc(bal);
             }
             npw += total;
         }
