@@ -154,53 +154,66 @@ k_resize(const CUtensorMap* __restrict__ tmaps, uint8_t* __restrict__ pyr, const
     }
     const int x = X0 + 4 * lane;
     const int yw = Y0 + RS_R * warp;
-    const bool live = x < D.w && yw < D.h;
-    int wk[4], sh[4]; unsigned ck[4];
+    const int Dw = D.w, Dh = D.h, dps = D.pstride;         // level constants in registers (P.lv[level] is an indexed constant load)
+    const bool live = yw < Dh;                             // warp-uniform (the row table is exchanged by shuffles); columns >= w are computed on clamped sources and never stored
+    uint8_t* inner = pyr + (size_t)f * P.frame_bytes + D.poff + (size_t)EDGE * dps + EDGE;
     if (live) {
+        // per column: byte address of its source word in box row 0, funnel-shift amount, coefficient pair
+        const unsigned char* ak[4]; int sh[4]; unsigned ck[4];
 #pragma unroll
         for (int k = 0; k < 4; k++) {
-            const int xk = min(x + k, D.w - 1);
+            const int xk = min(x + k, Dw - 1);
             const int s = __ldg(xofs + xk) + EDGE - bx;    // byte offset inside a box row
-            wk[k] = s >> 2; sh[k] = (s & 3) << 3; ck[k] = (unsigned)__ldg(xcoef + xk);
+            ak[k] = s_rs + (s & ~3); sh[k] = (s & 3) << 3; ck[k] = (unsigned)__ldg(xcoef + xk);
         }
-    }
-    mbar_wait(&s_mbar, 0);
-    const unsigned* S = reinterpret_cast<const unsigned*>(s_rs);
-    const int rw = P.rs_boxw >> 2;
-    uint8_t* inner = pyr + (size_t)f * P.frame_bytes + D.poff + (size_t)EDGE * D.pstride + EDGE;
-    if (live) {
-    int prev_sy = -100, h1[4] = {0, 0, 0, 0};
-    uint8_t* dst = inner + (size_t)yw * D.pstride + x;          // one row down per iteration
-    const bool fullw = x + 3 < D.w;
-#pragma unroll 2
-    for (int j = 0; j < RS_R; j++) {
-        const int y = yw + j;
-        if (y >= D.h) break;
-        const int sy = __ldg(yofs + y) + EDGE - by;
-        const int yc = __ldg(ycoef + y);
-        const int b0 = (short)(yc & 0xFFFF), b1 = (short)(yc >> 16);
-        const unsigned* R0 = S + sy * rw;
-        const unsigned* R1 = R0 + rw;                      // row sy+1 is valid (border row) when sy is the last row, and b1 == 0 there
-        int h0[4];
-        const bool reuse = sy == prev_sy + 1;
+        // the warp's row table: lane j holds source row and coefficient pair of output row yw + j (one load per warp, not per row)
+        static_assert(RS_R <= 32, "row table lives in one warp");
+        const int nrow = min(RS_R, Dh - yw);
+        int my_sy = 0, my_yc = 0;
+        if (lane < nrow) { my_sy = (__ldg(yofs + yw + lane) + EDGE - by) * P.rs_boxw; my_yc = __ldg(ycoef + yw + lane); }
+        const int rowb = P.rs_boxw;
+        uint8_t* dst = inner + (size_t)yw * dps + x;       // one row down per iteration
+        const bool fullw = x + 3 < Dw;
+        mbar_wait(&s_mbar, 0);
+        // horizontal pass of one source row (byte offset ro): (a0 * s[x] + a1 * s[x+1]) >> 4 for the thread's 4 columns
+        auto hrow = [&](int ro, int* h) {
 #pragma unroll
-        for (int k = 0; k < 4; k++) {
-            h0[k] = reuse ? h1[k] : (int)__dp2a_lo(ck[k], __funnelshift_r(R0[wk[k]], R0[wk[k] + 1], sh[k]), 0u);
-            h1[k] = (int)__dp2a_lo(ck[k], __funnelshift_r(R1[wk[k]], R1[wk[k] + 1], sh[k]), 0u);
-        }
-        prev_sy = sy;
-        unsigned o = 0;
+            for (int k = 0; k < 4; k++) {
+                const unsigned* q = reinterpret_cast<const unsigned*>(ak[k] + ro);
+                h[k] = (int)__dp2a_lo(ck[k], __funnelshift_r(q[0], q[1], sh[k]), 0u) >> 4;
+            }
+        };
+        // one output row: `top` holds source row sy if the previous output row's lower row was sy (5 rows out of 6 at scale
+        // 1.2), otherwise it is recomputed; the lower row goes to `bot`, which is the next row's `top` (roles swap, no moves)
+        int prev_ro = -0x40000000;
+        auto step = [&](int j, int* top, int* bot) {
+            const int ro = __shfl_sync(0xFFFFFFFFu, my_sy, j), yc = __shfl_sync(0xFFFFFFFFu, my_yc, j);
+            if (ro != prev_ro + rowb) hrow(ro, top);       // warp-uniform
+            hrow(ro + rowb, bot);                          // row sy+1 is valid (border row) when sy is the last row, and b1 == 0 there
+            prev_ro = ro;
+            const int b0 = (short)(yc & 0xFFFF), b1 = yc >> 16;
+            unsigned o = 0;
 #pragma unroll
-        for (int k = 0; k < 4; k++) {
-            // <= 255 by construction: coefficient pairs sum to at most 2049 on each axis
-            const int v = (((b0 * (h0[k] >> 4)) >> 16) + ((b1 * (h1[k] >> 4)) >> 16) + 2) >> 2;
-            o |= (unsigned)v << (8 * k);
+            for (int k = 0; k < 4; k++) {
+                // <= 255 by construction: coefficient pairs sum to at most 2049 on each axis
+                const int v = (((b0 * top[k]) >> 16) + ((b1 * bot[k]) >> 16) + 2) >> 2;
+                o |= (unsigned)v << (8 * k);
+            }
+            if (fullw) *reinterpret_cast<unsigned*>(dst) = o;
+            else for (int k = 0; k < 4; k++) if (x + k < Dw) dst[k] = (uint8_t)(o >> (8 * k));
+            dst += dps;
+            asm volatile("" : "+l"(dst));                 // keep the running pointer: the unrolled rows otherwise recompute a 64-bit address each
+        };
+        int hA[4] = {0, 0, 0, 0}, hB[4] = {0, 0, 0, 0};
+        static_assert(RS_R % 2 == 0, "rows are processed in pairs");
+#pragma unroll
+        for (int j = 0; j < RS_R; j += 2) {
+            if (j >= nrow) break;
+            step(j, hA, hB);
+            if (j + 1 >= nrow) break;
+            step(j + 1, hB, hA);
         }
-        if (fullw) *reinterpret_cast<unsigned*>(dst) = o;
-        else for (int k = 0; k < 4; k++) if (x + k < D.w) dst[k] = (uint8_t)(o >> (8 * k));
-        dst += D.pstride;
-    }
-    }
+    } else mbar_wait(&s_mbar, 0);
     // reflect-101 ring: every ring pixel whose source lies in this tile, after the tile is complete
     __syncthreads();
     build_ring(inner, D.pstride, D.w, D.h, X0, min(X0 + RS_W, D.w), Y0, min(Y0 + RS_H, D.h), tid, 256,
