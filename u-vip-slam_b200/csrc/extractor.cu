@@ -56,6 +56,9 @@ struct Plan {
     int f_irow, f_irows, f_srow, f_srows, f_gw;   // FAST shared-memory carve-up (largest tile over all levels)
     unsigned long long frame_bytes;
     LevelInfo lv[MAXLEV];
+    // host-side only, kept behind lv[] so that no kernel-visible offset depends on it: bit l = the byte pairs of columns 0..2 of
+    // every 4-column group of level l lie inside the first two window words of the resize (k_resize<NARROW>)
+    unsigned rs_narrow_mask;
 };
 
 // --------------------------------------------------------------------------------------------------------
@@ -88,6 +91,36 @@ __device__ __forceinline__ void build_ring(uint8_t* inner, int ps, int w, int h,
         else { const int j = i - na; const int r = j / tw; x = X0 + (j - r * tw); y = ry[r]; }
         inner[(ptrdiff_t)y * ps + x] = fetch(reflect101(x, w), reflect101(y, h));
     }
+}
+
+// The same ownership rule for one tile of a freshly written plane, all 256 threads of the CTA, no lists and no divisions: interior
+// tiles leave after four uniform compares; edge tiles copy (A) the mirrored columns of their interior rows and (B) the mirrored rows
+// over their columns and mirrored columns.  Sources are pixels this CTA wrote before the barrier that precedes the call.
+__device__ __forceinline__ void tile_ring(uint8_t* inner, int ps, int w, int h, int X0, int X1, int Y0, int Y1, int tid)
+{
+    const bool hl = X0 <= BORDER_W && X1 > 1, hr = X1 > w - 2 - BORDER_W && X0 < w - 1;
+    const bool vt = Y0 <= BORDER_W && Y1 > 1, vb = Y1 > h - 2 - BORDER_W && Y0 < h - 1;
+    if (!(hl | hr | vt | vb)) return;                         // uniform
+    const int tw = X1 - X0, th = Y1 - Y0;
+    if (hl | hr)
+        for (int i = tid; i < th * 2 * BORDER_W; i += 256) {
+            const int r = i / (2 * BORDER_W), m = i % (2 * BORDER_W), k = (m % BORDER_W) + 1;      // powers of two
+            const int c = m < BORDER_W ? k : w - 1 - k, p = m < BORDER_W ? -k : w - 1 + k;
+            if (c >= X0 && c < X1) { uint8_t* row = inner + (ptrdiff_t)(Y0 + r) * ps; row[p] = row[c]; }
+        }
+    if (vt | vb)
+#pragma unroll 1
+        for (int m = 0; m < 2 * BORDER_W; m++) {
+            const int k = (m % BORDER_W) + 1;
+            const int sr = m < BORDER_W ? k : h - 1 - k, pr = m < BORDER_W ? -k : h - 1 + k;
+            if (sr < Y0 || sr >= Y1) continue;                // uniform
+            for (int t = tid; t < tw + 2 * BORDER_W; t += 256) {       // the tile's columns, then the 4 left and the 4 right ring columns
+                const int e = t - tw;
+                const int p = e < 0 ? X0 + t : (e < BORDER_W ? -1 - e : w + e - BORDER_W);
+                const int c = reflect101(p, w);
+                if (c >= X0 && c < X1) inner[(ptrdiff_t)pr * ps + p] = inner[(ptrdiff_t)sr * ps + c];
+            }
+        }
 }
 
 __global__ void __launch_bounds__(256)
@@ -130,15 +163,15 @@ k_import(const uint8_t* __restrict__ frames, int stride, size_t frame_pitch, int
 #endif
 constexpr int RS_W = 128, RS_R = RS_R_, RS_H = 8 * RS_R;
 
+template <bool NARROW>
 __global__ void __launch_bounds__(256)
 k_resize(const CUtensorMap* __restrict__ tmaps, uint8_t* __restrict__ pyr, const int* __restrict__ tabs, int level, const __grid_constant__ Plan P)
 {
     extern __shared__ __align__(128) unsigned char s_rs[];
     __shared__ __align__(8) uint64_t s_mbar;
     const LevelInfo& D = P.lv[level];
-    const int f = blockIdx.y, tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
-    const int ntx = (D.w + RS_W - 1) / RS_W;
-    const int ty = blockIdx.x / ntx, tx = blockIdx.x - ty * ntx;
+    const int f = blockIdx.z, tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+    const int ty = blockIdx.y, tx = blockIdx.x;
     const int X0 = tx * RS_W, Y0 = ty * RS_H;
     const int* xofs = tabs + D.tab_off;
     const int* xcoef = xofs + D.w;
@@ -158,13 +191,23 @@ k_resize(const CUtensorMap* __restrict__ tmaps, uint8_t* __restrict__ pyr, const
     const bool live = yw < Dh;                             // warp-uniform (the row table is exchanged by shuffles); columns >= w are computed on clamped sources and never stored
     uint8_t* inner = pyr + (size_t)f * P.frame_bytes + D.poff + (size_t)EDGE * dps + EDGE;
     if (live) {
-        // per column: byte address of its source word in box row 0, funnel-shift amount, coefficient pair
-        const unsigned char* ak[4]; int sh[4]; unsigned ck[4];
+        // A thread's 4 columns read source bytes d_k, d_k + 1 of a 12-byte window that starts at the aligned word of column 0
+        // (d_3 + 1 <= 11 is checked at create time).  The window is 3 LDS per source row; PRMT picks the byte pair of each
+        // column: one PRMT over words 0-1, a second one bringing in word 2 where the pair can reach it (NARROW: only column 3;
+        // 8 LDS + 4 funnel shifts per row made the kernel shared-memory bound: 2-way bank conflicts at a lane stride of 1.2 words).
+        unsigned selA[4], selB[4], ck[4];
+        const unsigned char* a0;
+        {
+            const int s0 = __ldg(xofs + min(x, Dw - 1)) + EDGE - bx;    // byte offset inside a box row
+            a0 = s_rs + (s0 & ~3);
 #pragma unroll
-        for (int k = 0; k < 4; k++) {
-            const int xk = min(x + k, Dw - 1);
-            const int s = __ldg(xofs + xk) + EDGE - bx;    // byte offset inside a box row
-            ak[k] = s_rs + (s & ~3); sh[k] = (s & 3) << 3; ck[k] = (unsigned)__ldg(xcoef + xk);
+            for (int k = 0; k < 4; k++) {
+                const int xk = min(x + k, Dw - 1);
+                const int d = __ldg(xofs + xk) + EDGE - bx - (s0 & ~3);
+                ck[k] = (unsigned)__ldg(xcoef + xk);
+                selA[k] = (unsigned)((d <= 7 ? d : 0) | ((d + 1 <= 7 ? d + 1 : 0) << 4));
+                selB[k] = (unsigned)((d <= 7 ? 0 : d - 4) | ((d + 1 <= 7 ? 1 : d - 3) << 4));
+            }
         }
         // the warp's row table: lane j holds source row and coefficient pair of output row yw + j (one load per warp, not per row)
         static_assert(RS_R <= 32, "row table lives in one warp");
@@ -177,10 +220,13 @@ k_resize(const CUtensorMap* __restrict__ tmaps, uint8_t* __restrict__ pyr, const
         mbar_wait(&s_mbar, 0);
         // horizontal pass of one source row (byte offset ro): (a0 * s[x] + a1 * s[x+1]) >> 4 for the thread's 4 columns
         auto hrow = [&](int ro, int* h) {
+            const unsigned* q = reinterpret_cast<const unsigned*>(a0 + ro);
+            const unsigned w0 = q[0], w1 = q[1], w2 = q[2];
 #pragma unroll
             for (int k = 0; k < 4; k++) {
-                const unsigned* q = reinterpret_cast<const unsigned*>(ak[k] + ro);
-                h[k] = (int)__dp2a_lo(ck[k], __funnelshift_r(q[0], q[1], sh[k]), 0u) >> 4;
+                unsigned t = __byte_perm(w0, w1, selA[k]);
+                if (!NARROW || k == 3) t = __byte_perm(t, w2, selB[k]);
+                h[k] = (int)__dp2a_lo(ck[k], t, 0u) >> 4;
             }
         };
         // one output row: `top` holds source row sy if the previous output row's lower row was sy (5 rows out of 6 at scale
@@ -216,8 +262,7 @@ k_resize(const CUtensorMap* __restrict__ tmaps, uint8_t* __restrict__ pyr, const
     } else mbar_wait(&s_mbar, 0);
     // reflect-101 ring: every ring pixel whose source lies in this tile, after the tile is complete
     __syncthreads();
-    build_ring(inner, D.pstride, D.w, D.h, X0, min(X0 + RS_W, D.w), Y0, min(Y0 + RS_H, D.h), tid, 256,
-               [&](int sx, int sy) { return inner[(ptrdiff_t)sy * D.pstride + sx]; });
+    tile_ring(inner, dps, Dw, Dh, X0, min(X0 + RS_W, Dw), Y0, min(Y0 + RS_H, Dh), tid);
 }
 
 // --------------------------------------------------------------------------------------------------------
@@ -1551,9 +1596,20 @@ static int make_plan(const uvip_extractor* ex, int w, int h, Plan* out, std::vec
             for (int X0 = 0; X0 < D.w; X0 += RS_W) {
                 const int X1 = (X0 + RS_W < D.w ? X0 + RS_W : D.w) - 1;
                 const int bx = (ofs[X0] + EDGE) & ~15;
-                const int need = ofs[X1] + EDGE + 2 - bx + 3;       // + next pixel, + funnel-shift over-read of one word
+                const int need = ofs[X1] + EDGE + 12 - bx;          // a thread reads the 12-byte window from its column 0's aligned word
                 if (need > bw) bw = need;
             }
+            // window offsets of the 4 columns of every group (independent of the tile: the box origin is 16-byte aligned)
+            int narrow = 1;
+            for (int x = 0; x < D.w; x += 4) {
+                const int base = ofs[x] - ((ofs[x] + EDGE) & 3);
+                for (int k = 0; k < 4; k++) {
+                    const int d = ofs[x + k < D.w ? x + k : D.w - 1] - base;
+                    if (d + 1 > 11) { set_last_error("scale factor too large for the resize window"); return UVIP_ERR_UNSUPPORTED; }
+                    if (k < 3 && d + 1 > 7) narrow = 0;
+                }
+            }
+            if (narrow) P.rs_narrow_mask |= 1u << l;
             build_axis_table(S.h, D.h, ofs.data(), ofs.data() + D.h);
             for (int Y0 = 0; Y0 < D.h; Y0 += RS_H) {
                 const int Y1 = (Y0 + RS_H < D.h ? Y0 + RS_H : D.h) - 1;
@@ -1602,7 +1658,8 @@ static int ensure_plan(uvip_extractor* ex, int w, int h)
     UVIP_CUDA(cudaStreamSynchronize(ex->stream));
     UVIP_CUDA(cudaFuncSetAttribute(k_quadtree, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)qt_smem_bytes(P.node_cap)));
     UVIP_CUDA(cudaFuncSetAttribute(k_fast, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)fast_smem_bytes(P)));
-    UVIP_CUDA(cudaFuncSetAttribute(k_resize, cudaFuncAttributeMaxDynamicSharedMemorySize, P.rs_boxw * P.rs_boxh + 128));
+    UVIP_CUDA(cudaFuncSetAttribute(k_resize<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, P.rs_boxw * P.rs_boxh + 128));
+    UVIP_CUDA(cudaFuncSetAttribute(k_resize<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, P.rs_boxw * P.rs_boxh + 128));
     UVIP_CUDA(cudaMemcpy(ex->tabs.p, tabs.data(), tabs.size() * sizeof(int), cudaMemcpyHostToDevice));
     // TMA descriptors of the pyramid planes: (x bytes, rows, frame) with a box of one FAST tile
     {
@@ -1667,7 +1724,7 @@ static int enqueue_group(uvip_extractor* ex, const uint8_t* d_frames, int nframe
     }
     for (int l = 1; l < P.nlevels; l++) {
         const LevelInfo& L = P.lv[l];
-        k_resize<<<dim3(div_up(L.w, RS_W) * div_up(L.h, RS_H), nframes), 256, (size_t)P.rs_boxw * P.rs_boxh + 128, st>>>(
+        (((P.rs_narrow_mask >> l) & 1u) ? k_resize<true> : k_resize<false>)<<<dim3(div_up(L.w, RS_W), div_up(L.h, RS_H), nframes), 256, (size_t)P.rs_boxw * P.rs_boxh + 128, st>>>(
             ex->tmaps.as<CUtensorMap>(), pyr, ex->tabs.as<int>(), l, P);
         ex->launches++;
     }
