@@ -858,87 +858,97 @@ k_quadtree(const unsigned* __restrict__ cand, const int* __restrict__ cand_count
 // K6: GaussianBlur 7x7 sigma 2, fixed point [18,34,48,56,48,34,18]/256 per axis, out = (sum + 2^15) >> 16
 // (SURVEY A.6 variant A).  The blurred plane keeps the layout of the pyramid plane; its 4-px border ring holds the
 // UNBLURRED reflect-101 border, which is what the reference's in-place ROI blur leaves there.
-// One CTA per 128x128 tile: the tile + halo arrives as one TMA box; each thread owns 4 adjacent columns and walks
-// down 16 rows (measured: 8 rows 0.290 ms, 16 rows 0.256 ms per 256 frames — the 6 halo rows of the horizontal pass are
-// amortised over twice as many outputs) with a 7-row register window of horizontal sums (2 IDP4A per pixel), so the vertical pass never
-// touches shared memory.  The last tile entry of every level copies the border ring.
+// One CTA per 128x192 tile (host-built tile table: no level search, no division): the tile + halo arrives as one TMA box; each
+// thread owns 4 adjacent columns and walks down 24 rows (measured per 256 frames: 8 rows 0.290 ms, 16 rows 0.256 ms with the first
+// vertical pass; 16 rows 0.202 ms, 24 rows 0.194 ms with this one — the 6 halo rows of the horizontal pass are amortised over more
+// outputs; 32 rows would need a TMA box taller than 256).  Horizontal pass: 2 IDP.4A per pixel.  Vertical pass: the horizontal sums
+// of consecutive rows are kept packed 16x2 in a 6-row register window, so the 7 taps are 3 IDP.2A + 1 IMAD per pixel (was 3 IADD +
+// 4 IMAD), and the four output bytes are gathered by 3 PRMT (byte 2 of each sum).  The last tile entry of every level copies the
+// border ring.
 // --------------------------------------------------------------------------------------------------------
 #ifndef BL_R_
-#define BL_R_ 16
+#define BL_R_ 24
 #endif
 constexpr int BL_W = 128, BL_R = BL_R_, BL_H = 8 * BL_R;   // tile, rows per warp
 constexpr int BL_BOXW = BL_W + 32, BL_BOXH = BL_H + 6;  // TMA box: 16 B aligned start, 16 px slack left and right
 
 __global__ void __launch_bounds__(256)
-k_blur(const CUtensorMap* __restrict__ tmaps, const uint8_t* __restrict__ pyr, uint8_t* __restrict__ blur, const __grid_constant__ Plan P)
+k_blur(const CUtensorMap* __restrict__ tmaps, const unsigned* __restrict__ btab, const uint8_t* __restrict__ pyr, uint8_t* __restrict__ blur,
+       const __grid_constant__ Plan P)
 {
     __shared__ __align__(128) unsigned s_in[BL_BOXH * (BL_BOXW / 4)];
     __shared__ __align__(8) uint64_t s_mbar;
-    int level = 0;
-    const int tile = blockIdx.x;
-#pragma unroll 1
-    for (int l = 1; l < P.nlevels; l++) if (tile >= P.lv[l].btile_off) level = l;
+    const unsigned te = __ldg(btab + blockIdx.x);         // level | ty << 4 | tx << 16, bit 31 = ring tile (host-built: no search, no division)
+    const int level = te & 15;
     const LevelInfo& L = P.lv[level];
     const int f = blockIdx.y, tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
-    const int tl = tile - L.btile_off;
-    const size_t plane = (size_t)f * P.frame_bytes + L.poff + (size_t)EDGE * L.pstride + EDGE;
+    const int Lw = L.w, Lh = L.h, ps = L.pstride;
+    const size_t plane = (size_t)f * P.frame_bytes + L.poff + (size_t)EDGE * ps + EDGE;
     uint8_t* out = blur + plane;
-    if (tl == L.bntx * L.bnty) {                          // ring tile: unblurred border copy
+    if (te >> 31) {                                       // ring tile: unblurred border copy
         const uint8_t* in = pyr + plane;
-        const int rw = L.w + 2 * BORDER_W;
-        for (int i = tid; i < 2 * BORDER_W * rw; i += 256) {           // rows -4..-1 and h..h+3
-            const int r = i / rw, x = i - r * rw - BORDER_W;
-            const int y = r < BORDER_W ? r - BORDER_W : L.h + (r - BORDER_W);
-            out[(ptrdiff_t)y * L.pstride + x] = in[(ptrdiff_t)y * L.pstride + x];
+        const int rw = Lw + 2 * BORDER_W;
+        for (int r = 0; r < 2 * BORDER_W; r++) {                       // rows -4..-1 and h..h+3
+            const int y = r < BORDER_W ? r - BORDER_W : Lh + (r - BORDER_W);
+            for (int i = tid; i < rw; i += 256) out[(ptrdiff_t)y * ps + i - BORDER_W] = in[(ptrdiff_t)y * ps + i - BORDER_W];
         }
-        for (int i = tid; i < 2 * BORDER_W * L.h; i += 256) {          // columns -4..-1 and w..w+3
+        for (int i = tid; i < 2 * BORDER_W * Lh; i += 256) {          // columns -4..-1 and w..w+3
             const int y = i / (2 * BORDER_W), k = i - y * (2 * BORDER_W);
-            const int x = k < BORDER_W ? k - BORDER_W : L.w + (k - BORDER_W);
-            out[(ptrdiff_t)y * L.pstride + x] = in[(ptrdiff_t)y * L.pstride + x];
+            const int x = k < BORDER_W ? k - BORDER_W : Lw + (k - BORDER_W);
+            out[(ptrdiff_t)y * ps + x] = in[(ptrdiff_t)y * ps + x];
         }
         return;
     }
-    const int x0 = (tl % L.bntx) * BL_W, y0 = (tl / L.bntx) * BL_H;
+    const int x0 = (int)(te >> 16) * BL_W, y0 = (int)((te >> 4) & 0xFFF) * BL_H;
     if (tid == 0) { mbar_init(&s_mbar, 1); mbar_fence_init(); }
     __syncthreads();
     if (tid == 0) {
         mbar_arrive_expect_tx(&s_mbar, BL_BOXW * BL_BOXH);
         tma_load_3d(s_in, tmaps + MAXLEV + level, x0, y0 + EDGE - 3, f, &s_mbar);   // padded coords: image (x0-16, y0-3)
     }
-    mbar_wait(&s_mbar, 0);
     const int x = x0 + 4 * lane;                          // first of this thread's 4 columns
     const int yw = y0 + BL_R * warp;                      // first output row of this warp
-    if (x >= L.w || yw >= L.h) return;
     const unsigned K0 = 18u | (34u << 8) | (48u << 16) | (56u << 24);     // taps for bytes x-3..x
     const unsigned K1 = 48u | (34u << 8) | (18u << 16);                   // taps for bytes x+1..x+3
+    // vertical taps over row pairs packed 16x2 (a horizontal sum is at most 255 * 256): rows (j, j+1), (j+2, j+3), (j+4, j+5) by
+    // one IDP.2A each with these coefficient pairs, row j+6 by an IMAD that also adds the rounding constant
+    const unsigned V01 = 18u | (34u << 8), V23 = 48u | (56u << 8), V45 = 48u | (34u << 8);
     const unsigned* S = s_in + (BL_R * warp) * (BL_BOXW / 4) + 4 + lane;  // row yw-3, centre word
-    int h[7][4];
-    uint8_t* dst = out + (ptrdiff_t)yw * L.pstride + x;      // walks down one row per output: no per-row 64-bit address arithmetic
-    const int nrow = min(BL_R, L.h - yw);                  // rows of this warp inside the image (>= 1)
-    const bool full = x + 3 < L.w;
+    uint8_t* dst = out + (ptrdiff_t)yw * ps + x;          // walks down one row per output: no per-row 64-bit address arithmetic
+    const int nrow = min(BL_R, Lh - yw);                   // rows of this warp inside the image (>= 1 for live warps)
+    const bool full = x + 3 < Lw;
+    mbar_wait(&s_mbar, 0);
+    if (x >= Lw || yw >= Lh) return;
+    unsigned pr[6][4];                                     // pr[r % 6][k] = h(row r) | h(row r + 1) << 16
+    int hprev[4];
 #pragma unroll
     for (int r = 0; r < BL_R + 6; r++) {
         const unsigned l = S[r * (BL_BOXW / 4) - 1], m = S[r * (BL_BOXW / 4)], n = S[r * (BL_BOXW / 4) + 1];
-        int* hr = h[r % 7];
+        int hr[4];
         hr[0] = __dp4a(__funnelshift_r(l, m, 8), K0, __dp4a(__funnelshift_r(m, n, 8), K1, 0u));
         hr[1] = __dp4a(__funnelshift_r(l, m, 16), K0, __dp4a(__funnelshift_r(m, n, 16), K1, 0u));
         hr[2] = __dp4a(__funnelshift_r(l, m, 24), K0, __dp4a(__funnelshift_r(m, n, 24), K1, 0u));
         hr[3] = __dp4a(m, K0, __dp4a(n, K1, 0u));
+        if (r >= 1) {
+#pragma unroll
+            for (int k = 0; k < 4; k++) pr[(r - 1) % 6][k] = __byte_perm((unsigned)hprev[k], (unsigned)hr[k], 0x5410);
+        }
         if (r >= 6) {
             const int j = r - 6;                          // output row yw + j uses window rows j..j+6
             if (j < nrow) {
-                unsigned o = 0;
+                unsigned a[4];
 #pragma unroll
-                for (int k = 0; k < 4; k++) {
-                    const int a = 18 * (h[j % 7][k] + h[(j + 6) % 7][k]) + 34 * (h[(j + 1) % 7][k] + h[(j + 5) % 7][k]) +
-                                  48 * (h[(j + 2) % 7][k] + h[(j + 4) % 7][k]) + 56 * h[(j + 3) % 7][k];
-                    o |= (unsigned)((a + 32768) >> 16) << (8 * k);
-                }
+                for (int k = 0; k < 4; k++)
+                    a[k] = __dp2a_lo(pr[j % 6][k], V01, __dp2a_lo(pr[(j + 2) % 6][k], V23, __dp2a_lo(pr[(j + 4) % 6][k], V45, 18u * (unsigned)hr[k] + 32768u)));
+                // a < 2^24: the output pixel (a >> 16) is byte 2 of a
+                const unsigned o = __byte_perm(__byte_perm(a[0], a[1], 0x0062), __byte_perm(a[2], a[3], 0x0062), 0x5410);
                 if (full) *reinterpret_cast<unsigned*>(dst) = o;
-                else for (int k = 0; k < 4; k++) if (x + k < L.w) dst[k] = (uint8_t)(o >> (8 * k));
-                dst += L.pstride;
+                else for (int k = 0; k < 4; k++) if (x + k < Lw) dst[k] = (uint8_t)(o >> (8 * k));
+                dst += ps;
             }
         }
+#pragma unroll
+        for (int k = 0; k < 4; k++) hprev[k] = hr[k];
     }
 }
 
@@ -1622,12 +1632,19 @@ static int make_plan(const uvip_extractor* ex, int w, int h, Plan* out, std::vec
     }
     P.tile_tab_off = tab;
     if (tabs) {
-        tabs->assign(tab + ft + 1, 0);
+        tabs->assign(tab + ft + 1 + bt, 0);
         for (int l = 0; l < p.nlevels; l++) {
             const LevelInfo& L = P.lv[l];
             for (int ty = 0; ty < L.fnty; ty++)
                 for (int tx = 0; tx < L.fntx; tx++)
                     (*tabs)[tab + L.ftile_off + ty * L.fntx + tx] = (int)((unsigned)l | ((unsigned)(ty * FAST_CH) << 4) | ((unsigned)(tx * FAST_CW) << 16));
+        }
+        for (int l = 0; l < p.nlevels; l++) {                   // blur tiles: level | ty << 4 | tx << 16, bit 31 = the level's ring tile
+            const LevelInfo& L = P.lv[l];
+            int* t = tabs->data() + tab + ft + 1 + L.btile_off;
+            for (int ty = 0; ty < L.bnty; ty++)
+                for (int tx = 0; tx < L.bntx; tx++) t[ty * L.bntx + tx] = (int)((unsigned)l | ((unsigned)ty << 4) | ((unsigned)tx << 16));
+            t[L.bntx * L.bnty] = (int)((unsigned)l | 0x80000000u);
         }
         for (int l = 1; l < p.nlevels; l++) {
             const LevelInfo& D = P.lv[l]; const LevelInfo& S = P.lv[l - 1];
@@ -1738,7 +1755,7 @@ static int enqueue_group(uvip_extractor* ex, const uint8_t* d_frames, int nframe
         ex->status.as<int>(), P);
     ex->launches++;
     PROF_MARK(3);
-    k_blur<<<dim3(P.btiles, nframes), 256, 0, st>>>(ex->tmaps.as<CUtensorMap>(), pyr, blur, P);
+    k_blur<<<dim3(P.btiles, nframes), 256, 0, st>>>(ex->tmaps.as<CUtensorMap>(), ex->tabs.as<unsigned>() + P.tile_tab_off + P.ftiles + 1, pyr, blur, P);
     ex->launches++;
     PROF_MARK(4);
     k_select<<<nframes, 256, 0, st>>>(ex->winners.as<unsigned>(), win_count, ex->sel.as<unsigned>(), ex->nsel.as<int>(), ex->sel_cap,
