@@ -645,7 +645,7 @@ k_quadtree(const unsigned* __restrict__ cand, const int* __restrict__ cand_count
     __shared__ int s_warp[QT_THREADS / 32];
     __shared__ int s_nexp, s_ncand, s_ndiv;
 
-    const int level = blockIdx.x, f = blockIdx.y;
+    const int level = blockIdx.y, f = blockIdx.x;      // level-major dispatch: the large levels of every frame start first, the small ones fill the tail
     const LevelInfo& L = P.lv[level];
     const int cap = P.node_cap;
     const int tid = threadIdx.x;
@@ -1060,6 +1060,7 @@ __device__ __forceinline__ void sincos_as_float(float xf, float* s_out, float* c
 #define DESC_KPW_ 4
 #endif
 constexpr int DESC_WARPS = 8, DESC_KPW = DESC_KPW_;           // warps per CTA, keypoints per warp
+constexpr int DESC_PR = 18, DESC_PWORDS = 10;                 // staged patch: rows / columns -18..18 (|pattern coordinate| <= 13, rotated), 40-byte rows
 #ifndef DESC_MINB
 #define DESC_MINB 4          // 64 registers: four CTAs per SM (the kernel is latency-bound; measured 0.37 -> 0.27 ms at batch 256)
 #endif
@@ -1079,16 +1080,26 @@ k_describe(const uint8_t* __restrict__ pyr, const uint8_t* __restrict__ blur, co
     // pattern in shared memory, transposed [k][lane]: lane reads its 16 points (descriptor byte `lane`) conflict-free,
     // which keeps the kernel at 64 registers (occupancy matters more than the 16 LDS: the kernel is latency-bound)
     __shared__ float2 s_pat[512];
+    __shared__ unsigned s_patch[DESC_WARPS][(2 * DESC_PR + 1) * DESC_PWORDS];
     for (int i = threadIdx.x; i < 512; i += DESC_WARPS * 32) s_pat[i] = __ldg(pat_t + i);
     __syncthreads();
     if (slot0 >= n) return;
     const int u = lane - HALF_PATCH;
+    const int prr = lane / DESC_PWORDS, pw = lane - prr * DESC_PWORDS;     // patch staging: lane -> (row mod 3, word)
     const int vm = lane < 31 ? c_umax[u < 0 ? -u : u] : -1;       // disc rows |v| <= vm belong to column u (umax is symmetric)
+    // the warp's keypoints: lane i fetches selection entry and winner word of keypoint i, so that the two dependent global loads in
+    // front of every keypoint's pixel loads are paid once per warp
+    static_assert(DESC_KPW <= 32, "one lane per keypoint of the warp");
+    unsigned my_e = 0, my_w = 0;
+    if (lane < DESC_KPW && slot0 + lane < n && slot0 + lane < out_cap) {
+        my_e = sel[(size_t)f * sel_cap + slot0 + lane];
+        if ((my_e >> 16) != 0xFFFFu) my_w = winners[(size_t)f * P.kp_per_frame + P.lv[my_e >> 16].kp_off + (my_e & 0xFFFF)];
+    }
 #pragma unroll 1
     for (int i = 0; i < DESC_KPW; i++) {
         const int slot = slot0 + i;
         if (slot >= n || slot >= out_cap) break;
-        const unsigned e = sel[(size_t)f * sel_cap + slot];
+        const unsigned e = __shfl_sync(0xFFFFFFFFu, my_e, i), wv = __shfl_sync(0xFFFFFFFFu, my_w, i);
         int level, cx, cy; float response, size, ox, oy; int octave, class_id;
         if ((e >> 16) == 0xFFFFu) {                // incoming level-0 keypoint (ComputeKeyPointsCopy, :523-534)
             const uvip_keypoint k = incoming[e & 0xFFFF];
@@ -1096,7 +1107,7 @@ k_describe(const uint8_t* __restrict__ pyr, const uint8_t* __restrict__ blur, co
             response = k.response; size = k.size; ox = k.x; oy = k.y; octave = k.octave; class_id = k.class_id;
         } else {
             level = e >> 16;
-            const unsigned w = winners[(size_t)f * P.kp_per_frame + P.lv[level].kp_off + (e & 0xFFFF)];
+            const unsigned w = wv;
             cx = w & 0xFFF; cy = (w >> 12) & 0xFFF;
             response = (float)(w >> 24); size = P.lv[level].size; octave = level; class_id = -1;
             ox = (float)cx; oy = (float)cy;
@@ -1105,6 +1116,25 @@ k_describe(const uint8_t* __restrict__ pyr, const uint8_t* __restrict__ blur, co
         const LevelInfo& L = P.lv[level];
         const int ps = L.pstride;
         const size_t plane = (size_t)f * P.frame_bytes + L.poff + (size_t)EDGE * ps + EDGE;
+        // The 512 rotated pattern points lie within +-18 px of the keypoint (|pattern| <= 13 per axis).  The 37 x 40-byte blurred
+        // patch is staged in shared memory by 13 asynchronous 4-byte copies per lane (cp.async: no registers, in flight during the
+        // whole orientation phase); the 32 byte gathers per lane then cost a few bank-conflict cycles each instead of a fully
+        // divergent trip through the L1 tag stage and a 64-bit address each.
+        // (detected keypoints are >= 16 px inside the image; an incoming keypoint closer than 5 / 2 px to the border is moved so that the
+        // staged rows stay inside the plane's 16-px padding: such a point has no defined descriptor in this layout anyway)
+        const int cxs = min(max(cx, 5), L.w - 6), cys = min(max(cy, 2), L.h - 3);
+        {
+            const int xs = (cxs - DESC_PR) & ~3;                                  // word-aligned first column (planes are 16 B aligned)
+            const unsigned* src = reinterpret_cast<const unsigned*>(blur + plane + (ptrdiff_t)(cys - DESC_PR) * ps + xs) + prr * (ps >> 2) + pw;
+            const unsigned dsts = smem_u32(s_patch[threadIdx.x >> 5] + prr * DESC_PWORDS + pw);
+            __syncwarp();                                  // the previous keypoint's gathers are done
+            if (lane < 3 * DESC_PWORDS) {
+#pragma unroll
+                for (int it = 0; it < 13; it++)
+                    if (3 * it + prr < 2 * DESC_PR + 1)
+                        asm volatile("cp.async.ca.shared.global [%0], [%1], 4;" ::"r"(dsts + it * 3 * DESC_PWORDS * 4), "l"(src + it * 3 * (ps >> 2)) : "memory");
+            }
+        }
         // ---- IC_Angle: lane u sums column u of the radius-15 disc; all row loads are issued before the first use
         int m10 = 0, m01 = 0;
         {
@@ -1124,7 +1154,9 @@ k_describe(const uint8_t* __restrict__ pyr, const uint8_t* __restrict__ blur, co
         const float factorPI = (float)(3.14159265358979323846 / 180.f);
         float a, b;
         sincos_as_float(__fmul_rn(angle, factorPI), &b, &a);
-        const uint8_t* cb = blur + plane + (ptrdiff_t)cy * ps + cx;
+        asm volatile("cp.async.wait_all;" ::: "memory");
+        __syncwarp();                                      // the staged patch is complete and visible to every lane
+        const uint8_t* cb = reinterpret_cast<const uint8_t*>(s_patch[threadIdx.x >> 5]) + DESC_PR * (4 * DESC_PWORDS) + DESC_PR + ((cxs - DESC_PR) & 3);
         unsigned val = 0;
 #pragma unroll
         for (int k = 0; k < 8; k++) {
@@ -1132,7 +1164,7 @@ k_describe(const uint8_t* __restrict__ pyr, const uint8_t* __restrict__ blur, co
             const float x0 = p0.x, y0 = p0.y, x1 = p1.x, y1 = p1.y;
             const int r0 = __float2int_rn(__fadd_rn(__fmul_rn(x0, b), __fmul_rn(y0, a))), q0 = __float2int_rn(__fsub_rn(__fmul_rn(x0, a), __fmul_rn(y0, b)));
             const int r1 = __float2int_rn(__fadd_rn(__fmul_rn(x1, b), __fmul_rn(y1, a))), q1 = __float2int_rn(__fsub_rn(__fmul_rn(x1, a), __fmul_rn(y1, b)));
-            const int t0 = __ldg(cb + (r0 * ps + q0)), t1 = __ldg(cb + (r1 * ps + q1));
+            const int t0 = cb[r0 * (4 * DESC_PWORDS) + q0], t1 = cb[r1 * (4 * DESC_PWORDS) + q1];
             val |= (unsigned)(t0 < t1) << k;
         }
         desc[((size_t)f * out_cap + slot) * 32 + lane] = (uint8_t)val;
@@ -1750,7 +1782,7 @@ static int enqueue_group(uvip_extractor* ex, const uint8_t* d_frames, int nframe
                                                                      cand_count, ex->status.as<int>(), P);
     ex->launches++;
     PROF_MARK(2);
-    k_quadtree<<<dim3(P.nlevels, nframes), QT_THREADS, qt_smem_bytes(P.node_cap), st>>>(
+    k_quadtree<<<dim3(nframes, P.nlevels), QT_THREADS, qt_smem_bytes(P.node_cap), st>>>(
         ex->cand.as<unsigned>(), cand_count, ex->labels.as<unsigned short>(), ex->winners.as<unsigned>(), win_count,
         ex->status.as<int>(), P);
     ex->launches++;
