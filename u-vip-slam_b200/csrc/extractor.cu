@@ -67,33 +67,8 @@ struct Plan {
 // reflect-101 source coordinate of ring coordinate r in [-BORDER_W, n + BORDER_W)
 __device__ __forceinline__ int reflect101(int r, int n) { return r < 0 ? -r : (r >= n ? 2 * (n - 1) - r : r); }
 
-// Border ring owned by a tile: every ring pixel whose reflect-101 SOURCE pixel lies inside [X0,X1) x [Y0,Y1).
-// fetch(sx, sy) returns the source pixel (from the input frame for level 0, from the freshly written plane otherwise).
-template <class Fetch>
-__device__ __forceinline__ void build_ring(uint8_t* inner, int ps, int w, int h, int X0, int X1, int Y0, int Y1, int tid, int nthreads, Fetch fetch)
-{
-    // ring coordinates whose source falls into the tile, per axis (at most 2*BORDER_W each)
-    int rx[2 * BORDER_W], ry[2 * BORDER_W], nrx = 0, nry = 0;
-#pragma unroll
-    for (int k = 1; k <= BORDER_W; k++) {
-        if (k >= X0 && k < X1) rx[nrx++] = -k;
-        if (w - 1 - k >= X0 && w - 1 - k < X1) rx[nrx++] = w - 1 + k;
-        if (k >= Y0 && k < Y1) ry[nry++] = -k;
-        if (h - 1 - k >= Y0 && h - 1 - k < Y1) ry[nry++] = h - 1 + k;
-    }
-    if ((nrx | nry) == 0) return;
-    const int tw = X1 - X0, th = Y1 - Y0;
-    // A: mirrored columns x (interior rows + mirrored rows);  B: interior columns x mirrored rows
-    const int na = nrx * (th + nry), nb = tw * nry;
-    for (int i = tid; i < na + nb; i += nthreads) {
-        int x, y;
-        if (i < na) { const int c = i / (th + nry), r = i - c * (th + nry); x = rx[c]; y = r < th ? Y0 + r : ry[r - th]; }
-        else { const int j = i - na; const int r = j / tw; x = X0 + (j - r * tw); y = ry[r]; }
-        inner[(ptrdiff_t)y * ps + x] = fetch(reflect101(x, w), reflect101(y, h));
-    }
-}
-
-// The same ownership rule for one tile of a freshly written plane, all 256 threads of the CTA, no lists and no divisions: interior
+// Border ring of a tile of a freshly written plane: every ring pixel whose reflect-101 SOURCE pixel lies inside [X0,X1) x [Y0,Y1) is
+// owned by that tile.  All 256 threads of the CTA, no lists and no divisions: interior
 // tiles leave after four uniform compares; edge tiles copy (A) the mirrored columns of their interior rows and (B) the mirrored rows
 // over their columns and mirrored columns.  Sources are pixels this CTA wrote before the barrier that precedes the call.
 __device__ __forceinline__ void tile_ring(uint8_t* inner, int ps, int w, int h, int X0, int X1, int Y0, int Y1, int tid)
@@ -132,9 +107,21 @@ k_import(const uint8_t* __restrict__ frames, int stride, size_t frame_pitch, int
     const uint8_t* fsrc = frames + (size_t)f * frame_pitch;
     uint8_t* inner = pyr + (size_t)f * P.frame_bytes + L.poff + (size_t)EDGE * L.pstride + EDGE;
     if ((int)blockIdx.x >= copy_blocks) {                       // ring blocks: reflect-101 border straight from the input frame
-        const int nb = gridDim.x - copy_blocks, b = blockIdx.x - copy_blocks;
-        build_ring(inner, L.pstride, L.w, L.h, 0, L.w, 0, L.h, b * 256 + threadIdx.x, nb * 256,
-                   [&](int sx, int sy) { return __ldg(fsrc + (size_t)sy * stride + sx); });
+        // 2 * BORDER_W ring blocks: block m copies mirror row m (over the image columns and the mirrored columns) and an eighth of the
+        // mirrored columns of the interior rows; no lists, no divisions
+        const int m = blockIdx.x - copy_blocks, w = L.w, h = L.h, ps = L.pstride;
+        {
+            const int k = (m % BORDER_W) + 1;
+            const int sr = m < BORDER_W ? k : h - 1 - k, pr = m < BORDER_W ? -k : h - 1 + k;
+            for (int t = threadIdx.x; t < w + 2 * BORDER_W; t += 256) {
+                const int p = t - BORDER_W;
+                inner[(ptrdiff_t)pr * ps + p] = __ldg(fsrc + (size_t)sr * stride + reflect101(p, w));
+            }
+        }
+        for (int i = m * 256 + threadIdx.x; i < h * 2 * BORDER_W; i += 2 * BORDER_W * 256) {
+            const int r = i / (2 * BORDER_W), c = i % (2 * BORDER_W), k = (c % BORDER_W) + 1;      // powers of two
+            inner[(ptrdiff_t)r * ps + (c < BORDER_W ? -k : w - 1 + k)] = __ldg(fsrc + (size_t)r * stride + (c < BORDER_W ? k : w - 1 - k));
+        }
         return;
     }
     const int cpr = (L.w + 15) >> 4;                        // 16-px chunks per row
@@ -1768,7 +1755,7 @@ static int enqueue_group(uvip_extractor* ex, const uint8_t* d_frames, int nframe
         const int chunks = ((L.w + 15) >> 4) * L.h;
         const int vec_ok = (((uintptr_t)d_frames & 15) == 0 && (stride & 15) == 0 && (frame_pitch & 15) == 0) ? 1 : 0;
         const int copy_blocks = div_up(chunks, 256);
-        k_import<<<dim3(copy_blocks + 8, nframes), 256, 0, st>>>(d_frames, stride, frame_pitch, vec_ok, copy_blocks, pyr, P);
+        k_import<<<dim3(copy_blocks + 2 * BORDER_W, nframes), 256, 0, st>>>(d_frames, stride, frame_pitch, vec_ok, copy_blocks, pyr, P);
         ex->launches++;
     }
     for (int l = 1; l < P.nlevels; l++) {
