@@ -397,6 +397,27 @@ def test_extract_parameter_sweep(gpu, oracle, synth):
         ex.close()
 
 
+@pytest.mark.parametrize('sf,nlev,W,H', [(1.7, 4, 640, 480), (1.75, 3, 752, 480), (1.6, 4, 514, 402), (1.25, 8, 1026, 770)])
+def test_extract_wide_scale_factors(gpu, oracle, synth, sf, nlev, W, H):
+    """scale factors above 1.5 take the resize kernel's three-word byte selection for every column (k_resize<false>), and widths
+    such as 514 / 1026 leave a last tile narrower than the mirrored border columns (ring pixels owned by the tile before it):
+    pyramid, blurred planes, corners, winners, keypoints and descriptors must still equal the oracle's"""
+    img = synth.synth_frame(31 + nlev, W, H)
+    ex = gpu.ORBextractor(800, sf, nlev, 1, 20, max_width=W, max_height=H)
+    compare_frame(ex, oracle.Extractor(800, sf, nlev, 1, 20), img)
+    ex.close()
+
+
+def test_extract_scale_factor_beyond_the_resize_window_is_loud(gpu, synth):
+    """a scale factor whose source box or 4-column source span leaves the kernel's envelope is refused, not approximated"""
+    img = synth.synth_frame(5, 640, 480)
+    for sf in (2.0, 2.6):                                   # 2.0: source box of a 128-column tile wider than a TMA box; 2.6: window
+        with pytest.raises(gpu.capi.UvipError) as e:
+            ex = gpu.ORBextractor(500, sf, 2, 1, 20, max_width=640, max_height=480)
+            ex(img, cap=8192)
+        assert e.value.code == gpu.capi.ERR_UNSUPPORTED
+
+
 def test_clahe_preprocessing(gpu, oracle, synth, golden):
     """next row N3: CLAHE (clip 4, 12x12 tiles) bit-exact against the oracle and the cv2 golden hashes, then the full
     Enhance -> extract chain of Tracking::GrabImage (src/Tracking.cc:425-446)"""

@@ -353,7 +353,9 @@ k_fast(const CUtensorMap* __restrict__ tmaps, const unsigned* __restrict__ tile_
     unsigned short* pq = reinterpret_cast<unsigned short*>(s_score + (size_t)srow * P.f_srows) + FAST_WARPS * P.f_gw + warp * 4 * P.f_gw;   // candidate pixels
 
     const int gx0 = X0 & ~3, gxe = (X1 - 1) & ~3;         // first / last 4-pixel group (image coords)
-    const int ngx = ((gxe - gx0) >> 2) + 1;
+    // at least 2 groups per row: with one, the reciprocal below would be 2^32 and wrap to 0 (a sliver tile whose detection range lies
+    // inside one 4-pixel group: found by the 1026-px-wide parity case); the extra group's pixels are masked out by s_colvalid
+    const int ngx = max(((gxe - gx0) >> 2) + 1, 2);
     const int ax0 = ((gx0 - 4 + EDGE) & ~15) - EDGE;      // image coords of s_img[0][0]: TMA needs a 16-byte aligned start
     const int ay0 = Y0 - 3;
     const int cofs = (gx0 - 4 - ax0) >> 2;                // word column of the first group's left neighbour
