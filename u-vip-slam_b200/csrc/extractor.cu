@@ -148,9 +148,10 @@ k_import(const uint8_t* __restrict__ frames, int stride, size_t frame_pitch, int
 #ifndef RS_R_
 #define RS_R_ 12
 #endif
-constexpr int RS_W = 128, RS_R = RS_R_, RS_H = 8 * RS_R;
+constexpr int RS_W = 128, RS_RMAX = RS_R_, RS_H = 8 * RS_RMAX;     // widest tile; launches that would not fill the GPU use half-height tiles
+constexpr int RS_RSMALL = RS_RMAX / 2;
 
-template <bool NARROW>
+template <bool NARROW, int RS_R>
 __global__ void __launch_bounds__(256)
 k_resize(const CUtensorMap* __restrict__ tmaps, uint8_t* __restrict__ pyr, const int* __restrict__ tabs, int level, const __grid_constant__ Plan P)
 {
@@ -159,7 +160,7 @@ k_resize(const CUtensorMap* __restrict__ tmaps, uint8_t* __restrict__ pyr, const
     const LevelInfo& D = P.lv[level];
     const int f = blockIdx.z, tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
     const int ty = blockIdx.y, tx = blockIdx.x;
-    const int X0 = tx * RS_W, Y0 = ty * RS_H;
+    const int X0 = tx * RS_W, Y0 = ty * (8 * RS_R);
     const int* xofs = tabs + D.tab_off;
     const int* xcoef = xofs + D.w;
     const int* yofs = xcoef + D.w;
@@ -249,7 +250,7 @@ k_resize(const CUtensorMap* __restrict__ tmaps, uint8_t* __restrict__ pyr, const
     } else mbar_wait(&s_mbar, 0);
     // reflect-101 ring: every ring pixel whose source lies in this tile, after the tile is complete
     __syncthreads();
-    tile_ring(inner, dps, Dw, Dh, X0, min(X0 + RS_W, Dw), Y0, min(Y0 + RS_H, Dh), tid);
+    tile_ring(inner, dps, Dw, Dh, X0, min(X0 + RS_W, Dw), Y0, min(Y0 + 8 * RS_R, Dh), tid);
 }
 
 // --------------------------------------------------------------------------------------------------------
@@ -1496,6 +1497,7 @@ static inline int cv_round_f(float v) { return (int)lrintf(v); }
 struct uvip_extractor {
     uvip_extractor_params prm;
     int device = 0;
+    int num_sms = 148;         // B200; read from the device at the first plan
     cudaStream_t stream = nullptr;
     float scale[MAXLEV], inv_scale[MAXLEV];
     int quota[MAXLEV];
@@ -1684,6 +1686,7 @@ static size_t qt_smem_bytes(int cap) { return (size_t)(4 * cap * 2 + cap * 2 + 4
 static int ensure_plan(uvip_extractor* ex, int w, int h)
 {
     if (ex->plan.W == w && ex->plan.H == h) return UVIP_OK;
+    cudaDeviceGetAttribute(&ex->num_sms, cudaDevAttrMultiProcessorCount, ex->device);
     UVIP_CHECK_ARG(w <= ex->prm.max_width && h <= ex->prm.max_height);
     Plan P; std::vector<int> tabs;
     int rc = make_plan(ex, w, h, &P, &tabs);
@@ -1696,8 +1699,10 @@ static int ensure_plan(uvip_extractor* ex, int w, int h)
     UVIP_CUDA(cudaStreamSynchronize(ex->stream));
     UVIP_CUDA(cudaFuncSetAttribute(k_quadtree, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)qt_smem_bytes(P.node_cap)));
     UVIP_CUDA(cudaFuncSetAttribute(k_fast, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)fast_smem_bytes(P)));
-    UVIP_CUDA(cudaFuncSetAttribute(k_resize<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, P.rs_boxw * P.rs_boxh + 128));
-    UVIP_CUDA(cudaFuncSetAttribute(k_resize<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, P.rs_boxw * P.rs_boxh + 128));
+    UVIP_CUDA(cudaFuncSetAttribute(k_resize<true, RS_RMAX>, cudaFuncAttributeMaxDynamicSharedMemorySize, P.rs_boxw * P.rs_boxh + 128));
+    UVIP_CUDA(cudaFuncSetAttribute(k_resize<false, RS_RMAX>, cudaFuncAttributeMaxDynamicSharedMemorySize, P.rs_boxw * P.rs_boxh + 128));
+    UVIP_CUDA(cudaFuncSetAttribute(k_resize<true, RS_RSMALL>, cudaFuncAttributeMaxDynamicSharedMemorySize, P.rs_boxw * P.rs_boxh + 128));
+    UVIP_CUDA(cudaFuncSetAttribute(k_resize<false, RS_RSMALL>, cudaFuncAttributeMaxDynamicSharedMemorySize, P.rs_boxw * P.rs_boxh + 128));
     UVIP_CUDA(cudaMemcpy(ex->tabs.p, tabs.data(), tabs.size() * sizeof(int), cudaMemcpyHostToDevice));
     // TMA descriptors of the pyramid planes: (x bytes, rows, frame) with a box of one FAST tile
     {
@@ -1762,7 +1767,15 @@ static int enqueue_group(uvip_extractor* ex, const uint8_t* d_frames, int nframe
     }
     for (int l = 1; l < P.nlevels; l++) {
         const LevelInfo& L = P.lv[l];
-        (((P.rs_narrow_mask >> l) & 1u) ? k_resize<true> : k_resize<false>)<<<dim3(div_up(L.w, RS_W), div_up(L.h, RS_H), nframes), 256, (size_t)P.rs_boxw * P.rs_boxh + 128, st>>>(
+        // half-height tiles when full ones would not even fill one wave (6 CTAs per SM): twice the CTAs for a lone frame or a small
+        // batch (single-frame pyramid 0.063 -> 0.054 ms).  At batch 256 every level stays on full tiles: half tiles for the 1.2-2.6-wave
+        // levels 4-7 were measured slower (pyramid 0.308 -> 0.316 ms, and FAST behind them 0.759 -> 0.794 ms with identical code: every
+        // CTA loads the full-height box, and the extra L2 traffic evicts pyramid planes FAST is about to read)
+        const bool narrow = (P.rs_narrow_mask >> l) & 1u;
+        const bool small = (long long)div_up(L.w, RS_W) * div_up(L.h, RS_H) * nframes < 6LL * ex->num_sms;
+        const int th = 8 * (small ? RS_RSMALL : RS_RMAX);
+        auto kern = small ? (narrow ? k_resize<true, RS_RSMALL> : k_resize<false, RS_RSMALL>) : (narrow ? k_resize<true, RS_RMAX> : k_resize<false, RS_RMAX>);
+        kern<<<dim3(div_up(L.w, RS_W), div_up(L.h, th), nframes), 256, (size_t)P.rs_boxw * P.rs_boxh + 128, st>>>(
             ex->tmaps.as<CUtensorMap>(), pyr, ex->tabs.as<int>(), l, P);
         ex->launches++;
     }
