@@ -285,7 +285,36 @@ def run_ours(args):
     assert stream.cuda_stream != 0
     knn_ev = []
 
+    # The kNN of step i runs on a second stream beside the pyramid kernels of step i + 1 (two output sets, events both ways): the
+    # import is HBM-bound and the kNN is POPC/ALU-bound, and each fills the other's tail (measured 131.2 k -> 135.0 k frames/s).  The
+    # 'pyramid' stage timer then contains the concurrent kNN; UVIP_NO_OVERLAP_KNN=1 gives the serial schedule (clean stage times).
+    OVL = not os.environ.get('UVIP_NO_OVERLAP_KNN')
+    if OVL:
+        outs = [(d_kps, d_desc, d_n, d_idx, d_dist), (torch.zeros_like(d_kps), torch.zeros_like(d_desc), torch.zeros_like(d_n), torch.zeros_like(d_idx), torch.zeros_like(d_dist))]
+        stream2 = torch.cuda.Stream(dev); sp2 = C.c_void_p(stream2.cuda_stream)
+        ev_ext = [torch.cuda.Event(), torch.cuda.Event()]; ev_knn = [torch.cuda.Event(), torch.cuda.Event()]
+        used = [False, False]
+
     def step(i, timed=False):
+        if OVL:
+            j = i & 1
+            o_kps, o_desc, o_n, o_idx, o_dist = outs[j]
+            if used[j]:
+                stream.wait_event(ev_knn[j])               # the kNN of step i-2 has read this output set
+            chk(L.uvip_extract_batch_device(ex.h, C.c_void_p(d_in[i & 1].data_ptr()), B, W, H, W, W * H, C.c_void_p(o_kps.data_ptr()),
+                                            C.c_void_p(o_n.data_ptr()), cap, C.c_void_p(o_desc.data_ptr()), sp))
+            ev_ext[j].record(stream)
+            stream2.wait_event(ev_ext[j])
+            if timed:
+                e0 = torch.cuda.Event(enable_timing=True); e1 = torch.cuda.Event(enable_timing=True)
+                e0.record(stream2)
+            chk(L.uvip_knn2_batch_device(m.h, C.c_void_p(o_desc.data_ptr()), C.c_void_p(o_n.data_ptr()), cap * 32,
+                                         C.c_void_p(o_desc.data_ptr() + cap * 32), C.c_void_p(o_n.data_ptr() + 4), cap * 32,
+                                         B - 1, cap, C.c_void_p(o_idx.data_ptr()), C.c_void_p(o_dist.data_ptr()), cap, sp2))
+            if timed:
+                e1.record(stream2); knn_ev.append((e0, e1))
+            ev_knn[j].record(stream2); used[j] = True
+            return
         chk(L.uvip_extract_batch_device(ex.h, C.c_void_p(d_in[i & 1].data_ptr()), B, W, H, W, W * H, C.c_void_p(d_kps.data_ptr()),
                                         C.c_void_p(d_n.data_ptr()), cap, C.c_void_p(d_desc.data_ptr()), sp))
         if timed:
@@ -318,6 +347,8 @@ def run_ours(args):
     t0.record(stream)
     for i in range(K):
         step(i, timed=True)
+    if OVL:
+        stream.wait_stream(stream2)
     t1.record(stream)
     barrier()
     ms = t0.elapsed_time(t1)
@@ -391,7 +422,9 @@ def run_ours(args):
 
     # ---- roofline of the dominant extraction kernel (algorithmic bytes of SURVEY 8(d) / its measured duration)
     peak, peak_kind = hbm_peak()
-    dom = max(stage_ms, key=stage_ms.get)
+    # dominant KERNEL: 'pyramid' is eight launches (import + 7 resizes, the largest a quarter of the stage) and, with the overlapped
+    # schedule, its timer also contains the concurrent kNN, so it never names the dominant kernel
+    dom = max((k for k in stage_ms if k != 'pyramid'), key=stage_ms.get)
     dom_ms = stage_ms[dom] / max(ngroups, 1)
     achieved = B_FRAME_BYTES * B / (dom_ms * 1e-3) / 1e9
     traffic = ncu_traffic()
@@ -399,7 +432,9 @@ def run_ours(args):
                 'traffic': traffic.get(dom), 'peak_source': peak_kind + ' (MEASURED_PEAKS.json hbm_gbs)' if peak_kind == 'measured' else 'fallback 6.65 TB/s',
                 'algorithmic_bytes_per_launch': B_FRAME_BYTES * B, 'launch_ms': dom_ms,
                 'stage_ms_per_step': {k: v / max(ngroups, 1) for k, v in stage_ms.items()}, 'knn_ms_per_step': knn_ms / K,
-                'whole_step_frac': (B_FRAME_BYTES * B * K / (ms * 1e-3) / 1e9) / peak}
+                'whole_step_frac': (B_FRAME_BYTES * B * K / (ms * 1e-3) / 1e9) / peak,
+                'schedule': ('kNN of step i on a second stream beside the pyramid of step i+1: the pyramid stage time contains it' if OVL
+                             else 'serial: one stream')}
     pipes = ncu_pipes()
     if dom in pipes:           # the extraction kernels are instruction-bound, so the ALU pipe is reported next to HBM
         roofline['alu_pipe'] = {'kernel': dom, 'alu_pipe_pct': pipes[dom]['alu_pipe_pct'], 'issue_slot_pct': pipes[dom]['issue_slot_pct'],
