@@ -291,7 +291,7 @@ def run_ours(args):
     SERIAL = bool(os.environ.get('UVIP_SERIAL'))
     outs = [(d_kps, d_desc, d_n, d_idx, d_dist)]
     exs, mts, sts = [ex], [m], [stream]
-    if not SERIAL:
+    for _ in range(0 if SERIAL else max(1, int(os.environ.get('UVIP_INFLIGHT', '2'))) - 1):
         outs.append(tuple(torch.zeros_like(t) for t in outs[0]))
         exs.append(pkg.ORBextractor(NFEAT, SCALE, NLEVELS, pkg.ORBextractor.FAST_SCORE, FAST_TH, device=local, max_width=W, max_height=H, max_batch=B))
         mts.append(pkg.ORBmatcher(0.75, True, device=local))
