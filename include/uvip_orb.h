@@ -10,7 +10,11 @@
  * Conventions: plain pointers and sizes, no C++/torch types; every function returns an int status
  * (UVIP_OK = 0), never throws, never falls back to a CPU implementation.  "host" pointers are ordinary
  * process memory; "device" pointers (suffix _device) are CUDA device memory on the handle's GPU and the
- * call is asynchronous on the given cudaStream_t (passed as void*; NULL = the handle's own stream).
+ * call is asynchronous on the given cudaStream_t (passed as void*).  NULL selects the handle's OWN non-blocking stream,
+ * which is not ordered against any stream of the caller: order later work behind it with uvip_extractor_stream() /
+ * uvip_matcher_stream() (an event on that stream) or wait with uvip_extractor_status() / uvip_matcher_sync().  NULL is
+ * NOT the legacy default stream; pass cudaStreamLegacy ((void*)0x1) for that — what frameworks whose "default stream"
+ * handle is 0 (torch) must do.
  * A handle is not re-entrant (the reference extractor is stateful too, include/ORBextractor.h:90-91);
  * use one handle per calling thread — Tracking, LocalMapping and LoopClosing each own one matcher.
  */
@@ -105,6 +109,10 @@ int   uvip_extract_batch_device(uvip_extractor* ex, const uint8_t* d_frames, int
                                 size_t frame_pitch, uvip_keypoint* d_kps, int32_t* d_n_out, int cap, uint8_t* d_desc,
                                 void* stream);
 int   uvip_extractor_status(uvip_extractor* ex);   /* synchronises the handle; UVIP_OK or the sticky error of the last group */
+void* uvip_extractor_stream(uvip_extractor* ex);   /* the handle's own cudaStream_t (what a NULL stream argument selects) */
+/* how often uvip_extract had to capture + instantiate its CUDA graph (once per call SHAPE: frame geometry, cap, FullDetect,
+ * grid geometry — not per num_featsneeded / number of incoming keypoints, which change every frame at src/Tracking.cc:946) */
+long long uvip_extractor_graph_captures(const uvip_extractor* ex);
 
 /* debug taps for parity tests (valid after an extract call, frame < nframes of that call) */
 int   uvip_get_pyramid_level(uvip_extractor* ex, int frame, int level, int blurred,
@@ -152,6 +160,8 @@ enum { UVIP_TH_HIGH = 100, UVIP_TH_LOW = 50, UVIP_HISTO_LENGTH = 30 };   /* src/
 int   uvip_matcher_create(int device, uvip_matcher** out);
 int   uvip_matcher_destroy(uvip_matcher* m);
 long long uvip_matcher_launch_count(const uvip_matcher* m);
+void* uvip_matcher_stream(uvip_matcher* m);        /* the handle's own cudaStream_t (what a NULL stream argument selects) */
+int   uvip_matcher_sync(uvip_matcher* m);          /* waits for everything queued on the handle's own stream */
 
 /* ORBmatcher::DescriptorDistance (src/ORBmatcher.cc:1794-1810) for n row pairs: out[i] = popcount(a_i ^ b_i) */
 int   uvip_descriptor_distance(uvip_matcher* m, const uint8_t* a, const uint8_t* b, int n, int32_t* out);

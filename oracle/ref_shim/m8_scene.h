@@ -144,7 +144,10 @@ int run(int which, const Bundle& in, Bundle& out)
             if (S.vp[(size_t)i] && pf[4 * i + 2] && which == 0) S.pts[(size_t)i].obs[pKF] = 0;     // IsInKeyFrame(pKF)
             vp.push_back(S.vp[(size_t)i]);
         }
-        ret[0] = which == 0 ? matcher.Fuse(pKF, vp, S.th) : matcher.Fuse(pKF, S.Scw, vp, S.th);
+        // th < 0 in the bundle: call with the DEFAULT argument (include/ORBmatcher.h:85,88 — what src/LocalMapping.cc:1236,1261
+        // rely on), so that a drop-in header with a different default fails the comparison
+        if (S.th < 0.f) ret[0] = which == 0 ? matcher.Fuse(pKF, vp) : matcher.Fuse(pKF, S.Scw, vp);
+        else ret[0] = which == 0 ? matcher.Fuse(pKF, vp, S.th) : matcher.Fuse(pKF, S.Scw, vp, S.th);
         for (int k = 0; k < S.nk[0]; k++) slot_owner.push_back(S.id_of(pKF->mapPoints[(size_t)k]));
         for (int k = 0; k < S.nk[0]; k++) replaced.push_back(S.id_of(S.kmp[0][(size_t)k].replaced));
         for (int i = 0; i < S.np; i++) replaced.push_back(S.id_of(S.pts[(size_t)i].replaced));

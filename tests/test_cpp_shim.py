@@ -204,3 +204,34 @@ def test_shim_matches_oracle(pkg, oracle, synth, shim_exe, tmp_path):
     e12 = np.full(n, -1, np.int32); e12[q7[om7 >= 0]] = om7[om7 >= 0]
     assert nkk == int((om7 >= 0).sum()) and nkk > 200, (nkk, int((om7 >= 0).sum()))
     assert np.array_equal(o12, e12)
+
+
+@pytest.fixture(scope='module')
+def threads_exe(pkg, tmp_path_factory):
+    pkg.capi.lib()
+    out = str(tmp_path_factory.mktemp('shim') / 'test_threads')
+    libdir = os.path.join(ROOT, 'u-vip-slam_b200')
+    cxx = '/usr/bin/g++' if os.path.exists('/usr/bin/g++') else 'g++'
+    subprocess.check_call([cxx, '-std=c++14', '-O2', '-Wall', '-Werror', '-pthread', '-o', out, os.path.join(ROOT, 'tests', 'cpp', 'test_threads.cpp'),
+                           '-L', libdir, '-luvip_orb', '-Wl,-rpath,' + libdir])
+    return out
+
+
+def test_threads_driver_compiles_and_refuses_without_device(pkg, threads_exe):
+    if pkg.capi.lib().uvip_device_count() > 0:
+        pytest.skip('a CUDA device is present')
+    r = subprocess.run([threads_exe], capture_output=True, text=True)
+    assert r.returncode == 3 and 'no CPU fallback' in r.stderr
+
+
+@pytest.mark.gpu
+def test_three_matcher_threads_and_one_extractor_thread_equal_serial(threads_exe):
+    """stack-local ORBmatcher instances used concurrently from three host threads (src/Tracking.cc:2222,
+    src/LocalMapping.cc:1230, src/LoopClosing.cc:373) while the Tracking thread extracts; every concurrent result equals the
+    serial one.  The shim's device handle is thread-local, so the per-call construct / destruct allocates nothing."""
+    import json
+    r = subprocess.run([threads_exe, '40'], capture_output=True, text=True, timeout=600)
+    assert r.returncode == 0, (r.stdout, r.stderr)
+    rec = json.loads(r.stdout.strip().splitlines()[-1])
+    assert rec['mismatches'] == 0 and rec['threads'] == 4 and min(rec['matches']) >= 50
+    print('shim call shape (construct + SearchByProjection + destruct):', rec['construct_search_destruct_us'])

@@ -138,6 +138,77 @@ def test_extract_occupancy_grid_path(gpu, oracle, synth):
     assert np.array_equal(g3, grid) and len(kps) >= 1000
 
 
+def test_incoming_keypoints_near_the_border(gpu, oracle, synth):
+    """incoming level-0 keypoints (ComputeKeyPointsCopy, src/ORBextractor.cc:523-534) may lie anywhere inside the image: their
+    IC_Angle disc and descriptor pattern reach into the reference's 16-px reflect-101 border, which the CUDA path materialises
+    in full for such calls.  Points at least 2 px inside the image must equal the oracle and the reference's compiled operator()."""
+    from oracle import reference as R
+    W, H, mpd = 752, 480, 20
+    img = synth.synth_frame(33, W, H)
+    ex = gpu.ORBextractor(1000, 1.2, 8, 1, 20, max_width=W, max_height=H)
+    oex = oracle.Extractor(1000, 1.2, 8, 1, 20)
+    xs = [2, 3, 7, 15, 16, 40, W - 41, W - 17, W - 16, W - 8, W - 4, W - 3]
+    ys = [2, 5, 15, 16, 17, H - 17, H - 16, H - 6, H - 3]
+    pts = [(x, y) for x in xs for y in ys]
+    inc = np.zeros(len(pts), gpu.capi.KP_DTYPE)
+    inc['x'] = [p[0] for p in pts]; inc['y'] = [p[1] for p in pts]
+    inc['x'] += 0.25; inc['y'] -= 0.25                                       # cvRound of non-integer coordinates
+    inc['size'] = 31; inc['angle'] = -1; inc['octave'] = 0; inc['class_id'] = 3
+    grid = np.zeros((H // mpd + 2, W // mpd + 2), np.int32, order='F')
+    g1 = grid.copy(order='F'); g2 = grid.copy(order='F')
+    kps, desc = ex(img, keypoints=inc, grid_2d=g1, min_px_dist=mpd, FullDetect=False, num_featsneeded=200)
+    okps, odesc = oex(img, keypoints=inc, grid=g2, min_px_dist=mpd, full_detect=False, num_needed=200)
+    assert np.array_equal(g1, g2) and len(kps) == len(okps) > len(inc)
+    n = len(inc)
+    assert np.array_equal(kps['x'][:n], inc['x']) and np.array_equal(kps['class_id'][:n], inc['class_id'])
+    assert np.array_equal(kps['angle'], okps['angle'])
+    assert np.array_equal(desc, odesc)
+    if R.available():
+        g3 = grid.copy(order='F')
+        rk, rd = R.Extractor(1000, 1.2, 8, 1, 20)(img, keypoints=inc, grid=g3, min_px_dist=mpd, full_detect=False, num_needed=200)
+        assert np.array_equal(rk['angle'], kps['angle']) and np.array_equal(rd, desc) and np.array_equal(g3, g1)
+    # the same extractor goes back to border-free calls and full detection unchanged
+    k2, d2 = ex(img)
+    ok2, od2 = oex(img)
+    assert np.array_equal(d2, od2)
+
+
+def test_incoming_keypoints_outside_the_image_are_refused(gpu, synth):
+    W, H, mpd = 320, 240, 20
+    img = synth.synth_frame(5, W, H)
+    ex = gpu.ORBextractor(300, 1.2, 8, 1, 20, max_width=W, max_height=H)
+    for bad in ((-1.0, 50.0), (W + 0.0, 50.0), (50.0, H + 3.0), (float('nan'), 10.0), (float('inf'), 10.0), (1e12, 5.0)):
+        inc = np.zeros(2, gpu.capi.KP_DTYPE)
+        inc['x'] = [60.0, bad[0]]; inc['y'] = [60.0, bad[1]]
+        grid = np.zeros((H // mpd + 2, W // mpd + 2), np.int32, order='F')
+        with pytest.raises(gpu.capi.UvipError) as e:
+            ex(img, keypoints=inc, grid_2d=grid, min_px_dist=mpd, FullDetect=False, num_featsneeded=50)
+        assert e.value.code == gpu.capi.ERR_ARG
+        assert not grid.any()                                                   # a refused call leaves the caller's grid alone
+    k, d = ex(img)                                                              # the handle is still healthy (no sticky CUDA error)
+    assert len(k) >= 300
+
+
+def test_single_frame_graph_is_captured_once_per_call_shape(gpu, oracle, synth):
+    """src/Tracking.cc:946 changes num_featsneeded (and the grid contents) at every frame: the captured CUDA graph of the
+    single-frame call must survive that — one capture per call shape, results still equal to the oracle's"""
+    W, H, mpd = 752, 480, 20
+    ex = gpu.ORBextractor(1000, 1.2, 8, 1, 20, max_width=W, max_height=H)
+    oex = oracle.Extractor(1000, 1.2, 8, 1, 20)
+    c0 = ex.graph_captures()
+    for i, need in enumerate((400, 137, 1000, 3, 250, 999)):
+        img = synth.synth_frame(50 + i, W, H)
+        g1 = np.zeros((H // mpd + 2, W // mpd + 2), np.int32, order='F'); g1[i::7, ::3] = 1
+        g2 = g1.copy(order='F')
+        kps, desc = ex(img, grid_2d=g1, min_px_dist=mpd, FullDetect=False, num_featsneeded=need)
+        okps, odesc = oex(img, grid=g2, min_px_dist=mpd, full_detect=False, num_needed=need)
+        assert np.array_equal(g1, g2) and np.array_equal(kps['x'], okps['x']) and np.array_equal(desc, odesc)
+    assert ex.graph_captures() - c0 == 1
+    ex(synth.synth_frame(1, W, H))                                             # FullDetect=true is another shape
+    ex(synth.synth_frame(2, W, H))
+    assert ex.graph_captures() - c0 == 2
+
+
 def test_extract_batch_matches_single_frames(gpu, oracle, synth):
     """BASELINE config 2 shape: 640x512, 1500 kp, one HBM-resident batch; each frame equals its single-frame result."""
     nfr = 6

@@ -78,3 +78,25 @@ def test_gpu_klt_against_oracle_and_cv2(pkg, oracle, synth, golden):
     o1, ost, oerr = oracle.lk_track(P0, P1, pts, pts, 21, 5, 30, 0.01, 8)
     agree = st == ost
     assert agree.mean() > 0.99 and (np.abs(p1 - o1).max(1)[(st == 1) & (ost == 1)] <= POS_TOL).mean() >= 0.98
+
+
+@pytest.mark.gpu
+def test_gpu_klt_refuses_slots_of_another_geometry(pkg, synth):
+    """a pyramid built for another frame size invalidates the other slots (they are laid out for the old plan): tracking between
+    a stale slot and a fresh one is an argument error, not garbage with status 1"""
+    a = synth.synth_frame(1, 752, 480); c = synth.synth_frame(4, 401, 307)
+    klt = pkg.KLTTracker(752, 480, 21, 5, nslots=3)
+    klt.build_pyramid(0, a); klt.build_pyramid(1, a)
+    p0 = _pts(synth)[:50]
+    klt.track(0, 1, p0, p0, flags=8)
+    klt.build_pyramid(2, c)                                  # new geometry: slots 0 and 1 are stale now
+    with pytest.raises(pkg.capi.UvipError) as e:
+        klt.track(0, 2, p0, p0, flags=8)
+    assert e.value.code == pkg.capi.ERR_ARG
+    with pytest.raises(pkg.capi.UvipError):
+        klt.track(0, 1, p0, p0, flags=8)
+    klt.build_pyramid(0, c)
+    pts = p0[(p0[:, 0] < 390) & (p0[:, 1] < 300)]
+    p1, st, err = klt.track(0, 2, pts, pts, flags=8)         # same image in both slots: zero flow
+    assert st.sum() > 0 and np.abs(p1 - pts)[st == 1].max() < 1e-3
+    klt.close()

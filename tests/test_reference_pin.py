@@ -95,6 +95,24 @@ def test_oracle_equals_reference_occupancy_grid_sequence(oracle, synth):
 
 
 @needs_ref
+def test_oracle_equals_reference_incoming_keypoints_near_border(oracle, synth):
+    """incoming level-0 keypoints 2..15 px from the image border: IC_Angle and the descriptor pattern read the 16-px reflect-101
+    border of the level-0 buffer (src/ORBextractor.cc:523-534, :996-997); oracle and compiled reference agree bit for bit"""
+    W, H, mpd = 752, 480, 20
+    img = synth.synth_frame(33, W, H)
+    pts = [(x, y) for x in (2, 3, 7, 15, 16, 40, W - 41, W - 17, W - 16, W - 8, W - 4, W - 3) for y in (2, 5, 15, 16, 17, H - 17, H - 16, H - 6, H - 3)]
+    inc = np.zeros(len(pts), oracle.KP_DTYPE)
+    inc['x'] = [p[0] for p in pts]; inc['y'] = [p[1] for p in pts]
+    inc['x'] += 0.25; inc['y'] -= 0.25
+    inc['size'] = 31; inc['angle'] = -1; inc['octave'] = 0; inc['class_id'] = 3
+    g_o = np.zeros((H // mpd + 2, W // mpd + 2), np.int32, order='F'); g_r = g_o.copy(order='F')
+    a = oracle.Extractor(1000, 1.2, 8, 1, 20)(img, keypoints=inc, grid=g_o, min_px_dist=mpd, full_detect=False, num_needed=200)
+    b = R.Extractor(1000, 1.2, 8, 1, 20)(img, keypoints=inc, grid=g_r, min_px_dist=mpd, full_detect=False, num_needed=200)
+    assert_same(a, b, 'border')
+    assert np.array_equal(g_o, g_r) and len(a[0]) > len(inc)
+
+
+@needs_ref
 def test_reference_pointer_tiebreak_is_the_only_freedom(oracle, synth):
     """With plain malloc addresses the reference's (size, node pointer) sort (src/ORBextractor.cc:1151) may order
     equal-size nodes differently; the result may then differ from the pinned one only in a few keypoints per level."""
@@ -525,8 +543,9 @@ def test_fuse_equals_reference(oracle, synth, th):
 
 
 # ---------------------------------------------------------------------------------------------------- row M8 through the shim
-def m8_bundle(oracle, synth, which):
-    """scene for the keyframe-side searches (array order: oracle/ref_shim/m8_scene.h)"""
+def m8_bundle(oracle, synth, which, th=None):
+    """scene for the keyframe-side searches (array order: oracle/ref_shim/m8_scene.h); th < 0 makes the scene code call
+    Fuse with its DEFAULT th argument (include/ORBmatcher.h:85,88)"""
     f32 = np.float32
     W, H = 752, 480
     kps, desc = frame_for_matching(oracle, synth)
@@ -591,7 +610,7 @@ def m8_bundle(oracle, synth, which):
     R12 = (R1.astype(np.float64) @ R2.astype(np.float64).T).astype(np.float32)
     t12 = (t1.astype(np.float64) - R12.astype(np.float64) @ t2.astype(np.float64)).astype(np.float32)
     Scw = np.eye(4, dtype=np.float32); Scw[:3, :3] = f32(1.7) * R1; Scw[:3, 3] = f32(1.7) * t1
-    th = [3.0, 4.0, 10.0, 7.5, 0.0][which]
+    th = [3.0, 4.0, 10.0, 7.5, 0.0][which] if th is None else th
     pose = lambda R, t, O: np.concatenate([R.ravel(), t, O]).astype(np.float32)
     # fundamental matrix of the pair, F12 = K^-T [t12]x R12 K^-1 (src/LocalMapping.cc ComputeF12), and vocabulary nodes
     Kinv = np.linalg.inv(np.array([[fx, 0, cx], [0, fy, cy], [0, 0, 1]], np.float64))
@@ -627,6 +646,37 @@ def test_m8_reference_runs_every_branch(oracle, synth, which, tmp_path):
         assert (slot_owner >= 200000).sum() >= r
     else:
         assert (slot_owner >= 100000).sum() >= r
+
+
+@needs_mref
+@pytest.mark.parametrize('which', [0, 1])
+def test_m8_reference_fuse_default_is_2_5(oracle, synth, which, tmp_path):
+    """both Fuse overloads default to th = 2.5 (include/ORBmatcher.h:85,88; src/LocalMapping.cc:1236,1261 rely on it): the scene
+    called WITHOUT th equals th = 2.5 and differs from th = 3.0, so a drop-in header with another default cannot pass
+    test_shim_m8_fuse_defaults_equal_reference"""
+    out = {}
+    for name, th in (('default', -1.0), ('2.5', 2.5), ('3.0', 3.0)):
+        R.write_bundle(str(tmp_path / 's.bin'), m8_bundle(oracle, synth, which, th=th))
+        out[name] = R.m8_run(str(tmp_path / 's.bin'), str(tmp_path / 'o.bin'), which)
+    assert out['default'][0] == out['2.5'][0] and all(np.array_equal(a, b) for a, b in zip(out['default'][1], out['2.5'][1]))
+    assert not all(np.array_equal(a, b) for a, b in zip(out['default'][1], out['3.0'][1]))
+
+
+@needs_mref
+@pytest.mark.gpu
+@pytest.mark.parametrize('which', [0, 1])
+def test_shim_m8_fuse_defaults_equal_reference(gpu, oracle, synth, which, tmp_path):
+    """Fuse(pKF, vpMapPoints) / Fuse(pKF, Scw, vpPoints) with the default th through the shim == the reference's compiled call"""
+    import os, subprocess
+    assert os.path.exists(R.M8_EXE)
+    R.write_bundle(str(tmp_path / 's.bin'), m8_bundle(oracle, synth, which, th=-1.0))
+    r, ref = R.m8_run(str(tmp_path / 's.bin'), str(tmp_path / 'ref.bin'), which)
+    p = subprocess.run([R.M8_EXE, str(tmp_path / 's.bin'), str(tmp_path / 'shim.bin'), str(which)], capture_output=True, text=True)
+    assert p.returncode == 0, p.stderr
+    shim = R.read_bundle(str(tmp_path / 'shim.bin'))
+    assert int(p.stdout.strip()) == r and r > 100
+    for a, b, name in zip(shim, ref, ('return', 'slot owner', 'replaced', 'observation')):
+        assert np.array_equal(a, b), (M8_NAMES[which], name, int((a != b).sum()))
 
 
 @needs_mref

@@ -73,6 +73,13 @@ def lib():
         L.uvip_get_raw_corners.argtypes = [vp, i, i, vp, vp, vp, i, C.POINTER(i)]
         L.uvip_get_level_keypoints.argtypes = [vp, i, i, vp, vp, vp, i, C.POINTER(i)]
         L.uvip_extractor_launch_count.argtypes = [vp]
+        L.uvip_extractor_graph_captures.argtypes = [vp]
+        L.uvip_extractor_graph_captures.restype = C.c_longlong
+        L.uvip_extractor_stream.argtypes = [vp]
+        L.uvip_extractor_stream.restype = vp
+        L.uvip_matcher_stream.argtypes = [vp]
+        L.uvip_matcher_stream.restype = vp
+        L.uvip_matcher_sync.argtypes = [vp]
         L.uvip_extractor_profile.argtypes = [vp, i]
         L.uvip_extractor_stage_ms.argtypes = [vp, vp, C.POINTER(i)]
         L.uvip_clahe.argtypes = [vp, vp, i, i, i, C.c_double, i, i, vp, i]

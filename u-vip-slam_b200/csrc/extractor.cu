@@ -950,9 +950,12 @@ k_blur(const CUtensorMap* __restrict__ tmaps, const unsigned* __restrict__ btab,
 __global__ void __launch_bounds__(256)
 k_select(const unsigned* __restrict__ winners, const int* __restrict__ win_count, unsigned* __restrict__ sel, int* __restrict__ nsel,
          int sel_cap, int full_detect, int n_incoming, int32_t* __restrict__ grid, int grid_rows, int grid_cols, int min_px_dist, int num_needed,
-         int* __restrict__ status, const __grid_constant__ Plan P)
+         const int* __restrict__ dyn, int* __restrict__ status, const __grid_constant__ Plan P)
 {
     const int f = blockIdx.x, tid = threadIdx.x;
+    // single-frame call: the two arguments that change from call to call on the live path (src/Tracking.cc:946: num_featsneeded;
+    // the number of incoming keypoints) are read from device memory, so that the captured CUDA graph of the call stays valid
+    if (dyn) { n_incoming = dyn[0]; num_needed = dyn[1]; }
     const int* wc = win_count + (size_t)f * P.nlevels;
     unsigned* out = sel + (size_t)f * sel_cap;
     if (full_detect) {
@@ -993,6 +996,28 @@ k_select(const unsigned* __restrict__ winners, const int* __restrict__ win_count
     }
     if (over) { atomicOr(status, 8); n = 0; }
     nsel[f] = n;
+}
+
+// Level-0 border ring beyond BORDER_W, out to the full EDGE_THRESHOLD (16 px), in BOTH planes (the blurred plane's ring holds the
+// unblurred border).  Only the incoming level-0 keypoints of the occupancy-grid path (ComputeKeyPointsCopy,
+// src/ORBextractor.cc:523-534) can lie closer than 16 px to the image border: their IC_Angle disc reaches 15 px and their
+// descriptor pattern 18 px beyond the keypoint, i.e. into the reference's 16-px reflect-101 border.  Frame 0 of a single-frame call.
+__global__ void __launch_bounds__(256)
+k_ring16(uint8_t* __restrict__ pyr, uint8_t* __restrict__ blur, const __grid_constant__ Plan P)
+{
+    const LevelInfo& L = P.lv[0];
+    const int w = L.w, h = L.h, ps = L.pstride;
+    const size_t plane = L.poff + (size_t)EDGE * ps + EDGE;
+    uint8_t* a = pyr + plane; uint8_t* b = blur + plane;
+    const int RW = w + 2 * EDGE, NB = EDGE - BORDER_W;                   // bands of NB rows / columns outside the materialised ring
+    const int nrowpix = 2 * NB * RW, ncolpix = 2 * NB * (h + 2 * BORDER_W);
+    for (int i = blockIdx.x * 256 + threadIdx.x; i < nrowpix + ncolpix; i += gridDim.x * 256) {
+        int x, y;
+        if (i < nrowpix) { const int r = i / RW; x = i - r * RW - EDGE; y = r < NB ? r - EDGE : h + BORDER_W + (r - NB); }
+        else { const int j = i - nrowpix, r = j / (2 * NB), c = j - r * (2 * NB); y = r - BORDER_W; x = c < NB ? c - EDGE : w + BORDER_W + (c - NB); }
+        const uint8_t v = a[(ptrdiff_t)reflect101(y, h) * ps + reflect101(x, w)];
+        a[(ptrdiff_t)y * ps + x] = v; b[(ptrdiff_t)y * ps + x] = v;
+    }
 }
 
 // --------------------------------------------------------------------------------------------------------
@@ -1110,9 +1135,12 @@ k_describe(const uint8_t* __restrict__ pyr, const uint8_t* __restrict__ blur, co
         // patch is staged in shared memory by 13 asynchronous 4-byte copies per lane (cp.async: no registers, in flight during the
         // whole orientation phase); the 32 byte gathers per lane then cost a few bank-conflict cycles each instead of a fully
         // divergent trip through the L1 tag stage and a 64-bit address each.
-        // (detected keypoints are >= 16 px inside the image; an incoming keypoint closer than 5 / 2 px to the border is moved so that the
-        // staged rows stay inside the plane's 16-px padding: such a point has no defined descriptor in this layout anyway)
-        const int cxs = min(max(cx, 5), L.w - 6), cys = min(max(cy, 2), L.h - 3);
+        // (detected keypoints are >= 16 px inside the image.  An incoming level-0 keypoint may lie anywhere inside it: the full 16-px
+        // ring of level 0 is materialised for such calls (k_ring16), which covers every point at least 2 px inside the image exactly
+        // as the reference's padded buffer does; closer than 2 px the reference's own pattern reads leave its buffer row — undefined
+        // there — and the staged centre is moved to 2 px here.  A staged row is 40 bytes from an aligned start >= cx - 21: it may
+        // run past column w + 16 into the row padding / the next row, which is allocated memory that no gather touches.)
+        const int cxs = min(max(cx, 2), L.w - 3), cys = min(max(cy, 2), L.h - 3);
         {
             const int xs = (cxs - DESC_PR) & ~3;                                  // word-aligned first column (planes are 16 B aligned)
             const unsigned* src = reinterpret_cast<const unsigned*>(blur + plane + (ptrdiff_t)(cys - DESC_PR) * ps + xs) + prr * (ps >> 2) + pw;
@@ -1508,6 +1536,8 @@ struct uvip_extractor {
     DevBuf pyr, blur, cand, labels, winners, counters, sel, nsel, tabs, status, grid, incoming, tmaps, pat_t;
     DevBuf in_frames, out_kps, out_desc, out_n;      // staging for the host-buffer entry points
     DevBuf clahe_lut, clahe_io;                      // CLAHE LUTs and host-call staging
+    DevBuf dyn;                                      // single-frame call: {n_incoming, num_needed} read by k_select (outside the graph key)
+    int* h_dyn = nullptr;                            // pinned source of the dyn upload
     DevBuf in2, kps2, desc2, n2;                     // second staging set: uvip_extract_batch double-buffers its chunks
     cudaStream_t h2d_stream = nullptr, d2h_stream = nullptr;
     cudaEvent_t ev_h2d[2] = {nullptr, nullptr}, ev_comp[2] = {nullptr, nullptr}, ev_d2h[2] = {nullptr, nullptr};
@@ -1526,8 +1556,8 @@ struct uvip_extractor {
     // single-frame call (uvip_extract = operator()): the memsets + 13 kernels of one frame are captured once per call shape
     // into a CUDA graph and replayed (the call is launch-bound: a frame's kernels are tiny), results come back through one
     // pinned staging block with a single synchronisation
-    struct GraphKey { int w, h, stride, cap, full, n_in, gr, gc, mpd, need; const void *in, *kps, *desc, *n, *grid, *incoming, *pyr; };
-    GraphKey gkey; bool ghave = false; cudaGraphExec_t gexec = nullptr; long long glaunches = 0;
+    struct GraphKey { int w, h, stride, cap, full, has_in, gr, gc, mpd; const void *in, *kps, *desc, *n, *grid, *incoming, *pyr; };
+    GraphKey gkey; bool ghave = false; cudaGraphExec_t gexec = nullptr; long long glaunches = 0, gcaptures = 0;
     uint8_t* h_stage = nullptr; size_t h_stage_bytes = 0;      // pinned: [n, status | keypoints cap x 28 | descriptors cap x 32]
     std::mutex mu;
 };
@@ -1696,15 +1726,18 @@ static int ensure_plan(uvip_extractor* ex, int w, int h)
         set_last_error("frame %dx%d needs a larger working set than max_width x max_height provides", w, h);
         return UVIP_ERR_UNSUPPORTED;
     }
-    UVIP_CUDA(cudaStreamSynchronize(ex->stream));
+    // a new geometry rewrites the tables and tensor maps every queued launch group reads: nothing of this handle may still be running,
+    // on its own streams or on a caller's (device entry point)
+    if (ex->inflight) { set_last_error("frame geometry changes to %dx%d while a submitted batch is in flight: wait for its ticket first", w, h); return UVIP_ERR_ARG; }
+    UVIP_CUDA(cudaDeviceSynchronize());
     UVIP_CUDA(cudaFuncSetAttribute(k_quadtree, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)qt_smem_bytes(P.node_cap)));
     UVIP_CUDA(cudaFuncSetAttribute(k_fast, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)fast_smem_bytes(P)));
     UVIP_CUDA(cudaFuncSetAttribute(k_resize<true, RS_RMAX>, cudaFuncAttributeMaxDynamicSharedMemorySize, P.rs_boxw * P.rs_boxh + 128));
     UVIP_CUDA(cudaFuncSetAttribute(k_resize<false, RS_RMAX>, cudaFuncAttributeMaxDynamicSharedMemorySize, P.rs_boxw * P.rs_boxh + 128));
     UVIP_CUDA(cudaFuncSetAttribute(k_resize<true, RS_RSMALL>, cudaFuncAttributeMaxDynamicSharedMemorySize, P.rs_boxw * P.rs_boxh + 128));
     UVIP_CUDA(cudaFuncSetAttribute(k_resize<false, RS_RSMALL>, cudaFuncAttributeMaxDynamicSharedMemorySize, P.rs_boxw * P.rs_boxh + 128));
-    UVIP_CUDA(cudaMemcpy(ex->tabs.p, tabs.data(), tabs.size() * sizeof(int), cudaMemcpyHostToDevice));
-    // TMA descriptors of the pyramid planes: (x bytes, rows, frame) with a box of one FAST tile
+    // TMA descriptors of the pyramid planes: (x bytes, rows, frame) with a box of one FAST tile.  Everything is built in host
+    // temporaries first; tables, tensor maps and the plan are committed together once every encode has succeeded.
     {
         typedef CUresult (*encode_fn)(CUtensorMap*, CUtensorMapDataType, cuuint32_t, void*, const cuuint64_t*, const cuuint64_t*,
                                       const cuuint32_t*, const cuuint32_t*, CUtensorMapInterleave, CUtensorMapSwizzle,
@@ -1735,9 +1768,12 @@ static int ensure_plan(uvip_extractor* ex, int w, int h)
                                 CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
             if (r != CUDA_SUCCESS) { set_last_error("cuTensorMapEncodeTiled(resize, level %d) failed: %d", l, (int)r); return UVIP_ERR_CUDA; }
         }
+        ex->plan.W = 0;                                        // from here on the old plan is gone; a failed copy leaves "no plan"
+        UVIP_CUDA(cudaMemcpy(ex->tabs.p, tabs.data(), tabs.size() * sizeof(int), cudaMemcpyHostToDevice));
         UVIP_CUDA(cudaMemcpy(ex->tmaps.p, maps, sizeof(maps), cudaMemcpyHostToDevice));
     }
     ex->plan = P;
+    ex->ghave = false;                                         // a captured single-frame graph embeds the old plan
     return UVIP_OK;
 }
 
@@ -1745,7 +1781,7 @@ static int ensure_plan(uvip_extractor* ex, int w, int h)
 static int enqueue_group(uvip_extractor* ex, const uint8_t* d_frames, int nframes, int stride, size_t frame_pitch,
                          uvip_keypoint* d_kps, int32_t* d_n_out, int out_cap, uint8_t* d_desc,
                          int full_detect, int n_incoming, int grid_rows, int grid_cols, int min_px_dist, int num_needed, cudaStream_t st,
-                         bool reset_status = true)
+                         bool reset_status = true, const int* d_dyn = nullptr)
 {
     const Plan& P = ex->plan;
     uint8_t* pyr = ex->pyr.as<uint8_t>(); uint8_t* blur = ex->blur.as<uint8_t>();
@@ -1791,10 +1827,14 @@ static int enqueue_group(uvip_extractor* ex, const uint8_t* d_frames, int nframe
     PROF_MARK(3);
     k_blur<<<dim3(P.btiles, nframes), 256, 0, st>>>(ex->tmaps.as<CUtensorMap>(), ex->tabs.as<unsigned>() + P.tile_tab_off + P.ftiles + 1, pyr, blur, P);
     ex->launches++;
+    if (!full_detect && n_incoming > 0) {                      // incoming level-0 keypoints may sit inside the 16-px border zone
+        k_ring16<<<8, 256, 0, st>>>(pyr, blur, P);
+        ex->launches++;
+    }
     PROF_MARK(4);
     k_select<<<nframes, 256, 0, st>>>(ex->winners.as<unsigned>(), win_count, ex->sel.as<unsigned>(), ex->nsel.as<int>(), ex->sel_cap,
                                        full_detect, n_incoming, ex->grid.as<int32_t>(), grid_rows, grid_cols, min_px_dist, num_needed,
-                                       ex->status.as<int>(), P);
+                                       d_dyn, ex->status.as<int>(), P);
     ex->launches++;
     const int slots = out_cap < ex->sel_cap ? out_cap : ex->sel_cap;
     PROF_MARK(5);
@@ -1931,12 +1971,13 @@ int uvip_extractor_destroy(uvip_extractor* ex)
     if (ex->stream) cudaStreamSynchronize(ex->stream);
     DevBuf* bufs[] = {&ex->pyr, &ex->blur, &ex->cand, &ex->labels, &ex->winners, &ex->counters, &ex->sel,
                       &ex->nsel, &ex->tabs, &ex->status, &ex->grid, &ex->incoming, &ex->tmaps, &ex->pat_t, &ex->in_frames, &ex->out_kps, &ex->out_desc, &ex->out_n,
-                      &ex->in2, &ex->kps2, &ex->desc2, &ex->n2, &ex->clahe_lut, &ex->clahe_io};
+                      &ex->in2, &ex->kps2, &ex->desc2, &ex->n2, &ex->clahe_lut, &ex->clahe_io, &ex->dyn};
     for (DevBuf* b : bufs) b->release();
     for (cudaEvent_t e : ex->prof_ev) cudaEventDestroy(e);
     for (int i = 0; i < 2; i++) { if (ex->ev_h2d[i]) cudaEventDestroy(ex->ev_h2d[i]); if (ex->ev_comp[i]) cudaEventDestroy(ex->ev_comp[i]); if (ex->ev_d2h[i]) cudaEventDestroy(ex->ev_d2h[i]); }
     for (int i = 0; i < 2; i++) if (ex->ev_done[i]) cudaEventDestroy(ex->ev_done[i]);
     if (ex->h_status) cudaFreeHost(ex->h_status);
+    if (ex->h_dyn) cudaFreeHost(ex->h_dyn);
     if (ex->gexec) cudaGraphExecDestroy(ex->gexec);
     if (ex->h_stage) cudaFreeHost(ex->h_stage);
     if (ex->h2d_stream) cudaStreamDestroy(ex->h2d_stream);
@@ -1949,6 +1990,8 @@ int uvip_extractor_destroy(uvip_extractor* ex)
 int uvip_extractor_levels(const uvip_extractor* ex) { return ex ? ex->prm.nlevels : 0; }
 float uvip_extractor_scale_factor(const uvip_extractor* ex) { return ex ? (float)(double)ex->prm.scale_factor : 0.f; }
 long long uvip_extractor_launch_count(const uvip_extractor* ex) { return ex ? ex->launches : 0; }
+long long uvip_extractor_graph_captures(const uvip_extractor* ex) { return ex ? ex->gcaptures : 0; }
+void* uvip_extractor_stream(uvip_extractor* ex) { return ex ? (void*)ex->stream : nullptr; }
 
 int uvip_extractor_tables(const uvip_extractor* ex, float* scale, float* inv_scale, int32_t* quota, int32_t* umax)
 {
@@ -1967,6 +2010,10 @@ int uvip_extract_batch_device(uvip_extractor* ex, const uint8_t* d_frames, int n
 {
     UVIP_CHECK_ARG(ex && d_frames && d_kps && d_n_out && d_desc);
     UVIP_CHECK_ARG(nframes >= 1 && nframes <= ex->prm.max_batch && w > 0 && h > 0 && stride >= w && cap >= 1);
+    std::lock_guard<std::mutex> lk(ex->mu);
+    // the launch group uses the handle's pyramid / candidate / selection scratch, which batches queued by uvip_extract_batch_submit
+    // are still working on
+    if (ex->inflight) { set_last_error("a submitted batch is in flight on this handle: wait for its ticket first"); return UVIP_ERR_ARG; }
     DeviceGuard g(ex->device);
     int rc = ensure_plan(ex, w, h);
     if (rc) return rc;
@@ -2115,6 +2162,15 @@ int uvip_extract(uvip_extractor* ex, const uint8_t* image, int w, int h, int str
     const int n_in = (!full_detect && *n_inout > 0) ? *n_inout : 0;
     UVIP_CHECK_ARG(n_in <= 4096 && n_in <= cap);
     if (!full_detect) UVIP_CHECK_ARG(grid && grid_rows > 0 && grid_cols > 0 && min_px_dist > 0);
+    // incoming keypoints become level-0 points (ComputeKeyPointsCopy, src/ORBextractor.cc:523-534): the reference indexes its level-0
+    // buffer at (cvRound(y), cvRound(x)) unchecked — outside the image that is a read out of bounds there and a refused call here
+    for (int i = 0; i < n_in; i++) {
+        const float x = kps[i].x, y = kps[i].y;
+        if (!(x == x) || !(y == y) || !(fabsf(x) < 1e9f) || !(fabsf(y) < 1e9f) || lrintf(x) < 0 || lrintf(x) >= w || lrintf(y) < 0 || lrintf(y) >= h) {
+            set_last_error("incoming keypoint %d at (%g, %g) lies outside the %dx%d image", i, (double)x, (double)y, w, h);
+            return UVIP_ERR_ARG;
+        }
+    }
     std::lock_guard<std::mutex> lk(ex->mu);
     if (ex->inflight) { set_last_error("a submitted batch is in flight on this handle: wait for its ticket first"); return UVIP_ERR_ARG; }
     DeviceGuard g(ex->device);
@@ -2131,19 +2187,26 @@ int uvip_extract(uvip_extractor* ex, const uint8_t* image, int w, int h, int str
         if ((rc = ex->grid.reserve((size_t)grid_rows * grid_cols * 4))) return rc;
         UVIP_CUDA(cudaMemcpyAsync(ex->grid.p, grid, (size_t)grid_rows * grid_cols * 4, cudaMemcpyHostToDevice, st));
         if (n_in) {
-            if ((rc = ex->incoming.reserve((size_t)n_in * sizeof(uvip_keypoint)))) return rc;
+            if ((rc = ex->incoming.reserve(align_up((size_t)n_in, 512) * sizeof(uvip_keypoint)))) return rc;   // coarse steps: the pointer is part of the graph key
             UVIP_CUDA(cudaMemcpyAsync(ex->incoming.p, kps, (size_t)n_in * sizeof(uvip_keypoint), cudaMemcpyHostToDevice, st));
         }
     }
+    // the arguments that change from frame to frame on the live path reach k_select through device memory
+    if ((rc = ex->dyn.reserve(16))) return rc;
+    if (!ex->h_dyn) UVIP_CUDA(cudaHostAlloc((void**)&ex->h_dyn, 16, cudaHostAllocDefault));
+    ex->h_dyn[0] = n_in; ex->h_dyn[1] = num_needed;
+    UVIP_CUDA(cudaMemcpyAsync(ex->dyn.p, ex->h_dyn, 8, cudaMemcpyHostToDevice, st));
     if (ex->prof) {                                            // per-stage event timing wants plain launches
         rc = enqueue_group(ex, ex->in_frames.as<uint8_t>(), 1, stride, fbytes, ex->out_kps.as<uvip_keypoint>(), ex->out_n.as<int32_t>(),
-                           cap, ex->out_desc.as<uint8_t>(), full_detect ? 1 : 0, n_in, grid_rows, grid_cols, min_px_dist, num_needed, st);
+                           cap, ex->out_desc.as<uint8_t>(), full_detect ? 1 : 0, n_in, grid_rows, grid_cols, min_px_dist, num_needed, st, true, ex->dyn.as<int>());
         if (rc) return rc;
     } else {
         uvip_extractor::GraphKey key;
         memset(&key, 0, sizeof(key));
-        key.w = w; key.h = h; key.stride = stride; key.cap = cap; key.full = full_detect ? 1 : 0; key.n_in = n_in;
-        key.gr = full_detect ? 0 : grid_rows; key.gc = full_detect ? 0 : grid_cols; key.mpd = full_detect ? 0 : min_px_dist; key.need = full_detect ? 0 : num_needed;
+        // num_needed and the NUMBER of incoming keypoints are not part of the key (they change almost every frame while the system is
+        // WORKING, src/Tracking.cc:946: a key that contained them re-captured and re-instantiated the graph per call)
+        key.w = w; key.h = h; key.stride = stride; key.cap = cap; key.full = full_detect ? 1 : 0; key.has_in = n_in > 0 ? 1 : 0;
+        key.gr = full_detect ? 0 : grid_rows; key.gc = full_detect ? 0 : grid_cols; key.mpd = full_detect ? 0 : min_px_dist;
         key.in = ex->in_frames.p; key.kps = ex->out_kps.p; key.desc = ex->out_desc.p; key.n = ex->out_n.p; key.grid = ex->grid.p;
         key.incoming = ex->incoming.p; key.pyr = ex->pyr.p;
         if (!ex->ghave || memcmp(&key, &ex->gkey, sizeof(key)) != 0) {
@@ -2153,7 +2216,7 @@ int uvip_extract(uvip_extractor* ex, const uint8_t* image, int w, int h, int str
             const long long l0 = ex->launches;
             UVIP_CUDA(cudaStreamBeginCapture(st, cudaStreamCaptureModeThreadLocal));
             rc = enqueue_group(ex, ex->in_frames.as<uint8_t>(), 1, stride, fbytes, ex->out_kps.as<uvip_keypoint>(), ex->out_n.as<int32_t>(),
-                               cap, ex->out_desc.as<uint8_t>(), full_detect ? 1 : 0, n_in, grid_rows, grid_cols, min_px_dist, num_needed, st);
+                               cap, ex->out_desc.as<uint8_t>(), full_detect ? 1 : 0, n_in, grid_rows, grid_cols, min_px_dist, num_needed, st, true, ex->dyn.as<int>());
             const cudaError_t ce = cudaStreamEndCapture(st, &graph);
             ex->glaunches = ex->launches - l0; ex->launches = l0;
             if (rc) { if (graph) cudaGraphDestroy(graph); return rc; }
@@ -2161,7 +2224,7 @@ int uvip_extract(uvip_extractor* ex, const uint8_t* image, int w, int h, int str
             const cudaError_t ci = cudaGraphInstantiate(&ex->gexec, graph, 0);
             cudaGraphDestroy(graph);
             UVIP_CUDA(ci);
-            ex->gkey = key; ex->ghave = true;
+            ex->gkey = key; ex->ghave = true; ex->gcaptures++;
         }
         UVIP_CUDA(cudaGraphLaunch(ex->gexec, st));
         ex->launches += ex->glaunches;

@@ -176,6 +176,7 @@ using namespace uvip;
 struct uvip_klt {
     int device = 0, max_w = 0, max_h = 0, max_level = 0, win = 0, nslots = 0;
     int w = 0, h = 0;                                   // geometry of the current plan
+    std::vector<int> slot_w, slot_h;                    // geometry every slot's pyramid was built for (0 = empty / invalidated)
     KltPlan plan;
     size_t img_bytes = 0, der_elems = 0;
     cudaStream_t stream = nullptr;
@@ -225,6 +226,7 @@ int uvip_klt_create(int device, int max_width, int max_height, int win, int max_
     if (rc || cudaStreamCreateWithFlags(&k->stream, cudaStreamNonBlocking) != cudaSuccess) { uvip_klt_destroy(k); return UVIP_ERR_CUDA; }
     cudaMemset(k->der.p, 0, k->der.cap);                 // derivative borders are BORDER_CONSTANT 0 and are never written
     k->w = k->h = 0;
+    k->slot_w.assign((size_t)nslots, 0); k->slot_h.assign((size_t)nslots, 0);
     *out = k;
     return UVIP_OK;
 }
@@ -250,7 +252,10 @@ int uvip_klt_build_pyramid(uvip_klt* k, int slot, const uint8_t* image, int w, i
         klt_make_plan(k, w, h);
         k->img_bytes = ib; k->der_elems = de;
         UVIP_CUDA(cudaMemsetAsync(k->der.p, 0, k->der.cap, st));
+        // the other slots still hold pyramids laid out for the old geometry: they are unusable with the new plan
+        for (int s = 0; s < k->nslots; s++) k->slot_w[(size_t)s] = k->slot_h[(size_t)s] = 0;
     }
+    k->slot_w[(size_t)slot] = w; k->slot_h[(size_t)slot] = h;
     const KltPlan& P = k->plan;
     uint8_t* img = k->img.as<uint8_t>() + (size_t)slot * k->img_bytes;
     short2* der = k->der.as<short2>() + (size_t)slot * k->der_elems;
@@ -291,6 +296,11 @@ int uvip_klt_track(uvip_klt* k, int slot_prev, int slot_next, const float* prev_
     if (n == 0) return UVIP_OK;
     UVIP_CHECK_ARG(prev_pts && next_pts && status);
     std::lock_guard<std::mutex> lk(k->mu);
+    if (k->slot_w[(size_t)slot_prev] != k->w || k->slot_h[(size_t)slot_prev] != k->h || k->slot_w[(size_t)slot_next] != k->w || k->slot_h[(size_t)slot_next] != k->h) {
+        set_last_error("KLT slots %d / %d do not hold pyramids of the current %dx%d geometry (a build with another frame size invalidates the other slots)",
+                       slot_prev, slot_next, k->w, k->h);
+        return UVIP_ERR_ARG;
+    }
     DeviceGuard g(k->device);
     if (max_iter < 0) max_iter = 0; if (max_iter > 100) max_iter = 100;            // calcOpticalFlowPyrLK clamps the criteria
     if (epsilon < 0) epsilon = 0; if (epsilon > 10) epsilon = 10;

@@ -695,6 +695,14 @@ int uvip_matcher_destroy(uvip_matcher* m)
 }
 
 long long uvip_matcher_launch_count(const uvip_matcher* m) { return m ? m->launches : 0; }
+void* uvip_matcher_stream(uvip_matcher* m) { return m ? (void*)m->stream : nullptr; }
+int uvip_matcher_sync(uvip_matcher* m)
+{
+    UVIP_CHECK_ARG(m);
+    DeviceGuard g(m->device);
+    UVIP_CUDA(cudaStreamSynchronize(m->stream));
+    return UVIP_OK;
+}
 
 static int launch_knn2(uvip_matcher* m, const uint8_t* d_q, const int32_t* d_nq, size_t q_pitch,
                        const uint8_t* d_t, const int32_t* d_nt, size_t t_pitch, int npairs, int max_nq,

@@ -62,8 +62,8 @@ class ORBextractor:
             image = np.ascontiguousarray(image)
         H, W = image.shape
         n_in = 0 if keypoints is None else len(keypoints)
-        if cap is None:
-            cap = self.nfeatures + 8 * self.nlevels + 64 + n_in
+        if cap is None:      # incoming keypoints in steps of 256: cap is part of the single-frame call shape (CUDA-graph key)
+            cap = self.nfeatures + 8 * self.nlevels + 64 + (n_in + 255) // 256 * 256
         kps = np.zeros(cap, KP_DTYPE)
         if n_in:
             kps[:n_in] = keypoints
@@ -116,6 +116,9 @@ class ORBextractor:
 
     def launch_count(self):
         return int(lib().uvip_extractor_launch_count(self.h))
+
+    def graph_captures(self):
+        return int(lib().uvip_extractor_graph_captures(self.h))
 
     STAGES = ('pyramid', 'fast', 'quadtree', 'blur', 'select', 'describe')
 

@@ -43,7 +43,8 @@ public:
         assert(img.type() == CV_8UC1);
         ensure(img.cols, img.rows);
         const int n_in = FullDetect ? 0 : (int)keypoints.size();
-        const int cap = nfeatures + 8 * nlevels + 64 + n_in;
+        // incoming keypoints counted in steps of 256: cap is part of the call shape the library keys its captured CUDA graph on
+        const int cap = nfeatures + 8 * nlevels + 64 + (n_in + 255) / 256 * 256;
         std::vector<uvip_keypoint> kp((size_t)cap);
         static_assert(sizeof(uvip_keypoint) == sizeof(cv::KeyPoint), "cv::KeyPoint layout");
         if (n_in) std::memcpy(kp.data(), keypoints.data(), sizeof(uvip_keypoint) * (size_t)n_in);

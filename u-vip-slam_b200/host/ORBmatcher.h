@@ -23,10 +23,15 @@ namespace USLAM {
 
 class ORBmatcher {
 public:
+    // The reference builds a stack-local ORBmatcher in front of every search (src/Tracking.cc:2222,2387,2426,3015,
+    // src/LocalMapping.cc:1080,1230, src/LoopClosing.cc:373,454,699), from three host threads.  Construction and destruction
+    // therefore cost nothing here: the device handle (stream, scratch buffers, pinned staging) belongs to the CALLING THREAD
+    // (thread_local, created at the thread's first search, destroyed when the thread exits) and is looked up per call, so an
+    // instance can also be handed to another thread.
     ORBmatcher(float nnratio = 0.6, bool checkOri = true) : mfNNratio(nnratio), mbCheckOrientation(checkOri) {}
-    ~ORBmatcher() { if (handle_) uvip_matcher_destroy(handle_); }
-    ORBmatcher(const ORBmatcher&) = delete;
-    ORBmatcher& operator=(const ORBmatcher&) = delete;
+    ~ORBmatcher() {}
+    // device the calling thread's handle is created on (default 0); call before the thread's first search
+    static void SetDevice(int device) { tls().device = device; }
 
     // src/ORBmatcher.cc:1794-1810.  One pair of 32-byte rows: stays a host popcount, exactly as SURVEY section 2 row 4
     // prescribes for MapPoint::ComputeDistinctiveDescriptors (N is tiny); batches go through uvip_descriptor_distance.
@@ -361,7 +366,7 @@ protected:
 public:
     // Fuse(KeyFrame* pKF, vector<MapPoint*>& vpMapPoints, float th)  (src/ORBmatcher.cc:1016-1134; src/LocalMapping.cc:1236,1261)
     template <class KeyFrameT, class MapPointT>
-    int Fuse(KeyFrameT* pKF, std::vector<MapPointT*>& vpMapPoints, const float th = 3.0f)
+    int Fuse(KeyFrameT* pKF, std::vector<MapPointT*>& vpMapPoints, const float th = 2.5f)   // include/ORBmatcher.h:85
     {
         ensure();
         Pose3 P; read3x3(pKF->GetRotation(), P.R); read3(pKF->GetTranslation(), P.t); read3(pKF->GetCameraCenter(), P.Ow);
@@ -657,16 +662,23 @@ public:
 
 protected:
     float RadiusByViewingCos(const float& viewCos) { return uvip_radius_by_viewing_cos(viewCos); }
+    struct ThreadHandle {
+        uvip_matcher* h = nullptr; int device = 0;
+        ~ThreadHandle() { if (h) uvip_matcher_destroy(h); }
+    };
+    static ThreadHandle& tls() { static thread_local ThreadHandle t; return t; }
     void ensure()
     {
-        if (!handle_ && uvip_matcher_create(0, &handle_) != UVIP_OK)
+        ThreadHandle& t = tls();
+        if (!t.h && uvip_matcher_create(t.device, &t.h) != UVIP_OK)
             throw std::runtime_error(std::string("uvip_matcher_create: ") + uvip_last_error());
+        handle_ = t.h;
     }
     static void check(int rc, const char* what) { if (rc != UVIP_OK) throw std::runtime_error(std::string(what) + ": " + uvip_last_error()); }
 
     float mfNNratio;
     bool mbCheckOrientation;
-    uvip_matcher* handle_ = nullptr;
+    uvip_matcher* handle_ = nullptr;        // the calling thread's handle, refreshed by ensure() at every call (not owned)
 };
 
 }  // namespace USLAM

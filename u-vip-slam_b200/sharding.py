@@ -37,14 +37,22 @@ def merge_top2_numpy(idx_parts, dist_parts):
     return oi.astype(np.int32), od.astype(np.int32)
 
 
+CUDA_STREAM_LEGACY = 1      # cudaStreamLegacy: the C-ABI treats a NULL stream as "the handle's own stream", never as the default stream
+
+
 def gpu_sharded_knn2(pkg, matcher, d_q, d_t_shard, idx_base, world, dist_mod=None, stream_ptr=None):
-    """device path: uvip_knn2_device on the local shard, all_gather of the 2 x (nq, 2) int32 results, uvip_knn2_merge_device"""
+    """device path: uvip_knn2_device on the local shard, all_gather of the 2 x (nq, 2) int32 results, uvip_knn2_merge_device.
+    Every step runs on ONE stream — torch's current stream unless stream_ptr names another (which must then be torch's current
+    stream too, since the NCCL collectives are ordered against that one): the kernels write oi / od before the gather reads them
+    and the merge runs behind the gather.  Torch's default stream has handle 0; it is passed as cudaStreamLegacy."""
     import ctypes as C
     import torch
     L = pkg.capi.lib()
     nq = d_q.shape[0]
     oi = torch.empty((nq, 2), dtype=torch.int32, device=d_q.device); od = torch.empty_like(oi)
-    sp = C.c_void_p(stream_ptr) if stream_ptr else None
+    if stream_ptr is None:
+        stream_ptr = torch.cuda.current_stream(d_q.device).cuda_stream
+    sp = C.c_void_p(stream_ptr if stream_ptr else CUDA_STREAM_LEGACY)
     pkg.capi.check(L.uvip_knn2_device(matcher.h, C.c_void_p(d_q.data_ptr()), nq, C.c_void_p(d_t_shard.data_ptr()), d_t_shard.shape[0],
                                       int(idx_base), C.c_void_p(oi.data_ptr()), C.c_void_p(od.data_ptr()), sp))
     if world == 1:
