@@ -34,7 +34,7 @@ def parse():
     ap.add_argument('--warmup', type=int, default=3)
     ap.add_argument('--impl', default='ours', choices=['ours', 'reference'])
     ap.add_argument('--batch', type=int, default=256, help='frames per step and per GPU')
-    ap.add_argument('--ref-frames', type=int, default=0, help='frames per step of the reference arm (0 = 4 x cores)')
+    ap.add_argument('--ref-frames', type=int, default=0, help='frames per step of the reference arm (0 = --batch, the same step as our arm)')
     ap.add_argument('--e2e-chunk', type=int, default=0, help='frames per pipeline chunk of the host-buffer entry point (0 = batch/2)')
     ap.add_argument('--no-extras', action='store_true', help='skip the Hamming-only and cpu_baseline legs')
     ap.add_argument('--workload', default='frames', choices=['frames', 'knn', 'search', 'next'],
@@ -169,20 +169,81 @@ def hbm_peak():
         return FALLBACK_HBM_GBS, 'fallback'
 
 
-def ncu_pipes():
-    """per-kernel issue-slot / ALU-pipe utilisation from the committed ncu launch list (static evidence, not measured live)"""
+def kernel_source_hash():
+    """sha256 over the kernel sources: the committed ncu evidence names the sources it was captured from (tools/pipes_from_launches.py
+    writes the same hash), so a bench run on changed kernels reports that evidence as stale instead of quoting it"""
+    import hashlib
+    h = hashlib.sha256()
+    d = os.path.join(ROOT, 'u-vip-slam_b200', 'csrc')
+    for fn in sorted(os.listdir(d)):
+        if fn.endswith(('.cu', '.cuh', '.inc')):
+            h.update(fn.encode()); h.update(open(os.path.join(d, fn), 'rb').read())
+    return h.hexdigest()[:16]
+
+
+def _static_evidence(name):
     try:
-        return json.load(open(os.path.join(ROOT, 'profiles', 'kernel_pipes.json')))
+        d = json.load(open(os.path.join(ROOT, 'profiles', name)))
     except Exception:
-        return {}
+        return {}, True
+    return d, d.get('_source_hash') != kernel_source_hash()
+
+
+def ncu_pipes():
+    """per-kernel issue-slot / ALU-pipe utilisation and warp-instruction counts from the committed ncu launch list (static evidence:
+    the instruction count of a kernel is a property of the code and the input, the utilisation figures are not measured live);
+    returns (dict, stale)"""
+    return _static_evidence('kernel_pipes.json')
 
 
 def ncu_traffic():
-    """dram bytes per launch of the dominant kernel from the committed ncu --set full capture, if any"""
+    """dram bytes per launch of every stage's kernel from the committed ncu launch list; returns (dict, stale)"""
+    return _static_evidence('roofline_traffic.json')
+
+
+def _cv2_version():
     try:
-        return json.load(open(os.path.join(ROOT, 'profiles', 'roofline_traffic.json')))
+        import cv2
+        return cv2.__version__
     except Exception:
-        return {}
+        return 'absent'
+
+
+def cv2_composite(frames, threads):
+    """SURVEY 8(d) cross-check (iii): the OpenCV primitives the reference calls, through the cv2 wheel of this image (whole-level
+    FAST instead of per-cell calls, no quadtree / orientation / descriptors): pyramid (7 resize + 8 copyMakeBorder), FAST th 20
+    with NMS and GaussianBlur 7x7 sigma 2 on all 8 levels, then BFMatcher.knnMatch(k=2) on 1000 x 1000 descriptors per frame
+    pair.  Returns frames/s, or None when cv2 is missing."""
+    try:
+        import cv2
+        import numpy as np
+    except Exception:
+        return None
+    cv2.setNumThreads(threads)
+    fast = cv2.FastFeatureDetector_create(threshold=FAST_TH, nonmaxSuppression=True)
+    bf = cv2.BFMatcher(cv2.NORM_HAMMING)
+    rng = np.random.default_rng(0)
+    da = rng.integers(0, 256, (NFEAT, 32), dtype=np.uint8); db = rng.integers(0, 256, (NFEAT, 32), dtype=np.uint8)
+    inv = 1.0
+    sizes = []
+    for _ in range(1, NLEVELS):
+        inv /= SCALE
+        sizes.append((int(round(W * inv)), int(round(H * inv))))
+
+    def one(img):
+        lv = img
+        for l in range(NLEVELS):
+            if l:
+                lv = cv2.resize(lv, sizes[l - 1], interpolation=cv2.INTER_LINEAR)
+            cv2.copyMakeBorder(lv, 16, 16, 16, 16, cv2.BORDER_REFLECT_101)
+            fast.detect(lv, None)
+            cv2.GaussianBlur(lv, (7, 7), 2, 2, borderType=cv2.BORDER_REFLECT_101)
+        bf.knnMatch(da, db, k=2)
+    one(frames[0])
+    t0 = time.perf_counter(); n = 0
+    while n < 4 or time.perf_counter() - t0 < 1.5:
+        one(frames[n % len(frames)]); n += 1
+    return n / (time.perf_counter() - t0)
 
 
 # ------------------------------------------------------------------------------------------------ reference arm
@@ -225,7 +286,7 @@ def run_reference(args):
     from oracle import oracle as O
     O.lib()
     cores = os.cpu_count() or 1
-    nfr = args.ref_frames or max(8, 4 * cores)
+    nfr = args.ref_frames or args.batch
     frames = make_frames(pkg.synth, nfr, 1)
     for _ in range(max(1, min(args.warmup, 1))):
         cpu_reference(frames[:max(2, cores)], cores)
@@ -237,14 +298,95 @@ def run_reference(args):
         'impl': 'reference', 'metric': METRIC, 'value': fps, 'unit': 'frames/s', 'n_gpus': args.gpus, 'steps': args.steps,
         'warmup': args.warmup, 'ms_per_step': 1e3 * t / args.steps, 'higher_is_better': True, 'scaling': 'weak',
         'vs_baseline': None, 'dtype': 'u8', 'data': 'synthetic',
-        'config': {'workload': set_shape(args.shape) + ' + brute-force Hamming kNN2 of consecutive '
-                               'frames (BASELINE %s shape, batched)' % {'euroc': 'config 1', 'aqualoc': 'config 2', 'hd': 'config 5'}[args.shape], 'frames_per_step': nfr, 'keypoints': NFEAT},
+        'config': workload_config(args, nfr, args.gpus),
         'cpu_baseline': {'value': fps, 'unit': 'frames/s', 'cores': cores, 'kind': cpu_kind(),
                          'sample': '%d frames per step, OpenMP over frames; %s' % (nfr, CPU_KIND_NOTE[cpu_kind()])},
         'e2e': {'value': fps, 'unit': 'frames/s', 'h2d_bytes_per_step': 0, 'd2h_bytes_per_step': 0},
     }
     print(json.dumps(line), flush=True)
     return 0
+
+
+def workload_config(args, frames_per_step, world):
+    """the `config` object of both arms (identical for the same command line)"""
+    return {'workload': set_shape(args.shape) + ' + brute-force Hamming kNN2 of consecutive frames (BASELINE %s shape, batched)'
+                        % {'euroc': 'config 1', 'aqualoc': 'config 2', 'hd': 'config 5'}[args.shape],
+            'frames_per_step_per_gpu': frames_per_step, 'keypoints': NFEAT,
+            'l2': 'inputs alternate between two %d MB batches and each step streams a %.1f GB pyramid working set (> 126 MB L2)'
+                  % (frames_per_step * W * H >> 20, 2.0 * frames_per_step * B_FRAME_BYTES / 1e9),
+            'parallelism': 'frames sharded over %d GPU(s), no collective' % world}
+
+
+# ------------------------------------------------------------------------------------------------ sharded kNN (config 4)
+def sharded_knn_measure(pkg, torch, dist, dev, rank, world, local, n, passes, stream):
+    """BASELINE config 4: n x n brute-force kNN2, train rows sharded contiguously over the ranks, queries replicated, per-query top-2
+    all-gathered over NCCL and merged by (distance, global index).  Times the three phases separately (CUDA events on `stream`,
+    which must be torch's current stream: the collectives are ordered against it), max over ranks, and ALWAYS checks the first
+    2048 queries against the oracle's scan of the FULL train set on rank 0.  Returns the record on rank 0, None elsewhere."""
+    import ctypes as C
+    import numpy as np
+    L = pkg.capi.lib(); chk = pkg.capi.check
+    T, Q = pkg.synth.knn_database(n, n)
+    b = pkg.sharding.shard_bounds(n, world)
+    dq = torch.from_numpy(Q).to(dev); dt = torch.from_numpy(np.ascontiguousarray(T[b[rank]:b[rank + 1]])).to(dev)
+    m = pkg.ORBmatcher(0.75, True, device=local)
+    nq = n
+    oi = torch.empty((nq, 2), dtype=torch.int32, device=dev); od = torch.empty_like(oi)
+    gi = torch.empty((world, nq, 2), dtype=torch.int32, device=dev); gd = torch.empty_like(gi)
+    mi = torch.empty_like(oi); md = torch.empty_like(od)
+    sp = C.c_void_p(stream.cuda_stream)
+    P = lambda t: C.c_void_p(t.data_ptr())
+    ev = lambda: torch.cuda.Event(enable_timing=True)
+
+    def one(rec=None):
+        e = [ev() for _ in range(4)] if rec is not None else None
+        if e: e[0].record(stream)
+        chk(L.uvip_knn2_device(m.h, P(dq), nq, P(dt), dt.shape[0], int(b[rank]), P(oi), P(od), sp))
+        if e: e[1].record(stream)
+        if world > 1:
+            dist.all_gather_into_tensor(gi, oi); dist.all_gather_into_tensor(gd, od)
+        if e: e[2].record(stream)
+        if world > 1:
+            chk(L.uvip_knn2_merge_device(m.h, P(gi), P(gd), world, nq * 2, nq, P(mi), P(md), sp))
+        if e: e[3].record(stream); rec.append(e)
+    for _ in range(2):
+        one()
+    torch.cuda.synchronize(dev)
+    if world > 1:
+        dist.barrier()
+    rec = []
+    t0 = ev(); t1 = ev()
+    t0.record(stream)
+    for _ in range(passes):
+        one(rec)
+    t1.record(stream)
+    torch.cuda.synchronize(dev)
+    if world > 1:
+        dist.barrier()
+    tot = t0.elapsed_time(t1)
+    ph = [sum(e[i].elapsed_time(e[i + 1]) for e in rec) for i in range(3)]
+    if world > 1:
+        tt = torch.tensor([tot] + ph, dtype=torch.float64, device=dev); dist.all_reduce(tt, op=dist.ReduceOp.MAX)
+        tot, ph = float(tt[0].item()), [float(v) for v in tt[1:].tolist()]
+    ri_dev = (mi if world > 1 else oi)[:2048].cpu().numpy(); rd_dev = (md if world > 1 else od)[:2048].cpu().numpy()
+    if rank != 0:
+        return None
+    from oracle import oracle as O
+    tc = time.perf_counter()
+    ri, rd = O.knn2(Q[:2048], T, threads=os.cpu_count() or 1)
+    tc = time.perf_counter() - tc
+    ok = bool(np.array_equal(ri_dev, ri) and np.array_equal(rd_dev, rd))
+    ties = int((rd[:, 0] == rd[:, 1]).sum())
+    popc = C.c_double(); chk(L.uvip_popc_peak(local, 4096, C.byref(popc)))
+    pps = float(n) * n * passes / (tot * 1e-3)
+    return {'workload': 'BASELINE config 4: %d x %d 256-bit descriptors (SURVEY Appendix B row 4 generator), train rows sharded over %d GPU(s), queries '
+                        'replicated, NCCL all-gather of the per-query top-2 (16 B per query and rank) + (distance, global index) merge' % (n, n, world),
+            'pairs_per_s': pps, 'unit': 'pairs/s', 'n_gpus': world, 'passes': passes, 'ms_per_pass': tot / passes,
+            'phase_ms_per_pass': {'shard_knn2_kernel': ph[0] / passes, 'nccl_all_gather_x2': ph[1] / passes, 'merge_kernel': ph[2] / passes},
+            'scaling': 'strong', 'matches_oracle_first_2048_queries': ok, 'exact_distance_ties_in_checked_queries': ties,
+            'oracle_check_seconds': tc, 'popc_per_pair_issued': 4,
+            'popc_frac_issued_of_n_gpus': pps * 4 / (popc.value * world), 'popc_frac_8_per_pair_accounting': pps * 8 / (popc.value * world),
+            'popc_peak_measured_per_s_one_gpu': popc.value}
 
 
 # ------------------------------------------------------------------------------------------------ our arm
@@ -377,15 +519,16 @@ def run_ours(args):
     ex_e2e = pkg.ORBextractor(NFEAT, SCALE, NLEVELS, pkg.ORBextractor.FAST_SCORE, FAST_TH, device=local, max_width=W, max_height=H,
                               max_batch=args.e2e_chunk or max(1, B // 2))
 
+    # uvip_extract_match_batch_submit chains the consecutive-frame kNN2 behind the extraction ON THE DEVICE: the descriptors a step
+    # downloads are not uploaded again (round 1's e2e leg paid 8.9 MB of H2D per step for that: uvip_extract_batch_wait -> uvip_knn2_batch)
     def submit(j):
         t = C.c_int(-1)
-        chk(L.uvip_extract_batch_submit(ex_e2e.h, hp(hb[j]['inp']), B, W, H, W, W * H, hp(hb[j]['k']), hp(hb[j]['n']), cap, hp(hb[j]['d']), C.byref(t)))
+        chk(L.uvip_extract_match_batch_submit(ex_e2e.h, m.h, hp(hb[j]['inp']), B, W, H, W, W * H, hp(hb[j]['k']), hp(hb[j]['n']), cap, hp(hb[j]['d']),
+                                              hp(hb[j]['i']), hp(hb[j]['dd']), C.byref(t)))
         return t.value
 
     def finish(j, t):
         chk(L.uvip_extract_batch_wait(ex_e2e.h, t))
-        chk(L.uvip_knn2_batch(m.h, hp(hb[j]['d']), hp(hb[j]['n']), cap * 32, C.c_void_p(hb[j]['d'].data_ptr() + cap * 32),
-                              C.c_void_p(hb[j]['n'].data_ptr() + 4), cap * 32, B - 1, cap, hp(hb[j]['i']), hp(hb[j]['dd']), cap))
 
     def e2e_run(nsteps):
         t = submit(0)
@@ -406,7 +549,35 @@ def run_ours(args):
         dist.all_reduce(tt, op=dist.ReduceOp.MAX)
         e2e_s = float(tt.item())
     e2e_fps = world * B * Ke / e2e_s
-    h2d = B * W * H + B * cap * 32 + 2 * (B - 1) * 4
+    h2d = B * W * H
+    d2h = B * cap * 60 + B * 4 + 2 * (B - 1) * cap * 8
+    # the chained results equal the two-call path's on the last step's buffers (cheap: the kNN of 3 pairs through the host entry point)
+    jl = (Ke - 1) & 1
+    chk_i = np.zeros((3, cap, 2), np.int32); chk_d = np.zeros((3, cap, 2), np.int32)
+    chk(L.uvip_knn2_batch(m.h, hp(hb[jl]['d']), hp(hb[jl]['n']), cap * 32, C.c_void_p(hb[jl]['d'].data_ptr() + cap * 32),
+                          C.c_void_p(hb[jl]['n'].data_ptr() + 4), cap * 32, 3, cap, C.c_void_p(chk_i.ctypes.data), C.c_void_p(chk_d.ctypes.data), cap))
+    nn3 = hb[jl]['n'][:3].numpy()
+    e2e_knn_ok = all(np.array_equal(hb[jl]['i'][f, :nn3[f]].numpy(), chk_i[f, :nn3[f]]) and np.array_equal(hb[jl]['dd'][f, :nn3[f]].numpy(), chk_d[f, :nn3[f]])
+                     for f in range(3))
+    # ---- link ceiling: the step's copies alone (pinned memory, both directions at once, every rank at the same time), i.e. what the
+    # end-to-end path would reach if the kernels were free; at N > 1 this measures the HOST side shared by the N processes
+    s_up, s_dn = torch.cuda.Stream(dev), torch.cuda.Stream(dev)
+    def copies(n):
+        for i in range(n):
+            with torch.cuda.stream(s_up):
+                d_in[i & 1].copy_(hb[i & 1]['inp'], non_blocking=True)
+            with torch.cuda.stream(s_dn):
+                hb[i & 1]['k'].copy_(d_kps, non_blocking=True); hb[i & 1]['d'].copy_(d_desc, non_blocking=True)
+                hb[i & 1]['i'].copy_(d_idx, non_blocking=True); hb[i & 1]['dd'].copy_(d_dist, non_blocking=True)
+    copies(2)
+    barrier()
+    tl0 = time.perf_counter()
+    copies(Ke)
+    barrier()
+    link_s = time.perf_counter() - tl0
+    if world > 1:
+        tt = torch.tensor([link_s], dtype=torch.float64, device=dev); dist.all_reduce(tt, op=dist.ReduceOp.MAX); link_s = float(tt.item())
+    link_fps = world * B * Ke / link_s
     # single-frame latency of the reference-shaped call (uvip_extract = operator(), host image in, host keypoints out)
     one_k = np.zeros((cap, 7), np.float32); one_d = np.zeros((cap, 32), np.uint8)
     lat = []
@@ -417,7 +588,6 @@ def run_ours(args):
                            C.c_void_p(one_d.ctypes.data), None, 0, 0, 0, 1, 0))
         lat.append(time.perf_counter() - tl)
     lat_ms = float(np.median(lat[8:]) * 1e3)
-    d2h = B * cap * 60 + B * 4 + 2 * (B - 1) * cap * 8
 
     # ---- roofline of the dominant extraction kernel (algorithmic bytes of SURVEY 8(d) / its measured duration)
     peak, peak_kind = hbm_peak()
@@ -426,9 +596,14 @@ def run_ours(args):
     dom = max((k for k in stage_ms if k != 'pyramid'), key=stage_ms.get)
     dom_ms = region_ms[dom] / max(region_groups, 1)
     achieved = B_FRAME_BYTES * B / (dom_ms * 1e-3) / 1e9
-    traffic = ncu_traffic()
+    traffic, traffic_stale = ncu_traffic()
+    pipes, pipes_stale = ncu_pipes()
+    static_ok = args.shape == 'euroc' and B == 256          # the committed launch list is one step of this workload at batch 256
+    sm_hz = (clk.get('sm_mhz') or clk.get('sm_max_mhz') or 1965.0) * 1e6
+    issue_peak = 148 * 4 * sm_hz                            # warp instructions per second: 4 schedulers per SM, one issue per clock each
     roofline = {'bound': 'hbm', 'kernel': dom, 'achieved': achieved, 'peak': peak, 'unit': 'GB/s', 'frac': achieved / peak,
-                'traffic': traffic.get(dom), 'peak_source': peak_kind + ' (MEASURED_PEAKS.json hbm_gbs)' if peak_kind == 'measured' else 'fallback 6.65 TB/s',
+                'traffic': traffic.get(dom) if static_ok and not traffic_stale else None,
+                'peak_source': peak_kind + ' (MEASURED_PEAKS.json hbm_gbs)' if peak_kind == 'measured' else 'fallback 6.65 TB/s',
                 'algorithmic_bytes_per_launch': B_FRAME_BYTES * B, 'launch_ms': dom_ms,
                 'launch_ms_one_stream': stage_ms[dom] / max(ngroups, 1),
                 'stage_ms_per_step': {k: v / max(ngroups, 1) for k, v in stage_ms.items()}, 'knn_ms_per_step': knn_ms / KS,
@@ -436,27 +611,51 @@ def run_ours(args):
                                    'other step\'s kernels); launch_ms is the dominant kernel inside the timed region' % KS,
                 'whole_step_frac': (B_FRAME_BYTES * B * K / (ms * 1e-3) / 1e9) / peak,
                 'schedule': 'one stream' if SERIAL else 'two handle pairs on two streams, alternate steps (two batches in flight)'}
-    pipes = ncu_pipes()
-    if dom in pipes:           # the extraction kernels are instruction-bound, so the ALU pipe is reported next to HBM
-        roofline['alu_pipe'] = {'kernel': dom, 'alu_pipe_pct': pipes[dom]['alu_pipe_pct'], 'issue_slot_pct': pipes[dom]['issue_slot_pct'],
-                                'thread_instructions_per_pyramid_pixel': pipes[dom]['warp_instructions'] * 32.0 / (256 * 1117367.0),
-                                'source': 'profiles/kernel_pipes.json (ncu launch list of this command at batch 256, euroc shape)'}
+    if static_ok and not traffic_stale:
+        tsum = sum(v for k, v in traffic.items() if not k.startswith('_'))
+        roofline['traffic_all_stages'] = {'bytes_per_step': tsum, 'vs_algorithmic': tsum / (B_FRAME_BYTES * B),
+                                          'per_stage': {k: v for k, v in traffic.items() if not k.startswith('_')}}
+    elif static_ok:
+        roofline['traffic_note'] = 'profiles/roofline_traffic.json was captured from other kernel sources (hash mismatch): not quoted'
+    if static_ok and dom in pipes and not pipes_stale:
+        # the extraction kernels are instruction-bound.  Second roofline, LIVE in its time term: the warp instructions the
+        # kernel executes per launch (a property of code + input: ncu launch list of this command, same sources by hash) / the duration
+        # measured in this run / the chip's issue rate at the SM clock sampled in this run
+        wi = pipes[dom]['warp_instructions']
+        step_wi = sum(v['warp_instructions'] for k, v in pipes.items() if not k.startswith('_'))
+        roofline['issue'] = {'bound': 'issue', 'kernel': dom, 'warp_instructions_per_launch': wi,
+                             'achieved': wi / (dom_ms * 1e-3), 'peak': issue_peak, 'unit': 'warp-instr/s', 'frac': wi / (dom_ms * 1e-3) / issue_peak,
+                             'thread_instructions_per_pyramid_pixel': wi * 32.0 / (256 * 1117367.0),
+                             'alu_pipe_pct_ncu': pipes[dom]['alu_pipe_pct'], 'issue_slot_pct_ncu': pipes[dom]['issue_slot_pct'],
+                             'whole_step_warp_instructions': step_wi, 'whole_step_frac': step_wi * K / (ms * 1e-3) / issue_peak,
+                             'source': 'instruction counts: profiles/kernel_pipes.json (sources hash %s); durations and SM clock: this run' % kernel_source_hash()}
+    elif static_ok:
+        roofline['issue'] = {'bound': 'issue', 'stale': True, 'note': 'profiles/kernel_pipes.json was captured from other kernel sources (hash mismatch)'}
 
     line = {
         'metric': METRIC, 'value': fps, 'unit': 'frames/s', 'n_gpus': world, 'steps': K, 'warmup': Wm, 'ms_per_step': ms / K,
         'higher_is_better': True, 'scaling': 'weak', 'vs_baseline': None, 'dtype': 'u8', 'data': 'synthetic',
-        'config': {'workload': set_shape(args.shape) + ' + brute-force Hamming kNN2 of consecutive '
-                               'frames (BASELINE %s shape, batched)' % {'euroc': 'config 1', 'aqualoc': 'config 2', 'hd': 'config 5'}[args.shape], 'frames_per_step_per_gpu': B, 'keypoints': NFEAT,
-                   'l2': 'inputs alternate between two %d MB batches and each step streams a %.1f GB pyramid working set (> 126 MB L2)' % (B * W * H >> 20, 2.0 * B * B_FRAME_BYTES / 1e9),
-                   'parallelism': 'frames sharded over %d GPU(s), no collective' % world},
+        'config': workload_config(args, B, world),
         'clocks': clk,
         'e2e': {'value': e2e_fps, 'unit': 'frames/s', 'h2d_bytes_per_step': h2d, 'd2h_bytes_per_step': d2h, 'steps': Ke,
-                'chunk_frames': args.e2e_chunk or max(1, B // 2), 'pipeline': 'submit/wait, 2 batches in flight', 'single_frame_latency_ms': lat_ms},
+                'chunk_frames': args.e2e_chunk or max(1, B // 2), 'single_frame_latency_ms': lat_ms,
+                'pipeline': 'uvip_extract_match_batch_submit / _wait, 2 batches in flight; consecutive-frame kNN2 chained on the device (no descriptor re-upload)',
+                'chained_knn_equals_two_call_path': bool(e2e_knn_ok),
+                'link_ceiling_frames_per_s': link_fps, 'link_ceiling_gb_per_s_h2d': world * B * W * H * Ke / link_s / 1e9,
+                'link_ceiling_what': 'the same pinned H2D (frames) and D2H (keypoints, descriptors, kNN results) copies of %d steps with no kernels, '
+                                     'both directions at once, all %d rank(s) simultaneously (max over ranks)' % (Ke, world),
+                'frac_of_min_device_link': e2e_fps / min(fps, link_fps)},
         'gpu_launches': int(launches),
         'roofline': roofline,
         'hamming': {'pairs_per_s_in_step': pairs_step * KS / (knn_ms * 1e-3) if knn_ms > 0 else None, 'pairs_per_step': pairs_step},
     }
 
+    if world > 1 and not args.no_extras:
+        # BASELINE config 4 on the same ranks: the one path with a real exchange step (NCCL all-gather + merge), parity-checked
+        nk = int(os.environ.get('UVIP_KNN_SHARDED_N', '1048576'))
+        rec = sharded_knn_measure(pkg, torch, dist, dev, rank, world, local, nk, 2, stream)
+        if rank == 0:
+            line['knn_sharded'] = rec
     if rank == 0 and not args.no_extras:
         # Hamming-only leg: database-scale kNN2 (cfg4 shape at 64k x 64k) against the measured popc-pipe peak
         nq = nt = 65536
@@ -476,8 +675,9 @@ def run_ours(args):
         pps = 5.0 * nq * nt / (a.elapsed_time(b) * 1e-3)
         popc = C.c_double()
         chk(L.uvip_popc_peak(local, 4096, C.byref(popc)))
-        line['hamming'].update({'knn2_64k_pairs_per_s': pps, 'popc_per_pair': 8, 'popc_peak_measured_per_s': popc.value,
-                                'popc_frac': pps * 8 / popc.value,
+        # the kernel ISSUES 4 POPC per pair (carry-save tree over the 8 XOR words); the SURVEY's accounting of 8 per pair is secondary
+        line['hamming'].update({'knn2_64k_pairs_per_s': pps, 'popc_per_pair_issued': 4, 'popc_peak_measured_per_s': popc.value,
+                                'popc_frac_issued': pps * 4 / popc.value, 'popc_frac_8_per_pair_accounting': pps * 8 / popc.value,
                                 'popc_peak_nominal_per_s': 148 * 16 * (clk.get('sm_max_mhz') or 1965.0) * 1e6})
         if world == 1:
             # cpu_baseline: the oracle on this box's host cores, bounded sample of the same workload
@@ -494,7 +694,11 @@ def run_ours(args):
             line['cpu_baseline'] = {'value': reps * len(sample) / tc, 'unit': 'frames/s', 'cores': cores, 'kind': cpu_kind(), 'what': CPU_KIND_NOTE[cpu_kind()],
                                     'sample': '%d passes over %d frames of the same workload (extraction + consecutive-frame kNN2), OpenMP over '
                                               'frames on all host cores; single-thread figure on %d frames' % (reps, len(sample), n1),
-                                    'single_thread_frames_per_s': n1 / t1c}
+                                    'single_thread_frames_per_s': n1 / t1c,
+                                    'cv2_composite_frames_per_s': {'1_thread': cv2_composite(sample, 1), 'all_threads': cv2_composite(sample, cores),
+                                                                   'what': 'SURVEY 8(d) cross-check (iii): cv2 %s resize / copyMakeBorder / FAST / GaussianBlur on 8 '
+                                                                           'levels + BFMatcher.knnMatch(k=2) 1000 x 1000 per frame (no quadtree, orientation or '
+                                                                           'descriptors): bounds how soft the scalar OpenCV stand-ins of the reference build are' % _cv2_version()}}
     if rank == 0:
         print(json.dumps(line), flush=True)
     if world > 1:
@@ -505,8 +709,6 @@ def run_ours(args):
 def run_knn(args):
     """config 4: nq x nt brute-force kNN2, train rows sharded contiguously over the ranks, queries replicated, per-query
     top-2 all-gathered over NCCL and merged by (distance, global index).  value = descriptor pairs per second."""
-    import ctypes as C
-    import numpy as np
     import torch
     import __graft_entry__ as ge
     pkg = ge.load_package()
@@ -517,46 +719,22 @@ def run_knn(args):
     if world > 1:
         import torch.distributed as dist
         dist.init_process_group('nccl', device_id=dev)
-    n = args.knn_n
-    T, Q = pkg.synth.knn_database(n, n)
-    b = pkg.sharding.shard_bounds(n, world)
-    dq = torch.from_numpy(Q).to(dev); dt = torch.from_numpy(T[b[rank]:b[rank + 1]]).to(dev)
-    m = pkg.ORBmatcher(0.75, True, device=local)
     stream = torch.cuda.Stream(dev); torch.cuda.set_stream(stream)
     K, Wm = args.steps, max(args.warmup, 3)
-    for _ in range(Wm):
-        oi, od = pkg.sharding.gpu_sharded_knn2(pkg, m, dq, dt, b[rank], world, dist, stream.cuda_stream)
-    torch.cuda.synchronize(dev)
-    if world > 1:
-        dist.barrier()
     clocks = ClockSampler(local); clocks.start()
-    e0 = torch.cuda.Event(enable_timing=True); e1 = torch.cuda.Event(enable_timing=True)
-    e0.record(stream)
-    for _ in range(K):
-        oi, od = pkg.sharding.gpu_sharded_knn2(pkg, m, dq, dt, b[rank], world, dist, stream.cuda_stream)
-    e1.record(stream)
-    torch.cuda.synchronize(dev)
-    if world > 1:
-        dist.barrier()
-    ms = e0.elapsed_time(e1)
+    rec = sharded_knn_measure(pkg, torch, dist, dev, rank, world, local, args.knn_n, K, stream)
     clk = clocks.stop()
-    if world > 1:
-        tt = torch.tensor([ms], dtype=torch.float64, device=dev); dist.all_reduce(tt, op=dist.ReduceOp.MAX); ms = float(tt.item())
-    pps = float(n) * n * K / (ms * 1e-3)
-    check = None
-    if rank == 0 and n <= 65536:
-        from oracle import oracle as O
-        ri, rd = O.knn2(Q[:2048], T)
-        check = bool(np.array_equal(oi[:2048].cpu().numpy(), ri) and np.array_equal(od[:2048].cpu().numpy(), rd))
     if rank == 0:
-        popc = C.c_double(); pkg.capi.check(pkg.capi.lib().uvip_popc_peak(local, 4096, C.byref(popc)))
-        print(json.dumps({'metric': 'Hamming pairs/s (brute-force kNN2, database sharded over GPUs, NCCL top-2 merge)', 'value': pps,
-                          'unit': 'pairs/s', 'n_gpus': world, 'steps': K, 'warmup': Wm, 'ms_per_step': ms / K, 'higher_is_better': True,
+        print(json.dumps({'metric': 'Hamming pairs/s (brute-force kNN2, database sharded over GPUs, NCCL top-2 merge)', 'value': rec['pairs_per_s'],
+                          'unit': 'pairs/s', 'n_gpus': world, 'steps': K, 'warmup': Wm, 'ms_per_step': rec['ms_per_pass'], 'higher_is_better': True,
                           'scaling': 'strong', 'vs_baseline': None, 'dtype': 'u32 popc', 'data': 'synthetic',
-                          'config': {'workload': 'BASELINE config 4 shape: %d x %d 256-bit descriptors, ratio 0.75' % (n, n)},
-                          'clocks': clk, 'roofline': {'bound': 'popc', 'popc_per_pair': 8, 'achieved_popc_per_s': pps * 8,
-                                                      'peak_popc_per_s_measured_one_gpu': popc.value, 'frac_of_n_gpus': pps * 8 / (popc.value * world)},
-                          'matches_oracle_first_2048_queries': check}), flush=True)
+                          'config': {'workload': rec['workload']}, 'clocks': clk,
+                          'roofline': {'bound': 'popc', 'popc_per_pair_issued': 4, 'achieved_popc_per_s': rec['pairs_per_s'] * 4,
+                                       'peak_popc_per_s_measured_one_gpu': rec['popc_peak_measured_per_s_one_gpu'],
+                                       'frac': rec['popc_frac_issued_of_n_gpus'], 'frac_8_per_pair_accounting': rec['popc_frac_8_per_pair_accounting']},
+                          'phase_ms_per_pass': rec['phase_ms_per_pass'],
+                          'matches_oracle_first_2048_queries': rec['matches_oracle_first_2048_queries'],
+                          'exact_distance_ties_in_checked_queries': rec['exact_distance_ties_in_checked_queries']}), flush=True)
     if world > 1:
         dist.destroy_process_group()
     return 0

@@ -103,6 +103,15 @@ int   uvip_extract_batch(uvip_extractor* ex, const uint8_t* frames, int nframes,
 int   uvip_extract_batch_submit(uvip_extractor* ex, const uint8_t* frames, int nframes, int w, int h, int stride,
                                 size_t frame_pitch, uvip_keypoint* kps, int32_t* n_out, int cap, uint8_t* desc, int* ticket);
 int   uvip_extract_batch_wait(uvip_extractor* ex, int ticket);
+/* uvip_extract_batch_submit followed, ON THE DEVICE, by the brute-force kNN2 of consecutive frames (frame f = queries, frame f+1 =
+ * train; include/utils.h:81-111 semantics, see uvip_knn2): descriptors are matched where the extractor wrote them and never make
+ * the host round trip that uvip_extract_batch_wait + uvip_knn2_batch would force.  knn_idx / knn_dist: (nframes - 1) x cap x 2
+ * int32 host buffers, pair f at + f*cap*2, query i of the pair at + 2*i; rows >= n_out[f] are unspecified.  `m` supplies the kNN
+ * scratch and must not be used by another thread until the ticket has been waited for (uvip_extract_batch_wait). */
+struct uvip_matcher;
+int   uvip_extract_match_batch_submit(uvip_extractor* ex, struct uvip_matcher* m, const uint8_t* frames, int nframes, int w, int h,
+                                      int stride, size_t frame_pitch, uvip_keypoint* kps, int32_t* n_out, int cap, uint8_t* desc,
+                                      int32_t* knn_idx, int32_t* knn_dist, int* ticket);
 /* Device-resident variant: all pointers are device memory; asynchronous on `stream`.
  * uvip_extractor_status() after synchronising reports capacity overflow of the launch group. */
 int   uvip_extract_batch_device(uvip_extractor* ex, const uint8_t* d_frames, int nframes, int w, int h, int stride,

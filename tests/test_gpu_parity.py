@@ -138,6 +138,29 @@ def test_extract_occupancy_grid_path(gpu, oracle, synth):
     assert np.array_equal(g3, grid) and len(kps) >= 1000
 
 
+def test_extract_match_batch_chains_knn_on_the_device(gpu, oracle, synth):
+    """uvip_extract_match_batch_submit: extraction + consecutive-frame kNN2 without the descriptor round trip; chunk sizes 3, 3, 1
+    exercise the pair across a chunk boundary (query frame in the other staging set) and a one-frame chunk"""
+    nfr, W, H, NF = 7, 640, 512, 800
+    frames = synth.synth_batch(2000, nfr, W, H)
+    ex = gpu.ORBextractor(NF, 1.2, 8, 1, 20, max_width=W, max_height=H, max_batch=3)
+    m = gpu.ORBmatcher(0.75, True)
+    cap = NF + 8 * 8 + 64
+    for rep in range(2):                                       # the second batch reuses the staging sets and the chunk counter parity
+        kps = np.zeros((nfr, cap), gpu.capi.KP_DTYPE); desc = np.zeros((nfr, cap, 32), np.uint8); n = np.zeros(nfr, np.int32)
+        ki = np.full((nfr - 1, cap, 2), -7, np.int32); kd = np.full((nfr - 1, cap, 2), -7, np.int32)
+        fr = frames if rep == 0 else np.ascontiguousarray(frames[::-1])
+        t = ex.extract_match_batch_submit(m, fr, kps, n, desc, ki, kd)
+        ex.extract_batch_wait(t)
+        okps, on, odesc = oracle.extract_batch(fr, NF, 1.2, 8, 20, cap=cap)
+        assert np.array_equal(n, on) and n.min() >= NF
+        for f in range(nfr):
+            assert np.array_equal(desc[f, :n[f]], odesc[f, :n[f]])
+        for f in range(nfr - 1):
+            oi, od = oracle.knn2(odesc[f, :n[f]], odesc[f + 1, :n[f + 1]])
+            assert np.array_equal(ki[f, :n[f]], oi) and np.array_equal(kd[f, :n[f]], od), (rep, f)
+
+
 def test_incoming_keypoints_near_the_border(gpu, oracle, synth):
     """incoming level-0 keypoints (ComputeKeyPointsCopy, src/ORBextractor.cc:523-534) may lie anywhere inside the image: their
     IC_Angle disc and descriptor pattern reach into the reference's 16-px reflect-101 border, which the CUDA path materialises

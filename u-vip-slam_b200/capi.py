@@ -67,6 +67,7 @@ def lib():
         L.uvip_distinctive_descriptors.argtypes = [vp, vp, vp, i, vp, vp]
         L.uvip_extract_batch_submit.argtypes = [vp, vp, i, i, i, i, sz, vp, vp, i, vp, C.POINTER(i)]
         L.uvip_extract_batch_wait.argtypes = [vp, i]
+        L.uvip_extract_match_batch_submit.argtypes = [vp, vp, vp, i, i, i, i, sz, vp, vp, i, vp, vp, vp, C.POINTER(i)]
         L.uvip_extract_batch_device.argtypes = [vp, vp, i, i, i, i, sz, vp, vp, i, vp, vp]
         L.uvip_extractor_status.argtypes = [vp]
         L.uvip_get_pyramid_level.argtypes = [vp, i, i, i, vp, i, C.POINTER(i), C.POINTER(i)]

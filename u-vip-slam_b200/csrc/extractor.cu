@@ -1539,6 +1539,8 @@ struct uvip_extractor {
     DevBuf dyn;                                      // single-frame call: {n_incoming, num_needed} read by k_select (outside the graph key)
     int* h_dyn = nullptr;                            // pinned source of the dyn upload
     DevBuf in2, kps2, desc2, n2;                     // second staging set: uvip_extract_batch double-buffers its chunks
+    DevBuf knn_i[2], knn_d[2];                       // uvip_extract_match_batch_submit: kNN2 results of a chunk's frame pairs
+    int prev_nb = 0;                                 // frames of the previously submitted chunk (the boundary pair reads its last frame)
     cudaStream_t h2d_stream = nullptr, d2h_stream = nullptr;
     cudaEvent_t ev_h2d[2] = {nullptr, nullptr}, ev_comp[2] = {nullptr, nullptr}, ev_d2h[2] = {nullptr, nullptr};
     cudaEvent_t ev_done[2] = {nullptr, nullptr};       // one per ticket of uvip_extract_batch_submit
@@ -1971,7 +1973,8 @@ int uvip_extractor_destroy(uvip_extractor* ex)
     if (ex->stream) cudaStreamSynchronize(ex->stream);
     DevBuf* bufs[] = {&ex->pyr, &ex->blur, &ex->cand, &ex->labels, &ex->winners, &ex->counters, &ex->sel,
                       &ex->nsel, &ex->tabs, &ex->status, &ex->grid, &ex->incoming, &ex->tmaps, &ex->pat_t, &ex->in_frames, &ex->out_kps, &ex->out_desc, &ex->out_n,
-                      &ex->in2, &ex->kps2, &ex->desc2, &ex->n2, &ex->clahe_lut, &ex->clahe_io, &ex->dyn};
+                      &ex->in2, &ex->kps2, &ex->desc2, &ex->n2, &ex->clahe_lut, &ex->clahe_io, &ex->dyn,
+                      &ex->knn_i[0], &ex->knn_i[1], &ex->knn_d[0], &ex->knn_d[1]};
     for (DevBuf* b : bufs) b->release();
     for (cudaEvent_t e : ex->prof_ev) cudaEventDestroy(e);
     for (int i = 0; i < 2; i++) { if (ex->ev_h2d[i]) cudaEventDestroy(ex->ev_h2d[i]); if (ex->ev_comp[i]) cudaEventDestroy(ex->ev_comp[i]); if (ex->ev_d2h[i]) cudaEventDestroy(ex->ev_d2h[i]); }
@@ -2033,7 +2036,8 @@ int uvip_extractor_status(uvip_extractor* ex)
 // chunk c (two staging sets; pinned host memory is needed for the copies to be truly asynchronous).  The chunk counter
 // and the guard events live in the handle, so that two submitted batches overlap in the same way across calls.
 static int submit_batch(uvip_extractor* ex, const uint8_t* frames, int nframes, int w, int h, int stride,
-                        size_t frame_pitch, uvip_keypoint* kps, int32_t* n_out, int cap, uint8_t* desc, int* ticket_out)
+                        size_t frame_pitch, uvip_keypoint* kps, int32_t* n_out, int cap, uint8_t* desc, int* ticket_out,
+                        uvip_matcher* mt = nullptr, int32_t* knn_idx = nullptr, int32_t* knn_dist = nullptr)
 {
     if (ex->inflight >= 2) { set_last_error("two batches are already in flight: wait for a ticket first"); return UVIP_ERR_ARG; }
     DeviceGuard g(ex->device);
@@ -2061,6 +2065,12 @@ static int submit_batch(uvip_extractor* ex, const uint8_t* frames, int nframes, 
             if ((rc = on[s]->reserve((size_t)B * 4))) return rc;
         }
     }
+    if (mt)
+        for (int s = 0; s < 2; s++) {
+            if (ex->knn_i[s].cap < (size_t)B * cap * 8 && ex->inflight) { set_last_error("kNN staging must grow while a batch is in flight: wait first"); return UVIP_ERR_ARG; }
+            if ((rc = ex->knn_i[s].reserve((size_t)B * cap * 8))) return rc;
+            if ((rc = ex->knn_d[s].reserve((size_t)B * cap * 8))) return rc;
+        }
     if (!ex->h2d_stream) {
         UVIP_CUDA(cudaStreamCreateWithFlags(&ex->h2d_stream, cudaStreamNonBlocking));
         UVIP_CUDA(cudaStreamCreateWithFlags(&ex->d2h_stream, cudaStreamNonBlocking));
@@ -2095,8 +2105,29 @@ static int submit_batch(uvip_extractor* ex, const uint8_t* frames, int nframes, 
         rc = enqueue_group(ex, in[s]->as<uint8_t>(), nb, stride, fbytes, ok[s]->as<uvip_keypoint>(), on[s]->as<int32_t>(),
                            cap, od[s]->as<uint8_t>(), 1, 0, 1, 1, 1, 0, st, false);
         if (rc) return rc;
-        UVIP_CUDA(cudaEventRecord(ex->ev_comp[s], st));
-        UVIP_CUDA(cudaStreamWaitEvent(sd, ex->ev_comp[s], 0));
+        if (mt) {
+            // consecutive-frame kNN2 on the descriptors where they lie (frame f = queries, frame f + 1 = train): the pairs inside this
+            // chunk, and the pair across the chunk boundary, whose query frame is the last frame of the previous chunk — still intact in
+            // the other staging set, which the compute stream only overwrites two chunks later.  Device rows: 0 = boundary pair,
+            // 1 + j = pair (f0 + j, f0 + j + 1).
+            int32_t* ki = ex->knn_i[s].as<int32_t>(); int32_t* kd = ex->knn_d[s].as<int32_t>();
+            const size_t dp = (size_t)cap * 32, rp = (size_t)cap * 2;
+            if (c > 0 && (rc = uvip_knn2_batch_device(mt, od[s ^ 1]->as<uint8_t>() + (size_t)(ex->prev_nb - 1) * dp, on[s ^ 1]->as<int32_t>() + (ex->prev_nb - 1), dp,
+                                                      od[s]->as<uint8_t>(), on[s]->as<int32_t>(), dp, 1, cap, ki, kd, (size_t)cap, st))) return rc;
+            if (nb > 1 && (rc = uvip_knn2_batch_device(mt, od[s]->as<uint8_t>(), on[s]->as<int32_t>(), dp, od[s]->as<uint8_t>() + dp, on[s]->as<int32_t>() + 1, dp,
+                                                       nb - 1, cap, ki + rp, kd + rp, (size_t)cap, st))) return rc;
+            const int r0 = c > 0 ? 0 : 1, nr = nb - r0;                  // device rows r0 .. nb-1 -> host pairs f0 - 1 + r0 ..
+            UVIP_CUDA(cudaEventRecord(ex->ev_comp[s], st));
+            UVIP_CUDA(cudaStreamWaitEvent(sd, ex->ev_comp[s], 0));
+            if (nr > 0) {
+                UVIP_CUDA(cudaMemcpyAsync(knn_idx + (size_t)(f0 - 1 + r0) * rp, ki + (size_t)r0 * rp, (size_t)nr * rp * 4, cudaMemcpyDeviceToHost, sd));
+                UVIP_CUDA(cudaMemcpyAsync(knn_dist + (size_t)(f0 - 1 + r0) * rp, kd + (size_t)r0 * rp, (size_t)nr * rp * 4, cudaMemcpyDeviceToHost, sd));
+            }
+            ex->prev_nb = nb;
+        } else {
+            UVIP_CUDA(cudaEventRecord(ex->ev_comp[s], st));
+            UVIP_CUDA(cudaStreamWaitEvent(sd, ex->ev_comp[s], 0));
+        }
         UVIP_CUDA(cudaMemcpyAsync(n_out + f0, on[s]->p, (size_t)nb * 4, cudaMemcpyDeviceToHost, sd));
         UVIP_CUDA(cudaMemcpyAsync(kps + (size_t)f0 * cap, ok[s]->p, (size_t)nb * cap * sizeof(uvip_keypoint), cudaMemcpyDeviceToHost, sd));
         UVIP_CUDA(cudaMemcpyAsync(desc + (size_t)f0 * cap * 32, od[s]->p, (size_t)nb * cap * 32, cudaMemcpyDeviceToHost, sd));
@@ -2131,6 +2162,16 @@ int uvip_extract_batch_submit(uvip_extractor* ex, const uint8_t* frames, int nfr
     UVIP_CHECK_ARG(frame_pitch >= (size_t)stride * (h - 1) + w);
     std::lock_guard<std::mutex> lk(ex->mu);
     return submit_batch(ex, frames, nframes, w, h, stride, frame_pitch, kps, n_out, cap, desc, ticket);
+}
+
+int uvip_extract_match_batch_submit(uvip_extractor* ex, uvip_matcher* m, const uint8_t* frames, int nframes, int w, int h, int stride,
+                                    size_t frame_pitch, uvip_keypoint* kps, int32_t* n_out, int cap, uint8_t* desc,
+                                    int32_t* knn_idx, int32_t* knn_dist, int* ticket)
+{
+    UVIP_CHECK_ARG(ex && m && frames && kps && n_out && desc && knn_idx && knn_dist && ticket && nframes >= 1 && w > 0 && h > 0 && stride >= w && cap >= 1);
+    UVIP_CHECK_ARG(frame_pitch >= (size_t)stride * (h - 1) + w);
+    std::lock_guard<std::mutex> lk(ex->mu);
+    return submit_batch(ex, frames, nframes, w, h, stride, frame_pitch, kps, n_out, cap, desc, ticket, m, knn_idx, knn_dist);
 }
 
 int uvip_extract_batch_wait(uvip_extractor* ex, int ticket)

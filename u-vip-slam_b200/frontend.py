@@ -95,6 +95,16 @@ class ORBextractor:
         check(lib().uvip_extract_batch_submit(self.h, ptr(frames), nf, W, H, W, W * H, ptr(kps), ptr(n), cap, ptr(desc), C.byref(t)))
         return t.value
 
+    def extract_match_batch_submit(self, matcher, frames, kps, n, desc, knn_idx, knn_dist):
+        """extract_batch_submit + consecutive-frame kNN2 on the device (descriptors are matched where the extractor wrote them);
+        knn_idx / knn_dist: (nf - 1, cap, 2) int32, filled when extract_batch_wait(ticket) returns"""
+        nf, H, W = frames.shape
+        cap = kps.shape[1]
+        t = C.c_int(-1)
+        check(lib().uvip_extract_match_batch_submit(self.h, matcher.h, ptr(frames), nf, W, H, W, W * H, ptr(kps), ptr(n), cap, ptr(desc),
+                                                    ptr(knn_idx), ptr(knn_dist), C.byref(t)))
+        return t.value
+
     def extract_batch_wait(self, ticket):
         check(lib().uvip_extract_batch_wait(self.h, int(ticket)))
 

@@ -74,19 +74,31 @@ def flip_bits(desc, seed, counts):
 
 
 def knn_database(nt, nq, seed_t=42, seed_q=43):
-    """cfg4-shaped kNN inputs: train = uniform bits; even queries = a train row with up to 63 bit flips,
-    odd queries = fresh uniform rows (vectorised; bit positions may repeat -> <= k flips)."""
+    """config 4 inputs, SURVEY Appendix B row 4.  Train T: byte j of row i = draw(42, 32 i + j + 1) mod 256.  Queries: even i =
+    T[draw(43, 2 i + 1) mod nt] with k_i = draw(43, 2 i + 2) mod 64 DISTINCT bit flips, the positions being the first k_i distinct
+    values of draw(44, 128 i + j) mod 256, j = 1, 2, ... (a block of 128 draws of stream 44 per query: 63 distinct positions out of
+    256 need more than 128 draws with probability < 1e-9; asserted); odd i = uniform, byte j = draw(45, 32 i + j + 1) mod 256.
+    Unrelated pairs are ~Binomial(256, 1/2): many exact distance ties, which exercise the (distance, global index) rule."""
     T = random_descriptors(seed_t, nt)
     Q = random_descriptors(seed_q + 2, nq)
     ev = np.arange(0, nq, 2)
     src = (draw(seed_q, 2 * ev.astype(np.uint64) + np.uint64(1)) % np.uint64(nt)).astype(np.int64)
     kf = (draw(seed_q, 2 * ev.astype(np.uint64) + np.uint64(2)) % np.uint64(64)).astype(np.int64)
     Q[ev] = T[src]
-    for j in range(63):
-        sel = kf > j
-        p = (draw(seed_q + 1, ev.astype(np.uint64) * np.uint64(64) + np.uint64(j + 1)) % np.uint64(256)).astype(np.int64)
-        rows = ev[sel]
-        Q[rows, p[sel] >> 3] ^= (1 << (p[sel] & 7)).astype(np.uint8)
+    mask = np.zeros((len(ev), 32), np.uint8)                  # bit positions flipped so far (= the XOR mask)
+    cnt = np.zeros(len(ev), np.int64)
+    base = ev.astype(np.uint64) * np.uint64(128)
+    rows = np.arange(len(ev))
+    for j in range(1, 129):
+        if not (cnt < kf).any():
+            break
+        p = (draw(seed_q + 1, base + np.uint64(j)) % np.uint64(256)).astype(np.int64)
+        bit = (1 << (p & 7)).astype(np.uint8)
+        take = (cnt < kf) & ((mask[rows, p >> 3] & bit) == 0)
+        mask[rows[take], p[take] >> 3] |= bit[take]
+        cnt += take
+    assert (cnt == kf).all(), 'a query needed more than 128 draws for its distinct bit positions'
+    Q[ev] ^= mask
     return T, Q
 
 
