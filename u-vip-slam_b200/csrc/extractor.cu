@@ -11,6 +11,7 @@
 #include "common.cuh"
 #include <cuda.h>
 #include <math.h>
+#include <stdlib.h>
 #include <algorithm>
 #include <vector>
 
@@ -54,6 +55,11 @@ struct Plan {
     unsigned f_rcp_srow;      // ceil(2^32 / f_srow)
     int rs_boxw, rs_boxh;     // resize: TMA box of the source level
     int f_irow, f_irows, f_srow, f_srows, f_gw;   // FAST shared-memory carve-up (largest tile over all levels)
+    // k_fast2 (one warp per cell): per-warp score map (f2_srow x f2_srows bytes, padded to f2_score_bytes), group-queue capacity,
+    // bytes of one warp's private area, ceil(2^32 / ftiles)
+    int f2_srow, f2_srows, f2_score_bytes, f2_gcap, f2_wbytes;
+    int f2_tiles, f2_tab_off, f2_irows;          // tiles of F2_CW x 1 cells per frame, their table inside tabs, rows of a staged tile
+    unsigned f2_rcp_tiles;
     unsigned long long frame_bytes;
     LevelInfo lv[MAXLEV];
     // host-side only, kept behind lv[] so that no kernel-visible offset depends on it: bit l = the byte pairs of columns 0..2 of
@@ -560,6 +566,351 @@ k_fast(const CUtensorMap* __restrict__ tmaps, const unsigned* __restrict__ tile_
         }
         __syncthreads();                                   // s_surv complete before the retry pass reads it
     }
+}
+
+// --------------------------------------------------------------------------------------------------------
+// K2+K3, second design: the same computation (cv::FAST(th, nms=true) per 30-px cell ROI + the retry at the second threshold when a
+// cell returned nothing, src/ORBextractor.cc:772-812) organised around what the first kernel's profile showed: it was bound by the ALU
+// pipe (70 % busy at 74 % issue) and lost the rest to CTA barriers (1.4 stalled warps per issue), to a 300-instruction prologue per
+// 7.7 k-pixel CTA (11 % of all instructions) and to cell bookkeeping inside a 4 x 2-cell tile (which cell does this pixel belong to).
+//   * ONE WARP PER CELL.  NMS, the survivor count and the retry decision are cell-local, so a warp that owns a cell needs no CTA
+//     barrier at all: its queues, its score map and its retry loop are private.  Cell geometry is a handful of warp-uniform values.
+//   * PERSISTENT CTAs over the (tile, frame) space with a two-stage TMA pipeline: the box of tile i + 2 is requested by the warp that
+//     finishes the last cell of tile i; the eight warps meet only at the mbarrier of each tile's box.  Cell <-> warp assignment
+//     rotates from tile to tile, so edge tiles with fewer than eight cells do not idle the same warps.
+//   * ALU diet of the two filter stages: |ring - v| > t is tested as bit 7 of (a + K) | a with K = (127 - t) * 0x01010101 — without
+//     the & 0x7f7f7f7f of the exact SWAR compare.  A byte carry can only ADD a false positive (a == t beside a neighbour >= 129 + t),
+//     which is all a filter needs: the exact decision is the score stage's (score >= t  <=>  FAST-9 corner at t).  No early-out
+//     branch inside the compass test (it diverged on every warp), cell-edge masks from an 8-word table instead of compares.
+//   * queue entries are (row << 8 | column) relative to the cell: image offset, score-map position and output coordinates are one
+//     IMAD each; no divisions anywhere behind the first stage.
+// Stages per cell: B1 compass pre-test on 4-pixel groups -> B2 8 even ring positions (4 consecutive ones must differ) -> C exact
+// score, two pixels per lane packed 16x2 on VIMNMX3 -> D strict 3x3 NMS inside the cell, one global reservation per warp and cell.
+// --------------------------------------------------------------------------------------------------------
+constexpr int F2_IROW = 160;                 // row stride of the staged tile in the common case (4 cells of <= 33 px + halo + alignment)
+constexpr int F2_PQ = 1024;                  // candidate-pixel queue of a warp (flushed through the score stage when nearly full)
+__constant__ unsigned c_rcp32[33];           // ceil(2^32 / n), n = 1..32 (groups per cell row)
+
+constexpr int F2_CW = 4;                     // cells per tile: one row of four (a buffer is recycled as soon as its four cells are done)
+constexpr int F2_STAGES = 3, F2_RING = 8;    // staged tiles per CTA; ring of tile announcements (> F2_STAGES, power of two)
+
+#ifndef F2_MINB
+#define F2_MINB 4
+#endif
+template <int IROWT>                         // row stride of the staged tile in bytes; 0 = take it from the plan at run time
+__global__ void __launch_bounds__(256, F2_MINB)
+k_fast2(const CUtensorMap* __restrict__ tmaps, const unsigned* __restrict__ tile_tab, unsigned* __restrict__ cand,
+        int* __restrict__ cand_count, int* __restrict__ status, int nframes, const __grid_constant__ Plan P)
+{
+    extern __shared__ __align__(128) unsigned char s_f2[];
+    __shared__ __align__(8) uint64_t s_full[F2_STAGES];
+    __shared__ int s_done[F2_STAGES], s_loads[F2_STAGES], s_next, s_lock;
+    __shared__ volatile int s_issued;
+    // announcement of the CTA's tile number q (slot q & 7): which launch tile it is (-1: the launch has no more), where it lands and the
+    // parity of that buffer's mbarrier phase; s_rseq is written last
+    __shared__ volatile int s_rseq[F2_RING], s_rtile[F2_RING], s_rbuf[F2_RING];
+    const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+    const int irow = IROWT ? IROWT : P.f_irow;
+    const int imgbytes = irow * P.f2_irows, imgstride = (imgbytes + 127) & ~127;
+    const int T = P.f2_tiles * nframes;
+    int* tile_ctr = status + 2;                            // [2] next (tile, frame) of the launch, [3] CTAs that have left; both 0 between launches
+    // Request the CTA's next tile into buffer `buf` (free: every cell of its previous tile is done).  Tiles come from a launch-wide
+    // counter, so CTAs that meet dense tiles simply draw fewer; buffers are recycled in COMPLETION order, so a slow cell holds back its
+    // own buffer only.  One thread at a time (lock): tile numbers and launch tiles stay in the same order, which the hand-out of cells
+    // in tile order and the end-of-launch test rely on.
+    auto issue = [&](int buf) {
+        while (atomicCAS(&s_lock, 0, 1) != 0) __nanosleep(20);
+        const int q = s_issued; s_issued = q + 1;
+        const int t = atomicAdd(tile_ctr, 1);
+        __threadfence_block();
+        atomicExch(&s_lock, 0);
+        const int slot = q & (F2_RING - 1);
+        if (t >= T) { s_rtile[slot] = -1; __threadfence_block(); s_rseq[slot] = q; return; }
+        const int f = P.f2_tiles > 1 ? (int)__umulhi((unsigned)t, P.f2_rcp_tiles) : t, tl = t - f * P.f2_tiles;
+        const unsigned te = __ldg(tile_tab + tl);
+        const LevelInfo& L = P.lv[te & 15];
+        const int TX0 = EDGE + (int)(te >> 16) * L.wcell, TY0 = EDGE + (int)((te >> 4) & 0xFFF) * L.hcell;
+        const int ax0 = ((((TX0 & ~3) - 4 + EDGE) & ~15) - EDGE), ay0 = TY0 - 3;
+        const int par = s_loads[buf] & 1; s_loads[buf]++;
+        s_rtile[slot] = t; s_rbuf[slot] = buf | (par << 8); __threadfence_block(); s_rseq[slot] = q;
+        mbar_arrive_expect_tx(&s_full[buf], (unsigned)imgbytes);
+        tma_load_3d(s_f2 + (size_t)buf * imgstride, tmaps + 3 * MAXLEV + (te & 15), ax0 + EDGE, ay0 + EDGE, f, &s_full[buf]);
+    };
+    if (tid == 0) {
+        for (int k = 0; k < F2_STAGES; k++) { mbar_init(&s_full[k], 1); s_done[k] = 0; s_loads[k] = 0; }
+        mbar_fence_init();
+        for (int k = 0; k < F2_RING; k++) s_rseq[k] = -1;
+        s_next = 0; s_lock = 0; s_issued = 0;
+        for (int k = 0; k < F2_STAGES; k++) issue(k);
+    }
+    __syncthreads();                                       // the only CTA barrier: the mbarriers and the bookkeeping words exist
+
+    // the warp's private area
+    unsigned char* wb = s_f2 + F2_STAGES * (size_t)imgstride + (size_t)warp * P.f2_wbytes;
+    uint8_t* s_score = wb;
+    unsigned short* gq = reinterpret_cast<unsigned short*>(wb + P.f2_score_bytes);
+    unsigned short* pq = gq + P.f2_gcap;
+    // The corner list is the pixel queue compacted IN PLACE by the score stage (corner k of a round lands at pq[k], k <= the entries the
+    // round has read so far), so it needs no storage of its own.  That only works while one round covers the cell: a cell with more
+    // than F2_PQ candidate pixels (noise images) is scored in several rounds and takes the score-map sweep of stage D instead of a list.
+    unsigned short* cq = pq;
+    unsigned* vtab = reinterpret_cast<unsigned*>(pq + F2_PQ + 2);
+    const int srow = P.f2_srow;
+    const unsigned ltmask = (1u << lane) - 1u;
+    const int rsw = irow >> 2;
+
+    // Cells are handed out in order (cell n = cell n & 3 of the CTA's tile n >> 2): a warp that finishes early takes the next cell, of
+    // whichever staged tile comes next, instead of waiting for its tile's slowest cell.
+    for (;;) {
+        int n = 0;
+        if (lane == 0) n = atomicAdd(&s_next, 1);
+        n = __shfl_sync(0xFFFFFFFFu, n, 0);
+        const int q = n >> 2, cj = n & 3, slot = q & (F2_RING - 1);
+        static_assert(F2_CW == 4, "four cells per tile");
+        while (s_rseq[slot] != q) __nanosleep(64);         // the tile has not been announced yet (its buffer is still busy)
+        const int t = s_rtile[slot];
+        if (t < 0) break;                                  // the launch has no more tiles (cells are handed out in tile order)
+        const int bp = s_rbuf[slot], b = bp & 255;
+        const int f = P.f2_tiles > 1 ? (int)__umulhi((unsigned)t, P.f2_rcp_tiles) : t, tl = t - f * P.f2_tiles;
+        const unsigned te = __ldg(tile_tab + tl);
+        const int level = te & 15, tcy0 = (te >> 4) & 0xFFF, tcx0 = te >> 16;
+        const LevelInfo& L = P.lv[level];
+        const int wc = L.wcell, hc = L.hcell;
+        const int ci = 0;
+        const int TX0 = EDGE + tcx0 * wc, TY0 = EDGE + tcy0 * hc;
+        const int ax0 = ((((TX0 & ~3) - 4 + EDGE) & ~15) - EDGE), ay0 = TY0 - 3;
+        const int cx0 = TX0 + cj * wc, cx1 = min(cx0 + wc, L.w - EDGE);
+        const int cy0 = TY0 + ci * hc, cy1 = min(cy0 + hc, L.h - EDGE);
+        // the announcement names the phase: a buffer is only requested again once all four cells of its tile are done, this one
+        // included, so the parity cannot refer to a phase two steps away
+        mbar_wait(&s_full[b], (unsigned)(bp >> 8));
+        if (tcx0 + cj < L.ncols && tcy0 + ci < L.nrows && cx0 < cx1 && cy0 < cy1) {
+            const unsigned char* img = s_f2 + (size_t)b * imgstride;
+            const int gx0 = cx0 & ~3;
+            const int ngx_real = ((((cx1 - 1) & ~3) - gx0) >> 2) + 1;      // 4-pixel groups per row (<= 17 for cells <= 64 px)
+            const int ngx = max(ngx_real, 2);                              // c_rcp32[1] would be 2^32: a one-group sliver gets a masked second group
+            const int nrows = cy1 - cy0, ng = ngx * nrows;
+            const unsigned rcp = c_rcp32[ngx];
+            const unsigned* Wc = reinterpret_cast<const unsigned*>(img + (cy0 - ay0) * irow + (gx0 - ax0));   // word of group (0, 0)
+            const int rskip = rsw - ngx;
+            const uint8_t* cimg = img + (cy0 - 1 - ay0) * irow + (cx0 - 1 - ax0);   // pixel (xrel, yrel) = (0, 0): entries count from 1
+            const int xoff0 = gx0 - cx0 + 1;
+            // cell-edge masks per group column (bit 7 of the bytes inside [cx0, cx1)), and a clean score map
+            if (lane < ngx) {
+                unsigned m = lane < ngx_real ? 0x80808080u : 0u;
+                if (lane == 0) m &= 0x80808080u << (8 * (cx0 & 3));
+                if (lane == ngx_real - 1) m &= 0x80808080u >> (8 * (3 - ((cx1 - 1) & 3)));
+                vtab[lane] = m;
+            }
+            for (int k = lane; k < ((nrows + 2) * srow + 15) >> 4; k += 32) reinterpret_cast<uint4*>(s_score)[k] = make_uint4(0u, 0u, 0u, 0u);
+            __syncwarp();
+            int* gcount = cand_count + (size_t)f * P.nlevels + level;
+            unsigned* gdst = cand + (size_t)f * P.raw_per_frame + L.raw_off;
+            const unsigned recbase = (unsigned)(cx0 - 1) + ((unsigned)(cy0 - 1) << 12);
+
+            for (int pass = 0; pass < 2; pass++) {
+                const int t_exact = pass ? P.t2 : P.t1;
+                if (pass && P.t2 >= P.t1) break;                           // the retry cannot add anything
+                const unsigned K = (unsigned)(127 - min(t_exact, 127)) * 0x01010101u;
+                // ---- B1: compass pre-test on every group of the cell
+                int ngw = 0;
+                for (int g0 = 0; g0 < ng; g0 += 32) {
+                    const int g = g0 + lane;
+                    unsigned pf = 0;
+                    if (g < ng) {
+                        const int r = __umulhi((unsigned)g, rcp);
+                        const unsigned* W = Wc + g + r * rskip;
+                        const unsigned v = W[0];
+                        const unsigned a0 = __vabsdiffu4(W[3 * rsw], v), a8 = __vabsdiffu4(W[-3 * rsw], v);
+                        const unsigned a4 = __vabsdiffu4(__funnelshift_r(v, W[1], 24), v), a12 = __vabsdiffu4(__funnelshift_r(W[-1], v, 8), v);
+                        pf = ((a0 + K) | a0 | (a8 + K) | a8) & ((a4 + K) | a4 | (a12 + K) | a12) & 0x80808080u;
+                    }
+                    const unsigned bal = __ballot_sync(0xFFFFFFFFu, pf != 0);
+                    if (pf) gq[ngw + __popc(bal & ltmask)] = (unsigned short)g;
+                    ngw += __popc(bal);
+                }
+                __syncwarp();
+                // ---- B2 -> C, in rounds: B2 fills the pixel queue from the group queue until it is nearly full, C empties it
+                int ncw = 0, i0 = 0;
+                bool listok = true;
+                while (i0 < ngw) {
+                    int npw = 0;
+                    if (i0) { listok = false; ncw = 0; }                   // a second round: the first round's list is being overwritten
+                    for (; i0 < ngw && npw + 128 <= F2_PQ; i0 += 32) {
+                        const int gi = i0 + lane;
+                        unsigned cf = 0; int e0 = 0;
+                        if (gi < ngw) {
+                            const int g = gq[gi];
+                            const int r = __umulhi((unsigned)g, rcp), c = g - r * ngx;
+                            const unsigned* W = Wc + g + r * rskip;
+                            const unsigned v = W[0];
+                            unsigned fl[8];
+#define RINGF(k, word) { const unsigned a_ = __vabsdiffu4((word), v); fl[k] = (a_ + K) | a_; }
+                            RINGF(0, W[3 * rsw]);
+                            RINGF(4, W[-3 * rsw]);
+                            { const unsigned l = W[-1], rr = W[1]; RINGF(2, __funnelshift_r(v, rr, 24)); RINGF(6, __funnelshift_r(l, v, 8)); }
+                            { const unsigned* p = W + 2 * rsw; const unsigned* q = W - 2 * rsw;
+                              RINGF(1, __funnelshift_r(p[0], p[1], 16)); RINGF(7, __funnelshift_r(p[-1], p[0], 16));
+                              RINGF(3, __funnelshift_r(q[0], q[1], 16)); RINGF(5, __funnelshift_r(q[-1], q[0], 16)); }
+#undef RINGF
+                            unsigned out = 0;
+#pragma unroll
+                            for (int k = 0; k < 8; k++) out |= (fl[k] & fl[(k + 1) & 7] & fl[(k + 2) & 7]) & fl[(k + 3) & 7];
+                            cf = out & vtab[c];
+                            e0 = ((r + 1) << 8) + xoff0 + 4 * c;
+                        }
+                        int total = 0;
+#pragma unroll
+                        for (int bb = 0; bb < 4; bb++) {
+                            const bool on = (cf >> (8 * bb + 7)) & 1u;
+                            const unsigned bal = __ballot_sync(0xFFFFFFFFu, on);
+                            if (on) pq[npw + total + __popc(bal & ltmask)] = (unsigned short)(e0 + bb);
+                            total += __popc(bal);
+                        }
+                        npw += total;
+                    }
+                    __syncwarp();
+                    // ---- C: exact score of the queued pixels, two per lane packed 16x2
+                    const unsigned efirst = npw ? pq[0] : 0x0101u;
+                    for (int j0 = 0; j0 < npw; j0 += 64) {
+                        const int j = j0 + 2 * lane;
+                        const bool h0 = j < npw, h1 = j + 1 < npw;
+                        const unsigned ee = *reinterpret_cast<const unsigned*>(pq + j);
+                        const unsigned ea = h0 ? (ee & 0xFFFFu) : efirst, eb = h1 ? (ee >> 16) : ea;
+                        const int ya = ea >> 8, xa = ea & 255, yb = eb >> 8, xb = eb & 255;
+                        const uint8_t* pa = cimg + ya * irow + xa;
+                        const uint8_t* pb = cimg + yb * irow + xb;
+                        const int va = pa[0], vb = pb[0];
+                        unsigned w[16];
+#define PK(k, o) w[k] = (unsigned)pa[o] | ((unsigned)pb[o] << 16)
+                        PK(0, 3 * irow);      PK(1, 3 * irow + 1);   PK(2, 2 * irow + 2);   PK(3, irow + 3);
+                        PK(4, 3);             PK(5, -irow + 3);      PK(6, -2 * irow + 2);  PK(7, -3 * irow + 1);
+                        PK(8, -3 * irow);     PK(9, -3 * irow - 1);  PK(10, -2 * irow - 2); PK(11, -irow - 3);
+                        PK(12, -3);           PK(13, irow - 3);      PK(14, 2 * irow - 2);  PK(15, 3 * irow - 1);
+#undef PK
+                        unsigned A, Bm;
+                        {
+                            unsigned m3[16], m9[16];
+#pragma unroll
+                            for (int k = 0; k < 16; k++) m3[k] = __vimin3_u16x2(w[k], w[(k + 1) & 15], w[(k + 2) & 15]);
+#pragma unroll
+                            for (int k = 0; k < 16; k++) m9[k] = __vimin3_u16x2(m3[k], m3[(k + 3) & 15], m3[(k + 6) & 15]);
+                            A = __vimax3_u16x2(m9[0], m9[1], m9[2]);
+#pragma unroll
+                            for (int k = 3; k < 15; k += 2) A = __vimax3_u16x2(A, m9[k], m9[k + 1]);
+                            A = __vmaxu2(A, m9[15]);
+                        }
+                        {
+                            unsigned m3[16], m9[16];
+#pragma unroll
+                            for (int k = 0; k < 16; k++) m3[k] = __vimax3_u16x2(w[k], w[(k + 1) & 15], w[(k + 2) & 15]);
+#pragma unroll
+                            for (int k = 0; k < 16; k++) m9[k] = __vimax3_u16x2(m3[k], m3[(k + 3) & 15], m3[(k + 6) & 15]);
+                            Bm = __vimin3_u16x2(m9[0], m9[1], m9[2]);
+#pragma unroll
+                            for (int k = 3; k < 15; k += 2) Bm = __vimin3_u16x2(Bm, m9[k], m9[k + 1]);
+                            Bm = __vminu2(Bm, m9[15]);
+                        }
+                        const int sca = max((int)(A & 0xFFFFu) - va, va - (int)(Bm & 0xFFFFu)) - 1;
+                        const int scb = max((int)(A >> 16) - vb, vb - (int)(Bm >> 16)) - 1;
+                        const bool ca = h0 && sca >= t_exact, cb = h1 && scb >= t_exact;
+                        if (ca) s_score[ya * srow + xa] = (uint8_t)sca;
+                        if (cb) s_score[yb * srow + xb] = (uint8_t)scb;
+                        const unsigned bala = __ballot_sync(0xFFFFFFFFu, ca), balb = __ballot_sync(0xFFFFFFFFu, cb);
+                        const int ia = ncw + __popc(bala & ltmask), ib = ncw + __popc(bala) + __popc(balb & ltmask);
+                        // (every lane has read its two entries of this step before the ballots; slots below j0 + 64 are free)
+                        if (ca) cq[ia] = (unsigned short)ea;
+                        if (cb) cq[ib] = (unsigned short)eb;
+                        ncw += __popc(bala) + __popc(balb);
+                    }
+                    __syncwarp();
+                }
+                // ---- D: strict 3x3 NMS inside the cell (the map's frame of zeros stands for "outside the ROI interior"), survivors to
+                //      the (frame, level) list: sweep 1 decides and counts, ONE reservation per warp and cell, sweep 2 writes
+                int nkeep = 0;
+                if (listok) {
+                    for (int k0 = 0; k0 < ncw; k0 += 32) {
+                        const int k = k0 + lane;
+                        const unsigned e = k < ncw ? cq[k] : 0u;
+                        bool keep = false;
+                        if (e) {
+                            const uint8_t* sp = s_score + (e >> 8) * srow + (e & 255);
+                            const int sc = sp[0];
+                            const int m = max(max(max((int)sp[-1], (int)sp[1]), max((int)sp[-srow - 1], (int)sp[-srow])),
+                                              max(max((int)sp[-srow + 1], (int)sp[srow - 1]), max((int)sp[srow], (int)sp[srow + 1])));
+                            keep = sc > m;
+                            if (!keep) cq[k] = 0;                          // struck out (a valid entry is never 0: rows count from 1)
+                        }
+                        nkeep += __popc(__ballot_sync(0xFFFFFFFFu, keep));
+                    }
+                    if (nkeep) {
+                        int base = 0;
+                        if (lane == 0) base = atomicAdd(gcount, nkeep);
+                        base = __shfl_sync(0xFFFFFFFFu, base, 0);
+                        __syncwarp();
+                        for (int k0 = 0; k0 < ncw; k0 += 32) {
+                            const int k = k0 + lane;
+                            const unsigned e = k < ncw ? cq[k] : 0u;
+                            const unsigned bal = __ballot_sync(0xFFFFFFFFu, e != 0);
+                            if (e) {
+                                const unsigned rec = recbase + (e & 255u) + ((e >> 8) << 12) + ((unsigned)s_score[(e >> 8) * srow + (e & 255)] << 24);
+                                const int o = base + __popc(bal & ltmask);
+                                if (o < L.raw_cap) gdst[o] = rec; else atomicOr(status, 1);
+                            }
+                            base += __popc(bal);
+                        }
+                    }
+                } else {
+                    // a cell with more corners than the list holds (noise images): sweep its score map instead, twice
+                    const int ncols = cx1 - cx0;
+                    int base = 0;
+                    for (int sweep = 0; sweep < 2; sweep++) {
+                        if (sweep) {
+                            if (!nkeep) break;
+                            if (lane == 0) base = atomicAdd(gcount, nkeep);
+                            base = __shfl_sync(0xFFFFFFFFu, base, 0);
+                        }
+                        for (int yr = 1; yr <= nrows; yr++)
+                            for (int x0 = 1; x0 <= ncols; x0 += 32) {
+                                const int xr = x0 + lane;
+                                bool keep = false; int sc = 0;
+                                if (xr <= ncols) {
+                                    const uint8_t* sp = s_score + yr * srow + xr;
+                                    sc = sp[0];
+                                    const int m = max(max(max((int)sp[-1], (int)sp[1]), max((int)sp[-srow - 1], (int)sp[-srow])),
+                                                      max(max((int)sp[-srow + 1], (int)sp[srow - 1]), max((int)sp[srow], (int)sp[srow + 1])));
+                                    keep = sc > m;
+                                }
+                                const unsigned bal = __ballot_sync(0xFFFFFFFFu, keep);
+                                if (!sweep) nkeep += __popc(bal);
+                                else {
+                                    if (keep) {
+                                        const int o = base + __popc(bal & ltmask);
+                                        if (o < L.raw_cap) gdst[o] = recbase + (unsigned)xr + ((unsigned)yr << 12) + ((unsigned)sc << 24); else atomicOr(status, 1);
+                                    }
+                                    base += __popc(bal);
+                                }
+                            }
+                    }
+                }
+                __syncwarp();
+                if (nkeep) break;                                          // the cell returned keypoints: no retry (warp-uniform)
+            }
+        }
+        // this cell is done with its tile's box; the warp that completes the tile requests the CTA's next tile into the freed buffer
+        __syncwarp();
+        if (lane == 0) {
+            __threadfence_block();
+            if (atomicAdd(&s_done[b], 1) == F2_CW - 1) {
+                s_done[b] = 0;
+                fence_proxy_async_smem();                  // generic-proxy reads of the buffer before the async-proxy overwrite
+                issue(b);
+            }
+        }
+    }
+    // the last CTA to leave puts the launch-wide counters back to zero (every CTA has stopped drawing by then)
+    __syncthreads();
+    if (tid == 0 && atomicAdd(tile_ctr + 1, 1) == (int)gridDim.x - 1) { tile_ctr[0] = 0; tile_ctr[1] = 0; }
 }
 
 // --------------------------------------------------------------------------------------------------------
@@ -1526,6 +1877,8 @@ struct uvip_extractor {
     uvip_extractor_params prm;
     int device = 0;
     int num_sms = 148;         // B200; read from the device at the first plan
+    int fast2_ctas_per_sm = 0; // resident CTAs of k_fast2 per SM for the current plan (persistent grid = this x num_sms)
+    bool use_fast1 = false;    // UVIP_FAST1=1: the first FAST kernel (A/B measurements)
     cudaStream_t stream = nullptr;
     float scale[MAXLEV], inv_scale[MAXLEV];
     int quota[MAXLEV];
@@ -1644,10 +1997,30 @@ static int make_plan(const uvip_extractor* ex, int w, int h, Plan* out, std::vec
     {
         const int ngx_max = (max_tw + 2) / 4 + 1;
         P.f_irow = (int)align_up((size_t)4 * (ngx_max + 2) + 12, 16); P.f_irows = max_th + 6;   // TMA box: 16-byte aligned start and extent
+        if (P.f_irow <= F2_IROW) P.f_irow = F2_IROW;           // the common case (cells up to 33 px wide) runs k_fast2 with a compile-time row stride
         P.f_srow = (int)align_up((size_t)max_tw + 2 + FAST_CW, 4); P.f_srows = max_th + 2 + FAST_CH;   // one zero row / column between cells
         P.f_rcp_srow = 0xFFFFFFFFu / (unsigned)P.f_srow + 1u;
         P.f_gw = 32 * div_up(ngx_max * max_th, 32 * FAST_WARPS);           // groups one warp can meet
         if ((size_t)P.f_srow * P.f_srows >= 0xFFFFu) { set_last_error("FAST tile does not fit 16-bit positions"); return UVIP_ERR_UNSUPPORTED; }
+        // k_fast2: one warp per cell
+        int max_wc = 0, max_hc = 0, gcap = 0;
+        for (int l = 0; l < p.nlevels; l++) {
+            const LevelInfo& L = P.lv[l];
+            if (L.wcell > max_wc) max_wc = L.wcell;
+            if (L.hcell > max_hc) max_hc = L.hcell;
+            int ngx = (L.wcell + 6) / 4 + 1; if (ngx < 2) ngx = 2;       // any alignment of the cell inside its first / last group
+            if (ngx * L.hcell > gcap) gcap = ngx * L.hcell;
+        }
+        P.f2_srow = (int)align_up((size_t)max_wc + 2, 4); P.f2_srows = max_hc + 2;
+        P.f2_score_bytes = (int)align_up((size_t)P.f2_srow * P.f2_srows, 16);
+        P.f2_gcap = (int)align_up((size_t)gcap + 2, 8);
+        P.f2_wbytes = (int)align_up((size_t)P.f2_score_bytes + 2 * ((size_t)P.f2_gcap + F2_PQ + 2) + 4 * 20, 16);
+        P.f2_irows = max_hc + 6;
+        int f2t = 0;
+        for (int l = 0; l < p.nlevels; l++) f2t += div_up(P.lv[l].ncols, F2_CW) * P.lv[l].nrows;
+        P.f2_tiles = f2t;
+        P.f2_rcp_tiles = f2t > 1 ? 0xFFFFFFFFu / (unsigned)f2t + 1u : 0u;
+        if ((long long)f2t * p.max_batch >= (1LL << 30)) { set_last_error("too many FAST tiles for one launch group"); return UVIP_ERR_UNSUPPORTED; }
     }
     P.rcp_cpr = 0xFFFFFFFFu / (unsigned)((P.lv[0].w + 15) >> 4) + 1u;
     {
@@ -1686,8 +2059,15 @@ static int make_plan(const uvip_extractor* ex, int w, int h, Plan* out, std::vec
         if (P.rs_boxw > 256 || P.rs_boxh > 256) { set_last_error("scale factor too large for the resize tile"); return UVIP_ERR_UNSUPPORTED; }
     }
     P.tile_tab_off = tab;
+    P.f2_tab_off = tab + ft + 1 + bt;
     if (tabs) {
-        tabs->assign(tab + ft + 1 + bt, 0);
+        tabs->assign(tab + ft + 1 + bt + P.f2_tiles + 1, 0);
+        {   // k_fast2 tiles: level | cell row << 4 | first cell column << 16, level-major (the large levels of a frame first)
+            int* t = tabs->data() + P.f2_tab_off;
+            for (int l = 0; l < p.nlevels; l++)
+                for (int cy = 0; cy < P.lv[l].nrows; cy++)
+                    for (int tx = 0; tx < div_up(P.lv[l].ncols, F2_CW); tx++) *t++ = (int)((unsigned)l | ((unsigned)cy << 4) | ((unsigned)(tx * F2_CW) << 16));
+        }
         for (int l = 0; l < p.nlevels; l++) {
             const LevelInfo& L = P.lv[l];
             for (int ty = 0; ty < L.fnty; ty++)
@@ -1712,6 +2092,11 @@ static int make_plan(const uvip_extractor* ex, int w, int h, Plan* out, std::vec
     return UVIP_OK;
 }
 
+static size_t fast2_smem_bytes(const Plan& P, int irow)
+{
+    const size_t imgstride = align_up((size_t)irow * P.f2_irows, 128);
+    return F2_STAGES * imgstride + (size_t)FAST_WARPS * P.f2_wbytes;
+}
 static size_t fast_smem_bytes(const Plan& P) { return (size_t)P.f_irow * P.f_irows + (size_t)P.f_srow * P.f_srows + 2 * (size_t)FAST_WARPS * 5 * P.f_gw + 128; }
 static size_t qt_smem_bytes(int cap) { return (size_t)(4 * cap * 2 + cap * 2 + 4 * cap + cap + cap + (cap + 1) + cap + 4 * cap + cap + cap + cap) * 4; }
 
@@ -1734,6 +2119,19 @@ static int ensure_plan(uvip_extractor* ex, int w, int h)
     UVIP_CUDA(cudaDeviceSynchronize());
     UVIP_CUDA(cudaFuncSetAttribute(k_quadtree, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)qt_smem_bytes(P.node_cap)));
     UVIP_CUDA(cudaFuncSetAttribute(k_fast, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)fast_smem_bytes(P)));
+    {
+        const size_t sm2 = fast2_smem_bytes(P, P.f_irow);
+        int nb = 0;
+        if (P.f_irow == F2_IROW) {
+            UVIP_CUDA(cudaFuncSetAttribute(k_fast2<F2_IROW>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sm2));
+            UVIP_CUDA(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&nb, k_fast2<F2_IROW>, 256, sm2));
+        } else {
+            UVIP_CUDA(cudaFuncSetAttribute(k_fast2<0>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sm2));
+            UVIP_CUDA(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&nb, k_fast2<0>, 256, sm2));
+        }
+        if (nb < 1) { set_last_error("FAST kernel does not fit one SM (%zu bytes of shared memory)", sm2); return UVIP_ERR_UNSUPPORTED; }
+        ex->fast2_ctas_per_sm = nb;
+    }
     UVIP_CUDA(cudaFuncSetAttribute(k_resize<true, RS_RMAX>, cudaFuncAttributeMaxDynamicSharedMemorySize, P.rs_boxw * P.rs_boxh + 128));
     UVIP_CUDA(cudaFuncSetAttribute(k_resize<false, RS_RMAX>, cudaFuncAttributeMaxDynamicSharedMemorySize, P.rs_boxw * P.rs_boxh + 128));
     UVIP_CUDA(cudaFuncSetAttribute(k_resize<true, RS_RSMALL>, cudaFuncAttributeMaxDynamicSharedMemorySize, P.rs_boxw * P.rs_boxh + 128));
@@ -1747,7 +2145,7 @@ static int ensure_plan(uvip_extractor* ex, int w, int h)
         void* fp = nullptr; cudaDriverEntryPointQueryResult qres;
         UVIP_CUDA(cudaGetDriverEntryPoint("cuTensorMapEncodeTiled", &fp, cudaEnableDefault, &qres));
         if (!fp || qres != cudaDriverEntryPointSuccess) { set_last_error("cuTensorMapEncodeTiled is not available in this driver"); return UVIP_ERR_CUDA; }
-        alignas(64) CUtensorMap maps[3 * MAXLEV];         // FAST tile boxes | blur tile boxes | resize source boxes
+        alignas(64) CUtensorMap maps[4 * MAXLEV];         // FAST (first kernel) tile boxes | blur tile boxes | resize source boxes | k_fast2 tile boxes
         memset(maps, 0, sizeof(maps));
         for (int l = 0; l < P.nlevels; l++) {
             const LevelInfo& L = P.lv[l];
@@ -1769,6 +2167,11 @@ static int ensure_plan(uvip_extractor* ex, int w, int h)
                                 CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_NONE, CU_TENSOR_MAP_L2_PROMOTION_L2_128B,
                                 CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
             if (r != CUDA_SUCCESS) { set_last_error("cuTensorMapEncodeTiled(resize, level %d) failed: %d", l, (int)r); return UVIP_ERR_CUDA; }
+            const cuuint32_t f2box[3] = {(cuuint32_t)P.f_irow, (cuuint32_t)P.f2_irows, 1};
+            r = ((encode_fn)fp)(&maps[3 * MAXLEV + l], CU_TENSOR_MAP_DATA_TYPE_UINT8, 3, ex->pyr.as<uint8_t>() + L.poff, gdim, gstr, f2box, estr,
+                                CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_NONE, CU_TENSOR_MAP_L2_PROMOTION_L2_128B,
+                                CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+            if (r != CUDA_SUCCESS) { set_last_error("cuTensorMapEncodeTiled(FAST, level %d) failed: %d", l, (int)r); return UVIP_ERR_CUDA; }
         }
         ex->plan.W = 0;                                        // from here on the old plan is gone; a failed copy leaves "no plan"
         UVIP_CUDA(cudaMemcpy(ex->tabs.p, tabs.data(), tabs.size() * sizeof(int), cudaMemcpyHostToDevice));
@@ -1818,8 +2221,22 @@ static int enqueue_group(uvip_extractor* ex, const uint8_t* d_frames, int nframe
         ex->launches++;
     }
     PROF_MARK(1);
-    k_fast<<<dim3(P.ftiles, nframes), 256, fast_smem_bytes(P), st>>>(ex->tmaps.as<CUtensorMap>(), ex->tabs.as<unsigned>() + P.tile_tab_off, ex->cand.as<unsigned>(),
-                                                                     cand_count, ex->status.as<int>(), P);
+    if (ex->use_fast1)
+        k_fast<<<dim3(P.ftiles, nframes), 256, fast_smem_bytes(P), st>>>(ex->tmaps.as<CUtensorMap>(), ex->tabs.as<unsigned>() + P.tile_tab_off, ex->cand.as<unsigned>(),
+                                                                         cand_count, ex->status.as<int>(), P);
+    else {
+        // persistent CTAs: as many as stay resident, each walking the (tile, frame) space with stride gridDim.x
+        // (every CTA stages F2_STAGES tiles at once: a grid larger than T / F2_STAGES would only draw empty tickets)
+        const long long T = (long long)P.f2_tiles * nframes, res = (long long)ex->fast2_ctas_per_sm * ex->num_sms;
+        const long long want = (T + F2_STAGES - 1) / F2_STAGES;
+        const unsigned grid = (unsigned)(want < res ? want : res);
+        if (P.f_irow == F2_IROW)
+            k_fast2<F2_IROW><<<grid, 256, fast2_smem_bytes(P, P.f_irow), st>>>(ex->tmaps.as<CUtensorMap>(), ex->tabs.as<unsigned>() + P.f2_tab_off,
+                                                                               ex->cand.as<unsigned>(), cand_count, ex->status.as<int>(), nframes, P);
+        else
+            k_fast2<0><<<grid, 256, fast2_smem_bytes(P, P.f_irow), st>>>(ex->tmaps.as<CUtensorMap>(), ex->tabs.as<unsigned>() + P.f2_tab_off,
+                                                                         ex->cand.as<unsigned>(), cand_count, ex->status.as<int>(), nframes, P);
+    }
     ex->launches++;
     PROF_MARK(2);
     k_quadtree<<<dim3(nframes, P.nlevels), QT_THREADS, qt_smem_bytes(P.node_cap), st>>>(
@@ -1913,7 +2330,7 @@ int uvip_extractor_create(const uvip_extractor_params* params, uvip_extractor** 
     const int B = params->max_batch;
     ex->cap_frame_bytes = P.frame_bytes; ex->cap_cells = P.cells_per_frame; ex->cap_raw = P.raw_per_frame; ex->cap_kp = P.kp_per_frame;
     int tab = 0; for (int l = 1; l < nl; l++) tab += 2 * P.lv[l].w + 2 * P.lv[l].h;
-    ex->cap_tab = tab + P.ftiles + 4096;      // resize tables + FAST tile table (+ slack for other aspect ratios)
+    ex->cap_tab = tab + 2 * (P.ftiles + P.btiles + P.f2_tiles) + 4096;      // resize tables + tile tables (+ slack for other aspect ratios)
     ex->sel_cap = P.kp_per_frame + 4096;     // output rows per frame: quadtree winners + up to 4096 incoming keypoints
     cudaError_t e = cudaStreamCreateWithFlags(&ex->stream, cudaStreamNonBlocking);
     if (e != cudaSuccess) { set_last_error("cudaStreamCreate -> %s", cudaGetErrorString(e)); delete ex; return UVIP_ERR_CUDA; }
@@ -1930,7 +2347,7 @@ int uvip_extractor_create(const uvip_extractor_params* params, uvip_extractor** 
     rc |= ex->status.reserve(16);
     rc |= ex->grid.reserve(16);
     rc |= ex->incoming.reserve(sizeof(uvip_keypoint));
-    rc |= ex->tmaps.reserve(sizeof(CUtensorMap) * 3 * MAXLEV);
+    rc |= ex->tmaps.reserve(sizeof(CUtensorMap) * 4 * MAXLEV);
     rc |= ex->pat_t.reserve(sizeof(float) * 2 * 512);
     if (rc) { uvip_extractor_destroy(ex); return UVIP_ERR_CUDA; }
     // zero the planes once so halo loads never see uninitialised memory
@@ -1948,6 +2365,12 @@ int uvip_extractor_create(const uvip_extractor_params* params, uvip_extractor** 
             for (int vv = 0; vv <= HALF_PATCH; vv++)
                 if ((uu <= ex->umax[vv]) != (vv <= ex->umax[uu])) { set_last_error("umax table is not symmetric"); uvip_extractor_destroy(ex); return UVIP_ERR_UNSUPPORTED; }
     }
+    {
+        unsigned rcp[33]; rcp[0] = rcp[1] = 0;
+        for (int n = 2; n <= 32; n++) rcp[n] = 0xFFFFFFFFu / (unsigned)n + 1u;
+        if (cudaMemcpyToSymbol(c_rcp32, rcp, sizeof(rcp)) != cudaSuccess) { set_last_error("cudaMemcpyToSymbol(c_rcp32) failed"); uvip_extractor_destroy(ex); return UVIP_ERR_CUDA; }
+    }
+    { const char* e1 = getenv("UVIP_FAST1"); ex->use_fast1 = e1 && e1[0] == '1'; }
     if (cudaMemcpyToSymbol(c_pattern, h_pattern, sizeof(h_pattern)) != cudaSuccess ||
         cudaMemcpyToSymbol(c_umax, ex->umax, sizeof(ex->umax)) != cudaSuccess) {
         set_last_error("cudaMemcpyToSymbol failed: %s", cudaGetErrorString(cudaGetLastError()));
