@@ -6,6 +6,7 @@
 #include <string.h>
 #include <mutex>
 #include <string>
+#include <nvtx3/nvToolsExt.h>
 #include "../../include/uvip_orb.h"
 
 namespace uvip {
@@ -28,6 +29,13 @@ void set_last_error(const char* fmt, ...);
             return UVIP_ERR_ARG;                                                                \
         }                                                                                       \
     } while (0)
+
+// NVTX range around the host-side enqueue of one pipeline stage (header-only NVTX v3: a no-op unless a tool is attached).  ncu can
+// then select a stage by name: `ncu --nvtx --nvtx-include "uvip/fast/" ...` (tools/ncu_stage.sh).
+struct NvtxRange {
+    explicit NvtxRange(const char* name) { nvtxRangePushA(name); }
+    ~NvtxRange() { nvtxRangePop(); }
+};
 
 static inline int div_up(int a, int b) { return (a + b - 1) / b; }
 static inline size_t align_up(size_t a, size_t b) { return (a + b - 1) / b * b; }

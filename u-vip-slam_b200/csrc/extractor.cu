@@ -609,6 +609,7 @@ k_fast2(const CUtensorMap* __restrict__ tmaps, const unsigned* __restrict__ tile
     // announcement of the CTA's tile number q (slot q & 7): which launch tile it is (-1: the launch has no more), where it lands and the
     // parity of that buffer's mbarrier phase; s_rseq is written last
     __shared__ volatile int s_rseq[F2_RING], s_rtile[F2_RING], s_rbuf[F2_RING];
+    __shared__ volatile unsigned s_rte[F2_RING];          // the tile's table entry (level | cell row << 4 | first cell column << 16)
     const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
     const int irow = IROWT ? IROWT : P.f_irow;
     const int imgbytes = irow * P.f2_irows, imgstride = (imgbytes + 127) & ~127;
@@ -632,7 +633,7 @@ k_fast2(const CUtensorMap* __restrict__ tmaps, const unsigned* __restrict__ tile
         const int TX0 = EDGE + (int)(te >> 16) * L.wcell, TY0 = EDGE + (int)((te >> 4) & 0xFFF) * L.hcell;
         const int ax0 = ((((TX0 & ~3) - 4 + EDGE) & ~15) - EDGE), ay0 = TY0 - 3;
         const int par = s_loads[buf] & 1; s_loads[buf]++;
-        s_rtile[slot] = t; s_rbuf[slot] = buf | (par << 8); __threadfence_block(); s_rseq[slot] = q;
+        s_rtile[slot] = f; s_rte[slot] = te; s_rbuf[slot] = buf | (par << 8); __threadfence_block(); s_rseq[slot] = q;
         mbar_arrive_expect_tx(&s_full[buf], (unsigned)imgbytes);
         tma_load_3d(s_f2 + (size_t)buf * imgstride, tmaps + 3 * MAXLEV + (te & 15), ax0 + EDGE, ay0 + EDGE, f, &s_full[buf]);
     };
@@ -668,11 +669,10 @@ k_fast2(const CUtensorMap* __restrict__ tmaps, const unsigned* __restrict__ tile
         const int q = n >> 2, cj = n & 3, slot = q & (F2_RING - 1);
         static_assert(F2_CW == 4, "four cells per tile");
         while (s_rseq[slot] != q) __nanosleep(64);         // the tile has not been announced yet (its buffer is still busy)
-        const int t = s_rtile[slot];
-        if (t < 0) break;                                  // the launch has no more tiles (cells are handed out in tile order)
+        const int f = s_rtile[slot];                       // the tile's frame
+        if (f < 0) break;                                  // the launch has no more tiles (cells are handed out in tile order)
         const int bp = s_rbuf[slot], b = bp & 255;
-        const int f = P.f2_tiles > 1 ? (int)__umulhi((unsigned)t, P.f2_rcp_tiles) : t, tl = t - f * P.f2_tiles;
-        const unsigned te = __ldg(tile_tab + tl);
+        const unsigned te = s_rte[slot];
         const int level = te & 15, tcy0 = (te >> 4) & 0xFFF, tcx0 = te >> 16;
         const LevelInfo& L = P.lv[level];
         const int wc = L.wcell, hc = L.hcell;
@@ -2197,8 +2197,10 @@ static int enqueue_group(uvip_extractor* ex, const uint8_t* d_frames, int nframe
     if (reset_status) UVIP_CUDA(cudaMemsetAsync(ex->status.p, 0, sizeof(int), st));
     cudaEvent_t* pe = ex->prof ? ex->prof_ev.data() + (size_t)(ex->prof_groups % PROF_RING) * (UVIP_NUM_STAGES + 1) : nullptr;
 #define PROF_MARK(i) do { if (pe) UVIP_CUDA(cudaEventRecord(pe[i], st)); } while (0)
+    NvtxRange nv_group("uvip/extract_group");
     PROF_MARK(0);
     {
+        NvtxRange nv("uvip/pyramid");
         const LevelInfo& L = P.lv[0];
         const int chunks = ((L.w + 15) >> 4) * L.h;
         const int vec_ok = (((uintptr_t)d_frames & 15) == 0 && (stride & 15) == 0 && (frame_pitch & 15) == 0) ? 1 : 0;
@@ -2207,6 +2209,7 @@ static int enqueue_group(uvip_extractor* ex, const uint8_t* d_frames, int nframe
         ex->launches++;
     }
     for (int l = 1; l < P.nlevels; l++) {
+        NvtxRange nv("uvip/pyramid");
         const LevelInfo& L = P.lv[l];
         // half-height tiles when full ones would not even fill one wave (6 CTAs per SM): twice the CTAs for a lone frame or a small
         // batch (single-frame pyramid 0.063 -> 0.054 ms).  At batch 256 every level stays on full tiles: half tiles for the 1.2-2.6-wave
@@ -2221,6 +2224,8 @@ static int enqueue_group(uvip_extractor* ex, const uint8_t* d_frames, int nframe
         ex->launches++;
     }
     PROF_MARK(1);
+    {
+    NvtxRange nv("uvip/fast");
     if (ex->use_fast1)
         k_fast<<<dim3(P.ftiles, nframes), 256, fast_smem_bytes(P), st>>>(ex->tmaps.as<CUtensorMap>(), ex->tabs.as<unsigned>() + P.tile_tab_off, ex->cand.as<unsigned>(),
                                                                          cand_count, ex->status.as<int>(), P);
@@ -2238,29 +2243,42 @@ static int enqueue_group(uvip_extractor* ex, const uint8_t* d_frames, int nframe
                                                                          ex->cand.as<unsigned>(), cand_count, ex->status.as<int>(), nframes, P);
     }
     ex->launches++;
+    }
     PROF_MARK(2);
+    {
+    NvtxRange nv("uvip/quadtree");
     k_quadtree<<<dim3(nframes, P.nlevels), QT_THREADS, qt_smem_bytes(P.node_cap), st>>>(
         ex->cand.as<unsigned>(), cand_count, ex->labels.as<unsigned short>(), ex->winners.as<unsigned>(), win_count,
         ex->status.as<int>(), P);
     ex->launches++;
+    }
     PROF_MARK(3);
+    {
+    NvtxRange nv("uvip/blur");
     k_blur<<<dim3(P.btiles, nframes), 256, 0, st>>>(ex->tmaps.as<CUtensorMap>(), ex->tabs.as<unsigned>() + P.tile_tab_off + P.ftiles + 1, pyr, blur, P);
     ex->launches++;
     if (!full_detect && n_incoming > 0) {                      // incoming level-0 keypoints may sit inside the 16-px border zone
         k_ring16<<<8, 256, 0, st>>>(pyr, blur, P);
         ex->launches++;
     }
+    }
     PROF_MARK(4);
+    {
+    NvtxRange nv("uvip/select");
     k_select<<<nframes, 256, 0, st>>>(ex->winners.as<unsigned>(), win_count, ex->sel.as<unsigned>(), ex->nsel.as<int>(), ex->sel_cap,
                                        full_detect, n_incoming, ex->grid.as<int32_t>(), grid_rows, grid_cols, min_px_dist, num_needed,
                                        d_dyn, ex->status.as<int>(), P);
     ex->launches++;
+    }
     const int slots = out_cap < ex->sel_cap ? out_cap : ex->sel_cap;
     PROF_MARK(5);
+    {
+    NvtxRange nv("uvip/describe");
     k_describe<<<dim3(div_up(slots, DESC_WARPS * DESC_KPW), nframes), DESC_WARPS * 32, 0, st>>>(
         pyr, blur, ex->winners.as<unsigned>(), ex->sel.as<unsigned>(), ex->nsel.as<int>(), ex->sel_cap,
         ex->incoming.as<uvip_keypoint>(), ex->pat_t.as<float2>(), d_kps, d_desc, d_n_out, out_cap, ex->status.as<int>(), P);
     ex->launches++;
+    }
     PROF_MARK(6);
 #undef PROF_MARK
     if (pe) ex->prof_groups++;
