@@ -35,7 +35,7 @@ def parse():
     ap.add_argument('--impl', default='ours', choices=['ours', 'reference'])
     ap.add_argument('--batch', type=int, default=256, help='frames per step and per GPU')
     ap.add_argument('--ref-frames', type=int, default=0, help='frames per step of the reference arm (0 = --batch, the same step as our arm)')
-    ap.add_argument('--e2e-chunk', type=int, default=0, help='frames per pipeline chunk of the host-buffer entry point (0 = batch/2)')
+    ap.add_argument('--e2e-chunk', type=int, default=0, help='frames per pipeline chunk of the host-buffer entry point (0 = the batch)')
     ap.add_argument('--no-extras', action='store_true', help='skip the Hamming-only and cpu_baseline legs')
     ap.add_argument('--workload', default='frames', choices=['frames', 'knn', 'search', 'next'],
                     help="'frames' = the headline metric; 'knn' = BASELINE config 4: database-sharded brute-force kNN2 with NCCL top-2 merge; 'search' = BASELINE config 3: batched grid-windowed SearchByProjection")
@@ -516,29 +516,43 @@ def run_ours(args):
                        k=torch.zeros((B, cap, 28), dtype=torch.uint8).pin_memory(), d=torch.zeros((B, cap, 32), dtype=torch.uint8).pin_memory(),
                        n=torch.zeros(B, dtype=torch.int32).pin_memory(), i=torch.zeros((B, cap, 2), dtype=torch.int32).pin_memory(),
                        dd=torch.zeros((B, cap, 2), dtype=torch.int32).pin_memory()))
-    ex_e2e = pkg.ORBextractor(NFEAT, SCALE, NLEVELS, pkg.ORBextractor.FAST_SCORE, FAST_TH, device=local, max_width=W, max_height=H,
-                              max_batch=args.e2e_chunk or max(1, B // 2))
+    # UVIP_E2E_HANDLES (default 2) extractor / matcher handle pairs take alternate steps, UVIP_E2E_INFLIGHT (default 2 per handle) batches
+    # are in flight.  A handle runs its kernels on ONE stream; with two handles the kernels of consecutive steps overlap like in the
+    # HBM-resident schedule above, and with two batches queued per handle the upload of a step never waits for the host.  Measured on one
+    # B200 (tools/e2e_sweep.sh): 1 handle / 2 in flight / 128-frame chunks (round 1's schedule) 120.9 k frames/s; 2 / 2 / 128: 124.6 k;
+    # 2 / 4 / 128: 132.3 k; 2 / 4 / 64: 120.8 k; 3 / 6 / 128: 142.1 k; 2 / 4 / 256: 143.7 k = 96 % of the 149.4 k link ceiling
+    NH = max(1, int(os.environ.get('UVIP_E2E_HANDLES', '2')))
+    ex_e2es = [pkg.ORBextractor(NFEAT, SCALE, NLEVELS, pkg.ORBextractor.FAST_SCORE, FAST_TH, device=local, max_width=W, max_height=H,
+                                max_batch=args.e2e_chunk or B) for _ in range(NH)]
+    m_e2es = [m] + [pkg.ORBmatcher(0.75, True, device=local) for _ in range(NH - 1)]
+    ex_e2e = ex_e2es[0]
+    while len(hb) < max(2, int(os.environ.get('UVIP_E2E_INFLIGHT', str(2 * NH)))):
+        hb.append(dict(inp=hb[len(hb) % 2]['inp'], k=torch.zeros((B, cap, 28), dtype=torch.uint8).pin_memory(), d=torch.zeros((B, cap, 32), dtype=torch.uint8).pin_memory(),
+                       n=torch.zeros(B, dtype=torch.int32).pin_memory(), i=torch.zeros((B, cap, 2), dtype=torch.int32).pin_memory(),
+                       dd=torch.zeros((B, cap, 2), dtype=torch.int32).pin_memory()))
 
     # uvip_extract_match_batch_submit chains the consecutive-frame kNN2 behind the extraction ON THE DEVICE: the descriptors a step
     # downloads are not uploaded again (round 1's e2e leg paid 8.9 MB of H2D per step for that: uvip_extract_batch_wait -> uvip_knn2_batch)
-    def submit(j):
+    NB = len(hb)                                           # batches in flight = host buffer sets; step i uses set i % NB on handle i % NH
+
+    def submit(i):
+        j = i % NB
         t = C.c_int(-1)
-        chk(L.uvip_extract_match_batch_submit(ex_e2e.h, m.h, hp(hb[j]['inp']), B, W, H, W, W * H, hp(hb[j]['k']), hp(hb[j]['n']), cap, hp(hb[j]['d']),
-                                              hp(hb[j]['i']), hp(hb[j]['dd']), C.byref(t)))
+        chk(L.uvip_extract_match_batch_submit(ex_e2es[i % NH].h, m_e2es[i % NH].h, hp(hb[j]['inp']), B, W, H, W, W * H, hp(hb[j]['k']), hp(hb[j]['n']), cap,
+                                              hp(hb[j]['d']), hp(hb[j]['i']), hp(hb[j]['dd']), C.byref(t)))
         return t.value
 
-    def finish(j, t):
-        chk(L.uvip_extract_batch_wait(ex_e2e.h, t))
-
     def e2e_run(nsteps):
-        t = submit(0)
+        tickets = {}
+        for i in range(min(NB, nsteps)):
+            tickets[i] = submit(i)
         for i in range(nsteps):
-            tn = submit((i + 1) & 1) if i + 1 < nsteps else None
-            finish(i & 1, t)
-            t = tn
+            chk(L.uvip_extract_batch_wait(ex_e2es[i % NH].h, tickets.pop(i)))
+            if i + NB < nsteps:
+                tickets[i + NB] = submit(i + NB)
 
     Ke = max(3, min(K, 40))
-    e2e_run(2)
+    e2e_run(NB)
     barrier()
     te = time.perf_counter()
     e2e_run(Ke)
@@ -552,7 +566,7 @@ def run_ours(args):
     h2d = B * W * H
     d2h = B * cap * 60 + B * 4 + 2 * (B - 1) * cap * 8
     # the chained results equal the two-call path's on the last step's buffers (cheap: the kNN of 3 pairs through the host entry point)
-    jl = (Ke - 1) & 1
+    jl = (Ke - 1) % NB
     chk_i = np.zeros((3, cap, 2), np.int32); chk_d = np.zeros((3, cap, 2), np.int32)
     chk(L.uvip_knn2_batch(m.h, hp(hb[jl]['d']), hp(hb[jl]['n']), cap * 32, C.c_void_p(hb[jl]['d'].data_ptr() + cap * 32),
                           C.c_void_p(hb[jl]['n'].data_ptr() + 4), cap * 32, 3, cap, C.c_void_p(chk_i.ctypes.data), C.c_void_p(chk_d.ctypes.data), cap))
@@ -638,8 +652,8 @@ def run_ours(args):
         'config': workload_config(args, B, world),
         'clocks': clk,
         'e2e': {'value': e2e_fps, 'unit': 'frames/s', 'h2d_bytes_per_step': h2d, 'd2h_bytes_per_step': d2h, 'steps': Ke,
-                'chunk_frames': args.e2e_chunk or max(1, B // 2), 'single_frame_latency_ms': lat_ms,
-                'pipeline': 'uvip_extract_match_batch_submit / _wait, 2 batches in flight; consecutive-frame kNN2 chained on the device (no descriptor re-upload)',
+                'chunk_frames': args.e2e_chunk or B, 'single_frame_latency_ms': lat_ms,
+                'pipeline': 'uvip_extract_match_batch_submit / _wait, %d batches in flight over %d handle pair(s); consecutive-frame kNN2 chained on the device (no descriptor re-upload)' % (NB, NH),
                 'chained_knn_equals_two_call_path': bool(e2e_knn_ok),
                 'link_ceiling_frames_per_s': link_fps, 'link_ceiling_gb_per_s_h2d': world * B * W * H * Ke / link_s / 1e9,
                 'link_ceiling_what': 'the same pinned H2D (frames) and D2H (keypoints, descriptors, kNN results) copies of %d steps with no kernels, '

@@ -117,6 +117,11 @@ int   uvip_extract_match_batch_submit(uvip_extractor* ex, struct uvip_matcher* m
 int   uvip_extract_batch_device(uvip_extractor* ex, const uint8_t* d_frames, int nframes, int w, int h, int stride,
                                 size_t frame_pitch, uvip_keypoint* d_kps, int32_t* d_n_out, int cap, uint8_t* d_desc,
                                 void* stream);
+/* frames > 0: uvip_extract_batch_device enqueues a launch group as sub-batches of that many frames, each run through ALL stages before
+ * the next starts, so that a sub-batch's pyramid (1.33 MB per 752x480 frame and plane set) is still in the 126 MB L2 when FAST, the
+ * blur and the descriptor stage read it back: less DRAM traffic, more (smaller) launches.  0 = one launch per stage for the whole group
+ * (default).  Results are identical.  The debug taps address the frames of the LAST sub-batch. */
+int   uvip_extractor_set_subbatch(uvip_extractor* ex, int frames);
 int   uvip_extractor_status(uvip_extractor* ex);   /* synchronises the handle; UVIP_OK or the sticky error of the last group */
 void* uvip_extractor_stream(uvip_extractor* ex);   /* the handle's own cudaStream_t (what a NULL stream argument selects) */
 /* how often uvip_extract had to capture + instantiate its CUDA graph (once per call SHAPE: frame geometry, cap, FullDetect,
@@ -330,6 +335,14 @@ int         uvip_device_count(void);
 /* measurement utility (no reference counterpart): sustained __popc throughput of `device` in popc/s — the
  * denominator of the Hamming-kNN roofline */
 int         uvip_popc_peak(int device, int iters, double* popc_per_s);
+
+/* ---- bench / test utility (not part of the hot path) ----------------------------------------------------------------------------
+ * SURVEY.md Appendix B `synth_frame(seed, W, H, dx, dy, noise_seed)` on the device, byte-identical to the numpy generator of
+ * u-vip-slam_b200/synth.py: frame f is written at d_out + f*frame_pitch (w*h bytes, row-major).  d_seeds / d_noise_seeds: int64 per frame,
+ * d_dxy: (dx, dy) int32 pairs, |dx|, |dy| <= 32.  BASELINE config 5 (8 x 4096 frames of 1280x1024) is generated with it on the GPU box.
+ * There is no handle: `stream` is used as given (NULL = the legacy default stream). */
+int   uvip_synth_frames_device(const long long* d_seeds, const int* d_dxy, const long long* d_noise_seeds, int nframes, int w, int h,
+                               uint8_t* d_out, size_t frame_pitch, void* stream);
 
 #ifdef __cplusplus
 }

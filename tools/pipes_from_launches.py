@@ -19,8 +19,10 @@ for r in rows[i0 + 1:]:
 order = sorted(launches)
 # one step = import, 7 x resize, fast, quadtree, blur, select, describe, knn2: take the LAST complete step of the list
 names = [launches[i]['name'] for i in order]
-start = max(i for i, n in enumerate(names) if 'k_import' in n)
-step = [launches[order[i]] for i in range(start, len(order))]
+last_desc = max(i for i, n in enumerate(names) if 'k_describe' in n)
+start = max(i for i, n in enumerate(names) if 'k_import' in n and i < last_desc)        # the last COMPLETE step of the window
+nxt = [i for i, n in enumerate(names) if 'k_import' in n and i > start]
+step = [launches[order[i]] for i in range(start, nxt[0] if nxt else len(order))]
 # the kNN of a step follows the describe of the same step; if the list ends before it, take the one in front of the import
 knn = [l for l in step if 'k_knn2' in l['name']] or [launches[order[i]] for i in range(start) if 'k_knn2' in names[i]][-1:]
 def entry(l, extra=None):

@@ -7,7 +7,7 @@ import subprocess
 HERE = os.path.dirname(os.path.abspath(__file__))
 CSRC = os.path.join(HERE, 'csrc')
 SO = os.path.join(HERE, 'libuvip_orb.so')
-SOURCES = ['matcher.cu', 'extractor.cu', 'klt.cu']
+SOURCES = ['matcher.cu', 'extractor.cu', 'klt.cu', 'synth.cu']
 NVCC_FLAGS = ['-gencode', 'arch=compute_100a,code=sm_100a', '-O3', '-lineinfo', '-std=c++17',
               '-Xcompiler', '-fPIC', '-Xcompiler', '-Wall', '--shared', '-cudart', 'static',
               '-fmad=false',            # float parity: the reference build has no FMA contraction

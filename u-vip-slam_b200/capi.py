@@ -70,6 +70,7 @@ def lib():
         L.uvip_extract_match_batch_submit.argtypes = [vp, vp, vp, i, i, i, i, sz, vp, vp, i, vp, vp, vp, C.POINTER(i)]
         L.uvip_extract_batch_device.argtypes = [vp, vp, i, i, i, i, sz, vp, vp, i, vp, vp]
         L.uvip_extractor_status.argtypes = [vp]
+        L.uvip_extractor_set_subbatch.argtypes = [vp, i]
         L.uvip_get_pyramid_level.argtypes = [vp, i, i, i, vp, i, C.POINTER(i), C.POINTER(i)]
         L.uvip_get_raw_corners.argtypes = [vp, i, i, vp, vp, vp, i, C.POINTER(i)]
         L.uvip_get_level_keypoints.argtypes = [vp, i, i, vp, vp, vp, i, C.POINTER(i)]
@@ -118,6 +119,7 @@ def lib():
         L.uvip_klt_track.argtypes = [vp, i, i, vp, vp, i, i, i, C.c_double, i, C.c_double, vp, vp]
         L.uvip_klt_launch_count.argtypes = [vp]
         L.uvip_klt_launch_count.restype = C.c_longlong
+        L.uvip_synth_frames_device.argtypes = [vp, vp, vp, i, i, i, vp, sz, vp]
         L.uvip_popc_peak.argtypes = [i, i, C.POINTER(C.c_double)]
         _LIB = L
     return _LIB

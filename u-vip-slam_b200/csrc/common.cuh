@@ -31,7 +31,7 @@ void set_last_error(const char* fmt, ...);
     } while (0)
 
 // NVTX range around the host-side enqueue of one pipeline stage (header-only NVTX v3: a no-op unless a tool is attached).  ncu can
-// then select a stage by name: `ncu --nvtx --nvtx-include "uvip/fast/" ...` (tools/ncu_stage.sh).
+// then select a stage by name: `ncu --nvtx --nvtx-include "uvip_extract_group/uvip_fast/" ...` (tools/ncu_stage.sh).
 struct NvtxRange {
     explicit NvtxRange(const char* name) { nvtxRangePushA(name); }
     ~NvtxRange() { nvtxRangePop(); }

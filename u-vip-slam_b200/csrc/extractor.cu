@@ -1879,6 +1879,7 @@ struct uvip_extractor {
     int num_sms = 148;         // B200; read from the device at the first plan
     int fast2_ctas_per_sm = 0; // resident CTAs of k_fast2 per SM for the current plan (persistent grid = this x num_sms)
     bool use_fast1 = false;    // UVIP_FAST1=1: the first FAST kernel (A/B measurements)
+    int subbatch = 0;          // > 0: a launch group is enqueued as sub-batches of this many frames through ALL stages (L2-resident pyramid)
     cudaStream_t stream = nullptr;
     float scale[MAXLEV], inv_scale[MAXLEV];
     int quota[MAXLEV];
@@ -2197,10 +2198,10 @@ static int enqueue_group(uvip_extractor* ex, const uint8_t* d_frames, int nframe
     if (reset_status) UVIP_CUDA(cudaMemsetAsync(ex->status.p, 0, sizeof(int), st));
     cudaEvent_t* pe = ex->prof ? ex->prof_ev.data() + (size_t)(ex->prof_groups % PROF_RING) * (UVIP_NUM_STAGES + 1) : nullptr;
 #define PROF_MARK(i) do { if (pe) UVIP_CUDA(cudaEventRecord(pe[i], st)); } while (0)
-    NvtxRange nv_group("uvip/extract_group");
+    NvtxRange nv_group("uvip_extract_group");
     PROF_MARK(0);
     {
-        NvtxRange nv("uvip/pyramid");
+        NvtxRange nv("uvip_pyramid");
         const LevelInfo& L = P.lv[0];
         const int chunks = ((L.w + 15) >> 4) * L.h;
         const int vec_ok = (((uintptr_t)d_frames & 15) == 0 && (stride & 15) == 0 && (frame_pitch & 15) == 0) ? 1 : 0;
@@ -2209,7 +2210,7 @@ static int enqueue_group(uvip_extractor* ex, const uint8_t* d_frames, int nframe
         ex->launches++;
     }
     for (int l = 1; l < P.nlevels; l++) {
-        NvtxRange nv("uvip/pyramid");
+        NvtxRange nv("uvip_pyramid");
         const LevelInfo& L = P.lv[l];
         // half-height tiles when full ones would not even fill one wave (6 CTAs per SM): twice the CTAs for a lone frame or a small
         // batch (single-frame pyramid 0.063 -> 0.054 ms).  At batch 256 every level stays on full tiles: half tiles for the 1.2-2.6-wave
@@ -2225,7 +2226,7 @@ static int enqueue_group(uvip_extractor* ex, const uint8_t* d_frames, int nframe
     }
     PROF_MARK(1);
     {
-    NvtxRange nv("uvip/fast");
+    NvtxRange nv("uvip_fast");
     if (ex->use_fast1)
         k_fast<<<dim3(P.ftiles, nframes), 256, fast_smem_bytes(P), st>>>(ex->tmaps.as<CUtensorMap>(), ex->tabs.as<unsigned>() + P.tile_tab_off, ex->cand.as<unsigned>(),
                                                                          cand_count, ex->status.as<int>(), P);
@@ -2246,7 +2247,7 @@ static int enqueue_group(uvip_extractor* ex, const uint8_t* d_frames, int nframe
     }
     PROF_MARK(2);
     {
-    NvtxRange nv("uvip/quadtree");
+    NvtxRange nv("uvip_quadtree");
     k_quadtree<<<dim3(nframes, P.nlevels), QT_THREADS, qt_smem_bytes(P.node_cap), st>>>(
         ex->cand.as<unsigned>(), cand_count, ex->labels.as<unsigned short>(), ex->winners.as<unsigned>(), win_count,
         ex->status.as<int>(), P);
@@ -2254,7 +2255,7 @@ static int enqueue_group(uvip_extractor* ex, const uint8_t* d_frames, int nframe
     }
     PROF_MARK(3);
     {
-    NvtxRange nv("uvip/blur");
+    NvtxRange nv("uvip_blur");
     k_blur<<<dim3(P.btiles, nframes), 256, 0, st>>>(ex->tmaps.as<CUtensorMap>(), ex->tabs.as<unsigned>() + P.tile_tab_off + P.ftiles + 1, pyr, blur, P);
     ex->launches++;
     if (!full_detect && n_incoming > 0) {                      // incoming level-0 keypoints may sit inside the 16-px border zone
@@ -2264,7 +2265,7 @@ static int enqueue_group(uvip_extractor* ex, const uint8_t* d_frames, int nframe
     }
     PROF_MARK(4);
     {
-    NvtxRange nv("uvip/select");
+    NvtxRange nv("uvip_select");
     k_select<<<nframes, 256, 0, st>>>(ex->winners.as<unsigned>(), win_count, ex->sel.as<unsigned>(), ex->nsel.as<int>(), ex->sel_cap,
                                        full_detect, n_incoming, ex->grid.as<int32_t>(), grid_rows, grid_cols, min_px_dist, num_needed,
                                        d_dyn, ex->status.as<int>(), P);
@@ -2273,7 +2274,7 @@ static int enqueue_group(uvip_extractor* ex, const uint8_t* d_frames, int nframe
     const int slots = out_cap < ex->sel_cap ? out_cap : ex->sel_cap;
     PROF_MARK(5);
     {
-    NvtxRange nv("uvip/describe");
+    NvtxRange nv("uvip_describe");
     k_describe<<<dim3(div_up(slots, DESC_WARPS * DESC_KPW), nframes), DESC_WARPS * 32, 0, st>>>(
         pyr, blur, ex->winners.as<unsigned>(), ex->sel.as<unsigned>(), ex->nsel.as<int>(), ex->sel_cap,
         ex->incoming.as<uvip_keypoint>(), ex->pat_t.as<float2>(), d_kps, d_desc, d_n_out, out_cap, ex->status.as<int>(), P);
@@ -2389,6 +2390,7 @@ int uvip_extractor_create(const uvip_extractor_params* params, uvip_extractor** 
         if (cudaMemcpyToSymbol(c_rcp32, rcp, sizeof(rcp)) != cudaSuccess) { set_last_error("cudaMemcpyToSymbol(c_rcp32) failed"); uvip_extractor_destroy(ex); return UVIP_ERR_CUDA; }
     }
     { const char* e1 = getenv("UVIP_FAST1"); ex->use_fast1 = e1 && e1[0] == '1'; }
+    { const char* e2 = getenv("UVIP_SUBBATCH"); if (e2) ex->subbatch = atoi(e2) > 0 ? atoi(e2) : 0; }
     if (cudaMemcpyToSymbol(c_pattern, h_pattern, sizeof(h_pattern)) != cudaSuccess ||
         cudaMemcpyToSymbol(c_umax, ex->umax, sizeof(ex->umax)) != cudaSuccess) {
         set_last_error("cudaMemcpyToSymbol failed: %s", cudaGetErrorString(cudaGetLastError()));
@@ -2462,7 +2464,25 @@ int uvip_extract_batch_device(uvip_extractor* ex, const uint8_t* d_frames, int n
     int rc = ensure_plan(ex, w, h);
     if (rc) return rc;
     cudaStream_t st = stream ? (cudaStream_t)stream : ex->stream;
-    return enqueue_group(ex, d_frames, nframes, stride, frame_pitch, d_kps, d_n_out, cap, d_desc, 1, 0, 1, 1, 1, 0, st);
+    if (ex->subbatch <= 0 || ex->subbatch >= nframes)
+        return enqueue_group(ex, d_frames, nframes, stride, frame_pitch, d_kps, d_n_out, cap, d_desc, 1, 0, 1, 1, 1, 0, st);
+    // Sub-batches run through every stage before the next one starts and reuse the same scratch slots, so that a sub-batch's pyramid
+    // and blurred planes are still in the 126 MB L2 when FAST, the blur and the descriptor stage read them (uvip_extractor_set_subbatch)
+    for (int f0 = 0; f0 < nframes; f0 += ex->subbatch) {
+        const int nb = nframes - f0 < ex->subbatch ? nframes - f0 : ex->subbatch;
+        rc = enqueue_group(ex, d_frames + (size_t)f0 * frame_pitch, nb, stride, frame_pitch, d_kps + (size_t)f0 * cap, d_n_out + f0, cap,
+                           d_desc + (size_t)f0 * cap * 32, 1, 0, 1, 1, 1, 0, st, f0 == 0);
+        if (rc) return rc;
+    }
+    return UVIP_OK;
+}
+
+int uvip_extractor_set_subbatch(uvip_extractor* ex, int frames)
+{
+    UVIP_CHECK_ARG(ex && frames >= 0);
+    std::lock_guard<std::mutex> lk(ex->mu);
+    ex->subbatch = frames;
+    return UVIP_OK;
 }
 
 int uvip_extractor_status(uvip_extractor* ex)

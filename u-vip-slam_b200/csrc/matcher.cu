@@ -579,7 +579,7 @@ k_search_window(SearchCtx c, int nq, int nk, int32_t* __restrict__ taken, int32_
 static cudaError_t launch_search(cudaStream_t st, int nframes, const SearchCtx& c, int nq, int nk, int32_t* taken, int32_t* match, int* oa, int* ob,
                                  int* counts, const int32_t* d_nq, const int32_t* d_nk, int q_stride, int k_stride, int* flags)
 {
-    NvtxRange nv("uvip/search_window");
+    NvtxRange nv("uvip_search_window");
     const int cluster = nframes <= 32 ? 8 : 2, threads = nframes <= 32 ? 512 : 1024;
     cudaLaunchConfig_t cfg = {};
     cfg.gridDim = dim3((unsigned)(nframes * cluster)); cfg.blockDim = dim3((unsigned)threads); cfg.dynamicSmemBytes = 0; cfg.stream = st;
@@ -710,7 +710,7 @@ static int launch_knn2(uvip_matcher* m, const uint8_t* d_q, const int32_t* d_nq,
                        int nq_fixed, int nt_fixed, int idx_base, int32_t* d_idx2, int32_t* d_dist2, size_t res_pitch,
                        cudaStream_t st)
 {
-    NvtxRange nv("uvip/knn2");
+    NvtxRange nv("uvip_knn2");
     UVIP_CHECK_ARG(((uintptr_t)d_q & 15) == 0 && ((uintptr_t)d_t & 15) == 0 && (q_pitch & 15) == 0 && (t_pitch & 15) == 0);
     UVIP_CHECK_ARG(((uintptr_t)d_idx2 & 7) == 0 && ((uintptr_t)d_dist2 & 7) == 0);
     if (npairs <= 0 || max_nq <= 0) return UVIP_OK;
