@@ -37,8 +37,10 @@ def parse():
     ap.add_argument('--ref-frames', type=int, default=0, help='frames per step of the reference arm (0 = --batch, the same step as our arm)')
     ap.add_argument('--e2e-chunk', type=int, default=0, help='frames per pipeline chunk of the host-buffer entry point (0 = the batch)')
     ap.add_argument('--no-extras', action='store_true', help='skip the Hamming-only and cpu_baseline legs')
-    ap.add_argument('--workload', default='frames', choices=['frames', 'knn', 'search', 'next'],
-                    help="'frames' = the headline metric; 'knn' = BASELINE config 4: database-sharded brute-force kNN2 with NCCL top-2 merge; 'search' = BASELINE config 3: batched grid-windowed SearchByProjection")
+    ap.add_argument('--seq-frames', type=int, default=4096, help='frames per sequence of --workload cfg5')
+    ap.add_argument('--workload', default='frames', choices=['frames', 'knn', 'search', 'next', 'cfg5'],
+                    help="'frames' = the headline metric; 'knn' = BASELINE config 4: database-sharded brute-force kNN2 with NCCL top-2 merge; 'search' = BASELINE config 3: batched grid-windowed SearchByProjection; "
+                         "'cfg5' = BASELINE config 5 as written: one 4096-frame 1280x1024 sequence per GPU, streamed")
     ap.add_argument('--shape', default='euroc', choices=['euroc', 'aqualoc', 'hd'],
                     help='frame shape of --workload frames: euroc 752x480/1000 kp (the metric, config 1 shape), aqualoc 640x512/1500 kp (config 2), '
                          'hd 1280x1024/2000 kp (config 5)')
@@ -542,22 +544,29 @@ def run_ours(args):
                                               hp(hb[j]['d']), hp(hb[j]['i']), hp(hb[j]['dd']), C.byref(t)))
         return t.value
 
-    def e2e_run(nsteps):
+    def e2e_run(nsteps, mark_from=None, mark_to=None):
+        """steps 0 .. nsteps-1 through the pipeline (NB batches in flight); returns the host time between the COMPLETION of step
+        mark_from - 1 and the completion of step mark_to - 1: the pipeline is full at both ends, every timed step's upload and download
+        lie inside (overlapped with its neighbours'), and exactly mark_to - mark_from steps complete in between"""
         tickets = {}
+        ta = tb = None
         for i in range(min(NB, nsteps)):
             tickets[i] = submit(i)
         for i in range(nsteps):
             chk(L.uvip_extract_batch_wait(ex_e2es[i % NH].h, tickets.pop(i)))
+            if mark_from is not None and i == mark_from - 1:
+                ta = time.perf_counter()
+            if mark_to is not None and i == mark_to - 1:
+                tb = time.perf_counter()
             if i + NB < nsteps:
                 tickets[i + NB] = submit(i + NB)
+        return (tb - ta) if ta is not None and tb is not None else None
 
-    Ke = max(3, min(K, 40))
+    Ke = max(3, K)
     e2e_run(NB)
     barrier()
-    te = time.perf_counter()
-    e2e_run(Ke)
+    e2e_s = e2e_run(NB + Ke + NB, NB, NB + Ke)             # NB steps fill the pipeline, Ke are timed, NB keep it full behind them
     barrier()
-    e2e_s = time.perf_counter() - te
     if world > 1:
         tt = torch.tensor([e2e_s], dtype=torch.float64, device=dev)
         dist.all_reduce(tt, op=dist.ReduceOp.MAX)
@@ -566,7 +575,7 @@ def run_ours(args):
     h2d = B * W * H
     d2h = B * cap * 60 + B * 4 + 2 * (B - 1) * cap * 8
     # the chained results equal the two-call path's on the last step's buffers (cheap: the kNN of 3 pairs through the host entry point)
-    jl = (Ke - 1) % NB
+    jl = (NB + Ke + NB - 1) % NB
     chk_i = np.zeros((3, cap, 2), np.int32); chk_d = np.zeros((3, cap, 2), np.int32)
     chk(L.uvip_knn2_batch(m.h, hp(hb[jl]['d']), hp(hb[jl]['n']), cap * 32, C.c_void_p(hb[jl]['d'].data_ptr() + cap * 32),
                           C.c_void_p(hb[jl]['n'].data_ptr() + 4), cap * 32, 3, cap, C.c_void_p(chk_i.ctypes.data), C.c_void_p(chk_d.ctypes.data), cap))
@@ -651,7 +660,7 @@ def run_ours(args):
         'higher_is_better': True, 'scaling': 'weak', 'vs_baseline': None, 'dtype': 'u8', 'data': 'synthetic',
         'config': workload_config(args, B, world),
         'clocks': clk,
-        'e2e': {'value': e2e_fps, 'unit': 'frames/s', 'h2d_bytes_per_step': h2d, 'd2h_bytes_per_step': d2h, 'steps': Ke,
+        'e2e': {'value': e2e_fps, 'unit': 'frames/s', 'h2d_bytes_per_step': h2d, 'd2h_bytes_per_step': d2h, 'steps': Ke, 'timing': 'steady state: from the completion of the step in front of the %d timed steps to the completion of the last of them, pipeline full at both ends' % Ke,
                 'chunk_frames': args.e2e_chunk or B, 'single_frame_latency_ms': lat_ms,
                 'pipeline': 'uvip_extract_match_batch_submit / _wait, %d batches in flight over %d handle pair(s); consecutive-frame kNN2 chained on the device (no descriptor re-upload)' % (NB, NH),
                 'chained_knn_equals_two_call_path': bool(e2e_knn_ok),
@@ -670,6 +679,13 @@ def run_ours(args):
         rec = sharded_knn_measure(pkg, torch, dist, dev, rank, world, local, nk, 2, stream)
         if rank == 0:
             line['knn_sharded'] = rec
+        # BASELINE config 3 on the same ranks: grid-windowed search, frames sharded over the GPUs (no collective)
+        rec3 = search_measure(pkg, torch, dist, dev, rank, world, local, B, 10, 3)
+        if rank == 0:
+            line['search_sharded'] = {k: rec3[k] for k in ('metric', 'value', 'unit', 'n_gpus', 'ms_per_step', 'scaling', 'matches_oracle_frame0', 'cpu_baseline')
+                                      if k in rec3}
+            line['search_sharded']['workload'] = rec3['config']['workload']
+            line['search_sharded']['frames_per_step_per_gpu'] = B
     if rank == 0 and not args.no_extras:
         # Hamming-only leg: database-scale kNN2 (cfg4 shape at 64k x 64k) against the measured popc-pipe peak
         nq = nt = 65536
@@ -758,8 +774,6 @@ def run_search(args):
     """BASELINE config 3 as a throughput workload: SearchByProjection-style grid-windowed matching, 10 000 projected map points
     against a 2000-keypoint frame (radius search on the 64 x 48 frame grid, top-2 + ratio, claims), `--batch` frames per step in
     one launch pair (grid build + search), frames sharded over the GPUs with no collective.  value = map points per second."""
-    import ctypes as C
-    import numpy as np
     import torch
     import __graft_entry__ as ge
     pkg = ge.load_package()
@@ -770,8 +784,19 @@ def run_search(args):
     if world > 1:
         import torch.distributed as dist
         dist.init_process_group('nccl', device_id=dev)
+    line = search_measure(pkg, torch, dist, dev, rank, world, local, args.batch, args.steps, max(args.warmup, 3))
+    if rank == 0:
+        print(json.dumps(line), flush=True)
+    if world > 1:
+        dist.destroy_process_group()
+    return 0
+
+
+def search_measure(pkg, torch, dist, dev, rank, world, local, F, K, Wm):
+    """the measurement of run_search on an existing process group; returns the record on rank 0, None elsewhere"""
+    import ctypes as C
+    import numpy as np
     Wf, Hf, NQ, NK = 752, 480, 10000, 2000
-    F, K, Wm = args.batch, args.steps, max(args.warmup, 3)
     ndistinct = min(F, 16)
     cases = [pkg.synth.projection_case(seed_f=3 + 10 * i + 1000 * rank, seed_p=4 + 10 * i + 1000 * rank) for i in range(ndistinct)]
     m = pkg.ORBmatcher(0.8, True, device=local)
@@ -881,6 +906,147 @@ def run_search(args):
                                 start, items, 0.0, 0.0, float(inv_w), float(inv_h)); nfr += 1
             line['cpu_baseline'] = {'value': NQ * nfr / (time.perf_counter() - tc), 'unit': 'map points/s', 'cores': 1, 'kind': 'port',
                                     'sample': '%d frames through the C oracle' % nfr}
+    return line
+
+
+def run_cfg5(args):
+    """BASELINE config 5 as written: 8 concurrent synthetic sequences x 4096 frames of 1280x1024, sequence s ->
+    GPU s, frame f = synth_frame(100000 s + f, dx = 3f mod 29, dy = 2f mod 23), extractor(2000, 1.2, 8, FAST 20/7) + brute-force kNN2
+    between consecutive frames of the sequence.  The sequence is generated on the device (uvip_synth_frames_device, byte-identical to
+    the numpy generator) and parked in pinned host memory.  e2e: ONE uvip_extract_match_batch_submit over the whole sequence — the
+    library streams it in chunks of `--batch` frames through its copy / compute pipeline, matching frames across chunk boundaries on
+    the device.  value: the same chunks from an HBM-resident copy through the device-pointer entry points.  One chunk is checked
+    against the reference's own compiled extractor (oracle/_ref) and the oracle's kNN2 on rank 0."""
+    import ctypes as C
+    import numpy as np
+    import torch
+    import __graft_entry__ as ge
+    pkg = ge.load_package()
+    rank = int(os.environ.get('RANK', '0')); world = int(os.environ.get('WORLD_SIZE', '1')); local = int(os.environ.get('LOCAL_RANK', '0'))
+    torch.cuda.set_device(local)
+    dev = torch.device('cuda', local)
+    dist = None
+    if world > 1:
+        import torch.distributed as dist
+        dist.init_process_group('nccl', device_id=dev)
+    set_shape('hd')
+    L = pkg.capi.lib(); chk = pkg.capi.check
+    NF, CH = args.seq_frames, min(args.batch, 64) if args.batch == 256 else args.batch
+    cap = NFEAT + 8 * NLEVELS + 24
+    stream = torch.cuda.Stream(dev); torch.cuda.set_stream(stream)
+    sp = C.c_void_p(stream.cuda_stream)
+    P = lambda t: C.c_void_p(t.data_ptr())
+    # ---- the sequence: generated on the device chunk by chunk, kept in HBM (5.4 GB) and in pinned host memory
+    fidx = torch.arange(NF, dtype=torch.int64)
+    seeds = (100000 * rank + fidx).to(dev)
+    dxy = torch.stack([(3 * fidx) % 29, (2 * fidx) % 23], 1).to(torch.int32).to(dev).contiguous()
+    d_seq = torch.empty((NF, H, W), dtype=torch.uint8, device=dev)
+    tg = time.perf_counter()
+    for f0 in range(0, NF, 256):
+        nb = min(256, NF - f0)
+        chk(L.uvip_synth_frames_device(P(seeds[f0:]), P(dxy[f0:]), P(seeds[f0:]), nb, W, H, P(d_seq[f0:]), W * H, sp))
+    torch.cuda.synchronize(dev)
+    gen_s = time.perf_counter() - tg
+    h_seq = torch.empty((NF, H, W), dtype=torch.uint8).pin_memory()
+    h_seq.copy_(d_seq); torch.cuda.synchronize(dev)
+    h_k = torch.zeros((NF, cap, 28), dtype=torch.uint8).pin_memory(); h_d = torch.zeros((NF, cap, 32), dtype=torch.uint8).pin_memory()
+    h_n = torch.zeros(NF, dtype=torch.int32).pin_memory()
+    h_i = torch.zeros((NF - 1, cap, 2), dtype=torch.int32).pin_memory(); h_dd = torch.zeros((NF - 1, cap, 2), dtype=torch.int32).pin_memory()
+    ex = pkg.ORBextractor(NFEAT, SCALE, NLEVELS, pkg.ORBextractor.FAST_SCORE, FAST_TH, device=local, max_width=W, max_height=H, max_batch=CH)
+    m = pkg.ORBmatcher(0.75, True, device=local)
+
+    def barrier():
+        torch.cuda.synchronize(dev)
+        if world > 1:
+            dist.barrier()
+
+    # ---- end to end: the whole sequence through one submit / wait (host frames in, host keypoints / descriptors / matches out)
+    def e2e_pass(nframes):
+        t = C.c_int(-1)
+        chk(L.uvip_extract_match_batch_submit(ex.h, m.h, P(h_seq), nframes, W, H, W, W * H, P(h_k), P(h_n), cap, P(h_d), P(h_i), P(h_dd), C.byref(t)))
+        chk(L.uvip_extract_batch_wait(ex.h, t.value))
+    e2e_pass(min(NF, 4 * CH))                              # warm-up: plan, staging buffers, first-use allocations
+    barrier()
+    clocks = ClockSampler(local); clocks.start()
+    te = time.perf_counter()
+    e2e_pass(NF)
+    barrier()
+    e2e_s = time.perf_counter() - te
+    clk = clocks.stop()
+    n_host = h_n.numpy().copy()
+    # ---- HBM-resident: chunks through the device-pointer entry points, two output sets, the pair across a chunk boundary matched too
+    outs = [dict(k=torch.zeros((CH, cap, 28), dtype=torch.uint8, device=dev), d=torch.zeros((CH, cap, 32), dtype=torch.uint8, device=dev),
+                 n=torch.zeros(CH, dtype=torch.int32, device=dev), i=torch.zeros((CH, cap, 2), dtype=torch.int32, device=dev),
+                 dd=torch.zeros((CH, cap, 2), dtype=torch.int32, device=dev)) for _ in range(2)]
+    launches0 = ex.launch_count() + m.launch_count()
+
+    def dev_pass(nframes):
+        for c, f0 in enumerate(range(0, nframes, CH)):
+            nb = min(CH, nframes - f0); o = outs[c & 1]; pv = outs[(c & 1) ^ 1]
+            chk(L.uvip_extract_batch_device(ex.h, P(d_seq[f0:]), nb, W, H, W, W * H, P(o['k']), P(o['n']), cap, P(o['d']), sp))
+            if c:                                         # last frame of the previous chunk against the first frame of this one
+                chk(L.uvip_knn2_batch_device(m.h, C.c_void_p(pv['d'].data_ptr() + (CH - 1) * cap * 32), C.c_void_p(pv['n'].data_ptr() + 4 * (CH - 1)), cap * 32,
+                                             P(o['d']), P(o['n']), cap * 32, 1, cap, P(pv['i'][CH - 1:]), P(pv['dd'][CH - 1:]), cap, sp))
+            if nb > 1:
+                chk(L.uvip_knn2_batch_device(m.h, P(o['d']), P(o['n']), cap * 32, C.c_void_p(o['d'].data_ptr() + cap * 32), C.c_void_p(o['n'].data_ptr() + 4),
+                                             cap * 32, nb - 1, cap, P(o['i']), P(o['dd']), cap, sp))
+    dev_pass(min(NF, 4 * CH))
+    barrier()
+    e0 = torch.cuda.Event(enable_timing=True); e1 = torch.cuda.Event(enable_timing=True)
+    e0.record(stream)
+    dev_pass(NF)
+    e1.record(stream)
+    barrier()
+    ms = e0.elapsed_time(e1)
+    launches = ex.launch_count() + m.launch_count() - launches0
+    ex.status()
+    if world > 1:
+        tt = torch.tensor([ms, e2e_s], dtype=torch.float64, device=dev); dist.all_reduce(tt, op=dist.ReduceOp.MAX); ms, e2e_s = [float(v) for v in tt.tolist()]
+    if rank == 0:
+        # ---- parity spot check of one chunk of the streamed (end-to-end) results: the reference's compiled extractor + the oracle's kNN2
+        from oracle import oracle as O
+        from oracle import reference as R
+        c0 = min(10 * CH, max(0, NF - CH)) if NF > CH else 0
+        nchk = min(8, NF - c0)
+        fr = h_seq[c0:c0 + nchk].numpy()
+        if os.path.exists(R.SO):
+            rk, rn, rd = R.extract_batch(fr, NFEAT, SCALE, NLEVELS, FAST_TH, threads=os.cpu_count() or 1, cap=cap)
+            kind = 'reference (oracle/_ref)'
+        else:
+            rk, rn, rd = O.extract_batch(fr, NFEAT, SCALE, NLEVELS, FAST_TH, cap=cap)
+            kind = 'oracle port'
+        ok_ext = bool(np.array_equal(rn, n_host[c0:c0 + nchk]))
+        kview = h_k.numpy().view(pkg.capi.KP_DTYPE).reshape(NF, cap)
+        for f in range(nchk):
+            nn = int(rn[f])
+            ok_ext = ok_ext and bool(np.array_equal(kview[c0 + f, :nn]['x'], rk[f, :nn]['x']) and np.array_equal(kview[c0 + f, :nn]['y'], rk[f, :nn]['y'])
+                                     and np.array_equal(kview[c0 + f, :nn]['angle'], rk[f, :nn]['angle']) and np.array_equal(h_d[c0 + f, :nn].numpy(), rd[f, :nn]))
+        ok_knn = True
+        pairs = list(range(c0 - 1 if c0 > 0 else c0, c0 + nchk - 1))      # includes the pair that crosses the chunk boundary in front of c0
+        for f in pairs:
+            na = int(n_host[f]); nb_ = int(n_host[f + 1])
+            oi, od = O.knn2(h_d[f, :na].numpy(), h_d[f + 1, :nb_].numpy(), threads=os.cpu_count() or 1)
+            ok_knn = ok_knn and bool(np.array_equal(h_i[f, :na].numpy(), oi) and np.array_equal(h_dd[f, :na].numpy(), od))
+        peak, peak_kind = hbm_peak()
+        fps = world * NF / (ms * 1e-3)
+        line = {'metric': METRIC, 'value': fps, 'unit': 'frames/s', 'n_gpus': world, 'steps': 1, 'warmup': 1, 'ms_per_step': ms, 'higher_is_better': True,
+                'scaling': 'weak', 'vs_baseline': None, 'dtype': 'u8', 'data': 'synthetic',
+                'config': {'workload': 'BASELINE config 5 as written: %d concurrent synthetic sequences x %d frames of %dx%d (seed 100000 s + f, dx = 3f mod 29, '
+                                       'dy = 2f mod 23), sequence -> GPU, ORBextractor %d kp / 8 levels / 1.2 / FAST 20-7 + brute-force kNN2 of consecutive frames, '
+                                       'streamed in chunks of %d frames with matching across chunk boundaries' % (world, NF, W, H, NFEAT, CH),
+                           'frames_per_sequence': NF, 'chunk_frames': CH, 'keypoints': NFEAT, 'input_gb_per_gpu': NF * W * H / 1e9,
+                           'l2': 'every chunk streams a %.0f MB pyramid working set (> 126 MB L2)' % (2.0 * CH * B_FRAME_BYTES / 1e6),
+                           'parallelism': 'one sequence per GPU, no collective'},
+                'clocks': clk, 'gpu_launches': int(launches),
+                'e2e': {'value': world * NF / e2e_s, 'unit': 'frames/s', 'h2d_bytes_per_step': NF * W * H, 'd2h_bytes_per_step': NF * cap * 60 + NF * 4 + 2 * (NF - 1) * cap * 8,
+                        'seconds_per_sequence': e2e_s, 'what': 'one uvip_extract_match_batch_submit + wait over the whole sequence from pinned host memory'},
+                'roofline': {'bound': 'hbm', 'achieved': B_FRAME_BYTES * NF / (ms * 1e-3) / 1e9, 'peak': peak, 'unit': 'GB/s',
+                             'frac': B_FRAME_BYTES * NF / (ms * 1e-3) / 1e9 / peak, 'traffic': None, 'what': 'whole sequence pass (all stages + kNN2), algorithmic bytes of SURVEY 8(d)',
+                             'algorithmic_bytes_per_frame': B_FRAME_BYTES},
+                'keypoints_per_frame': {'min': int(n_host.min()), 'mean': float(n_host.mean())},
+                'generator': {'seconds_for_sequence_on_device': gen_s},
+                'parity_spot_check': {'frames': [c0, c0 + nchk - 1], 'pairs': [pairs[0], pairs[-1]] if pairs else None, 'against': kind,
+                                      'extraction_identical': ok_ext, 'knn2_identical_incl_chunk_boundary_pair': ok_knn}}
         print(json.dumps(line), flush=True)
     if world > 1:
         dist.destroy_process_group()
@@ -975,4 +1141,5 @@ if __name__ == '__main__':
     assert a.shape != 'euroc' or B_FRAME_BYTES == 1177367
     if a.impl == 'reference':
         sys.exit(run_reference(a))
-    sys.exit(run_knn(a) if a.workload == 'knn' else run_next(a) if a.workload == 'next' else run_search(a) if a.workload == 'search' else run_ours(a))
+    sys.exit(run_knn(a) if a.workload == 'knn' else run_next(a) if a.workload == 'next' else run_search(a) if a.workload == 'search'
+             else run_cfg5(a) if a.workload == 'cfg5' else run_ours(a))

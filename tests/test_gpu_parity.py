@@ -667,3 +667,22 @@ def test_new_entry_points_edge_cases(gpu, oracle, synth):
     assert np.isfinite(ex.harris_responses(3, [20.0], [20.0])).all()
     # batched search with zero frames
     m.search_window_batch_device(0, 100, (0, 752, 0, 480), 0, (0, 0, 0, 0, 0, 0), 0, 1, (0, 0, 0, 0), 0, 1, 0, 0, 0)
+
+
+def test_device_frame_generator_equals_numpy(gpu, synth):
+    """uvip_synth_frames_device (SURVEY Appendix B synth_frame on the device, used to produce BASELINE config 5 on the GPU box) gives
+    the bytes of the numpy generator, shifts and separate noise seeds included"""
+    import ctypes as C
+    import torch
+    L = gpu.capi.lib()
+    for (W, H), cases in (((752, 480), [(1, 0, 0, 1), (1, 5, 3, 2), (77, -4, 9, 77)]), ((1280, 1024), [(300007, 21, 14, 300007)]), ((321, 243), [(9, 28, 22, 5)])):
+        seeds = torch.tensor([c[0] for c in cases], dtype=torch.int64, device='cuda')
+        dxy = torch.tensor([[c[1], c[2]] for c in cases], dtype=torch.int32, device='cuda')
+        nse = torch.tensor([c[3] for c in cases], dtype=torch.int64, device='cuda')
+        out = torch.zeros((len(cases), H, W), dtype=torch.uint8, device='cuda')
+        gpu.capi.check(L.uvip_synth_frames_device(C.c_void_p(seeds.data_ptr()), C.c_void_p(dxy.data_ptr()), C.c_void_p(nse.data_ptr()), len(cases), W, H,
+                                                  C.c_void_p(out.data_ptr()), W * H, None))
+        torch.cuda.synchronize()
+        got = out.cpu().numpy()
+        for k, (seed, dx, dy, ns) in enumerate(cases):
+            assert np.array_equal(got[k], synth.synth_frame(seed, W, H, dx=dx, dy=dy, noise_seed=ns)), (W, H, seed, dx, dy, ns)
