@@ -326,6 +326,15 @@ int   uvip_klt_build_pyramid(uvip_klt* k, int slot, const uint8_t* image, int w,
 int   uvip_klt_get_level(uvip_klt* k, int slot, int level, uint8_t* img, int16_t* der_xy, int* w, int* h);   /* debug tap */
 int   uvip_klt_track(uvip_klt* k, int slot_prev, int slot_next, const float* prev_pts, float* next_pts_inout, int n, int max_level,
                      int max_iter, double epsilon, int flags, double min_eig_threshold, uint8_t* status, float* err);
+/* cv::findFundamentalMat(pts0, pts1, FM_RANSAC, threshold, ...) of src/Tracking.cc:1062, of which the reference keeps the inlier mask:
+ * 7-point hypotheses scored by OpenCV's residual (max of the two squared point-to-epipolar-line distances, double, cast to float,
+ * compared with (float)(threshold^2)); the mask of the best hypothesis is returned together with its count and, optionally, its F
+ * (row-major, Frobenius norm 1; pts1^T F pts0 = 0).  pts: n x 2 float, n >= 15 (below that OpenCV runs LMedS instead:
+ * UVIP_ERR_UNSUPPORTED).  cv::RNG's sample sequence is not reproducible, so the samples come from a counter-based generator and nhyp
+ * hypotheses are always evaluated (OpenCV: at most 1000 with early stop; 2048 is a good default): the inlier SET is what is pinned
+ * against cv2 (tests/golden/cv2_ransac.npz), the result itself is deterministic and identical to the CPU oracle's. */
+int   uvip_klt_ransac_fundamental(uvip_klt* k, const float* pts0, const float* pts1, int n, double threshold, int nhyp, uint8_t* mask,
+                                  double* F, int* ninliers);
 long long uvip_klt_launch_count(const uvip_klt* k);
 
 /* ---- misc ---------------------------------------------------------------------------------------------- */

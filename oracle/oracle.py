@@ -386,6 +386,17 @@ def lk_track(pyr0, pyr1, prev_pts, next_pts, win=21, max_level=5, max_iter=30, e
     return nxt, status, err
 
 
+def ransac_fundamental(pts0, pts1, threshold=1.0, nhyp=1024, seed=0x5EED):
+    """cv::findFundamentalMat(pts0, pts1, FM_RANSAC, threshold, ...) inlier mask (src/Tracking.cc:1062): (count, mask, F)"""
+    p0 = np.ascontiguousarray(pts0, np.float32).reshape(-1, 2); p1 = np.ascontiguousarray(pts1, np.float32).reshape(-1, 2)
+    n = len(p0)
+    mask = np.zeros(n, np.uint8); F = np.zeros(9, np.float64)
+    L = lib()
+    L.uo_ransac_fundamental.argtypes = [C.c_void_p, C.c_void_p, C.c_int, C.c_double, C.c_int, C.c_ulonglong, C.c_void_p, C.c_void_p]
+    cnt = L.uo_ransac_fundamental(_p(p0), _p(p1), n, float(threshold), int(nhyp), int(seed), _p(mask), _p(F))
+    return cnt, mask, F.reshape(3, 3)
+
+
 def pyr_down(img):
     img = np.ascontiguousarray(img, np.uint8)
     h, w = img.shape

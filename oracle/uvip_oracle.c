@@ -1255,3 +1255,162 @@ void uo_distinctive_descriptors(const uint8_t* desc, const int32_t* start, int n
         best_idx[p] = BestIdx; if (best_median) best_median[p] = BestMedian;
     }
 }
+
+/* ------------------------------------------------------------------------------------------------------------------------------
+ * N1, last third: cv::findFundamentalMat(pts0, pts1, FM_RANSAC, 1, 0.999, mask) as called at src/Tracking.cc:1062 (only the
+ * inlier MASK is used there).  OpenCV (calib3d/fundam.cpp, ptsetreg.cpp): 7-point minimal solver inside a RANSAC loop, at most
+ * 1000 iterations with early stop by confidence, samples from cv::RNG; residual = max of the two squared point-to-epipolar-line
+ * distances, computed in double, cast to float and compared with (float)(threshold^2); the mask of the BEST hypothesis is returned.
+ * cv::RNG's sample sequence and OpenCV's SVD cannot be reproduced bit for bit, so the restatement pins the ALGORITHM with its own
+ * deterministic sampler (counter-based SplitMix64) and evaluates a fixed number of hypotheses (no early stop: a superset of what
+ * OpenCV would have tried); tests compare the inlier SET with cv2's on synthetic two-view data (tests/golden/cv2_ransac.npz).
+ * The cubic is solved by bisection (only + - * / and sqrt), so the CUDA kernel reproduces this function bit for bit.
+ * ------------------------------------------------------------------------------------------------------------------------------ */
+static unsigned long long uo_sm64(unsigned long long seed, unsigned long long k)
+{
+    unsigned long long z = seed + k * 0x9E3779B97F4A7C15ULL;
+    z = (z ^ (z >> 30)) * 0xBF58476D1CE4E5B9ULL;
+    z = (z ^ (z >> 27)) * 0x94D049BB133111EBULL;
+    return z ^ (z >> 31);
+}
+static double uo_det3(const double* F)
+{
+    return F[0] * (F[4] * F[8] - F[5] * F[7]) - F[1] * (F[3] * F[8] - F[5] * F[6]) + F[2] * (F[3] * F[7] - F[4] * F[6]);
+}
+static double uo_cubic_eval(const double* c, double x) { return ((c[3] * x + c[2]) * x + c[1]) * x + c[0]; }
+/* real root of c(x) inside [lo, hi] where c(lo) and c(hi) differ in sign: 200 bisection steps (deterministic on any IEEE machine) */
+static double uo_bisect(const double* c, double lo, double hi)
+{
+    double flo = uo_cubic_eval(c, lo);
+    for (int it = 0; it < 200; it++) {
+        const double mid = 0.5 * (lo + hi);
+        if (mid == lo || mid == hi) break;
+        const double fm = uo_cubic_eval(c, mid);
+        if ((fm < 0) == (flo < 0)) { lo = mid; flo = fm; } else hi = mid;
+    }
+    return 0.5 * (lo + hi);
+}
+/* real roots of c[3] x^3 + c[2] x^2 + c[1] x + c[0] (ascending); returns their number (0..3) */
+static int uo_cubic_roots(const double* c, double* r)
+{
+    double m = fabs(c[0]); if (fabs(c[1]) > m) m = fabs(c[1]); if (fabs(c[2]) > m) m = fabs(c[2]);
+    if (fabs(c[3]) <= 1e-12 * m || c[3] == 0) {                       /* (near) quadratic */
+        if (fabs(c[2]) <= 1e-12 * m || c[2] == 0) { if (c[1] == 0) return 0; r[0] = -c[0] / c[1]; return 1; }
+        const double disc = c[1] * c[1] - 4 * c[2] * c[0];
+        if (disc < 0) return 0;
+        const double s = sqrt(disc);
+        double a = (-c[1] - s) / (2 * c[2]), b = (-c[1] + s) / (2 * c[2]);
+        if (a > b) { const double t = a; a = b; b = t; }
+        r[0] = a; r[1] = b; return 2;
+    }
+    const double B = 1.0 + m / fabs(c[3]);                           /* Cauchy bound on |root| */
+    /* stationary points of the cubic: 3 c3 x^2 + 2 c2 x + c1 = 0 */
+    const double disc = c[2] * c[2] - 3 * c[3] * c[1];
+    int n = 0;
+    if (disc <= 0) {                                                 /* monotone: one real root */
+        r[n++] = uo_bisect(c, -B, B);
+        return n;
+    }
+    const double s = sqrt(disc);
+    double x1 = (-c[2] - s) / (3 * c[3]), x2 = (-c[2] + s) / (3 * c[3]);
+    if (x1 > x2) { const double t = x1; x1 = x2; x2 = t; }
+    const double fB0 = uo_cubic_eval(c, -B), f1 = uo_cubic_eval(c, x1), f2 = uo_cubic_eval(c, x2), fB1 = uo_cubic_eval(c, B);
+    if ((fB0 < 0) != (f1 < 0)) r[n++] = uo_bisect(c, -B, x1);
+    if ((f1 < 0) != (f2 < 0)) r[n++] = uo_bisect(c, x1, x2);
+    if ((f2 < 0) != (fB1 < 0)) r[n++] = uo_bisect(c, x2, B);
+    return n;
+}
+/* 7-point solver: up to three 3x3 matrices F (row-major, m1^T F m0 = 0 for the seven pairs); returns their number */
+static int uo_seven_point(const double* x0, const double* y0, const double* x1, const double* y1, double* Fs)
+{
+    double A[7][9];
+    for (int i = 0; i < 7; i++) {
+        A[i][0] = x1[i] * x0[i]; A[i][1] = x1[i] * y0[i]; A[i][2] = x1[i];
+        A[i][3] = y1[i] * x0[i]; A[i][4] = y1[i] * y0[i]; A[i][5] = y1[i];
+        A[i][6] = x0[i]; A[i][7] = y0[i]; A[i][8] = 1.0;
+    }
+    /* Gauss-Jordan with full pivoting: 7 pivot columns, 2 free ones */
+    int pivcol[7]; int used[9] = {0, 0, 0, 0, 0, 0, 0, 0, 0};
+    for (int k = 0; k < 7; k++) {
+        int br = k, bc = -1; double best = 0;
+        for (int i = k; i < 7; i++)
+            for (int j = 0; j < 9; j++)
+                if (!used[j] && fabs(A[i][j]) > best) { best = fabs(A[i][j]); br = i; bc = j; }
+        if (bc < 0 || best < 1e-300) return 0;                           /* degenerate sample */
+        if (br != k) for (int j = 0; j < 9; j++) { const double t = A[k][j]; A[k][j] = A[br][j]; A[br][j] = t; }
+        used[bc] = 1; pivcol[k] = bc;
+        const double inv = 1.0 / A[k][bc];
+        for (int j = 0; j < 9; j++) A[k][j] *= inv;
+        for (int i = 0; i < 7; i++)
+            if (i != k) {
+                const double f = A[i][bc];
+                if (f != 0) for (int j = 0; j < 9; j++) A[i][j] -= f * A[k][j];
+            }
+    }
+    int fre[2], nf = 0;
+    for (int j = 0; j < 9; j++) if (!used[j]) fre[nf++] = j;
+    double F1[9], F2[9];
+    for (int j = 0; j < 9; j++) { F1[j] = 0; F2[j] = 0; }
+    F1[fre[0]] = 1.0; F2[fre[1]] = 1.0;
+    for (int k = 0; k < 7; k++) { F1[pivcol[k]] = -A[k][fre[0]]; F2[pivcol[k]] = -A[k][fre[1]]; }
+    /* det(l F1 + (1 - l) F2) is a cubic in l: interpolate it through l = 0, 1, -1, 2 */
+    double G[9], c[4];
+    const double d0 = uo_det3(F2), d1 = uo_det3(F1);
+    for (int j = 0; j < 9; j++) G[j] = 2.0 * F2[j] - F1[j];
+    const double dm = uo_det3(G);
+    for (int j = 0; j < 9; j++) G[j] = 2.0 * F1[j] - F2[j];
+    const double d2 = uo_det3(G);
+    c[0] = d0;
+    c[3] = (d2 - 3.0 * d1 + 3.0 * d0 - dm) / 6.0;
+    c[2] = 0.5 * (d1 + dm) - d0;
+    c[1] = d1 - d0 - c[2] - c[3];
+    double r[3];
+    const int nr = uo_cubic_roots(c, r);
+    for (int k = 0; k < nr; k++) {
+        double nrm = 0;
+        for (int j = 0; j < 9; j++) { Fs[9 * k + j] = r[k] * F1[j] + (1.0 - r[k]) * F2[j]; nrm += Fs[9 * k + j] * Fs[9 * k + j]; }
+        nrm = sqrt(nrm);
+        if (nrm > 0) for (int j = 0; j < 9; j++) Fs[9 * k + j] /= nrm;
+    }
+    return nr;
+}
+static int uo_fm_inlier(const double* F, double x0, double y0, double x1, double y1, float t2)
+{
+    double a = F[0] * x0 + F[1] * y0 + F[2], b = F[3] * x0 + F[4] * y0 + F[5], c = F[6] * x0 + F[7] * y0 + F[8];
+    const double s2 = 1.0 / (a * a + b * b), d2 = x1 * a + y1 * b + c;
+    a = F[0] * x1 + F[3] * y1 + F[6]; b = F[1] * x1 + F[4] * y1 + F[7]; c = F[2] * x1 + F[5] * y1 + F[8];
+    const double s1 = 1.0 / (a * a + b * b), d1 = x0 * a + y0 * b + c;
+    const double e1 = d1 * d1 * s1, e2 = d2 * d2 * s2;
+    const float err = (float)(e1 > e2 ? e1 : e2);
+    return err <= t2;
+}
+/* pts: n x 2 float each; mask[n] out; F[9] out (best hypothesis, Frobenius-normalised; may be NULL).  Returns the inlier count,
+ * 0 when no hypothesis had more than 6 inliers, -1 when n < 15 (OpenCV switches to LMedS below 15 points: not restated). */
+int uo_ransac_fundamental(const float* pts0, const float* pts1, int n, double threshold, int nhyp, unsigned long long seed, uint8_t* mask, double* Fout)
+{
+    if (n < 15) return -1;
+    const float t2 = (float)(threshold * threshold);
+    int best = 6; double bestF[9]; int have = 0;
+    for (int h = 0; h < nhyp; h++) {
+        int idx[7], ns = 0;
+        for (int k = 1; k <= 16 && ns < 7; k++) {
+            const int cand = (int)(uo_sm64(seed, (unsigned long long)h * 16ULL + (unsigned long long)k) % (unsigned long long)n);
+            int dup = 0;
+            for (int j = 0; j < ns; j++) dup |= idx[j] == cand;
+            if (!dup) idx[ns++] = cand;
+        }
+        if (ns < 7) continue;
+        double x0[7], y0[7], x1[7], y1[7], Fs[27];
+        for (int j = 0; j < 7; j++) { x0[j] = pts0[2 * idx[j]]; y0[j] = pts0[2 * idx[j] + 1]; x1[j] = pts1[2 * idx[j]]; y1[j] = pts1[2 * idx[j] + 1]; }
+        const int nm = uo_seven_point(x0, y0, x1, y1, Fs);
+        for (int k = 0; k < nm; k++) {
+            int cnt = 0;
+            for (int i = 0; i < n; i++) cnt += uo_fm_inlier(Fs + 9 * k, pts0[2 * i], pts0[2 * i + 1], pts1[2 * i], pts1[2 * i + 1], t2);
+            if (cnt > best) { best = cnt; memcpy(bestF, Fs + 9 * k, sizeof(bestF)); have = 1; }     /* strict: the first best hypothesis wins */
+        }
+    }
+    if (!have) { for (int i = 0; i < n; i++) mask[i] = 0; return 0; }
+    for (int i = 0; i < n; i++) mask[i] = (uint8_t)uo_fm_inlier(bestF, pts0[2 * i], pts0[2 * i + 1], pts1[2 * i], pts1[2 * i + 1], t2);
+    if (Fout) memcpy(Fout, bestF, sizeof(bestF));
+    return best;
+}

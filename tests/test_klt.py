@@ -100,3 +100,63 @@ def test_gpu_klt_refuses_slots_of_another_geometry(pkg, synth):
     p1, st, err = klt.track(0, 2, pts, pts, flags=8)         # same image in both slots: zero flow
     assert st.sum() > 0 and np.abs(p1 - pts)[st == 1].max() < 1e-3
     klt.close()
+
+
+# ---- N1, last third: cv::findFundamentalMat(FM_RANSAC) inlier mask (src/Tracking.cc:1062) ------------------------------------------
+RANSAC_CASES = (101, 102, 103, 104)
+
+
+def _ransac_golden():
+    return np.load(os.path.join(os.path.dirname(os.path.abspath(__file__)), 'golden', 'cv2_ransac.npz'))
+
+
+def _inliers_of(F, p0, p1, thr=1.0):
+    """OpenCV's FMEstimatorCallback::computeError + the (float) threshold test, in numpy"""
+    p0 = p0.astype(np.float64); p1 = p1.astype(np.float64)
+    x0, y0, x1, y1 = p0[:, 0], p0[:, 1], p1[:, 0], p1[:, 1]
+    a = F[0, 0] * x0 + F[0, 1] * y0 + F[0, 2]; b = F[1, 0] * x0 + F[1, 1] * y0 + F[1, 2]; c = F[2, 0] * x0 + F[2, 1] * y0 + F[2, 2]
+    s2 = 1.0 / (a * a + b * b); d2 = x1 * a + y1 * b + c
+    a = F[0, 0] * x1 + F[1, 0] * y1 + F[2, 0]; b = F[0, 1] * x1 + F[1, 1] * y1 + F[2, 1]; c = F[0, 2] * x1 + F[1, 2] * y1 + F[2, 2]
+    s1 = 1.0 / (a * a + b * b); d1 = x0 * a + y0 * b + c
+    return (np.maximum(d1 * d1 * s1, d2 * d2 * s2).astype(np.float32) <= np.float32(thr * thr)).astype(np.uint8)
+
+
+def test_oracle_ransac_against_cv2(oracle):
+    """cv::RNG cannot be reproduced, so the pin is (i) the residual + threshold test: with cv2's own F it reproduces cv2's mask exactly;
+    (ii) the consensus: the restatement (2048 hypotheses, no early stop) finds at least cv2's inlier count, its inliers are true
+    inliers of the synthetic geometry, and the two masks agree on >= 95 % of the points"""
+    g = _ransac_golden()
+    for seed in RANSAC_CASES:
+        p0, p1, cm, out = g['p0_%d' % seed], g['p1_%d' % seed], g['mask_%d' % seed], g['outlier_%d' % seed]
+        assert np.array_equal(_inliers_of(g['F_%d' % seed], p0, p1), cm), seed            # (i)
+        cnt, mask, F = oracle.ransac_fundamental(p0, p1, 1.0, nhyp=2048)
+        assert cnt == mask.sum() and np.array_equal(_inliers_of(F, p0, p1), mask)
+        assert cnt >= cm.sum(), (seed, cnt, int(cm.sum()))                                # (ii)
+        assert (mask == cm).mean() >= 0.95, (seed, (mask == cm).mean())
+        assert mask[out == 1].sum() <= 0.02 * len(mask) + 2                               # gross outliers are rejected
+        assert abs(np.linalg.det(F)) < 1e-9                                               # rank 2 (the cubic's root)
+    cnt, mask, F = oracle.ransac_fundamental(g['p0_101'][:14], g['p1_101'][:14])
+    assert cnt == -1                                                                      # below 15 points OpenCV runs LMedS
+
+
+@pytest.mark.gpu
+def test_gpu_ransac_equals_oracle(pkg, oracle):
+    """one warp per hypothesis on the GPU == the sequential oracle, bit for bit (count, mask and F): the solver uses only + - * / sqrt"""
+    g = _ransac_golden()
+    klt = pkg.KLTTracker(752, 480, 21, 5)
+    for seed in RANSAC_CASES:
+        p0, p1 = g['p0_%d' % seed], g['p1_%d' % seed]
+        for nh in (64, 2048):
+            cnt, mask, F = klt.ransac_fundamental(p0, p1, 1.0, nhyp=nh)
+            ocnt, omask, oF = oracle.ransac_fundamental(p0, p1, 1.0, nhyp=nh)
+            assert cnt == ocnt and np.array_equal(mask, omask) and np.array_equal(F, oF), (seed, nh, cnt, ocnt)
+        assert cnt >= g['mask_%d' % seed].sum()
+    with pytest.raises(pkg.capi.UvipError) as e:
+        klt.ransac_fundamental(g['p0_101'][:14], g['p1_101'][:14])
+    assert e.value.code == pkg.capi.ERR_UNSUPPORTED
+    # all points on one degenerate configuration (identical points): no hypothesis, empty mask, no fault
+    z = np.zeros((20, 2), np.float32)
+    cnt, mask, F = klt.ransac_fundamental(z, z)
+    ocnt, omask, oF = oracle.ransac_fundamental(z, z, 1.0, nhyp=2048)
+    assert cnt == ocnt and np.array_equal(mask, omask)
+    klt.close()

@@ -208,6 +208,179 @@ static void klt_make_plan(uvip_klt* k, int w, int h)
     k->img_bytes = ioff; k->der_elems = doff; k->w = w; k->h = h;
 }
 
+// --------------------------------------------------------------------------------------------------------
+// N1, last third: cv::findFundamentalMat(pts0, pts1, FM_RANSAC, 1, 0.999, mask) of src/Tracking.cc:1062 (only the inlier mask is used
+// there).  OpenCV's algorithm (calib3d/fundam.cpp, ptsetreg.cpp): 7-point minimal solver in a RANSAC loop, residual = max of the two
+// squared point-to-epipolar-line distances in double, cast to float, compared with (float)(threshold^2); the mask of the best
+// hypothesis is returned.  cv::RNG's samples cannot be reproduced, so the sampler is a counter-based SplitMix64 and a FIXED number of
+// hypotheses is evaluated (no early stop: more than OpenCV tries) — one warp per hypothesis: lane 0 solves the 7-point problem
+// (Gauss-Jordan null space, cubic by bisection: only + - * / sqrt, so the CPU oracle is reproduced bit for bit), all lanes count
+// inliers.  The winner is the (count, lowest hypothesis, lowest root) maximum; a second kernel writes its mask.
+// --------------------------------------------------------------------------------------------------------
+__device__ __forceinline__ unsigned long long rs_sm64(unsigned long long seed, unsigned long long k)
+{
+    unsigned long long z = seed + k * 0x9E3779B97F4A7C15ULL;
+    z = (z ^ (z >> 30)) * 0xBF58476D1CE4E5B9ULL;
+    z = (z ^ (z >> 27)) * 0x94D049BB133111EBULL;
+    return z ^ (z >> 31);
+}
+__device__ __forceinline__ double rs_det3(const double* F)
+{
+    return F[0] * (F[4] * F[8] - F[5] * F[7]) - F[1] * (F[3] * F[8] - F[5] * F[6]) + F[2] * (F[3] * F[7] - F[4] * F[6]);
+}
+__device__ __forceinline__ double rs_ceval(const double* c, double x) { return ((c[3] * x + c[2]) * x + c[1]) * x + c[0]; }
+__device__ double rs_bisect(const double* c, double lo, double hi)
+{
+    double flo = rs_ceval(c, lo);
+    for (int it = 0; it < 200; it++) {
+        const double mid = 0.5 * (lo + hi);
+        if (mid == lo || mid == hi) break;
+        const double fm = rs_ceval(c, mid);
+        if ((fm < 0) == (flo < 0)) { lo = mid; flo = fm; } else hi = mid;
+    }
+    return 0.5 * (lo + hi);
+}
+__device__ int rs_cubic_roots(const double* c, double* r)
+{
+    double m = fabs(c[0]); if (fabs(c[1]) > m) m = fabs(c[1]); if (fabs(c[2]) > m) m = fabs(c[2]);
+    if (fabs(c[3]) <= 1e-12 * m || c[3] == 0) {
+        if (fabs(c[2]) <= 1e-12 * m || c[2] == 0) { if (c[1] == 0) return 0; r[0] = -c[0] / c[1]; return 1; }
+        const double disc = c[1] * c[1] - 4 * c[2] * c[0];
+        if (disc < 0) return 0;
+        const double s = sqrt(disc);
+        double a = (-c[1] - s) / (2 * c[2]), b = (-c[1] + s) / (2 * c[2]);
+        if (a > b) { const double t = a; a = b; b = t; }
+        r[0] = a; r[1] = b; return 2;
+    }
+    const double B = 1.0 + m / fabs(c[3]);
+    const double disc = c[2] * c[2] - 3 * c[3] * c[1];
+    int n = 0;
+    if (disc <= 0) { r[n++] = rs_bisect(c, -B, B); return n; }
+    const double s = sqrt(disc);
+    double x1 = (-c[2] - s) / (3 * c[3]), x2 = (-c[2] + s) / (3 * c[3]);
+    if (x1 > x2) { const double t = x1; x1 = x2; x2 = t; }
+    const double fB0 = rs_ceval(c, -B), f1 = rs_ceval(c, x1), f2 = rs_ceval(c, x2), fB1 = rs_ceval(c, B);
+    if ((fB0 < 0) != (f1 < 0)) r[n++] = rs_bisect(c, -B, x1);
+    if ((f1 < 0) != (f2 < 0)) r[n++] = rs_bisect(c, x1, x2);
+    if ((f2 < 0) != (fB1 < 0)) r[n++] = rs_bisect(c, x2, B);
+    return n;
+}
+__device__ int rs_seven_point(const double* x0, const double* y0, const double* x1, const double* y1, double* Fs)
+{
+    double A[7][9];
+    for (int i = 0; i < 7; i++) {
+        A[i][0] = x1[i] * x0[i]; A[i][1] = x1[i] * y0[i]; A[i][2] = x1[i];
+        A[i][3] = y1[i] * x0[i]; A[i][4] = y1[i] * y0[i]; A[i][5] = y1[i];
+        A[i][6] = x0[i]; A[i][7] = y0[i]; A[i][8] = 1.0;
+    }
+    int pivcol[7]; int used[9] = {0, 0, 0, 0, 0, 0, 0, 0, 0};
+    for (int k = 0; k < 7; k++) {
+        int br = k, bc = -1; double best = 0;
+        for (int i = k; i < 7; i++)
+            for (int j = 0; j < 9; j++)
+                if (!used[j] && fabs(A[i][j]) > best) { best = fabs(A[i][j]); br = i; bc = j; }
+        if (bc < 0 || best < 1e-300) return 0;
+        if (br != k) for (int j = 0; j < 9; j++) { const double t = A[k][j]; A[k][j] = A[br][j]; A[br][j] = t; }
+        used[bc] = 1; pivcol[k] = bc;
+        const double inv = 1.0 / A[k][bc];
+        for (int j = 0; j < 9; j++) A[k][j] *= inv;
+        for (int i = 0; i < 7; i++)
+            if (i != k) {
+                const double f = A[i][bc];
+                if (f != 0) for (int j = 0; j < 9; j++) A[i][j] -= f * A[k][j];
+            }
+    }
+    int fre[2], nf = 0;
+    for (int j = 0; j < 9; j++) if (!used[j]) fre[nf++] = j;
+    double F1[9], F2[9];
+    for (int j = 0; j < 9; j++) { F1[j] = 0; F2[j] = 0; }
+    F1[fre[0]] = 1.0; F2[fre[1]] = 1.0;
+    for (int k = 0; k < 7; k++) { F1[pivcol[k]] = -A[k][fre[0]]; F2[pivcol[k]] = -A[k][fre[1]]; }
+    double G[9], c[4];
+    const double d0 = rs_det3(F2), d1 = rs_det3(F1);
+    for (int j = 0; j < 9; j++) G[j] = 2.0 * F2[j] - F1[j];
+    const double dm = rs_det3(G);
+    for (int j = 0; j < 9; j++) G[j] = 2.0 * F1[j] - F2[j];
+    const double d2 = rs_det3(G);
+    c[0] = d0;
+    c[3] = (d2 - 3.0 * d1 + 3.0 * d0 - dm) / 6.0;
+    c[2] = 0.5 * (d1 + dm) - d0;
+    c[1] = d1 - d0 - c[2] - c[3];
+    double r[3];
+    const int nr = rs_cubic_roots(c, r);
+    for (int k = 0; k < nr; k++) {
+        double nrm = 0;
+        for (int j = 0; j < 9; j++) { Fs[9 * k + j] = r[k] * F1[j] + (1.0 - r[k]) * F2[j]; nrm += Fs[9 * k + j] * Fs[9 * k + j]; }
+        nrm = sqrt(nrm);
+        if (nrm > 0) for (int j = 0; j < 9; j++) Fs[9 * k + j] /= nrm;
+    }
+    return nr;
+}
+__device__ __forceinline__ bool rs_inlier(const double* F, double x0, double y0, double x1, double y1, float t2)
+{
+    double a = F[0] * x0 + F[1] * y0 + F[2], b = F[3] * x0 + F[4] * y0 + F[5], c = F[6] * x0 + F[7] * y0 + F[8];
+    const double s2 = 1.0 / (a * a + b * b), d2 = x1 * a + y1 * b + c;
+    a = F[0] * x1 + F[3] * y1 + F[6]; b = F[1] * x1 + F[4] * y1 + F[7]; c = F[2] * x1 + F[5] * y1 + F[8];
+    const double s1 = 1.0 / (a * a + b * b), d1 = x0 * a + y0 * b + c;
+    const double e1 = d1 * d1 * s1, e2 = d2 * d2 * s2;
+    return (float)(e1 > e2 ? e1 : e2) <= t2;
+}
+
+// best[0]: (count << 32 | ~(hypothesis * 4 + root)) maximum; Fbuf: 27 doubles per hypothesis
+__global__ void __launch_bounds__(256)
+k_ransac_fm(const float2* __restrict__ p0, const float2* __restrict__ p1, int n, float t2, int nhyp, unsigned long long seed,
+            double* __restrict__ Fbuf, unsigned long long* __restrict__ best)
+{
+    __shared__ double s_F[8][27];
+    __shared__ int s_nm[8];
+    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+    const int h = blockIdx.x * 8 + warp;
+    if (h >= nhyp) return;
+    if (lane == 0) {
+        int idx[7], ns = 0;
+        for (int k = 1; k <= 16 && ns < 7; k++) {
+            const int cand = (int)(rs_sm64(seed, (unsigned long long)h * 16ULL + (unsigned long long)k) % (unsigned long long)n);
+            bool dup = false;
+            for (int j = 0; j < ns; j++) dup |= idx[j] == cand;
+            if (!dup) idx[ns++] = cand;
+        }
+        int nm = 0;
+        if (ns == 7) {
+            double x0[7], y0[7], x1[7], y1[7];
+            for (int j = 0; j < 7; j++) { const float2 a = p0[idx[j]], b = p1[idx[j]]; x0[j] = a.x; y0[j] = a.y; x1[j] = b.x; y1[j] = b.y; }
+            nm = rs_seven_point(x0, y0, x1, y1, s_F[warp]);
+        }
+        s_nm[warp] = nm;
+        for (int j = 0; j < 9 * nm; j++) Fbuf[(size_t)h * 27 + j] = s_F[warp][j];
+    }
+    __syncwarp();
+    const int nm = s_nm[warp];
+    for (int k = 0; k < nm; k++) {
+        double F[9];
+#pragma unroll
+        for (int j = 0; j < 9; j++) F[j] = s_F[warp][9 * k + j];
+        int cnt = 0;
+        for (int i = lane; i < n; i += 32) { const float2 a = p0[i], b = p1[i]; cnt += rs_inlier(F, a.x, a.y, b.x, b.y, t2) ? 1 : 0; }
+#pragma unroll
+        for (int o = 16; o > 0; o >>= 1) cnt += __shfl_xor_sync(0xFFFFFFFFu, cnt, o);
+        if (lane == 0 && cnt > 6)
+            atomicMax(best, ((unsigned long long)cnt << 32) | (unsigned long long)(0xFFFFFFFFu - (unsigned)(h * 4 + k)));
+    }
+}
+
+__global__ void __launch_bounds__(256)
+k_ransac_mask(const float2* __restrict__ p0, const float2* __restrict__ p1, int n, float t2, const double* __restrict__ Fbuf,
+              const unsigned long long* __restrict__ best, uint8_t* __restrict__ mask, double* __restrict__ Fout)
+{
+    const unsigned long long b = best[0];
+    const int i = blockIdx.x * 256 + threadIdx.x;
+    if (b == 0) { if (i < n) mask[i] = 0; return; }
+    const unsigned id = 0xFFFFFFFFu - (unsigned)(b & 0xFFFFFFFFu);
+    const double* F = Fbuf + (size_t)(id >> 2) * 27 + 9 * (id & 3);
+    if (i < 9) Fout[i] = F[i];
+    if (i < n) { const float2 a = p0[i], c = p1[i]; mask[i] = rs_inlier(F, a.x, a.y, c.x, c.y, t2) ? 1 : 0; }
+}
+
 extern "C" {
 
 int uvip_klt_create(int device, int max_width, int max_height, int win, int max_level, int nslots, uvip_klt** out)
@@ -327,6 +500,40 @@ int uvip_klt_track(uvip_klt* k, int slot_prev, int slot_next, const float* prev_
     UVIP_CUDA(cudaMemcpyAsync(status, base + o_st, (size_t)n, cudaMemcpyDeviceToHost, st));
     if (err) UVIP_CUDA(cudaMemcpyAsync(err, base + o_err, (size_t)n * 4, cudaMemcpyDeviceToHost, st));
     UVIP_CUDA(cudaStreamSynchronize(st));
+    return UVIP_OK;
+}
+
+int uvip_klt_ransac_fundamental(uvip_klt* k, const float* pts0, const float* pts1, int n, double threshold, int nhyp, uint8_t* mask, double* F,
+                                int* ninliers)
+{
+    UVIP_CHECK_ARG(k && pts0 && pts1 && mask && ninliers && n >= 0 && threshold > 0 && nhyp >= 1 && nhyp <= (1 << 20));
+    if (n < 15) { set_last_error("findFundamentalMat(FM_RANSAC) needs at least 15 points (OpenCV switches to LMedS below that; not built)"); return UVIP_ERR_UNSUPPORTED; }
+    std::lock_guard<std::mutex> lk(k->mu);
+    DeviceGuard g(k->device);
+    int rc;
+    const size_t o_p1 = align_up((size_t)n * 8, 256), o_F = 2 * o_p1, o_best = o_F + align_up((size_t)nhyp * 27 * 8, 256), o_mask = o_best + 256,
+                 o_Fout = o_mask + align_up((size_t)n, 256);
+    if ((rc = k->pts.reserve(o_Fout + 128))) return rc;
+    uint8_t* base = k->pts.as<uint8_t>();
+    cudaStream_t st = k->stream;
+    UVIP_CUDA(cudaMemcpyAsync(base, pts0, (size_t)n * 8, cudaMemcpyHostToDevice, st));
+    UVIP_CUDA(cudaMemcpyAsync(base + o_p1, pts1, (size_t)n * 8, cudaMemcpyHostToDevice, st));
+    UVIP_CUDA(cudaMemsetAsync(base + o_best, 0, 8, st));
+    UVIP_CUDA(cudaMemsetAsync(base + o_Fout, 0, 72, st));
+    const float t2 = (float)(threshold * threshold);
+    k_ransac_fm<<<div_up(nhyp, 8), 256, 0, st>>>((const float2*)base, (const float2*)(base + o_p1), n, t2, nhyp, 0x5EEDULL, (double*)(base + o_F),
+                                                 (unsigned long long*)(base + o_best));
+    k_ransac_mask<<<div_up(n > 9 ? n : 9, 256), 256, 0, st>>>((const float2*)base, (const float2*)(base + o_p1), n, t2, (const double*)(base + o_F),
+                                                              (const unsigned long long*)(base + o_best), base + o_mask, (double*)(base + o_Fout));
+    k->launches += 2;
+    UVIP_CUDA(cudaGetLastError());
+    unsigned long long best = 0; double Fh[9];
+    UVIP_CUDA(cudaMemcpyAsync(mask, base + o_mask, (size_t)n, cudaMemcpyDeviceToHost, st));
+    UVIP_CUDA(cudaMemcpyAsync(&best, base + o_best, 8, cudaMemcpyDeviceToHost, st));
+    UVIP_CUDA(cudaMemcpyAsync(Fh, base + o_Fout, 72, cudaMemcpyDeviceToHost, st));
+    UVIP_CUDA(cudaStreamSynchronize(st));
+    *ninliers = (int)(best >> 32);
+    if (F) memcpy(F, Fh, 72);
     return UVIP_OK;
 }
 

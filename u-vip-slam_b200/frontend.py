@@ -514,6 +514,14 @@ class KLTTracker:
         check(lib().uvip_klt_get_level(self.h, slot, l, ptr(img), ptr(der), C.byref(w), C.byref(h)))
         return img, der
 
+    def ransac_fundamental(self, pts0, pts1, threshold=1.0, nhyp=2048):
+        """cv::findFundamentalMat(pts0, pts1, FM_RANSAC, threshold, 0.999, mask) of src/Tracking.cc:1062: (inlier count, mask, F)"""
+        p0 = np.ascontiguousarray(pts0, np.float32).reshape(-1, 2); p1 = np.ascontiguousarray(pts1, np.float32).reshape(-1, 2)
+        n = len(p0)
+        mask = np.zeros(n, np.uint8); F = np.zeros(9, np.float64); cnt = C.c_int()
+        check(lib().uvip_klt_ransac_fundamental(self.h, ptr(p0), ptr(p1), n, float(threshold), int(nhyp), ptr(mask), ptr(F), C.byref(cnt)))
+        return cnt.value, mask, F.reshape(3, 3)
+
     def track(self, slot_prev, slot_next, prev_pts, next_pts, max_iter=30, eps=0.01, flags=12, min_eig_thr=1e-4):
         prev_pts = np.ascontiguousarray(prev_pts, np.float32).reshape(-1, 2)
         nxt = np.ascontiguousarray(next_pts, np.float32).reshape(-1, 2).copy()
