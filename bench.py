@@ -1115,6 +1115,26 @@ def run_next(args):
     P0 = O.LKPyramid(a_img, 21, 5); P1 = O.LKPyramid(b_img, 21, 5); O.lk_track(P0, P1, p0, p0, 21, 5, 30, 0.01, 8)
     tc = time.perf_counter() - t0
     out['klt'] = {'frame_pairs_per_s_e2e': 1.0 / tg, 'points': len(p0), 'tracked': int(st.sum()), 'cpu_oracle_frame_pairs_per_s_1thread': 1.0 / tc}
+    # batched, device-resident: a 64-frame sequence (pyramids of all frames, then the 63 consecutive pairs in one launch), 1000 points per pair
+    NS = 64
+    seq = torch.from_numpy(np.stack([pkg.synth.synth_frame(1, W, H, dx=(3 * f) % 29, dy=(2 * f) % 23, noise_seed=100 + f) for f in range(NS)])).to(dev)
+    klt_b = pkg.KLTTracker(W, H, 21, 5, nslots=NS)
+    prevp = torch.from_numpy(np.tile(p0[None], (NS - 1, 1, 1))).to(dev).contiguous(); nextp = prevp.clone()
+    stt = torch.zeros((NS - 1, len(p0)), dtype=torch.uint8, device=dev); err_t = torch.zeros((NS - 1, len(p0)), dtype=torch.float32, device=dev)
+    Pp = lambda t: C.c_void_p(t.data_ptr())
+    def klt_step():
+        nextp.copy_(prevp)
+        chk(L.uvip_klt_track_sequence_device(klt_b.h, Pp(seq), NS, W, H, W, W * H, Pp(prevp), Pp(nextp), len(p0), 5, 30, 0.01, 8, 1e-4, Pp(stt), Pp(err_t), sp))
+    ms = timed(klt_step)
+    # algorithmic bytes of the tracker: per frame the level-0 image + its pyramid (4/3) is read once, the int16 derivative pair planes (4 B per
+    # pixel) are written and read once; the windows themselves are L2 / shared-memory traffic
+    klt_bytes = NS * W * H * (4.0 / 3.0) * (1 + 1 + 4 + 4)
+    out['klt_sequence_device'] = {'frames': NS, 'pairs': NS - 1, 'points_per_pair': len(p0), 'ms_per_sequence': ms, 'frame_pairs_per_s': (NS - 1) / (ms * 1e-3),
+                                  'points_per_s': (NS - 1) * len(p0) / (ms * 1e-3), 'tracked_frac': float(stt.float().mean().item()),
+                                  'roofline': {'bound': 'hbm', 'achieved': klt_bytes / (ms * 1e-3) / 1e9, 'peak': peak, 'unit': 'GB/s',
+                                               'frac': klt_bytes / (ms * 1e-3) / 1e9 / peak, 'traffic': None,
+                                               'note': 'the tracker is arithmetic/latency-bound (30 Lucas-Kanade iterations over a 21x21 window per point and level, '
+                                                       'one warp per point): see profiles/ for the ncu capture of k_klt_track'}}
     # ---- N4 (descriptor half): batched MapPoint::ComputeDistinctiveDescriptors, 100k map points with 2..30 observations
     rng = np.random.default_rng(4)
     sizes = rng.integers(2, 31, 100000)

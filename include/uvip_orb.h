@@ -326,6 +326,13 @@ int   uvip_klt_build_pyramid(uvip_klt* k, int slot, const uint8_t* image, int w,
 int   uvip_klt_get_level(uvip_klt* k, int slot, int level, uint8_t* img, int16_t* der_xy, int* w, int* h);   /* debug tap */
 int   uvip_klt_track(uvip_klt* k, int slot_prev, int slot_next, const float* prev_pts, float* next_pts_inout, int n, int max_level,
                      int max_iter, double epsilon, int flags, double min_eig_threshold, uint8_t* status, float* err);
+/* buildOpticalFlowPyramid + calcOpticalFlowPyrLK for a SEQUENCE resident in device memory (throughput form of the two calls above):
+ * pyramids of nframes <= nslots frames into slots 0 .. nframes-1, then frame f -> f+1 tracked for every f in one launch.
+ * d_prev_pts / d_next_pts / d_status / d_err: (nframes - 1) x npts (x 2 floats); d_next_pts holds the initial guesses when
+ * OPTFLOW_USE_INITIAL_FLOW (4) is set.  Asynchronous on `stream`. */
+int   uvip_klt_track_sequence_device(uvip_klt* k, const uint8_t* d_frames, int nframes, int w, int h, int stride, size_t frame_pitch,
+                                     const float* d_prev_pts, float* d_next_pts, int npts, int max_level, int max_iter, double epsilon,
+                                     int flags, double min_eig_threshold, uint8_t* d_status, float* d_err, void* stream);
 /* cv::findFundamentalMat(pts0, pts1, FM_RANSAC, threshold, ...) of src/Tracking.cc:1062, of which the reference keeps the inlier mask:
  * 7-point hypotheses scored by OpenCV's residual (max of the two squared point-to-epipolar-line distances, double, cast to float,
  * compared with (float)(threshold^2)); the mask of the best hypothesis is returned together with its count and, optionally, its F

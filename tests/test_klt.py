@@ -160,3 +160,32 @@ def test_gpu_ransac_equals_oracle(pkg, oracle):
     ocnt, omask, oF = oracle.ransac_fundamental(z, z, 1.0, nhyp=2048)
     assert cnt == ocnt and np.array_equal(mask, omask)
     klt.close()
+
+
+@pytest.mark.gpu
+def test_gpu_klt_sequence_device_equals_pairwise_calls(pkg, synth):
+    """uvip_klt_track_sequence_device (pyramids of a whole device-resident sequence, all consecutive pairs in one launch) gives exactly
+    what build_pyramid + track give pair by pair"""
+    import ctypes as C
+    import torch
+    W, H, NFR, NP = 752, 480, 5, 400
+    frames = np.stack([synth.synth_frame(1, W, H, dx=2 * f, dy=f, noise_seed=10 + f) for f in range(NFR)])
+    p0 = _pts(synth)[:NP]
+    klt = pkg.KLTTracker(W, H, 21, 5, nslots=8)
+    want = []
+    for f in range(NFR - 1):
+        klt.build_pyramid(0, frames[f]); klt.build_pyramid(1, frames[f + 1])
+        want.append(klt.track(0, 1, p0, p0 + np.float32([1.0, 0.5])))
+    d_fr = torch.from_numpy(frames).cuda()
+    prev = torch.from_numpy(np.tile(p0[None], (NFR - 1, 1, 1))).cuda().contiguous()
+    nxt = (prev + torch.tensor([1.0, 0.5], device='cuda')).contiguous()
+    st = torch.zeros((NFR - 1, NP), dtype=torch.uint8, device='cuda'); er = torch.zeros((NFR - 1, NP), dtype=torch.float32, device='cuda')
+    P = lambda t: C.c_void_p(t.data_ptr())
+    pkg.capi.check(pkg.capi.lib().uvip_klt_track_sequence_device(klt.h, P(d_fr), NFR, W, H, W, W * H, P(prev), P(nxt), NP, 5, 30, 0.01, 12, 1e-4, P(st), P(er),
+                                                                 C.c_void_p(torch.cuda.current_stream().cuda_stream or 1)))
+    torch.cuda.synchronize()
+    for f in range(NFR - 1):
+        p1, s1, e1 = want[f]
+        assert np.array_equal(nxt[f].cpu().numpy(), p1) and np.array_equal(st[f].cpu().numpy(), s1) and np.array_equal(er[f].cpu().numpy(), e1), f
+    assert st.sum().item() > 0.9 * (NFR - 1) * NP
+    klt.close()

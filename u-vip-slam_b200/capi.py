@@ -118,6 +118,7 @@ def lib():
         L.uvip_klt_get_level.argtypes = [vp, i, i, vp, vp, C.POINTER(i), C.POINTER(i)]
         L.uvip_klt_track.argtypes = [vp, i, i, vp, vp, i, i, i, C.c_double, i, C.c_double, vp, vp]
         L.uvip_klt_launch_count.argtypes = [vp]
+        L.uvip_klt_track_sequence_device.argtypes = [vp, vp, i, i, i, i, sz, vp, vp, i, i, i, C.c_double, i, C.c_double, vp, vp, vp]
         L.uvip_klt_ransac_fundamental.argtypes = [vp, vp, vp, i, C.c_double, i, vp, vp, C.POINTER(i)]
         L.uvip_klt_launch_count.restype = C.c_longlong
         L.uvip_synth_frames_device.argtypes = [vp, vp, vp, i, i, i, vp, sz, vp]

@@ -26,8 +26,9 @@ __device__ __forceinline__ int refl(int p, int n) { return p < 0 ? -p : (p >= n 
 
 // level 0: padded copy of the input frame (reflect-101 border of win + 2 pixels)
 __global__ void __launch_bounds__(256)
-k_klt_import(const uint8_t* __restrict__ src, int stride, uint8_t* __restrict__ img, const __grid_constant__ KltPlan P)
+k_klt_import(const uint8_t* __restrict__ src, int stride, uint8_t* __restrict__ img, size_t src_pitch, size_t slot_img, const __grid_constant__ KltPlan P)
 {
+    src += (size_t)blockIdx.y * src_pitch; img += (size_t)blockIdx.y * slot_img;        // batched form: frame blockIdx.y -> slot blockIdx.y
     const KltLevel& L = P.lv[0];
     const int pw = L.w + 2 * L.B, ph = L.h + 2 * L.B;
     const int i = blockIdx.x * 256 + threadIdx.x;
@@ -38,8 +39,9 @@ k_klt_import(const uint8_t* __restrict__ src, int stride, uint8_t* __restrict__ 
 
 // level l from level l-1: cv::pyrDown (5x5 binomial, (sum + 128) >> 8, REFLECT_101), written for every padded position
 __global__ void __launch_bounds__(256)
-k_klt_pyrdown(uint8_t* __restrict__ img, int level, const __grid_constant__ KltPlan P)
+k_klt_pyrdown(uint8_t* __restrict__ img, int level, size_t slot_img, const __grid_constant__ KltPlan P)
 {
+    img += (size_t)blockIdx.y * slot_img;
     const KltLevel& D = P.lv[level]; const KltLevel& S = P.lv[level - 1];
     const int pw = D.w + 2 * D.B, ph = D.h + 2 * D.B;
     const int i = blockIdx.x * 256 + threadIdx.x;
@@ -59,8 +61,9 @@ k_klt_pyrdown(uint8_t* __restrict__ img, int level, const __grid_constant__ KltP
 
 // Scharr derivatives (calcSharrDeriv): Ix = [3 10 3]^T x [-1 0 1], Iy = [-1 0 1]^T x [3 10 3], int16, interior only
 __global__ void __launch_bounds__(256)
-k_klt_scharr(const uint8_t* __restrict__ img, short2* __restrict__ der, int level, const __grid_constant__ KltPlan P)
+k_klt_scharr(const uint8_t* __restrict__ img, short2* __restrict__ der, int level, size_t slot_img, size_t slot_der, const __grid_constant__ KltPlan P)
 {
+    img += (size_t)blockIdx.y * slot_img; der += (size_t)blockIdx.y * slot_der;
     const KltLevel& L = P.lv[level];
     const int i = blockIdx.x * 256 + threadIdx.x;
     if (i >= L.w * L.h) return;
@@ -81,12 +84,18 @@ k_klt_scharr(const uint8_t* __restrict__ img, short2* __restrict__ der, int leve
 __global__ void __launch_bounds__(256)
 k_klt_track(const uint8_t* __restrict__ img0, const short2* __restrict__ der0, const uint8_t* __restrict__ img1,
             const float2* __restrict__ prev_pts, float2* __restrict__ next_pts, int n, int max_level, int max_iter, double eps2,
-            int flags, double min_eig_thr, uint8_t* __restrict__ status, float* __restrict__ err, const __grid_constant__ KltPlan P)
+            int flags, double min_eig_thr, uint8_t* __restrict__ status, float* __restrict__ err, size_t slot_img, size_t slot_der,
+            const __grid_constant__ KltPlan P)
 {
     extern __shared__ short s_win[];                   // per warp: win*win intensities, then win*win (Ix, Iy)
     const int lane = threadIdx.x & 31, wib = threadIdx.x >> 5;
     const int pt = blockIdx.x * 8 + wib;
     if (pt >= n) return;
+    {   // batched form: pair blockIdx.y tracks slot y -> slot y + 1 with its own n points (img1 is img0's base: one slot further)
+        const size_t pr = blockIdx.y;
+        img0 += pr * slot_img; der0 += pr * slot_der; img1 += pr * slot_img;
+        prev_pts += pr * n; next_pts += pr * n; status += pr * n; if (err) err += pr * n;
+    }
     const int win = P.win, npx = win * win;
     const int npx_pad = (npx + 1) & ~1;                   // keeps the short2 part 4-byte aligned
     short* Iw = s_win + (size_t)wib * 3 * npx_pad;
@@ -433,14 +442,14 @@ int uvip_klt_build_pyramid(uvip_klt* k, int slot, const uint8_t* image, int w, i
     uint8_t* img = k->img.as<uint8_t>() + (size_t)slot * k->img_bytes;
     short2* der = k->der.as<short2>() + (size_t)slot * k->der_elems;
     UVIP_CUDA(cudaMemcpy2DAsync(k->stage.p, w, image, stride, w, h, cudaMemcpyHostToDevice, st));
-    { const KltLevel& L = P.lv[0]; k_klt_import<<<div_up((L.w + 2 * L.B) * (L.h + 2 * L.B), 256), 256, 0, st>>>(k->stage.as<uint8_t>(), w, img, P); k->launches++; }
+    { const KltLevel& L = P.lv[0]; k_klt_import<<<div_up((L.w + 2 * L.B) * (L.h + 2 * L.B), 256), 256, 0, st>>>(k->stage.as<uint8_t>(), w, img, 0, 0, P); k->launches++; }
     for (int l = 1; l < P.nlevels; l++) {
         const KltLevel& L = P.lv[l];
-        k_klt_pyrdown<<<div_up((L.w + 2 * L.B) * (L.h + 2 * L.B), 256), 256, 0, st>>>(img, l, P); k->launches++;
+        k_klt_pyrdown<<<div_up((L.w + 2 * L.B) * (L.h + 2 * L.B), 256), 256, 0, st>>>(img, l, 0, P); k->launches++;
     }
     for (int l = 0; l < P.nlevels; l++) {
         const KltLevel& L = P.lv[l];
-        k_klt_scharr<<<div_up(L.w * L.h, 256), 256, 0, st>>>(img, der, l, P); k->launches++;
+        k_klt_scharr<<<div_up(L.w * L.h, 256), 256, 0, st>>>(img, der, l, 0, 0, P); k->launches++;
     }
     UVIP_CUDA(cudaGetLastError());
     UVIP_CUDA(cudaStreamSynchronize(st));
@@ -493,13 +502,54 @@ int uvip_klt_track(uvip_klt* k, int slot_prev, int slot_next, const float* prev_
     UVIP_CUDA(cudaFuncSetAttribute(k_klt_track, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
     k_klt_track<<<div_up(n, 8), 256, smem, st>>>(k->img.as<uint8_t>() + (size_t)slot_prev * k->img_bytes, k->der.as<short2>() + (size_t)slot_prev * k->der_elems,
                                                 k->img.as<uint8_t>() + (size_t)slot_next * k->img_bytes, (const float2*)base, (float2*)(base + o_next), n,
-                                                max_level, max_iter, eps2, flags, min_eig_threshold, base + o_st, (float*)(base + o_err), P);
+                                                max_level, max_iter, eps2, flags, min_eig_threshold, base + o_st, (float*)(base + o_err), 0, 0, P);
     k->launches++;
     UVIP_CUDA(cudaGetLastError());
     UVIP_CUDA(cudaMemcpyAsync(next_pts, base + o_next, (size_t)n * 8, cudaMemcpyDeviceToHost, st));
     UVIP_CUDA(cudaMemcpyAsync(status, base + o_st, (size_t)n, cudaMemcpyDeviceToHost, st));
     if (err) UVIP_CUDA(cudaMemcpyAsync(err, base + o_err, (size_t)n * 4, cudaMemcpyDeviceToHost, st));
     UVIP_CUDA(cudaStreamSynchronize(st));
+    return UVIP_OK;
+}
+
+// Batched, device-resident form of the two calls above for a SEQUENCE: the pyramids of nframes frames are built in slots 0 .. nframes-1
+// (one launch per pyramid level over all frames), then frame f -> f + 1 is tracked for f = 0 .. nframes-2 in ONE launch (one warp per
+// point and pair).  All pointers are device memory; asynchronous on `stream` (NULL = the handle's stream).
+int uvip_klt_track_sequence_device(uvip_klt* k, const uint8_t* d_frames, int nframes, int w, int h, int stride, size_t frame_pitch,
+                                   const float* d_prev_pts, float* d_next_pts, int npts, int max_level, int max_iter, double epsilon, int flags,
+                                   double min_eig_threshold, uint8_t* d_status, float* d_err, void* stream)
+{
+    UVIP_CHECK_ARG(k && d_frames && d_prev_pts && d_next_pts && d_status && nframes >= 2 && nframes <= k->nslots && npts >= 1);
+    UVIP_CHECK_ARG(w > 0 && h > 0 && stride >= w && w <= k->max_w && h <= k->max_h && frame_pitch >= (size_t)stride * (h - 1) + w);
+    std::lock_guard<std::mutex> lk(k->mu);
+    DeviceGuard g(k->device);
+    cudaStream_t st = stream ? (cudaStream_t)stream : k->stream;
+    if (w != k->w || h != k->h) {
+        const size_t ib = k->img_bytes, de = k->der_elems;
+        klt_make_plan(k, w, h);
+        k->img_bytes = ib; k->der_elems = de;
+        UVIP_CUDA(cudaMemsetAsync(k->der.p, 0, k->der.cap, st));
+        for (int s2 = 0; s2 < k->nslots; s2++) k->slot_w[(size_t)s2] = k->slot_h[(size_t)s2] = 0;
+    }
+    for (int s2 = 0; s2 < nframes; s2++) { k->slot_w[(size_t)s2] = w; k->slot_h[(size_t)s2] = h; }
+    const KltPlan& P = k->plan;
+    uint8_t* img = k->img.as<uint8_t>(); short2* der = k->der.as<short2>();
+    const size_t si = k->img_bytes, sd = k->der_elems;
+    { const KltLevel& L = P.lv[0]; k_klt_import<<<dim3(div_up((L.w + 2 * L.B) * (L.h + 2 * L.B), 256), nframes), 256, 0, st>>>(d_frames, stride, img, frame_pitch, si, P); }
+    for (int l = 1; l < P.nlevels; l++) { const KltLevel& L = P.lv[l]; k_klt_pyrdown<<<dim3(div_up((L.w + 2 * L.B) * (L.h + 2 * L.B), 256), nframes), 256, 0, st>>>(img, l, si, P); }
+    for (int l = 0; l < P.nlevels; l++) { const KltLevel& L = P.lv[l]; k_klt_scharr<<<dim3(div_up(L.w * L.h, 256), nframes), 256, 0, st>>>(img, der, l, si, sd, P); }
+    k->launches += 2 * P.nlevels;
+    if (max_iter < 0) max_iter = 0; if (max_iter > 100) max_iter = 100;
+    if (epsilon < 0) epsilon = 0; if (epsilon > 10) epsilon = 10;
+    if (max_level > P.nlevels - 1) max_level = P.nlevels - 1;
+    if (max_level < 0) max_level = 0;
+    const int npx = P.win * P.win;
+    const size_t smem = (size_t)8 * 3 * ((npx + 1) & ~1) * sizeof(short);
+    UVIP_CUDA(cudaFuncSetAttribute(k_klt_track, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+    k_klt_track<<<dim3(div_up(npts, 8), nframes - 1), 256, smem, st>>>(img, der, img + si, (const float2*)d_prev_pts, (float2*)d_next_pts, npts, max_level, max_iter,
+                                                                      epsilon * epsilon, flags, min_eig_threshold, d_status, d_err, si, sd, P);
+    k->launches++;
+    UVIP_CUDA(cudaGetLastError());
     return UVIP_OK;
 }
 
