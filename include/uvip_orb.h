@@ -228,7 +228,9 @@ int   uvip_grid_build(uvip_matcher* m, const float* kx, const float* ky, int n,
 typedef struct uvip_search_params {
     int32_t mode;        /* 0: top-2 with same-level ratio rule; 1: best only; 4: best only without claims (Fuse,
                           * src/ORBmatcher.cc:1075-1100: taken[] is neither read nor written, several queries may return
-                          * the same keypoint and the caller replays Replace / AddObservation in query order) */
+                          * the same keypoint and the caller replays Replace / AddObservation in query order);
+                          * 6: top-2 without levels, accept (float)best <= (float)best2 * ratio and best <= th_dist, claims
+                          * (WindowSearch :409-516 and SearchByProjection(F1, F2, windowSize, ...) :519-596 — uncalled in this fork) */
     int32_t th_dist;     /* UVIP_TH_HIGH for mode 0, ORBdist for mode 1 */
     float   ratio;       /* mfNNratio */
     float   min_x, min_y, inv_w, inv_h;   /* FrameKTL::mnMinX, mnMinY, mfGridElementWidthInv, mfGridElementHeightInv */

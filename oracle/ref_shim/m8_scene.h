@@ -127,13 +127,61 @@ struct Scene {
     }
 };
 
+// The two keyframes of the scene as FRAMES (FrameKTL stand-ins), for the frame-side overloads of include/ORBmatcher.h:49-72 that no
+// caller of this fork reaches: same keypoints, descriptors, map points and poses
+inline void frame_of(const Scene& S, int k, USLAM::FrameKTL& F, const int32_t* bd)
+{
+    const USLAM::KeyFrame& K = S.K[k];
+    F.mvKeysUn = K.keysUn; F.mvKeys = K.keysUn;
+    F.mDescriptors = K.descriptors.clone();
+    F.mvpMapPoints = K.mapPoints;
+    F.mvbOutlier.assign(K.keysUn.size(), false);
+    for (size_t i = 0; i < F.mvbOutlier.size(); i++) F.mvbOutlier[i] = (i % 17) == 3;
+    F.mvScaleFactors = K.scaleFactors; F.mnScaleLevels = (int)K.scaleFactors.size();
+    F.fx = K.fx; F.fy = K.fy; F.cx = K.cx; F.cy = K.cy;
+    F.mnMinX = (float)bd[0]; F.mnMaxX = (float)bd[1]; F.mnMinY = (float)bd[2]; F.mnMaxY = (float)bd[3];
+    F.mfGridElementWidthInv = (float)FRAME_GRID_COLS / (F.mnMaxX - F.mnMinX); F.mfGridElementHeightInv = (float)FRAME_GRID_ROWS / (F.mnMaxY - F.mnMinY);
+    F.grid.build(F.mvKeysUn, F.mnMinX, F.mnMaxX, F.mnMinY, F.mnMaxY);
+    F.mTcw = cv::Mat::eye(4, 4, CV_32F);
+    for (int r = 0; r < 3; r++) { for (int c = 0; c < 3; c++) F.mTcw.at<float>(r, c) = K.Rcw.at<float>(r, c); F.mTcw.at<float>(r, 3) = K.tcw.at<float>(r); }
+    F.mnId = (unsigned long)k;
+}
+
 // which: 0 Fuse(KF, MPs, th)   1 Fuse(KF, Scw, MPs, th)   2 SearchByProjection(KF, Scw, MPs, vpMatched, th)   3 SearchBySim3
 //        4 SearchForTriangulation(KF1, KF2, F12, keys1, keys2, pairs)
+//        5 WindowSearch(F1, F2, (int)th, matches2)    6 SearchByProjection(F1, F2, (int)th, matches2)    7 SearchForInitialization(F1, F2,
+//        prev, matches12, (int)th)    8 SearchByProjection(F2 = current, F1 = last, th)    9 WindowSearch with octave limits 1..3
 template <class Matcher>
 int run(int which, const Bundle& in, Bundle& out)
 {
     Scene S; S.build(in);
     Matcher matcher(S.nnratio, true);
+    if (which >= 5) {
+        const int32_t* bd = in.get<int32_t>(A_BOUNDS);
+        USLAM::FrameKTL F1, F2; frame_of(S, 0, F1, bd); frame_of(S, 1, F2, bd);
+        std::vector<int32_t> ret(1, 0), slot_owner, replaced, obs_slot;
+        if (which == 5 || which == 9 || which == 6) {
+            std::vector<USLAM::MapPoint*> m2;
+            if (which == 5) ret[0] = matcher.WindowSearch(F1, F2, (int)S.th, m2);
+            else if (which == 9) ret[0] = matcher.WindowSearch(F1, F2, (int)S.th, m2, 1, 3);
+            else ret[0] = matcher.SearchByProjection(F1, F2, (int)S.th, m2);
+            for (size_t k = 0; k < m2.size(); k++) slot_owner.push_back(S.id_of(m2[k]));
+        } else if (which == 7) {
+            std::vector<cv::Point2f> prev(F1.mvKeysUn.size()); std::vector<int> m12;
+            for (size_t i = 0; i < prev.size(); i++) { prev[i] = F1.mvKeysUn[i].pt; prev[i].x += (float)((int)(i % 5) - 2) * 0.5f; prev[i].y -= (float)((int)(i % 3) - 1) * 0.5f; }
+            for (size_t i = 0; i < F1.mvKeysUn.size(); i++) if (i % 3 != 2) { F1.mvKeysUn[i].octave = 0; }      // the function only looks at level 0
+            for (size_t i = 0; i < F2.mvKeysUn.size(); i++) if (i % 3 != 2) { F2.mvKeysUn[i].octave = 0; }
+            F2.grid.build(F2.mvKeysUn, F2.mnMinX, F2.mnMaxX, F2.mnMinY, F2.mnMaxY);
+            ret[0] = matcher.SearchForInitialization(F1, F2, prev, m12, (int)S.th);
+            for (size_t i = 0; i < m12.size(); i++) slot_owner.push_back(m12[i]);
+            for (size_t i = 0; i < prev.size(); i++) { replaced.push_back((int32_t)(prev[i].x * 64.f)); replaced.push_back((int32_t)(prev[i].y * 64.f)); }
+        } else {
+            ret[0] = matcher.SearchByProjection(F2, F1, S.th);
+            for (size_t k = 0; k < F2.mvpMapPoints.size(); k++) slot_owner.push_back(S.id_of(F2.mvpMapPoints[k]));
+        }
+        out.put(ret); out.put(slot_owner); out.put(replaced); out.put(obs_slot);
+        return ret[0];
+    }
     const int32_t* pf = in.get<int32_t>(P_FLAGS);
     std::vector<int32_t> ret(1, 0), slot_owner, replaced, obs_slot;
     USLAM::KeyFrame* pKF = &S.K[0];

@@ -52,7 +52,8 @@ public:
 
 class FrameKTL {
 public:
-    FrameKTL() : fx(0), fy(0), cx(0), cy(0), mnMinX(0), mnMaxX(0), mnMinY(0), mnMaxY(0), mnScaleLevels(0), mnId(0) {}
+    FrameKTL() : fx(0), fy(0), cx(0), cy(0), mnMinX(0), mnMaxX(0), mnMinY(0), mnMaxY(0), mfGridElementWidthInv(0), mfGridElementHeightInv(0),
+                 mnScaleLevels(0), mnId(0) {}
     std::vector<cv::KeyPoint> mvKeys, mvKeysUn;
     cv::Mat mDescriptors, mTcw;
     std::vector<MapPoint*> mvpMapPoints;
@@ -61,6 +62,7 @@ public:
     DBoW2::FeatureVector mFeatVec;
     float fx, fy, cx, cy;
     float mnMinX, mnMaxX, mnMinY, mnMaxY;       // static members in the reference (include/FrameKTL.h:173-176)
+    float mfGridElementWidthInv, mfGridElementHeightInv;     // static members in the reference (include/FrameKTL.h:157-158); read by the drop-in shim
     int mnScaleLevels; long unsigned int mnId;
     GridStandin grid;
     std::vector<size_t> GetFeaturesInArea(const float& x, const float& y, const float& r, const int minLevel = -1, const int maxLevel = -1) const

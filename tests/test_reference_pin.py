@@ -610,7 +610,7 @@ def m8_bundle(oracle, synth, which, th=None):
     R12 = (R1.astype(np.float64) @ R2.astype(np.float64).T).astype(np.float32)
     t12 = (t1.astype(np.float64) - R12.astype(np.float64) @ t2.astype(np.float64)).astype(np.float32)
     Scw = np.eye(4, dtype=np.float32); Scw[:3, :3] = f32(1.7) * R1; Scw[:3, 3] = f32(1.7) * t1
-    th = [3.0, 4.0, 10.0, 7.5, 0.0][which] if th is None else th
+    th = [3.0, 4.0, 10.0, 7.5, 0.0, 12.0, 12.0, 14.0, 7.0, 15.0][which] if th is None else th
     pose = lambda R, t, O: np.concatenate([R.ravel(), t, O]).astype(np.float32)
     # fundamental matrix of the pair, F12 = K^-T [t12]x R12 K^-1 (src/LocalMapping.cc ComputeF12), and vocabulary nodes
     Kinv = np.linalg.inv(np.array([[fx, 0, cx], [0, fy, cy], [0, 0, 1]], np.float64))
@@ -623,12 +623,14 @@ def m8_bundle(oracle, synth, which, th=None):
             F12, node1, node2]
 
 
-M8_NAMES = ['Fuse(KF, MPs, th)', 'Fuse(KF, Scw, MPs, th)', 'SearchByProjection(KF, Scw, MPs, vpMatched, th)', 'SearchBySim3', 'SearchForTriangulation']
-M8_MIN = [150, 150, 150, 150, 25]
+M8_NAMES = ['Fuse(KF, MPs, th)', 'Fuse(KF, Scw, MPs, th)', 'SearchByProjection(KF, Scw, MPs, vpMatched, th)', 'SearchBySim3', 'SearchForTriangulation',
+            'WindowSearch(F1, F2, windowSize, matches2)', 'SearchByProjection(F1, F2, windowSize, matches2)', 'SearchForInitialization',
+            'SearchByProjection(CurrentFrame, LastFrame, th)', 'WindowSearch(F1, F2, windowSize, matches2, 1, 3)']
+M8_MIN = [150, 150, 150, 150, 25, 100, 20, 100, 20, 50]
 
 
 @needs_mref
-@pytest.mark.parametrize('which', [0, 1, 2, 3, 4])
+@pytest.mark.parametrize('which', [0, 1, 2, 3, 4, 5, 6, 7, 8, 9])
 def test_m8_reference_runs_every_branch(oracle, synth, which, tmp_path):
     """the scenes must exercise the reference's code paths (otherwise the GPU comparison below proves little)"""
     R.write_bundle(str(tmp_path / 's.bin'), m8_bundle(oracle, synth, which))
@@ -644,8 +646,12 @@ def test_m8_reference_runs_every_branch(oracle, synth, which, tmp_path):
             assert (replaced[:len(slot_owner)] >= 200000).sum() > 30              # Fuse(Scw) replaces the KEYFRAME's points
     elif which == 2:
         assert (slot_owner >= 200000).sum() >= r
-    else:
+    elif which == 3:
         assert (slot_owner >= 100000).sum() >= r
+    elif which == 7:
+        assert (slot_owner >= 0).sum() == r and len(replaced) == 2 * len(slot_owner)      # vnMatches12 and the updated vbPrevMatched
+    else:
+        assert (slot_owner >= 0).sum() >= r                                             # frame 2's slots hold frame 1's map points
 
 
 @needs_mref
@@ -691,10 +697,12 @@ def test_shim_m8_driver_refuses_without_device(pkg, oracle, synth, tmp_path):
 
 @needs_mref
 @pytest.mark.gpu
-@pytest.mark.parametrize('which', [0, 1, 2, 3, 4])
+@pytest.mark.parametrize('which', [0, 1, 2, 3, 4, 5, 6, 7, 8, 9])
 def test_shim_m8_equals_reference(gpu, oracle, synth, which, tmp_path):
     """row M8 end to end: the drop-in shim (host geometry + uvip_search_window on the GPU) against the reference's compiled
-    ORBmatcher, same scene code, same stand-in SLAM types, same call signatures; result bundles must be identical."""
+    ORBmatcher, same scene code, same stand-in SLAM types, same call signatures; result bundles must be identical.  which >= 5:
+    the four public overloads of include/ORBmatcher.h:49-72 that this fork never calls (WindowSearch, SearchByProjection(F1, F2, ...),
+    SearchForInitialization, SearchByProjection(CurrentFrame, LastFrame, th))."""
     import os, subprocess
     assert os.path.exists(R.M8_EXE), 'oracle/_ref/test_shim_m8 is prebuilt by `make -C oracle ref` in the build container'
     R.write_bundle(str(tmp_path / 's.bin'), m8_bundle(oracle, synth, which))

@@ -424,7 +424,7 @@ __device__ int search_one(const SearchCtx& c, int q, const int* owner)
     const bool same = check && (minL == maxL);
     const uint4 u = __ldg(reinterpret_cast<const uint4*>(c.qdesc + (size_t)q * 32));
     const uint4 v = __ldg(reinterpret_cast<const uint4*>(c.qdesc + (size_t)q * 32) + 1);
-    int bestDist = sp.mode == 0 ? 256 : INT_MAX, bestDist2 = 256, bestLevel = -1, bestLevel2 = -1, bestIdx = -1;
+    int bestDist = sp.mode == 0 ? 256 : INT_MAX, bestDist2 = sp.mode == 6 ? INT_MAX : 256, bestLevel = -1, bestLevel2 = -1, bestIdx = -1;
     for (int ix = cx0; ix <= cx1; ix++)
         for (int iy = cy0; iy <= cy1; iy++) {
             const int cell = ix * sp.rows + iy;
@@ -442,11 +442,15 @@ __device__ int search_one(const SearchCtx& c, int q, const int* owner)
                 if (sp.mode == 0) {                                // src/ORBmatcher.cc:98-111
                     if (dist < bestDist) { bestDist2 = bestDist; bestDist = dist; bestLevel2 = bestLevel; bestLevel = oct; bestIdx = id; }
                     else if (dist < bestDist2) { bestLevel2 = oct; bestDist2 = dist; }
+                } else if (sp.mode == 6) {                         // WindowSearch / SearchByProjection(F1, F2, ...): top-2 without levels (:454-465)
+                    if (dist < bestDist) { bestDist2 = bestDist; bestDist = dist; bestIdx = id; }
+                    else if (dist < bestDist2) bestDist2 = dist;
                 } else if (dist < bestDist) { bestDist = dist; bestIdx = id; }   // :1697-1701
             }
         }
     if (bestIdx < 0 || bestDist > sp.th_dist) return -1;
     if (sp.mode == 0 && bestLevel == bestLevel2 && (float)bestDist > __fmul_rn(sp.ratio, (float)bestDist2)) return -1;   // :116-117
+    if (sp.mode == 6 && !((float)bestDist <= __fmul_rn((float)bestDist2, sp.ratio))) return -1;                         // :470, :585
     return bestIdx;
 }
 
@@ -1091,7 +1095,7 @@ int uvip_search_frame(uvip_matcher* m, const uvip_search_params* sp,
                       int32_t* taken, int32_t* match, int* nmatches)
 {
     UVIP_CHECK_ARG(m && sp && nq >= 0 && nk >= 0 && sp->cols > 0 && sp->rows > 0);
-    UVIP_CHECK_ARG(sp->mode == 0 || sp->mode == 1 || sp->mode == 4);
+    UVIP_CHECK_ARG(sp->mode == 0 || sp->mode == 1 || sp->mode == 4 || sp->mode == 6);
     if (nmatches) *nmatches = 0;
     if (nq == 0) return UVIP_OK;
     UVIP_CHECK_ARG(qu && qv && qr && qmin_level && qmax_level && qdesc && match);
@@ -1263,7 +1267,7 @@ int uvip_search_window_batch_device(uvip_matcher* m, const uvip_search_params* s
                                     int32_t* d_taken, int32_t* d_match, int32_t* d_counts, void* stream)
 {
     UVIP_CHECK_ARG(m && sp && nframes >= 0 && q_stride > 0 && k_stride > 0 && sp->cols > 0 && sp->rows > 0);
-    UVIP_CHECK_ARG(sp->mode == 0 || sp->mode == 1 || sp->mode == 4);
+    UVIP_CHECK_ARG(sp->mode == 0 || sp->mode == 1 || sp->mode == 4 || sp->mode == 6);
     if (nframes == 0) return UVIP_OK;
     UVIP_CHECK_ARG(d_qu && d_qv && d_qr && d_qmin_level && d_qmax_level && d_qdesc && d_nq && d_kx && d_ky && d_octave && d_kdesc && d_nk &&
                    d_taken && d_match && d_counts);

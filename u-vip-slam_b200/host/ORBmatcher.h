@@ -4,6 +4,7 @@
 // SCATTERED back, so Tracking / LocalMapping / LoopClosing stay untouched.  The member templates accept
 // the reference's own FrameKTL / MapPoint types (they only use the members cited below), or mock types in tests.
 #pragma once
+#include <climits>
 #include <cmath>
 #include <cstring>
 #include <algorithm>
@@ -11,6 +12,7 @@
 #include <set>
 #include <stdexcept>
 #include <string>
+#include <type_traits>
 #include <vector>
 #ifdef UVIP_WITH_OPENCV
 #include <opencv2/core/core.hpp>
@@ -172,6 +174,212 @@ public:
             check(uvip_rot_hist_filter(handle_, kept.data(), nq, qa.data(), ka.data(), &nmatches), "uvip_rot_hist_filter");
             for (int q = 0; q < nq; q++) if (match[q] >= 0 && kept[q] < 0) CurrentFrame.mvpMapPoints[match[q]] = static_cast<MapPointT*>(NULL);
         }
+        return nmatches;
+    }
+
+    // ------------------------------------------------------------------------------------------------------------------
+    // The four public overloads of include/ORBmatcher.h:49-72 that no caller of this fork reaches (inherited from ORB-SLAM): kept so
+    // that the header swap drops no member.  WindowSearch and SearchByProjection(F1, F2, ...) run in uvip_search_frame mode 6 (top-2
+    // without levels), SearchByProjection(CurrentFrame, LastFrame, th) in mode 1; SearchForInitialization lets a later keypoint STEAL an
+    // earlier match (:641-665), a dependency the claim table cannot express: its candidates come from the frame's own
+    // GetFeaturesInArea, all candidate distances from one uvip_descriptor_distance call, and the sequential bookkeeping is replayed here.
+    // ------------------------------------------------------------------------------------------------------------------
+protected:
+    // flattened keypoints of a frame for uvip_search_frame
+    template <class FrameT>
+    struct FlatFrame {
+        std::vector<float> kx, ky, ka; std::vector<int32_t> oct; std::vector<unsigned char> kd;
+        explicit FlatFrame(const FrameT& F)
+        {
+            const int nk = (int)F.mvKeysUn.size();
+            kx.resize((size_t)nk); ky.resize((size_t)nk); ka.resize((size_t)nk); oct.resize((size_t)nk); kd.resize((size_t)nk * 32 + 32);
+            for (int i = 0; i < nk; i++) {
+                kx[(size_t)i] = F.mvKeysUn[(size_t)i].pt.x; ky[(size_t)i] = F.mvKeysUn[(size_t)i].pt.y; ka[(size_t)i] = F.mvKeysUn[(size_t)i].angle;
+                oct[(size_t)i] = F.mvKeysUn[(size_t)i].octave;
+                std::memcpy(&kd[(size_t)i * 32], F.mDescriptors.ptr(i), 32);
+            }
+        }
+    };
+    template <class FrameT>
+    uvip_search_params frame_params(const FrameT& F, int mode, int th_dist)
+    {
+        uvip_search_params sp;
+        sp.mode = mode; sp.th_dist = th_dist; sp.ratio = mfNNratio;
+        sp.min_x = (float)F.mnMinX; sp.min_y = (float)F.mnMinY; sp.inv_w = F.mfGridElementWidthInv; sp.inv_h = F.mfGridElementHeightInv;
+        sp.cols = 64; sp.rows = 48;
+        return sp;
+    }
+
+public:
+    // WindowSearch(F1, F2, windowSize, vpMapPointMatches2, minOctave, maxOctave)  (src/ORBmatcher.cc:409-516)
+    template <class FrameT, class MapPointT>
+    int WindowSearch(FrameT& F1, FrameT& F2, int windowSize, std::vector<MapPointT*>& vpMapPointMatches2, int minScaleLevel = -1, int maxScaleLevel = INT_MAX)
+    {
+        ensure();
+        vpMapPointMatches2 = std::vector<MapPointT*>(F2.mvpMapPoints.size(), static_cast<MapPointT*>(NULL));
+        const bool bMinLevel = minScaleLevel > 0, bMaxLevel = maxScaleLevel < INT_MAX;
+        std::vector<float> qu, qv, qr, qa; std::vector<int32_t> ql; std::vector<unsigned char> qd; std::vector<MapPointT*> who;
+        for (size_t i1 = 0; i1 < F1.mvpMapPoints.size(); i1++) {
+            MapPointT* pMP1 = F1.mvpMapPoints[i1];
+            if (!pMP1) continue;
+            if (pMP1->isBad()) continue;
+            const cv::KeyPoint& kp1 = F1.mvKeysUn[i1];
+            const int level1 = kp1.octave;
+            if (bMinLevel && level1 < minScaleLevel) continue;
+            if (bMaxLevel && level1 > maxScaleLevel) continue;
+            qu.push_back(kp1.pt.x); qv.push_back(kp1.pt.y); qr.push_back((float)windowSize); ql.push_back(level1); qa.push_back(kp1.angle);
+            qd.insert(qd.end(), F1.mDescriptors.ptr((int)i1), F1.mDescriptors.ptr((int)i1) + 32);
+            who.push_back(pMP1);
+        }
+        const int nq = (int)who.size(), nk = (int)F2.mvKeysUn.size();
+        if (nq == 0 || nk == 0) return 0;
+        const FlatFrame<FrameT> K(F2);
+        std::vector<int32_t> taken((size_t)nk, -1), match((size_t)nq);
+        uvip_search_params sp = frame_params(F2, 6, TH_HIGH);
+        int nmatches = 0;
+        check(uvip_search_frame(handle_, &sp, qu.data(), qv.data(), qr.data(), ql.data(), ql.data(), qd.data(), nq, K.kx.data(), K.ky.data(), K.oct.data(),
+                                K.kd.data(), nk, taken.data(), match.data(), &nmatches), "uvip_search_frame");
+        if (mbCheckOrientation) check(uvip_rot_hist_filter(handle_, match.data(), nq, qa.data(), K.ka.data(), &nmatches), "uvip_rot_hist_filter");   // :487-513
+        for (int q = 0; q < nq; q++) if (match[(size_t)q] >= 0) vpMapPointMatches2[(size_t)match[(size_t)q]] = who[(size_t)q];
+        return nmatches;
+    }
+
+    // SearchByProjection(F1, F2, windowSize, vpMapPointMatches2)  (src/ORBmatcher.cc:519-596): F1's map points projected with F2's pose
+    template <class FrameT, class MapPointT>
+    int SearchByProjection(FrameT& F1, FrameT& F2, int windowSize, std::vector<MapPointT*>& vpMapPointMatches2)
+    {
+        ensure();
+        vpMapPointMatches2 = F2.mvpMapPoints;
+        const std::set<MapPointT*> spMapPointsAlreadyFound(vpMapPointMatches2.begin(), vpMapPointMatches2.end());
+        float R[3][3], t[3];
+        for (int r = 0; r < 3; r++) { const float* row = F2.mTcw.template ptr<float>(r); for (int c = 0; c < 3; c++) R[r][c] = row[c]; t[r] = row[3]; }
+        std::vector<float> qu, qv, qr; std::vector<int32_t> ql; std::vector<unsigned char> qd; std::vector<MapPointT*> who;
+        for (size_t i1 = 0; i1 < F1.mvpMapPoints.size(); i1++) {
+            MapPointT* pMP1 = F1.mvpMapPoints[i1];
+            if (!pMP1) continue;
+            if (pMP1->isBad() || spMapPointsAlreadyFound.count(pMP1)) continue;
+            const int level1 = F1.mvKeysUn[i1].octave;
+            float X[3], c3[3]; read3(pMP1->GetWorldPos(), X); mul_add3(R, X, t, c3);
+            const float invz = (float)(1.0 / c3[2]);
+            const float u2 = F2.fx * c3[0] * invz + F2.cx, v2 = F2.fy * c3[1] * invz + F2.cy;
+            qu.push_back(u2); qv.push_back(v2); qr.push_back((float)windowSize); ql.push_back(level1);
+            qd.insert(qd.end(), F1.mDescriptors.ptr((int)i1), F1.mDescriptors.ptr((int)i1) + 32);
+            who.push_back(pMP1);
+        }
+        const int nq = (int)who.size(), nk = (int)F2.mvKeysUn.size();
+        if (nq == 0 || nk == 0) return 0;
+        const FlatFrame<FrameT> K(F2);
+        std::vector<int32_t> taken((size_t)nk), match((size_t)nq);
+        for (int i = 0; i < nk; i++) taken[(size_t)i] = vpMapPointMatches2[(size_t)i] ? -2 : -1;
+        uvip_search_params sp = frame_params(F2, 6, TH_HIGH);
+        int nmatches = 0;
+        check(uvip_search_frame(handle_, &sp, qu.data(), qv.data(), qr.data(), ql.data(), ql.data(), qd.data(), nq, K.kx.data(), K.ky.data(), K.oct.data(),
+                                K.kd.data(), nk, taken.data(), match.data(), &nmatches), "uvip_search_frame");
+        for (int q = 0; q < nq; q++) if (match[(size_t)q] >= 0) vpMapPointMatches2[(size_t)match[(size_t)q]] = who[(size_t)q];
+        return nmatches;
+    }
+
+    // SearchByProjection(CurrentFrame, LastFrame, th)  (src/ORBmatcher.cc:1507-1620): the last frame's map points, best-only, rotation histogram
+    template <class FrameT>
+    int SearchByProjection(FrameT& CurrentFrame, const FrameT& LastFrame, const float th)
+    {
+        ensure();
+        typedef typename std::remove_pointer<typename std::remove_reference<decltype(CurrentFrame.mvpMapPoints[0])>::type>::type MapPointT;
+        float R[3][3], t[3];
+        for (int r = 0; r < 3; r++) { const float* row = CurrentFrame.mTcw.template ptr<float>(r); for (int c = 0; c < 3; c++) R[r][c] = row[c]; t[r] = row[3]; }
+        std::vector<float> qu, qv, qr, qa; std::vector<int32_t> qmin, qmax; std::vector<unsigned char> qd; std::vector<MapPointT*> who;
+        for (size_t i = 0; i < LastFrame.mvpMapPoints.size(); i++) {
+            MapPointT* pMP = LastFrame.mvpMapPoints[i];
+            if (!pMP || LastFrame.mvbOutlier[i]) continue;
+            float X[3], c3[3]; read3(pMP->GetWorldPos(), X); mul_add3(R, X, t, c3);
+            const float invzc = (float)(1.0 / c3[2]);
+            const float u = CurrentFrame.fx * c3[0] * invzc + CurrentFrame.cx, v = CurrentFrame.fy * c3[1] * invzc + CurrentFrame.cy;
+            if (u < CurrentFrame.mnMinX || u > CurrentFrame.mnMaxX) continue;
+            if (v < CurrentFrame.mnMinY || v > CurrentFrame.mnMaxY) continue;
+            const int nPredictedOctave = LastFrame.mvKeys[i].octave;
+            qu.push_back(u); qv.push_back(v); qr.push_back(th * CurrentFrame.mvScaleFactors[(size_t)nPredictedOctave]);
+            qmin.push_back(nPredictedOctave - 1); qmax.push_back(nPredictedOctave + 1);
+            qd.insert(qd.end(), LastFrame.mDescriptors.ptr((int)i), LastFrame.mDescriptors.ptr((int)i) + 32);
+            qa.push_back(LastFrame.mvKeysUn[i].angle);
+            who.push_back(pMP);
+        }
+        const int nq = (int)who.size(), nk = (int)CurrentFrame.mvKeysUn.size();
+        if (nq == 0 || nk == 0) return 0;
+        const FlatFrame<FrameT> K(CurrentFrame);
+        std::vector<int32_t> taken((size_t)nk), match((size_t)nq);
+        for (int i = 0; i < nk; i++) taken[(size_t)i] = CurrentFrame.mvpMapPoints[(size_t)i] ? -2 : -1;
+        uvip_search_params sp = frame_params(CurrentFrame, 1, TH_HIGH);
+        int nmatches = 0;
+        check(uvip_search_frame(handle_, &sp, qu.data(), qv.data(), qr.data(), qmin.data(), qmax.data(), qd.data(), nq, K.kx.data(), K.ky.data(), K.oct.data(),
+                                K.kd.data(), nk, taken.data(), match.data(), &nmatches), "uvip_search_frame");
+        for (int q = 0; q < nq; q++) if (match[(size_t)q] >= 0) CurrentFrame.mvpMapPoints[(size_t)match[(size_t)q]] = who[(size_t)q];
+        if (mbCheckOrientation) {
+            std::vector<int32_t> kept(match);
+            check(uvip_rot_hist_filter(handle_, kept.data(), nq, qa.data(), K.ka.data(), &nmatches), "uvip_rot_hist_filter");
+            for (int q = 0; q < nq; q++) if (match[(size_t)q] >= 0 && kept[(size_t)q] < 0) CurrentFrame.mvpMapPoints[(size_t)match[(size_t)q]] = static_cast<MapPointT*>(NULL);
+        }
+        return nmatches;
+    }
+
+    // SearchForInitialization(F1, F2, vbPrevMatched, vnMatches12, windowSize)  (src/ORBmatcher.cc:598-713)
+    template <class FrameT>
+    int SearchForInitialization(FrameT& F1, FrameT& F2, std::vector<cv::Point2f>& vbPrevMatched, std::vector<int>& vnMatches12, int windowSize = 10)
+    {
+        ensure();
+        const int n1 = (int)F1.mvKeysUn.size(), n2 = (int)F2.mvKeysUn.size();
+        vnMatches12 = std::vector<int>((size_t)n1, -1);
+        // candidates of every level-0 keypoint, in the order the reference's loop meets them, and their distances in one device call
+        std::vector<int32_t> cs(1, 0), ci; std::vector<int> qi;
+        for (int i1 = 0; i1 < n1; i1++) {
+            if (F1.mvKeysUn[(size_t)i1].octave > 0) continue;
+            const std::vector<size_t> vIndices2 = F2.GetFeaturesInArea(vbPrevMatched[(size_t)i1].x, vbPrevMatched[(size_t)i1].y, (float)windowSize, 0, 0);
+            if (vIndices2.empty()) continue;
+            for (size_t k = 0; k < vIndices2.size(); k++) ci.push_back((int32_t)vIndices2[k]);
+            cs.push_back((int32_t)ci.size()); qi.push_back(i1);
+        }
+        const int npairs = (int)ci.size();
+        std::vector<int32_t> dist((size_t)npairs + 1);
+        if (npairs) {
+            std::vector<unsigned char> a((size_t)npairs * 32), b((size_t)npairs * 32);
+            for (size_t q = 0; q < qi.size(); q++)
+                for (int j = cs[q]; j < cs[q + 1]; j++) {
+                    std::memcpy(&a[(size_t)j * 32], F1.mDescriptors.ptr(qi[q]), 32);
+                    std::memcpy(&b[(size_t)j * 32], F2.mDescriptors.ptr(ci[(size_t)j]), 32);
+                }
+            check(uvip_descriptor_distance(handle_, a.data(), b.data(), npairs, dist.data()), "uvip_descriptor_distance");
+        }
+        // the sequential part, as written at :620-680 (a later keypoint with a strictly smaller distance steals the match)
+        int nmatches = 0;
+        std::vector<int> vMatchedDistance((size_t)n2, INT_MAX), vnMatches21((size_t)n2, -1), accepted;   // accepted: i1 in rotHist push order
+        std::vector<float> a1, a2;                                                        // angle pair of every accepted match, at acceptance
+        for (size_t q = 0; q < qi.size(); q++) {
+            const int i1 = qi[q];
+            int bestDist = INT_MAX, bestDist2 = INT_MAX, bestIdx2 = -1;
+            for (int j = cs[q]; j < cs[q + 1]; j++) {
+                const int i2 = ci[(size_t)j], d = dist[(size_t)j];
+                if (vMatchedDistance[(size_t)i2] <= d) continue;
+                if (d < bestDist) { bestDist2 = bestDist; bestDist = d; bestIdx2 = i2; }
+                else if (d < bestDist2) bestDist2 = d;
+            }
+            if (bestDist <= TH_LOW && bestDist < (float)bestDist2 * mfNNratio) {
+                if (vnMatches21[(size_t)bestIdx2] >= 0) { vnMatches12[(size_t)vnMatches21[(size_t)bestIdx2]] = -1; nmatches--; }
+                vnMatches12[(size_t)i1] = bestIdx2; vnMatches21[(size_t)bestIdx2] = i1; vMatchedDistance[(size_t)bestIdx2] = bestDist;
+                nmatches++;
+                if (mbCheckOrientation) { accepted.push_back(i1); a1.push_back(F1.mvKeysUn[(size_t)i1].angle); a2.push_back(F2.mvKeysUn[(size_t)bestIdx2].angle); }
+            }
+        }
+        if (mbCheckOrientation && !accepted.empty()) {
+            // the histogram counts every ACCEPTED pair, stolen ones included (their bin entry stays, :667-676); only matches that are
+            // still valid are removed afterwards (:694-698)
+            std::vector<int32_t> m(accepted.size());
+            for (size_t k = 0; k < m.size(); k++) m[k] = (int32_t)k;
+            int kept = 0;
+            check(uvip_rot_hist_filter(handle_, m.data(), (int)m.size(), a1.data(), a2.data(), &kept), "uvip_rot_hist_filter");
+            for (size_t j = 0; j < accepted.size(); j++)
+                if (m[j] < 0 && vnMatches12[(size_t)accepted[j]] >= 0) { vnMatches12[(size_t)accepted[j]] = -1; nmatches--; }
+        }
+        for (size_t i1 = 0; i1 < vnMatches12.size(); i1++)                                // :708-710
+            if (vnMatches12[i1] >= 0) vbPrevMatched[i1] = F2.mvKeysUn[(size_t)vnMatches12[i1]].pt;
         return nmatches;
     }
 
