@@ -603,13 +603,14 @@ k_fast2(const CUtensorMap* __restrict__ tmaps, const unsigned* __restrict__ tile
         int* __restrict__ cand_count, int* __restrict__ status, int nframes, const __grid_constant__ Plan P)
 {
     extern __shared__ __align__(128) unsigned char s_f2[];
-    __shared__ __align__(8) uint64_t s_full[F2_STAGES];
-    __shared__ int s_done[F2_STAGES], s_loads[F2_STAGES], s_next, s_lock;
-    __shared__ volatile int s_issued;
+    __shared__ __align__(8) uint64_t s_full[F2_STAGES], s_ann[F2_RING];
+    __shared__ int s_loads[F2_STAGES], s_next, s_lock, s_issued;
     // announcement of the CTA's tile number q (slot q & 7): which launch tile it is (-1: the launch has no more), where it lands and the
-    // parity of that buffer's mbarrier phase; s_rseq is written last
-    __shared__ volatile int s_rseq[F2_RING], s_rtile[F2_RING], s_rbuf[F2_RING];
-    __shared__ volatile unsigned s_rte[F2_RING];          // the tile's table entry (level | cell row << 4 | first cell column << 16)
+    // parity of that buffer's mbarrier phase.  The issuing thread writes the fields and arrives on s_ann[slot] (release); the four warps
+    // that take the tile's cells wait on it (acquire) with the parity of the slot's use number q / F2_RING.  s_rdone counts the cells
+    // of the slot's tile that are done: at F2_CW the tile's buffer is requested again, and the slot may be announced again.
+    __shared__ int s_rdone[F2_RING], s_rtile[F2_RING], s_rbuf[F2_RING];
+    __shared__ unsigned s_rte[F2_RING];                   // the tile's table entry (level | cell row << 4 | first cell column << 16)
     const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
     const int irow = IROWT ? IROWT : P.f_irow;
     const int imgbytes = irow * P.f2_irows, imgstride = (imgbytes + 127) & ~127;
@@ -621,26 +622,29 @@ k_fast2(const CUtensorMap* __restrict__ tmaps, const unsigned* __restrict__ tile
     // in tile order and the end-of-launch test rely on.
     auto issue = [&](int buf) {
         while (atomicCAS(&s_lock, 0, 1) != 0) __nanosleep(20);
-        const int q = s_issued; s_issued = q + 1;
+        const int q = atomicAdd(&s_issued, 1);
         const int t = atomicAdd(tile_ctr, 1);
-        __threadfence_block();
         atomicExch(&s_lock, 0);
         const int slot = q & (F2_RING - 1);
-        if (t >= T) { s_rtile[slot] = -1; __threadfence_block(); s_rseq[slot] = q; return; }
+        // the slot's previous tile (q - F2_RING) must be complete, i.e. its four warps have read the announcement.  With three buffers
+        // a tile that far behind is still running only if one cell outlasts seven whole tiles: the wait is there for the proof.
+        while (atomicCAS(&s_rdone[slot], F2_CW, 0) != F2_CW) __nanosleep(20);
+        if (t >= T) { s_rtile[slot] = -1; mbar_arrive(&s_ann[slot]); return; }
         const int f = P.f2_tiles > 1 ? (int)__umulhi((unsigned)t, P.f2_rcp_tiles) : t, tl = t - f * P.f2_tiles;
         const unsigned te = __ldg(tile_tab + tl);
         const LevelInfo& L = P.lv[te & 15];
         const int TX0 = EDGE + (int)(te >> 16) * L.wcell, TY0 = EDGE + (int)((te >> 4) & 0xFFF) * L.hcell;
         const int ax0 = ((((TX0 & ~3) - 4 + EDGE) & ~15) - EDGE), ay0 = TY0 - 3;
-        const int par = s_loads[buf] & 1; s_loads[buf]++;
-        s_rtile[slot] = f; s_rte[slot] = te; s_rbuf[slot] = buf | (par << 8); __threadfence_block(); s_rseq[slot] = q;
+        const int par = atomicAdd(&s_loads[buf], 1) & 1;
+        s_rtile[slot] = f; s_rte[slot] = te; s_rbuf[slot] = buf | (par << 8);
+        mbar_arrive(&s_ann[slot]);
         mbar_arrive_expect_tx(&s_full[buf], (unsigned)imgbytes);
         tma_load_3d(s_f2 + (size_t)buf * imgstride, tmaps + 3 * MAXLEV + (te & 15), ax0 + EDGE, ay0 + EDGE, f, &s_full[buf]);
     };
     if (tid == 0) {
-        for (int k = 0; k < F2_STAGES; k++) { mbar_init(&s_full[k], 1); s_done[k] = 0; s_loads[k] = 0; }
+        for (int k = 0; k < F2_STAGES; k++) { mbar_init(&s_full[k], 1); s_loads[k] = 0; }
+        for (int k = 0; k < F2_RING; k++) { mbar_init(&s_ann[k], 1); s_rdone[k] = F2_CW; }
         mbar_fence_init();
-        for (int k = 0; k < F2_RING; k++) s_rseq[k] = -1;
         s_next = 0; s_lock = 0; s_issued = 0;
         for (int k = 0; k < F2_STAGES; k++) issue(k);
     }
@@ -668,7 +672,8 @@ k_fast2(const CUtensorMap* __restrict__ tmaps, const unsigned* __restrict__ tile
         n = __shfl_sync(0xFFFFFFFFu, n, 0);
         const int q = n >> 2, cj = n & 3, slot = q & (F2_RING - 1);
         static_assert(F2_CW == 4, "four cells per tile");
-        while (s_rseq[slot] != q) __nanosleep(64);         // the tile has not been announced yet (its buffer is still busy)
+        static_assert((F2_RING & (F2_RING - 1)) == 0 && F2_RING > F2_STAGES + 2, "ring of announcements");
+        mbar_wait(&s_ann[slot], (unsigned)(q / F2_RING) & 1u);   // until the tile is announced (its buffer may still be busy)
         const int f = s_rtile[slot];                       // the tile's frame
         if (f < 0) break;                                  // the launch has no more tiles (cells are handed out in tile order)
         const int bp = s_rbuf[slot], b = bp & 255;
@@ -818,7 +823,7 @@ k_fast2(const CUtensorMap* __restrict__ tmaps, const unsigned* __restrict__ tile
                         if (cb) s_score[yb * srow + xb] = (uint8_t)scb;
                         const unsigned bala = __ballot_sync(0xFFFFFFFFu, ca), balb = __ballot_sync(0xFFFFFFFFu, cb);
                         const int ia = ncw + __popc(bala & ltmask), ib = ncw + __popc(bala) + __popc(balb & ltmask);
-                        // (every lane has read its two entries of this step before the ballots; slots below j0 + 64 are free)
+                        __syncwarp();                      // every lane has read its two entries of this step: slots below j0 + 64 are free
                         if (ca) cq[ia] = (unsigned short)ea;
                         if (cb) cq[ib] = (unsigned short)eb;
                         ncw += __popc(bala) + __popc(balb);
@@ -901,8 +906,7 @@ k_fast2(const CUtensorMap* __restrict__ tmaps, const unsigned* __restrict__ tile
         __syncwarp();
         if (lane == 0) {
             __threadfence_block();
-            if (atomicAdd(&s_done[b], 1) == F2_CW - 1) {
-                s_done[b] = 0;
+            if (atomicAdd(&s_rdone[slot], 1) == F2_CW - 1) {
                 fence_proxy_async_smem();                  // generic-proxy reads of the buffer before the async-proxy overwrite
                 issue(b);
             }
