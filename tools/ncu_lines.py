@@ -29,7 +29,7 @@ lines = []
 for cb in sorted(os.listdir(tmp)):
     if not cb.endswith('.cubin') or '-' in cb:
         continue
-    asm = subprocess.run(['nvdisasm', '--print-line-info', os.path.join(tmp, cb)], capture_output=True, text=True).stdout
+    asm = subprocess.run(['nvdisasm', '--print-line-info-inline', os.path.join(tmp, cb)], capture_output=True, text=True).stdout
     cur = None; line = ('', 0); fn = None
     for ln in asm.split('\n'):
         m = re.match(r'\s*\.section\s+\.text\.(\S+?),', ln)
@@ -42,7 +42,9 @@ for cb in sorted(os.listdir(tmp)):
             continue
         m = re.search(r'//## File "(.*?)", line (\d+)', ln)
         if m:
-            line = (os.path.basename(m.group(1)), int(m.group(2))); continue
+            # an inlined intrinsic / helper is charged to the outermost call site ("... inlined at <file>, line N")
+            mi = re.findall(r'inlined at "(.*?)", line (\d+)', ln)
+            line = (os.path.basename(mi[-1][0]), int(mi[-1][1])) if mi else (os.path.basename(m.group(1)), int(m.group(2))); continue
         if re.match(r'\s*/\*[0-9a-f]{4,}\*/\s+\S', ln):
             cur.append(line)
 best = None

@@ -24,7 +24,10 @@ case "$what" in
   full)
     stage=${1:?stage name: pyramid fast quadtree blur select describe knn2}; tag=${2:-r2}
     case "$stage" in knn2|search_window) expr="uvip_${stage}/";; *) expr="uvip_extract_group/uvip_${stage}/";; esac
-    UVIP_SERIAL=1 ncu --set full --import-source on --clock-control none --nvtx --nvtx-include "$expr" -s 1 -c 8 \
+    # the stage's kernels of ONE step (the second: the first is cold); reports of eight launches are 15-25 MB each and gpurun brings
+    # back 64 MiB at most
+    case "$stage" in pyramid) n=8;; *) n=1;; esac
+    UVIP_SERIAL=1 ncu --set full --import-source on --clock-control none --nvtx --nvtx-include "$expr" -s $n -c $n \
         -o gpurun_out/${tag}_${stage} -f $BENCH > gpurun_out/${tag}_${stage}.log 2>&1
     python tools/ncu_summary.py gpurun_out/${tag}_${stage}.ncu-rep
     ;;

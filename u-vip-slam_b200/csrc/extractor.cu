@@ -588,14 +588,23 @@ k_fast(const CUtensorMap* __restrict__ tmaps, const unsigned* __restrict__ tile_
 // score, two pixels per lane packed 16x2 on VIMNMX3 -> D strict 3x3 NMS inside the cell, one global reservation per warp and cell.
 // --------------------------------------------------------------------------------------------------------
 constexpr int F2_IROW = 160;                 // row stride of the staged tile in the common case (4 cells of <= 33 px + halo + alignment)
-constexpr int F2_PQ = 1024;                  // candidate-pixel queue of a warp (flushed through the score stage when nearly full)
+#ifndef F2_PQ_
+#define F2_PQ_ 1024
+#endif
+constexpr int F2_PQ = F2_PQ_;                  // candidate-pixel queue of a warp (flushed through the score stage when nearly full)
 __constant__ unsigned c_rcp32[33];           // ceil(2^32 / n), n = 1..32 (groups per cell row)
 
 constexpr int F2_CW = 4;                     // cells per tile: one row of four (a buffer is recycled as soon as its four cells are done)
-constexpr int F2_STAGES = 3, F2_RING = 8;    // staged tiles per CTA; ring of tile announcements (> F2_STAGES, power of two)
+#ifndef F2_STAGES_
+#define F2_STAGES_ 3
+#endif
+constexpr int F2_STAGES = F2_STAGES_, F2_RING = 8;    // staged tiles per CTA; ring of tile announcements (> F2_STAGES, power of two)
 
 #ifndef F2_MINB
 #define F2_MINB 4
+#endif
+#ifndef F2_PARK_NS
+#define F2_PARK_NS 2000
 #endif
 template <int IROWT>                         // row stride of the staged tile in bytes; 0 = take it from the plan at run time
 __global__ void __launch_bounds__(256, F2_MINB)
@@ -673,7 +682,7 @@ k_fast2(const CUtensorMap* __restrict__ tmaps, const unsigned* __restrict__ tile
         const int q = n >> 2, cj = n & 3, slot = q & (F2_RING - 1);
         static_assert(F2_CW == 4, "four cells per tile");
         static_assert((F2_RING & (F2_RING - 1)) == 0 && F2_RING > F2_STAGES + 2, "ring of announcements");
-        mbar_wait(&s_ann[slot], (unsigned)(q / F2_RING) & 1u);   // until the tile is announced (its buffer may still be busy)
+        mbar_wait_parked(&s_ann[slot], (unsigned)(q / F2_RING) & 1u, F2_PARK_NS);   // until the tile is announced (its buffer may still be busy)
         const int f = s_rtile[slot];                       // the tile's frame
         if (f < 0) break;                                  // the launch has no more tiles (cells are handed out in tile order)
         const int bp = s_rbuf[slot], b = bp & 255;
