@@ -1439,7 +1439,12 @@ __device__ __forceinline__ void sincos_as_float(float xf, float* s_out, float* c
 #define DESC_KPW_ 4
 #endif
 constexpr int DESC_WARPS = 8, DESC_KPW = DESC_KPW_;           // warps per CTA, keypoints per warp
-constexpr int DESC_PR = 18, DESC_PWORDS = 10;                 // staged patch: rows / columns -18..18 (|pattern coordinate| <= 13, rotated), 40-byte rows
+constexpr int DESC_AROW = 48;                                  // bytes per staged row of the IC_Angle patch (31 columns from a 16-byte aligned start)
+constexpr int DESC_PR = 18, DESC_PROW = 80;                   // staged patch: rows / columns -18..18 (|pattern coordinate| <= 13, rotated): 64 bytes per row from a
+                                                              // 16-byte aligned start, rows 80 bytes apart (20 words: the random byte gathers spread over all banks)
+constexpr int DESC_PATCH_BYTES = (2 * DESC_PR + 1) * DESC_PROW, DESC_APATCH_BYTES = (2 * HALF_PATCH + 1) * DESC_AROW;
+constexpr int DESC_SM_WU = 512 * 8, DESC_SM_PATCH = DESC_SM_WU + 8 * 32 * 4, DESC_SM_APATCH = DESC_SM_PATCH + DESC_WARPS * DESC_PATCH_BYTES,
+              DESC_SMEM = DESC_SM_APATCH + DESC_WARPS * 2 * DESC_APATCH_BYTES;      // dynamic shared memory of k_describe
 #ifndef DESC_MINB
 #define DESC_MINB 4          // 64 registers: four CTAs per SM (the kernel is latency-bound; measured 0.37 -> 0.27 ms at batch 256)
 #endif
@@ -1458,14 +1463,29 @@ k_describe(const uint8_t* __restrict__ pyr, const uint8_t* __restrict__ blur, co
     if ((int)(blockIdx.x * DESC_WARPS * DESC_KPW) >= n) return;          // whole CTA idle (uniform)
     // pattern in shared memory, transposed [k][lane]: lane reads its 16 points (descriptor byte `lane`) conflict-free,
     // which keeps the kernel at 64 registers (occupancy matters more than the 16 LDS: the kernel is latency-bound)
-    __shared__ float2 s_pat[512];
-    __shared__ unsigned s_patch[DESC_WARPS][(2 * DESC_PR + 1) * DESC_PWORDS];
+    extern __shared__ __align__(16) unsigned char s_desc[];
+    float2* s_pat = reinterpret_cast<float2*>(s_desc);                                           // [512]
+    unsigned (*s_wu)[32] = reinterpret_cast<unsigned (*)[32]>(s_desc + DESC_SM_WU);              // [8][32]
+    unsigned char* s_patch_w = s_desc + DESC_SM_PATCH + (threadIdx.x >> 5) * DESC_PATCH_BYTES;   // the warp's blurred patch
+    unsigned char* s_apatch_w = s_desc + DESC_SM_APATCH + (threadIdx.x >> 5) * 2 * DESC_APATCH_BYTES;   // its two IC_Angle patches
+    // IC_Angle weights of disc row v = lane - 15: byte b of word j stands for column u = 4 j + b - 15 and holds u + 16 (1..31) where
+    // |u| <= umax[|v|], 0 elsewhere (and everywhere for lane 31).  sum (u + 16) I - 16 sum I = sum u I; the 0/1 weights of the row
+    // sum are the non-zero bytes of the same word
     for (int i = threadIdx.x; i < 512; i += DESC_WARPS * 32) s_pat[i] = __ldg(pat_t + i);
+    {
+        const int j = threadIdx.x >> 5, ln = threadIdx.x & 31, v = ln - HALF_PATCH;
+        const int vmr = ln < 31 ? c_umax[v < 0 ? -v : v] : -1;
+        unsigned wu = 0;
+#pragma unroll
+        for (int b = 0; b < 4; b++) {
+            const int uu = 4 * j + b - HALF_PATCH;
+            if ((uu < 0 ? -uu : uu) <= vmr) wu |= (unsigned)(uu + 16) << (8 * b);
+        }
+        s_wu[j][ln] = wu;
+    }
+    static_assert(DESC_WARPS == 8, "one warp of the CTA per weight word");
     __syncthreads();
     if (slot0 >= n) return;
-    const int u = lane - HALF_PATCH;
-    const int prr = lane / DESC_PWORDS, pw = lane - prr * DESC_PWORDS;     // patch staging: lane -> (row mod 3, word)
-    const int vm = lane < 31 ? c_umax[u < 0 ? -u : u] : -1;       // disc rows |v| <= vm belong to column u (umax is symmetric)
     // the warp's keypoints: lane i fetches selection entry and winner word of keypoint i, so that the two dependent global loads in
     // front of every keypoint's pixel loads are paid once per warp
     static_assert(DESC_KPW <= 32, "one lane per keypoint of the warp");
@@ -1474,60 +1494,98 @@ k_describe(const uint8_t* __restrict__ pyr, const uint8_t* __restrict__ blur, co
         my_e = sel[(size_t)f * sel_cap + slot0 + lane];
         if ((my_e >> 16) != 0xFFFFu) my_w = winners[(size_t)f * P.kp_per_frame + P.lv[my_e >> 16].kp_off + (my_e & 0xFFFF)];
     }
-#pragma unroll 1
-    for (int i = 0; i < DESC_KPW; i++) {
+    // where keypoint i of the warp is (its level and integer position); false behind the warp's last keypoint
+    auto locate = [&](int i, unsigned& e, unsigned& wv, int& level, int& cx, int& cy) -> bool {
         const int slot = slot0 + i;
-        if (slot >= n || slot >= out_cap) break;
-        const unsigned e = __shfl_sync(0xFFFFFFFFu, my_e, i), wv = __shfl_sync(0xFFFFFFFFu, my_w, i);
-        int level, cx, cy; float response, size, ox, oy; int octave, class_id;
+        if (i >= DESC_KPW || slot >= n || slot >= out_cap) return false;
+        e = __shfl_sync(0xFFFFFFFFu, my_e, i); wv = __shfl_sync(0xFFFFFFFFu, my_w, i);
         if ((e >> 16) == 0xFFFFu) {                // incoming level-0 keypoint (ComputeKeyPointsCopy, :523-534)
             const uvip_keypoint k = incoming[e & 0xFFFF];
             level = 0; cx = __float2int_rn(k.x); cy = __float2int_rn(k.y);
+        } else { level = e >> 16; cx = wv & 0xFFF; cy = (wv >> 12) & 0xFFF; }
+        return true;
+    };
+    // IC_Angle patch of a keypoint: rows cy-15..cy+15 of the UNBLURRED level, 48 bytes each from the 16-byte aligned column at or below
+    // cx-15, staged by three 16-byte asynchronous copies per lane into one of the warp's two buffers (committed as one cp.async group)
+    auto stage_angle_patch = [&](int level, int cx, int cy, int buf) {
+        const LevelInfo& L = P.lv[level];
+        const int ps = L.pstride;
+        const unsigned char* src = pyr + (size_t)f * P.frame_bytes + L.poff + (size_t)EDGE * ps + EDGE + (ptrdiff_t)(cy - HALF_PATCH) * ps + ((cx - HALF_PATCH) & ~15);
+        const unsigned dst = smem_u32(s_apatch_w + buf * DESC_APATCH_BYTES);
+#pragma unroll
+        for (int it = 0; it < 3; it++) {
+            const int idx = it * 32 + lane, row = idx / 3, ch = idx - 3 * row;
+            if (idx < (2 * HALF_PATCH + 1) * 3)
+                asm volatile("cp.async.cg.shared.global [%0], [%1], 16;" ::"r"(dst + row * DESC_AROW + ch * 16), "l"(src + (ptrdiff_t)row * ps + ch * 16) : "memory");
+        }
+    };
+    unsigned e = 0, wv = 0; int level = 0, cx = 0, cy = 0;
+    bool have = locate(0, e, wv, level, cx, cy);
+    if (have) stage_angle_patch(level, cx, cy, 0);
+    asm volatile("cp.async.commit_group;" ::: "memory");
+#pragma unroll 1
+    for (int i = 0; i < DESC_KPW && have; i++) {
+        const int slot = slot0 + i;
+        float response, size, ox, oy; int octave, class_id;
+        if ((e >> 16) == 0xFFFFu) {
+            const uvip_keypoint k = incoming[e & 0xFFFF];
             response = k.response; size = k.size; ox = k.x; oy = k.y; octave = k.octave; class_id = k.class_id;
         } else {
-            level = e >> 16;
-            const unsigned w = wv;
-            cx = w & 0xFFF; cy = (w >> 12) & 0xFFF;
-            response = (float)(w >> 24); size = P.lv[level].size; octave = level; class_id = -1;
+            response = (float)(wv >> 24); size = P.lv[level].size; octave = level; class_id = -1;
             ox = (float)cx; oy = (float)cy;
             if (level != 0) { ox = __fmul_rn(ox, P.lv[level].scale); oy = __fmul_rn(oy, P.lv[level].scale); }   // :951-957
         }
         const LevelInfo& L = P.lv[level];
         const int ps = L.pstride;
         const size_t plane = (size_t)f * P.frame_bytes + L.poff + (size_t)EDGE * ps + EDGE;
-        // The 512 rotated pattern points lie within +-18 px of the keypoint (|pattern| <= 13 per axis).  The 37 x 40-byte blurred
-        // patch is staged in shared memory by 13 asynchronous 4-byte copies per lane (cp.async: no registers, in flight during the
+        // The 512 rotated pattern points lie within +-18 px of the keypoint (|pattern| <= 13 per axis).  The 37 x 64-byte blurred
+        // patch is staged in shared memory by 5 asynchronous 16-byte copies per lane (cp.async: no registers, in flight during the
         // whole orientation phase); the 32 byte gathers per lane then cost a few bank-conflict cycles each instead of a fully
         // divergent trip through the L1 tag stage and a 64-bit address each.
         // (detected keypoints are >= 16 px inside the image.  An incoming level-0 keypoint may lie anywhere inside it: the full 16-px
         // ring of level 0 is materialised for such calls (k_ring16), which covers every point at least 2 px inside the image exactly
         // as the reference's padded buffer does; closer than 2 px the reference's own pattern reads leave its buffer row — undefined
-        // there — and the staged centre is moved to 2 px here.  A staged row is 40 bytes from an aligned start >= cx - 21: it may
-        // run past column w + 16 into the row padding / the next row, which is allocated memory that no gather touches.)
+        // there — and the staged centre is moved to 2 px here.  A staged row is 64 bytes from an aligned start >= cx - 33: it may
+        // run past column w + 16 into the row padding / the next row, which is allocated memory that no gather touches; the buffers
+        // carry 4 KB of slack behind the last plane.)
         const int cxs = min(max(cx, 2), L.w - 3), cys = min(max(cy, 2), L.h - 3);
         {
-            const int xs = (cxs - DESC_PR) & ~3;                                  // word-aligned first column (planes are 16 B aligned)
-            const unsigned* src = reinterpret_cast<const unsigned*>(blur + plane + (ptrdiff_t)(cys - DESC_PR) * ps + xs) + prr * (ps >> 2) + pw;
-            const unsigned dsts = smem_u32(s_patch[threadIdx.x >> 5] + prr * DESC_PWORDS + pw);
+            const int xs = (cxs - DESC_PR) & ~15;                                 // 16-byte aligned first column (planes are 16 B aligned)
+            const unsigned char* src = blur + plane + (ptrdiff_t)(cys - DESC_PR + (lane >> 2)) * ps + xs + (lane & 3) * 16;
+            const unsigned dsts = smem_u32(s_patch_w) + (lane >> 2) * DESC_PROW + (lane & 3) * 16;
             __syncwarp();                                  // the previous keypoint's gathers are done
-            if (lane < 3 * DESC_PWORDS) {
 #pragma unroll
-                for (int it = 0; it < 13; it++)
-                    if (3 * it + prr < 2 * DESC_PR + 1)
-                        asm volatile("cp.async.ca.shared.global [%0], [%1], 4;" ::"r"(dsts + it * 3 * DESC_PWORDS * 4), "l"(src + it * 3 * (ps >> 2)) : "memory");
-            }
+            for (int it = 0; it < 5; it++)                 // 37 rows x 4 chunks of 16 bytes, 32 chunks (8 rows) per step
+                if (it < 4 || lane < (2 * DESC_PR + 1 - 32) * 4)
+                    asm volatile("cp.async.cg.shared.global [%0], [%1], 16;" ::"r"(dsts + it * 8 * DESC_PROW), "l"(src + (ptrdiff_t)it * 8 * ps) : "memory");
+            asm volatile("cp.async.commit_group;" ::: "memory");
         }
-        // ---- IC_Angle: lane u sums column u of the radius-15 disc; all row loads are issued before the first use
+        // the next keypoint's IC_Angle patch goes into the other buffer while this keypoint is worked on
+        unsigned ne = 0, nwv = 0; int nlevel = 0, ncx = 0, ncy = 0;
+        const bool nhave = locate(i + 1, ne, nwv, nlevel, ncx, ncy);
+        if (nhave) stage_angle_patch(nlevel, ncx, ncy, (i + 1) & 1);
+        asm volatile("cp.async.commit_group;" ::: "memory");
+        asm volatile("cp.async.wait_group 2;" ::: "memory");       // everything but this keypoint's blurred patch and the next angle patch
+        __syncwarp();
+        // ---- IC_Angle: lane r sums row v = r - 15 of the radius-15 disc.  The row's 31 pixels lie in 9 aligned words of the staged
+        //      patch; funnel shifts bring column -15 to byte 0, then sum u I and the row sum are one IDP.4A each per word
         int m10 = 0, m01 = 0;
         {
-            const uint8_t* p = pyr + plane + (ptrdiff_t)(cy - HALF_PATCH) * ps + (cx + u);
-            int vals[2 * HALF_PATCH + 1];
-#pragma unroll
-            for (int v = -HALF_PATCH; v <= HALF_PATCH; v++) { vals[v + HALF_PATCH] = ((v < 0 ? -v : v) <= vm) ? (int)__ldg(p) : 0; p += ps; }
-            int colsum = 0;
-#pragma unroll
-            for (int v = -HALF_PATCH; v <= HALF_PATCH; v++) { colsum += vals[v + HALF_PATCH]; m01 += v * vals[v + HALF_PATCH]; }
-            m10 = u * colsum;
+            const int x0 = cx - HALF_PATCH;
+            // the lane's row as three 16-byte loads (rows are 48 bytes apart: conflict-free per quarter warp); which 9 of the 12 words
+            // hold the 31 columns depends on the keypoint only, so the choice is a warp-uniform branch
+            const uint4* rp = reinterpret_cast<const uint4*>(s_apatch_w + (i & 1) * DESC_APATCH_BYTES + min(lane, 2 * HALF_PATCH) * DESC_AROW);
+            const uint4 q0 = rp[0], q1 = rp[1], q2 = rp[2];
+            const unsigned w[12] = {q0.x, q0.y, q0.z, q0.w, q1.x, q1.y, q1.z, q1.w, q2.x, q2.y, q2.z, q2.w};
+            const int sh = (x0 & 3) * 8;
+            unsigned wsum = 0, rowsum = 0;
+#define IC_ROW(WO) { _Pragma("unroll") for (int j = 0; j < 8; j++) { \
+                const unsigned x = __funnelshift_r(w[WO + j], w[WO + j + 1], sh), wt = s_wu[j][lane]; \
+                wsum = __dp4a(wt, x, wsum); rowsum = __dp4a(((wt + 0x7F7F7F7Fu) >> 7) & 0x01010101u, x, rowsum); } }
+            switch ((x0 & 15) >> 2) { case 0: IC_ROW(0) break; case 1: IC_ROW(1) break; case 2: IC_ROW(2) break; default: IC_ROW(3) break; }
+#undef IC_ROW
+            m10 = (int)wsum - 16 * (int)rowsum;
+            m01 = (lane - HALF_PATCH) * (int)rowsum;
         }
 #pragma unroll
         for (int o = 16; o > 0; o >>= 1) { m10 += __shfl_xor_sync(0xFFFFFFFFu, m10, o); m01 += __shfl_xor_sync(0xFFFFFFFFu, m01, o); }
@@ -1536,9 +1594,9 @@ k_describe(const uint8_t* __restrict__ pyr, const uint8_t* __restrict__ blur, co
         const float factorPI = (float)(3.14159265358979323846 / 180.f);
         float a, b;
         sincos_as_float(__fmul_rn(angle, factorPI), &b, &a);
-        asm volatile("cp.async.wait_all;" ::: "memory");
-        __syncwarp();                                      // the staged patch is complete and visible to every lane
-        const uint8_t* cb = reinterpret_cast<const uint8_t*>(s_patch[threadIdx.x >> 5]) + DESC_PR * (4 * DESC_PWORDS) + DESC_PR + ((cxs - DESC_PR) & 3);
+        asm volatile("cp.async.wait_group 1;" ::: "memory");       // this keypoint's blurred patch has landed
+        __syncwarp();                                      // ... and is visible to every lane
+        const uint8_t* cb = s_patch_w + DESC_PR * DESC_PROW + DESC_PR + ((cxs - DESC_PR) & 15);
         unsigned val = 0;
 #pragma unroll
         for (int k = 0; k < 8; k++) {
@@ -1546,7 +1604,7 @@ k_describe(const uint8_t* __restrict__ pyr, const uint8_t* __restrict__ blur, co
             const float x0 = p0.x, y0 = p0.y, x1 = p1.x, y1 = p1.y;
             const int r0 = __float2int_rn(__fadd_rn(__fmul_rn(x0, b), __fmul_rn(y0, a))), q0 = __float2int_rn(__fsub_rn(__fmul_rn(x0, a), __fmul_rn(y0, b)));
             const int r1 = __float2int_rn(__fadd_rn(__fmul_rn(x1, b), __fmul_rn(y1, a))), q1 = __float2int_rn(__fsub_rn(__fmul_rn(x1, a), __fmul_rn(y1, b)));
-            const int t0 = cb[r0 * (4 * DESC_PWORDS) + q0], t1 = cb[r1 * (4 * DESC_PWORDS) + q1];
+            const int t0 = cb[r0 * DESC_PROW + q0], t1 = cb[r1 * DESC_PROW + q1];
             val |= (unsigned)(t0 < t1) << k;
         }
         desc[((size_t)f * out_cap + slot) * 32 + lane] = (uint8_t)val;
@@ -1555,6 +1613,7 @@ k_describe(const uint8_t* __restrict__ pyr, const uint8_t* __restrict__ blur, co
             o.x = ox; o.y = oy; o.size = size; o.angle = angle; o.response = response; o.octave = octave; o.class_id = class_id;
             kps[(size_t)f * out_cap + slot] = o;
         }
+        have = nhave; e = ne; wv = nwv; level = nlevel; cx = ncx; cy = ncy;
     }
 }
 
@@ -2132,6 +2191,7 @@ static int ensure_plan(uvip_extractor* ex, int w, int h)
     if (ex->inflight) { set_last_error("frame geometry changes to %dx%d while a submitted batch is in flight: wait for its ticket first", w, h); return UVIP_ERR_ARG; }
     UVIP_CUDA(cudaDeviceSynchronize());
     UVIP_CUDA(cudaFuncSetAttribute(k_quadtree, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)qt_smem_bytes(P.node_cap)));
+    UVIP_CUDA(cudaFuncSetAttribute(k_describe, cudaFuncAttributeMaxDynamicSharedMemorySize, DESC_SMEM));
     UVIP_CUDA(cudaFuncSetAttribute(k_fast, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)fast_smem_bytes(P)));
     {
         const size_t sm2 = fast2_smem_bytes(P, P.f_irow);
@@ -2288,7 +2348,7 @@ static int enqueue_group(uvip_extractor* ex, const uint8_t* d_frames, int nframe
     PROF_MARK(5);
     {
     NvtxRange nv("uvip_describe");
-    k_describe<<<dim3(div_up(slots, DESC_WARPS * DESC_KPW), nframes), DESC_WARPS * 32, 0, st>>>(
+    k_describe<<<dim3(div_up(slots, DESC_WARPS * DESC_KPW), nframes), DESC_WARPS * 32, DESC_SMEM, st>>>(
         pyr, blur, ex->winners.as<unsigned>(), ex->sel.as<unsigned>(), ex->nsel.as<int>(), ex->sel_cap,
         ex->incoming.as<uvip_keypoint>(), ex->pat_t.as<float2>(), d_kps, d_desc, d_n_out, out_cap, ex->status.as<int>(), P);
     ex->launches++;
