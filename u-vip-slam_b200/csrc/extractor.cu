@@ -58,6 +58,7 @@ struct Plan {
     // k_fast2 (one warp per cell): per-warp score map (f2_srow x f2_srows bytes, padded to f2_score_bytes), group-queue capacity,
     // bytes of one warp's private area, ceil(2^32 / ftiles)
     int f2_srow, f2_srows, f2_score_bytes, f2_gcap, f2_wbytes;
+    int f2_imgbytes, f2_imgstride;               // bytes of a staged tile (row stride x rows) and the 128-byte aligned distance between stages
     int f2_tiles, f2_tab_off, f2_irows;          // tiles of F2_CW x 1 cells per frame, their table inside tabs, rows of a staged tile
     unsigned f2_rcp_tiles;
     unsigned long long frame_bytes;
@@ -614,6 +615,8 @@ k_fast2(const CUtensorMap* __restrict__ tmaps, const unsigned* __restrict__ tile
     extern __shared__ __align__(128) unsigned char s_f2[];
     __shared__ __align__(8) uint64_t s_full[F2_STAGES], s_ann[F2_RING];
     __shared__ int s_loads[F2_STAGES], s_next, s_lock, s_issued;
+    __shared__ int s_woff[FAST_WARPS];                    // offset of each warp's private area (read back per cell: one LDS instead of the
+                                                          // special-register and constant-bank arithmetic the compiler re-materialises)
     // announcement of the CTA's tile number q (slot q & 7): which launch tile it is (-1: the launch has no more), where it lands and the
     // parity of that buffer's mbarrier phase.  The issuing thread writes the fields and arrives on s_ann[slot] (release); the four warps
     // that take the tile's cells wait on it (acquire) with the parity of the slot's use number q / F2_RING.  s_rdone counts the cells
@@ -622,7 +625,7 @@ k_fast2(const CUtensorMap* __restrict__ tmaps, const unsigned* __restrict__ tile
     __shared__ unsigned s_rte[F2_RING];                   // the tile's table entry (level | cell row << 4 | first cell column << 16)
     const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
     const int irow = IROWT ? IROWT : P.f_irow;
-    const int imgbytes = irow * P.f2_irows, imgstride = (imgbytes + 127) & ~127;
+    const int imgbytes = P.f2_imgbytes, imgstride = P.f2_imgstride;
     const int T = P.f2_tiles * nframes;
     int* tile_ctr = status + 2;                            // [2] next (tile, frame) of the launch, [3] CTAs that have left; both 0 between launches
     // Request the CTA's next tile into buffer `buf` (free: every cell of its previous tile is done).  Tiles come from a launch-wide
@@ -650,6 +653,7 @@ k_fast2(const CUtensorMap* __restrict__ tmaps, const unsigned* __restrict__ tile
         mbar_arrive_expect_tx(&s_full[buf], (unsigned)imgbytes);
         tma_load_3d(s_f2 + (size_t)buf * imgstride, tmaps + 3 * MAXLEV + (te & 15), ax0 + EDGE, ay0 + EDGE, f, &s_full[buf]);
     };
+    if (lane == 0) s_woff[warp] = F2_STAGES * imgstride + warp * P.f2_wbytes;
     if (tid == 0) {
         for (int k = 0; k < F2_STAGES; k++) { mbar_init(&s_full[k], 1); s_loads[k] = 0; }
         for (int k = 0; k < F2_RING; k++) { mbar_init(&s_ann[k], 1); s_rdone[k] = F2_CW; }
@@ -660,7 +664,7 @@ k_fast2(const CUtensorMap* __restrict__ tmaps, const unsigned* __restrict__ tile
     __syncthreads();                                       // the only CTA barrier: the mbarriers and the bookkeeping words exist
 
     // the warp's private area
-    unsigned char* wb = s_f2 + F2_STAGES * (size_t)imgstride + (size_t)warp * P.f2_wbytes;
+    unsigned char* wb = s_f2 + *reinterpret_cast<volatile int*>(&s_woff[warp]);
     uint8_t* s_score = wb;
     unsigned short* gq = reinterpret_cast<unsigned short*>(wb + P.f2_score_bytes);
     unsigned short* pq = gq + P.f2_gcap;
@@ -677,7 +681,7 @@ k_fast2(const CUtensorMap* __restrict__ tmaps, const unsigned* __restrict__ tile
     // whichever staged tile comes next, instead of waiting for its tile's slowest cell.
     for (;;) {
         int n = 0;
-        if (lane == 0) n = atomicAdd(&s_next, 1);
+        if (lane == 0) n = atom_add_shared(&s_next, 1);         // (plain PTX: atomicAdd() on shared memory expands to the warp-aggregation idiom)
         n = __shfl_sync(0xFFFFFFFFu, n, 0);
         const int q = n >> 2, cj = n & 3, slot = q & (F2_RING - 1);
         static_assert(F2_CW == 4, "four cells per tile");
@@ -716,7 +720,12 @@ k_fast2(const CUtensorMap* __restrict__ tmaps, const unsigned* __restrict__ tile
                 if (lane == ngx_real - 1) m &= 0x80808080u >> (8 * (3 - ((cx1 - 1) & 3)));
                 vtab[lane] = m;
             }
-            for (int k = lane; k < ((nrows + 2) * srow + 15) >> 4; k += 32) reinterpret_cast<uint4*>(s_score)[k] = make_uint4(0u, 0u, 0u, 0u);
+            {   // the whole map of the largest cell (75 x 16 bytes for 30-px cells): three predicated stores, no loop in the common case
+                const int n16 = P.f2_score_bytes >> 4;
+#pragma unroll
+                for (int it = 0; it < 3; it++) if (lane + 32 * it < n16) reinterpret_cast<uint4*>(s_score)[lane + 32 * it] = make_uint4(0u, 0u, 0u, 0u);
+                for (int k = lane + 96; k < n16; k += 32) reinterpret_cast<uint4*>(s_score)[k] = make_uint4(0u, 0u, 0u, 0u);
+            }
             __syncwarp();
             int* gcount = cand_count + (size_t)f * P.nlevels + level;
             unsigned* gdst = cand + (size_t)f * P.raw_per_frame + L.raw_off;
@@ -915,7 +924,7 @@ k_fast2(const CUtensorMap* __restrict__ tmaps, const unsigned* __restrict__ tile
         __syncwarp();
         if (lane == 0) {
             __threadfence_block();
-            if (atomicAdd(&s_rdone[slot], 1) == F2_CW - 1) {
+            if (atom_add_shared(&s_rdone[slot], 1) == F2_CW - 1) {
                 fence_proxy_async_smem();                  // generic-proxy reads of the buffer before the async-proxy overwrite
                 issue(b);
             }
@@ -2089,6 +2098,7 @@ static int make_plan(const uvip_extractor* ex, int w, int h, Plan* out, std::vec
         P.f2_gcap = (int)align_up((size_t)gcap + 2, 8);
         P.f2_wbytes = (int)align_up((size_t)P.f2_score_bytes + 2 * ((size_t)P.f2_gcap + F2_PQ + 2) + 4 * 20, 16);
         P.f2_irows = max_hc + 6;
+        P.f2_imgbytes = P.f_irow * P.f2_irows; P.f2_imgstride = (int)align_up((size_t)P.f2_imgbytes, 128);
         int f2t = 0;
         for (int l = 0; l < p.nlevels; l++) f2t += div_up(P.lv[l].ncols, F2_CW) * P.lv[l].nrows;
         P.f2_tiles = f2t;
