@@ -83,26 +83,41 @@ __device__ __forceinline__ void tile_ring(uint8_t* inner, int ps, int w, int h, 
     const bool hl = X0 <= BORDER_W && X1 > 1, hr = X1 > w - 2 - BORDER_W && X0 < w - 1;
     const bool vt = Y0 <= BORDER_W && Y1 > 1, vb = Y1 > h - 2 - BORDER_W && Y0 < h - 1;
     if (!(hl | hr | vt | vb)) return;                         // uniform
-    const int tw = X1 - X0, th = Y1 - Y0;
+    const int th = Y1 - Y0;
+    // (A) mirrored columns of the tile's rows: one thread per (row, side), its four ring pixels in sequence
     if (hl | hr)
-        for (int i = tid; i < th * 2 * BORDER_W; i += 256) {
-            const int r = i / (2 * BORDER_W), m = i % (2 * BORDER_W), k = (m % BORDER_W) + 1;      // powers of two
-            const int c = m < BORDER_W ? k : w - 1 - k, p = m < BORDER_W ? -k : w - 1 + k;
-            if (c >= X0 && c < X1) { uint8_t* row = inner + (ptrdiff_t)(Y0 + r) * ps; row[p] = row[c]; }
-        }
-    if (vt | vb)
-#pragma unroll 1
-        for (int m = 0; m < 2 * BORDER_W; m++) {
-            const int k = (m % BORDER_W) + 1;
-            const int sr = m < BORDER_W ? k : h - 1 - k, pr = m < BORDER_W ? -k : h - 1 + k;
-            if (sr < Y0 || sr >= Y1) continue;                // uniform
-            for (int t = tid; t < tw + 2 * BORDER_W; t += 256) {       // the tile's columns, then the 4 left and the 4 right ring columns
-                const int e = t - tw;
-                const int p = e < 0 ? X0 + t : (e < BORDER_W ? -1 - e : w + e - BORDER_W);
-                const int c = reflect101(p, w);
-                if (c >= X0 && c < X1) inner[(ptrdiff_t)pr * ps + p] = inner[(ptrdiff_t)sr * ps + c];
+        for (int i = tid; i < 2 * th; i += 256) {
+            const int side = i & 1;
+            if (side ? hr : hl) {
+                uint8_t* row = inner + (ptrdiff_t)(Y0 + (i >> 1)) * ps;
+#pragma unroll
+                for (int k = 1; k <= BORDER_W; k++) {
+                    const int c = side ? w - 1 - k : k, p = side ? w - 1 + k : -k;
+                    if (c >= X0 && c < X1) row[p] = row[c];
+                }
             }
         }
+    // (B) mirrored rows: threads 0..63 copy the tile's columns in 16-byte pieces (tiles start at multiples of 128, plane rows are
+    //     16-byte aligned), threads 64..127 the 4 + 4 ring columns beside the image; mirror row m = t >> 3 of 2 * BORDER_W
+    if ((vt | vb) && tid < 128) {
+        const int m = (tid >> 3) & 7, k = (m % BORDER_W) + 1;
+        const int sr = m < BORDER_W ? k : h - 1 - k, pr = m < BORDER_W ? -k : h - 1 + k;
+        if (sr >= Y0 && sr < Y1) {
+            const uint8_t* src = inner + (ptrdiff_t)sr * ps;
+            uint8_t* dst = inner + (ptrdiff_t)pr * ps;
+            if (tid < 64) {
+                for (int x = X0 + 16 * (tid & 7); x < X1; x += 128) {
+                    if (x + 16 <= X1) *reinterpret_cast<uint4*>(dst + x) = *reinterpret_cast<const uint4*>(src + x);
+                    else for (int c = x; c < X1; c++) dst[c] = src[c];
+                }
+            } else {
+                const int e = tid & 7;
+                const int p = e < BORDER_W ? -1 - e : w + e - BORDER_W;
+                const int c = reflect101(p, w);
+                if (c >= X0 && c < X1) dst[p] = src[c];
+            }
+        }
+    }
 }
 
 __global__ void __launch_bounds__(256)
@@ -2214,6 +2229,7 @@ static int ensure_plan(uvip_extractor* ex, int w, int h)
             UVIP_CUDA(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&nb, k_fast2<0>, 256, sm2));
         }
         if (nb < 1) { set_last_error("FAST kernel does not fit one SM (%zu bytes of shared memory)", sm2); return UVIP_ERR_UNSUPPORTED; }
+        if (const char* e = getenv("UVIP_FAST2_CTAS")) { const int v = atoi(e); if (v >= 1 && v < nb) nb = v; }   // tuning: leave room for co-running kernels
         ex->fast2_ctas_per_sm = nb;
     }
     UVIP_CUDA(cudaFuncSetAttribute(k_resize<true, RS_RMAX>, cudaFuncAttributeMaxDynamicSharedMemorySize, P.rs_boxw * P.rs_boxh + 128));
