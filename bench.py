@@ -171,14 +171,19 @@ def hbm_peak():
         return FALLBACK_HBM_GBS, 'fallback'
 
 
+# sources that hold no kernel of the benchmark step (KLT / RANSAC row N1, the synthetic-frame generator): changing them does not
+# invalidate the ncu evidence of the step
+STEP_UNRELATED = ('klt.cu', 'synth.cu')
+
+
 def kernel_source_hash():
-    """sha256 over the kernel sources: the committed ncu evidence names the sources it was captured from (tools/pipes_from_launches.py
+    """sha256 over the sources of the step's kernels: the committed ncu evidence names the sources it was captured from (tools/pipes_from_launches.py
     writes the same hash), so a bench run on changed kernels reports that evidence as stale instead of quoting it"""
     import hashlib
     h = hashlib.sha256()
     d = os.path.join(ROOT, 'u-vip-slam_b200', 'csrc')
     for fn in sorted(os.listdir(d)):
-        if fn.endswith(('.cu', '.cuh', '.inc')):
+        if fn.endswith(('.cu', '.cuh', '.inc')) and fn not in STEP_UNRELATED:
             h.update(fn.encode()); h.update(open(os.path.join(d, fn), 'rb').read())
     return h.hexdigest()[:16]
 

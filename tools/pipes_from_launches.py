@@ -60,10 +60,11 @@ for k, v in pipes.items():
         v['share_of_step_pct'] = round(100.0 * v['ncu_time_us'] / total, 2)
 root = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
 # the kernel sources this evidence was captured from (bench.py quotes it only while they are unchanged)
+STEP_UNRELATED = ('klt.cu', 'synth.cu')       # same rule as bench.py kernel_source_hash()
 h = hashlib.sha256()
 d = os.path.join(root, 'u-vip-slam_b200', 'csrc')
 for fn in sorted(os.listdir(d)):
-    if fn.endswith(('.cu', '.cuh', '.inc')):
+    if fn.endswith(('.cu', '.cuh', '.inc')) and fn not in STEP_UNRELATED:
         h.update(fn.encode()); h.update(open(os.path.join(d, fn), 'rb').read())
 pipes['_source_hash'] = traf['_source_hash'] = h.hexdigest()[:16]
 json.dump(pipes, open(os.path.join(root, 'profiles', 'kernel_pipes.json'), 'w'), indent=1)

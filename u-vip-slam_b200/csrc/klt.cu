@@ -178,6 +178,139 @@ k_klt_track(const uint8_t* __restrict__ img0, const short2* __restrict__ der0, c
     if (lane == 0) { next_pts[pt] = np; status[pt] = ok ? 1 : 0; if (err) err[pt] = errv; }
 }
 
+
+// The same tracker for the window the reference uses (21 x 21, src/Tracking.cc:1044), organised around what the first kernel's profile
+// showed: it is bound by instruction issue, and two thirds of the instructions of an iteration were address arithmetic (a division and
+// 64-bit pointers per pixel) and four byte loads from global memory per pixel.  Here
+//   * the pixel offsets of a lane's 14 window pixels are computed once per kernel and live in registers;
+//   * the part of the second image the window can reach is staged in shared memory once per level (32 rows x 36 bytes around the start
+//     position, restaged only if the window moves more than 5 px), so an iteration reads it with 32-bit addresses and immediates;
+//   * the derivative window is stored as float2: (float)(diff * d) == (float)diff * (float)d for integers (one rounding of the exact
+//     product either way), which replaces two integer multiplies and two conversions per pixel by one conversion.
+// Arithmetic and summation order are those of k_klt_track: the two kernels return identical bits.
+constexpr int KLT_W21 = 21, KLT_NPX21 = KLT_W21 * KLT_W21, KLT_K21 = (KLT_NPX21 + 31) / 32;
+constexpr int KLT_RS = 36, KLT_RR = 32, KLT_M = 5;       // staged region: row stride, rows, margin around the start position
+constexpr int KLT_WARP_BYTES21 = 896 + 3536 + KLT_RS * KLT_RR;   // intensities (short), derivatives (float2), region of the second image
+
+__global__ void __launch_bounds__(256)
+k_klt_track21(const uint8_t* __restrict__ img0, const short2* __restrict__ der0, const uint8_t* __restrict__ img1,
+              const float2* __restrict__ prev_pts, float2* __restrict__ next_pts, int n, int max_level, int max_iter, double eps2,
+              int flags, double min_eig_thr, uint8_t* __restrict__ status, float* __restrict__ err, size_t slot_img, size_t slot_der,
+              const __grid_constant__ KltPlan P)
+{
+    extern __shared__ __align__(16) unsigned char s_klt[];
+    const int lane = threadIdx.x & 31, wib = threadIdx.x >> 5;
+    const int pt = blockIdx.x * 8 + wib;
+    if (pt >= n) return;
+    {
+        const size_t pr = blockIdx.y;
+        img0 += pr * slot_img; der0 += pr * slot_der; img1 += pr * slot_img;
+        prev_pts += pr * n; next_pts += pr * n; status += pr * n; if (err) err += pr * n;
+    }
+    constexpr int win = KLT_W21, npx = KLT_NPX21;
+    short* Iw = reinterpret_cast<short*>(s_klt + (size_t)wib * KLT_WARP_BYTES21);
+    float2* dF = reinterpret_cast<float2*>(s_klt + (size_t)wib * KLT_WARP_BYTES21 + 896);
+    unsigned char* reg = s_klt + (size_t)wib * KLT_WARP_BYTES21 + 896 + 3536;
+    int off[KLT_K21];                                     // offset of the lane's k-th window pixel inside the staged region
+#pragma unroll
+    for (int k = 0; k < KLT_K21; k++) { const int i = lane + 32 * k, y = i / win; off[k] = y * KLT_RS + (i - y * win); }
+    const float half = (win - 1) * 0.5f;
+    const float FLT_SCALE = 1.f / (1 << 20);
+    const float2 pp = prev_pts[pt];
+    float2 np = next_pts[pt];
+    bool ok = true;
+    float errv = 0.f;
+    for (int level = max_level; level >= 0; level--) {
+        const KltLevel& L = P.lv[level];
+        const float sc = (float)(1. / (1 << level));
+        float px = pp.x * sc, py = pp.y * sc, nx, ny;
+        if (level == max_level) {
+            if (flags & 4) { nx = np.x * sc; ny = np.y * sc; } else { nx = px; ny = py; }
+        } else { nx = np.x * 2.f; ny = np.y * 2.f; }
+        np = make_float2(nx, ny);
+        px -= half; py -= half;
+        const int ipx = (int)floorf(px), ipy = (int)floorf(py);
+        if (ipx < -win || ipx >= L.w || ipy < -win || ipy >= L.h) { if (level == 0) { ok = false; errv = 0.f; } continue; }
+        float a = px - ipx, b = py - ipy;
+        int iw00 = __float2int_rn((1.f - a) * (1.f - b) * 16384.f), iw01 = __float2int_rn(a * (1.f - b) * 16384.f);
+        int iw10 = __float2int_rn((1.f - a) * b * 16384.f), iw11 = 16384 - iw00 - iw01 - iw10;
+        const uint8_t* I0 = img0 + L.ioff + (size_t)(ipy + L.B) * L.istride + (ipx + L.B);
+        const short2* D0 = der0 + L.doff + (size_t)(ipy + L.B) * L.dstride + (ipx + L.B);
+        float A11 = 0.f, A12 = 0.f, A22 = 0.f;
+        __syncwarp();
+#pragma unroll 2
+        for (int k = 0; k < KLT_K21; k++) {
+            const int i = lane + 32 * k;
+            if (i < npx) {
+                const int y = i / win, x = i - y * win;
+                const uint8_t* p = I0 + y * L.istride + x;
+                const short2* q = D0 + y * L.dstride + x;
+                const int ival = KLT_DESCALE(p[0] * iw00 + p[1] * iw01 + p[L.istride] * iw10 + p[L.istride + 1] * iw11, 9);
+                const short2 d00 = q[0], d01 = q[1], d10 = q[L.dstride], d11 = q[L.dstride + 1];
+                const int ixval = KLT_DESCALE(d00.x * iw00 + d01.x * iw01 + d10.x * iw10 + d11.x * iw11, 14);
+                const int iyval = KLT_DESCALE(d00.y * iw00 + d01.y * iw01 + d10.y * iw10 + d11.y * iw11, 14);
+                Iw[i] = (short)ival; dF[i] = make_float2((float)(short)ixval, (float)(short)iyval);
+                A11 += (float)(ixval * ixval); A12 += (float)(ixval * iyval); A22 += (float)(iyval * iyval);
+            }
+        }
+#pragma unroll
+        for (int o = 16; o > 0; o >>= 1) {
+            A11 += __shfl_xor_sync(0xFFFFFFFFu, A11, o); A12 += __shfl_xor_sync(0xFFFFFFFFu, A12, o); A22 += __shfl_xor_sync(0xFFFFFFFFu, A22, o);
+        }
+        __syncwarp();
+        A11 *= FLT_SCALE; A12 *= FLT_SCALE; A22 *= FLT_SCALE;
+        float D = A11 * A22 - A12 * A12;
+        const float minEig = (A22 + A11 - sqrtf((A11 - A22) * (A11 - A22) + 4.f * A12 * A12)) / (float)(2 * win * win);
+        if (flags & 8) errv = minEig;
+        if (minEig < min_eig_thr || D < FLT_EPSILON) { if (level == 0) ok = false; continue; }
+        D = 1.f / D;
+        nx -= half; ny -= half;
+        float pdx = 0.f, pdy = 0.f;
+        int ox = 0, oy = 0; bool staged = false;          // origin of the staged region in image coordinates
+        for (int j = 0; j < max_iter; j++) {
+            const int inx = (int)floorf(nx), iny = (int)floorf(ny);
+            if (inx < -win || inx >= L.w || iny < -win || iny >= L.h) { if (level == 0) ok = false; break; }
+            if (!staged || inx < ox || inx - ox > KLT_RS - (win + 1) || iny < oy || iny - oy > KLT_RR - (win + 1)) {
+                // (re)stage: rows oy .. oy + 31, 36 bytes from a 4-byte aligned column at or below inx - 5, clamped to the padded plane
+                const int gx = min(max((inx - KLT_M + L.B) & ~3, 0), L.istride - KLT_RS);
+                const int gy = min(max(iny - KLT_M + L.B, 0), L.h + 2 * L.B - KLT_RR);
+                ox = gx - L.B; oy = gy - L.B; staged = true;
+                const unsigned* src = reinterpret_cast<const unsigned*>(img1 + L.ioff + (size_t)(gy + lane) * L.istride + gx);
+                unsigned* dst = reinterpret_cast<unsigned*>(reg + lane * KLT_RS);
+                __syncwarp();
+#pragma unroll
+                for (int w = 0; w < KLT_RS / 4; w++) dst[w] = __ldg(src + w);
+                __syncwarp();
+            }
+            a = nx - inx; b = ny - iny;
+            iw00 = __float2int_rn((1.f - a) * (1.f - b) * 16384.f); iw01 = __float2int_rn(a * (1.f - b) * 16384.f);
+            iw10 = __float2int_rn((1.f - a) * b * 16384.f); iw11 = 16384 - iw00 - iw01 - iw10;
+            const unsigned char* J = reg + (iny - oy) * KLT_RS + (inx - ox);
+            float b1 = 0.f, b2 = 0.f;
+#pragma unroll
+            for (int k = 0; k < KLT_K21; k++) {
+                if (k < KLT_K21 - 1 || lane + 32 * k < npx) {
+                    const unsigned char* p = J + off[k];
+                    const int diff = KLT_DESCALE(p[0] * iw00 + p[1] * iw01 + p[KLT_RS] * iw10 + p[KLT_RS + 1] * iw11, 9) - Iw[lane + 32 * k];
+                    const float fd = (float)diff;
+                    const float2 d = dF[lane + 32 * k];
+                    b1 += fd * d.x; b2 += fd * d.y;
+                }
+            }
+#pragma unroll
+            for (int o = 16; o > 0; o >>= 1) { b1 += __shfl_xor_sync(0xFFFFFFFFu, b1, o); b2 += __shfl_xor_sync(0xFFFFFFFFu, b2, o); }
+            b1 *= FLT_SCALE; b2 *= FLT_SCALE;
+            const float dx = (A12 * b2 - A22 * b1) * D, dy = (A12 * b1 - A11 * b2) * D;
+            nx += dx; ny += dy;
+            np = make_float2(nx + half, ny + half);
+            if ((double)dx * dx + (double)dy * dy <= eps2) break;
+            if (j > 0 && fabsf(dx + pdx) < 0.01 && fabsf(dy + pdy) < 0.01) { np.x -= dx * 0.5f; np.y -= dy * 0.5f; break; }
+            pdx = dx; pdy = dy;
+        }
+    }
+    if (lane == 0) { next_pts[pt] = np; status[pt] = ok ? 1 : 0; if (err) err[pt] = errv; }
+}
+
 }  // namespace uvip
 
 using namespace uvip;
@@ -498,9 +631,11 @@ int uvip_klt_track(uvip_klt* k, int slot_prev, int slot_next, const float* prev_
     UVIP_CUDA(cudaMemcpyAsync(base, prev_pts, (size_t)n * 8, cudaMemcpyHostToDevice, st));
     UVIP_CUDA(cudaMemcpyAsync(base + o_next, next_pts, (size_t)n * 8, cudaMemcpyHostToDevice, st));
     const int npx = P.win * P.win;
-    const size_t smem = (size_t)8 * 3 * ((npx + 1) & ~1) * sizeof(short);
-    UVIP_CUDA(cudaFuncSetAttribute(k_klt_track, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-    k_klt_track<<<div_up(n, 8), 256, smem, st>>>(k->img.as<uint8_t>() + (size_t)slot_prev * k->img_bytes, k->der.as<short2>() + (size_t)slot_prev * k->der_elems,
+    const bool w21 = P.win == KLT_W21 && !getenv("UVIP_KLT_GENERIC");
+    const size_t smem = w21 ? (size_t)8 * KLT_WARP_BYTES21 : (size_t)8 * 3 * ((npx + 1) & ~1) * sizeof(short);
+    auto kern = w21 ? k_klt_track21 : k_klt_track;
+    UVIP_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+    kern<<<div_up(n, 8), 256, smem, st>>>(k->img.as<uint8_t>() + (size_t)slot_prev * k->img_bytes, k->der.as<short2>() + (size_t)slot_prev * k->der_elems,
                                                 k->img.as<uint8_t>() + (size_t)slot_next * k->img_bytes, (const float2*)base, (float2*)(base + o_next), n,
                                                 max_level, max_iter, eps2, flags, min_eig_threshold, base + o_st, (float*)(base + o_err), 0, 0, P);
     k->launches++;
@@ -544,9 +679,11 @@ int uvip_klt_track_sequence_device(uvip_klt* k, const uint8_t* d_frames, int nfr
     if (max_level > P.nlevels - 1) max_level = P.nlevels - 1;
     if (max_level < 0) max_level = 0;
     const int npx = P.win * P.win;
-    const size_t smem = (size_t)8 * 3 * ((npx + 1) & ~1) * sizeof(short);
-    UVIP_CUDA(cudaFuncSetAttribute(k_klt_track, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-    k_klt_track<<<dim3(div_up(npts, 8), nframes - 1), 256, smem, st>>>(img, der, img + si, (const float2*)d_prev_pts, (float2*)d_next_pts, npts, max_level, max_iter,
+    const bool w21 = P.win == KLT_W21 && !getenv("UVIP_KLT_GENERIC");
+    const size_t smem = w21 ? (size_t)8 * KLT_WARP_BYTES21 : (size_t)8 * 3 * ((npx + 1) & ~1) * sizeof(short);
+    auto kern = w21 ? k_klt_track21 : k_klt_track;
+    UVIP_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+    kern<<<dim3(div_up(npts, 8), nframes - 1), 256, smem, st>>>(img, der, img + si, (const float2*)d_prev_pts, (float2*)d_next_pts, npts, max_level, max_iter,
                                                                       epsilon * epsilon, flags, min_eig_threshold, d_status, d_err, si, sd, P);
     k->launches++;
     UVIP_CUDA(cudaGetLastError());
