@@ -102,6 +102,29 @@ def test_gpu_klt_refuses_slots_of_another_geometry(pkg, synth):
     klt.close()
 
 
+@pytest.mark.gpu
+def test_gpu_klt_21x21_kernel_equals_generic_kernel(pkg, synth):
+    """the tracker specialised for the reference's 21x21 window (offsets in registers, second image staged in shared memory, float
+    derivative window) returns the bits of the generic kernel: same integer interpolation, same float products, same summation order.
+    Large initial errors force the staged region to be re-centred inside a level."""
+    a = synth.synth_frame(1, 752, 480); b = synth.synth_frame(1, 752, 480, dx=5, dy=3, noise_seed=2)
+    p0 = _pts(synth)
+    klt = pkg.KLTTracker(752, 480, 21, 5, nslots=2)
+    klt.build_pyramid(0, a); klt.build_pyramid(1, b)
+    for guess, flags in ((np.float32([2.0, 1.5]), 12), (np.float32([-14.0, 11.0]), 12), (np.float32([0, 0]), 8)):
+        os.environ.pop('UVIP_KLT_GENERIC', None)
+        fast = klt.track(0, 1, p0, p0 + guess, flags=flags)
+        os.environ['UVIP_KLT_GENERIC'] = '1'
+        try:
+            gen = klt.track(0, 1, p0, p0 + guess, flags=flags)
+        finally:
+            os.environ.pop('UVIP_KLT_GENERIC', None)
+        for x, y in zip(fast, gen):
+            assert np.array_equal(x, y)
+        assert fast[1].sum() > 300
+    klt.close()
+
+
 # ---- N1, last third: cv::findFundamentalMat(FM_RANSAC) inlier mask (src/Tracking.cc:1062) ------------------------------------------
 RANSAC_CASES = (101, 102, 103, 104)
 

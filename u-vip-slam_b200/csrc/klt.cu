@@ -190,9 +190,17 @@ k_klt_track(const uint8_t* __restrict__ img0, const short2* __restrict__ der0, c
 // Arithmetic and summation order are those of k_klt_track: the two kernels return identical bits.
 constexpr int KLT_W21 = 21, KLT_NPX21 = KLT_W21 * KLT_W21, KLT_K21 = (KLT_NPX21 + 31) / 32;
 constexpr int KLT_RS = 36, KLT_RR = 32, KLT_M = 5;       // staged region: row stride, rows, margin around the start position
+#ifndef KLT_BUILD_UNROLL
+#define KLT_BUILD_UNROLL 7
+#endif
+constexpr int KLT_BUILD_UNROLL_N = KLT_BUILD_UNROLL;
+#ifndef KLT_WPB21_
+#define KLT_WPB21_ 1
+#endif
+constexpr int KLT_WPB21 = KLT_WPB21_;                     // warps (= points) per CTA: a CTA lives as long as its slowest point, small CTAs waste fewer warp slots
 constexpr int KLT_WARP_BYTES21 = 896 + 3536 + KLT_RS * KLT_RR;   // intensities (short), derivatives (float2), region of the second image
 
-__global__ void __launch_bounds__(256)
+__global__ void __launch_bounds__(KLT_WPB21 * 32)
 k_klt_track21(const uint8_t* __restrict__ img0, const short2* __restrict__ der0, const uint8_t* __restrict__ img1,
               const float2* __restrict__ prev_pts, float2* __restrict__ next_pts, int n, int max_level, int max_iter, double eps2,
               int flags, double min_eig_thr, uint8_t* __restrict__ status, float* __restrict__ err, size_t slot_img, size_t slot_der,
@@ -200,7 +208,7 @@ k_klt_track21(const uint8_t* __restrict__ img0, const short2* __restrict__ der0,
 {
     extern __shared__ __align__(16) unsigned char s_klt[];
     const int lane = threadIdx.x & 31, wib = threadIdx.x >> 5;
-    const int pt = blockIdx.x * 8 + wib;
+    const int pt = blockIdx.x * KLT_WPB21 + wib;
     if (pt >= n) return;
     {
         const size_t pr = blockIdx.y;
@@ -238,17 +246,19 @@ k_klt_track21(const uint8_t* __restrict__ img0, const short2* __restrict__ der0,
         const short2* D0 = der0 + L.doff + (size_t)(ipy + L.B) * L.dstride + (ipx + L.B);
         float A11 = 0.f, A12 = 0.f, A22 = 0.f;
         __syncwarp();
-#pragma unroll 2
+#pragma unroll KLT_BUILD_UNROLL_N
         for (int k = 0; k < KLT_K21; k++) {
-            const int i = lane + 32 * k;
+            // (the last step covers 25 pixels: the other lanes repeat pixel 440 and drop the result, so that no load sits behind a branch
+            //  and the loads of several steps can be in flight together)
+            const int i = lane + 32 * k, ic = min(i, npx - 1);
+            const int y = ic / win, x = ic - y * win;
+            const uint8_t* p = I0 + y * L.istride + x;
+            const short2* q = D0 + y * L.dstride + x;
+            const int ival = KLT_DESCALE(p[0] * iw00 + p[1] * iw01 + p[L.istride] * iw10 + p[L.istride + 1] * iw11, 9);
+            const short2 d00 = q[0], d01 = q[1], d10 = q[L.dstride], d11 = q[L.dstride + 1];
+            const int ixval = KLT_DESCALE(d00.x * iw00 + d01.x * iw01 + d10.x * iw10 + d11.x * iw11, 14);
+            const int iyval = KLT_DESCALE(d00.y * iw00 + d01.y * iw01 + d10.y * iw10 + d11.y * iw11, 14);
             if (i < npx) {
-                const int y = i / win, x = i - y * win;
-                const uint8_t* p = I0 + y * L.istride + x;
-                const short2* q = D0 + y * L.dstride + x;
-                const int ival = KLT_DESCALE(p[0] * iw00 + p[1] * iw01 + p[L.istride] * iw10 + p[L.istride + 1] * iw11, 9);
-                const short2 d00 = q[0], d01 = q[1], d10 = q[L.dstride], d11 = q[L.dstride + 1];
-                const int ixval = KLT_DESCALE(d00.x * iw00 + d01.x * iw01 + d10.x * iw10 + d11.x * iw11, 14);
-                const int iyval = KLT_DESCALE(d00.y * iw00 + d01.y * iw01 + d10.y * iw10 + d11.y * iw11, 14);
                 Iw[i] = (short)ival; dF[i] = make_float2((float)(short)ixval, (float)(short)iyval);
                 A11 += (float)(ixval * ixval); A12 += (float)(ixval * iyval); A22 += (float)(iyval * iyval);
             }
@@ -632,10 +642,11 @@ int uvip_klt_track(uvip_klt* k, int slot_prev, int slot_next, const float* prev_
     UVIP_CUDA(cudaMemcpyAsync(base + o_next, next_pts, (size_t)n * 8, cudaMemcpyHostToDevice, st));
     const int npx = P.win * P.win;
     const bool w21 = P.win == KLT_W21 && !getenv("UVIP_KLT_GENERIC");
-    const size_t smem = w21 ? (size_t)8 * KLT_WARP_BYTES21 : (size_t)8 * 3 * ((npx + 1) & ~1) * sizeof(short);
+    const size_t smem = w21 ? (size_t)KLT_WPB21 * KLT_WARP_BYTES21 : (size_t)8 * 3 * ((npx + 1) & ~1) * sizeof(short);
     auto kern = w21 ? k_klt_track21 : k_klt_track;
+    const int wpb = w21 ? KLT_WPB21 : 8;
     UVIP_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-    kern<<<div_up(n, 8), 256, smem, st>>>(k->img.as<uint8_t>() + (size_t)slot_prev * k->img_bytes, k->der.as<short2>() + (size_t)slot_prev * k->der_elems,
+    kern<<<div_up(n, wpb), wpb * 32, smem, st>>>(k->img.as<uint8_t>() + (size_t)slot_prev * k->img_bytes, k->der.as<short2>() + (size_t)slot_prev * k->der_elems,
                                                 k->img.as<uint8_t>() + (size_t)slot_next * k->img_bytes, (const float2*)base, (float2*)(base + o_next), n,
                                                 max_level, max_iter, eps2, flags, min_eig_threshold, base + o_st, (float*)(base + o_err), 0, 0, P);
     k->launches++;
@@ -680,10 +691,11 @@ int uvip_klt_track_sequence_device(uvip_klt* k, const uint8_t* d_frames, int nfr
     if (max_level < 0) max_level = 0;
     const int npx = P.win * P.win;
     const bool w21 = P.win == KLT_W21 && !getenv("UVIP_KLT_GENERIC");
-    const size_t smem = w21 ? (size_t)8 * KLT_WARP_BYTES21 : (size_t)8 * 3 * ((npx + 1) & ~1) * sizeof(short);
+    const size_t smem = w21 ? (size_t)KLT_WPB21 * KLT_WARP_BYTES21 : (size_t)8 * 3 * ((npx + 1) & ~1) * sizeof(short);
     auto kern = w21 ? k_klt_track21 : k_klt_track;
+    const int wpb = w21 ? KLT_WPB21 : 8;
     UVIP_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-    kern<<<dim3(div_up(npts, 8), nframes - 1), 256, smem, st>>>(img, der, img + si, (const float2*)d_prev_pts, (float2*)d_next_pts, npts, max_level, max_iter,
+    kern<<<dim3(div_up(npts, wpb), nframes - 1), wpb * 32, smem, st>>>(img, der, img + si, (const float2*)d_prev_pts, (float2*)d_next_pts, npts, max_level, max_iter,
                                                                       epsilon * epsilon, flags, min_eig_threshold, d_status, d_err, si, sd, P);
     k->launches++;
     UVIP_CUDA(cudaGetLastError());
