@@ -753,16 +753,18 @@ k_fast2(const CUtensorMap* __restrict__ tmaps, const unsigned* __restrict__ tile
                 // ---- B1: compass pre-test on every group of the cell
                 int ngw = 0;
                 for (int g0 = 0; g0 < ng; g0 += 32) {
-                    const int g = g0 + lane;
-                    unsigned pf = 0;
-                    if (g < ng) {
-                        const int r = __umulhi((unsigned)g, rcp);
-                        const unsigned* W = Wc + g + r * rskip;
+                    // (lanes behind the last group repeat it and drop the result: no branch around the loads)
+                    const int g = g0 + lane, gc = min(g, ng - 1);
+                    unsigned pf;
+                    {
+                        const int r = __umulhi((unsigned)gc, rcp);
+                        const unsigned* W = Wc + gc + r * rskip;
                         const unsigned v = W[0];
                         const unsigned a0 = __vabsdiffu4(W[3 * rsw], v), a8 = __vabsdiffu4(W[-3 * rsw], v);
                         const unsigned a4 = __vabsdiffu4(__funnelshift_r(v, W[1], 24), v), a12 = __vabsdiffu4(__funnelshift_r(W[-1], v, 8), v);
                         pf = ((a0 + K) | a0 | (a8 + K) | a8) & ((a4 + K) | a4 | (a12 + K) | a12) & 0x80808080u;
                     }
+                    if (g >= ng) pf = 0;
                     const unsigned bal = __ballot_sync(0xFFFFFFFFu, pf != 0);
                     if (pf) gq[ngw + __popc(bal & ltmask)] = (unsigned short)g;
                     ngw += __popc(bal);
@@ -776,9 +778,9 @@ k_fast2(const CUtensorMap* __restrict__ tmaps, const unsigned* __restrict__ tile
                     if (i0) { listok = false; ncw = 0; }                   // a second round: the first round's list is being overwritten
                     for (; i0 < ngw && npw + 128 <= F2_PQ; i0 += 32) {
                         const int gi = i0 + lane;
-                        unsigned cf = 0; int e0 = 0;
-                        if (gi < ngw) {
-                            const int g = gq[gi];
+                        unsigned cf; int e0;
+                        {   // (lanes behind the last queued group repeat it and drop the result)
+                            const int g = gq[min(gi, ngw - 1)];
                             const int r = __umulhi((unsigned)g, rcp), c = g - r * ngx;
                             const unsigned* W = Wc + g + r * rskip;
                             const unsigned v = W[0];
@@ -794,7 +796,7 @@ k_fast2(const CUtensorMap* __restrict__ tmaps, const unsigned* __restrict__ tile
                             unsigned out = 0;
 #pragma unroll
                             for (int k = 0; k < 8; k++) out |= (fl[k] & fl[(k + 1) & 7] & fl[(k + 2) & 7]) & fl[(k + 3) & 7];
-                            cf = out & vtab[c];
+                            cf = gi < ngw ? out & vtab[c] : 0u;
                             e0 = ((r + 1) << 8) + xoff0 + 4 * c;
                         }
                         int total = 0;
@@ -867,6 +869,8 @@ k_fast2(const CUtensorMap* __restrict__ tmaps, const unsigned* __restrict__ tile
                 //      the (frame, level) list: sweep 1 decides and counts, ONE reservation per warp and cell, sweep 2 writes
                 int nkeep = 0;
                 if (listok) {
+                    // sweep 1: decide, and compact the survivors to the front of the list (a survivor moves to a slot at or below its own;
+                    // the barrier separates the step's reads from its writes)
                     for (int k0 = 0; k0 < ncw; k0 += 32) {
                         const int k = k0 + lane;
                         const unsigned e = k < ncw ? cq[k] : 0u;
@@ -877,25 +881,23 @@ k_fast2(const CUtensorMap* __restrict__ tmaps, const unsigned* __restrict__ tile
                             const int m = max(max(max((int)sp[-1], (int)sp[1]), max((int)sp[-srow - 1], (int)sp[-srow])),
                                               max(max((int)sp[-srow + 1], (int)sp[srow - 1]), max((int)sp[srow], (int)sp[srow + 1])));
                             keep = sc > m;
-                            if (!keep) cq[k] = 0;                          // struck out (a valid entry is never 0: rows count from 1)
                         }
-                        nkeep += __popc(__ballot_sync(0xFFFFFFFFu, keep));
+                        const unsigned bal = __ballot_sync(0xFFFFFFFFu, keep);
+                        __syncwarp();
+                        if (keep) cq[nkeep + __popc(bal & ltmask)] = (unsigned short)e;
+                        nkeep += __popc(bal);
                     }
                     if (nkeep) {
                         int base = 0;
                         if (lane == 0) base = atomicAdd(gcount, nkeep);
                         base = __shfl_sync(0xFFFFFFFFu, base, 0);
                         __syncwarp();
-                        for (int k0 = 0; k0 < ncw; k0 += 32) {
-                            const int k = k0 + lane;
-                            const unsigned e = k < ncw ? cq[k] : 0u;
-                            const unsigned bal = __ballot_sync(0xFFFFFFFFu, e != 0);
-                            if (e) {
-                                const unsigned rec = recbase + (e & 255u) + ((e >> 8) << 12) + ((unsigned)s_score[(e >> 8) * srow + (e & 255)] << 24);
-                                const int o = base + __popc(bal & ltmask);
-                                if (o < L.raw_cap) gdst[o] = rec; else atomicOr(status, 1);
-                            }
-                            base += __popc(bal);
+                        // sweep 2: the survivors, in list order
+                        for (int k = lane; k < nkeep; k += 32) {
+                            const unsigned e = cq[k];
+                            const unsigned rec = recbase + (e & 255u) + ((e >> 8) << 12) + ((unsigned)s_score[(e >> 8) * srow + (e & 255)] << 24);
+                            const int o = base + k;
+                            if (o < L.raw_cap) gdst[o] = rec; else atomicOr(status, 1);
                         }
                     }
                 } else {
