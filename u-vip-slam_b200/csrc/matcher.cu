@@ -397,7 +397,14 @@ struct SearchCtx {
     const int32_t *cand_start, *cand_idx;          // explicit candidate lists (node-restricted searches); NULL = grid window
     const float* qline;                            // mode 5: epipolar line (a, b, c, a*a+b*b) per query
     const double* kthr;                            // mode 5: 3.84 * sigma2(octave) per keypoint
+    // optional per-query candidate cache of the grid-window search (NULL = none): the keypoints that pass the level and radius tests of
+    // a query do not depend on the claims, and neither do their distances, so the first round of the claim iteration records them
+    // (in scan order: id | octave << 19 | distance << 23) and later rounds only replay the list under the new claims.
+    // qcache_n[q] = entries, or -1 when the query has more than SW_CACHE_K (it is searched in full every round).
+    unsigned* qcache; int* qcache_n;
 };
+constexpr int SW_CACHE_K = 6;
+static bool env_set(const char* name) { const char* e = getenv(name); return e && *e && *e != '0'; }
 
 __device__ __forceinline__ int hamming256(const uint4& u, const uint4& v, const uint8_t* __restrict__ row)
 {
@@ -406,20 +413,51 @@ __device__ __forceinline__ int hamming256(const uint4& u, const uint4& v, const 
            __popc(v.x ^ y.x) + __popc(v.y ^ y.y) + __popc(v.z ^ y.z) + __popc(v.w ^ y.w);
 }
 
-__device__ int search_one(const SearchCtx& c, int q, const int* owner)
+// the accept rule at the end of a scan (src/ORBmatcher.cc:113-117, :470, :1703)
+__device__ __forceinline__ int search_accept(const uvip_search_params& sp, int bestIdx, int bestDist, int bestDist2, int bestLevel, int bestLevel2)
+{
+    if (bestIdx < 0 || bestDist > sp.th_dist) return -1;
+    if (sp.mode == 0 && bestLevel == bestLevel2 && (float)bestDist > __fmul_rn(sp.ratio, (float)bestDist2)) return -1;   // :116-117
+    if (sp.mode == 6 && !((float)bestDist <= __fmul_rn((float)bestDist2, sp.ratio))) return -1;                         // :470, :585
+    return bestIdx;
+}
+
+// round >= 1 of the claim iteration: replay the query's recorded candidates under the current claims
+__device__ __forceinline__ int search_replay(const SearchCtx& c, int q, const int* owner, int n)
 {
     const uvip_search_params& sp = c.sp;
+    int bestDist = sp.mode == 0 ? 256 : INT_MAX, bestDist2 = sp.mode == 6 ? INT_MAX : 256, bestLevel = -1, bestLevel2 = -1, bestIdx = -1;
+    const unsigned* e = c.qcache + (size_t)q * SW_CACHE_K;
+    for (int j = 0; j < n; j++) {
+        const unsigned w = e[j];
+        const int id = (int)(w & 0x7FFFFu), oct = (int)((w >> 19) & 15u), dist = (int)(w >> 23);
+        if (owner[id] < q) continue;
+        if (sp.mode == 0) {
+            if (dist < bestDist) { bestDist2 = bestDist; bestDist = dist; bestLevel2 = bestLevel; bestLevel = oct; bestIdx = id; }
+            else if (dist < bestDist2) { bestLevel2 = oct; bestDist2 = dist; }
+        } else if (sp.mode == 6) {
+            if (dist < bestDist) { bestDist2 = bestDist; bestDist = dist; bestIdx = id; }
+            else if (dist < bestDist2) bestDist2 = dist;
+        } else if (dist < bestDist) { bestDist = dist; bestIdx = id; }
+    }
+    return search_accept(sp, bestIdx, bestDist, bestDist2, bestLevel, bestLevel2);
+}
+
+__device__ int search_one(const SearchCtx& c, int q, const int* owner, bool record)
+{
+    const uvip_search_params& sp = c.sp;
+    int nrec = 0;                                      // recorded candidates (record == true); > SW_CACHE_K = overflow
     const float x = c.qu[q], y = c.qv[q], r = c.qr[q];
     const int minL = c.qminL[q], maxL = c.qmaxL[q];
     // FrameKTL::GetFeaturesInArea, src/FrameKTL.cc:359-386 (float ops rounded one by one, no FMA)
     int cx0 = (int)floorf(__fmul_rn(__fsub_rn(__fsub_rn(x, sp.min_x), r), sp.inv_w)); cx0 = max(0, cx0);
-    if (cx0 >= sp.cols) return -1;
+    if (cx0 >= sp.cols) { if (record) c.qcache_n[q] = 0; return -1; }
     int cx1 = (int)ceilf(__fmul_rn(__fadd_rn(__fsub_rn(x, sp.min_x), r), sp.inv_w)); cx1 = min(sp.cols - 1, cx1);
-    if (cx1 < 0) return -1;
+    if (cx1 < 0) { if (record) c.qcache_n[q] = 0; return -1; }
     int cy0 = (int)floorf(__fmul_rn(__fsub_rn(__fsub_rn(y, sp.min_y), r), sp.inv_h)); cy0 = max(0, cy0);
-    if (cy0 >= sp.rows) return -1;
+    if (cy0 >= sp.rows) { if (record) c.qcache_n[q] = 0; return -1; }
     int cy1 = (int)ceilf(__fmul_rn(__fadd_rn(__fsub_rn(y, sp.min_y), r), sp.inv_h)); cy1 = min(sp.rows - 1, cy1);
-    if (cy1 < 0) return -1;
+    if (cy1 < 0) { if (record) c.qcache_n[q] = 0; return -1; }
     const bool check = !(minL == -1 && maxL == -1);
     const bool same = check && (minL == maxL);
     const uint4 u = __ldg(reinterpret_cast<const uint4*>(c.qdesc + (size_t)q * 32));
@@ -437,8 +475,15 @@ __device__ int search_one(const SearchCtx& c, int q, const int* owner)
                     else if (oct < minL || oct > maxL) continue;
                 }
                 if (fabsf(__fsub_rn(c.kx[id], x)) > r || fabsf(__fsub_rn(c.ky[id], y)) > r) continue;
-                if (owner[id] < q) continue;                       // F.mvpMapPoints[idx] already set (:91 / :1689)
+                const int own = owner[id];
+                if (own == -2) continue;                           // taken before the call: never a candidate of any round
+                if (!record && own < q) continue;                  // F.mvpMapPoints[idx] already set (:91 / :1689)
                 const int dist = hamming256(u, v, c.kdesc + (size_t)id * 32);
+                if (record) {                                      // (round 0: nothing is claimed yet, so every candidate is scored anyway)
+                    if (nrec < SW_CACHE_K) c.qcache[(size_t)q * SW_CACHE_K + nrec] = (unsigned)id | ((unsigned)oct << 19) | ((unsigned)dist << 23);
+                    nrec += ((unsigned)oct > 15u || id >= (1 << 19)) ? SW_CACHE_K + 1 : 1;       // what the entry cannot hold: search in full every round
+                    if (own < q) continue;
+                }
                 if (sp.mode == 0) {                                // src/ORBmatcher.cc:98-111
                     if (dist < bestDist) { bestDist2 = bestDist; bestDist = dist; bestLevel2 = bestLevel; bestLevel = oct; bestIdx = id; }
                     else if (dist < bestDist2) { bestLevel2 = oct; bestDist2 = dist; }
@@ -448,10 +493,8 @@ __device__ int search_one(const SearchCtx& c, int q, const int* owner)
                 } else if (dist < bestDist) { bestDist = dist; bestIdx = id; }   // :1697-1701
             }
         }
-    if (bestIdx < 0 || bestDist > sp.th_dist) return -1;
-    if (sp.mode == 0 && bestLevel == bestLevel2 && (float)bestDist > __fmul_rn(sp.ratio, (float)bestDist2)) return -1;   // :116-117
-    if (sp.mode == 6 && !((float)bestDist <= __fmul_rn((float)bestDist2, sp.ratio))) return -1;                         // :470, :585
-    return bestIdx;
+    if (record) c.qcache_n[q] = nrec <= SW_CACHE_K ? nrec : -1;
+    return search_accept(sp, bestIdx, bestDist, bestDist2, bestLevel, bestLevel2);
 }
 
 // node-restricted search (SearchByBoW inner loops, src/ORBmatcher.cc:186-245 and :751-811; mode 1 = best-only lists)
@@ -534,6 +577,7 @@ k_search_window(SearchCtx c, int nq, int nk, int32_t* __restrict__ taken, int32_
         c.qu += qo; c.qv += qo; c.qr += qo; c.qminL += qo; c.qmaxL += qo; c.qdesc += qo * 32;
         c.kx += ko; c.ky += ko; c.octave += ko; c.kdesc += ko * 32;
         c.cell_start += f * (size_t)(c.sp.cols * c.sp.rows + 1); c.cell_items += ko;
+        if (c.qcache) { c.qcache += qo * SW_CACHE_K; c.qcache_n += qo; }
         taken += ko; match += qo; ownerA += ko; ownerB += ko; out_counts += 2 * f; flags += 4 * f;
         if (d_nq) nq = d_nq[f];
         if (d_nk) nk = d_nk[f];
@@ -550,7 +594,10 @@ k_search_window(SearchCtx c, int nq, int nk, int32_t* __restrict__ taken, int32_
         if (t0 == 0) flags[(rounds + 1) % 3] = 0;          // next round's flag: nobody reads or writes it during this round
         cl.sync();
         for (int q = t0; q < nq; q += T) {
-            const int r = c.cand_start ? (c.sp.mode == 5 ? search_one_epipolar(c, q, prev) : search_one_list(c, q, prev)) : search_one(c, q, prev);
+            int r;
+            if (c.cand_start) r = c.sp.mode == 5 ? search_one_epipolar(c, q, prev) : search_one_list(c, q, prev);
+            else if (c.qcache && rounds > 0 && c.qcache_n[q] >= 0) r = search_replay(c, q, prev, c.qcache_n[q]);
+            else r = search_one(c, q, prev, c.qcache != nullptr && rounds == 0);
             match[q] = r;
             if (r >= 0 && claims) atomicMin(&cur[r], q);
         }
@@ -654,7 +701,7 @@ using namespace uvip;
 struct uvip_matcher {
     int device = 0;
     cudaStream_t stream = nullptr;
-    DevBuf q, t, idx, dist, misc, misc2, misc3, misc4;
+    DevBuf q, t, idx, dist, misc, misc2, misc3, misc4, qcache;
     long long launches = 0;
     uint8_t* h_stage = nullptr; size_t h_stage_bytes = 0;      // pinned mirror of the upload / download block of uvip_search_frame
     std::mutex mu;
@@ -692,7 +739,7 @@ int uvip_matcher_destroy(uvip_matcher* m)
     DeviceGuard g(m->device);
     cudaStreamSynchronize(m->stream);
     m->q.release(); m->t.release(); m->idx.release(); m->dist.release();
-    m->misc.release(); m->misc2.release(); m->misc3.release(); m->misc4.release();
+    m->misc.release(); m->misc2.release(); m->misc3.release(); m->misc4.release(); m->qcache.release();
     if (m->h_stage) cudaFreeHost(m->h_stage);
     cudaStreamDestroy(m->stream);
     delete m;
@@ -1115,6 +1162,7 @@ int uvip_search_frame(uvip_matcher* m, const uvip_search_params* sp,
     const size_t o_match = sect((size_t)nq * 4), o_cnt = sect(32);
     const size_t down_bytes = off - o_taken;
     const size_t o_cs = sect((size_t)(ncell + 1) * 4), o_ci = sect(nkk * 4), o_cof = sect(nkk * 4), o_oa = sect(nkk * 4), o_ob = sect(nkk * 4);
+    const size_t o_qc = sect((size_t)nq * SW_CACHE_K * 4), o_qcn = sect((size_t)nq * 4);
     int rc;
     if ((rc = m->misc.reserve(off))) return rc;
     if (m->h_stage_bytes < o_cs) {
@@ -1141,6 +1189,7 @@ int uvip_search_frame(uvip_matcher* m, const uvip_search_params* sp,
     c.qminL = (const int32_t*)(base + o_qmin); c.qmaxL = (const int32_t*)(base + o_qmax); c.qdesc = base + o_qd;
     c.kx = (const float*)(base + o_kx); c.ky = (const float*)(base + o_ky); c.octave = (const int32_t*)(base + o_oct);
     c.kdesc = base + o_kd; c.cell_start = (const int32_t*)(base + o_cs); c.cell_items = (const int32_t*)(base + o_ci);
+    if (!env_set("UVIP_SEARCH_NOCACHE")) { c.qcache = (unsigned*)(base + o_qc); c.qcache_n = (int*)(base + o_qcn); }
     UVIP_CUDA(launch_search(st, 1, c, nq, nk, (int32_t*)(base + o_taken), (int32_t*)(base + o_match), (int*)(base + o_oa), (int*)(base + o_ob),
                             (int*)(base + o_cnt), nullptr, nullptr, 0, 0, (int*)(base + o_cnt) + 4));
     m->launches += 2;
@@ -1291,6 +1340,11 @@ int uvip_search_window_batch_device(uvip_matcher* m, const uvip_search_params* s
     c.sp = *sp;
     c.qu = d_qu; c.qv = d_qv; c.qr = d_qr; c.qminL = d_qmin_level; c.qmaxL = d_qmax_level; c.qdesc = d_qdesc;
     c.kx = d_kx; c.ky = d_ky; c.octave = d_octave; c.kdesc = d_kdesc; c.cell_start = cs; c.cell_items = ci;
+    if (!env_set("UVIP_SEARCH_NOCACHE")) {                                           // candidate cache of the claim rounds (SearchCtx)
+        const size_t nq_all = (size_t)nframes * q_stride;
+        if ((rc = m->qcache.reserve(nq_all * (SW_CACHE_K + 1) * 4))) return rc;
+        c.qcache = m->qcache.as<unsigned>(); c.qcache_n = m->qcache.as<int>() + nq_all * SW_CACHE_K;
+    }
     UVIP_CUDA(launch_search(st, nframes, c, 0, 0, d_taken, d_match, m->misc4.as<int>(), m->misc4.as<int>() + nk_all, d_counts, d_nq, d_nk, q_stride, k_stride,
                             m->misc4.as<int>() + 2 * nk_all));
     m->launches += 2;
