@@ -2,6 +2,7 @@
 oracle on the same seeded inputs.  Bars (BASELINE.json north_star): pyramid, blur, FAST keypoint sets, Hamming
 distances and match indices bit-exact; angles within 1e-3 rad; descriptor bits >= 99.9 %."""
 import hashlib
+import os
 
 import numpy as np
 import pytest
@@ -427,6 +428,45 @@ def test_search_window_claim_chain(gpu, oracle, synth):
                                                   grid['start'], grid['items'], grid['minX'], grid['minY'], grid['inv_w'], grid['inv_h'])
         assert n == on and np.array_equal(match, omatch) and np.array_equal(taken, otaken), mode
     assert n <= nk
+
+
+def test_search_frame_candidate_cache_equals_sequential_scan(gpu, oracle, synth):
+    """uvip_search_frame replays per-query candidate lists in the claim rounds after the first (csrc/matcher.cu, SearchCtx::qcache).
+    Cases the list must get right: queries with 0, a few and more than six candidates (the last are searched in full every round),
+    octaves beyond what an entry holds (> 15), pre-taken keypoints, and heavy competition for the same keypoints (many rounds);
+    with and without level gates, best-only and top-2 modes.  The switch UVIP_SEARCH_NOCACHE must not change a single entry."""
+    rng = np.random.RandomState(5)
+    nk, nq = 400, 1500
+    kx = (60 + rng.rand(nk) * 120).astype(np.float32); ky = (60 + rng.rand(nk) * 90).astype(np.float32)
+    kdesc = synth.random_descriptors(91, nk)
+    src = rng.randint(0, nk, nq)
+    qdesc = synth.flip_bits(kdesc[src], 901, rng.randint(0, 40, nq).tolist())
+    qu = (kx[src] + rng.randn(nq) * 2).astype(np.float32); qv = (ky[src] + rng.randn(nq) * 2).astype(np.float32)
+    qr = np.where(rng.rand(nq) < 0.5, 2.5, np.where(rng.rand(nq) < 0.5, 9.0, 30.0)).astype(np.float32)     # few / several / dozens of candidates
+    qu[::50] += 4000                                                                                        # windows outside the grid
+    bounds = (0, 752, 0, 480)
+    m = gpu.ORBmatcher(0.9, True)
+    pre = np.full(nk, -1, np.int32); pre[::11] = 12345
+    for octmax in (8, 21):
+        octave = rng.randint(0, octmax, nk).astype(np.int32)
+        start, items = oracle.grid_build(kx, ky, 0.0, 0.0, float(np.float32(64) / np.float32(752)), float(np.float32(48) / np.float32(480)))
+        for gated in (False, True):
+            lo = (octave[src] - 1).astype(np.int32) if gated else np.full(nq, -1, np.int32)
+            hi = (octave[src] + 1).astype(np.int32) if gated else np.full(nq, -1, np.int32)
+            for mode, th in ((0, 256), (0, 60), (1, 256), (6, 256), (4, 100)):
+                # (mode 6, the level-free top-2 of WindowSearch, has no oracle restatement: it is pinned through the shim against the
+                #  reference's compiled functions; here the cached and the plain search must agree)
+                want = None if mode == 6 else oracle.search_window(mode, th, 0.9, qu, qv, qr, lo, hi, qdesc, kx, ky, octave, kdesc, start, items, 0.0, 0.0,
+                                                                   float(np.float32(64) / np.float32(752)), float(np.float32(48) / np.float32(480)), taken=pre)
+                got = m.search_frame(mode, th, qu, qv, qr, lo, hi, qdesc, kx, ky, octave, kdesc, bounds, taken=pre)
+                os.environ['UVIP_SEARCH_NOCACHE'] = '1'
+                try:
+                    plain = m.search_frame(mode, th, qu, qv, qr, lo, hi, qdesc, kx, ky, octave, kdesc, bounds, taken=pre)
+                finally:
+                    os.environ.pop('UVIP_SEARCH_NOCACHE', None)
+                for a, b, c in zip(got, want or got, plain):
+                    assert np.array_equal(a, b) and np.array_equal(a, c), (octmax, gated, mode, th)
+                assert got[0] > 50
 
 
 def test_search_by_bow_node_restricted_lists(gpu, oracle, synth):
